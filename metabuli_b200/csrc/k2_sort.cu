@@ -1,0 +1,128 @@
+// K2 / K4 — device radix sorts (reference rows A4 and A9: KmerExtractor.cpp:79 with Kmer::compareQueryKmer,
+// Kmer.h:89-94; KmerMatcher.cpp:1071-1078 with compareMatches, :1149-1166).  The reference uses ips4o on
+// 16-byte / 32-byte structs; here keys and payloads are split (SoA) and run through CUB's onesweep radix
+// sort on exactly the bits that carry order:
+//   query metamers : the 40-bit amino-acid part only (bits 24..63).  The merge kernel treats an
+//                    amino-acid group as a set, so order inside a group is free.
+//   matches        : two stable LSD passes over a 32-bit permutation — first (frame,pos,hamming,dna),
+//                    then (seqID,species) — each trimmed to the bits the batch actually uses.
+#include <cub/cub.cuh>
+
+#include "kernels.cuh"
+
+namespace mbl {
+
+size_t sort_kmers_temp_bytes(size_t n) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<uint64_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (long long)n, 24, 64);
+    return bytes;
+}
+
+void sort_kmers(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint64_t* val_a, uint64_t* val_b, size_t n,
+                int& result_in_b, cudaStream_t st) {
+    cub::DoubleBuffer<uint64_t> k(key_a, key_b), v(val_a, val_b);
+    MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 24, 64, st));
+    result_in_b = k.selector;
+}
+
+size_t scan_temp_bytes(size_t n) {
+    size_t a = 0, b = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, a, (const uint64_t*)nullptr, (uint64_t*)nullptr, (long long)n);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (long long)n);
+    return a > b ? a : b;
+}
+void exclusive_sum_u64(void* tmp, size_t tmp_bytes, const uint64_t* in, uint64_t* out, size_t n, cudaStream_t st) {
+    MBL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (long long)n, st));
+}
+void exclusive_sum_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st) {
+    MBL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (long long)n, st));
+}
+
+// ---- match ordering ---------------------------------------------------------------------------------
+namespace {
+
+__device__ __host__ inline int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) ++b; return b; }
+
+// low key: frame | pos | hamming(3 bits, <= 7 by construction) | dna(24)
+__global__ void match_lowkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, int pos_bits, uint64_t* __restrict__ key,
+                                    uint32_t* __restrict__ idx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t q = m[i].qinfo;
+    uint64_t k = (uint64_t)qi_frame(q);
+    k = (k << pos_bits) | (uint64_t)qi_pos(q);
+    k = (k << 3) | (uint64_t)(m[i].hamming & 7u);
+    k = (k << 24) | (uint64_t)(m[i].dna_encoding & 0xFFFFFFu);
+    key[i] = k;
+    idx[i] = (uint32_t)i;
+}
+// high key: seqID | species, gathered through the permutation of the first pass
+__global__ void match_highkey_kernel(const mbl_match_rec* __restrict__ m, const uint32_t* __restrict__ idx, size_t n, int sp_bits,
+                                     uint64_t* __restrict__ key) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const mbl_match_rec& x = m[idx[i]];
+    key[i] = ((uint64_t)qi_seq(x.qinfo) << sp_bits) | (uint64_t)(uint32_t)x.species_id;
+}
+__global__ void match_gather_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restrict__ idx, size_t n,
+                                    mbl_match_rec* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[i]);
+    uint64_t* d = reinterpret_cast<uint64_t*>(out + i);
+    uint64_t a = s[0], b = s[1], c = s[2];
+    d[0] = a; d[1] = b; d[2] = c;
+}
+// seg_begin/seg_end per read from the sorted match list (Classifier.cpp:174-185 MatchBlocks)
+__global__ void segment_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t n_reads, uint64_t* __restrict__ seg_begin,
+                               uint64_t* __restrict__ seg_end) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = qi_seq(m[i].qinfo);
+    if (s == 0 || s > n_reads) return;
+    if (i == 0 || qi_seq(m[i - 1].qinfo) != s) seg_begin[s - 1] = i;
+    if (i + 1 == n || qi_seq(m[i + 1].qinfo) != s) seg_end[s - 1] = i + 1;
+}
+
+}  // namespace
+
+size_t sort_matches_temp_bytes(size_t n) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (long long)n, 0, 64);
+    return bytes;
+}
+
+void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
+                  int32_t max_taxid, uint32_t max_pos, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b,
+                  cudaStream_t st) {
+    if (!n) return;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const int pos_bits = bits_for(max_pos);
+    const int sp_bits = bits_for((uint64_t)(uint32_t)max_taxid);
+    const int seq_bits = bits_for(n_reads);
+    match_lowkey_kernel<<<blocks, 256, 0, st>>>(in, n, pos_bits, key_a, idx_a);
+    cub::DoubleBuffer<uint64_t> k(key_a, key_b);
+    cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
+    MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, 3 + pos_bits + 27, st));
+    uint32_t* perm1 = v.Current();
+    uint64_t* kcur = k.Current();
+    uint64_t* kalt = k.Alternate();
+    match_highkey_kernel<<<blocks, 256, 0, st>>>(in, perm1, n, sp_bits, kalt);
+    // second pass: keys live in kalt, permutation in perm1
+    cub::DoubleBuffer<uint64_t> k2(kalt, kcur);
+    cub::DoubleBuffer<uint32_t> v2(perm1, v.Alternate());
+    MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k2, v2, (long long)n, 0, seq_bits + sp_bits, st));
+    match_gather_kernel<<<blocks, 256, 0, st>>>(in, v2.Current(), n, out);
+}
+
+void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, uint64_t* seg_begin, uint64_t* seg_end, cudaStream_t st) {
+    MBL_CUDA(cudaMemsetAsync(seg_begin, 0, 8 * (size_t)n_reads, st));
+    MBL_CUDA(cudaMemsetAsync(seg_end, 0, 8 * (size_t)n_reads, st));
+    if (!n) return;
+    segment_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sorted, n, n_reads, seg_begin, seg_end);
+}
+
+}  // namespace mbl

@@ -1,0 +1,125 @@
+// Launch interfaces of the classify-path kernels (definitions in k1_extract.cu, k2_sort.cu, k3_index.cu,
+// k3_merge.cu, k5_score.cu).  Host code in mbl_api.cu strings them together.
+#pragma once
+#include "mbl_common.cuh"
+
+namespace mbl {
+
+constexpr uint32_t kTileMaxKmers = 4096;    // k-mers a shared-memory tile can hold
+constexpr uint32_t kItemQueries = 1u << 15; // queries per merge work item (hot tiles are split)
+
+struct TileDirectory {
+    Tile* tiles = nullptr;          // [n_tiles]
+    uint64_t* cell_k = nullptr;     // [n_cells] k-mer index of the first k-mer ending in the cell
+    uint64_t* cell_v = nullptr;     // [n_cells] value of the last k-mer ending before the cell
+    uint64_t* jumbo_vals = nullptr; // pre-decoded values of jumbo tiles
+    uint64_t n_tiles = 0, n_cells = 0, n_jumbo = 0, n_jumbo_kmers = 0;
+    uint64_t n_kmers_decoded = 0;   // number of end flags in the stream (must equal the info count)
+};
+
+struct DeviceTaxonomy {             // reference arrays as stored in taxonomyDB
+    const int32_t *D = nullptr, *E = nullptr, *L = nullptr, *H = nullptr, *M = nullptr;
+    const int32_t *node_taxid = nullptr, *node_parent = nullptr;
+    const uint8_t* node_prune = nullptr;
+    const int8_t* node_rank = nullptr;
+    const int32_t* taxid2species = nullptr;
+    int32_t max_taxid = 0, M_k = 0, eukaryota = 0;
+    uint32_t max_nodes = 0;
+};
+
+struct ScoreParams {
+    float min_score, min_sp_score, tie_ratio;
+    int min_cons_cnt, min_cons_cnt_euk, accession_level, denominator, kmer_format;
+};
+
+// K1
+void launch_read_meta(const uint64_t* off1, const uint64_t* off2, uint32_t n_reads, int32_t* cov1, int32_t* cov2,
+                      int32_t* w1, int32_t* w2, uint64_t* slots, uint32_t* quot_cnt, cudaStream_t st);
+void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2,
+                    uint32_t n_reads, const int32_t* cov1, const int32_t* w1, const int32_t* w2, const uint64_t* slot_off,
+                    const uint8_t* base_code, const uint8_t* codon, uint64_t* value, uint64_t* qinfo,
+                    unsigned long long* n_valid, int sm_count, cudaStream_t st);
+
+// K2 / K4 (radix sorts) and scans
+size_t sort_kmers_temp_bytes(size_t n);
+void sort_kmers(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint64_t* val_a, uint64_t* val_b, size_t n,
+                int& result_in_b, cudaStream_t st);
+size_t scan_temp_bytes(size_t n);
+void exclusive_sum_u64(void* tmp, size_t tmp_bytes, const uint64_t* in, uint64_t* out, size_t n, cudaStream_t st);
+void exclusive_sum_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st);
+// full reference order (seqID, species, frame, pos, hamming, dna): sorted copy of `in` in `out`
+size_t sort_matches_temp_bytes(size_t n);
+void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
+                  int32_t max_taxid, uint32_t max_pos, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b,
+                  cudaStream_t st);
+void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, uint64_t* seg_begin, uint64_t* seg_end, cudaStream_t st);
+
+// K3 directory (load time)
+void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, cudaStream_t st,
+                          TileDirectory& dir);
+void free_tile_directory(TileDirectory& dir);
+
+// K3 merge (per batch)
+struct MergeArgs {
+    const uint16_t* diff;
+    const int32_t* info;
+    uint32_t info_mask;
+    const Tile* tiles;
+    uint64_t n_tiles;
+    const uint64_t* cell_k;
+    const uint64_t* cell_v;
+    const uint64_t* jumbo_vals;
+    const uint64_t* q_value;        // sorted by amino-acid part
+    const uint64_t* q_info;
+    uint64_t n_query;               // non-blank
+    const int32_t* taxid2species;
+    int32_t max_taxid;
+    const uint16_t* ham_pair;       // 4096-entry table in HBM
+    int kmer_format;
+    mbl_match_rec* out;
+    uint64_t out_cap;
+    unsigned long long* out_count;  // total matches found (may exceed out_cap => overflow)
+    unsigned int* error_flag;       // Q2
+    // work list
+    uint64_t* q_lo;                 // [n_tiles + 1]
+    uint32_t* item_cnt;             // [n_tiles + 1]
+    uint32_t* item_off;             // [n_tiles + 1]
+    MergeItem* items;
+    uint64_t items_cap;
+    unsigned int* item_cursor;
+    void* scan_tmp;
+    size_t scan_tmp_bytes;
+};
+void launch_merge_plan(const MergeArgs& a, cudaStream_t st);      // partition + work items
+void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st);
+size_t merge_smem_bytes();
+
+// K5
+struct ScoreArgs {
+    const mbl_match_rec* matches;       // sorted
+    uint64_t n_match;
+    uint32_t n_reads;
+    const uint64_t* seg_begin;      // per read (seqID - 1)
+    const uint64_t* seg_end;
+    const int32_t* cov1;
+    const int32_t* cov2;
+    const uint32_t* quot_off;       // [n_reads + 1] exclusive scan of per-read quotient-table sizes
+    DeviceTaxonomy tax;
+    ScoreParams par;
+    // scratch, one entry per match
+    float* l_score; int32_t* l_start; int32_t* l_ham; int32_t* l_depth; uint32_t* l_smatch; uint8_t* l_conn;
+    int32_t* p_start; int32_t* p_end; float* p_score; int32_t* p_ham; int32_t* p_depth; uint32_t* p_smatch; uint32_t* p_ematch;
+    int32_t* c_start; int32_t* c_end; float* s_score;
+    // scratch, per quotient
+    int32_t* q_tax; uint8_t* q_ham; uint8_t* q_has;
+    // outputs
+    mbl_read_result* results;
+    int32_t* taxcnt_pairs;          // 2 x int32 per entry, region of a read starts at quot_off[r]
+};
+void launch_score(const ScoreArgs& a, cudaStream_t st);
+void launch_compact_taxcnt(const mbl_read_result* results, uint32_t n_reads, const uint32_t* quot_off,
+                           const int32_t* pairs_in, const uint32_t* out_off, int32_t* pairs_out, mbl_read_result* results_out,
+                           cudaStream_t st);
+void launch_taxcnt_len(const mbl_read_result* results, uint32_t n_reads, uint32_t* len, cudaStream_t st);
+
+}  // namespace mbl

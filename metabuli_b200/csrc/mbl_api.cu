@@ -1,0 +1,748 @@
+// C-ABI of the B200 classify path (include/metabuli_b200.h): context, index upload + tile directory,
+// and the batch pipeline  K1 extract -> K2 sort -> K3 merge -> K4 match sort -> K5 score
+// (reference: Classifier::startClassify, src/commons/Classifier.cpp:44-164).
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "mbl_tables.hpp"
+
+using namespace mbl;
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T>
+    T* get(size_t count) {
+        size_t bytes = count * sizeof(T) + 64;
+        if (bytes > cap) {
+            if (p) cudaFree(p);
+            p = nullptr; cap = 0;
+            size_t want = bytes + bytes / 16;
+            MBL_CUDA(cudaMalloc(&p, want));
+            cap = want;
+        }
+        return reinterpret_cast<T*>(p);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct SubBatch { uint32_t r0, r1; uint64_t slots, quots; uint32_t max_pos; };
+
+}  // namespace
+
+struct mbl_ctx {
+    mbl_config cfg{};
+    std::string err;
+    int sm_count = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[16] = {};
+    // tables
+    uint8_t *d_base_code = nullptr, *d_codon = nullptr;
+    uint16_t* d_ham_pair = nullptr;
+    // index
+    uint16_t* d_diff = nullptr;
+    int32_t* d_info = nullptr;
+    uint64_t n_u16 = 0, n_kmers = 0;
+    TileDirectory dir;
+    DeviceTaxonomy tax;
+    std::vector<void*> tax_allocs;
+    size_t db_bytes = 0;
+    bool db_loaded = false;
+    // resident batch
+    Buf bases1, bases2, off1, off2;
+    uint32_t n_reads = 0;
+    bool paired = false;
+    std::vector<SubBatch> subs;
+    // workspace
+    Buf cov1, cov2, w1, w2, slots, slot_off, quot_cnt, quot_off, seg_b, seg_e, res_sub, tax_len, tax_off;
+    Buf val_a, val_b, qi_a, qi_b, cub_tmp;
+    Buf m_raw, m_sorted, key_a, key_b, idx_a, idx_b;
+    Buf l_score, l_start, l_ham, l_depth, l_smatch, l_conn, p_start, p_end, p_score, p_ham, p_depth, p_smatch, p_ematch,
+        c_start, c_end, s_score;
+    Buf q_tax, q_ham, q_has, pairs_raw;
+    Buf q_lo, item_cnt, item_off, items, counters;
+    // results of the whole batch
+    Buf results, pairs;
+    uint64_t n_pairs = 0;
+    double match_ratio = 0.0;   // matches per slot seen so far (sizes the match buffer)
+    mbl_stats stats{};
+};
+
+namespace {
+
+int fail(mbl_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+int fail_cuda(mbl_ctx* c, const CudaError& e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.file, e.line);
+    cudaGetLastError();
+    return fail(c, MBL_E_CUDA, buf);
+}
+
+template <class T>
+T* upload(mbl_ctx* c, const T* h, size_t n, size_t pad_elems = 16) {
+    T* d = nullptr;
+    MBL_CUDA(cudaMalloc(&d, (n + pad_elems) * sizeof(T)));
+    MBL_CUDA(cudaMemsetAsync(d, 0, (n + pad_elems) * sizeof(T), c->st));
+    if (n) MBL_CUDA(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, c->st));
+    return d;
+}
+
+struct StageTimer {
+    mbl_ctx* c;
+    int stage;
+    cudaEvent_t a, b;
+    StageTimer(mbl_ctx* ctx, int s) : c(ctx), stage(s) {
+        a = c->ev[2 * (s % 7)]; b = c->ev[2 * (s % 7) + 1];
+        cudaEventRecord(a, c->st);
+    }
+    void stop() {
+        cudaEventRecord(b, c->st);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        c->stats.ms[stage] += ms;
+    }
+};
+
+void free_db(mbl_ctx* c) {
+    cudaFree(c->d_diff); cudaFree(c->d_info);
+    c->d_diff = nullptr; c->d_info = nullptr;
+    free_tile_directory(c->dir);
+    for (void* p : c->tax_allocs) cudaFree(p);
+    c->tax_allocs.clear();
+    c->tax = DeviceTaxonomy();
+    c->db_loaded = false;
+    c->db_bytes = 0;
+}
+
+// host-side planning of sub-batches from the read lengths (QueryIndexer::indexQueryFile analogue,
+// QueryIndexer.cpp:30-147, with the HBM budget in place of --max-ram)
+void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
+    c->subs.clear();
+    SubBatch cur{0, 0, 0, 0, 0};
+    for (uint32_t r = 0; r < b->n_reads; ++r) {
+        int l1 = (int)(b->offsets[r + 1] - b->offsets[r]);
+        int w1 = windows_per_frame(l1), c1 = max_covered_length(l1), w2 = 0, c2 = 0;
+        if (b->offsets2) {
+            int l2 = (int)(b->offsets2[r + 1] - b->offsets2[r]);
+            w2 = windows_per_frame(l2); c2 = max_covered_length(l2);
+        }
+        bool empty = w1 < 1 || (b->offsets2 && w2 < 1);
+        uint64_t s = empty ? 0 : 6ull * (uint64_t)(w1 + w2);
+        int ql = c1 + c2;
+        uint64_t q = ql + 3 > 0 ? (uint64_t)((ql + 3) / 3 + 1) : 1;
+        if (cur.r1 > cur.r0 && (cur.slots + s > max_slots || cur.quots + q > 0xF0000000ull)) {
+            c->subs.push_back(cur);
+            cur = SubBatch{r, r, 0, 0, 0};
+        }
+        cur.r1 = r + 1; cur.slots += s; cur.quots += q;
+        uint32_t mp = (uint32_t)std::max(0, c1 + 3 + c2 + 8);
+        cur.max_pos = std::max(cur.max_pos, mp);
+    }
+    if (cur.r1 > cur.r0) c->subs.push_back(cur);
+}
+
+uint64_t slots_budget(mbl_ctx* c) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    // bytes the workspace currently holds can be reused
+    size_t held = 0;
+    for (Buf* b : {&c->val_a, &c->val_b, &c->qi_a, &c->qi_b, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b,
+                   &c->l_score, &c->l_start, &c->l_ham, &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score,
+                   &c->p_ham, &c->p_depth, &c->p_smatch, &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->cub_tmp})
+        held += b->cap;
+    double budget = 0.80 * (double)(free_b + held);
+    // ~32 B per slot (keys + payload, double buffered) + ~0.6 matches per slot x 140 B + sort scratch
+    uint64_t s = (uint64_t)(budget / 150.0);
+    s = std::min<uint64_t>(s, 1ull << 31);
+    s = std::max<uint64_t>(s, 1ull << 16);
+    return s;
+}
+
+// the pipeline over one sub-batch of resident reads
+int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
+    cudaStream_t st = c->st;
+    const uint32_t n = sb.r1 - sb.r0;
+    const uint64_t S = sb.slots;
+    const uint8_t* bases1 = (const uint8_t*)c->bases1.p;
+    const uint8_t* bases2 = c->paired ? (const uint8_t*)c->bases2.p : nullptr;
+    const uint64_t* off1 = (const uint64_t*)c->off1.p + sb.r0;
+    const uint64_t* off2 = c->paired ? (const uint64_t*)c->off2.p + sb.r0 : nullptr;
+
+    int32_t *cov1 = c->cov1.get<int32_t>(n), *cov2 = c->cov2.get<int32_t>(n), *w1 = c->w1.get<int32_t>(n), *w2 = c->w2.get<int32_t>(n);
+    uint64_t *slots = c->slots.get<uint64_t>(n + 1), *slot_off = c->slot_off.get<uint64_t>(n + 1);
+    uint32_t *quot_cnt = c->quot_cnt.get<uint32_t>(n + 1), *quot_off = c->quot_off.get<uint32_t>(n + 1);
+    const size_t scan_bytes = std::max(scan_temp_bytes(n + 1), scan_temp_bytes(c->dir.n_tiles + 2));
+    const size_t sortk_bytes = sort_kmers_temp_bytes(S);
+    unsigned long long* counters = c->counters.get<unsigned long long>(8);   // [0] n_valid [1] reserved [2] matches [3] err|cursor
+
+    // ---- K1 ------------------------------------------------------------------------------------------
+    {
+        StageTimer t(c, MBL_STAGE_EXTRACT);
+        MBL_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+        MBL_CUDA(cudaMemsetAsync(slots + n, 0, 8, st));
+        MBL_CUDA(cudaMemsetAsync(quot_cnt + n, 0, 4, st));
+        launch_read_meta(off1, off2, n, cov1, cov2, w1, w2, slots, quot_cnt, st);
+        void* tmp = c->cub_tmp.get<uint8_t>(std::max(scan_bytes, sortk_bytes));
+        exclusive_sum_u64(tmp, c->cub_tmp.cap, slots, slot_off, n + 1, st);
+        exclusive_sum_u32(tmp, c->cub_tmp.cap, quot_cnt, quot_off, n + 1, st);
+        uint64_t *va = c->val_a.get<uint64_t>(S), *qa = c->qi_a.get<uint64_t>(S);
+        launch_extract(c->cfg.kmer_format, bases1, off1, bases2, off2, n, cov1, w1, w2, slot_off, c->d_base_code, c->d_codon,
+                       va, qa, counters, c->sm_count, st);
+        c->stats.kernel_launches += 2;
+        t.stop();
+    }
+    // ---- K2 ------------------------------------------------------------------------------------------
+    uint64_t *qv = nullptr, *qi = nullptr;
+    {
+        StageTimer t(c, MBL_STAGE_SORT);
+        uint64_t *va = (uint64_t*)c->val_a.p, *qa = (uint64_t*)c->qi_a.p;
+        uint64_t *vb = c->val_b.get<uint64_t>(S), *qb = c->qi_b.get<uint64_t>(S);
+        int in_b = 0;
+        if (S) sort_kmers(c->cub_tmp.p, c->cub_tmp.cap, va, vb, qa, qb, S, in_b, st);
+        qv = in_b ? vb : va;
+        qi = in_b ? qb : qa;
+        t.stop();
+    }
+    unsigned long long h_cnt[4] = {0, 0, 0, 0};
+    MBL_CUDA(cudaMemcpyAsync(h_cnt, counters, 8, cudaMemcpyDeviceToHost, st));
+    MBL_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_query = h_cnt[0];
+    c->stats.n_query_kmers += n_query;
+
+    // ---- K3 ------------------------------------------------------------------------------------------
+    uint64_t cap = (uint64_t)((double)S * std::max(c->match_ratio * 1.25, 0.125 * (double)std::max(1, c->cfg.match_per_kmer))) + (1u << 16);
+    uint64_t reserved = 0, n_match = 0;
+    MergeArgs ma{};
+    ma.diff = c->d_diff; ma.info = c->d_info;
+    ma.info_mask = ~((uint32_t)(c->cfg.skip_redundancy == 0) << 31);
+    ma.tiles = c->dir.tiles; ma.n_tiles = c->dir.n_tiles; ma.cell_k = c->dir.cell_k; ma.cell_v = c->dir.cell_v;
+    ma.jumbo_vals = c->dir.jumbo_vals;
+    ma.q_value = qv; ma.q_info = qi; ma.n_query = n_query;
+    ma.taxid2species = c->tax.taxid2species; ma.max_taxid = c->tax.max_taxid;
+    ma.ham_pair = c->d_ham_pair; ma.kmer_format = c->cfg.kmer_format;
+    ma.out_count = counters + 1;
+    ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
+    ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
+    ma.q_lo = c->q_lo.get<uint64_t>(c->dir.n_tiles + 2);
+    ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
+    ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
+    ma.items_cap = c->dir.n_tiles + n_query / kItemQueries + 2;
+    ma.items = c->items.get<MergeItem>(ma.items_cap);
+    ma.scan_tmp = c->cub_tmp.p; ma.scan_tmp_bytes = c->cub_tmp.cap;
+    for (int attempt = 0;; ++attempt) {
+        ma.out = c->m_raw.get<mbl_match_rec>(cap);
+        ma.out_cap = cap;
+        MBL_CUDA(cudaMemsetAsync(counters + 1, 0, 24, st));
+        {
+            StageTimer t(c, MBL_STAGE_MERGE);
+            if (n_query && c->dir.n_tiles) {
+                launch_merge_plan(ma, st);
+                launch_merge(ma, c->sm_count, st);
+                c->stats.kernel_launches += 4;
+                c->stats.merge_launches += 1;
+            }
+            t.stop();
+        }
+        MBL_CUDA(cudaMemcpyAsync(h_cnt, counters, 32, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        MBL_CUDA(cudaGetLastError());
+        reserved = h_cnt[1]; n_match = h_cnt[2];
+        if ((uint32_t)h_cnt[3] & 1u) return fail(c, MBL_E_BAD_DB, "target k-mer with taxid 0 or unmapped species (reference exits, KmerMatcher.cpp:292-300)");
+        if (reserved <= cap) break;
+        // Classifier.cpp:127-130: the reference bumps matchPerKmer and restarts; here only the merge is redone
+        c->stats.overflow_retries += 1;
+        cap = reserved + reserved / 8 + (1u << 16);
+        if (attempt > 4) return fail(c, MBL_E_MATCH_OVERFLOW, "match buffer overflow persists");
+    }
+    c->stats.n_matches += n_match;
+    c->stats.merge_bytes += 2 * c->n_u16 + 4 * c->n_kmers + 16 * n_query + 24 * n_match;
+    if (S) c->match_ratio = std::max(c->match_ratio, (double)reserved / (double)S);
+    if (reserved >= (1ull << 32)) return fail(c, MBL_E_UNSUPPORTED, "more than 2^32 matches in one sub-batch");
+
+    // ---- K4 ------------------------------------------------------------------------------------------
+    const uint64_t M = reserved;
+    mbl_match_rec* sorted = c->m_sorted.get<mbl_match_rec>(M + 1);
+    uint64_t *seg_b = c->seg_b.get<uint64_t>(n + 1), *seg_e = c->seg_e.get<uint64_t>(n + 1);
+    {
+        StageTimer t(c, MBL_STAGE_MSORT);
+        const size_t sm_bytes = sort_matches_temp_bytes(M);
+        void* tmp = c->cub_tmp.get<uint8_t>(std::max(sm_bytes, std::max(scan_bytes, sortk_bytes)));
+        // note: cub_tmp may have been reallocated; the k-mer buffers are no longer needed
+        sort_matches(tmp, c->cub_tmp.cap, (const mbl_match_rec*)c->m_raw.p, sorted, M, n, c->tax.max_taxid, sb.max_pos,
+                     c->key_a.get<uint64_t>(M + 1), c->key_b.get<uint64_t>(M + 1), c->idx_a.get<uint32_t>(M + 1),
+                     c->idx_b.get<uint32_t>(M + 1), st);
+        launch_segments(sorted, M, n, seg_b, seg_e, st);
+        c->stats.kernel_launches += M ? 4 : 0;
+        t.stop();
+    }
+    // ---- K5 ------------------------------------------------------------------------------------------
+    {
+        StageTimer t(c, MBL_STAGE_SCORE);
+        ScoreArgs sa{};
+        sa.matches = sorted; sa.n_match = M; sa.n_reads = n; sa.seg_begin = seg_b; sa.seg_end = seg_e;
+        sa.cov1 = cov1; sa.cov2 = cov2; sa.quot_off = quot_off;
+        sa.tax = c->tax;
+        sa.par.min_score = c->cfg.min_score; sa.par.min_sp_score = c->cfg.min_sp_score; sa.par.tie_ratio = c->cfg.tie_ratio;
+        sa.par.min_cons_cnt = c->cfg.min_cons_cnt; sa.par.min_cons_cnt_euk = c->cfg.min_cons_cnt_euk;
+        sa.par.accession_level = c->cfg.accession_level;
+        sa.par.denominator = (c->cfg.seq_mode == 1 || c->cfg.seq_mode == 2) ? 100 : 1000;      // Taxonomer.cpp:44-48
+        sa.par.kmer_format = c->cfg.kmer_format;
+        const size_t Mp = M + 1;
+        sa.l_score = c->l_score.get<float>(Mp); sa.l_start = c->l_start.get<int32_t>(Mp); sa.l_ham = c->l_ham.get<int32_t>(Mp);
+        sa.l_depth = c->l_depth.get<int32_t>(Mp); sa.l_smatch = c->l_smatch.get<uint32_t>(Mp); sa.l_conn = c->l_conn.get<uint8_t>(Mp);
+        sa.p_start = c->p_start.get<int32_t>(Mp); sa.p_end = c->p_end.get<int32_t>(Mp); sa.p_score = c->p_score.get<float>(Mp);
+        sa.p_ham = c->p_ham.get<int32_t>(Mp); sa.p_depth = c->p_depth.get<int32_t>(Mp); sa.p_smatch = c->p_smatch.get<uint32_t>(Mp);
+        sa.p_ematch = c->p_ematch.get<uint32_t>(Mp); sa.c_start = c->c_start.get<int32_t>(Mp); sa.c_end = c->c_end.get<int32_t>(Mp);
+        sa.s_score = c->s_score.get<float>(Mp);
+        sa.q_tax = c->q_tax.get<int32_t>(sb.quots + 1); sa.q_ham = c->q_ham.get<uint8_t>(sb.quots + 1); sa.q_has = c->q_has.get<uint8_t>(sb.quots + 1);
+        sa.taxcnt_pairs = c->pairs_raw.get<int32_t>(2 * (sb.quots + 1));
+        sa.results = c->res_sub.get<mbl_read_result>(n);
+        launch_score(sa, st);
+        // compact the (taxid,count) lists behind the pairs of earlier sub-batches
+        uint32_t *tl = c->tax_len.get<uint32_t>(n + 1), *to = c->tax_off.get<uint32_t>(n + 1);
+        launch_taxcnt_len(sa.results, n, tl, st);
+        exclusive_sum_u32(c->cub_tmp.p, c->cub_tmp.cap, tl, to, n + 1, st);
+        uint32_t total = 0;
+        MBL_CUDA(cudaMemcpyAsync(&total, to + n, 4, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        // grow the batch-level pair array, keeping what is there
+        if ((c->n_pairs + total) * 8 + 64 > c->pairs.cap) {
+            Buf nb;
+            int32_t* np = nb.get<int32_t>(2 * (c->n_pairs + total) + 2 * (size_t)c->n_reads);
+            if (c->n_pairs) MBL_CUDA(cudaMemcpyAsync(np, c->pairs.p, c->n_pairs * 8, cudaMemcpyDeviceToDevice, st));
+            MBL_CUDA(cudaStreamSynchronize(st));
+            c->pairs.release();
+            c->pairs = nb;
+        }
+        launch_compact_taxcnt(sa.results, n, quot_off, sa.taxcnt_pairs, to, (int32_t*)c->pairs.p + 2 * c->n_pairs,
+                              (mbl_read_result*)c->results.p + sb.r0, st);
+        c->stats.kernel_launches += 3;
+        t.stop();
+        // make taxcnt_begin batch-global on download (offset by the pairs of earlier sub-batches)
+        c->n_pairs += total;
+    }
+    MBL_CUDA(cudaGetLastError());
+    return MBL_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
+    if (!cfg || !out) return MBL_E_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return MBL_E_NO_DEVICE;
+    }
+    mbl_ctx* c = new mbl_ctx();
+    c->cfg = *cfg;
+    try {
+        if (cfg->reduced_aa || cfg->syncmer) { delete c; return MBL_E_UNSUPPORTED; }
+        if (cfg->kmer_format != 1 && cfg->kmer_format != 2) { delete c; return MBL_E_UNSUPPORTED; }
+        MBL_CUDA(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        MBL_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+        c->sm_count = prop.multiProcessorCount;
+        MBL_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        for (auto& e : c->ev) MBL_CUDA(cudaEventCreate(&e));
+        HostTables t;
+        c->d_base_code = upload(c, t.base_code, 256);
+        c->d_codon = upload(c, t.codon, 512);
+        c->d_ham_pair = upload(c, t.ham_pair, 4096);
+        MBL_CUDA(cudaStreamSynchronize(c->st));
+    } catch (const CudaError& e) {
+        fail_cuda(c, e);
+        delete c;
+        return MBL_E_CUDA;
+    }
+    *out = c;
+    return MBL_OK;
+}
+
+void mbl_destroy(mbl_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->st);
+    free_db(c);
+    for (Buf* b : {&c->bases1, &c->bases2, &c->off1, &c->off2, &c->cov1, &c->cov2, &c->w1, &c->w2, &c->slots, &c->slot_off, &c->quot_cnt,
+                   &c->quot_off, &c->seg_b, &c->seg_e, &c->res_sub, &c->tax_len, &c->tax_off, &c->val_a, &c->val_b, &c->qi_a, &c->qi_b,
+                   &c->cub_tmp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
+                   &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score, &c->p_ham, &c->p_depth, &c->p_smatch,
+                   &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw, &c->q_lo,
+                   &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs})
+        b->release();
+    cudaFree(c->d_base_code); cudaFree(c->d_codon); cudaFree(c->d_ham_pair);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+const char* mbl_last_error(const mbl_ctx* c) { return c ? c->err.c_str() : "no context"; }
+
+int mbl_load_db(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx) {
+    if (!c || !db || !tx || !db->diff_idx || !db->info) return fail(c, MBL_E_BAD_ARG, "null argument");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        free_db(c);
+        c->n_u16 = db->n_u16; c->n_kmers = db->n_kmers;
+        c->d_diff = upload(c, db->diff_idx, db->n_u16, 64);
+        c->d_info = upload(c, db->info, db->n_kmers, 64);
+        auto up = [&](auto* h, size_t n) { auto* d = upload(c, h, n); c->tax_allocs.push_back((void*)d); return d; };
+        const size_t N = tx->max_nodes, T = (size_t)tx->max_taxid + 1;
+        c->tax.D = up(tx->D, T); c->tax.E = up(tx->E, 2 * N); c->tax.L = up(tx->L, 2 * N); c->tax.H = up(tx->H, N);
+        c->tax.M = up(tx->M, 2 * N * (size_t)tx->M_k);
+        c->tax.node_taxid = up(tx->node_taxid, N); c->tax.node_parent = up(tx->node_parent, N);
+        c->tax.node_prune = up(tx->node_prune, N); c->tax.node_rank = up(tx->node_rank, N);
+        c->tax.taxid2species = up(tx->taxid2species, T);
+        c->tax.max_taxid = tx->max_taxid; c->tax.M_k = tx->M_k; c->tax.eukaryota = tx->eukaryota; c->tax.max_nodes = (uint32_t)N;
+        MBL_CUDA(cudaStreamSynchronize(c->st));
+        build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->st, c->dir);
+        // the k-mer count implied by the end flags must agree with the info file
+        if (c->dir.n_kmers_decoded != c->n_kmers) {
+            char msg[256];
+            snprintf(msg, sizeof msg, "diffIdx holds %llu k-mers but info has %llu entries", (unsigned long long)c->dir.n_kmers_decoded,
+                     (unsigned long long)c->n_kmers);
+            free_db(c);
+            return fail(c, MBL_E_BAD_DB, msg);
+        }
+        c->db_bytes = 2 * c->n_u16 + 4 * c->n_kmers + sizeof(Tile) * c->dir.n_tiles + 16 * c->dir.n_cells + 8 * c->dir.n_jumbo_kmers;
+        c->db_loaded = true;
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_upload_batch(mbl_ctx* c, const mbl_batch* b) {
+    if (!c || !b || !b->bases || !b->offsets) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (b->n_reads >= (1u << 29)) return fail(c, MBL_E_BAD_ARG, "at most 2^29-1 reads per batch (29-bit sequenceID, Kmer.h:13)");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        StageTimer t(c, MBL_STAGE_H2D);
+        const uint32_t n = b->n_reads;
+        c->n_reads = n;
+        c->paired = b->bases2 != nullptr && b->offsets2 != nullptr;
+        const uint64_t nb1 = b->offsets[n];
+        uint8_t* d1 = c->bases1.get<uint8_t>(nb1 + 64);
+        MBL_CUDA(cudaMemcpyAsync(d1, b->bases, nb1, cudaMemcpyHostToDevice, c->st));
+        MBL_CUDA(cudaMemcpyAsync(c->off1.get<uint64_t>(n + 1), b->offsets, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->st));
+        if (c->paired) {
+            const uint64_t nb2 = b->offsets2[n];
+            uint8_t* d2 = c->bases2.get<uint8_t>(nb2 + 64);
+            MBL_CUDA(cudaMemcpyAsync(d2, b->bases2, nb2, cudaMemcpyHostToDevice, c->st));
+            MBL_CUDA(cudaMemcpyAsync(c->off2.get<uint64_t>(n + 1), b->offsets2, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->st));
+        }
+        t.stop();
+        plan_sub_batches(c, b, slots_budget(c));
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_classify_resident(mbl_ctx* c) {
+    if (!c) return MBL_E_BAD_ARG;
+    if (!c->db_loaded) return fail(c, MBL_E_BAD_ARG, "mbl_load_db has not been called");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        float h2d = c->stats.ms[MBL_STAGE_H2D];
+        c->stats = mbl_stats{};
+        c->stats.ms[MBL_STAGE_H2D] = h2d;
+        c->n_pairs = 0;
+        c->results.get<mbl_read_result>(c->n_reads + 1);
+        c->stats.sub_batches = (uint32_t)c->subs.size();
+        for (const SubBatch& sb : c->subs) {
+            int rc = run_sub_batch(c, sb);
+            if (rc != MBL_OK) return rc;
+        }
+        MBL_CUDA(cudaStreamSynchronize(c->st));
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_download_results(mbl_ctx* c, mbl_read_result* out, int32_t* taxcnt_pairs, size_t cap_pairs, size_t* used_pairs) {
+    if (!c || !out) return fail(c, MBL_E_BAD_ARG, "null argument");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        if (used_pairs) *used_pairs = c->n_pairs;
+        if (c->n_pairs > cap_pairs) return fail(c, MBL_E_CAPACITY, "taxcnt_pairs too small");
+        StageTimer t(c, MBL_STAGE_D2H);
+        if (c->n_reads) MBL_CUDA(cudaMemcpyAsync(out, c->results.p, sizeof(mbl_read_result) * (size_t)c->n_reads, cudaMemcpyDeviceToHost, c->st));
+        if (c->n_pairs && taxcnt_pairs) MBL_CUDA(cudaMemcpyAsync(taxcnt_pairs, c->pairs.p, 8 * c->n_pairs, cudaMemcpyDeviceToHost, c->st));
+        t.stop();
+        // taxcnt_begin is relative to the sub-batch's first pair: make it batch-global
+        uint64_t base = 0;
+        for (const SubBatch& sb : c->subs) {
+            uint64_t cnt = 0;
+            for (uint32_t r = sb.r0; r < sb.r1; ++r) { out[r].taxcnt_begin += (uint32_t)base; cnt += out[r].taxcnt_len; }
+            base += cnt;
+        }
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_classify_batch(mbl_ctx* c, const mbl_batch* b, mbl_read_result* out, int32_t* taxcnt_pairs, size_t cap_pairs, size_t* used_pairs) {
+    if (!c) return MBL_E_BAD_ARG;
+    c->stats.ms[MBL_STAGE_H2D] = 0;
+    int rc = mbl_upload_batch(c, b);
+    if (rc != MBL_OK) return rc;
+    rc = mbl_classify_resident(c);
+    if (rc != MBL_OK) return rc;
+    return mbl_download_results(c, out, taxcnt_pairs, cap_pairs, used_pairs);
+}
+
+int mbl_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return MBL_E_BAD_ARG;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MBL_E_NO_DEVICE : MBL_E_CUDA; }
+    return MBL_OK;
+}
+int mbl_host_unregister(void* ptr) {
+    if (!ptr) return MBL_E_BAD_ARG;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return MBL_E_CUDA; }
+    return MBL_OK;
+}
+
+int mbl_get_stats(const mbl_ctx* c, mbl_stats* out) {
+    if (!c || !out) return MBL_E_BAD_ARG;
+    *out = c->stats;
+    return MBL_OK;
+}
+
+int mbl_get_db_info(const mbl_ctx* c, mbl_db_info* out) {
+    if (!c || !out) return MBL_E_BAD_ARG;
+    out->n_tiles = c->dir.n_tiles; out->n_jumbo = c->dir.n_jumbo; out->n_kmers = c->n_kmers; out->n_u16 = c->n_u16;
+    out->hbm_bytes = c->db_bytes;
+    return MBL_OK;
+}
+
+// ---- stage-level entry points ------------------------------------------------------------------------
+int mbl_extract(mbl_ctx* c, const mbl_batch* b, uint64_t* value, uint64_t* qinfo, size_t cap, size_t* n_out) {
+    if (!c || !b || !n_out) return fail(c, MBL_E_BAD_ARG, "null argument");
+    int rc = mbl_upload_batch(c, b);
+    if (rc != MBL_OK) return rc;
+    try {
+        uint64_t total = 0;
+        for (auto& s : c->subs) total += s.slots;
+        *n_out = total;
+        if (total > cap || !value || !qinfo) return fail(c, MBL_E_CAPACITY, "k-mer buffers too small");
+        cudaStream_t st = c->st;
+        const uint32_t n = b->n_reads;
+        int32_t *cov1 = c->cov1.get<int32_t>(n), *cov2 = c->cov2.get<int32_t>(n), *w1 = c->w1.get<int32_t>(n), *w2 = c->w2.get<int32_t>(n);
+        uint64_t *slots = c->slots.get<uint64_t>(n + 1), *slot_off = c->slot_off.get<uint64_t>(n + 1);
+        uint32_t* quot_cnt = c->quot_cnt.get<uint32_t>(n + 1);
+        unsigned long long* counters = c->counters.get<unsigned long long>(8);
+        MBL_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+        MBL_CUDA(cudaMemsetAsync(slots + n, 0, 8, st));
+        const uint64_t* off2 = c->paired ? (const uint64_t*)c->off2.p : nullptr;
+        launch_read_meta((const uint64_t*)c->off1.p, off2, n, cov1, cov2, w1, w2, slots, quot_cnt, st);
+        void* tmp = c->cub_tmp.get<uint8_t>(scan_temp_bytes(n + 1));
+        exclusive_sum_u64(tmp, c->cub_tmp.cap, slots, slot_off, n + 1, st);
+        uint64_t *va = c->val_a.get<uint64_t>(total), *qa = c->qi_a.get<uint64_t>(total);
+        launch_extract(c->cfg.kmer_format, (const uint8_t*)c->bases1.p, (const uint64_t*)c->off1.p,
+                       c->paired ? (const uint8_t*)c->bases2.p : nullptr, off2, n, cov1, w1, w2, slot_off, c->d_base_code,
+                       c->d_codon, va, qa, counters, c->sm_count, st);
+        MBL_CUDA(cudaMemcpyAsync(value, va, 8 * total, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaMemcpyAsync(qinfo, qa, 8 * total, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        MBL_CUDA(cudaGetLastError());
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_sort_kmers(mbl_ctx* c, uint64_t* value, uint64_t* qinfo, size_t n) {
+    if (!c || (n && (!value || !qinfo))) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (!n) return MBL_OK;
+    try {
+        cudaStream_t st = c->st;
+        uint64_t *va = c->val_a.get<uint64_t>(n), *vb = c->val_b.get<uint64_t>(n), *qa = c->qi_a.get<uint64_t>(n), *qb = c->qi_b.get<uint64_t>(n);
+        MBL_CUDA(cudaMemcpyAsync(va, value, 8 * n, cudaMemcpyHostToDevice, st));
+        MBL_CUDA(cudaMemcpyAsync(qa, qinfo, 8 * n, cudaMemcpyHostToDevice, st));
+        void* tmp = c->cub_tmp.get<uint8_t>(sort_kmers_temp_bytes(n));
+        int in_b = 0;
+        sort_kmers(tmp, c->cub_tmp.cap, va, vb, qa, qb, n, in_b, st);
+        MBL_CUDA(cudaMemcpyAsync(value, in_b ? vb : va, 8 * n, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaMemcpyAsync(qinfo, in_b ? qb : qa, 8 * n, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n, mbl_match_rec* out, size_t cap, size_t* n_match) {
+    if (!c || !n_match || (n && (!value || !qinfo))) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (!c->db_loaded) return fail(c, MBL_E_BAD_ARG, "mbl_load_db has not been called");
+    try {
+        cudaStream_t st = c->st;
+        // blanks (UINT64_MAX) sort last; the merge only looks at the non-blank prefix
+        size_t nq = n;
+        while (nq > 0 && value[nq - 1] == kBlank) --nq;
+        uint64_t *va = c->val_a.get<uint64_t>(n + 1), *qa = c->qi_a.get<uint64_t>(n + 1);
+        if (n) {
+            MBL_CUDA(cudaMemcpyAsync(va, value, 8 * n, cudaMemcpyHostToDevice, st));
+            MBL_CUDA(cudaMemcpyAsync(qa, qinfo, 8 * n, cudaMemcpyHostToDevice, st));
+        }
+        unsigned long long* counters = c->counters.get<unsigned long long>(8);
+        MergeArgs ma{};
+        ma.diff = c->d_diff; ma.info = c->d_info;
+        ma.info_mask = ~((uint32_t)(c->cfg.skip_redundancy == 0) << 31);
+        ma.tiles = c->dir.tiles; ma.n_tiles = c->dir.n_tiles; ma.cell_k = c->dir.cell_k; ma.cell_v = c->dir.cell_v;
+        ma.jumbo_vals = c->dir.jumbo_vals;
+        ma.q_value = va; ma.q_info = qa; ma.n_query = nq;
+        ma.taxid2species = c->tax.taxid2species; ma.max_taxid = c->tax.max_taxid;
+        ma.ham_pair = c->d_ham_pair; ma.kmer_format = c->cfg.kmer_format;
+        ma.out_count = counters + 1;
+        ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
+        ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
+        ma.q_lo = c->q_lo.get<uint64_t>(c->dir.n_tiles + 2);
+        ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
+        ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
+        ma.items_cap = c->dir.n_tiles + nq / kItemQueries + 2;
+        ma.items = c->items.get<MergeItem>(ma.items_cap);
+        ma.scan_tmp = c->cub_tmp.get<uint8_t>(scan_temp_bytes(c->dir.n_tiles + 2));
+        ma.scan_tmp_bytes = c->cub_tmp.cap;
+        uint64_t dcap = cap + 148ull * 8 * 3 * 256 + 65536;
+        unsigned long long h_cnt[4];
+        std::vector<mbl_match_rec> host;
+        for (int attempt = 0;; ++attempt) {
+            ma.out = c->m_raw.get<mbl_match_rec>(dcap);
+            ma.out_cap = dcap;
+            MBL_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+            if (nq && c->dir.n_tiles) { launch_merge_plan(ma, st); launch_merge(ma, c->sm_count, st); }
+            MBL_CUDA(cudaMemcpyAsync(h_cnt, counters, 32, cudaMemcpyDeviceToHost, st));
+            MBL_CUDA(cudaStreamSynchronize(st));
+            MBL_CUDA(cudaGetLastError());
+            if ((uint32_t)h_cnt[3] & 1u) return fail(c, MBL_E_BAD_DB, "target k-mer with taxid 0 or unmapped species");
+            if (h_cnt[1] <= dcap) break;
+            if (attempt > 3) return fail(c, MBL_E_MATCH_OVERFLOW, "match buffer overflow persists");
+            dcap = h_cnt[1] + 65536;
+        }
+        *n_match = h_cnt[2];
+        if (h_cnt[2] > cap || !out) return fail(c, MBL_E_MATCH_OVERFLOW, "match buffer too small");
+        host.resize(h_cnt[1]);
+        if (h_cnt[1]) MBL_CUDA(cudaMemcpy(host.data(), c->m_raw.p, sizeof(mbl_match_rec) * h_cnt[1], cudaMemcpyDeviceToHost));
+        size_t w = 0;
+        for (const mbl_match_rec& m : host)
+            if (qi_seq(m.qinfo) != 0) out[w++] = m;       // drop the blank tails of the warp chunks
+        if (w != h_cnt[2]) return fail(c, MBL_E_CUDA, "internal: match count mismatch");
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_sort_matches(mbl_ctx* c, mbl_match_rec* m, size_t n) {
+    if (!c || (n && !m)) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (!n) return MBL_OK;
+    if (n >= (1ull << 32)) return fail(c, MBL_E_UNSUPPORTED, "too many matches");
+    try {
+        cudaStream_t st = c->st;
+        uint32_t max_seq = 0, max_pos = 0;
+        int32_t max_sp = 1;
+        for (size_t i = 0; i < n; ++i) {
+            max_seq = std::max(max_seq, qi_seq(m[i].qinfo));
+            max_pos = std::max(max_pos, qi_pos(m[i].qinfo));
+            max_sp = std::max(max_sp, m[i].species_id);
+        }
+        mbl_match_rec* raw = c->m_raw.get<mbl_match_rec>(n + 1);
+        mbl_match_rec* sorted = c->m_sorted.get<mbl_match_rec>(n + 1);
+        MBL_CUDA(cudaMemcpyAsync(raw, m, sizeof(mbl_match_rec) * n, cudaMemcpyHostToDevice, st));
+        void* tmp = c->cub_tmp.get<uint8_t>(sort_matches_temp_bytes(n));
+        sort_matches(tmp, c->cub_tmp.cap, raw, sorted, n, max_seq, max_sp, max_pos, c->key_a.get<uint64_t>(n + 1),
+                     c->key_b.get<uint64_t>(n + 1), c->idx_a.get<uint32_t>(n + 1), c->idx_b.get<uint32_t>(n + 1), st);
+        MBL_CUDA(cudaMemcpyAsync(m, sorted, sizeof(mbl_match_rec) * n, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        MBL_CUDA(cudaGetLastError());
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_score(mbl_ctx* c, const mbl_match_rec* sorted_h, size_t M, uint32_t n, const int32_t* cov_len1, const int32_t* cov_len2,
+              mbl_read_result* out, int32_t* taxcnt_pairs, size_t cap_pairs, size_t* used_pairs) {
+    if (!c || !out || !cov_len1 || (M && !sorted_h)) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (!c->db_loaded) return fail(c, MBL_E_BAD_ARG, "mbl_load_db has not been called");
+    try {
+        cudaStream_t st = c->st;
+        std::vector<uint32_t> qcnt(n + 1, 0);
+        std::vector<int32_t> zero(n, 0);
+        uint64_t quots = 0;
+        for (uint32_t r = 0; r < n; ++r) {
+            int ql = cov_len1[r] + (cov_len2 ? cov_len2[r] : 0);
+            qcnt[r] = ql + 3 > 0 ? (uint32_t)((ql + 3) / 3 + 1) : 1u;
+            quots += qcnt[r];
+        }
+        int32_t *cov1 = c->cov1.get<int32_t>(n), *cov2 = c->cov2.get<int32_t>(n);
+        uint32_t *quot_cnt = c->quot_cnt.get<uint32_t>(n + 1), *quot_off = c->quot_off.get<uint32_t>(n + 1);
+        MBL_CUDA(cudaMemcpyAsync(cov1, cov_len1, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        MBL_CUDA(cudaMemcpyAsync(cov2, cov_len2 ? cov_len2 : zero.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        MBL_CUDA(cudaMemcpyAsync(quot_cnt, qcnt.data(), 4 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+        void* tmp = c->cub_tmp.get<uint8_t>(scan_temp_bytes(n + 1));
+        exclusive_sum_u32(tmp, c->cub_tmp.cap, quot_cnt, quot_off, n + 1, st);
+        mbl_match_rec* sorted = c->m_sorted.get<mbl_match_rec>(M + 1);
+        if (M) MBL_CUDA(cudaMemcpyAsync(sorted, sorted_h, sizeof(mbl_match_rec) * M, cudaMemcpyHostToDevice, st));
+        uint64_t *seg_b = c->seg_b.get<uint64_t>(n + 1), *seg_e = c->seg_e.get<uint64_t>(n + 1);
+        launch_segments(sorted, M, n, seg_b, seg_e, st);
+        ScoreArgs sa{};
+        sa.matches = sorted; sa.n_match = M; sa.n_reads = n; sa.seg_begin = seg_b; sa.seg_end = seg_e;
+        sa.cov1 = cov1; sa.cov2 = cov2; sa.quot_off = quot_off; sa.tax = c->tax;
+        sa.par.min_score = c->cfg.min_score; sa.par.min_sp_score = c->cfg.min_sp_score; sa.par.tie_ratio = c->cfg.tie_ratio;
+        sa.par.min_cons_cnt = c->cfg.min_cons_cnt; sa.par.min_cons_cnt_euk = c->cfg.min_cons_cnt_euk;
+        sa.par.accession_level = c->cfg.accession_level;
+        sa.par.denominator = (c->cfg.seq_mode == 1 || c->cfg.seq_mode == 2) ? 100 : 1000;
+        sa.par.kmer_format = c->cfg.kmer_format;
+        const size_t Mp = M + 1;
+        sa.l_score = c->l_score.get<float>(Mp); sa.l_start = c->l_start.get<int32_t>(Mp); sa.l_ham = c->l_ham.get<int32_t>(Mp);
+        sa.l_depth = c->l_depth.get<int32_t>(Mp); sa.l_smatch = c->l_smatch.get<uint32_t>(Mp); sa.l_conn = c->l_conn.get<uint8_t>(Mp);
+        sa.p_start = c->p_start.get<int32_t>(Mp); sa.p_end = c->p_end.get<int32_t>(Mp); sa.p_score = c->p_score.get<float>(Mp);
+        sa.p_ham = c->p_ham.get<int32_t>(Mp); sa.p_depth = c->p_depth.get<int32_t>(Mp); sa.p_smatch = c->p_smatch.get<uint32_t>(Mp);
+        sa.p_ematch = c->p_ematch.get<uint32_t>(Mp); sa.c_start = c->c_start.get<int32_t>(Mp); sa.c_end = c->c_end.get<int32_t>(Mp);
+        sa.s_score = c->s_score.get<float>(Mp);
+        sa.q_tax = c->q_tax.get<int32_t>(quots + 1); sa.q_ham = c->q_ham.get<uint8_t>(quots + 1); sa.q_has = c->q_has.get<uint8_t>(quots + 1);
+        sa.taxcnt_pairs = c->pairs_raw.get<int32_t>(2 * (quots + 1));
+        sa.results = c->res_sub.get<mbl_read_result>(n);
+        launch_score(sa, st);
+        uint32_t *tl = c->tax_len.get<uint32_t>(n + 1), *to = c->tax_off.get<uint32_t>(n + 1);
+        launch_taxcnt_len(sa.results, n, tl, st);
+        exclusive_sum_u32(c->cub_tmp.p, c->cub_tmp.cap, tl, to, n + 1, st);
+        uint32_t total = 0;
+        MBL_CUDA(cudaMemcpyAsync(&total, to + n, 4, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        if (used_pairs) *used_pairs = total;
+        if (total > cap_pairs) return fail(c, MBL_E_CAPACITY, "taxcnt_pairs too small");
+        int32_t* pc = c->pairs.get<int32_t>(2 * (size_t)total + 2);
+        mbl_read_result* rc = c->results.get<mbl_read_result>(n + 1);
+        launch_compact_taxcnt(sa.results, n, quot_off, sa.taxcnt_pairs, to, pc, rc, st);
+        MBL_CUDA(cudaMemcpyAsync(out, rc, sizeof(mbl_read_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (total && taxcnt_pairs) MBL_CUDA(cudaMemcpyAsync(taxcnt_pairs, pc, 8 * (size_t)total, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        MBL_CUDA(cudaGetLastError());
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+}  // extern "C"

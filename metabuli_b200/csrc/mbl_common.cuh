@@ -1,0 +1,71 @@
+// Shared definitions of the B200 classify path: PODs, bit layouts, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/metabuli_b200.h"
+
+#define MBL_HD __host__ __device__ __forceinline__
+
+namespace mbl {
+
+// ---- k-mer / qinfo bit layout (reference Kmer.h:11-16, KmerScanner.h:110-114) --------------------
+constexpr uint64_t kDnaMask = 0xFFFFFFull;          // low 24 bits: 8 x 3-bit synonymous-codon ids
+constexpr uint64_t kAaMask = ~kDnaMask;             // high 40 bits: 8 x 5-bit amino acids
+constexpr uint64_t kBlank = 0xFFFFFFFFFFFFFFFFull;  // blank slot marker (sorts last; never matches)
+
+MBL_HD uint64_t aa_part(uint64_t v) { return v & kAaMask; }
+MBL_HD uint64_t pack_qinfo(uint32_t seqId, uint32_t pos, uint32_t frame) {
+    return (uint64_t)pos | ((uint64_t)(seqId & 0x1FFFFFFFu) << 32) | ((uint64_t)(frame & 7u) << 61);
+}
+MBL_HD uint32_t qi_pos(uint64_t q) { return (uint32_t)q; }
+MBL_HD uint32_t qi_seq(uint64_t q) { return (uint32_t)((q >> 32) & 0x1FFFFFFFu); }
+MBL_HD uint32_t qi_frame(uint64_t q) { return (uint32_t)(q >> 61); }
+
+// LocalUtil.h:46-60
+MBL_HD int max_covered_length(int len) {
+    int r = len % 3;
+    return r == 2 ? len - 2 : (r == 1 ? len - 4 : len - 3);
+}
+// windows per frame = cov/3 - 7; the reference's kmerCnt is 6x this (LocalUtil.h:46-49)
+MBL_HD int windows_per_frame(int len) { return max_covered_length(len) / 3 - 7; }
+
+// ---- in-HBM tile directory of the differential index -------------------------------------------
+// A tile is an amino-acid-group-aligned run of k-mers; the decoder additionally restarts at fixed
+// cells of kCellU16 fragments, each with its own (k-mer index, running value) checkpoint.
+constexpr int kCellU16 = 1024;            // decode checkpoint grid (u16 fragments)
+constexpr int kTileCells = 4;             // nominal tile = 4 cells = 4096 fragments (8 KiB)
+constexpr int kTileMaxU16 = 8192;         // tiles longer than this are "jumbo" (pre-decoded in HBM)
+
+struct Tile {
+    uint64_t diff_begin;     // u16 index of the first fragment of the tile's first k-mer
+    uint64_t info_begin;     // k-mer index of the tile's first k-mer
+    uint64_t base_value;     // value of the k-mer preceding the tile (0 at the stream start)
+    uint64_t first_aa;       // amino-acid part of the tile's first k-mer
+    uint32_t n_u16;          // fragments in the tile
+    uint32_t n_kmers;        // k-mers in the tile (after the Q1 trim of the very last k-mer)
+    uint64_t jumbo_off;      // offset into the pre-decoded value array, or ~0 when not jumbo
+};
+
+struct MergeItem {           // one unit of merge work: a tile and a slice of its queries
+    uint32_t tile;
+    uint32_t pad;
+    uint64_t q_begin, q_end;
+};
+
+// ---- error handling ------------------------------------------------------------------------------
+struct CudaError {
+    cudaError_t code;
+    const char* file;
+    int line;
+};
+#define MBL_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) throw ::mbl::CudaError{_e, __FILE__, __LINE__};                 \
+    } while (0)
+
+}  // namespace mbl

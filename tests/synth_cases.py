@@ -1,0 +1,50 @@
+"""Seeded synthetic parity cases shared by the golden generator, the CPU tests and the GPU tests."""
+import hashlib
+import os
+
+import numpy as np
+
+CASES = {
+    # name: (db kwargs, read kwargs, seq_mode)
+    "multi_se": (dict(genera=6, species_per_genus=4, strains_per_species=2, codons=3000, seed=3, eukaryote_genera=1),
+                 dict(n_reads=4000, length=150, seed=4, n_rate=0.002), 1),
+    "multi_pe": (dict(genera=6, species_per_genus=4, strains_per_species=2, codons=3000, seed=3, eukaryote_genera=1),
+                 dict(n_reads=3000, length=150, seed=5, n_rate=0.002, paired=True), 2),
+    # close species => many score ties within tie-ratio => LCA classifications above species
+    "ties_se": (dict(genera=3, species_per_genus=5, strains_per_species=3, codons=2500, seed=7, species_div=0.02, strain_div=0.004),
+                dict(n_reads=4000, length=151, seed=8, sub_rate=0.02), 1),
+    # ragged lengths incl. reads too short for a single k-mer, many Ns
+    "ragged_se": (dict(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, seed=11),
+                  dict(n_reads=3000, length=140, seed=12, n_rate=0.01, length_jitter=125), 1),
+    # long reads (seq-mode 3: denominator 1000)
+    "long": (dict(genera=3, species_per_genus=3, strains_per_species=2, codons=6000, seed=13),
+             dict(n_reads=300, length=6000, seed=14, sub_rate=0.05), 3),
+}
+
+
+def build(name):
+    from metabuli_b200 import synth
+    dbkw, rkw, seq_mode = CASES[name]
+    sdb = synth.make_db(**dbkw)
+    reads = synth.make_reads(sdb, **rkw)
+    return sdb, reads, seq_mode
+
+
+def fingerprint(sdb, reads) -> str:
+    h = hashlib.md5()
+    h.update(np.ascontiguousarray(sdb.database.diff_idx).tobytes())
+    h.update(np.ascontiguousarray(sdb.database.info).tobytes())
+    h.update(sdb.taxonomy_blob)
+    for a in reads:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def write_fasta(path, bases, offsets):
+    with open(path, "w") as f:
+        for i in range(offsets.size - 1):
+            f.write(">r%d\n%s\n" % (i, bytes(bases[int(offsets[i]):int(offsets[i + 1])]).decode()))
+
+
+def names(n):
+    return ["r%d" % i for i in range(n)]

@@ -1,0 +1,80 @@
+"""GPU parity on seeded synthetic databases: end-to-end TSV against the reference binary's own output
+(tests/golden/synth) and stage-by-stage against the oracle."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import synth_cases
+
+pytestmark = pytest.mark.gpu
+BLANK = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _sorted_records(a):
+    return np.sort(a, order=list(a.dtype.names))
+
+
+@pytest.mark.parametrize("name", list(synth_cases.CASES))
+def test_synthetic_case(name, golden_dir, tmp_path):
+    from metabuli_b200 import Classifier, ClassifyOptions
+    sdb, reads, seq_mode = synth_cases.build(name)
+    want_fp = open(os.path.join(golden_dir, "synth", name + ".md5")).read().strip()
+    assert synth_cases.fingerprint(sdb, reads) == want_fp
+    clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
+    try:
+        # end to end vs the reference's TSV
+        res, pairs = clf.classify_batch(*reads)
+        tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
+        golden = gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
+        assert tsv == golden
+        # stages vs the oracle
+        db_dir = str(tmp_path / "db")
+        sdb.write(db_dir)
+        odb = oracle.OracleDb(db_dir)
+        gv, gq = clf.extract(*reads)
+        ov, oq, cov1, cov2 = oracle.extract(*reads, kmer_format=2)
+        assert gv.size == ov.size
+        gm_ = gv != BLANK
+        om_ = ((oq >> np.uint64(32)) & np.uint64(0x1FFFFFFF)) != 0
+        g = np.stack([gv[gm_], gq[gm_]], 1)
+        o = np.stack([ov[om_], oq[om_]], 1)
+        assert np.array_equal(g[np.lexsort((g[:, 1], g[:, 0]))], o[np.lexsort((o[:, 1], o[:, 0]))])
+        sv, sq = clf.sort_kmers(gv, gq)
+        aa = sv >> np.uint64(24)
+        assert np.all(aa[1:] >= aa[:-1])
+        osv, osq = oracle.sort_kmers(ov, oq)
+        om = odb.match(osv, osq)
+        gm = clf.match(sv, sq)
+        assert np.array_equal(_sorted_records(gm), _sorted_records(om))
+        gs = clf.sort_matches(gm)
+        os_ = oracle.sort_matches(om)
+        assert np.array_equal(gs, os_)
+        c2 = cov2 if seq_mode == 2 else None
+        gres, gpairs = clf.score(gs, cov1, c2)
+        ores, opairs = odb.score(os_, cov1, c2, seq_mode=seq_mode)
+        for f in ("classification", "query_length", "taxcnt_len", "is_classified"):
+            assert np.array_equal(gres[f], ores[f]), f
+        assert np.array_equal(gres["score"].view(np.uint32), ores["score"].view(np.uint32))
+        assert np.array_equal(gpairs, opairs)
+        odb.close()
+    finally:
+        clf.close()
+
+
+def test_empty_and_tiny_batches():
+    from metabuli_b200 import Classifier, ClassifyOptions
+    sdb, reads, _ = synth_cases.build("ragged_se")
+    clf = Classifier(None, ClassifyOptions(seq_mode=1), database=sdb.database)
+    try:
+        res, pairs = clf.classify_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+        assert res.size == 0 and pairs.shape[0] == 0
+        # a single read too short for any k-mer, and one read of Ns only
+        b = np.frombuffer(b"ACGTACGTACGTACGTACGTACG" + b"N" * 150, dtype=np.uint8).copy()
+        o = np.array([0, 23, 173], dtype=np.uint64)
+        res, pairs = clf.classify_batch(b, o)
+        assert list(res["is_classified"]) == [0, 0] and list(res["query_length"]) == [21, 147]
+    finally:
+        clf.close()

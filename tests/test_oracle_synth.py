@@ -1,0 +1,29 @@
+"""Oracle vs the reference binary on seeded synthetic databases (multi-species, LCA ties, Ns, ragged and
+long reads, paired ends): the TSVs in tests/golden/synth were written by the reference itself
+(tests/golden/gen_synth_golden.py).  Also checks that the synthetic generator is reproducible here."""
+import gzip
+import os
+
+import pytest
+
+import oracle
+import synth_cases
+
+
+@pytest.mark.parametrize("name", list(synth_cases.CASES))
+def test_oracle_matches_reference_on_synthetic(name, golden_dir, tmp_path):
+    sdb, reads, seq_mode = synth_cases.build(name)
+    want_fp = open(os.path.join(golden_dir, "synth", name + ".md5")).read().strip()
+    assert synth_cases.fingerprint(sdb, reads) == want_fp, "synthetic inputs differ from the ones the golden TSV was made from"
+    db_dir = str(tmp_path / "db")
+    sdb.write(db_dir)
+    q1 = str(tmp_path / "r1.fna")
+    synth_cases.write_fasta(q1, reads[0], reads[1])
+    q2 = None
+    if seq_mode == 2:
+        q2 = str(tmp_path / "r2.fna")
+        synth_cases.write_fasta(q2, reads[2], reads[3])
+    out = str(tmp_path / "o.tsv")
+    oracle.classify_files(q1, q2, db_dir, seq_mode, out, threads=3)
+    golden = gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
+    assert open(out, "rb").read() == golden
