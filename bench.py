@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — reads/s of the B200 classify hot path on BASELINE.json's configuration
+("10M synthetic 150 bp SE reads vs 8 GiB synthetic index on 1xB200"), one step = one pass of the hot path
+(extract -> sort -> merge vs diffIdx -> match sort -> score) over one batch of synthetic reads.
+
+  python bench.py --gpus 1 --steps K --warmup W            our arm (N>1: one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    the reference algorithm on the host cores
+                                                           (oracle port, OpenMP, bounded sample per step)
+
+Legs of our arm, both timed over exactly K steps after W warm-up steps:
+  value : reads resident in HBM, mbl_classify_resident() per step (device pipeline only)
+  e2e   : mbl_classify_batch() per step from pinned host buffers: H2D of the reads and D2H of the per-read
+          results happen inside the timed region
+`roofline` is the merge kernel: algorithmic bytes (S_diff + 4K + 16Nq + 24Nm) over its
+CUDA-event time, against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "reads/sec classified (150bp SE)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per step and GPU")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--db-gib", type=float, default=8.0, help="target size of diffIdx+info")
+    ap.add_argument("--ref-reads", type=int, default=1_000_000, help="reads per step of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def db_shape(db_gib: float):
+    """(genera, species_per_genus, strains, codons) giving ~db_gib of diffIdx+info."""
+    target_kmers = db_gib * (1 << 30) / 9.9          # 4 B info + ~2.95 fragments x 2 B per k-mer
+    species = int(min(10_000, max(12, target_kmers // 60_000)))
+    spg = 20 if species >= 200 else 4
+    genera = max(3, species // spg)
+    codons = int(target_kmers / (genera * spg * 1.10)) + 8
+    return genera, spg, 2, codons
+
+
+def build_workload(args, device, seed_reads):
+    import torch
+    from metabuli_b200 import synth
+    genera, spg, strains, codons = db_shape(args.db_gib)
+    t0 = time.time()
+    sdb = synth.make_db(genera=genera, species_per_genus=spg, strains_per_species=strains, codons=codons, seed=3, device=device)
+    if device != "cpu":
+        torch.cuda.synchronize()
+    t1 = time.time()
+    reads = synth.make_reads(sdb, args.reads, args.read_len, seed=seed_reads, random_frac=0.3, sub_rate=0.01)
+    if device != "cpu":
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    info = dict(db_gen_s=round(t1 - t0, 1), reads_gen_s=round(time.time() - t1, 1), genera=genera, species=genera * spg,
+                codons=codons, n_kmers=int(sdb.database.info.size), n_u16=int(sdb.database.diff_idx.size),
+                index_gib=round((2 * sdb.database.diff_idx.size + 4 * sdb.database.info.size) / (1 << 30), 3))
+    return sdb, reads, info
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().split("\n") if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per merge launch from the committed ncu capture, if there is one."""
+    p = os.path.join(ROOT, "profiles", "merge_ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_arm(sdb, reads, n_sample, threads, steps, warmup):
+    """The reference algorithm (oracle port) on the host cores over a bounded sample; -> (reads/s, list of step seconds)."""
+    import oracle
+    odb = oracle.OracleDb.from_synth(sdb)
+    b, o = reads[0], reads[1]
+    n = min(n_sample, o.size - 1)
+    o_s = np.ascontiguousarray(o[: n + 1])
+    b_s = np.ascontiguousarray(b[: int(o_s[-1])])
+    secs = []
+    for i in range(warmup + steps):
+        sec, _, nk, nm = odb.classify_arrays(b_s, o_s, seq_mode=1, threads=threads, want_results=False)
+        if i >= warmup:
+            secs.append(sec)
+    odb.close()
+    return n, secs
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    have_gpu = torch.cuda.is_available()
+    threads = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        device = f"cuda:{local_rank}" if have_gpu else "cpu"
+        if have_gpu:
+            torch.cuda.set_device(local_rank)
+        args.reads = max(args.ref_reads, 1)
+        sdb, reads, winfo = build_workload(args, device, seed_reads=4)
+        n, secs = cpu_arm(sdb, reads, args.ref_reads, threads, args.steps, max(args.warmup, 0))
+        total = sum(secs)
+        value = n * len(secs) / total
+        line = {"metric": METRIC, "value": value, "unit": "reads/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000 * total / len(secs), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": f"{n} synthetic {args.read_len} bp SE reads per step vs {winfo['index_gib']} GiB synthetic index "
+                                       "(bounded sample of BASELINE configs[1])", **winfo},
+                "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port",
+                                 "sample": f"{n} reads x {len(secs)} steps, OpenMP oracle port of the reference path"},
+                "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------------
+    if not have_gpu:
+        print(json.dumps({"metric": METRIC, "error": "no CUDA device: the classify path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    from metabuli_b200 import Classifier, ClassifyOptions, _ffi
+
+    sdb, reads, winfo = build_workload(args, f"cuda:{local_rank}", seed_reads=4 + rank)
+    bases, offs = np.ascontiguousarray(reads[0]), np.ascontiguousarray(reads[1])
+    n_reads = offs.size - 1
+    t0 = time.time()
+    clf = Classifier(None, ClassifyOptions(seq_mode=1, device=local_rank), database=sdb.database)
+    winfo["db_load_s"] = round(time.time() - t0, 1)
+    winfo.update({"db_" + k: v for k, v in clf.db_info().items() if k in ("n_tiles", "n_jumbo")})
+    lib = clf.lib
+    lib.mbl_host_register(bases.ctypes.data_as(C.c_void_p), bases.nbytes)
+    lib.mbl_host_register(offs.ctypes.data_as(C.c_void_p), offs.nbytes)
+    out = np.zeros(n_reads, dtype=_ffi.RESULT_DTYPE)
+    pairs = np.zeros((max(16, 4 * n_reads), 2), dtype=np.int32)
+    lib.mbl_host_register(out.ctypes.data_as(C.c_void_p), out.nbytes)
+    lib.mbl_host_register(pairs.ctypes.data_as(C.c_void_p), pairs.nbytes)
+    batch, keep = clf.make_batch(bases, offs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def check(rc):
+        if rc != 0:
+            raise RuntimeError(f"rc={rc}: {lib.mbl_last_error(clf.ctx).decode()}")
+
+    # ---- value leg: reads resident in HBM ------------------------------------------------------------------
+    check(lib.mbl_upload_batch(clf.ctx, C.byref(batch)))
+    for _ in range(args.warmup):
+        check(lib.mbl_classify_resident(clf.ctx))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    stage_ms = {}
+    merge_ms = merge_bytes = launches = merge_launches = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        check(lib.mbl_classify_resident(clf.ctx))
+        st = clf.stats()
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+        merge_ms += st["ms_merge_kernel"]; merge_bytes += st["merge_bytes"]; launches += st["kernel_launches"]
+        merge_launches += st["merge_launches"]
+    barrier()
+    t_res = time.perf_counter() - t0
+    clocks = sampler.stop()
+    last = clf.stats()
+
+    # ---- e2e leg: host buffers in, results out -----------------------------------------------------------------
+    used = C.c_size_t(0)
+    check(lib.mbl_classify_batch(clf.ctx, C.byref(batch), out.ctypes.data_as(C.c_void_p), pairs.ctypes.data_as(C.c_void_p),
+                                 pairs.shape[0], C.byref(used)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        check(lib.mbl_classify_batch(clf.ctx, C.byref(batch), out.ctypes.data_as(C.c_void_p), pairs.ctypes.data_as(C.c_void_p),
+                                     pairs.shape[0], C.byref(used)))
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    h2d = int(bases.nbytes + offs.nbytes)
+    d2h = int(out.nbytes + 8 * used.value)
+    classified = int(out["is_classified"].sum())
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = float(t[0]), float(t[1])
+    total_reads = n_reads * world * args.steps
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            n, secs = cpu_arm(sdb, reads, args.ref_reads, threads, 1, 0)
+            cpu = {"value": n / secs[0], "unit": "reads/s", "cores": threads, "kind": "port",
+                   "sample": f"first {n} reads of the step's batch, one pass, OpenMP oracle port of the reference path"}
+        except Exception as e:  # the baseline is a reported number, never a reason to fail the bench
+            cpu = {"value": None, "unit": "reads/s", "cores": threads, "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = (merge_bytes / 1e9) / (merge_ms / 1e3) if merge_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": total_reads / t_res, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * t_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{n_reads} synthetic {args.read_len} bp SE reads per GPU per step vs {winfo['index_gib']} GiB synthetic "
+                                   f"index replicated per GPU (BASELINE configs[1])", "l2": "inputs_exceed_l2",
+                       "parallelism": f"replica x{world}: reads sharded, index replicated, no data-path collective", **winfo,
+                       "query_kmers_per_step": last["n_query_kmers"], "matches_per_step": last["n_matches"],
+                       "classified_per_step": classified, "sub_batches": last["sub_batches"], "overflow_retries": last["overflow_retries"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": ncu_traffic(), "kernel": "merge_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": merge_bytes / max(1, merge_launches),
+                         "ms_per_launch": merge_ms / max(1, merge_launches)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": total_reads / t_e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1000 * t_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+        }
+        print(json.dumps(line))
+    for a in (bases, offs, out, pairs):
+        lib.mbl_host_unregister(a.ctypes.data_as(C.c_void_p))
+    clf.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -158,6 +158,7 @@ int  mbl_host_unregister(void* ptr);
 #define MBL_STAGE_COUNT    7
 typedef struct {
     float    ms[MBL_STAGE_COUNT];     /* CUDA-event time of each stage in the last classify call       */
+    float    merge_kernel_ms;         /* the merge kernel launches alone, CUDA events on their stream   */
     uint64_t n_query_kmers;           /* non-blank                                                      */
     uint64_t n_matches;
     uint64_t merge_bytes;             /* algorithmic bytes of the merge launches: S_diff+4K+16Nq+24Nm   */

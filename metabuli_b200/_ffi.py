@@ -59,7 +59,7 @@ class ReadResult(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("ms", C.c_float * 7), ("n_query_kmers", C.c_uint64), ("n_matches", C.c_uint64), ("merge_bytes", C.c_uint64),
+    _fields_ = [("ms", C.c_float * 7), ("merge_kernel_ms", C.c_float), ("n_query_kmers", C.c_uint64), ("n_matches", C.c_uint64), ("merge_bytes", C.c_uint64),
                 ("merge_launches", C.c_uint32), ("kernel_launches", C.c_uint32), ("overflow_retries", C.c_uint32),
                 ("sub_batches", C.c_uint32)]
 

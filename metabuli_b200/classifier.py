@@ -115,7 +115,7 @@ class Classifier:
         s = _ffi.Stats()
         self.lib.mbl_get_stats(self.ctx, C.byref(s))
         d = {f"ms_{n}": float(s.ms[i]) for i, n in enumerate(_ffi.STAGE_NAMES)}
-        d.update(n_query_kmers=int(s.n_query_kmers), n_matches=int(s.n_matches), merge_bytes=int(s.merge_bytes),
+        d.update(ms_merge_kernel=float(s.merge_kernel_ms), n_query_kmers=int(s.n_query_kmers), n_matches=int(s.n_matches), merge_bytes=int(s.merge_bytes),
                  merge_launches=int(s.merge_launches), kernel_launches=int(s.kernel_launches),
                  overflow_retries=int(s.overflow_retries), sub_batches=int(s.sub_batches))
         return d

@@ -246,7 +246,13 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
             StageTimer t(c, MBL_STAGE_MERGE);
             if (n_query && c->dir.n_tiles) {
                 launch_merge_plan(ma, st);
+                cudaEventRecord(c->ev[14], st);
                 launch_merge(ma, c->sm_count, st);
+                cudaEventRecord(c->ev[15], st);
+                cudaEventSynchronize(c->ev[15]);
+                float kms = 0;
+                cudaEventElapsedTime(&kms, c->ev[14], c->ev[15]);
+                c->stats.merge_kernel_ms += kms;
                 c->stats.kernel_launches += 4;
                 c->stats.merge_launches += 1;
             }

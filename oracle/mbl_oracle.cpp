@@ -486,7 +486,12 @@ static int flog2(size_t v) { int r = 0; while (v >>= 1) ++r; return r; }
 bool Taxonomy::load(const std::string &path, std::string *err) {
     std::ifstream f(path, std::ios::binary);
     if (!f) { if (err) *err = "cannot open " + path; return false; }
-    blob.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    std::vector<char> b((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    return load_blob(b.data(), b.size(), err);
+}
+
+bool Taxonomy::load_blob(const char *data, size_t size, std::string *err) {
+    blob.assign(data, data + size);
     const char *p = blob.data();
     int32_t version; memcpy(&version, p, 4); p += 4;
     if (version != 2) { if (err) *err = "unsupported taxonomyDB version"; return false; }

@@ -69,6 +69,7 @@ struct Taxonomy {
     int32_t eukaryota = 0;
 
     bool load(const std::string &path, std::string *err);
+    bool load_blob(const char *data, size_t size, std::string *err);
     bool nodeExists(int32_t t) const { return t <= maxTaxID && D[t] != -1; }
     int nodeId(int32_t t) const { return D[t]; }
     const char *str(uint64_t idx) const { return strData + strOffsets[idx]; }

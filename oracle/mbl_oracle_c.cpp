@@ -31,6 +31,21 @@ void* orc_db_open(const char* dir, char* err, size_t errlen) {
     if (!db->load(dir, &e)) { set_err(err, errlen, e); delete db; return nullptr; }
     return db;
 }
+// in-memory variant (bench.py builds multi-GiB synthetic indexes without touching the disk)
+void* orc_db_from_arrays(const uint16_t* diff, size_t n_u16, const int32_t* info, size_t n_kmers, const uint64_t* split, size_t n_split,
+                         const char* taxonomy_blob, size_t blob_size, const int32_t* taxid_list, size_t n_list, int kmer_format,
+                         int skip_redundancy, char* err, size_t errlen) {
+    Database* db = new Database();
+    std::string e;
+    db->params.kmerFormat = kmer_format; db->params.skipRedundancy = skip_redundancy;
+    db->diffIdx.assign(diff, diff + n_u16);
+    db->info.assign(info, info + n_kmers);
+    db->split.resize(n_split);
+    memcpy(db->split.data(), split, n_split * 24);
+    if (!db->tax.load_blob(taxonomy_blob, blob_size, &e)) { set_err(err, errlen, e); delete db; return nullptr; }
+    build_taxid2species(db->tax, std::vector<int32_t>(taxid_list, taxid_list + n_list), db->taxid2species);
+    return db;
+}
 void orc_db_close(void* db) { delete (Database*)db; }
 int orc_db_kmer_format(void* db) { return ((Database*)db)->params.kmerFormat; }
 

@@ -29,6 +29,8 @@ def lib():
         L.orc_db_open.argtypes = [C.c_char_p, C.c_char_p, sz]
         L.orc_db_open.restype = vp
         L.orc_db_close.argtypes = [vp]
+        L.orc_db_from_arrays.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, C.c_int, C.c_int, C.c_char_p, sz]
+        L.orc_db_from_arrays.restype = vp
         L.orc_db_kmer_format.argtypes = [vp]
         L.orc_extract.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_int, vp, vp, sz, C.POINTER(sz), vp, vp]
         L.orc_sort_kmers.argtypes = [vp, vp, sz, C.c_int]
@@ -59,12 +61,29 @@ def _p(a):
 
 
 class OracleDb:
-    def __init__(self, db_dir: str):
-        err = C.create_string_buffer(512)
-        self.h = lib().orc_db_open(db_dir.encode(), err, 512)
-        if not self.h:
-            raise RuntimeError(err.value.decode())
+    def __init__(self, db_dir: str | None, handle=None):
+        if handle is not None:
+            self.h = handle
+        else:
+            err = C.create_string_buffer(512)
+            self.h = lib().orc_db_open(db_dir.encode(), err, 512)
+            if not self.h:
+                raise RuntimeError(err.value.decode())
         self.kmer_format = lib().orc_db_kmer_format(self.h)
+
+    @classmethod
+    def from_synth(cls, sdb):
+        """Build from a metabuli_b200.synth.SynthDb without going through files."""
+        d = sdb.database
+        diff = np.ascontiguousarray(d.diff_idx); info = np.ascontiguousarray(d.info); split = np.ascontiguousarray(d.split)
+        blob = np.frombuffer(sdb.taxonomy_blob, dtype=np.uint8)
+        tl = np.ascontiguousarray(sdb.taxid_list, dtype=np.int32)
+        err = C.create_string_buffer(512)
+        h = lib().orc_db_from_arrays(_p(diff), diff.size, _p(info), info.size, _p(split), split.size // 3, _p(blob), blob.size,
+                                     _p(tl), tl.size, d.params.kmer_format, d.params.skip_redundancy, err, 512)
+        if not h:
+            raise RuntimeError(err.value.decode())
+        return cls(None, handle=h)
 
     def close(self):
         if self.h:

@@ -1,0 +1,55 @@
+"""The C-ABI shared library loads without a GPU, exports every symbol include/metabuli_b200.h declares, and
+fails loudly (MBL_E_NO_DEVICE) instead of falling back when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "metabuli_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(mbl_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported():
+    from metabuli_b200 import _ffi
+    lib = _ffi.load_library()
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(_ffi.EXPORTS) == set(names)
+
+
+def test_struct_layouts():
+    from metabuli_b200 import _ffi
+    assert C.sizeof(_ffi.ReadResult) == 28
+    assert _ffi.MATCH_DTYPE.itemsize == 24
+    assert C.sizeof(_ffi.Stats) == 4 * 8 + 3 * 8 + 4 * 4
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from metabuli_b200 import _ffi
+    lib = _ffi.load_library()
+    cfg = _ffi.Config(kmer_format=2, seq_mode=1, tie_ratio=0.95, min_cons_cnt=4, min_cons_cnt_euk=9, match_per_kmer=4)
+    ctx = C.c_void_p()
+    assert lib.mbl_create(C.byref(cfg), C.byref(ctx)) == _ffi.MBL_E_NO_DEVICE
+    assert not ctx.value
+
+
+def test_product_does_not_touch_oracle():
+    """Nothing under metabuli_b200/ may reference the oracle (rule ③)."""
+    for base, _, files in os.walk(os.path.join(ROOT, "metabuli_b200")):
+        if "_lib" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "mbl_oracle" not in txt and "import oracle" not in txt and "/oracle/" not in txt, os.path.join(base, f)
