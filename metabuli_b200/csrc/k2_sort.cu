@@ -4,8 +4,10 @@
 // sort on exactly the bits that carry order:
 //   query metamers : the 40-bit amino-acid part only (bits 24..63).  The merge kernel treats an
 //                    amino-acid group as a set, so order inside a group is free.
-//   matches        : two stable LSD passes over a 32-bit permutation — first (frame,pos,hamming,dna),
-//                    then (seqID,species) — each trimmed to the bits the batch actually uses.
+//   matches        : one radix sort of a 32-bit permutation on (seqID, species, frame, pos) packed into the
+//                    bits the batch actually uses (48 for 150-bp reads), then the short runs that share that
+//                    key are ordered by (hamming, dna) in place — together the reference's total order.
+//                    Batches whose packed key would not fit 64 bits fall back to two stable LSD passes.
 #include <cub/cub.cuh>
 
 #include "kernels.cuh"
@@ -74,6 +76,41 @@ __global__ void match_gather_kernel(const mbl_match_rec* __restrict__ in, const 
     uint64_t a = s[0], b = s[1], c = s[2];
     d[0] = a; d[1] = b; d[2] = c;
 }
+// single-pass key: seqID | species | frame | pos
+__global__ void match_fullkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, int sp_bits, int pos_bits, uint64_t* __restrict__ key,
+                                     uint32_t* __restrict__ idx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t q = m[i].qinfo;
+    uint64_t k = (uint64_t)qi_seq(q);
+    k = (k << sp_bits) | (uint64_t)(uint32_t)m[i].species_id;
+    k = (k << 3) | (uint64_t)qi_frame(q);
+    k = (k << pos_bits) | (uint64_t)qi_pos(q);
+    key[i] = k;
+    idx[i] = (uint32_t)i;
+}
+// order the run of records that share (seqID, species, frame, pos) by (hamming, dna): the thread that owns
+// the first record of a run insertion-sorts it in place (runs are 1-3 records long in practice)
+__global__ void match_fix_runs_kernel(mbl_match_rec* __restrict__ m, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t q = m[i].qinfo;
+    const int32_t sp = m[i].species_id;
+    if (i > 0 && m[i - 1].qinfo == q && m[i - 1].species_id == sp) return;      // not a run start
+    size_t e = i + 1;
+    while (e < n && m[e].qinfo == q && m[e].species_id == sp) ++e;
+    if (e - i < 2) return;
+    auto less = [](const mbl_match_rec& a, const mbl_match_rec& b) {
+        if (a.hamming != b.hamming) return a.hamming < b.hamming;
+        return a.dna_encoding < b.dna_encoding;
+    };
+    for (size_t a = i + 1; a < e; ++a) {
+        mbl_match_rec v = m[a];
+        size_t b = a;
+        while (b > i && less(v, m[b - 1])) { m[b] = m[b - 1]; --b; }
+        m[b] = v;
+    }
+}
 // seg_begin/seg_end per read from the sorted match list (Classifier.cpp:174-185 MatchBlocks)
 __global__ void segment_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t n_reads, uint64_t* __restrict__ seg_begin,
                                uint64_t* __restrict__ seg_end) {
@@ -103,6 +140,15 @@ void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
     const int pos_bits = bits_for(max_pos);
     const int sp_bits = bits_for((uint64_t)(uint32_t)max_taxid);
     const int seq_bits = bits_for(n_reads);
+    if (seq_bits + sp_bits + 3 + pos_bits <= 64) {
+        match_fullkey_kernel<<<blocks, 256, 0, st>>>(in, n, sp_bits, pos_bits, key_a, idx_a);
+        cub::DoubleBuffer<uint64_t> k(key_a, key_b);
+        cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
+        MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, seq_bits + sp_bits + 3 + pos_bits, st));
+        match_gather_kernel<<<blocks, 256, 0, st>>>(in, v.Current(), n, out);
+        match_fix_runs_kernel<<<blocks, 256, 0, st>>>(out, n);
+        return;
+    }
     match_lowkey_kernel<<<blocks, 256, 0, st>>>(in, n, pos_bits, key_a, idx_a);
     cub::DoubleBuffer<uint64_t> k(key_a, key_b);
     cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);

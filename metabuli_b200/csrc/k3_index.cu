@@ -56,11 +56,11 @@ cell_boundary_kernel(const uint16_t* __restrict__ diff, uint64_t n_u16, uint64_t
 }
 
 // one thread per nominal tile grid point: the cell that holds the first group start at or after it
-__global__ void tile_candidate_kernel(const uint64_t* __restrict__ b_kidx, uint64_t n_cells, uint64_t n_grid,
+__global__ void tile_candidate_kernel(const uint64_t* __restrict__ b_kidx, uint64_t n_cells, uint64_t n_grid, uint32_t tile_cells,
                                       uint64_t* __restrict__ cand) {
     uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_grid) return;
-    uint64_t c = m * kTileCells;
+    uint64_t c = m * tile_cells;
     while (c < n_cells && b_kidx[c] == kNone) ++c;
     cand[m] = c < n_cells ? c : kNone;
 }
@@ -131,12 +131,16 @@ jumbo_decode_kernel(const uint16_t* __restrict__ diff, const Tile* __restrict__ 
 }
 
 // -------------------------------------------------------------------------------------------------
-void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, cudaStream_t st,
-                          TileDirectory& dir) {
+void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
+                          cudaStream_t st, TileDirectory& dir) {
     dir = TileDirectory();
+    if (tile_cells < 1) tile_cells = 1;
+    dir.tile_cells = tile_cells;
+    dir.max_u16 = 2 * tile_cells * kCellU16 - 16;
+    dir.max_kmers = tile_cells * kCellU16;
     if (n_u16 == 0 || n_kmers == 0) return;
     const uint64_t n_cells = (n_u16 + kCellU16 - 1) / kCellU16;
-    const uint64_t n_grid = (n_cells + kTileCells - 1) / kTileCells;
+    const uint64_t n_grid = (n_cells + tile_cells - 1) / tile_cells;
     const uint64_t n_kmers_eff = n_kmers - 1;                       // Q1
     uint64_t *cell_cnt, *cell_sum, *b_kidx, *b_off, *b_base, *b_aa, *cand;
     uint32_t *flag, *rank;
@@ -162,7 +166,7 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cell_cnt, dir.cell_k, n_cells, st);
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cell_sum, dir.cell_v, n_cells, st);
     cell_boundary_kernel<<<blocks, kWarps * 32, 0, st>>>(d_diff, n_u16, n_cells, dir.cell_k, dir.cell_v, b_kidx, b_off, b_base, b_aa);
-    tile_candidate_kernel<<<(unsigned)((n_grid + 255) / 256), 256, 0, st>>>(b_kidx, n_cells, n_grid, cand);
+    tile_candidate_kernel<<<(unsigned)((n_grid + 255) / 256), 256, 0, st>>>(b_kidx, n_cells, n_grid, tile_cells, cand);
     MBL_CUDA(cudaMemsetAsync(flag, 0, 4 * (n_grid + 1), st));
     tile_flag_kernel<<<(unsigned)((n_grid + 255) / 256), 256, 0, st>>>(cand, n_grid, flag);
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, rank, n_grid + 1, st);
@@ -181,7 +185,7 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
     MBL_CUDA(cudaMalloc(&d_cnt, 16));
     MBL_CUDA(cudaMemsetAsync(d_cnt, 0, 16, st));
     tile_extent_kernel<<<(unsigned)((dir.n_tiles + 255) / 256), 256, 0, st>>>(dir.tiles, dir.n_tiles, n_u16, n_kmers_eff,
-                                                                            kTileMaxU16 - 16, kTileMaxKmers, d_cnt, d_cnt + 1);
+                                                                            dir.max_u16, dir.max_kmers, d_cnt, d_cnt + 1);
     unsigned long long h_cnt[2];
     MBL_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
     MBL_CUDA(cudaStreamSynchronize(st));

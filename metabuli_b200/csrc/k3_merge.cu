@@ -7,11 +7,18 @@
 // candidates whose codon-level Hamming sum is <= min(2*min, 7).
 //
 // B200: the index lives in HBM behind a tile directory (k3_index.cu).  A persistent CTA pulls work
-// items (tile, query slice); the tile's fragments and taxids are staged into shared memory with two
-// 1-D TMA bulk copies (cp.async.bulk + mbarrier), eight warps decode the tile's cells independently
-// from their checkpoints (delta_decode.cuh) into a sorted value array in shared memory, and the CTA then
-// streams its slice of the sorted queries through: binary search of the amino-acid group, Hamming
-// filter via a 4096-entry two-codon table, Match records written through warp-private output chunks.
+// items (tile, query slice):
+//   1. stage   two 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) bring the tile's fragments
+//              and taxids into shared memory;
+//   2. decode  eight warps decode the tile's cells independently from their checkpoints
+//              (delta_decode.cuh) into a sorted value array; a second sweep records, per amino-acid group
+//              start, where the group ends, and fills a bucket table (monotone hash of the amino-acid part)
+//              so a query finds its group in O(1);
+//   3. match   a warp takes 32 consecutive queries: bucket lookup -> (group start, size) per lane, then the
+//              (query, candidate) PAIRS of the whole warp are spread evenly over the lanes (shuffle search
+//              over the inclusive scan), Hamming sums come from a 4 KiB two-codon table, per-query minima
+//              from match_any + reduce_min, and the surviving pairs are ballot-compacted into the warp's
+//              private output chunk, so Match records leave as coalesced 24-byte rows.
 // HBM traffic per launch = index once + 8 B per query (+ 8 B qinfo per matching query) + 24 B per match.
 #include "delta_decode.cuh"
 #include "kernels.cuh"
@@ -24,16 +31,27 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kOutChunk = 256;          // match slots a warp reserves at a time
 constexpr uint64_t kNone = ~0ull;
+constexpr uint32_t kFull = 0xffffffffu;
 
-struct __align__(16) MergeSmem {
-    unsigned long long mbar;
-    unsigned int item;
-    unsigned int pad;
-    uint16_t ham[4096];
-    uint16_t frag[kTileMaxU16 + 16];
-    int32_t info[kTileMaxKmers + 8];
-    uint64_t vals[kTileMaxKmers];
+// dynamic shared memory layout (sizes depend on the tile geometry chosen at load time)
+struct SmemLayout {
+    uint32_t off_ham, off_ham1, off_minh, off_frag, off_info, off_vals, off_gend, off_bstart, total;
 };
+__host__ __device__ inline SmemLayout smem_layout(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets) {
+    SmemLayout l;
+    uint32_t o = 16;                                   // mbarrier + item slot
+    l.off_ham = o;   o += 4096;                        // two-codon Hamming sums (u8)
+    l.off_ham1 = o;  o += 64;                          // single-codon distances (u8)
+    l.off_minh = o;  o += kWarps * 32 * 4;             // per-warp per-query minima (general path)
+    l.off_frag = o;  o += (max_u16 + 16) * 2;
+    l.off_info = o;  o += (max_kmers + 8) * 4;
+    o = (o + 15) & ~15u;
+    l.off_vals = o;  o += max_kmers * 8;
+    l.off_gend = o;  o += (max_kmers + 8) * 2;
+    l.off_bstart = o; o += (n_buckets + 8) * 2;
+    l.total = (o + 15) & ~15u;
+    return l;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -66,22 +84,49 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
     return v;
 }
 
-struct HamOut { uint32_t sum, plain, rev; };
-// codon-level Hamming distances of two 24-bit DNA parts via the two-codon table
-__device__ __forceinline__ HamOut hamming(const uint16_t* ham, uint32_t q, uint32_t t) {
-    uint32_t e0 = ham[((q & 63u) << 6) | (t & 63u)];
-    uint32_t e1 = ham[(((q >> 6) & 63u) << 6) | ((t >> 6) & 63u)];
-    uint32_t e2 = ham[(((q >> 12) & 63u) << 6) | ((t >> 12) & 63u)];
-    uint32_t e3 = ham[(((q >> 18) & 63u) << 6) | ((t >> 18) & 63u)];
-    HamOut o;
-    o.sum = (e0 & 15u) + (e1 & 15u) + (e2 & 15u) + (e3 & 15u);
-    o.plain = ((e0 >> 4) & 15u) | (((e1 >> 4) & 15u) << 4) | (((e2 >> 4) & 15u) << 8) | (((e3 >> 4) & 15u) << 12);
-    o.rev = ((e3 >> 8) & 15u) | (((e2 >> 8) & 15u) << 4) | (((e1 >> 8) & 15u) << 8) | (((e0 >> 8) & 15u) << 12);
-    return o;
+// sum of the 8 codon distances of two 24-bit DNA parts: four lookups in the two-codon table
+__device__ __forceinline__ uint32_t ham_sum(const uint8_t* ham, uint32_t q, uint32_t t) {
+    return (uint32_t)ham[((q & 63u) << 6) | (t & 63u)] + ham[(((q >> 6) & 63u) << 6) | ((t >> 6) & 63u)] +
+           ham[(((q >> 12) & 63u) << 6) | ((t >> 12) & 63u)] + ham[((q >> 18) << 6) | (t >> 18)];
 }
-__device__ __forceinline__ uint32_t ham_sum_only(const uint16_t* ham, uint32_t q, uint32_t t) {
-    return (ham[((q & 63u) << 6) | (t & 63u)] & 15u) + (ham[(((q >> 6) & 63u) << 6) | ((t >> 6) & 63u)] & 15u) +
-           (ham[(((q >> 12) & 63u) << 6) | ((t >> 12) & 63u)] & 15u) + (ham[(((q >> 18) & 63u) << 6) | ((t >> 18) & 63u)] & 15u);
+// per-codon 2-bit fields (KmerMatcher.h:386-416): codon at value bits 3i goes to field bits 2i ("plain",
+// getHammings) or 2(7-i) (getHammings_reverse); HAMMING_LUT7 rows 4-5 x columns 6-7 hold 1 instead of 0 (Q3)
+__device__ __forceinline__ uint32_t ham_fields(const uint8_t* ham1, uint32_t q, uint32_t t, bool plain) {
+    uint32_t f = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t d = ham1[(((q >> (3 * i)) & 7u) << 3) | ((t >> (3 * i)) & 7u)] & 3u;
+        f |= d << (plain ? 2 * i : 2 * (7 - i));
+    }
+    const uint32_t qc = plain ? (q >> 21) & 7u : q & 7u, tc = plain ? (t >> 21) & 7u : t & 7u;
+    if ((qc & 6u) == 4u && tc >= 6u) f |= 0x4000u;
+    return f;
+}
+
+// warp-private output chunk (reserved from the global cursor kOutChunk slots at a time)
+struct OutChunk {
+    uint64_t base = 0;
+    uint32_t used = kOutChunk;
+};
+// reserve `cnt` (warp-uniform) consecutive logical slots; returns the slot of logical index r via slot_of()
+struct Reservation { uint64_t old_base, new_base; uint32_t old_used, rem; };
+__device__ __forceinline__ Reservation reserve(OutChunk& c, uint32_t cnt, unsigned long long* cursor, int lane) {
+    Reservation r;
+    r.old_base = c.base; r.old_used = c.used; r.rem = kOutChunk - c.used; r.new_base = 0;
+    if (cnt > r.rem) {
+        const uint32_t need = max(kOutChunk, cnt - r.rem);
+        unsigned long long nb = 0;
+        if (lane == 0) nb = atomicAdd(cursor, (unsigned long long)need);
+        r.new_base = __shfl_sync(kFull, nb, 0);
+        c.base = r.new_base;
+        c.used = (cnt - r.rem > kOutChunk) ? kOutChunk : cnt - r.rem;
+    } else {
+        c.used += cnt;
+    }
+    return r;
+}
+__device__ __forceinline__ uint64_t slot_of(const Reservation& r, uint32_t i) {
+    return i < r.rem ? r.old_base + r.old_used + i : r.new_base + (i - r.rem);
 }
 
 }  // namespace
@@ -130,164 +175,225 @@ __global__ void merge_item_fill_kernel(uint64_t n_tiles, const uint64_t* __restr
 }
 
 // ---- the merge kernel ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 merge_kernel(MergeArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    MergeSmem& sm = *reinterpret_cast<MergeSmem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SmemLayout L = smem_layout(a.max_u16, a.max_kmers, a.n_buckets);
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);
+    unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 8);
+    uint8_t* s_ham = smem + L.off_ham;
+    uint8_t* s_ham1 = smem + L.off_ham1;
+    uint32_t* s_minh = reinterpret_cast<uint32_t*>(smem + L.off_minh);
+    uint16_t* s_frag = reinterpret_cast<uint16_t*>(smem + L.off_frag);
+    int32_t* s_info = reinterpret_cast<int32_t*>(smem + L.off_info);
+    uint64_t* s_vals = reinterpret_cast<uint64_t*>(smem + L.off_vals);
+    uint16_t* s_gend = reinterpret_cast<uint16_t*>(smem + L.off_gend);
+    uint16_t* s_bstart = reinterpret_cast<uint16_t*>(smem + L.off_bstart);
 
-    for (int i = tid; i < 4096; i += kThreads) sm.ham[i] = a.ham_pair[i];
-    if (tid == 0) mbar_init(&sm.mbar, 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 4096; i += kThreads) s_ham[i] = (uint8_t)(a.ham_pair[i] & 15u);
+    if (tid < 64) s_ham1[tid] = a.ham_single[tid];
+    if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     unsigned parity = 0;
     const uint32_t n_items = a.item_off[a.n_tiles];
     const bool fmt2 = a.kmer_format == 2;
-
-    // warp-private output chunk
-    uint64_t chunk_base = 0;
-    uint32_t chunk_used = kOutChunk;         // forces a reservation on first use
+    uint32_t* my_minh = s_minh + warp * 32;
+    OutChunk chunk;
     unsigned long long my_matches = 0;
 
     while (true) {
-        if (tid == 0) sm.item = atomicAdd(a.item_cursor, 1u);
+        if (tid == 0) *s_item = atomicAdd(a.item_cursor, 1u);
         __syncthreads();
-        const uint32_t item = sm.item;
+        const uint32_t item = *s_item;
         if (item >= n_items) break;
         const MergeItem it = a.items[item];
         const Tile tl = a.tiles[it.tile];
         const uint32_t nk = tl.n_kmers;
+        const bool jumbo = tl.jumbo_off != kNone;
         const uint64_t* vals;
         const int32_t* infos;
-        if (tl.jumbo_off == kNone) {
-            // -- stage the tile: fragments + taxids, two bulk copies on one mbarrier
+        uint64_t base40 = 0, last40 = 0;
+        uint32_t shift = 0;
+        if (!jumbo) {
+            // -- 1. stage the tile: fragments + taxids, two bulk copies on one mbarrier
             const uint64_t d0 = tl.diff_begin, d1 = tl.diff_begin + tl.n_u16;
             const uint64_t a0 = d0 & ~7ull, a1 = (d1 + 7ull) & ~7ull;
             const uint64_t i0 = tl.info_begin & ~3ull, i1 = (tl.info_begin + nk + 3ull) & ~3ull;
             if (tid == 0) {
                 fence_proxy_async();
                 const unsigned fb = (unsigned)((a1 - a0) * 2), ib = (unsigned)((i1 - i0) * 4);
-                mbar_expect_tx(&sm.mbar, fb + ib);
-                tma_load_1d(sm.frag, a.diff + a0, fb, &sm.mbar);
-                if (ib) tma_load_1d(sm.info, a.info + i0, ib, &sm.mbar);
+                mbar_expect_tx(mbar, fb + ib);
+                tma_load_1d(s_frag, a.diff + a0, fb, mbar);
+                if (ib) tma_load_1d(s_info, a.info + i0, ib, mbar);
             }
-            mbar_wait(&sm.mbar, parity);
+            mbar_wait(mbar, parity);
             parity ^= 1u;
-            // -- decode: one warp per checkpoint cell
+            // -- 2a. decode: one warp per checkpoint cell
             const uint64_t c0 = d0 / kCellU16, c1 = (d1 + kCellU16 - 1) / kCellU16;
             for (uint64_t c = c0 + warp; c < c1; c += kWarps) {
                 const uint64_t s_abs = max(c * (uint64_t)kCellU16, d0), e_abs = min((c + 1) * (uint64_t)kCellU16, d1);
                 uint64_t v, k;
                 if (s_abs == d0) { v = tl.base_value; k = tl.info_begin; }
                 else { v = a.cell_v[c]; k = a.cell_k[c]; }
-                uint64_t* out_vals = sm.vals;
                 const uint64_t kb = tl.info_begin;
-                warp_decode(sm.frag, (long long)(d0 - a0), (long long)(s_abs - a0), (long long)(e_abs - a0), v, k,
+                warp_decode(s_frag, (long long)(d0 - a0), (long long)(s_abs - a0), (long long)(e_abs - a0), v, k,
                             [&](uint64_t kk, uint64_t val, uint64_t, long long) {
                                 uint64_t rel = kk - kb;
-                                if (rel < nk) out_vals[rel] = val;
+                                if (rel < nk) s_vals[rel] = val;
                             });
             }
             __syncthreads();
-            vals = sm.vals;
-            infos = sm.info + (tl.info_begin - i0);
+            // -- 2b. group ends + bucket table.  bucket(aa) = (aa40 - base40) >> shift is monotone, so bucket b's
+            //        k-mers are [bstart[b], bstart[b+1])
+            base40 = s_vals[0] >> 24;
+            last40 = s_vals[nk - 1] >> 24;
+            {
+                const uint64_t span = last40 - base40;
+                const int bits = 64 - __clzll(span | 1ull);
+                const int lb = 31 - __clz(a.n_buckets);
+                shift = bits > lb ? (uint32_t)(bits - lb) : 0u;
+            }
+            for (uint32_t i = tid; i < nk; i += kThreads) {
+                const uint64_t aa = s_vals[i] >> 24;
+                const bool start = i == 0 || (s_vals[i - 1] >> 24) != aa;
+                if (start) {
+                    uint32_t j = i + 1;
+                    while (j < nk && (s_vals[j] >> 24) == aa) ++j;
+                    s_gend[i] = (uint16_t)j;
+                    const uint32_t b = (uint32_t)((aa - base40) >> shift);
+                    const int32_t pb = i == 0 ? -1 : (int32_t)(((s_vals[i - 1] >> 24) - base40) >> shift);
+                    for (int32_t x = pb + 1; x <= (int32_t)b; ++x) s_bstart[x] = (uint16_t)i;
+                }
+            }
+            {
+                const uint32_t lastb = (uint32_t)((last40 - base40) >> shift);
+                for (uint32_t x = lastb + 1 + tid; x <= a.n_buckets; x += kThreads) s_bstart[x] = (uint16_t)nk;
+            }
+            __syncthreads();
+            vals = s_vals;
+            infos = s_info + (tl.info_begin - i0);
         } else {
             vals = a.jumbo_vals + tl.jumbo_off;
             infos = a.info + tl.info_begin;
         }
 
-        // -- stream the query slice
+        // -- 3. stream the query slice, 32 queries per warp iteration
         for (uint64_t qb = it.q_begin + (uint64_t)warp * 32; qb < it.q_end; qb += kThreads) {
             const uint64_t qi = qb + lane;
             const bool active = qi < it.q_end;
             const uint64_t qv = active ? ld_stream_u64(a.q_value + qi) : kBlank;
-            const uint64_t qaa = aa_part(qv);
-            uint32_t lo = 0, hi = nk;
-            while (lo < hi) {
-                uint32_t mid = (lo + hi) >> 1;
-                if (vals[mid] < qaa) lo = mid + 1; else hi = mid;
-            }
-            uint32_t g0 = lo, g1 = lo, cnt = 0, maxH = 0;
-            const uint32_t qd = (uint32_t)(qv & kDnaMask);
-            if (active && g0 < nk && aa_part(vals[g0]) == qaa) {
-                uint32_t minH = 255;
-                for (; g1 < nk && aa_part(vals[g1]) == qaa; ++g1)
-                    minH = min(minH, ham_sum_only(sm.ham, qd, (uint32_t)(vals[g1] & kDnaMask)));
-                maxH = min(minH * 2u, 7u);                                   // KmerMatcher.cpp:1136
-                for (uint32_t j = g0; j < g1; ++j)
-                    cnt += ham_sum_only(sm.ham, qd, (uint32_t)(vals[j] & kDnaMask)) <= maxH;
-            }
-            // warp-aggregated slot assignment inside the warp's private chunk
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += n;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total == 0) continue;
-            const uint32_t rem = kOutChunk - chunk_used;
-            uint64_t new_base = 0;
-            if (total > rem) {
-                const uint32_t need = max(kOutChunk, total - rem);
-                if (lane == 0) new_base = atomicAdd(a.out_count, (unsigned long long)need);
-                new_base = __shfl_sync(0xffffffffu, new_base, 0);
-            }
-            if (cnt) {
-                const uint64_t qinfo = a.q_info[qi];
-                const uint32_t frame = qi_frame(qinfo);
-                const bool plain = !((frame < 3) ^ fmt2);                    // KmerMatcher.cpp:1140
-                uint32_t w = incl - cnt;
-                for (uint32_t j = g0; j < g1; ++j) {
-                    const uint64_t tv = vals[j];
-                    const uint32_t td = (uint32_t)(tv & kDnaMask);
-                    const HamOut h = hamming(sm.ham, qd, td);
-                    if (h.sum > maxH) continue;
-                    uint32_t field = plain ? h.plain : h.rev;
-                    // HAMMING_LUT7 rows 4-5 x columns 6-7 hold 1 (Q3); it serves the codon at value bits 21..23
-                    // in the plain orientation and the codon at bits 0..2 in the reversed one
-                    const uint32_t qc = plain ? (qd >> 21) & 7u : qd & 7u, tc = plain ? (td >> 21) & 7u : td & 7u;
-                    if ((qc & 6u) == 4u && tc >= 6u) field |= 0x4000u;
-                    const int32_t taxid = (int32_t)((uint32_t)infos[j] & a.info_mask);
-                    const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
-                    if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);   // Q2
-                    const uint64_t slot = (w < rem) ? chunk_base + chunk_used + w : new_base + (w - rem);
-                    if (slot < a.out_cap) {
-                        uint64_t* o = reinterpret_cast<uint64_t*>(a.out + slot);
-                        o[0] = qinfo;
-                        o[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
-                        o[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(h.sum & 0xFFu) << 48);
-                    }
-                    ++w;
+            const uint64_t q40 = qv >> 24;
+            uint32_t g0 = 0, n = 0;
+            if (!jumbo) {
+                if (active && q40 >= base40 && q40 <= last40) {
+                    const uint32_t b = (uint32_t)((q40 - base40) >> shift);
+                    uint32_t j = s_bstart[b];
+                    const uint32_t e = s_bstart[b + 1];
+                    while (j < e && (vals[j] >> 24) < q40) j = s_gend[j];      // hop from group start to group start
+                    if (j < e && (vals[j] >> 24) == q40) { g0 = j; n = s_gend[j] - j; }
+                }
+            } else if (active) {
+                uint32_t lo = 0, hi = nk;
+                while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((vals[mid] >> 24) < q40) lo = mid + 1; else hi = mid; }
+                if (lo < nk && (vals[lo] >> 24) == q40) {
+                    g0 = lo;
+                    uint32_t j = lo + 1;
+                    while (j < nk && (vals[j] >> 24) == q40) ++j;
+                    n = j - lo;
                 }
             }
-            my_matches += cnt;
-            if (total > rem) {
-                chunk_base = new_base;
-                chunk_used = total - rem;
-                // a reservation larger than one chunk is consumed entirely by this request
-                if (total - rem > kOutChunk) chunk_used = kOutChunk;
-            } else {
-                chunk_used += total;
+            // inclusive scan of the candidate counts: pair p of the warp belongs to the lane o with excl[o] <= p < incl[o]
+            uint32_t incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            if (total == 0) continue;
+            const uint32_t excl = incl - n;
+            const uint32_t qd = (uint32_t)qv & 0xFFFFFFu;
+            const bool single = total <= 32;
+            if (!single) { my_minh[lane] = 255u; __syncwarp(); }
+            // sweep 1 (general path only): per-query minimum of the Hamming sums
+            if (!single) {
+                for (uint32_t pb = 0; pb < total; pb += 32) {
+                    const uint32_t p = pb + lane;
+                    const bool valid = p < total;
+                    uint32_t o = 0;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, (o + s - 1) & 31); if (v <= p) o += s; }
+                    o &= 31u;
+                    const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
+                    const uint32_t oq = __shfl_sync(kFull, qd, o);
+                    const uint32_t sum = valid ? ham_sum(s_ham, oq, (uint32_t)vals[valid ? j : 0] & 0xFFFFFFu) : 255u;
+                    const uint32_t grp = __match_any_sync(kFull, valid ? o : 32u + lane);
+                    const uint32_t mn = __reduce_min_sync(grp, sum);
+                    if (valid && (grp & ((1u << lane) - 1)) == 0) my_minh[o] = min(my_minh[o], mn);
+                    __syncwarp();
+                }
+            }
+            // sweep 2: select, compact, emit
+            for (uint32_t pb = 0; pb < total; pb += 32) {
+                const uint32_t p = pb + lane;
+                const bool valid = p < total;
+                uint32_t o = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, (o + s - 1) & 31); if (v <= p) o += s; }
+                o &= 31u;
+                const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
+                const uint32_t oq = __shfl_sync(kFull, qd, o);
+                const uint32_t td = valid ? (uint32_t)vals[j] & 0xFFFFFFu : 0u;
+                const uint32_t sum = valid ? ham_sum(s_ham, oq, td) : 255u;
+                uint32_t mn;
+                if (single) {
+                    const uint32_t grp = __match_any_sync(kFull, valid ? o : 32u + lane);
+                    mn = __reduce_min_sync(grp, sum);
+                } else {
+                    mn = my_minh[o];
+                }
+                const uint32_t maxH = min(mn * 2u, 7u);                               // KmerMatcher.cpp:1136
+                const bool sel = valid && sum <= maxH;
+                const uint32_t bal = __ballot_sync(kFull, sel);
+                const uint32_t cnt = __popc(bal);
+                if (cnt == 0) continue;
+                const Reservation rs = reserve(chunk, cnt, a.out_count, lane);
+                if (sel) {
+                    const uint64_t qinfo = a.q_info[qb + o];
+                    const uint32_t frame = qi_frame(qinfo);
+                    const bool plain = !((frame < 3) ^ fmt2);                          // KmerMatcher.cpp:1140
+                    const uint32_t field = ham_fields(s_ham1, oq, td, plain);
+                    const int32_t taxid = (int32_t)((uint32_t)infos[j] & a.info_mask);
+                    const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
+                    if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);        // Q2
+                    const uint64_t slot = slot_of(rs, __popc(bal & ((1u << lane) - 1)));
+                    if (slot < a.out_cap) {
+                        uint64_t* w = reinterpret_cast<uint64_t*>(a.out + slot);
+                        w[0] = qinfo;
+                        w[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
+                        w[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
+                    }
+                }
+                my_matches += cnt;
             }
         }
         __syncthreads();
     }
     // blank out the unused tail of the warp's last chunk (seqID 0 == not a match)
-    if (chunk_used < kOutChunk) {
-        for (uint32_t w = chunk_used + lane; w < kOutChunk; w += 32) {
-            const uint64_t slot = chunk_base + w;
+    if (chunk.used < kOutChunk) {
+        for (uint32_t w = chunk.used + lane; w < kOutChunk; w += 32) {
+            const uint64_t slot = chunk.base + w;
             if (slot < a.out_cap) {
                 uint64_t* o = reinterpret_cast<uint64_t*>(a.out + slot);
                 o[0] = 0; o[1] = 0; o[2] = 0;
             }
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_matches += __shfl_xor_sync(0xffffffffu, my_matches, o);
     if (lane == 0 && my_matches) atomicAdd(a.out_count + 1, my_matches);
 }
 
-size_t merge_smem_bytes() { return sizeof(MergeSmem); }
+size_t merge_smem_bytes(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets) { return smem_layout(max_u16, max_kmers, n_buckets).total; }
 
 void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
     const unsigned blocks = (unsigned)((a.n_tiles + 1 + 255) / 256);
@@ -298,11 +404,11 @@ void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
 }
 
 void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st) {
-    static bool attr_set = false;
-    const size_t smem = sizeof(MergeSmem);
-    if (!attr_set) {
+    static size_t attr_smem = 0;
+    const size_t smem = smem_layout(a.max_u16, a.max_kmers, a.n_buckets).total;
+    if (attr_smem != smem) {
         MBL_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_smem = smem;
     }
     int per_sm = 0;
     MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel, kThreads, smem));

@@ -5,7 +5,6 @@
 
 namespace mbl {
 
-constexpr uint32_t kTileMaxKmers = 4096;    // k-mers a shared-memory tile can hold
 constexpr uint32_t kItemQueries = 1u << 15; // queries per merge work item (hot tiles are split)
 
 struct TileDirectory {
@@ -14,6 +13,9 @@ struct TileDirectory {
     uint64_t* cell_v = nullptr;     // [n_cells] value of the last k-mer ending before the cell
     uint64_t* jumbo_vals = nullptr; // pre-decoded values of jumbo tiles
     uint64_t n_tiles = 0, n_cells = 0, n_jumbo = 0, n_jumbo_kmers = 0;
+    // geometry chosen at load time: nominal tile = tile_cells cells; tiles with more than max_u16 fragments or
+    // max_kmers k-mers are jumbo (pre-decoded in HBM)
+    uint32_t tile_cells = 4, max_u16 = 0, max_kmers = 0;
     uint64_t n_kmers_decoded = 0;   // number of end flags in the stream (must equal the info count)
 };
 
@@ -55,8 +57,8 @@ void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
 void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, uint64_t* seg_begin, uint64_t* seg_end, cudaStream_t st);
 
 // K3 directory (load time)
-void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, cudaStream_t st,
-                          TileDirectory& dir);
+void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
+                          cudaStream_t st, TileDirectory& dir);
 void free_tile_directory(TileDirectory& dir);
 
 // K3 merge (per batch)
@@ -74,7 +76,9 @@ struct MergeArgs {
     uint64_t n_query;               // non-blank
     const int32_t* taxid2species;
     int32_t max_taxid;
-    const uint16_t* ham_pair;       // 4096-entry table in HBM
+    const uint16_t* ham_pair;       // 4096-entry two-codon table in HBM
+    const uint8_t* ham_single;      // 64-entry single-codon distances
+    uint32_t max_u16, max_kmers, n_buckets;   // shared-memory tile geometry (see smem_layout in k3_merge.cu)
     int kmer_format;
     mbl_match_rec* out;
     uint64_t out_cap;
@@ -92,7 +96,7 @@ struct MergeArgs {
 };
 void launch_merge_plan(const MergeArgs& a, cudaStream_t st);      // partition + work items
 void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st);
-size_t merge_smem_bytes();
+size_t merge_smem_bytes(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets);
 
 // K5
 struct ScoreArgs {

@@ -2,6 +2,7 @@
 // and the batch pipeline  K1 extract -> K2 sort -> K3 merge -> K4 match sort -> K5 score
 // (reference: Classifier::startClassify, src/commons/Classifier.cpp:44-164).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -44,6 +45,8 @@ struct mbl_ctx {
     // tables
     uint8_t *d_base_code = nullptr, *d_codon = nullptr;
     uint16_t* d_ham_pair = nullptr;
+    uint8_t* d_ham_single = nullptr;
+    uint32_t tile_cells = 4;
     // index
     uint16_t* d_diff = nullptr;
     int32_t* d_info = nullptr;
@@ -229,6 +232,8 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     ma.q_value = qv; ma.q_info = qi; ma.n_query = n_query;
     ma.taxid2species = c->tax.taxid2species; ma.max_taxid = c->tax.max_taxid;
     ma.ham_pair = c->d_ham_pair; ma.kmer_format = c->cfg.kmer_format;
+    ma.ham_single = c->d_ham_single; ma.max_u16 = c->dir.max_u16 + 16; ma.max_kmers = c->dir.max_kmers;
+    ma.n_buckets = 1; while (ma.n_buckets < ma.max_kmers) ma.n_buckets <<= 1;
     ma.out_count = counters + 1;
     ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
     ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
@@ -368,6 +373,8 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         c->d_base_code = upload(c, t.base_code, 256);
         c->d_codon = upload(c, t.codon, 512);
         c->d_ham_pair = upload(c, t.ham_pair, 4096);
+        c->d_ham_single = upload(c, t.ham_sum, 64);
+        if (const char* e = getenv("MBL_TILE_CELLS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->tile_cells = (uint32_t)v; }
         MBL_CUDA(cudaStreamSynchronize(c->st));
     } catch (const CudaError& e) {
         fail_cuda(c, e);
@@ -390,7 +397,7 @@ void mbl_destroy(mbl_ctx* c) {
                    &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw, &c->q_lo,
                    &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs})
         b->release();
-    cudaFree(c->d_base_code); cudaFree(c->d_codon); cudaFree(c->d_ham_pair);
+    cudaFree(c->d_base_code); cudaFree(c->d_codon); cudaFree(c->d_ham_pair); cudaFree(c->d_ham_single);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
     delete c;
@@ -415,7 +422,7 @@ int mbl_load_db(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx) {
         c->tax.taxid2species = up(tx->taxid2species, T);
         c->tax.max_taxid = tx->max_taxid; c->tax.M_k = tx->M_k; c->tax.eukaryota = tx->eukaryota; c->tax.max_nodes = (uint32_t)N;
         MBL_CUDA(cudaStreamSynchronize(c->st));
-        build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->st, c->dir);
+        build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->tile_cells, c->st, c->dir);
         // the k-mer count implied by the end flags must agree with the info file
         if (c->dir.n_kmers_decoded != c->n_kmers) {
             char msg[256];
@@ -618,6 +625,8 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
         ma.q_value = va; ma.q_info = qa; ma.n_query = nq;
         ma.taxid2species = c->tax.taxid2species; ma.max_taxid = c->tax.max_taxid;
         ma.ham_pair = c->d_ham_pair; ma.kmer_format = c->cfg.kmer_format;
+        ma.ham_single = c->d_ham_single; ma.max_u16 = c->dir.max_u16 + 16; ma.max_kmers = c->dir.max_kmers;
+        ma.n_buckets = 1; while (ma.n_buckets < ma.max_kmers) ma.n_buckets <<= 1;
         ma.out_count = counters + 1;
         ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
         ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;

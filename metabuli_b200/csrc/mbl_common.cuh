@@ -37,8 +37,6 @@ MBL_HD int windows_per_frame(int len) { return max_covered_length(len) / 3 - 7; 
 // A tile is an amino-acid-group-aligned run of k-mers; the decoder additionally restarts at fixed
 // cells of kCellU16 fragments, each with its own (k-mer index, running value) checkpoint.
 constexpr int kCellU16 = 1024;            // decode checkpoint grid (u16 fragments)
-constexpr int kTileCells = 4;             // nominal tile = 4 cells = 4096 fragments (8 KiB)
-constexpr int kTileMaxU16 = 8192;         // tiles longer than this are "jumbo" (pre-decoded in HBM)
 
 struct Tile {
     uint64_t diff_begin;     // u16 index of the first fragment of the tile's first k-mer
