@@ -51,7 +51,7 @@ def parse():
 
 def db_shape(db_gib: float):
     """(genera, species_per_genus, strains, codons) giving ~db_gib of diffIdx+info."""
-    target_kmers = db_gib * (1 << 30) / 9.9          # 4 B info + ~2.95 fragments x 2 B per k-mer
+    target_kmers = db_gib * (1 << 30) / 7.9          # 4 B info + ~1.95 fragments x 2 B per k-mer (measured on this generator)
     species = int(min(10_000, max(12, target_kmers // 60_000)))
     spg = 20 if species >= 200 else 4
     genera = max(3, species // spg)

@@ -96,6 +96,7 @@ __global__ void match_fix_runs_kernel(mbl_match_rec* __restrict__ m, size_t n) {
     if (i >= n) return;
     const uint64_t q = m[i].qinfo;
     const int32_t sp = m[i].species_id;
+    if (qi_seq(q) == 0) return;                                                   // blank chunk tails
     if (i > 0 && m[i - 1].qinfo == q && m[i - 1].species_id == sp) return;      // not a run start
     size_t e = i + 1;
     while (e < n && m[e].qinfo == q && m[e].species_id == sp) ++e;

@@ -29,7 +29,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr uint32_t kOutChunk = 256;          // match slots a warp reserves at a time
+constexpr uint32_t kQueue = 64;              // per-warp hit queue (power of two, >= 63)
+constexpr uint32_t kLaneMaxCand = 48;        // groups larger than this are worked on by the whole warp
 constexpr uint64_t kNone = ~0ull;
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -40,9 +41,9 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout smem_layout(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets) {
     SmemLayout l;
     uint32_t o = 16;                                   // mbarrier + item slot
-    l.off_ham = o;   o += 4096;                        // two-codon Hamming sums (u8)
-    l.off_ham1 = o;  o += 64;                          // single-codon distances (u8)
-    l.off_minh = o;  o += kWarps * 32 * 4;             // per-warp per-query minima (general path)
+    l.off_ham = o;   o += 8192;                        // two-codon table: sum | plain nibble | reversed nibble (u16)
+    l.off_ham1 = o;  o += 0;
+    l.off_minh = o;  o += kWarps * kQueue * 16;        // per-warp hit queues {g0, n, query offset, query dna}
     l.off_frag = o;  o += (max_u16 + 16) * 2;
     l.off_info = o;  o += (max_kmers + 8) * 4;
     o = (o + 15) & ~15u;
@@ -84,49 +85,41 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
     return v;
 }
 
-// sum of the 8 codon distances of two 24-bit DNA parts: four lookups in the two-codon table
-__device__ __forceinline__ uint32_t ham_sum(const uint8_t* ham, uint32_t q, uint32_t t) {
-    return (uint32_t)ham[((q & 63u) << 6) | (t & 63u)] + ham[(((q >> 6) & 63u) << 6) | ((t >> 6) & 63u)] +
-           ham[(((q >> 12) & 63u) << 6) | ((t >> 12) & 63u)] + ham[((q >> 18) << 6) | (t >> 18)];
+// codon-level Hamming distances of two 24-bit DNA parts: four lookups in the two-codon table, whose
+// entries hold {sum:4, plain nibble:4, reversed nibble:4}; the four entries are kept so the per-codon fields
+// of a surviving candidate cost no further lookups
+struct HamQuad { uint32_t e0, e1, e2, e3; };
+__device__ __forceinline__ HamQuad ham_lookup(const uint16_t* ham, uint32_t q, uint32_t t) {
+    HamQuad h;
+    h.e0 = ham[((q & 63u) << 6) | (t & 63u)];
+    h.e1 = ham[(((q >> 6) & 63u) << 6) | ((t >> 6) & 63u)];
+    h.e2 = ham[(((q >> 12) & 63u) << 6) | ((t >> 12) & 63u)];
+    h.e3 = ham[((q >> 18) << 6) | (t >> 18)];
+    return h;
 }
+__device__ __forceinline__ uint32_t ham_sum(const HamQuad& h) { return (h.e0 & 15u) + (h.e1 & 15u) + (h.e2 & 15u) + (h.e3 & 15u); }
 // per-codon 2-bit fields (KmerMatcher.h:386-416): codon at value bits 3i goes to field bits 2i ("plain",
 // getHammings) or 2(7-i) (getHammings_reverse); HAMMING_LUT7 rows 4-5 x columns 6-7 hold 1 instead of 0 (Q3)
-__device__ __forceinline__ uint32_t ham_fields(const uint8_t* ham1, uint32_t q, uint32_t t, bool plain) {
-    uint32_t f = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint32_t d = ham1[(((q >> (3 * i)) & 7u) << 3) | ((t >> (3 * i)) & 7u)] & 3u;
-        f |= d << (plain ? 2 * i : 2 * (7 - i));
-    }
+__device__ __forceinline__ uint32_t ham_fields(const HamQuad& h, uint32_t q, uint32_t t, bool plain) {
+    uint32_t f = plain ? (((h.e0 >> 4) & 15u) | (((h.e1 >> 4) & 15u) << 4) | (((h.e2 >> 4) & 15u) << 8) | (((h.e3 >> 4) & 15u) << 12))
+                       : (((h.e3 >> 8) & 15u) | (((h.e2 >> 8) & 15u) << 4) | (((h.e1 >> 8) & 15u) << 8) | (((h.e0 >> 8) & 15u) << 12));
     const uint32_t qc = plain ? (q >> 21) & 7u : q & 7u, tc = plain ? (t >> 21) & 7u : t & 7u;
     if ((qc & 6u) == 4u && tc >= 6u) f |= 0x4000u;
     return f;
 }
 
-// warp-private output chunk (reserved from the global cursor kOutChunk slots at a time)
-struct OutChunk {
-    uint64_t base = 0;
-    uint32_t used = kOutChunk;
-};
-// reserve `cnt` (warp-uniform) consecutive logical slots; returns the slot of logical index r via slot_of()
-struct Reservation { uint64_t old_base, new_base; uint32_t old_used, rem; };
-__device__ __forceinline__ Reservation reserve(OutChunk& c, uint32_t cnt, unsigned long long* cursor, int lane) {
-    Reservation r;
-    r.old_base = c.base; r.old_used = c.used; r.rem = kOutChunk - c.used; r.new_base = 0;
-    if (cnt > r.rem) {
-        const uint32_t need = max(kOutChunk, cnt - r.rem);
-        unsigned long long nb = 0;
-        if (lane == 0) nb = atomicAdd(cursor, (unsigned long long)need);
-        r.new_base = __shfl_sync(kFull, nb, 0);
-        c.base = r.new_base;
-        c.used = (cnt - r.rem > kOutChunk) ? kOutChunk : cnt - r.rem;
-    } else {
-        c.used += cnt;
+// one 24-byte Match record (Match.h:9-26 without the vptr); Q2: taxid 0 / unmapped species raise the error flag
+__device__ __forceinline__ void emit_match(const MergeArgs& a, uint64_t slot, uint64_t qinfo, int32_t raw_taxid, uint32_t td,
+                                           uint32_t field, uint32_t sum) {
+    const int32_t taxid = (int32_t)((uint32_t)raw_taxid & a.info_mask);
+    const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
+    if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);
+    if (slot < a.out_cap) {
+        uint64_t* w = reinterpret_cast<uint64_t*>(a.out + slot);
+        w[0] = qinfo;
+        w[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
+        w[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
     }
-    return r;
-}
-__device__ __forceinline__ uint64_t slot_of(const Reservation& r, uint32_t i) {
-    return i < r.rem ? r.old_base + r.old_used + i : r.new_base + (i - r.rem);
 }
 
 }  // namespace
@@ -181,9 +174,8 @@ merge_kernel(MergeArgs a) {
     const SmemLayout L = smem_layout(a.max_u16, a.max_kmers, a.n_buckets);
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);
     unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 8);
-    uint8_t* s_ham = smem + L.off_ham;
-    uint8_t* s_ham1 = smem + L.off_ham1;
-    uint32_t* s_minh = reinterpret_cast<uint32_t*>(smem + L.off_minh);
+    uint16_t* s_ham = reinterpret_cast<uint16_t*>(smem + L.off_ham);
+    uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + L.off_minh);
     uint16_t* s_frag = reinterpret_cast<uint16_t*>(smem + L.off_frag);
     int32_t* s_info = reinterpret_cast<int32_t*>(smem + L.off_info);
     uint64_t* s_vals = reinterpret_cast<uint64_t*>(smem + L.off_vals);
@@ -191,15 +183,13 @@ merge_kernel(MergeArgs a) {
     uint16_t* s_bstart = reinterpret_cast<uint16_t*>(smem + L.off_bstart);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 4096; i += kThreads) s_ham[i] = (uint8_t)(a.ham_pair[i] & 15u);
-    if (tid < 64) s_ham1[tid] = a.ham_single[tid];
+    for (int i = tid; i < 4096; i += kThreads) s_ham[i] = a.ham_pair[i];
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     unsigned parity = 0;
     const uint32_t n_items = a.item_off[a.n_tiles];
     const bool fmt2 = a.kmer_format == 2;
-    uint32_t* my_minh = s_minh + warp * 32;
-    OutChunk chunk;
+    uint32_t* my_queue = s_queue + warp * kQueue * 4;
     unsigned long long my_matches = 0;
 
     while (true) {
@@ -278,7 +268,92 @@ merge_kernel(MergeArgs a) {
             infos = a.info + tl.info_begin;
         }
 
-        // -- 3. stream the query slice, 32 queries per warp iteration
+        // -- 3. stream the query slice.  A warp looks up 32 queries per iteration and appends the ones that found
+        //       their amino-acid group ("hits") to its private queue; whenever 32 hits are queued they are processed
+        //       one hit per lane, so every lane of the candidate loops has work.
+        uint32_t q_head = 0, q_count = 0;
+        auto process_hits = [&](uint32_t m) {
+            const bool valid = (uint32_t)lane < m;
+            const uint4 rec = *reinterpret_cast<const uint4*>(my_queue + 4u * ((q_head + lane) & (kQueue - 1)));
+            uint32_t g0 = 0, n = 0, qoff = 0, qd = 0;
+            if (valid) { g0 = rec.x; n = rec.y; qoff = rec.z; qd = rec.w; }
+            q_head = (q_head + m) & (kQueue - 1);
+            q_count -= m;
+            // (a) oversized groups: the whole warp works on one hit at a time
+            uint32_t big = __ballot_sync(kFull, n > kLaneMaxCand);
+            while (big) {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                const uint32_t bg0 = __shfl_sync(kFull, g0, src), bn = __shfl_sync(kFull, n, src);
+                const uint32_t bqd = __shfl_sync(kFull, qd, src), bqoff = __shfl_sync(kFull, qoff, src);
+                uint32_t mn = 255u;
+                for (uint32_t c = lane; c < bn; c += 32) mn = min(mn, ham_sum(ham_lookup(s_ham, bqd, (uint32_t)vals[bg0 + c] & 0xFFFFFFu)));
+                mn = __reduce_min_sync(kFull, mn);
+                const uint32_t maxH = min(mn * 2u, 7u);
+                const uint64_t qinfo = a.q_info[it.q_begin + bqoff];
+                const bool plain = !((qi_frame(qinfo) < 3) ^ fmt2);
+                for (uint32_t cb = 0; cb < bn; cb += 32) {
+                    const uint32_t c = cb + lane;
+                    const uint32_t td = c < bn ? (uint32_t)vals[bg0 + c] & 0xFFFFFFu : 0u;
+                    const HamQuad hq = ham_lookup(s_ham, bqd, td);
+                    const uint32_t sum = ham_sum(hq);
+                    const bool sel = c < bn && sum <= maxH;
+                    const uint32_t bal = __ballot_sync(kFull, sel);
+                    if (!bal) continue;
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(a.out_count, (unsigned long long)__popc(bal));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (sel) emit_match(a, base + __popc(bal & ((1u << lane) - 1)), qinfo, infos[bg0 + c], td, ham_fields(hq, bqd, td, plain), sum);
+                    my_matches += __popc(bal);
+                }
+                if (lane == src) n = 0;
+            }
+            // (b) one hit per lane.  pass 1: minimum Hamming sum; the sums of the first 16 candidates are kept as nibbles
+            uint32_t nmax = n;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(kFull, nmax, o));
+            uint32_t mn = 255u;
+            uint64_t nib = 0;
+            for (uint32_t c = 0; c < nmax; ++c) {
+                if (c < n) {
+                    const uint32_t s = ham_sum(ham_lookup(s_ham, qd, (uint32_t)vals[g0 + c] & 0xFFFFFFu));
+                    mn = min(mn, s);
+                    if (c < 16) nib |= (uint64_t)min(s, 15u) << (4 * c);
+                }
+            }
+            const uint32_t maxH = min(mn * 2u, 7u);                                     // KmerMatcher.cpp:1136
+            // pass 2: how many survive
+            uint32_t cnt = 0;
+            for (uint32_t c = 0; c < nmax; ++c) {
+                if (c < n) {
+                    const uint32_t s = c < 16 ? (uint32_t)(nib >> (4 * c)) & 15u
+                                              : ham_sum(ham_lookup(s_ham, qd, (uint32_t)vals[g0 + c] & 0xFFFFFFu));
+                    cnt += s <= maxH;
+                }
+            }
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            if (total == 0) return;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.out_count, (unsigned long long)total);
+            base = __shfl_sync(kFull, base, 0) + (incl - cnt);
+            my_matches += total;
+            // pass 3: emit
+            uint64_t qinfo = 0;
+            bool plain = true;
+            if (cnt) { qinfo = a.q_info[it.q_begin + qoff]; plain = !((qi_frame(qinfo) < 3) ^ fmt2); }   // KmerMatcher.cpp:1140
+            for (uint32_t c = 0; c < nmax; ++c) {
+                if (c < n && cnt) {
+                    const uint32_t td = (uint32_t)vals[g0 + c] & 0xFFFFFFu;
+                    const HamQuad hq = ham_lookup(s_ham, qd, td);
+                    const uint32_t sum = ham_sum(hq);
+                    if (sum <= maxH) { emit_match(a, base, qinfo, infos[g0 + c], td, ham_fields(hq, qd, td, plain), sum); ++base; }
+                }
+            }
+        };
+
         for (uint64_t qb = it.q_begin + (uint64_t)warp * 32; qb < it.q_end; qb += kThreads) {
             const uint64_t qi = qb + lane;
             const bool active = qi < it.q_end;
@@ -303,92 +378,19 @@ merge_kernel(MergeArgs a) {
                     n = j - lo;
                 }
             }
-            // inclusive scan of the candidate counts: pair p of the warp belongs to the lane o with excl[o] <= p < incl[o]
-            uint32_t incl = n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const uint32_t total = __shfl_sync(kFull, incl, 31);
-            if (total == 0) continue;
-            const uint32_t excl = incl - n;
-            const uint32_t qd = (uint32_t)qv & 0xFFFFFFu;
-            const bool single = total <= 32;
-            if (!single) { my_minh[lane] = 255u; __syncwarp(); }
-            // sweep 1 (general path only): per-query minimum of the Hamming sums
-            if (!single) {
-                for (uint32_t pb = 0; pb < total; pb += 32) {
-                    const uint32_t p = pb + lane;
-                    const bool valid = p < total;
-                    uint32_t o = 0;
-#pragma unroll
-                    for (int s = 16; s > 0; s >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, (o + s - 1) & 31); if (v <= p) o += s; }
-                    o &= 31u;
-                    const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
-                    const uint32_t oq = __shfl_sync(kFull, qd, o);
-                    const uint32_t sum = valid ? ham_sum(s_ham, oq, (uint32_t)vals[valid ? j : 0] & 0xFFFFFFu) : 255u;
-                    const uint32_t grp = __match_any_sync(kFull, valid ? o : 32u + lane);
-                    const uint32_t mn = __reduce_min_sync(grp, sum);
-                    if (valid && (grp & ((1u << lane) - 1)) == 0) my_minh[o] = min(my_minh[o], mn);
-                    __syncwarp();
+            const uint32_t bal = __ballot_sync(kFull, n > 0);
+            if (bal) {
+                if (n > 0) {
+                    uint32_t* rec = my_queue + 4u * ((q_head + q_count + __popc(bal & ((1u << lane) - 1))) & (kQueue - 1));
+                    *reinterpret_cast<uint4*>(rec) = make_uint4(g0, n, (uint32_t)(qi - it.q_begin), (uint32_t)qv & 0xFFFFFFu);
                 }
-            }
-            // sweep 2: select, compact, emit
-            for (uint32_t pb = 0; pb < total; pb += 32) {
-                const uint32_t p = pb + lane;
-                const bool valid = p < total;
-                uint32_t o = 0;
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, (o + s - 1) & 31); if (v <= p) o += s; }
-                o &= 31u;
-                const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
-                const uint32_t oq = __shfl_sync(kFull, qd, o);
-                const uint32_t td = valid ? (uint32_t)vals[j] & 0xFFFFFFu : 0u;
-                const uint32_t sum = valid ? ham_sum(s_ham, oq, td) : 255u;
-                uint32_t mn;
-                if (single) {
-                    const uint32_t grp = __match_any_sync(kFull, valid ? o : 32u + lane);
-                    mn = __reduce_min_sync(grp, sum);
-                } else {
-                    mn = my_minh[o];
-                }
-                const uint32_t maxH = min(mn * 2u, 7u);                               // KmerMatcher.cpp:1136
-                const bool sel = valid && sum <= maxH;
-                const uint32_t bal = __ballot_sync(kFull, sel);
-                const uint32_t cnt = __popc(bal);
-                if (cnt == 0) continue;
-                const Reservation rs = reserve(chunk, cnt, a.out_count, lane);
-                if (sel) {
-                    const uint64_t qinfo = a.q_info[qb + o];
-                    const uint32_t frame = qi_frame(qinfo);
-                    const bool plain = !((frame < 3) ^ fmt2);                          // KmerMatcher.cpp:1140
-                    const uint32_t field = ham_fields(s_ham1, oq, td, plain);
-                    const int32_t taxid = (int32_t)((uint32_t)infos[j] & a.info_mask);
-                    const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
-                    if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);        // Q2
-                    const uint64_t slot = slot_of(rs, __popc(bal & ((1u << lane) - 1)));
-                    if (slot < a.out_cap) {
-                        uint64_t* w = reinterpret_cast<uint64_t*>(a.out + slot);
-                        w[0] = qinfo;
-                        w[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
-                        w[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
-                    }
-                }
-                my_matches += cnt;
+                q_count += __popc(bal);
+                __syncwarp();
+                if (q_count >= 32) { process_hits(32); __syncwarp(); }
             }
         }
+        if (q_count) { process_hits(q_count); __syncwarp(); }
         __syncthreads();
-    }
-    // blank out the unused tail of the warp's last chunk (seqID 0 == not a match)
-    if (chunk.used < kOutChunk) {
-        for (uint32_t w = chunk.used + lane; w < kOutChunk; w += 32) {
-            const uint64_t slot = chunk.base + w;
-            if (slot < a.out_cap) {
-                uint64_t* o = reinterpret_cast<uint64_t*>(a.out + slot);
-                o[0] = 0; o[1] = 0; o[2] = 0;
-            }
-        }
     }
     if (lane == 0 && my_matches) atomicAdd(a.out_count + 1, my_matches);
 }

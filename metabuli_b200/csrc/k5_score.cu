@@ -6,7 +6,7 @@
 
 namespace mbl {
 
-__global__ void __launch_bounds__(128) score_kernel(ScoreArgs a) {
+__global__ void __launch_bounds__(128, 4) score_kernel(ScoreArgs a) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.n_reads) return;
     score_read(a, r);

@@ -32,6 +32,7 @@ struct DeviceTaxonomy {             // reference arrays as stored in taxonomyDB
 struct ScoreParams {
     float min_score, min_sp_score, tie_ratio;
     int min_cons_cnt, min_cons_cnt_euk, accession_level, denominator, kmer_format;
+    int force_scratch_dp;      // tests only: skip the register-resident DP fast path
 };
 
 // K1

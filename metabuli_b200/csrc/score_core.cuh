@@ -156,7 +156,99 @@ MBL_HD int left_part_ham(uint32_t reh, int range) { int s = 0; for (int i = 0; i
 
 // ---- getMatchPaths for one (species, frame) group [gs, ge) (Taxonomer.cpp:487-648) ----------------------
 // Emitted paths are appended at a.p_*[pbase + np].
+//
+// The DP only ever looks one position back, so when no position of the group holds more than kDpWidth
+// matches (the common case: one or two target k-mers per query position and species) the state of the
+// "current" and "next" position lives in registers and nothing but the emitted paths touches HBM.
+// Groups with a wider position fall back to the scratch-array version below (same arithmetic, same order).
+constexpr int kDpWidth = 4;
+
+struct DpCell { float score; int32_t start, ham, depth; uint32_t smatch, idx, dna; bool conn; };
+
+MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge, int min_depth, uint64_t pbase, uint32_t& np) {
+    const mbl_match_rec* ml = a.matches;
+    // pre-scan: widest position of the group
+    {
+        uint32_t run = 1;
+        for (uint64_t i = gs + 1; i < ge; ++i) {
+            run = qi_pos(ml[i].qinfo) == qi_pos(ml[i - 1].qinfo) ? run + 1 : 1;
+            if (run > (uint32_t)kDpWidth) return false;
+        }
+    }
+    const bool forward = qi_frame(ml[gs].qinfo) < 3;
+    const bool fmt2 = a.par.kmer_format == 2;
+    DpCell cur[kDpWidth], nxt[kDpWidth];
+    int ncur = 0, nnxt = 0;
+    auto load = [&](DpCell& c, uint64_t i) {
+        c.score = match_score(ml[i].right_end_hamming);
+        c.start = (int32_t)qi_pos(ml[i].qinfo);
+        c.ham = ml[i].hamming; c.depth = 1; c.smatch = (uint32_t)(i - gs); c.idx = (uint32_t)(i - gs);
+        c.dna = ml[i].dna_encoding; c.conn = false;
+    };
+    auto push = [&](const DpCell& c) {
+        const uint64_t o = pbase + np++;
+        const uint64_t i = gs + c.idx;
+        a.p_start[o] = c.start;
+        a.p_end[o] = (int32_t)qi_pos(ml[i].qinfo) + 23;
+        a.p_score[o] = c.score; a.p_ham[o] = c.ham; a.p_depth[o] = c.depth;
+        a.p_smatch[o] = (uint32_t)(gs - pbase) + c.smatch;
+        a.p_ematch[o] = (uint32_t)(i - pbase);
+    };
+    uint64_t i = gs;
+    uint64_t curPos = qi_pos(ml[gs].qinfo);
+    while (i < ge && qi_pos(ml[i].qinfo) == curPos) { load(cur[ncur++], i); ++i; }
+    while (i < ge) {
+        const uint32_t nextPos = qi_pos(ml[i].qinfo);
+        nnxt = 0;
+        while (i < ge && qi_pos(ml[i].qinfo) == nextPos) { load(nxt[nnxt++], i); ++i; }
+        const int shift = (int)(((uint64_t)nextPos - curPos) / 3);
+        if (shift == 1) {
+            const uint32_t lowMask = (1u << 21) - 1;
+#pragma unroll
+            for (int nx = 0; nx < kDpWidth; ++nx) {
+                if (nx >= nnxt) break;
+                const int h = ml[gs + nxt[nx].idx].right_end_hamming & 3;
+                const float inc = codon_score(h);
+                int best = -1;
+                float bestScore = 0.f;
+#pragma unroll
+                for (int cu = 0; cu < kDpWidth; ++cu) {
+                    if (cu >= ncur) break;
+                    const uint32_t m1 = forward ? cur[cu].dna : nxt[nx].dna, m2 = forward ? nxt[nx].dna : cur[cu].dna;
+                    const bool cons = fmt2 ? ((m1 & lowMask) == (m2 >> 3)) : ((m1 >> 3) == (m2 & lowMask));
+                    if (cons) {
+                        cur[cu].conn = true;
+                        if (cur[cu].score > bestScore) { best = cu; bestScore = cur[cu].score; }
+                    }
+                }
+                if (best >= 0) {
+#pragma unroll
+                    for (int cu = 0; cu < kDpWidth; ++cu)
+                        if (cu == best) {
+                            nxt[nx].start = cur[cu].start; nxt[nx].score = cur[cu].score + inc; nxt[nx].ham = cur[cu].ham + h;
+                            nxt[nx].depth = cur[cu].depth + 1; nxt[nx].smatch = cur[cu].smatch;
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int cu = 0; cu < kDpWidth; ++cu)
+            if (cu < ncur && !cur[cu].conn && cur[cu].depth >= min_depth) push(cur[cu]);
+        if (i == ge) {
+#pragma unroll
+            for (int nx = 0; nx < kDpWidth; ++nx)
+                if (nx < nnxt && nxt[nx].depth >= min_depth) push(nxt[nx]);
+        }
+#pragma unroll
+        for (int k = 0; k < kDpWidth; ++k) cur[k] = nxt[k];
+        ncur = nnxt;
+        curPos = nextPos;
+    }
+    return true;
+}
+
 MBL_HD void score_frame_group(const ScoreArgs& a, uint64_t gs, uint64_t ge, int min_depth, uint64_t pbase, uint32_t& np) {
+    if (!a.par.force_scratch_dp && score_frame_group_fast(a, gs, ge, min_depth, pbase, np)) return;
     const mbl_match_rec* ml = a.matches;
     const bool forward = qi_frame(ml[gs].qinfo) < 3;
     const bool fmt2 = a.par.kmer_format == 2;

@@ -25,7 +25,7 @@ void ht_sort_paths(const float* score, const int* ham, const int* start, int n, 
 
 int ht_score(const mbl_match_rec* matches, size_t n_match, uint32_t n_reads, const int32_t* cov1, const int32_t* cov2,
              const mbl_taxonomy* tx, int seq_mode, float min_score, float min_sp_score, float tie_ratio, int min_cons, int min_cons_euk,
-             int accession_level, int kmer_format, mbl_read_result* results, int32_t* pairs_out, size_t cap_pairs, size_t* used_pairs) {
+             int accession_level, int kmer_format, int force_scratch_dp, mbl_read_result* results, int32_t* pairs_out, size_t cap_pairs, size_t* used_pairs) {
     std::vector<uint64_t> seg_b(n_reads, 0), seg_e(n_reads, 0);
     for (size_t i = 0; i < n_match; ++i) {
         uint32_t s = qi_seq(matches[i].qinfo);
@@ -53,7 +53,7 @@ int ht_score(const mbl_match_rec* matches, size_t n_match, uint32_t n_reads, con
     a.tax.max_nodes = (uint32_t)tx->max_nodes;
     a.par.min_score = min_score; a.par.min_sp_score = min_sp_score; a.par.tie_ratio = tie_ratio; a.par.min_cons_cnt = min_cons;
     a.par.min_cons_cnt_euk = min_cons_euk; a.par.accession_level = accession_level;
-    a.par.denominator = (seq_mode == 1 || seq_mode == 2) ? 100 : 1000; a.par.kmer_format = kmer_format;
+    a.par.denominator = (seq_mode == 1 || seq_mode == 2) ? 100 : 1000; a.par.kmer_format = kmer_format; a.par.force_scratch_dp = force_scratch_dp;
     a.l_score = l_score.data(); a.l_start = l_start.data(); a.l_ham = l_ham.data(); a.l_depth = l_depth.data();
     a.l_smatch = l_smatch.data(); a.l_conn = l_conn.data(); a.p_start = p_start.data(); a.p_end = p_end.data();
     a.p_score = p_score.data(); a.p_ham = p_ham.data(); a.p_depth = p_depth.data(); a.p_smatch = p_smatch.data();
