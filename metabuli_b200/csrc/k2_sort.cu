@@ -123,7 +123,23 @@ __global__ void segment_kernel(const mbl_match_rec* __restrict__ m, size_t n, ui
     if (i + 1 == n || qi_seq(m[i + 1].qinfo) != s) seg_end[s - 1] = i + 1;
 }
 
+// first match of every chunk of `chunk_reads` reads: bounds[k] = lower_bound(seqID >= k*chunk_reads + 1)
+__global__ void seq_bounds_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t chunk_reads, uint32_t n_chunks,
+                                  uint64_t* __restrict__ bounds) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n_chunks) return;
+    if (k == n_chunks) { bounds[k] = n; return; }
+    const uint64_t want = (uint64_t)k * chunk_reads + 1;
+    size_t lo = 0, hi = n;
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if ((uint64_t)qi_seq(m[mid].qinfo) < want) lo = mid + 1; else hi = mid; }
+    bounds[k] = lo;
+}
+
 }  // namespace
+
+void launch_seq_bounds(const mbl_match_rec* sorted, size_t n, uint32_t chunk_reads, uint32_t n_chunks, uint64_t* bounds, cudaStream_t st) {
+    seq_bounds_kernel<<<(n_chunks + 1 + 127) / 128, 128, 0, st>>>(sorted, n, chunk_reads, n_chunks, bounds);
+}
 
 size_t sort_matches_temp_bytes(size_t n) {
     size_t bytes = 0;

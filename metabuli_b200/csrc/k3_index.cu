@@ -83,13 +83,13 @@ __global__ void tile_fill_kernel(const uint64_t* __restrict__ cand, const uint32
     t.info_begin = b_kidx[c];
     t.base_value = b_base[c];
     t.first_aa = b_aa[c];
-    t.n_u16 = 0; t.n_kmers = 0; t.jumbo_off = kNone;
+    t.n_u16 = 0; t.n_kmers = 0; t.jumbo_off = kNone; t.last_value = 0;
     tiles[rank[m]] = t;
 }
 
 // extents from the successor; Q1: the numerically last k-mer of the DB is never a candidate
 // (KmerMatcher.cpp:378-380), so the directory simply does not contain it.
-__global__ void tile_extent_kernel(Tile* __restrict__ tiles, uint64_t n_tiles, uint64_t n_u16, uint64_t n_kmers_eff,
+__global__ void tile_extent_kernel(Tile* __restrict__ tiles, uint64_t n_tiles, uint64_t n_u16, uint64_t n_kmers_eff, uint64_t final_value,
                                    uint32_t max_u16, uint32_t max_kmers, unsigned long long* __restrict__ jumbo_kmers,
                                    unsigned long long* __restrict__ jumbo_tiles) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,6 +99,8 @@ __global__ void tile_extent_kernel(Tile* __restrict__ tiles, uint64_t n_tiles, u
     if (kend > n_kmers_eff) kend = n_kmers_eff;
     uint64_t nk = kend > tiles[t].info_begin ? kend - tiles[t].info_begin : 0;
     uint64_t nu = dend - tiles[t].diff_begin;
+    // the k-mer before the next tile is this tile's last one (for the final tile: the last k-mer of the stream)
+    tiles[t].last_value = t + 1 < n_tiles ? tiles[t + 1].base_value : final_value;
     tiles[t].n_u16 = (uint32_t)min(nu, (uint64_t)0xFFFFFFFFu);
     tiles[t].n_kmers = (uint32_t)min(nk, (uint64_t)0xFFFFFFFFu);
     if (nu > max_u16 || nk > max_kmers) {
@@ -171,10 +173,12 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
     tile_flag_kernel<<<(unsigned)((n_grid + 255) / 256), 256, 0, st>>>(cand, n_grid, flag);
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, rank, n_grid + 1, st);
     uint32_t n_tiles32 = 0;
-    uint64_t last_k = 0, last_c = 0;
+    uint64_t last_k = 0, last_c = 0, last_v = 0, last_s = 0;
     MBL_CUDA(cudaMemcpyAsync(&n_tiles32, rank + n_grid, 4, cudaMemcpyDeviceToHost, st));
     MBL_CUDA(cudaMemcpyAsync(&last_k, dir.cell_k + (n_cells - 1), 8, cudaMemcpyDeviceToHost, st));
     MBL_CUDA(cudaMemcpyAsync(&last_c, cell_cnt + (n_cells - 1), 8, cudaMemcpyDeviceToHost, st));
+    MBL_CUDA(cudaMemcpyAsync(&last_v, dir.cell_v + (n_cells - 1), 8, cudaMemcpyDeviceToHost, st));
+    MBL_CUDA(cudaMemcpyAsync(&last_s, cell_sum + (n_cells - 1), 8, cudaMemcpyDeviceToHost, st));
     MBL_CUDA(cudaStreamSynchronize(st));
     dir.n_kmers_decoded = last_k + last_c;
     dir.n_tiles = n_tiles32;
@@ -184,7 +188,7 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
     unsigned long long* d_cnt;
     MBL_CUDA(cudaMalloc(&d_cnt, 16));
     MBL_CUDA(cudaMemsetAsync(d_cnt, 0, 16, st));
-    tile_extent_kernel<<<(unsigned)((dir.n_tiles + 255) / 256), 256, 0, st>>>(dir.tiles, dir.n_tiles, n_u16, n_kmers_eff,
+    tile_extent_kernel<<<(unsigned)((dir.n_tiles + 255) / 256), 256, 0, st>>>(dir.tiles, dir.n_tiles, n_u16, n_kmers_eff, last_v + last_s,
                                                                             dir.max_u16, dir.max_kmers, d_cnt, d_cnt + 1);
     unsigned long long h_cnt[2];
     MBL_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));

@@ -11,14 +11,14 @@
 //   1. stage   two 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) bring the tile's fragments
 //              and taxids into shared memory;
 //   2. decode  eight warps decode the tile's cells independently from their checkpoints
-//              (delta_decode.cuh) into a sorted value array; a second sweep records, per amino-acid group
-//              start, where the group ends, and fills a bucket table (monotone hash of the amino-acid part)
-//              so a query finds its group in O(1);
-//   3. match   a warp takes 32 consecutive queries: bucket lookup -> (group start, size) per lane, then the
-//              (query, candidate) PAIRS of the whole warp are spread evenly over the lanes (shuffle search
-//              over the inclusive scan), Hamming sums come from a 4 KiB two-codon table, per-query minima
-//              from match_any + reduce_min, and the surviving pairs are ballot-compacted into the warp's
-//              private output chunk, so Match records leave as coalesced 24-byte rows.
+//              (delta_decode.cuh) into a sorted value array; every k-mer that starts an amino-acid group is
+//              entered into a tagged bucket table (bucket = monotone hash of the 40-bit amino-acid part, entry =
+//              {group start, 18-bit tag, collision flag}) so a query misses in ~12 instructions and one LDS;
+//   3. match   a warp looks up 32 queries per iteration and queues the hits; 32 queued hits are processed one
+//              per lane: a scan of the group finds its size and whether the query's exact value is present
+//              (Hamming sum 0 <=> identical DNA part, so the survivors are exactly the equal values and no
+//              table lookups are needed); only the remaining hits run the min / select Hamming passes over a
+//              8 KiB two-codon table.  Output slots come from one atomicAdd per 32 hits.
 // HBM traffic per launch = index once + 8 B per query (+ 8 B qinfo per matching query) + 24 B per match.
 #include "delta_decode.cuh"
 #include "kernels.cuh"
@@ -33,23 +33,31 @@ constexpr uint32_t kQueue = 64;              // per-warp hit queue (power of two
 constexpr uint32_t kLaneMaxCand = 48;        // groups larger than this are worked on by the whole warp
 constexpr uint64_t kNone = ~0ull;
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kEmpty = 0xffffffffu;     // bucket table: no group hashes here
+
+// bucket table entry = group start (13 bits) << 19 | tag (18 bits) << 1 | collision flag.  The tag is the top 18
+// bits of what the bucket function shifts out, so tag + bucket identify the amino-acid part (exactly when
+// shift <= 18; otherwise the hit is verified against the value array anyway).
+__device__ __forceinline__ uint32_t bucket_tag(uint64_t d, uint32_t shift) {
+    const uint64_t r = d & ((1ull << shift) - 1ull);
+    return (uint32_t)(shift > 18 ? r >> (shift - 18) : r) & 0x3FFFFu;
+}
 
 // dynamic shared memory layout (sizes depend on the tile geometry chosen at load time)
 struct SmemLayout {
-    uint32_t off_ham, off_ham1, off_minh, off_frag, off_info, off_vals, off_gend, off_bstart, total;
+    uint32_t off_ham, off_ham1, off_minh, off_frag, off_info, off_vals, off_tab, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets) {
     SmemLayout l;
     uint32_t o = 16;                                   // mbarrier + item slot
     l.off_ham = o;   o += 8192;                        // two-codon table: sum | plain nibble | reversed nibble (u16)
     l.off_ham1 = o;  o += 0;
-    l.off_minh = o;  o += kWarps * kQueue * 16;        // per-warp hit queues {g0, n, query offset, query dna}
+    l.off_minh = o;  o += kWarps * kQueue * 12;        // per-warp hit queues {group start, query dna, query offset}
     l.off_frag = o;  o += (max_u16 + 16) * 2;
     l.off_info = o;  o += (max_kmers + 8) * 4;
     o = (o + 15) & ~15u;
     l.off_vals = o;  o += max_kmers * 8;
-    l.off_gend = o;  o += (max_kmers + 8) * 2;
-    l.off_bstart = o; o += (n_buckets + 8) * 2;
+    l.off_tab = o;   o += n_buckets * 4;               // tagged bucket table
     l.total = (o + 15) & ~15u;
     return l;
 }
@@ -179,8 +187,7 @@ merge_kernel(MergeArgs a) {
     uint16_t* s_frag = reinterpret_cast<uint16_t*>(smem + L.off_frag);
     int32_t* s_info = reinterpret_cast<int32_t*>(smem + L.off_info);
     uint64_t* s_vals = reinterpret_cast<uint64_t*>(smem + L.off_vals);
-    uint16_t* s_gend = reinterpret_cast<uint16_t*>(smem + L.off_gend);
-    uint16_t* s_bstart = reinterpret_cast<uint16_t*>(smem + L.off_bstart);
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + L.off_tab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 4096; i += kThreads) s_ham[i] = a.ham_pair[i];
@@ -189,7 +196,7 @@ merge_kernel(MergeArgs a) {
     unsigned parity = 0;
     const uint32_t n_items = a.item_off[a.n_tiles];
     const bool fmt2 = a.kmer_format == 2;
-    uint32_t* my_queue = s_queue + warp * kQueue * 4;
+    uint32_t* my_queue = s_queue + warp * kQueue * 3;
     unsigned long long my_matches = 0;
 
     while (true) {
@@ -203,7 +210,7 @@ merge_kernel(MergeArgs a) {
         const bool jumbo = tl.jumbo_off != kNone;
         const uint64_t* vals;
         const int32_t* infos;
-        uint64_t base40 = 0, last40 = 0;
+        uint64_t base40 = 0, span40 = 0;
         uint32_t shift = 0;
         if (!jumbo) {
             // -- 1. stage the tile: fragments + taxids, two bulk copies on one mbarrier
@@ -217,9 +224,19 @@ merge_kernel(MergeArgs a) {
                 tma_load_1d(s_frag, a.diff + a0, fb, mbar);
                 if (ib) tma_load_1d(s_info, a.info + i0, ib, mbar);
             }
+            // bucket geometry from the directory (first / last value of the tile); clear the table while the copies fly
+            base40 = tl.first_aa >> 24;
+            span40 = (tl.last_value >> 24) - base40;
+            {
+                const int bits = 64 - __clzll(span40 | 1ull);
+                const int lb = 31 - __clz(a.n_buckets);
+                shift = bits > lb ? (uint32_t)(bits - lb) : 0u;
+            }
+            for (uint32_t x = tid; x < a.n_buckets; x += kThreads) s_tab[x] = kEmpty;
+            __syncthreads();
             mbar_wait(mbar, parity);
             parity ^= 1u;
-            // -- 2a. decode: one warp per checkpoint cell
+            // -- 2. decode: one warp per checkpoint cell; group starts go into the tagged bucket table
             const uint64_t c0 = d0 / kCellU16, c1 = (d1 + kCellU16 - 1) / kCellU16;
             for (uint64_t c = c0 + warp; c < c1; c += kWarps) {
                 const uint64_t s_abs = max(c * (uint64_t)kCellU16, d0), e_abs = min((c + 1) * (uint64_t)kCellU16, d1);
@@ -227,38 +244,22 @@ merge_kernel(MergeArgs a) {
                 if (s_abs == d0) { v = tl.base_value; k = tl.info_begin; }
                 else { v = a.cell_v[c]; k = a.cell_k[c]; }
                 const uint64_t kb = tl.info_begin;
+                const uint64_t b40 = base40;
+                const uint32_t sh = shift;
                 warp_decode(s_frag, (long long)(d0 - a0), (long long)(s_abs - a0), (long long)(e_abs - a0), v, k,
-                            [&](uint64_t kk, uint64_t val, uint64_t, long long) {
-                                uint64_t rel = kk - kb;
-                                if (rel < nk) s_vals[rel] = val;
+                            [&](uint64_t kk, uint64_t val, uint64_t delta, long long) {
+                                const uint64_t rel = kk - kb;
+                                if (rel >= nk) return;
+                                s_vals[rel] = val;
+                                const uint64_t aa = val >> 24;
+                                if (rel == 0 || ((val - delta) >> 24) != aa) {
+                                    const uint64_t d = aa - b40;
+                                    const uint32_t bkt = (uint32_t)(d >> sh);
+                                    const uint32_t entry = ((uint32_t)rel << 19) | (bucket_tag(d, sh) << 1);
+                                    const uint32_t old = atomicMin(&s_tab[bkt], entry);
+                                    if (old != kEmpty) atomicOr(&s_tab[bkt], 1u);       // more than one group in this bucket
+                                }
                             });
-            }
-            __syncthreads();
-            // -- 2b. group ends + bucket table.  bucket(aa) = (aa40 - base40) >> shift is monotone, so bucket b's
-            //        k-mers are [bstart[b], bstart[b+1])
-            base40 = s_vals[0] >> 24;
-            last40 = s_vals[nk - 1] >> 24;
-            {
-                const uint64_t span = last40 - base40;
-                const int bits = 64 - __clzll(span | 1ull);
-                const int lb = 31 - __clz(a.n_buckets);
-                shift = bits > lb ? (uint32_t)(bits - lb) : 0u;
-            }
-            for (uint32_t i = tid; i < nk; i += kThreads) {
-                const uint64_t aa = s_vals[i] >> 24;
-                const bool start = i == 0 || (s_vals[i - 1] >> 24) != aa;
-                if (start) {
-                    uint32_t j = i + 1;
-                    while (j < nk && (s_vals[j] >> 24) == aa) ++j;
-                    s_gend[i] = (uint16_t)j;
-                    const uint32_t b = (uint32_t)((aa - base40) >> shift);
-                    const int32_t pb = i == 0 ? -1 : (int32_t)(((s_vals[i - 1] >> 24) - base40) >> shift);
-                    for (int32_t x = pb + 1; x <= (int32_t)b; ++x) s_bstart[x] = (uint16_t)i;
-                }
-            }
-            {
-                const uint32_t lastb = (uint32_t)((last40 - base40) >> shift);
-                for (uint32_t x = lastb + 1 + tid; x <= a.n_buckets; x += kThreads) s_bstart[x] = (uint16_t)nk;
             }
             __syncthreads();
             vals = s_vals;
@@ -274,18 +275,46 @@ merge_kernel(MergeArgs a) {
         uint32_t q_head = 0, q_count = 0;
         auto process_hits = [&](uint32_t m) {
             const bool valid = (uint32_t)lane < m;
-            const uint4 rec = *reinterpret_cast<const uint4*>(my_queue + 4u * ((q_head + lane) & (kQueue - 1)));
-            uint32_t g0 = 0, n = 0, qoff = 0, qd = 0;
-            if (valid) { g0 = rec.x; n = rec.y; qoff = rec.z; qd = rec.w; }
+            const uint32_t* rec = my_queue + 3u * ((q_head + lane) & (kQueue - 1));
+            const uint32_t g0 = valid ? rec[0] : 0u;                                // group start inside the tile
+            const uint32_t qd = valid ? rec[1] : 0u;                                // query DNA part
+            const uint32_t qoff = valid ? rec[2] : 0u;                              // query index relative to the item
             q_head = (q_head + m) & (kQueue - 1);
             q_count -= m;
-            // (a) oversized groups: the whole warp works on one hit at a time
-            uint32_t big = __ballot_sync(kFull, n > kLaneMaxCand);
+            const uint64_t aa = valid ? vals[g0] >> 24 : 0ull;
+            // pass A: size of the group (capped) and the run of candidates equal to the query value.  Candidates are
+            // sorted by value, Hamming sum 0 <=> identical DNA part (the distance table is 0 only on its diagonal),
+            // so when such a run exists min = 0, maxHamming = 0 and the survivors are exactly that run.
+            uint32_t n = 0, ex0 = 0, exn = 0;
+            bool open_end = valid;
+            for (uint32_t c = 0; c <= kLaneMaxCand; ++c) {
+                if (open_end) {
+                    const uint32_t j = g0 + c;
+                    const uint64_t v = j < nk ? vals[j] : ~0ull;
+                    if ((v >> 24) != aa) { open_end = false; }
+                    else {
+                        n = c + 1;
+                        if (((uint32_t)v & 0xFFFFFFu) == qd) { if (!exn) ex0 = j; ++exn; }
+                    }
+                }
+                if (!__any_sync(kFull, open_end)) break;
+            }
+            // (a) oversized groups (still open after the cap): the whole warp works on one hit at a time
+            uint32_t big = __ballot_sync(kFull, open_end);
             while (big) {
                 const int src = __ffs(big) - 1;
                 big &= big - 1;
-                const uint32_t bg0 = __shfl_sync(kFull, g0, src), bn = __shfl_sync(kFull, n, src);
+                const uint32_t bg0 = __shfl_sync(kFull, g0, src);
                 const uint32_t bqd = __shfl_sync(kFull, qd, src), bqoff = __shfl_sync(kFull, qoff, src);
+                const uint64_t baa = __shfl_sync(kFull, aa, src);
+                uint32_t bn = 0;                                  // group size, found cooperatively
+                for (uint32_t cb = 0;; cb += 32) {
+                    const uint32_t j = bg0 + cb + lane;
+                    const bool in = j < nk && (vals[j] >> 24) == baa;
+                    const uint32_t bal = __ballot_sync(kFull, in);
+                    bn += __popc(bal);
+                    if (bal != kFull) break;
+                }
                 uint32_t mn = 255u;
                 for (uint32_t c = lane; c < bn; c += 32) mn = min(mn, ham_sum(ham_lookup(s_ham, bqd, (uint32_t)vals[bg0 + c] & 0xFFFFFFu)));
                 mn = __reduce_min_sync(kFull, mn);
@@ -306,29 +335,29 @@ merge_kernel(MergeArgs a) {
                     if (sel) emit_match(a, base + __popc(bal & ((1u << lane) - 1)), qinfo, infos[bg0 + c], td, ham_fields(hq, bqd, td, plain), sum);
                     my_matches += __popc(bal);
                 }
-                if (lane == src) n = 0;
+                if (lane == src) { n = 0; exn = 0; }
             }
-            // (b) one hit per lane.  pass 1: minimum Hamming sum; the sums of the first 16 candidates are kept as nibbles
-            uint32_t nmax = n;
+            // (b) hits without an exact run: minimum Hamming sum, then the survivors (KmerMatcher.cpp:1117-1146)
+            const uint32_t ne = exn ? 0u : n;                     // candidates this lane still has to evaluate
+            uint32_t nmax = ne;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(kFull, nmax, o));
             uint32_t mn = 255u;
-            uint64_t nib = 0;
+            uint64_t nib = 0;                                     // sums of the first 16 candidates, 4 bits each
             for (uint32_t c = 0; c < nmax; ++c) {
-                if (c < n) {
-                    const uint32_t s = ham_sum(ham_lookup(s_ham, qd, (uint32_t)vals[g0 + c] & 0xFFFFFFu));
-                    mn = min(mn, s);
-                    if (c < 16) nib |= (uint64_t)min(s, 15u) << (4 * c);
+                if (c < ne) {
+                    const uint32_t sm = ham_sum(ham_lookup(s_ham, qd, (uint32_t)vals[g0 + c] & 0xFFFFFFu));
+                    mn = min(mn, sm);
+                    if (c < 16) nib |= (uint64_t)min(sm, 15u) << (4 * c);
                 }
             }
             const uint32_t maxH = min(mn * 2u, 7u);                                     // KmerMatcher.cpp:1136
-            // pass 2: how many survive
-            uint32_t cnt = 0;
+            uint32_t cnt = exn;
             for (uint32_t c = 0; c < nmax; ++c) {
-                if (c < n) {
-                    const uint32_t s = c < 16 ? (uint32_t)(nib >> (4 * c)) & 15u
-                                              : ham_sum(ham_lookup(s_ham, qd, (uint32_t)vals[g0 + c] & 0xFFFFFFu));
-                    cnt += s <= maxH;
+                if (c < ne) {
+                    const uint32_t sm = c < 16 ? (uint32_t)(nib >> (4 * c)) & 15u
+                                               : ham_sum(ham_lookup(s_ham, qd, (uint32_t)vals[g0 + c] & 0xFFFFFFu));
+                    cnt += sm <= maxH;
                 }
             }
             uint32_t incl = cnt;
@@ -340,12 +369,17 @@ merge_kernel(MergeArgs a) {
             if (lane == 0) base = atomicAdd(a.out_count, (unsigned long long)total);
             base = __shfl_sync(kFull, base, 0) + (incl - cnt);
             my_matches += total;
-            // pass 3: emit
             uint64_t qinfo = 0;
             bool plain = true;
             if (cnt) { qinfo = a.q_info[it.q_begin + qoff]; plain = !((qi_frame(qinfo) < 3) ^ fmt2); }   // KmerMatcher.cpp:1140
+            // exact runs: Hamming 0, all per-codon fields 0
+            uint32_t xmax = exn;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) xmax = max(xmax, __shfl_xor_sync(kFull, xmax, o));
+            for (uint32_t c = 0; c < xmax; ++c)
+                if (c < exn) { emit_match(a, base, qinfo, infos[ex0 + c], qd, 0u, 0u); ++base; }
             for (uint32_t c = 0; c < nmax; ++c) {
-                if (c < n && cnt) {
+                if (c < ne && cnt) {
                     const uint32_t td = (uint32_t)vals[g0 + c] & 0xFFFFFFu;
                     const HamQuad hq = ham_lookup(s_ham, qd, td);
                     const uint32_t sum = ham_sum(hq);
@@ -359,30 +393,34 @@ merge_kernel(MergeArgs a) {
             const bool active = qi < it.q_end;
             const uint64_t qv = active ? ld_stream_u64(a.q_value + qi) : kBlank;
             const uint64_t q40 = qv >> 24;
-            uint32_t g0 = 0, n = 0;
+            uint32_t g0 = 0;
+            bool hit = false;
             if (!jumbo) {
-                if (active && q40 >= base40 && q40 <= last40) {
-                    const uint32_t b = (uint32_t)((q40 - base40) >> shift);
-                    uint32_t j = s_bstart[b];
-                    const uint32_t e = s_bstart[b + 1];
-                    while (j < e && (vals[j] >> 24) < q40) j = s_gend[j];      // hop from group start to group start
-                    if (j < e && (vals[j] >> 24) == q40) { g0 = j; n = s_gend[j] - j; }
+                const uint64_t d = q40 - base40;                 // wraps to a huge value when q40 < base40
+                if (d <= span40) {
+                    const uint32_t bkt = (uint32_t)(d >> shift);
+                    const uint32_t e = s_tab[bkt];
+                    if (e != kEmpty) {
+                        const uint32_t st = e >> 19;
+                        if (((e >> 1) & 0x3FFFFu) == bucket_tag(d, shift) && (vals[st] >> 24) == q40) { g0 = st; hit = true; }
+                        else if (e & 1u) {                      // several groups share the bucket: walk it
+                            for (uint32_t j = st + 1; j < nk; ++j) {
+                                const uint64_t v40 = vals[j] >> 24;
+                                if (v40 >= q40) { if (v40 == q40) { g0 = j; hit = true; } break; }
+                            }
+                        }
+                    }
                 }
             } else if (active) {
                 uint32_t lo = 0, hi = nk;
                 while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((vals[mid] >> 24) < q40) lo = mid + 1; else hi = mid; }
-                if (lo < nk && (vals[lo] >> 24) == q40) {
-                    g0 = lo;
-                    uint32_t j = lo + 1;
-                    while (j < nk && (vals[j] >> 24) == q40) ++j;
-                    n = j - lo;
-                }
+                if (lo < nk && (vals[lo] >> 24) == q40) { g0 = lo; hit = true; }
             }
-            const uint32_t bal = __ballot_sync(kFull, n > 0);
+            const uint32_t bal = __ballot_sync(kFull, hit);
             if (bal) {
-                if (n > 0) {
-                    uint32_t* rec = my_queue + 4u * ((q_head + q_count + __popc(bal & ((1u << lane) - 1))) & (kQueue - 1));
-                    *reinterpret_cast<uint4*>(rec) = make_uint4(g0, n, (uint32_t)(qi - it.q_begin), (uint32_t)qv & 0xFFFFFFu);
+                if (hit) {
+                    uint32_t* rec = my_queue + 3u * ((q_head + q_count + __popc(bal & ((1u << lane) - 1))) & (kQueue - 1));
+                    rec[0] = g0; rec[1] = (uint32_t)qv & 0xFFFFFFu; rec[2] = (uint32_t)(qi - it.q_begin);
                 }
                 q_count += __popc(bal);
                 __syncwarp();

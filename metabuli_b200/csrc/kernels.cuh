@@ -55,6 +55,7 @@ size_t sort_matches_temp_bytes(size_t n);
 void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
                   int32_t max_taxid, uint32_t max_pos, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b,
                   cudaStream_t st);
+void launch_seq_bounds(const mbl_match_rec* sorted, size_t n, uint32_t chunk_reads, uint32_t n_chunks, uint64_t* bounds, cudaStream_t st);
 void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, uint64_t* seg_begin, uint64_t* seg_end, cudaStream_t st);
 
 // K3 directory (load time)
@@ -103,6 +104,7 @@ size_t merge_smem_bytes(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets
 struct ScoreArgs {
     const mbl_match_rec* matches;       // sorted
     uint64_t n_match;
+    uint32_t read_begin;            // reads [read_begin, read_begin + n_reads) of the sub-batch are scored by one launch
     uint32_t n_reads;
     const uint64_t* seg_begin;      // per read (seqID - 1)
     const uint64_t* seg_end;

@@ -33,6 +33,7 @@ struct Buf {
 };
 
 struct SubBatch { uint32_t r0, r1; uint64_t slots, quots; uint32_t max_pos; };
+constexpr uint32_t kScoreChunkReads = 1u << 20;   // reads scored per launch (bounds the per-match scratch)
 
 }  // namespace
 
@@ -64,6 +65,7 @@ struct mbl_ctx {
     // workspace
     Buf cov1, cov2, w1, w2, slots, slot_off, quot_cnt, quot_off, seg_b, seg_e, res_sub, tax_len, tax_off;
     Buf val_a, val_b, qi_a, qi_b, cub_tmp;
+    Buf arena, chunk_bounds;     // phase 1: k-mer keys/payloads (32 B per slot); phase 2: match sort buffers
     Buf m_raw, m_sorted, key_a, key_b, idx_a, idx_b;
     Buf l_score, l_start, l_ham, l_depth, l_smatch, l_conn, p_start, p_end, p_score, p_ham, p_depth, p_smatch, p_ematch,
         c_start, c_end, s_score;
@@ -156,16 +158,19 @@ void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
 uint64_t slots_budget(mbl_ctx* c) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    // bytes the workspace currently holds can be reused
+    // what the workspace already holds is reusable
     size_t held = 0;
-    for (Buf* b : {&c->val_a, &c->val_b, &c->qi_a, &c->qi_b, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b,
-                   &c->l_score, &c->l_start, &c->l_ham, &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score,
-                   &c->p_ham, &c->p_depth, &c->p_smatch, &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->cub_tmp})
+    for (Buf* b : {&c->arena, &c->m_raw, &c->l_score, &c->l_start, &c->l_ham, &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end,
+                   &c->p_score, &c->p_ham, &c->p_depth, &c->p_smatch, &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->cub_tmp,
+                   &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw, &c->seg_b, &c->seg_e, &c->res_sub})
         held += b->cap;
-    double budget = 0.80 * (double)(free_b + held);
-    // ~32 B per slot (keys + payload, double buffered) + ~0.6 matches per slot x 140 B + sort scratch
-    uint64_t s = (uint64_t)(budget / 150.0);
-    s = std::min<uint64_t>(s, 1ull << 31);
+    // per slot: 32 B keys+payloads (arena; reused by the match sort: 48 B per match) + 24 B per raw match + ~4 B per-read tables;
+    // fixed: scoring scratch of one chunk + results
+    const double r = std::max(0.5, c->match_ratio * 1.3);
+    const double per_slot = std::max(32.0, 48.0 * r) + 24.0 * r + 4.0;
+    double budget = 0.88 * (double)(free_b + held) - 10.0e9;
+    uint64_t s = budget > 0 ? (uint64_t)(budget / per_slot) : 0;
+    s = std::min<uint64_t>(s, (uint64_t)(3.9e9 / r));            // 32-bit match permutation
     s = std::max<uint64_t>(s, 1ull << 16);
     return s;
 }
@@ -175,6 +180,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     cudaStream_t st = c->st;
     const uint32_t n = sb.r1 - sb.r0;
     const uint64_t S = sb.slots;
+    const uint64_t S8 = (S + 31) & ~31ull;
     const uint8_t* bases1 = (const uint8_t*)c->bases1.p;
     const uint8_t* bases2 = c->paired ? (const uint8_t*)c->bases2.p : nullptr;
     const uint64_t* off1 = (const uint64_t*)c->off1.p + sb.r0;
@@ -197,7 +203,9 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         void* tmp = c->cub_tmp.get<uint8_t>(std::max(scan_bytes, sortk_bytes));
         exclusive_sum_u64(tmp, c->cub_tmp.cap, slots, slot_off, n + 1, st);
         exclusive_sum_u32(tmp, c->cub_tmp.cap, quot_cnt, quot_off, n + 1, st);
-        uint64_t *va = c->val_a.get<uint64_t>(S), *qa = c->qi_a.get<uint64_t>(S);
+        // phase-1 layout of the arena: value A | qinfo A | value B | qinfo B, S8 entries each
+        uint64_t* ar = c->arena.get<uint64_t>(4 * S8 + 64);
+        uint64_t *va = ar, *qa = ar + S8;
         launch_extract(c->cfg.kmer_format, bases1, off1, bases2, off2, n, cov1, w1, w2, slot_off, c->d_base_code, c->d_codon,
                        va, qa, counters, c->sm_count, st);
         c->stats.kernel_launches += 2;
@@ -207,8 +215,8 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     uint64_t *qv = nullptr, *qi = nullptr;
     {
         StageTimer t(c, MBL_STAGE_SORT);
-        uint64_t *va = (uint64_t*)c->val_a.p, *qa = (uint64_t*)c->qi_a.p;
-        uint64_t *vb = c->val_b.get<uint64_t>(S), *qb = c->qi_b.get<uint64_t>(S);
+        uint64_t* ar = (uint64_t*)c->arena.p;
+        uint64_t *va = ar, *qa = ar + S8, *vb = ar + 2 * S8, *qb = ar + 3 * S8;
         int in_b = 0;
         if (S) sort_kmers(c->cub_tmp.p, c->cub_tmp.cap, va, vb, qa, qb, S, in_b, st);
         qv = in_b ? vb : va;
@@ -280,17 +288,22 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     if (reserved >= (1ull << 32)) return fail(c, MBL_E_UNSUPPORTED, "more than 2^32 matches in one sub-batch");
 
     // ---- K4 ------------------------------------------------------------------------------------------
+    // the k-mer buffers are dead now: phase-2 layout of the arena = sorted matches | key A | key B | idx A | idx B
     const uint64_t M = reserved;
-    mbl_match_rec* sorted = c->m_sorted.get<mbl_match_rec>(M + 1);
+    const uint64_t M8 = (M + 32) & ~31ull;
+    uint8_t* ar2 = c->arena.get<uint8_t>(48 * M8 + 256);
+    mbl_match_rec* sorted = reinterpret_cast<mbl_match_rec*>(ar2);
+    uint64_t* key_a = reinterpret_cast<uint64_t*>(ar2 + 24 * M8);
+    uint64_t* key_b = key_a + M8;
+    uint32_t* idx_a = reinterpret_cast<uint32_t*>(key_b + M8);
+    uint32_t* idx_b = idx_a + M8;
     uint64_t *seg_b = c->seg_b.get<uint64_t>(n + 1), *seg_e = c->seg_e.get<uint64_t>(n + 1);
     {
         StageTimer t(c, MBL_STAGE_MSORT);
         const size_t sm_bytes = sort_matches_temp_bytes(M);
         void* tmp = c->cub_tmp.get<uint8_t>(std::max(sm_bytes, std::max(scan_bytes, sortk_bytes)));
-        // note: cub_tmp may have been reallocated; the k-mer buffers are no longer needed
-        sort_matches(tmp, c->cub_tmp.cap, (const mbl_match_rec*)c->m_raw.p, sorted, M, n, c->tax.max_taxid, sb.max_pos,
-                     c->key_a.get<uint64_t>(M + 1), c->key_b.get<uint64_t>(M + 1), c->idx_a.get<uint32_t>(M + 1),
-                     c->idx_b.get<uint32_t>(M + 1), st);
+        sort_matches(tmp, c->cub_tmp.cap, (const mbl_match_rec*)c->m_raw.p, sorted, M, n, c->tax.max_taxid, sb.max_pos, key_a, key_b,
+                     idx_a, idx_b, st);
         launch_segments(sorted, M, n, seg_b, seg_e, st);
         c->stats.kernel_launches += M ? 4 : 0;
         t.stop();
@@ -299,7 +312,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     {
         StageTimer t(c, MBL_STAGE_SCORE);
         ScoreArgs sa{};
-        sa.matches = sorted; sa.n_match = M; sa.n_reads = n; sa.seg_begin = seg_b; sa.seg_end = seg_e;
+        sa.matches = sorted; sa.n_match = M; sa.seg_begin = seg_b; sa.seg_end = seg_e;
         sa.cov1 = cov1; sa.cov2 = cov2; sa.quot_off = quot_off;
         sa.tax = c->tax;
         sa.par.min_score = c->cfg.min_score; sa.par.min_sp_score = c->cfg.min_sp_score; sa.par.tie_ratio = c->cfg.tie_ratio;
@@ -307,17 +320,37 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         sa.par.accession_level = c->cfg.accession_level;
         sa.par.denominator = (c->cfg.seq_mode == 1 || c->cfg.seq_mode == 2) ? 100 : 1000;      // Taxonomer.cpp:44-48
         sa.par.kmer_format = c->cfg.kmer_format;
-        const size_t Mp = M + 1;
-        sa.l_score = c->l_score.get<float>(Mp); sa.l_start = c->l_start.get<int32_t>(Mp); sa.l_ham = c->l_ham.get<int32_t>(Mp);
-        sa.l_depth = c->l_depth.get<int32_t>(Mp); sa.l_smatch = c->l_smatch.get<uint32_t>(Mp); sa.l_conn = c->l_conn.get<uint8_t>(Mp);
-        sa.p_start = c->p_start.get<int32_t>(Mp); sa.p_end = c->p_end.get<int32_t>(Mp); sa.p_score = c->p_score.get<float>(Mp);
-        sa.p_ham = c->p_ham.get<int32_t>(Mp); sa.p_depth = c->p_depth.get<int32_t>(Mp); sa.p_smatch = c->p_smatch.get<uint32_t>(Mp);
-        sa.p_ematch = c->p_ematch.get<uint32_t>(Mp); sa.c_start = c->c_start.get<int32_t>(Mp); sa.c_end = c->c_end.get<int32_t>(Mp);
-        sa.s_score = c->s_score.get<float>(Mp);
         sa.q_tax = c->q_tax.get<int32_t>(sb.quots + 1); sa.q_ham = c->q_ham.get<uint8_t>(sb.quots + 1); sa.q_has = c->q_has.get<uint8_t>(sb.quots + 1);
         sa.taxcnt_pairs = c->pairs_raw.get<int32_t>(2 * (sb.quots + 1));
         sa.results = c->res_sub.get<mbl_read_result>(n);
-        launch_score(sa, st);
+        // reads are scored in chunks so the per-match scratch only has to cover one chunk
+        const uint32_t chunk_reads = kScoreChunkReads;
+        const uint32_t n_chunks = (n + chunk_reads - 1) / chunk_reads;
+        uint64_t* d_bounds = c->chunk_bounds.get<uint64_t>(n_chunks + 2);
+        std::vector<uint64_t> bounds(n_chunks + 1, 0);
+        launch_seq_bounds(sorted, M, chunk_reads, n_chunks, d_bounds, st);
+        MBL_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds, 8 * (size_t)(n_chunks + 1), cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        uint64_t max_chunk = 0;
+        for (uint32_t k = 0; k < n_chunks; ++k) max_chunk = std::max(max_chunk, bounds[k + 1] - bounds[k]);
+        const size_t Mp = max_chunk + 1;
+        float *l_score = c->l_score.get<float>(Mp), *p_score = c->p_score.get<float>(Mp), *s_score = c->s_score.get<float>(Mp);
+        int32_t *l_start = c->l_start.get<int32_t>(Mp), *l_ham = c->l_ham.get<int32_t>(Mp), *l_depth = c->l_depth.get<int32_t>(Mp);
+        uint32_t *l_smatch = c->l_smatch.get<uint32_t>(Mp), *p_smatch = c->p_smatch.get<uint32_t>(Mp), *p_ematch = c->p_ematch.get<uint32_t>(Mp);
+        uint8_t* l_conn = c->l_conn.get<uint8_t>(Mp);
+        int32_t *p_start = c->p_start.get<int32_t>(Mp), *p_end = c->p_end.get<int32_t>(Mp), *p_ham = c->p_ham.get<int32_t>(Mp),
+                *p_depth = c->p_depth.get<int32_t>(Mp), *c_start = c->c_start.get<int32_t>(Mp), *c_end = c->c_end.get<int32_t>(Mp);
+        for (uint32_t k = 0; k < n_chunks; ++k) {
+            const uint64_t f = bounds[k];                 // scratch is indexed by (match index - f)
+            sa.read_begin = k * chunk_reads;
+            sa.n_reads = std::min(chunk_reads, n - sa.read_begin);
+            sa.l_score = l_score - f; sa.l_start = l_start - f; sa.l_ham = l_ham - f; sa.l_depth = l_depth - f; sa.l_smatch = l_smatch - f;
+            sa.l_conn = l_conn - f; sa.p_start = p_start - f; sa.p_end = p_end - f; sa.p_score = p_score - f; sa.p_ham = p_ham - f;
+            sa.p_depth = p_depth - f; sa.p_smatch = p_smatch - f; sa.p_ematch = p_ematch - f; sa.c_start = c_start - f; sa.c_end = c_end - f;
+            sa.s_score = s_score - f;
+            launch_score(sa, st);
+            c->stats.kernel_launches += 1;
+        }
         // compact the (taxid,count) lists behind the pairs of earlier sub-batches
         uint32_t *tl = c->tax_len.get<uint32_t>(n + 1), *to = c->tax_off.get<uint32_t>(n + 1);
         launch_taxcnt_len(sa.results, n, tl, st);
@@ -338,7 +371,6 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
                               (mbl_read_result*)c->results.p + sb.r0, st);
         c->stats.kernel_launches += 3;
         t.stop();
-        // make taxcnt_begin batch-global on download (offset by the pairs of earlier sub-batches)
         c->n_pairs += total;
     }
     MBL_CUDA(cudaGetLastError());
@@ -392,7 +424,7 @@ void mbl_destroy(mbl_ctx* c) {
     free_db(c);
     for (Buf* b : {&c->bases1, &c->bases2, &c->off1, &c->off2, &c->cov1, &c->cov2, &c->w1, &c->w2, &c->slots, &c->slot_off, &c->quot_cnt,
                    &c->quot_off, &c->seg_b, &c->seg_e, &c->res_sub, &c->tax_len, &c->tax_off, &c->val_a, &c->val_b, &c->qi_a, &c->qi_b,
-                   &c->cub_tmp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
+                   &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
                    &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score, &c->p_ham, &c->p_depth, &c->p_smatch,
                    &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw, &c->q_lo,
                    &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs})

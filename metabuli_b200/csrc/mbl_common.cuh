@@ -46,6 +46,7 @@ struct Tile {
     uint32_t n_u16;          // fragments in the tile
     uint32_t n_kmers;        // k-mers in the tile (after the Q1 trim of the very last k-mer)
     uint64_t jumbo_off;      // offset into the pre-decoded value array, or ~0 when not jumbo
+    uint64_t last_value;     // value of the tile's last k-mer (bucket geometry of the merge kernel)
 };
 
 struct MergeItem {           // one unit of merge work: a tile and a slice of its queries

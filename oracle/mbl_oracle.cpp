@@ -243,29 +243,46 @@ void extract_kmers(const std::vector<Read> &m1, const std::vector<Read> *m2, int
 // =================================================================================================
 // A4  Kmer::compareQueryKmer (Kmer.h:89-94)
 // =================================================================================================
-template <class It, class Cmp>
-static void par_sort(It b, It e, Cmp cmp, int threads) {
-    size_t n = (size_t)(e - b);
-    if (threads <= 1 || n < (1u << 16)) { std::stable_sort(b, e, cmp); return; }
-    int parts = threads;
-    std::vector<size_t> cut(parts + 1);
-    for (int i = 0; i <= parts; ++i) cut[i] = n * (size_t)i / (size_t)parts;
-#pragma omp parallel for num_threads(threads) schedule(static, 1)
-    for (int i = 0; i < parts; ++i) std::stable_sort(b + cut[i], b + cut[i + 1], cmp);
-    for (int w = 1; w < parts; w *= 2) {
-#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
-        for (int i = 0; i < parts; i += 2 * w) {
-            int mid = std::min(i + w, parts), hi = std::min(i + 2 * w, parts);
-            if (mid < hi) std::inplace_merge(b + cut[i], b + cut[mid], b + cut[hi], cmp);
-        }
+// Parallel sort used by the timed CPU baseline: bucket by a monotone key (counting partition, OpenMP), then
+// std::sort the buckets in parallel — the role ips4o plays in the reference (FastSort.h:3-20).  The result is the
+// same total order as a plain std::sort with `cmp` as long as bucket(a) < bucket(b) implies cmp(a, b).
+template <class T, class Cmp, class BucketFn>
+static void par_sort(std::vector<T> &v, Cmp cmp, BucketFn bucket, size_t nbuckets, int threads) {
+    const size_t n = v.size();
+    if (threads <= 1 || n < (1u << 16)) { std::sort(v.begin(), v.end(), cmp); return; }
+    std::vector<size_t> cnt((size_t)threads * nbuckets, 0);
+    std::vector<T> tmp(n);
+#pragma omp parallel num_threads(threads)
+    {
+        const int t = omp_get_thread_num();
+        const size_t b = n * (size_t)t / (size_t)threads, e = n * (size_t)(t + 1) / (size_t)threads;
+        size_t *c = cnt.data() + (size_t)t * nbuckets;
+        for (size_t i = b; i < e; ++i) ++c[bucket(v[i])];
     }
+    std::vector<size_t> start(nbuckets + 1, 0);
+    size_t run = 0;
+    for (size_t k = 0; k < nbuckets; ++k) {
+        start[k] = run;
+        for (int t = 0; t < threads; ++t) { size_t c = cnt[(size_t)t * nbuckets + k]; cnt[(size_t)t * nbuckets + k] = run; run += c; }
+    }
+    start[nbuckets] = run;
+#pragma omp parallel num_threads(threads)
+    {
+        const int t = omp_get_thread_num();
+        const size_t b = n * (size_t)t / (size_t)threads, e = n * (size_t)(t + 1) / (size_t)threads;
+        size_t *c = cnt.data() + (size_t)t * nbuckets;
+        for (size_t i = b; i < e; ++i) tmp[c[bucket(v[i])]++] = v[i];
+    }
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 4)
+    for (long long k = 0; k < (long long)nbuckets; ++k) std::sort(tmp.begin() + (long)start[k], tmp.begin() + (long)start[k + 1], cmp);
+    v.swap(tmp);
 }
 
 void sort_kmers(std::vector<Kmer> &kmers, int threads) {
-    par_sort(kmers.begin(), kmers.end(), [](const Kmer &a, const Kmer &b) {
+    par_sort(kmers, [](const Kmer &a, const Kmer &b) {
         if (a.value != b.value) return a.value < b.value;
         return qi_seq(a.qinfo) < qi_seq(b.qinfo);
-    }, threads);
+    }, [](const Kmer &k) { return (size_t)(k.value >> 50); }, (size_t)1 << 14, threads);
 }
 
 // =================================================================================================
@@ -464,7 +481,13 @@ static bool compare_matches(const Match &a, const Match &b) {
     if (a.hamming != b.hamming) return a.hamming < b.hamming;
     return a.dnaEncoding < b.dnaEncoding;
 }
-void sort_matches(std::vector<Match> &m, int threads) { par_sort(m.begin(), m.end(), compare_matches, threads); }
+void sort_matches(std::vector<Match> &m, int threads) {
+    uint32_t maxSeq = 0;
+    for (const Match &x : m) maxSeq = std::max(maxSeq, qi_seq(x.qinfo));
+    const size_t nb = 1 << 14;
+    const uint64_t div = (uint64_t)maxSeq / nb + 1;
+    par_sort(m, compare_matches, [div](const Match &x) { return (size_t)(qi_seq(x.qinfo) / div); }, nb, threads);
+}
 
 // =================================================================================================
 // A8''  taxonomy (TaxonomyWrapper.cpp:363-421, NcbiTaxonomy.cpp:250-330, 415-432)
