@@ -72,7 +72,7 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
                const int32_t* __restrict__ cov1, const int32_t* __restrict__ w1, const int32_t* __restrict__ w2,
                const uint64_t* __restrict__ slot_off, const uint8_t* __restrict__ g_base_code,
                const uint8_t* __restrict__ g_codon, uint64_t* __restrict__ value, uint64_t* __restrict__ qinfo,
-               unsigned long long* __restrict__ n_valid) {
+               uint32_t* __restrict__ slot_idx, unsigned long long* __restrict__ n_valid) {
     __shared__ uint8_t s_code[256];
     __shared__ uint8_t s_codon[512];
     __shared__ WarpScratch s_warp[kWarpsPerBlock];
@@ -142,6 +142,7 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
                     qinfo[sF] = okF ? pack_qinfo(r + 1, pos, frameF) : 0ull;
                     value[sR] = okR ? ((aaR << 24) | (dnaR & 0xFFFFFFu)) : kBlank;
                     qinfo[sR] = okR ? pack_qinfo(r + 1, pos, frameR) : 0ull;
+                    if (slot_idx) { slot_idx[sF] = (uint32_t)sF; slot_idx[sR] = (uint32_t)sR; }   // sort payload (see k2_sort.cu)
                     valid_cnt += (unsigned)okF + (unsigned)okR;
                 }
                 __syncwarp();
@@ -161,7 +162,7 @@ void launch_read_meta(const uint64_t* off1, const uint64_t* off2, uint32_t n_rea
 
 void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2,
                     uint32_t n_reads, const int32_t* cov1, const int32_t* w1, const int32_t* w2, const uint64_t* slot_off,
-                    const uint8_t* base_code, const uint8_t* codon, uint64_t* value, uint64_t* qinfo,
+                    const uint8_t* base_code, const uint8_t* codon, uint64_t* value, uint64_t* qinfo, uint32_t* slot_idx,
                     unsigned long long* n_valid, int sm_count, cudaStream_t st) {
     if (!n_reads) return;
     unsigned blocks = (n_reads + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -169,10 +170,10 @@ void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, con
     if (blocks > cap) blocks = cap;
     if (format == 2)
         extract_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, st>>>(bases1, off1, bases2, off2, n_reads, cov1, w1, w2,
-                                                                 slot_off, base_code, codon, value, qinfo, n_valid);
+                                                                 slot_off, base_code, codon, value, qinfo, slot_idx, n_valid);
     else
         extract_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, st>>>(bases1, off1, bases2, off2, n_reads, cov1, w1, w2,
-                                                                 slot_off, base_code, codon, value, qinfo, n_valid);
+                                                                 slot_off, base_code, codon, value, qinfo, slot_idx, n_valid);
 }
 
 }  // namespace mbl

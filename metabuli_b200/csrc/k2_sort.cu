@@ -28,6 +28,14 @@ void sort_kmers(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, u
     result_in_b = k.selector;
 }
 
+void sort_kmers_idx(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b, size_t n,
+                    int& result_in_b, cudaStream_t st) {
+    cub::DoubleBuffer<uint64_t> k(key_a, key_b);
+    cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
+    MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 24, 64, st));
+    result_in_b = k.selector;
+}
+
 size_t scan_temp_bytes(size_t n) {
     size_t a = 0, b = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, a, (const uint64_t*)nullptr, (uint64_t*)nullptr, (long long)n);
@@ -135,7 +143,36 @@ __global__ void seq_bounds_kernel(const mbl_match_rec* __restrict__ m, size_t n,
     bounds[k] = lo;
 }
 
+// scoring order: inside each chunk of `chunk_reads` reads, reads with similar match counts become neighbours so
+// the lanes of a warp (one read per thread in K5) run loops of similar length
+__global__ void read_len_key_kernel(const uint64_t* __restrict__ seg_b, const uint64_t* __restrict__ seg_e, uint32_t n, uint32_t chunk_reads,
+                                    uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint64_t len = seg_e[r] - seg_b[r];
+    key[r] = ((r / chunk_reads) << 16) | (uint32_t)min(len, (uint64_t)0xFFFF);
+    idx[r] = r;
+}
+
 }  // namespace
+
+size_t order_reads_temp_bytes(size_t n) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (long long)n, 0, 32);
+    return bytes;
+}
+// -> pointer to the permutation (one of idx_a / idx_b)
+const uint32_t* order_reads_by_matches(void* tmp, size_t tmp_bytes, const uint64_t* seg_b, const uint64_t* seg_e, uint32_t n,
+                                       uint32_t chunk_reads, uint32_t* key_a, uint32_t* key_b, uint32_t* idx_a, uint32_t* idx_b, cudaStream_t st) {
+    if (!n) return idx_a;
+    read_len_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(seg_b, seg_e, n, chunk_reads, key_a, idx_a);
+    cub::DoubleBuffer<uint32_t> k(key_a, key_b), v(idx_a, idx_b);
+    int chunk_bits = 1;
+    while ((1u << chunk_bits) <= (n - 1) / chunk_reads) ++chunk_bits;
+    MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, 16 + chunk_bits, st));
+    return v.Current();
+}
 
 void launch_seq_bounds(const mbl_match_rec* sorted, size_t n, uint32_t chunk_reads, uint32_t n_chunks, uint64_t* bounds, cudaStream_t st) {
     seq_bounds_kernel<<<(n_chunks + 1 + 127) / 128, 128, 0, st>>>(sorted, n, chunk_reads, n_chunks, bounds);

@@ -35,29 +35,23 @@ constexpr uint64_t kNone = ~0ull;
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kEmpty = 0xffffffffu;     // bucket table: no group hashes here
 
-// bucket table entry = group start (13 bits) << 19 | tag (18 bits) << 1 | collision flag.  The tag is the top 18
-// bits of what the bucket function shifts out, so tag + bucket identify the amino-acid part (exactly when
-// shift <= 18; otherwise the hit is verified against the value array anyway).
-__device__ __forceinline__ uint32_t bucket_tag(uint64_t d, uint32_t shift) {
-    const uint64_t r = d & ((1ull << shift) - 1ull);
-    return (uint32_t)(shift > 18 ? r >> (shift - 18) : r) & 0x3FFFFu;
-}
+// hash table entry = group start (13 bits) << 19 | tag (19 bits).  Bucket and tag come from disjoint bits of a
+// multiplicative hash of the 40-bit amino-acid part; a tag match is verified against the value array.
+__device__ __forceinline__ uint32_t aa_hash(uint64_t aa40) { return (uint32_t)((aa40 * 0x9E3779B97F4A7C15ull) >> 32); }
 
 // dynamic shared memory layout (sizes depend on the tile geometry chosen at load time)
 struct SmemLayout {
-    uint32_t off_ham, off_ham1, off_minh, off_frag, off_info, off_vals, off_tab, total;
+    uint32_t off_ham, off_queue, off_frag0, off_frag1, off_vals, off_tab, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets) {
     SmemLayout l;
-    uint32_t o = 16;                                   // mbarrier + item slot
-    l.off_ham = o;   o += 8192;                        // two-codon table: sum | plain nibble | reversed nibble (u16)
-    l.off_ham1 = o;  o += 0;
-    l.off_minh = o;  o += kWarps * kQueue * 12;        // per-warp hit queues {group start, query dna, query offset}
-    l.off_frag = o;  o += (max_u16 + 16) * 2;
-    l.off_info = o;  o += (max_kmers + 8) * 4;
-    o = (o + 15) & ~15u;
-    l.off_vals = o;  o += max_kmers * 8;
-    l.off_tab = o;   o += n_buckets * 4;               // tagged bucket table
+    uint32_t o = 32;                                   // two mbarriers + two item slots
+    l.off_ham = o;    o += 8192;                       // two-codon table: sum | plain nibble | reversed nibble (u16)
+    l.off_queue = o;  o += kWarps * kQueue * 12;       // per-warp hit queues {group start, query dna, query offset}
+    l.off_frag0 = o;  o += (max_u16 + 16) * 2;         // fragment tile, double buffered: the next item's tile is
+    l.off_frag1 = o;  o += (max_u16 + 16) * 2;         // in flight (TMA) while the current one is being matched
+    l.off_vals = o;   o += max_kmers * 8;
+    l.off_tab = o;    o += n_buckets * 4;              // open-addressing hash table of amino-acid group starts
     l.total = (o + 15) & ~15u;
     return l;
 }
@@ -114,6 +108,10 @@ __device__ __forceinline__ uint32_t ham_fields(const HamQuad& h, uint32_t q, uin
     const uint32_t qc = plain ? (q >> 21) & 7u : q & 7u, tc = plain ? (t >> 21) & 7u : t & 7u;
     if ((qc & 6u) == 4u && tc >= 6u) f |= 0x4000u;
     return f;
+}
+
+__device__ __forceinline__ uint64_t load_qinfo(const MergeArgs& a, uint64_t sorted_pos) {
+    return a.q_info[a.q_idx ? (uint64_t)a.q_idx[sorted_pos] : sorted_pos];
 }
 
 // one 24-byte Match record (Match.h:9-26 without the vptr); Q2: taxid 0 / unmapped species raise the error flag
@@ -176,67 +174,69 @@ __global__ void merge_item_fill_kernel(uint64_t n_tiles, const uint64_t* __restr
 }
 
 // ---- the merge kernel ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 3)
 merge_kernel(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = smem_layout(a.max_u16, a.max_kmers, a.n_buckets);
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);
-    unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 8);
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);          // [2]
+    unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 16);                 // [2]
     uint16_t* s_ham = reinterpret_cast<uint16_t*>(smem + L.off_ham);
-    uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + L.off_minh);
-    uint16_t* s_frag = reinterpret_cast<uint16_t*>(smem + L.off_frag);
-    int32_t* s_info = reinterpret_cast<int32_t*>(smem + L.off_info);
+    uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + L.off_queue);
+    uint16_t* s_frag0 = reinterpret_cast<uint16_t*>(smem + L.off_frag0);
+    const uint32_t frag_stride = (L.off_frag1 - L.off_frag0) / 2;     // in u16
     uint64_t* s_vals = reinterpret_cast<uint64_t*>(smem + L.off_vals);
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + L.off_tab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 4096; i += kThreads) s_ham[i] = a.ham_pair[i];
-    if (tid == 0) mbar_init(mbar, 1);
+    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
     __syncthreads();
-    unsigned parity = 0;
+    unsigned parity_bits = 0u;                        // bit b = phase parity of mbarrier b
     const uint32_t n_items = a.item_off[a.n_tiles];
     const bool fmt2 = a.kmer_format == 2;
+    const uint32_t tab_mask = a.n_buckets - 1;
+    const int hash_shift = 32 - (31 - __clz(a.n_buckets));
     uint32_t* my_queue = s_queue + warp * kQueue * 3;
     unsigned long long my_matches = 0;
 
-    while (true) {
-        if (tid == 0) *s_item = atomicAdd(a.item_cursor, 1u);
-        __syncthreads();
-        const uint32_t item = *s_item;
-        if (item >= n_items) break;
+    // thread 0: start the TMA copy of an item's fragment tile into buffer `buf`
+    auto stage = [&](uint32_t item, int buf) {
+        if (item >= n_items) return;
+        const Tile t = a.tiles[a.items[item].tile];
+        if (t.jumbo_off != kNone) return;
+        const uint64_t d0 = t.diff_begin, d1 = t.diff_begin + t.n_u16;
+        const uint64_t a0 = d0 & ~7ull, a1 = (d1 + 7ull) & ~7ull;
+        fence_proxy_async();
+        mbar_expect_tx(mbar + buf, (unsigned)((a1 - a0) * 2));
+        tma_load_1d(s_frag0 + (uint32_t)buf * frag_stride, a.diff + a0, (unsigned)((a1 - a0) * 2), mbar + buf);
+    };
+
+    if (tid == 0) { s_item[0] = atomicAdd(a.item_cursor, 1u); stage(s_item[0], 0); }
+    __syncthreads();
+    uint32_t item = s_item[0];
+    int buf = 0;
+
+    while (item < n_items) {
         const MergeItem it = a.items[item];
         const Tile tl = a.tiles[it.tile];
         const uint32_t nk = tl.n_kmers;
         const bool jumbo = tl.jumbo_off != kNone;
         const uint64_t* vals;
-        const int32_t* infos;
-        uint64_t base40 = 0, span40 = 0;
-        uint32_t shift = 0;
+        const int32_t* infos = a.info + tl.info_begin;
+        // claim the next item and clear the hash table (the previous item's lookups ended at the barrier below)
+        if (tid == 0) s_item[buf ^ 1] = atomicAdd(a.item_cursor, 1u);
+        for (uint32_t x = tid; x < a.n_buckets; x += kThreads) s_tab[x] = kEmpty;
+        __syncthreads();
+        const uint32_t next_item = s_item[buf ^ 1];
+        if (tid == 0) stage(next_item, buf ^ 1);             // its tile streams in while this item is decoded and matched
         if (!jumbo) {
-            // -- 1. stage the tile: fragments + taxids, two bulk copies on one mbarrier
+            // -- 1. the tile's fragments were requested one item ago
             const uint64_t d0 = tl.diff_begin, d1 = tl.diff_begin + tl.n_u16;
-            const uint64_t a0 = d0 & ~7ull, a1 = (d1 + 7ull) & ~7ull;
-            const uint64_t i0 = tl.info_begin & ~3ull, i1 = (tl.info_begin + nk + 3ull) & ~3ull;
-            if (tid == 0) {
-                fence_proxy_async();
-                const unsigned fb = (unsigned)((a1 - a0) * 2), ib = (unsigned)((i1 - i0) * 4);
-                mbar_expect_tx(mbar, fb + ib);
-                tma_load_1d(s_frag, a.diff + a0, fb, mbar);
-                if (ib) tma_load_1d(s_info, a.info + i0, ib, mbar);
-            }
-            // bucket geometry from the directory (first / last value of the tile); clear the table while the copies fly
-            base40 = tl.first_aa >> 24;
-            span40 = (tl.last_value >> 24) - base40;
-            {
-                const int bits = 64 - __clzll(span40 | 1ull);
-                const int lb = 31 - __clz(a.n_buckets);
-                shift = bits > lb ? (uint32_t)(bits - lb) : 0u;
-            }
-            for (uint32_t x = tid; x < a.n_buckets; x += kThreads) s_tab[x] = kEmpty;
-            __syncthreads();
-            mbar_wait(mbar, parity);
-            parity ^= 1u;
-            // -- 2. decode: one warp per checkpoint cell; group starts go into the tagged bucket table
+            const uint64_t a0 = d0 & ~7ull;
+            mbar_wait(mbar + buf, (parity_bits >> buf) & 1u);
+            parity_bits ^= 1u << buf;
+            // -- 2. decode: one warp per checkpoint cell; group starts go into the hash table
+            const uint16_t* frag = s_frag0 + (uint32_t)buf * frag_stride;
             const uint64_t c0 = d0 / kCellU16, c1 = (d1 + kCellU16 - 1) / kCellU16;
             for (uint64_t c = c0 + warp; c < c1; c += kWarps) {
                 const uint64_t s_abs = max(c * (uint64_t)kCellU16, d0), e_abs = min((c + 1) * (uint64_t)kCellU16, d1);
@@ -244,29 +244,24 @@ merge_kernel(MergeArgs a) {
                 if (s_abs == d0) { v = tl.base_value; k = tl.info_begin; }
                 else { v = a.cell_v[c]; k = a.cell_k[c]; }
                 const uint64_t kb = tl.info_begin;
-                const uint64_t b40 = base40;
-                const uint32_t sh = shift;
-                warp_decode(s_frag, (long long)(d0 - a0), (long long)(s_abs - a0), (long long)(e_abs - a0), v, k,
+                warp_decode(frag, (long long)(d0 - a0), (long long)(s_abs - a0), (long long)(e_abs - a0), v, k,
                             [&](uint64_t kk, uint64_t val, uint64_t delta, long long) {
                                 const uint64_t rel = kk - kb;
                                 if (rel >= nk) return;
                                 s_vals[rel] = val;
                                 const uint64_t aa = val >> 24;
                                 if (rel == 0 || ((val - delta) >> 24) != aa) {
-                                    const uint64_t d = aa - b40;
-                                    const uint32_t bkt = (uint32_t)(d >> sh);
-                                    const uint32_t entry = ((uint32_t)rel << 19) | (bucket_tag(d, sh) << 1);
-                                    const uint32_t old = atomicMin(&s_tab[bkt], entry);
-                                    if (old != kEmpty) atomicOr(&s_tab[bkt], 1u);       // more than one group in this bucket
+                                    const uint32_t h = aa_hash(aa);
+                                    const uint32_t entry = ((uint32_t)rel << 19) | (h & 0x7FFFFu);
+                                    uint32_t slot = h >> hash_shift;
+                                    while (atomicCAS(&s_tab[slot], kEmpty, entry) != kEmpty) slot = (slot + 1) & tab_mask;
                                 }
                             });
             }
             __syncthreads();
             vals = s_vals;
-            infos = s_info + (tl.info_begin - i0);
         } else {
             vals = a.jumbo_vals + tl.jumbo_off;
-            infos = a.info + tl.info_begin;
         }
 
         // -- 3. stream the query slice.  A warp looks up 32 queries per iteration and appends the ones that found
@@ -319,7 +314,7 @@ merge_kernel(MergeArgs a) {
                 for (uint32_t c = lane; c < bn; c += 32) mn = min(mn, ham_sum(ham_lookup(s_ham, bqd, (uint32_t)vals[bg0 + c] & 0xFFFFFFu)));
                 mn = __reduce_min_sync(kFull, mn);
                 const uint32_t maxH = min(mn * 2u, 7u);
-                const uint64_t qinfo = a.q_info[it.q_begin + bqoff];
+                const uint64_t qinfo = load_qinfo(a, it.q_begin + bqoff);
                 const bool plain = !((qi_frame(qinfo) < 3) ^ fmt2);
                 for (uint32_t cb = 0; cb < bn; cb += 32) {
                     const uint32_t c = cb + lane;
@@ -371,7 +366,7 @@ merge_kernel(MergeArgs a) {
             my_matches += total;
             uint64_t qinfo = 0;
             bool plain = true;
-            if (cnt) { qinfo = a.q_info[it.q_begin + qoff]; plain = !((qi_frame(qinfo) < 3) ^ fmt2); }   // KmerMatcher.cpp:1140
+            if (cnt) { qinfo = load_qinfo(a, it.q_begin + qoff); plain = !((qi_frame(qinfo) < 3) ^ fmt2); }   // KmerMatcher.cpp:1140
             // exact runs: Hamming 0, all per-codon fields 0
             uint32_t xmax = exn;
 #pragma unroll
@@ -396,19 +391,12 @@ merge_kernel(MergeArgs a) {
             uint32_t g0 = 0;
             bool hit = false;
             if (!jumbo) {
-                const uint64_t d = q40 - base40;                 // wraps to a huge value when q40 < base40
-                if (d <= span40) {
-                    const uint32_t bkt = (uint32_t)(d >> shift);
-                    const uint32_t e = s_tab[bkt];
-                    if (e != kEmpty) {
-                        const uint32_t st = e >> 19;
-                        if (((e >> 1) & 0x3FFFFu) == bucket_tag(d, shift) && (vals[st] >> 24) == q40) { g0 = st; hit = true; }
-                        else if (e & 1u) {                      // several groups share the bucket: walk it
-                            for (uint32_t j = st + 1; j < nk; ++j) {
-                                const uint64_t v40 = vals[j] >> 24;
-                                if (v40 >= q40) { if (v40 == q40) { g0 = j; hit = true; } break; }
-                            }
-                        }
+                if (active) {
+                    const uint32_t h = aa_hash(q40);
+                    const uint32_t tag = h & 0x7FFFFu;
+                    uint32_t slot = h >> hash_shift;
+                    for (uint32_t e = s_tab[slot]; e != kEmpty; e = s_tab[slot = (slot + 1) & tab_mask]) {
+                        if ((e & 0x7FFFFu) == tag && (vals[e >> 19] >> 24) == q40) { g0 = e >> 19; hit = true; break; }
                     }
                 }
             } else if (active) {
@@ -429,6 +417,8 @@ merge_kernel(MergeArgs a) {
         }
         if (q_count) { process_hits(q_count); __syncwarp(); }
         __syncthreads();
+        item = next_item;
+        buf ^= 1;
     }
     if (lane == 0 && my_matches) atomicAdd(a.out_count + 1, my_matches);
 }

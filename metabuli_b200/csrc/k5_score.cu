@@ -9,7 +9,7 @@ namespace mbl {
 __global__ void __launch_bounds__(128, 4) score_kernel(ScoreArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_reads) return;
-    score_read(a, a.read_begin + i);
+    score_read(a, a.read_perm ? a.read_perm[a.read_begin + i] : a.read_begin + i);
 }
 
 __global__ void taxcnt_len_kernel(const mbl_read_result* __restrict__ res, uint32_t n, uint32_t* __restrict__ len) {

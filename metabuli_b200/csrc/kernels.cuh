@@ -40,13 +40,16 @@ void launch_read_meta(const uint64_t* off1, const uint64_t* off2, uint32_t n_rea
                       int32_t* w1, int32_t* w2, uint64_t* slots, uint32_t* quot_cnt, cudaStream_t st);
 void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2,
                     uint32_t n_reads, const int32_t* cov1, const int32_t* w1, const int32_t* w2, const uint64_t* slot_off,
-                    const uint8_t* base_code, const uint8_t* codon, uint64_t* value, uint64_t* qinfo,
+                    const uint8_t* base_code, const uint8_t* codon, uint64_t* value, uint64_t* qinfo, uint32_t* slot_idx,
                     unsigned long long* n_valid, int sm_count, cudaStream_t st);
 
 // K2 / K4 (radix sorts) and scans
 size_t sort_kmers_temp_bytes(size_t n);
 void sort_kmers(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint64_t* val_a, uint64_t* val_b, size_t n,
                 int& result_in_b, cudaStream_t st);
+// pipeline variant: the payload is the 32-bit slot index; qinfo stays where K1 wrote it and is gathered for hits only
+void sort_kmers_idx(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b, size_t n,
+                    int& result_in_b, cudaStream_t st);
 size_t scan_temp_bytes(size_t n);
 void exclusive_sum_u64(void* tmp, size_t tmp_bytes, const uint64_t* in, uint64_t* out, size_t n, cudaStream_t st);
 void exclusive_sum_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st);
@@ -55,6 +58,9 @@ size_t sort_matches_temp_bytes(size_t n);
 void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
                   int32_t max_taxid, uint32_t max_pos, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b,
                   cudaStream_t st);
+size_t order_reads_temp_bytes(size_t n);
+const uint32_t* order_reads_by_matches(void* tmp, size_t tmp_bytes, const uint64_t* seg_b, const uint64_t* seg_e, uint32_t n,
+                                       uint32_t chunk_reads, uint32_t* key_a, uint32_t* key_b, uint32_t* idx_a, uint32_t* idx_b, cudaStream_t st);
 void launch_seq_bounds(const mbl_match_rec* sorted, size_t n, uint32_t chunk_reads, uint32_t n_chunks, uint64_t* bounds, cudaStream_t st);
 void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, uint64_t* seg_begin, uint64_t* seg_end, cudaStream_t st);
 
@@ -75,6 +81,7 @@ struct MergeArgs {
     const uint64_t* jumbo_vals;
     const uint64_t* q_value;        // sorted by amino-acid part
     const uint64_t* q_info;
+    const uint32_t* q_idx;          // optional: q_info is indexed through q_idx[sorted position] (unsorted qinfo array)
     uint64_t n_query;               // non-blank
     const int32_t* taxid2species;
     int32_t max_taxid;
@@ -105,6 +112,7 @@ struct ScoreArgs {
     const mbl_match_rec* matches;       // sorted
     uint64_t n_match;
     uint32_t read_begin;            // reads [read_begin, read_begin + n_reads) of the sub-batch are scored by one launch
+    const uint32_t* read_perm;      // optional: thread i scores read read_perm[read_begin + i] (reads ordered by match count)
     uint32_t n_reads;
     const uint64_t* seg_begin;      // per read (seqID - 1)
     const uint64_t* seg_end;

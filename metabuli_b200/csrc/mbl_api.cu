@@ -65,7 +65,7 @@ struct mbl_ctx {
     // workspace
     Buf cov1, cov2, w1, w2, slots, slot_off, quot_cnt, quot_off, seg_b, seg_e, res_sub, tax_len, tax_off;
     Buf val_a, val_b, qi_a, qi_b, cub_tmp;
-    Buf arena, chunk_bounds;     // phase 1: k-mer keys/payloads (32 B per slot); phase 2: match sort buffers
+    Buf arena, chunk_bounds, order_keys;     // phase 1: k-mer keys/payloads (32 B per slot); phase 2: match sort buffers
     Buf m_raw, m_sorted, key_a, key_b, idx_a, idx_b;
     Buf l_score, l_start, l_ham, l_depth, l_smatch, l_conn, p_start, p_end, p_score, p_ham, p_depth, p_smatch, p_ematch,
         c_start, c_end, s_score;
@@ -171,6 +171,7 @@ uint64_t slots_budget(mbl_ctx* c) {
     double budget = 0.88 * (double)(free_b + held) - 10.0e9;
     uint64_t s = budget > 0 ? (uint64_t)(budget / per_slot) : 0;
     s = std::min<uint64_t>(s, (uint64_t)(3.9e9 / r));            // 32-bit match permutation
+    s = std::min<uint64_t>(s, 4000000000ull);                    // 32-bit slot index (K2 payload)
     s = std::max<uint64_t>(s, 1ull << 16);
     return s;
 }
@@ -203,24 +204,28 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         void* tmp = c->cub_tmp.get<uint8_t>(std::max(scan_bytes, sortk_bytes));
         exclusive_sum_u64(tmp, c->cub_tmp.cap, slots, slot_off, n + 1, st);
         exclusive_sum_u32(tmp, c->cub_tmp.cap, quot_cnt, quot_off, n + 1, st);
-        // phase-1 layout of the arena: value A | qinfo A | value B | qinfo B, S8 entries each
+        // phase-1 layout of the arena (32 B per slot): value A | value B | qinfo (stays unsorted) | slot idx A | slot idx B
         uint64_t* ar = c->arena.get<uint64_t>(4 * S8 + 64);
-        uint64_t *va = ar, *qa = ar + S8;
+        uint64_t *va = ar, *qa = ar + 2 * S8;
+        uint32_t* ia = reinterpret_cast<uint32_t*>(ar + 3 * S8);
         launch_extract(c->cfg.kmer_format, bases1, off1, bases2, off2, n, cov1, w1, w2, slot_off, c->d_base_code, c->d_codon,
-                       va, qa, counters, c->sm_count, st);
+                       va, qa, ia, counters, c->sm_count, st);
         c->stats.kernel_launches += 2;
         t.stop();
     }
     // ---- K2 ------------------------------------------------------------------------------------------
     uint64_t *qv = nullptr, *qi = nullptr;
+    uint32_t* qidx = nullptr;
     {
         StageTimer t(c, MBL_STAGE_SORT);
         uint64_t* ar = (uint64_t*)c->arena.p;
-        uint64_t *va = ar, *qa = ar + S8, *vb = ar + 2 * S8, *qb = ar + 3 * S8;
+        uint64_t *va = ar, *vb = ar + S8;
+        uint32_t *ia = reinterpret_cast<uint32_t*>(ar + 3 * S8), *ib = ia + S8;
         int in_b = 0;
-        if (S) sort_kmers(c->cub_tmp.p, c->cub_tmp.cap, va, vb, qa, qb, S, in_b, st);
+        if (S) sort_kmers_idx(c->cub_tmp.p, c->cub_tmp.cap, va, vb, ia, ib, S, in_b, st);
         qv = in_b ? vb : va;
-        qi = in_b ? qb : qa;
+        qidx = in_b ? ib : ia;
+        qi = ar + 2 * S8;
         t.stop();
     }
     unsigned long long h_cnt[4] = {0, 0, 0, 0};
@@ -237,11 +242,11 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     ma.info_mask = ~((uint32_t)(c->cfg.skip_redundancy == 0) << 31);
     ma.tiles = c->dir.tiles; ma.n_tiles = c->dir.n_tiles; ma.cell_k = c->dir.cell_k; ma.cell_v = c->dir.cell_v;
     ma.jumbo_vals = c->dir.jumbo_vals;
-    ma.q_value = qv; ma.q_info = qi; ma.n_query = n_query;
+    ma.q_value = qv; ma.q_info = qi; ma.q_idx = qidx; ma.n_query = n_query;
     ma.taxid2species = c->tax.taxid2species; ma.max_taxid = c->tax.max_taxid;
     ma.ham_pair = c->d_ham_pair; ma.kmer_format = c->cfg.kmer_format;
     ma.ham_single = c->d_ham_single; ma.max_u16 = c->dir.max_u16 + 16; ma.max_kmers = c->dir.max_kmers;
-    ma.n_buckets = 1; while (ma.n_buckets < ma.max_kmers) ma.n_buckets <<= 1;
+    ma.n_buckets = 2; while (ma.n_buckets <= ma.max_kmers) ma.n_buckets <<= 1;    // hash table load <= 50 %
     ma.out_count = counters + 1;
     ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
     ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
@@ -333,6 +338,14 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         MBL_CUDA(cudaStreamSynchronize(st));
         uint64_t max_chunk = 0;
         for (uint32_t k = 0; k < n_chunks; ++k) max_chunk = std::max(max_chunk, bounds[k + 1] - bounds[k]);
+        // inside a chunk, threads take the reads in order of match count (less divergence between the lanes of a warp)
+        {
+            void* tmp = c->cub_tmp.get<uint8_t>(std::max(order_reads_temp_bytes(n), scan_bytes));
+            uint32_t* ok = c->order_keys.get<uint32_t>(4 * (size_t)(n + 1));
+            sa.read_perm = order_reads_by_matches(tmp, c->cub_tmp.cap, seg_b, seg_e, n, chunk_reads, ok, ok + (n + 1), ok + 2 * (size_t)(n + 1),
+                                                  ok + 3 * (size_t)(n + 1), st);
+            c->stats.kernel_launches += 1;
+        }
         const size_t Mp = max_chunk + 1;
         float *l_score = c->l_score.get<float>(Mp), *p_score = c->p_score.get<float>(Mp), *s_score = c->s_score.get<float>(Mp);
         int32_t *l_start = c->l_start.get<int32_t>(Mp), *l_ham = c->l_ham.get<int32_t>(Mp), *l_depth = c->l_depth.get<int32_t>(Mp);
@@ -424,7 +437,7 @@ void mbl_destroy(mbl_ctx* c) {
     free_db(c);
     for (Buf* b : {&c->bases1, &c->bases2, &c->off1, &c->off2, &c->cov1, &c->cov2, &c->w1, &c->w2, &c->slots, &c->slot_off, &c->quot_cnt,
                    &c->quot_off, &c->seg_b, &c->seg_e, &c->res_sub, &c->tax_len, &c->tax_off, &c->val_a, &c->val_b, &c->qi_a, &c->qi_b,
-                   &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
+                   &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->order_keys, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
                    &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score, &c->p_ham, &c->p_depth, &c->p_smatch,
                    &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw, &c->q_lo,
                    &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs})
@@ -604,7 +617,7 @@ int mbl_extract(mbl_ctx* c, const mbl_batch* b, uint64_t* value, uint64_t* qinfo
         uint64_t *va = c->val_a.get<uint64_t>(total), *qa = c->qi_a.get<uint64_t>(total);
         launch_extract(c->cfg.kmer_format, (const uint8_t*)c->bases1.p, (const uint64_t*)c->off1.p,
                        c->paired ? (const uint8_t*)c->bases2.p : nullptr, off2, n, cov1, w1, w2, slot_off, c->d_base_code,
-                       c->d_codon, va, qa, counters, c->sm_count, st);
+                       c->d_codon, va, qa, nullptr, counters, c->sm_count, st);
         MBL_CUDA(cudaMemcpyAsync(value, va, 8 * total, cudaMemcpyDeviceToHost, st));
         MBL_CUDA(cudaMemcpyAsync(qinfo, qa, 8 * total, cudaMemcpyDeviceToHost, st));
         MBL_CUDA(cudaStreamSynchronize(st));
@@ -658,7 +671,7 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
         ma.taxid2species = c->tax.taxid2species; ma.max_taxid = c->tax.max_taxid;
         ma.ham_pair = c->d_ham_pair; ma.kmer_format = c->cfg.kmer_format;
         ma.ham_single = c->d_ham_single; ma.max_u16 = c->dir.max_u16 + 16; ma.max_kmers = c->dir.max_kmers;
-        ma.n_buckets = 1; while (ma.n_buckets < ma.max_kmers) ma.n_buckets <<= 1;
+        ma.n_buckets = 2; while (ma.n_buckets <= ma.max_kmers) ma.n_buckets <<= 1;    // hash table load <= 50 %
         ma.out_count = counters + 1;
         ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
         ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;

@@ -148,7 +148,21 @@ MBL_HD int32_t tax_parent(const DeviceTaxonomy& t, int32_t id) { return tax_exis
 
 // ---- Match score helpers (Match.h:32-88) ---------------------------------------------------------------
 MBL_HD float codon_score(int d) { return d == 0 ? 3.0f : 2.0f - 0.5f * (float)d; }
-MBL_HD float match_score(uint32_t reh) { float s = 0.f; for (int i = 0; i < 8; ++i) s += codon_score((reh >> (2 * i)) & 3); return s; }
+MBL_HD int popc16(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+// Match::getScore (Match.h:32-44): sum over the 8 codons of {0:3.0, 1:1.5, 2:1.0, 3:0.5}.  Every term is a multiple of
+// 0.5, so the float sum is exact in any order; count the codons per distance instead of looping.
+MBL_HD float match_score(uint32_t reh) {
+    const uint32_t lo = reh & 0x5555u, hi = (reh >> 1) & 0x5555u;
+    const int n3 = popc16(lo & hi), n2 = popc16(hi & ~lo), n1 = popc16(lo & ~hi);
+    const int n0 = 8 - n1 - n2 - n3;
+    return 3.0f * (float)n0 + 1.5f * (float)n1 + 1.0f * (float)n2 + 0.5f * (float)n3;
+}
 MBL_HD float right_part_score(uint32_t reh, int range) { float s = 0.f; for (int i = 0; i < range; ++i) s += codon_score((reh >> (2 * i)) & 3); return s; }
 MBL_HD float left_part_score(uint32_t reh, int range) { float s = 0.f; for (int i = 0; i < range; ++i) s += codon_score((reh >> (14 - 2 * i)) & 3); return s; }
 MBL_HD int right_part_ham(uint32_t reh, int range) { int s = 0; for (int i = 0; i < range; ++i) s += (reh >> (2 * i)) & 3; return s; }
@@ -177,7 +191,7 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
     }
     const bool forward = qi_frame(ml[gs].qinfo) < 3;
     const bool fmt2 = a.par.kmer_format == 2;
-    DpCell cur[kDpWidth], nxt[kDpWidth];
+    DpCell bufA[kDpWidth], bufB[kDpWidth];
     int ncur = 0, nnxt = 0;
     auto load = [&](DpCell& c, uint64_t i) {
         c.score = match_score(ml[i].right_end_hamming);
@@ -196,8 +210,9 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
     };
     uint64_t i = gs;
     uint64_t curPos = qi_pos(ml[gs].qinfo);
-    while (i < ge && qi_pos(ml[i].qinfo) == curPos) { load(cur[ncur++], i); ++i; }
-    while (i < ge) {
+    while (i < ge && qi_pos(ml[i].qinfo) == curPos) { load(bufA[ncur++], i); ++i; }
+    // one DP step: `cur` holds the paths ending at curPos, `nxt` receives those ending at the next position
+    auto step = [&](DpCell* cur, DpCell* nxt) {
         const uint32_t nextPos = qi_pos(ml[i].qinfo);
         nnxt = 0;
         while (i < ge && qi_pos(ml[i].qinfo) == nextPos) { load(nxt[nnxt++], i); ++i; }
@@ -239,10 +254,13 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
             for (int nx = 0; nx < kDpWidth; ++nx)
                 if (nx < nnxt && nxt[nx].depth >= min_depth) push(nxt[nx]);
         }
-#pragma unroll
-        for (int k = 0; k < kDpWidth; ++k) cur[k] = nxt[k];
         ncur = nnxt;
         curPos = nextPos;
+    };
+    while (i < ge) {
+        step(bufA, bufB);
+        if (i >= ge) break;
+        step(bufB, bufA);
     }
     return true;
 }

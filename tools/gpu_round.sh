@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 echo "== pytest -m gpu"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
-echo "== tune"; timeout 600 python tools/tune_merge.py --cells 2,4 2>&1 | tail -8 | tee gpurun_out/tune.jsonl
+echo "== tune"; timeout 600 python tools/tune_merge.py --cells 1,2,4 2>&1 | tail -8 | tee gpurun_out/tune.jsonl
 BEST=$(tail -1 gpurun_out/tune.jsonl | python -c "import json,sys; print(json.loads(sys.stdin.read()).get('best_tile_cells',4))" 2>/dev/null || echo 4)
 export MBL_TILE_CELLS=${MBL_TILE_CELLS_FORCE:-$BEST}
 echo "== using MBL_TILE_CELLS=$MBL_TILE_CELLS"
@@ -19,11 +19,11 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --db-gib 1 --reads 2000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_run.log 2>&1
 tail -1 gpurun_out/ncu_launch_run.log | cut -c1-300
-echo "== ncu full (merge + score kernels)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:merge_kernel -s 1 -c 2 -o gpurun_out/merge_prof -f \
-    python bench.py --db-gib 1 --reads 2000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
+echo "== ncu full (merge kernel, FULL bench workload; score kernel, reduced workload)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:merge_kernel -s 1 -c 1 -o gpurun_out/merge_prof -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
 tail -2 gpurun_out/ncu_full_run.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_kernel -s 1 -c 1 -o gpurun_out/score_prof -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_kernel -s 2 -c 1 -o gpurun_out/score_prof -f \
     python bench.py --db-gib 1 --reads 2000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_score_run.log 2>&1
 tail -1 gpurun_out/ncu_score_run.log | cut -c1-200
 ls -la gpurun_out

@@ -85,6 +85,6 @@ if os.path.exists(rep):
                 pass
     if dram:
         json.dump({"dram_bytes_per_launch": sum(dram) / len(dram), "launches": len(dram), "source": f"profiles/{tag}_merge_ncu.md",
-                   "note": "ncu workload = bench.py --db-gib 1 --reads 2000000 (smaller than the bench line's workload)"},
+                   "note": "ncu workload = bench.py default workload (10M reads vs ~8 GiB index), one merge launch"},
                   open(os.path.join(out_dir, "merge_ncu_summary.json"), "w"))
     print("wrote", f"{tag}_merge_ncu.md", len(data), "launches")
