@@ -103,4 +103,104 @@ __device__ __forceinline__ void warp_decode(const uint16_t* frag, long long lo, 
     }
 }
 
+
+// Block-wide variant for the merge kernel: all kThreadsDecode threads take one octet each (2048 fragments per
+// sweep), so a tile of a few KiB keeps every warp busy and needs no per-cell checkpoints.  Same octet logic as
+// warp_decode; the (count, sum) pairs are scanned inside each warp with shuffles and across warps through a tiny
+// double-buffered shared array (one __syncthreads per sweep).  `scan` must hold 2 * 2 * (threads/32) uint64_t.
+// All threads of the block must call; v0 / k0 are block-uniform running totals.
+template <int kThreadsDecode, class Emit>
+__device__ __forceinline__ void block_decode(const uint16_t* frag, long long lo, long long s, long long e, uint64_t& v0, uint64_t& k0,
+                                             uint64_t* scan, Emit emit) {
+    constexpr int kW = kThreadsDecode / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int flip = 0;
+    for (long long p0 = s & ~7ll; p0 < e; p0 += 8ll * kThreadsDecode, flip ^= 1) {
+        const long long p = p0 + 8ll * threadIdx.x;
+        uint16_t f[8];
+        uint16_t lb[4];
+        if (p < e) {
+            uint4 v = *reinterpret_cast<const uint4*>(frag + p);
+            f[0] = (uint16_t)v.x; f[1] = (uint16_t)(v.x >> 16); f[2] = (uint16_t)v.y; f[3] = (uint16_t)(v.y >> 16);
+            f[4] = (uint16_t)v.z; f[5] = (uint16_t)(v.z >> 16); f[6] = (uint16_t)v.w; f[7] = (uint16_t)(v.w >> 16);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0;
+        }
+        if (p < e && p - 4 >= (lo & ~3ll) && p >= 4) {
+            uint2 v = *reinterpret_cast<const uint2*>(frag + p - 4);
+            lb[0] = (uint16_t)v.x; lb[1] = (uint16_t)(v.x >> 16); lb[2] = (uint16_t)v.y; lb[3] = (uint16_t)(v.y >> 16);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lb[j] = 0x8000u;
+        }
+        uint64_t acc = 0;
+        long long kstart = p - 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long idx = p - 4 + j;
+            const bool cut = (lb[j] & 0x8000u) || idx < lo;
+            acc = cut ? 0ull : ((acc << 15) | lb[j]);
+            if (cut) kstart = idx + 1;
+        }
+        uint32_t cnt = 0;
+        uint64_t sum = 0;
+        {
+            uint64_t a = acc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long idx = p + j;
+                const bool dead = idx < lo;
+                a = dead ? 0ull : ((a << 15) | (uint64_t)(f[j] & 0x7FFFu));
+                if (!dead && (f[j] & 0x8000u)) {
+                    if (idx >= s && idx < e) { ++cnt; sum += a; }
+                    a = 0;
+                }
+            }
+        }
+        uint32_t icnt = cnt;
+        uint64_t isum = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o);
+            uint64_t s2 = __shfl_up_sync(0xffffffffu, isum, o);
+            if (lane >= o) { icnt += c2; isum += s2; }
+        }
+        uint64_t* sc = scan + flip * 2 * kW;
+        if (lane == 31) { sc[warp] = icnt; sc[kW + warp] = isum; }
+        __syncthreads();
+        uint64_t wk = 0, wv = 0, tk = 0, tv = 0;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) {
+            const uint64_t c = sc[w], v = sc[kW + w];
+            if (w < warp) { wk += c; wv += v; }
+            tk += c; tv += v;
+        }
+        uint64_t k = k0 + wk + (icnt - cnt);
+        uint64_t val = v0 + wv + (isum - sum);
+        {
+            uint64_t a = acc;
+            long long ks = kstart;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long idx = p + j;
+                const bool dead = idx < lo;
+                a = dead ? 0ull : ((a << 15) | (uint64_t)(f[j] & 0x7FFFu));
+                if (dead) ks = idx + 1;
+                if (!dead && (f[j] & 0x8000u)) {
+                    if (idx >= s && idx < e) {
+                        val += a;
+                        emit(k, val, a, ks);
+                        ++k;
+                    }
+                    a = 0;
+                    ks = idx + 1;
+                }
+            }
+        }
+        k0 += tk;
+        v0 += tv;
+    }
+}
+
 }  // namespace mbl

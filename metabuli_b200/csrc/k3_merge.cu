@@ -30,28 +30,34 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kQueue = 64;              // per-warp hit queue (power of two, >= 63)
-constexpr uint32_t kLaneMaxCand = 48;        // groups larger than this are worked on by the whole warp
 constexpr uint64_t kNone = ~0ull;
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr uint32_t kEmpty = 0xffffffffu;     // bucket table: no group hashes here
+constexpr uint32_t kEmpty = 0xffffffffu;     // hash table: free slot
 
-// hash table entry = group start (13 bits) << 19 | tag (19 bits).  Bucket and tag come from disjoint bits of a
-// multiplicative hash of the 40-bit amino-acid part; a tag match is verified against the value array.
+// hash table of amino-acid group starts: buckets of two entries, entry = group start (13 bits) << 19 | tag (19 bits).
+// Bucket and tag come from disjoint bits of a multiplicative hash of the 40-bit amino-acid part; a tag match is
+// verified against the value array.
 __device__ __forceinline__ uint32_t aa_hash(uint64_t aa40) { return (uint32_t)((aa40 * 0x9E3779B97F4A7C15ull) >> 32); }
 
 // dynamic shared memory layout (sizes depend on the tile geometry chosen at load time)
 struct SmemLayout {
-    uint32_t off_ham, off_queue, off_frag0, off_frag1, off_vals, off_tab, total;
+    uint32_t off_scan, off_ham, off_queue, off_own, off_bits, off_frag0, off_frag1, off_info, off_vals, off_tab, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets) {
     SmemLayout l;
-    uint32_t o = 32;                                   // two mbarriers + two item slots
+    uint32_t o = 64;                                   // three mbarriers + two item slots
+    l.off_scan = o;   o += 2 * 2 * kWarps * 8;         // block_decode cross-warp scan
     l.off_ham = o;    o += 8192;                       // two-codon table: sum | plain nibble | reversed nibble (u16)
     l.off_queue = o;  o += kWarps * kQueue * 12;       // per-warp hit queues {group start, query dna, query offset}
+    l.off_own = o;    o += kWarps * 32 * 4;            // per-warp, per-hit minimum Hamming sum of the current round
+    l.off_bits = o;   o += ((max_kmers + 63) / 32) * 4;   // bitmap: k-mer starts an amino-acid group
+    o = (o + 15) & ~15u;
     l.off_frag0 = o;  o += (max_u16 + 16) * 2;         // fragment tile, double buffered: the next item's tile is
     l.off_frag1 = o;  o += (max_u16 + 16) * 2;         // in flight (TMA) while the current one is being matched
+    l.off_info = o;   o += (max_kmers + 8) * 4;        // taxids of the current tile
+    o = (o + 15) & ~15u;
     l.off_vals = o;   o += max_kmers * 8;
-    l.off_tab = o;    o += n_buckets * 4;              // open-addressing hash table of amino-acid group starts
+    l.off_tab = o;    o += n_buckets * 4;              // hash table (n_buckets entries = n_buckets / 2 two-entry buckets)
     l.total = (o + 15) & ~15u;
     return l;
 }
@@ -178,25 +184,31 @@ __global__ void __launch_bounds__(kThreads, 3)
 merge_kernel(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = smem_layout(a.max_u16, a.max_kmers, a.n_buckets);
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);          // [2]
-    unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 16);                 // [2]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);          // [0],[1] fragments, [2] taxids
+    unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 32);                 // [2]
+    uint64_t* s_scan = reinterpret_cast<uint64_t*>(smem + L.off_scan);
     uint16_t* s_ham = reinterpret_cast<uint16_t*>(smem + L.off_ham);
     uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + L.off_queue);
+    uint32_t* s_own = reinterpret_cast<uint32_t*>(smem + L.off_own);
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.off_bits);
     uint16_t* s_frag0 = reinterpret_cast<uint16_t*>(smem + L.off_frag0);
-    const uint32_t frag_stride = (L.off_frag1 - L.off_frag0) / 2;     // in u16
+    const uint32_t frag_stride = (L.off_frag1 - L.off_frag0) / 2;                      // in u16
+    int32_t* s_info = reinterpret_cast<int32_t*>(smem + L.off_info);
     uint64_t* s_vals = reinterpret_cast<uint64_t*>(smem + L.off_vals);
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + L.off_tab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 4096; i += kThreads) s_ham[i] = a.ham_pair[i];
-    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
+    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); mbar_init(mbar + 2, 1); }
     __syncthreads();
     unsigned parity_bits = 0u;                        // bit b = phase parity of mbarrier b
     const uint32_t n_items = a.item_off[a.n_tiles];
     const bool fmt2 = a.kmer_format == 2;
-    const uint32_t tab_mask = a.n_buckets - 1;
-    const int hash_shift = 32 - (31 - __clz(a.n_buckets));
+    const uint32_t bucket_mask = a.n_buckets / 2 - 1;
+    const int hash_shift = 32 - (31 - __clz(a.n_buckets / 2));
+    const uint32_t bit_words = (a.max_kmers + 63) / 32;
     uint32_t* my_queue = s_queue + warp * kQueue * 3;
+    uint32_t* my_own = s_own + warp * 32;
     unsigned long long my_matches = 0;
 
     // thread 0: start the TMA copy of an item's fragment tile into buffer `buf`
@@ -222,10 +234,20 @@ merge_kernel(MergeArgs a) {
         const uint32_t nk = tl.n_kmers;
         const bool jumbo = tl.jumbo_off != kNone;
         const uint64_t* vals;
-        const int32_t* infos = a.info + tl.info_begin;
-        // claim the next item and clear the hash table (the previous item's lookups ended at the barrier below)
-        if (tid == 0) s_item[buf ^ 1] = atomicAdd(a.item_cursor, 1u);
+        const int32_t* infos;
+        // claim the next item, clear the hash table and the group-start bitmap (the previous item's lookups ended at the
+        // barrier that closes the loop body), request this tile's taxids
+        if (tid == 0) {
+            s_item[buf ^ 1] = atomicAdd(a.item_cursor, 1u);
+            if (!jumbo) {
+                const uint64_t i0 = tl.info_begin & ~3ull, i1 = (tl.info_begin + nk + 3ull) & ~3ull;
+                fence_proxy_async();
+                mbar_expect_tx(mbar + 2, (unsigned)((i1 - i0) * 4));
+                tma_load_1d(s_info, a.info + i0, (unsigned)((i1 - i0) * 4), mbar + 2);
+            }
+        }
         for (uint32_t x = tid; x < a.n_buckets; x += kThreads) s_tab[x] = kEmpty;
+        for (uint32_t x = tid; x < bit_words; x += kThreads) s_bits[x] = 0u;
         __syncthreads();
         const uint32_t next_item = s_item[buf ^ 1];
         if (tid == 0) stage(next_item, buf ^ 1);             // its tile streams in while this item is decoded and matched
@@ -235,38 +257,43 @@ merge_kernel(MergeArgs a) {
             const uint64_t a0 = d0 & ~7ull;
             mbar_wait(mbar + buf, (parity_bits >> buf) & 1u);
             parity_bits ^= 1u << buf;
-            // -- 2. decode: one warp per checkpoint cell; group starts go into the hash table
-            const uint16_t* frag = s_frag0 + (uint32_t)buf * frag_stride;
-            const uint64_t c0 = d0 / kCellU16, c1 = (d1 + kCellU16 - 1) / kCellU16;
-            for (uint64_t c = c0 + warp; c < c1; c += kWarps) {
-                const uint64_t s_abs = max(c * (uint64_t)kCellU16, d0), e_abs = min((c + 1) * (uint64_t)kCellU16, d1);
-                uint64_t v, k;
-                if (s_abs == d0) { v = tl.base_value; k = tl.info_begin; }
-                else { v = a.cell_v[c]; k = a.cell_k[c]; }
-                const uint64_t kb = tl.info_begin;
-                warp_decode(frag, (long long)(d0 - a0), (long long)(s_abs - a0), (long long)(e_abs - a0), v, k,
-                            [&](uint64_t kk, uint64_t val, uint64_t delta, long long) {
-                                const uint64_t rel = kk - kb;
-                                if (rel >= nk) return;
-                                s_vals[rel] = val;
-                                const uint64_t aa = val >> 24;
-                                if (rel == 0 || ((val - delta) >> 24) != aa) {
-                                    const uint32_t h = aa_hash(aa);
-                                    const uint32_t entry = ((uint32_t)rel << 19) | (h & 0x7FFFFu);
-                                    uint32_t slot = h >> hash_shift;
-                                    while (atomicCAS(&s_tab[slot], kEmpty, entry) != kEmpty) slot = (slot + 1) & tab_mask;
-                                }
-                            });
-            }
+            // -- 2. block-wide decode; every k-mer that starts an amino-acid group is flagged in the bitmap and entered
+            //       into the hash table
+            uint64_t v = tl.base_value, k = tl.info_begin;
+            const uint64_t kb = tl.info_begin;
+            block_decode<kThreads>(s_frag0 + (uint32_t)buf * frag_stride, (long long)(d0 - a0), (long long)(d0 - a0), (long long)(d1 - a0), v, k,
+                                   s_scan, [&](uint64_t kk, uint64_t val, uint64_t delta, long long) {
+                const uint64_t rel = kk - kb;
+                if (rel >= nk) return;
+                s_vals[rel] = val;
+                const uint64_t aa = val >> 24;
+                if (rel == 0 || ((val - delta) >> 24) != aa) {
+                    atomicOr(&s_bits[rel >> 5], 1u << (rel & 31));
+                    const uint32_t h = aa_hash(aa);
+                    const uint32_t entry = ((uint32_t)rel << 19) | (h & 0x7FFFFu);
+                    uint32_t slot = 2u * (h >> hash_shift);
+                    while (true) {
+                        if (atomicCAS(&s_tab[slot], kEmpty, entry) == kEmpty) break;
+                        if (atomicCAS(&s_tab[slot + 1], kEmpty, entry) == kEmpty) break;
+                        slot = (slot + 2) & (2u * bucket_mask + 1u);
+                    }
+                }
+            });
+            mbar_wait(mbar + 2, (parity_bits >> 2) & 1u);
+            parity_bits ^= 4u;
             __syncthreads();
             vals = s_vals;
+            infos = s_info + (tl.info_begin & 3ull);
         } else {
             vals = a.jumbo_vals + tl.jumbo_off;
+            infos = a.info + tl.info_begin;
         }
 
         // -- 3. stream the query slice.  A warp looks up 32 queries per iteration and appends the ones that found
-        //       their amino-acid group ("hits") to its private queue; whenever 32 hits are queued they are processed
-        //       one hit per lane, so every lane of the candidate loops has work.
+        //       their amino-acid group ("hits") to its private queue.  32 queued hits are expanded into their
+        //       (query, candidate) pairs, which are spread evenly over the lanes in batches of 32: sweep 1 finds every
+        //       hit's minimum Hamming sum, sweep 2 keeps the candidates with sum <= min(2*min, 7) (KmerMatcher.cpp:1117-
+        //       1146) and writes them, ballot-compacted, as coalesced 24-byte Match rows.
         uint32_t q_head = 0, q_count = 0;
         auto process_hits = [&](uint32_t m) {
             const bool valid = (uint32_t)lane < m;
@@ -276,111 +303,80 @@ merge_kernel(MergeArgs a) {
             const uint32_t qoff = valid ? rec[2] : 0u;                              // query index relative to the item
             q_head = (q_head + m) & (kQueue - 1);
             q_count -= m;
-            const uint64_t aa = valid ? vals[g0] >> 24 : 0ull;
-            // pass A: size of the group (capped) and the run of candidates equal to the query value.  Candidates are
-            // sorted by value, Hamming sum 0 <=> identical DNA part (the distance table is 0 only on its diagonal),
-            // so when such a run exists min = 0, maxHamming = 0 and the survivors are exactly that run.
-            uint32_t n = 0, ex0 = 0, exn = 0;
-            bool open_end = valid;
-            for (uint32_t c = 0; c <= kLaneMaxCand; ++c) {
-                if (open_end) {
-                    const uint32_t j = g0 + c;
-                    const uint64_t v = j < nk ? vals[j] : ~0ull;
-                    if ((v >> 24) != aa) { open_end = false; }
-                    else {
-                        n = c + 1;
-                        if (((uint32_t)v & 0xFFFFFFu) == qd) { if (!exn) ex0 = j; ++exn; }
-                    }
-                }
-                if (!__any_sync(kFull, open_end)) break;
-            }
-            // (a) oversized groups (still open after the cap): the whole warp works on one hit at a time
-            uint32_t big = __ballot_sync(kFull, open_end);
-            while (big) {
-                const int src = __ffs(big) - 1;
-                big &= big - 1;
-                const uint32_t bg0 = __shfl_sync(kFull, g0, src);
-                const uint32_t bqd = __shfl_sync(kFull, qd, src), bqoff = __shfl_sync(kFull, qoff, src);
-                const uint64_t baa = __shfl_sync(kFull, aa, src);
-                uint32_t bn = 0;                                  // group size, found cooperatively
-                for (uint32_t cb = 0;; cb += 32) {
-                    const uint32_t j = bg0 + cb + lane;
-                    const bool in = j < nk && (vals[j] >> 24) == baa;
-                    const uint32_t bal = __ballot_sync(kFull, in);
-                    bn += __popc(bal);
-                    if (bal != kFull) break;
-                }
-                uint32_t mn = 255u;
-                for (uint32_t c = lane; c < bn; c += 32) mn = min(mn, ham_sum(ham_lookup(s_ham, bqd, (uint32_t)vals[bg0 + c] & 0xFFFFFFu)));
-                mn = __reduce_min_sync(kFull, mn);
-                const uint32_t maxH = min(mn * 2u, 7u);
-                const uint64_t qinfo = load_qinfo(a, it.q_begin + bqoff);
-                const bool plain = !((qi_frame(qinfo) < 3) ^ fmt2);
-                for (uint32_t cb = 0; cb < bn; cb += 32) {
-                    const uint32_t c = cb + lane;
-                    const uint32_t td = c < bn ? (uint32_t)vals[bg0 + c] & 0xFFFFFFu : 0u;
-                    const HamQuad hq = ham_lookup(s_ham, bqd, td);
-                    const uint32_t sum = ham_sum(hq);
-                    const bool sel = c < bn && sum <= maxH;
-                    const uint32_t bal = __ballot_sync(kFull, sel);
-                    if (!bal) continue;
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(a.out_count, (unsigned long long)__popc(bal));
-                    base = __shfl_sync(kFull, base, 0);
-                    if (sel) emit_match(a, base + __popc(bal & ((1u << lane) - 1)), qinfo, infos[bg0 + c], td, ham_fields(hq, bqd, td, plain), sum);
-                    my_matches += __popc(bal);
-                }
-                if (lane == src) { n = 0; exn = 0; }
-            }
-            // (b) hits without an exact run: minimum Hamming sum, then the survivors (KmerMatcher.cpp:1117-1146)
-            const uint32_t ne = exn ? 0u : n;                     // candidates this lane still has to evaluate
-            uint32_t nmax = ne;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(kFull, nmax, o));
-            uint32_t mn = 255u;
-            uint64_t nib = 0;                                     // sums of the first 16 candidates, 4 bits each
-            for (uint32_t c = 0; c < nmax; ++c) {
-                if (c < ne) {
-                    const uint32_t sm = ham_sum(ham_lookup(s_ham, qd, (uint32_t)vals[g0 + c] & 0xFFFFFFu));
-                    mn = min(mn, sm);
-                    if (c < 16) nib |= (uint64_t)min(sm, 15u) << (4 * c);
+            // group size = distance to the next group start
+            uint32_t n = 0;
+            if (valid) {
+                if (!jumbo) {
+                    uint32_t w = (g0 + 1) >> 5;
+                    uint32_t bits = w < bit_words ? s_bits[w] & (0xffffffffu << ((g0 + 1) & 31)) : 0u;
+                    while (!bits && ++w < bit_words) bits = s_bits[w];
+                    const uint32_t nxt = bits ? (w << 5) + (uint32_t)__ffs(bits) - 1u : nk;
+                    n = min(nxt, nk) - g0;
+                } else {
+                    const uint64_t aa = vals[g0] >> 24;
+                    uint32_t j = g0 + 1;
+                    while (j < nk && (vals[j] >> 24) == aa) ++j;
+                    n = j - g0;
                 }
             }
-            const uint32_t maxH = min(mn * 2u, 7u);                                     // KmerMatcher.cpp:1136
-            uint32_t cnt = exn;
-            for (uint32_t c = 0; c < nmax; ++c) {
-                if (c < ne) {
-                    const uint32_t sm = c < 16 ? (uint32_t)(nib >> (4 * c)) & 15u
-                                               : ham_sum(ham_lookup(s_ham, qd, (uint32_t)vals[g0 + c] & 0xFFFFFFu));
-                    cnt += sm <= maxH;
-                }
-            }
-            uint32_t incl = cnt;
+            uint32_t incl = n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
             const uint32_t total = __shfl_sync(kFull, incl, 31);
-            if (total == 0) return;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.out_count, (unsigned long long)total);
-            base = __shfl_sync(kFull, base, 0) + (incl - cnt);
-            my_matches += total;
-            uint64_t qinfo = 0;
-            bool plain = true;
-            if (cnt) { qinfo = load_qinfo(a, it.q_begin + qoff); plain = !((qi_frame(qinfo) < 3) ^ fmt2); }   // KmerMatcher.cpp:1140
-            // exact runs: Hamming 0, all per-codon fields 0
-            uint32_t xmax = exn;
+            const uint32_t excl = incl - n;
+            my_own[lane] = 255u;
+            __syncwarp();
+            // sweep 1: per-hit minimum (an identical DNA part is the only way to distance 0)
+            for (uint32_t pb = 0; pb < total; pb += 32) {
+                const uint32_t p = pb + lane;
+                const bool pv = p < total;
+                uint32_t o = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) xmax = max(xmax, __shfl_xor_sync(kFull, xmax, o));
-            for (uint32_t c = 0; c < xmax; ++c)
-                if (c < exn) { emit_match(a, base, qinfo, infos[ex0 + c], qd, 0u, 0u); ++base; }
-            for (uint32_t c = 0; c < nmax; ++c) {
-                if (c < ne && cnt) {
-                    const uint32_t td = (uint32_t)vals[g0 + c] & 0xFFFFFFu;
-                    const HamQuad hq = ham_lookup(s_ham, qd, td);
-                    const uint32_t sum = ham_sum(hq);
-                    if (sum <= maxH) { emit_match(a, base, qinfo, infos[g0 + c], td, ham_fields(hq, qd, td, plain), sum); ++base; }
+                for (int st = 16; st > 0; st >>= 1) { const uint32_t t = __shfl_sync(kFull, incl, (o + st - 1) & 31); if (t <= p) o += st; }
+                o &= 31u;
+                const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
+                const uint32_t oq = __shfl_sync(kFull, qd, o);
+                uint32_t sum = 255u;
+                if (pv) {
+                    const uint32_t td = (uint32_t)vals[j] & 0xFFFFFFu;
+                    sum = td == oq ? 0u : ham_sum(ham_lookup(s_ham, oq, td));
                 }
+                const uint32_t grp = __match_any_sync(kFull, pv ? o : 32u + lane);
+                const uint32_t mn = __reduce_min_sync(grp, sum);
+                if (pv && (grp & ((1u << lane) - 1)) == 0) my_own[o] = min(my_own[o], mn);
+                __syncwarp();
             }
+            // sweep 2: survivors
+            for (uint32_t pb = 0; pb < total; pb += 32) {
+                const uint32_t p = pb + lane;
+                const bool pv = p < total;
+                uint32_t o = 0;
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1) { const uint32_t t = __shfl_sync(kFull, incl, (o + st - 1) & 31); if (t <= p) o += st; }
+                o &= 31u;
+                const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
+                const uint32_t oq = __shfl_sync(kFull, qd, o);
+                const uint32_t ooff = __shfl_sync(kFull, qoff, o);
+                uint32_t td = 0, sum = 255u;
+                HamQuad hq{0u, 0u, 0u, 0u};
+                if (pv) {
+                    td = (uint32_t)vals[j] & 0xFFFFFFu;
+                    if (td == oq) sum = 0u; else { hq = ham_lookup(s_ham, oq, td); sum = ham_sum(hq); }
+                }
+                const bool sel = pv && sum <= min(my_own[o] * 2u, 7u);                  // KmerMatcher.cpp:1136
+                const uint32_t bal = __ballot_sync(kFull, sel);
+                if (!bal) continue;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.out_count, (unsigned long long)__popc(bal));
+                base = __shfl_sync(kFull, base, 0);
+                if (sel) {
+                    const uint64_t qinfo = load_qinfo(a, it.q_begin + ooff);
+                    const bool plain = !((qi_frame(qinfo) < 3) ^ fmt2);                 // KmerMatcher.cpp:1140
+                    emit_match(a, base + __popc(bal & ((1u << lane) - 1)), qinfo, infos[j], td, sum ? ham_fields(hq, oq, td, plain) : 0u, sum);
+                }
+                my_matches += __popc(bal);
+            }
+            __syncwarp();
         };
 
         for (uint64_t qb = it.q_begin + (uint64_t)warp * 32; qb < it.q_end; qb += kThreads) {
@@ -394,9 +390,14 @@ merge_kernel(MergeArgs a) {
                 if (active) {
                     const uint32_t h = aa_hash(q40);
                     const uint32_t tag = h & 0x7FFFFu;
-                    uint32_t slot = h >> hash_shift;
-                    for (uint32_t e = s_tab[slot]; e != kEmpty; e = s_tab[slot = (slot + 1) & tab_mask]) {
-                        if ((e & 0x7FFFFu) == tag && (vals[e >> 19] >> 24) == q40) { g0 = e >> 19; hit = true; break; }
+                    uint32_t bkt = h >> hash_shift;
+                    while (true) {
+                        const uint2 e = *reinterpret_cast<const uint2*>(s_tab + 2u * bkt);
+                        if (e.x == kEmpty) break;
+                        if ((e.x & 0x7FFFFu) == tag && (vals[e.x >> 19] >> 24) == q40) { g0 = e.x >> 19; hit = true; break; }
+                        if (e.y == kEmpty) break;
+                        if ((e.y & 0x7FFFFu) == tag && (vals[e.y >> 19] >> 24) == q40) { g0 = e.y >> 19; hit = true; break; }
+                        bkt = (bkt + 1) & bucket_mask;
                     }
                 }
             } else if (active) {
@@ -412,10 +413,10 @@ merge_kernel(MergeArgs a) {
                 }
                 q_count += __popc(bal);
                 __syncwarp();
-                if (q_count >= 32) { process_hits(32); __syncwarp(); }
+                if (q_count >= 32) process_hits(32);
             }
         }
-        if (q_count) { process_hits(q_count); __syncwarp(); }
+        if (q_count) process_hits(q_count);
         __syncthreads();
         item = next_item;
         buf ^= 1;
