@@ -105,54 +105,60 @@ __device__ __forceinline__ void warp_decode(const uint16_t* frag, long long lo, 
 
 
 // Block-wide variant for the merge kernel: all kThreadsDecode threads take one octet each (2048 fragments per
-// sweep), so a tile of a few KiB keeps every warp busy and needs no per-cell checkpoints.  Same octet logic as
-// warp_decode; the (count, sum) pairs are scanned inside each warp with shuffles and across warps through a tiny
-// double-buffered shared array (one __syncthreads per sweep).  `scan` must hold 2 * 2 * (threads/32) uint64_t.
-// All threads of the block must call; v0 / k0 are block-uniform running totals.
+// sweep), so a tile of a few KiB keeps every warp busy and needs no per-cell checkpoints.  The (count, sum) pairs
+// are scanned inside each warp with shuffles and across warps through a tiny double-buffered shared array (one
+// __syncthreads per sweep).  `scan` must hold 2 * 2 * (threads/32) uint64_t.  Indices are 32-bit (a tile is a
+// few thousand fragments); octets that lie completely inside [s, e) with their look-back inside [lo, ...) take a
+// path without per-element range tests.  All threads of the block must call; v0 / k0 are block-uniform totals.
+// emit(k, value, delta) — no first-fragment index here.
 template <int kThreadsDecode, class Emit>
-__device__ __forceinline__ void block_decode(const uint16_t* frag, long long lo, long long s, long long e, uint64_t& v0, uint64_t& k0,
-                                             uint64_t* scan, Emit emit) {
+__device__ __forceinline__ void block_decode(const uint16_t* frag, int lo, int s, int e, uint64_t& v0, uint64_t& k0, uint64_t* scan, Emit emit) {
     constexpr int kW = kThreadsDecode / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int flip = 0;
-    for (long long p0 = s & ~7ll; p0 < e; p0 += 8ll * kThreadsDecode, flip ^= 1) {
-        const long long p = p0 + 8ll * threadIdx.x;
-        uint16_t f[8];
-        uint16_t lb[4];
+    for (int p0 = s & ~7; p0 < e; p0 += 8 * kThreadsDecode, flip ^= 1) {
+        const int p = p0 + 8 * (int)threadIdx.x;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};          // the octet as four pairs of fragments
+        uint32_t l0 = 0x80008000u, l1 = 0x80008000u;   // look-back quartet (cuts when unavailable)
         if (p < e) {
-            uint4 v = *reinterpret_cast<const uint4*>(frag + p);
-            f[0] = (uint16_t)v.x; f[1] = (uint16_t)(v.x >> 16); f[2] = (uint16_t)v.y; f[3] = (uint16_t)(v.y >> 16);
-            f[4] = (uint16_t)v.z; f[5] = (uint16_t)(v.z >> 16); f[6] = (uint16_t)v.w; f[7] = (uint16_t)(v.w >> 16);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = 0;
+            const uint4 v = *reinterpret_cast<const uint4*>(frag + p);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            if (p >= 4 && p - 4 >= (lo & ~3)) { const uint2 b = *reinterpret_cast<const uint2*>(frag + p - 4); l0 = b.x; l1 = b.y; }
         }
-        if (p < e && p - 4 >= (lo & ~3ll) && p >= 4) {
-            uint2 v = *reinterpret_cast<const uint2*>(frag + p - 4);
-            lb[0] = (uint16_t)v.x; lb[1] = (uint16_t)(v.x >> 16); lb[2] = (uint16_t)v.y; lb[3] = (uint16_t)(v.y >> 16);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) lb[j] = 0x8000u;
-        }
+        const bool inner = p >= s && p + 8 <= e && p - 4 >= lo;
         uint64_t acc = 0;
-        long long kstart = p - 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long long idx = p - 4 + j;
-            const bool cut = (lb[j] & 0x8000u) || idx < lo;
-            acc = cut ? 0ull : ((acc << 15) | lb[j]);
-            if (cut) kstart = idx + 1;
-        }
         uint32_t cnt = 0;
         uint64_t sum = 0;
-        {
+        if (inner) {
+            // incoming partial delta: fragments after the last end flag of the look-back quartet
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t fr = ((j & 2 ? l1 : l0) >> (16 * (j & 1))) & 0xFFFFu;
+                acc = (fr & 0x8000u) ? 0ull : ((acc << 15) | fr);
+            }
             uint64_t a = acc;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const long long idx = p + j;
+                const uint32_t fr = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                a = (a << 15) | (uint64_t)(fr & 0x7FFFu);
+                if (fr & 0x8000u) { ++cnt; sum += a; a = 0; }
+            }
+        } else if (p < e) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = p - 4 + j;
+                const uint32_t fr = ((j & 2 ? l1 : l0) >> (16 * (j & 1))) & 0xFFFFu;
+                const bool cut = (fr & 0x8000u) || idx < lo;
+                acc = cut ? 0ull : ((acc << 15) | fr);
+            }
+            uint64_t a = acc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = p + j;
+                const uint32_t fr = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
                 const bool dead = idx < lo;
-                a = dead ? 0ull : ((a << 15) | (uint64_t)(f[j] & 0x7FFFu));
-                if (!dead && (f[j] & 0x8000u)) {
+                a = dead ? 0ull : ((a << 15) | (uint64_t)(fr & 0x7FFFu));
+                if (!dead && (fr & 0x8000u)) {
                     if (idx >= s && idx < e) { ++cnt; sum += a; }
                     a = 0;
                 }
@@ -162,8 +168,8 @@ __device__ __forceinline__ void block_decode(const uint16_t* frag, long long lo,
         uint64_t isum = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o);
-            uint64_t s2 = __shfl_up_sync(0xffffffffu, isum, o);
+            const uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o);
+            const uint64_t s2 = __shfl_up_sync(0xffffffffu, isum, o);
             if (lane >= o) { icnt += c2; isum += s2; }
         }
         uint64_t* sc = scan + flip * 2 * kW;
@@ -171,30 +177,28 @@ __device__ __forceinline__ void block_decode(const uint16_t* frag, long long lo,
         __syncthreads();
         uint64_t wk = 0, wv = 0, tk = 0, tv = 0;
 #pragma unroll
-        for (int w = 0; w < kW; ++w) {
-            const uint64_t c = sc[w], v = sc[kW + w];
-            if (w < warp) { wk += c; wv += v; }
+        for (int x = 0; x < kW; ++x) {
+            const uint64_t c = sc[x], v = sc[kW + x];
+            if (x < warp) { wk += c; wv += v; }
             tk += c; tv += v;
         }
         uint64_t k = k0 + wk + (icnt - cnt);
         uint64_t val = v0 + wv + (isum - sum);
-        {
+        if (cnt) {
             uint64_t a = acc;
-            long long ks = kstart;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const long long idx = p + j;
-                const bool dead = idx < lo;
-                a = dead ? 0ull : ((a << 15) | (uint64_t)(f[j] & 0x7FFFu));
-                if (dead) ks = idx + 1;
-                if (!dead && (f[j] & 0x8000u)) {
-                    if (idx >= s && idx < e) {
+                const int idx = p + j;
+                const uint32_t fr = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                const bool dead = !inner && idx < lo;
+                a = dead ? 0ull : ((a << 15) | (uint64_t)(fr & 0x7FFFu));
+                if (!dead && (fr & 0x8000u)) {
+                    if (inner || (idx >= s && idx < e)) {
                         val += a;
-                        emit(k, val, a, ks);
+                        emit(k, val, a);
                         ++k;
                     }
                     a = 0;
-                    ks = idx + 1;
                 }
             }
         }

@@ -30,6 +30,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kQueue = 64;              // per-warp hit queue (power of two, >= 63)
+constexpr uint32_t kOutChunk = 1024;         // match slots a warp reserves from the global cursor at a time
 constexpr uint64_t kNone = ~0ull;
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kEmpty = 0xffffffffu;     // hash table: free slot
@@ -118,6 +119,31 @@ __device__ __forceinline__ uint32_t ham_fields(const HamQuad& h, uint32_t q, uin
 
 __device__ __forceinline__ uint64_t load_qinfo(const MergeArgs& a, uint64_t sorted_pos) {
     return a.q_info[a.q_idx ? (uint64_t)a.q_idx[sorted_pos] : sorted_pos];
+}
+
+// Output slots: a single global cursor would serialise ~10^7 atomics per launch, so every warp reserves kOutChunk
+// slots at a time and hands them out locally; a request that does not fit is split across the old and the new chunk.
+// What is left of the last chunk at kernel end is filled with blank records (seqID 0), which sort first and are
+// ignored downstream.
+struct OutChunk { uint64_t base = 0; uint32_t used = kOutChunk; };
+struct Reservation { uint64_t old_base, new_base; uint32_t old_used, rem; };
+__device__ __forceinline__ Reservation reserve(OutChunk& c, uint32_t cnt, unsigned long long* cursor, int lane) {
+    Reservation r;
+    r.old_base = c.base; r.old_used = c.used; r.rem = kOutChunk - c.used; r.new_base = 0;
+    if (cnt > r.rem) {
+        const uint32_t need = max(kOutChunk, cnt - r.rem);
+        unsigned long long nb = 0;
+        if (lane == 0) nb = atomicAdd(cursor, (unsigned long long)need);
+        r.new_base = __shfl_sync(kFull, nb, 0);
+        c.base = r.new_base;
+        c.used = (cnt - r.rem > kOutChunk) ? kOutChunk : cnt - r.rem;
+    } else {
+        c.used += cnt;
+    }
+    return r;
+}
+__device__ __forceinline__ uint64_t slot_of(const Reservation& r, uint32_t i) {
+    return i < r.rem ? r.old_base + r.old_used + i : r.new_base + (i - r.rem);
 }
 
 // one 24-byte Match record (Match.h:9-26 without the vptr); Q2: taxid 0 / unmapped species raise the error flag
@@ -210,6 +236,7 @@ merge_kernel(MergeArgs a) {
     uint32_t* my_queue = s_queue + warp * kQueue * 3;
     uint32_t* my_own = s_own + warp * 32;
     unsigned long long my_matches = 0;
+    OutChunk chunk;
 
     // thread 0: start the TMA copy of an item's fragment tile into buffer `buf`
     auto stage = [&](uint32_t item, int buf) {
@@ -261,8 +288,8 @@ merge_kernel(MergeArgs a) {
             //       into the hash table
             uint64_t v = tl.base_value, k = tl.info_begin;
             const uint64_t kb = tl.info_begin;
-            block_decode<kThreads>(s_frag0 + (uint32_t)buf * frag_stride, (long long)(d0 - a0), (long long)(d0 - a0), (long long)(d1 - a0), v, k,
-                                   s_scan, [&](uint64_t kk, uint64_t val, uint64_t delta, long long) {
+            block_decode<kThreads>(s_frag0 + (uint32_t)buf * frag_stride, (int)(d0 - a0), (int)(d0 - a0), (int)(d1 - a0), v, k,
+                                   s_scan, [&](uint64_t kk, uint64_t val, uint64_t delta) {
                 const uint64_t rel = kk - kb;
                 if (rel >= nk) return;
                 s_vals[rel] = val;
@@ -341,9 +368,7 @@ merge_kernel(MergeArgs a) {
                     const uint32_t td = (uint32_t)vals[j] & 0xFFFFFFu;
                     sum = td == oq ? 0u : ham_sum(ham_lookup(s_ham, oq, td));
                 }
-                const uint32_t grp = __match_any_sync(kFull, pv ? o : 32u + lane);
-                const uint32_t mn = __reduce_min_sync(grp, sum);
-                if (pv && (grp & ((1u << lane) - 1)) == 0) my_own[o] = min(my_own[o], mn);
+                if (pv) atomicMin(&my_own[o], sum);
                 __syncwarp();
             }
             // sweep 2: survivors
@@ -366,13 +391,11 @@ merge_kernel(MergeArgs a) {
                 const bool sel = pv && sum <= min(my_own[o] * 2u, 7u);                  // KmerMatcher.cpp:1136
                 const uint32_t bal = __ballot_sync(kFull, sel);
                 if (!bal) continue;
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.out_count, (unsigned long long)__popc(bal));
-                base = __shfl_sync(kFull, base, 0);
+                const Reservation rs = reserve(chunk, __popc(bal), a.out_count, lane);
                 if (sel) {
                     const uint64_t qinfo = load_qinfo(a, it.q_begin + ooff);
                     const bool plain = !((qi_frame(qinfo) < 3) ^ fmt2);                 // KmerMatcher.cpp:1140
-                    emit_match(a, base + __popc(bal & ((1u << lane) - 1)), qinfo, infos[j], td, sum ? ham_fields(hq, oq, td, plain) : 0u, sum);
+                    emit_match(a, slot_of(rs, __popc(bal & ((1u << lane) - 1))), qinfo, infos[j], td, sum ? ham_fields(hq, oq, td, plain) : 0u, sum);
                 }
                 my_matches += __popc(bal);
             }
@@ -420,6 +443,16 @@ merge_kernel(MergeArgs a) {
         __syncthreads();
         item = next_item;
         buf ^= 1;
+    }
+    // blank out the unused tail of the warp's last chunk (seqID 0 == not a match)
+    if (chunk.used < kOutChunk) {
+        for (uint32_t w = chunk.used + lane; w < kOutChunk; w += 32) {
+            const uint64_t slot = chunk.base + w;
+            if (slot < a.out_cap) {
+                uint64_t* o = reinterpret_cast<uint64_t*>(a.out + slot);
+                o[0] = 0; o[1] = 0; o[2] = 0;
+            }
+        }
     }
     if (lane == 0 && my_matches) atomicAdd(a.out_count + 1, my_matches);
 }

@@ -2,6 +2,8 @@
 // Taxonomer.cpp).  One read per thread over the match list sorted in the reference's order; the
 // algorithm itself is in score_core.cuh (shared with the CPU unit tests).  Read-level parallelism is
 // ample (10^6-10^7 reads per batch); all state is in HBM scratch sized by the match count.
+#include <cub/cub.cuh>
+
 #include "score_core.cuh"
 
 namespace mbl {
@@ -10,6 +12,57 @@ __global__ void __launch_bounds__(128, 4) score_kernel(ScoreArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_reads) return;
     score_read(a, a.read_perm ? a.read_perm[a.read_begin + i] : a.read_begin + i);
+}
+
+// ---- flat pipeline ---------------------------------------------------------------------------------------------
+__global__ void score_mark_kernel(const mbl_match_rec* __restrict__ m, uint64_t begin, uint64_t end, uint8_t* __restrict__ flag_fg,
+                                  uint8_t* __restrict__ flag_sp) {
+    const uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    bool sp = true, fg = true;
+    if (i > begin) {
+        const uint64_t q = m[i].qinfo, pq = m[i - 1].qinfo;
+        sp = qi_seq(q) != qi_seq(pq) || m[i].species_id != m[i - 1].species_id;
+        fg = sp || qi_frame(q) != qi_frame(pq);
+    }
+    flag_sp[i - begin] = sp;
+    flag_fg[i - begin] = fg;
+}
+__global__ void __launch_bounds__(128, 4) score_fg_kernel(ScoreArgs a) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < a.n_fg) score_task_frame_group(a, g);
+}
+__global__ void __launch_bounds__(128, 4) score_sp_kernel(ScoreArgs a) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < a.n_sp) score_task_species(a, s);
+}
+
+size_t score_flat_temp_bytes(size_t n) {
+    size_t bytes = 0;
+    cub::DeviceSelect::Flagged(nullptr, bytes, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)nullptr, (uint32_t*)nullptr,
+                               (uint32_t*)nullptr, (long long)n);
+    return bytes;
+}
+
+void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch& s, cudaStream_t st) {
+    const uint64_t n = a.match_end - match_begin;
+    if (a.n_reads == 0) return;
+    uint32_t h_counts[2] = {0, 0};
+    if (n) {
+        score_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.matches, match_begin, a.match_end, s.flags_fg, s.flags_sp);
+        size_t tb = s.cub_tmp_bytes;
+        MBL_CUDA(cub::DeviceSelect::Flagged(s.cub_tmp, tb, cub::CountingInputIterator<uint32_t>((uint32_t)match_begin), s.flags_fg, s.fg_list,
+                                            s.counts, (long long)n, st));
+        tb = s.cub_tmp_bytes;
+        MBL_CUDA(cub::DeviceSelect::Flagged(s.cub_tmp, tb, cub::CountingInputIterator<uint32_t>((uint32_t)match_begin), s.flags_sp, s.sp_list,
+                                            s.counts + 1, (long long)n, st));
+        MBL_CUDA(cudaMemcpyAsync(h_counts, s.counts, 8, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+    }
+    a.fg_list = s.fg_list; a.n_fg = h_counts[0]; a.sp_list = s.sp_list; a.n_sp = h_counts[1];
+    if (a.n_fg) score_fg_kernel<<<(a.n_fg + 127) / 128, 128, 0, st>>>(a);
+    if (a.n_sp) score_sp_kernel<<<(a.n_sp + 127) / 128, 128, 0, st>>>(a);
+    score_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);
 }
 
 __global__ void taxcnt_len_kernel(const mbl_read_result* __restrict__ res, uint32_t n, uint32_t* __restrict__ len) {

@@ -125,6 +125,8 @@ struct ScoreArgs {
     float* l_score; int32_t* l_start; int32_t* l_ham; int32_t* l_depth; uint32_t* l_smatch; uint8_t* l_conn;
     int32_t* p_start; int32_t* p_end; float* p_score; int32_t* p_ham; int32_t* p_depth; uint32_t* p_smatch; uint32_t* p_ematch;
     int32_t* c_start; int32_t* c_end; float* s_score;
+    // flat task lists (first match index of every (species, frame) group / (read, species) group); optional
+    const uint32_t* fg_list; uint32_t n_fg; const uint32_t* sp_list; uint32_t n_sp; uint32_t* g_np; uint64_t match_end;
     // scratch, per quotient
     int32_t* q_tax; uint8_t* q_ham; uint8_t* q_has;
     // outputs
@@ -132,6 +134,10 @@ struct ScoreArgs {
     int32_t* taxcnt_pairs;          // 2 x int32 per entry, region of a read starts at quot_off[r]
 };
 void launch_score(const ScoreArgs& a, cudaStream_t st);
+// flat pipeline over the matches [match_begin, a.match_end) of the reads [a.read_begin, +a.n_reads)
+struct ScoreFlatScratch { uint8_t* flags_fg; uint8_t* flags_sp; uint32_t* fg_list; uint32_t* sp_list; uint32_t* counts; void* cub_tmp; size_t cub_tmp_bytes; };
+size_t score_flat_temp_bytes(size_t n_matches);
+void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch& s, cudaStream_t st);
 void launch_compact_taxcnt(const mbl_read_result* results, uint32_t n_reads, const uint32_t* quot_off,
                            const int32_t* pairs_in, const uint32_t* out_off, int32_t* pairs_out, mbl_read_result* results_out,
                            cudaStream_t st);

@@ -65,7 +65,7 @@ struct mbl_ctx {
     // workspace
     Buf cov1, cov2, w1, w2, slots, slot_off, quot_cnt, quot_off, seg_b, seg_e, res_sub, tax_len, tax_off;
     Buf val_a, val_b, qi_a, qi_b, cub_tmp;
-    Buf arena, chunk_bounds, order_keys;     // phase 1: k-mer keys/payloads (32 B per slot); phase 2: match sort buffers
+    Buf arena, chunk_bounds, order_keys, g_np, flag_fg, flag_sp, fg_list, sp_list, flat_tmp;     // phase 1: k-mer keys/payloads (32 B per slot); phase 2: match sort buffers
     Buf m_raw, m_sorted, key_a, key_b, idx_a, idx_b;
     Buf l_score, l_start, l_ham, l_depth, l_smatch, l_conn, p_start, p_end, p_score, p_ham, p_depth, p_smatch, p_ematch,
         c_start, c_end, s_score;
@@ -353,6 +353,12 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         uint8_t* l_conn = c->l_conn.get<uint8_t>(Mp);
         int32_t *p_start = c->p_start.get<int32_t>(Mp), *p_end = c->p_end.get<int32_t>(Mp), *p_ham = c->p_ham.get<int32_t>(Mp),
                 *p_depth = c->p_depth.get<int32_t>(Mp), *c_start = c->c_start.get<int32_t>(Mp), *c_end = c->c_end.get<int32_t>(Mp);
+        uint32_t* g_np = c->g_np.get<uint32_t>(Mp);
+        ScoreFlatScratch flat{};
+        flat.flags_fg = c->flag_fg.get<uint8_t>(Mp); flat.flags_sp = c->flag_sp.get<uint8_t>(Mp);
+        flat.fg_list = c->fg_list.get<uint32_t>(Mp); flat.sp_list = c->sp_list.get<uint32_t>(Mp);
+        flat.counts = reinterpret_cast<uint32_t*>(c->counters.get<unsigned long long>(8)) + 12;
+        flat.cub_tmp = c->flat_tmp.get<uint8_t>(score_flat_temp_bytes(Mp)); flat.cub_tmp_bytes = c->flat_tmp.cap;
         for (uint32_t k = 0; k < n_chunks; ++k) {
             const uint64_t f = bounds[k];                 // scratch is indexed by (match index - f)
             sa.read_begin = k * chunk_reads;
@@ -361,8 +367,10 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
             sa.l_conn = l_conn - f; sa.p_start = p_start - f; sa.p_end = p_end - f; sa.p_score = p_score - f; sa.p_ham = p_ham - f;
             sa.p_depth = p_depth - f; sa.p_smatch = p_smatch - f; sa.p_ematch = p_ematch - f; sa.c_start = c_start - f; sa.c_end = c_end - f;
             sa.s_score = s_score - f;
-            launch_score(sa, st);
-            c->stats.kernel_launches += 1;
+            sa.g_np = g_np - f;
+            sa.match_end = bounds[k + 1];
+            launch_score_flat(sa, f, flat, st);
+            c->stats.kernel_launches += 4;
         }
         // compact the (taxid,count) lists behind the pairs of earlier sub-batches
         uint32_t *tl = c->tax_len.get<uint32_t>(n + 1), *to = c->tax_off.get<uint32_t>(n + 1);
@@ -437,7 +445,7 @@ void mbl_destroy(mbl_ctx* c) {
     free_db(c);
     for (Buf* b : {&c->bases1, &c->bases2, &c->off1, &c->off2, &c->cov1, &c->cov2, &c->w1, &c->w2, &c->slots, &c->slot_off, &c->quot_cnt,
                    &c->quot_off, &c->seg_b, &c->seg_e, &c->res_sub, &c->tax_len, &c->tax_off, &c->val_a, &c->val_b, &c->qi_a, &c->qi_b,
-                   &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->order_keys, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
+                   &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->order_keys, &c->g_np, &c->flag_fg, &c->flag_sp, &c->fg_list, &c->sp_list, &c->flat_tmp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
                    &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score, &c->p_ham, &c->p_depth, &c->p_smatch,
                    &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw, &c->q_lo,
                    &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs})

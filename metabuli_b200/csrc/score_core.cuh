@@ -205,8 +205,8 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
         a.p_start[o] = c.start;
         a.p_end[o] = (int32_t)qi_pos(ml[i].qinfo) + 23;
         a.p_score[o] = c.score; a.p_ham[o] = c.ham; a.p_depth[o] = c.depth;
-        a.p_smatch[o] = (uint32_t)(gs - pbase) + c.smatch;
-        a.p_ematch[o] = (uint32_t)(i - pbase);
+        a.p_smatch[o] = (uint32_t)(gs + c.smatch);                // absolute match indices
+        a.p_ematch[o] = (uint32_t)i;
     };
     uint64_t i = gs;
     uint64_t curPos = qi_pos(ml[gs].qinfo);
@@ -285,8 +285,8 @@ MBL_HD void score_frame_group(const ScoreArgs& a, uint64_t gs, uint64_t ge, int 
         a.p_score[o] = a.l_score[i];
         a.p_ham[o] = a.l_ham[i];
         a.p_depth[o] = a.l_depth[i];
-        a.p_smatch[o] = (uint32_t)(gs - pbase) + a.l_smatch[i];   // match index relative to pbase
-        a.p_ematch[o] = (uint32_t)(i - pbase);
+        a.p_smatch[o] = (uint32_t)(gs + a.l_smatch[i]);           // absolute match indices
+        a.p_ematch[o] = (uint32_t)i;
     };
     uint64_t i = gs;
     uint64_t curPos = qi_pos(ml[gs].qinfo);
@@ -336,9 +336,11 @@ MBL_HD void score_frame_group(const ScoreArgs& a, uint64_t gs, uint64_t ge, int 
 }
 
 // ---- combineMatchPaths for the np paths of one species at pbase (Taxonomer.cpp:410-468) ------------------
-MBL_HD float score_combine(const ScoreArgs& a, uint64_t pbase, uint32_t np, int read_length) {
-    int32_t* perm = a.l_start + pbase;          // the DP scratch is free now; np <= matches of the species
-    for (uint32_t i = 0; i < np; ++i) perm[i] = (int32_t)i;
+// `perm` (at a.l_start + pbase: the DP scratch is free by now, np <= matches of the species) lists the paths of the
+// species as offsets from pbase in the order the reference generated them; perm_ready says it is already filled.
+MBL_HD float score_combine(const ScoreArgs& a, uint64_t pbase, uint32_t np, int read_length, bool perm_ready = false) {
+    int32_t* perm = a.l_start + pbase;
+    if (!perm_ready) for (uint32_t i = 0; i < np; ++i) perm[i] = (int32_t)i;
     const float* ps = a.p_score + pbase;
     const int32_t* ph = a.p_ham + pbase;
     const int32_t* pst = a.p_start + pbase;
@@ -347,7 +349,7 @@ MBL_HD float score_combine(const ScoreArgs& a, uint64_t pbase, uint32_t np, int 
         if (ph[x] != ph[y]) return ph[x] < ph[y];
         return pst[x] > pst[y];
     });
-    const mbl_match_rec* ml = a.matches + pbase;
+    const mbl_match_rec* ml = a.matches;
     float score = 0.f;
     uint32_t nc = 0;
     for (uint32_t ii = 0; ii < np; ++ii) {
@@ -389,6 +391,53 @@ MBL_HD float score_combine(const ScoreArgs& a, uint64_t pbase, uint32_t np, int 
     return score / (float)read_length;
 }
 
+// =====================================================================================================================
+// Flat formulation used by the CUDA pipeline (k5_score.cu): the nested loops of chooseBestTaxon are cut into three
+// passes over flat task lists so that the threads of a warp do the same kind of work —
+//   A. one (species, frame) group per thread : getMatchPaths            -> paths at p_*[group start + k], g_np[group start]
+//   B. one (read, species) group per thread   : combineMatchPaths        -> s_score[species group start]
+//   C. one read per thread                    : tie set / LCA / votes / clade descent -> mbl_read_result
+// fg_list / sp_list hold the first match index of every frame group / species group, ascending.
+// =====================================================================================================================
+MBL_HD uint32_t list_lower_bound(const uint32_t* list, uint32_t n, uint64_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint64_t)list[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+MBL_HD void score_task_frame_group(const ScoreArgs& a, uint32_t g) {
+    const uint64_t gs = a.fg_list[g];
+    const uint64_t ge = g + 1 < a.n_fg ? a.fg_list[g + 1] : a.match_end;
+    uint32_t np = 0;
+    if (ge - gs > 1) {                                                            // Q9
+        const int32_t species = a.matches[gs].species_id;
+        int min_depth = a.par.min_cons_cnt;
+        if (tax_is_ancestor(a.tax, a.tax.eukaryota, species)) min_depth = a.par.min_cons_cnt_euk;
+        score_frame_group(a, gs, ge, min_depth, gs, np);
+    }
+    a.g_np[gs] = np;
+}
+
+MBL_HD void score_task_species(const ScoreArgs& a, uint32_t sidx) {
+    const uint64_t spS = a.sp_list[sidx];
+    const uint64_t spE = sidx + 1 < a.n_sp ? a.sp_list[sidx + 1] : a.match_end;
+    int32_t* perm = a.l_start + spS;
+    uint32_t np = 0;
+    for (uint32_t g = list_lower_bound(a.fg_list, a.n_fg, spS); g < a.n_fg && a.fg_list[g] < spE; ++g) {
+        const uint64_t gs = a.fg_list[g];
+        const uint32_t cnt = a.g_np[gs];
+        for (uint32_t k = 0; k < cnt; ++k) perm[np++] = (int32_t)(gs - spS + k);
+    }
+    float out = -3.0e38f;                                                         // "no entry in sp2score"
+    if (np > 0) {
+        const uint32_t r = qi_seq(a.matches[spS].qinfo) - 1;
+        float score = score_combine(a, spS, np, a.cov1[r] + a.cov2[r], true);
+        score = fminf(score, 1.0f);
+        if (!(score < a.par.min_score)) out = score;
+    }
+    a.s_score[spS] = out;
+}
+
 // ---- chooseBestTaxon for read r -----------------------------------------------------------------------
 MBL_HD void score_read(const ScoreArgs& a, uint32_t r) {
     mbl_read_result res;
@@ -407,6 +456,19 @@ MBL_HD void score_read(const ScoreArgs& a, uint32_t r) {
     uint32_t meaningful = 0;
     uint64_t bestS = 0, bestE = 0;
     uint64_t i = ms;
+    if (a.sp_list) {
+        // flat pipeline: the species scores are already in s_score (tasks A and B)
+        for (uint32_t sidx = list_lower_bound(a.sp_list, a.n_sp, ms); sidx < a.n_sp && a.sp_list[sidx] < me; ++sidx) {
+            const uint64_t spS = a.sp_list[sidx];
+            const uint64_t spE = sidx + 1 < a.n_sp && a.sp_list[sidx + 1] < me ? a.sp_list[sidx + 1] : me;
+            const float score = a.s_score[spS];
+            if (score > -1.0e38f) {
+                if (score > 0.f) ++meaningful;
+                if (score > bestSpScore) { bestSpScore = score; bestS = spS; bestE = spE; }
+            }
+        }
+        i = me;
+    }
     while (i < me) {
         const int32_t species = ml[i].species_id;
         const uint64_t spS = i;
@@ -438,10 +500,12 @@ MBL_HD void score_read(const ScoreArgs& a, uint32_t r) {
         int red = 0;
         bool haveRed = false;
         i = ms;
+        uint32_t sidx = a.sp_list ? list_lower_bound(a.sp_list, a.n_sp, ms) : 0;
         while (i < me) {
             const int32_t species = ml[i].species_id;
             const uint64_t spS = i;
-            while (i < me && ml[i].species_id == species) ++i;
+            if (a.sp_list) { ++sidx; i = sidx < a.n_sp && a.sp_list[sidx] < me ? a.sp_list[sidx] : me; }
+            else while (i < me && ml[i].species_id == species) ++i;
             const float sc = a.s_score[spS];
             if (sc > -1.0e38f && sc >= thr) {
                 if (nMax == 0) taxId = species;

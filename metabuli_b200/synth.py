@@ -175,15 +175,25 @@ def make_genomes(tx: SynthTaxonomy, codons: int, species_div: float, strain_div:
     return _mutate(sp[idx], strain_div, gen)
 
 
-def _metamers(codons: torch.Tensor) -> torch.Tensor:
-    """All in-frame format-2 metamers of each row: int64 bit patterns of the uint64 values [rows, codons-7]."""
+def _metamers(codons: torch.Tensor, kmer_format: int = 2) -> torch.Tensor:
+    """All in-frame metamers of each row: int64 bit patterns of the uint64 values [rows, codons-7].
+    format 2 (KmerScanner.h:74-117): 8 x 5-bit amino acids, first codon most significant.
+    format 1 (KmerScanner.h:137-181): codons are read from the far end, the amino-acid part is a base-21 number
+    whose most significant digit is the LAST codon of the window; codon ids follow the same order."""
     dev = codons.device
     aa = torch.as_tensor(_AA, device=dev)[codons.long()]
     cid = torch.as_tensor(_CID, device=dev)[codons.long()]
     w = codons.shape[1] - 7
     val = torch.zeros((codons.shape[0], w), dtype=torch.int64, device=dev)
-    for k in range(8):
-        val |= (aa[:, k:k + w] << (24 + 5 * (7 - k))) | (cid[:, k:k + w] << (3 * (7 - k)))
+    if kmer_format == 2:
+        for k in range(8):
+            val |= (aa[:, k:k + w] << (24 + 5 * (7 - k))) | (cid[:, k:k + w] << (3 * (7 - k)))
+    else:
+        aap = torch.zeros_like(val)
+        for k in range(7, -1, -1):
+            aap = aap * 21 + aa[:, k:k + w]
+            val |= cid[:, k:k + w] << (3 * k)
+        val |= aap << 24
     return val
 
 
@@ -209,7 +219,7 @@ class SynthDb:
             f.write("".join(f"{int(t)}\n" for t in self.taxid_list))
         with open(os.path.join(path, "db.parameters"), "w") as f:
             f.write("DB_name\tsynthetic\nCreation_date\t2026-1-1\nReduced_alphabet\t0\nAccession_level\t0\nMask_mode\t0\n"
-                    "Mask_prob\t0.900000\nSkip_redundancy\t1\nSyncmer\t0\nKmer_format\t2\n")
+                    "Mask_prob\t0.900000\nSkip_redundancy\t1\nSyncmer\t0\nKmer_format\t%d\n" % self.database.params.kmer_format)
 
 
 def encode_index(values_i64: torch.Tensor, split_num: int = 4096):
@@ -259,14 +269,14 @@ def encode_index(values_i64: torch.Tensor, split_num: int = 4096):
     return diff, split
 
 
-def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, chunk_rows: int = 4096) -> SynthDb:
+def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, chunk_rows: int = 4096, kmer_format: int = 2) -> SynthDb:
     dev = genomes.device
     strain_t = torch.as_tensor(tx.strain_ids.astype(np.int64), device=dev)
     species_t = torch.as_tensor(tx.species_of_strain.astype(np.int64), device=dev)
     vals, tids, sps = [], [], []
     for r0 in range(0, genomes.shape[0], chunk_rows):
         g = genomes[r0:r0 + chunk_rows]
-        v = _metamers(g)
+        v = _metamers(g, kmer_format)
         vals.append(v.flatten())
         tids.append(strain_t[r0:r0 + chunk_rows, None].expand_as(v).flatten())
         sps.append(species_t[r0:r0 + chunk_rows, None].expand_as(v).flatten())
@@ -299,16 +309,16 @@ def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, ch
     taxdb = TaxonomyDB(tmp)
     os.remove(tmp)
     taxid_list = np.concatenate([tx.strain_ids, tx.species_ids]).astype(np.int32)
-    params = DbParameters(kmer_format=2, skip_redundancy=1)
+    params = DbParameters(kmer_format=kmer_format, skip_redundancy=1)
     db = Database(params, diff, info.cpu().numpy(), split, taxdb, taxdb.build_taxid2species(taxid_list))
     return SynthDb(db, tx, genomes, blob, taxid_list)
 
 
 def make_db(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, species_div=0.12, strain_div=0.01, seed=3,
-            eukaryote_genera=0, device="cpu", split_num=4096) -> SynthDb:
+            eukaryote_genera=0, device="cpu", split_num=4096, kmer_format=2) -> SynthDb:
     tx = make_taxonomy(genera, species_per_genus, strains_per_species, eukaryote_genera)
     genomes = make_genomes(tx, codons, species_div, strain_div, seed, device)
-    return build_db(tx, genomes, split_num)
+    return build_db(tx, genomes, split_num, kmer_format=kmer_format)
 
 
 # ---- reads ---------------------------------------------------------------------------------------------------------

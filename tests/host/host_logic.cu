@@ -25,7 +25,7 @@ void ht_sort_paths(const float* score, const int* ham, const int* start, int n, 
 
 int ht_score(const mbl_match_rec* matches, size_t n_match, uint32_t n_reads, const int32_t* cov1, const int32_t* cov2,
              const mbl_taxonomy* tx, int seq_mode, float min_score, float min_sp_score, float tie_ratio, int min_cons, int min_cons_euk,
-             int accession_level, int kmer_format, int force_scratch_dp, mbl_read_result* results, int32_t* pairs_out, size_t cap_pairs, size_t* used_pairs) {
+             int accession_level, int kmer_format, int force_scratch_dp, int flat, mbl_read_result* results, int32_t* pairs_out, size_t cap_pairs, size_t* used_pairs) {
     std::vector<uint64_t> seg_b(n_reads, 0), seg_e(n_reads, 0);
     for (size_t i = 0; i < n_match; ++i) {
         uint32_t s = qi_seq(matches[i].qinfo);
@@ -60,6 +60,19 @@ int ht_score(const mbl_match_rec* matches, size_t n_match, uint32_t n_reads, con
     a.p_ematch = p_ematch.data(); a.c_start = c_start.data(); a.c_end = c_end.data(); a.s_score = s_score.data();
     a.q_tax = q_tax.data(); a.q_ham = q_ham.data(); a.q_has = q_has.data();
     a.results = results; a.taxcnt_pairs = praw.data();
+    std::vector<uint32_t> fg, sp, gnp(M, 0);
+    if (flat) {                      // the three-pass task formulation the CUDA pipeline uses
+        for (size_t i = 0; i < n_match; ++i) {
+            bool s = i == 0 || qi_seq(matches[i].qinfo) != qi_seq(matches[i - 1].qinfo) || matches[i].species_id != matches[i - 1].species_id;
+            bool f = s || qi_frame(matches[i].qinfo) != qi_frame(matches[i - 1].qinfo);
+            if (s) sp.push_back((uint32_t)i);
+            if (f) fg.push_back((uint32_t)i);
+        }
+        a.fg_list = fg.data(); a.n_fg = (uint32_t)fg.size(); a.sp_list = sp.data(); a.n_sp = (uint32_t)sp.size();
+        a.g_np = gnp.data(); a.match_end = n_match;
+        for (uint32_t g = 0; g < a.n_fg; ++g) score_task_frame_group(a, g);
+        for (uint32_t k = 0; k < a.n_sp; ++k) score_task_species(a, k);
+    }
     for (uint32_t r = 0; r < n_reads; ++r) score_read(a, r);
     size_t used = 0;
     for (uint32_t r = 0; r < n_reads; ++r) used += results[r].taxcnt_len;

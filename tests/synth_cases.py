@@ -16,6 +16,9 @@ CASES = {
     # ragged lengths incl. reads too short for a single k-mer, many Ns
     "ragged_se": (dict(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, seed=11),
                   dict(n_reads=3000, length=140, seed=12, n_rate=0.01, length_jitter=125), 1),
+    # format-1 database (OldMetamerScanner: base-21 amino-acid part, reversed codon order)
+    "format1_pe": (dict(genera=4, species_per_genus=4, strains_per_species=2, codons=2500, seed=17, species_div=0.05, kmer_format=1),
+                   dict(n_reads=3000, length=150, seed=18, n_rate=0.002, sub_rate=0.02, paired=True), 2),
     # long reads (seq-mode 3: denominator 1000)
     "long": (dict(genera=3, species_per_genus=3, strains_per_species=2, codons=6000, seed=13),
              dict(n_reads=300, length=6000, seed=14, sub_rate=0.05), 3),

@@ -52,9 +52,10 @@ def test_sort_replays_std_sort(hl):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("flat", [0, 1])
 @pytest.mark.parametrize("force_scratch", [0, 1])
 @pytest.mark.parametrize("name", ["multi_pe", "ties_se", "long"])
-def test_score_core_matches_oracle(hl, name, force_scratch, tmp_path):
+def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
     from metabuli_b200 import _ffi
     sdb, reads, seq_mode = synth_cases.build(name)
     odb = oracle.OracleDb.from_synth(sdb)
@@ -72,9 +73,9 @@ def test_score_core_matches_oracle(hl, name, force_scratch, tmp_path):
     pairs = np.zeros((max(16, opairs.shape[0] + 16), 2), dtype=np.int32)
     used = C.c_size_t(0)
     hl.ht_score.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
-                            C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+                            C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     mm = np.ascontiguousarray(m)
-    rc = hl.ht_score(_p(mm), mm.size, n, _p(cov1), _p(c2), C.byref(tx), seq_mode, 0.0, 0.0, 0.95, 4, 9, 0, 2, force_scratch, _p(res), _p(pairs),
+    rc = hl.ht_score(_p(mm), mm.size, n, _p(cov1), _p(c2), C.byref(tx), seq_mode, 0.0, 0.0, 0.95, 4, 9, 0, 2, force_scratch, flat, _p(res), _p(pairs),
                      pairs.shape[0], C.byref(used))
     assert rc == 0
     for f in ("classification", "query_length", "taxcnt_len", "is_classified", "taxcnt_begin"):
