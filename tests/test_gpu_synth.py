@@ -35,7 +35,7 @@ def test_synthetic_case(name, golden_dir, tmp_path):
         sdb.write(db_dir)
         odb = oracle.OracleDb(db_dir)
         gv, gq = clf.extract(*reads)
-        ov, oq, cov1, cov2 = oracle.extract(*reads, kmer_format=sdb.database.kmer_format)
+        ov, oq, cov1, cov2 = oracle.extract(*reads, kmer_format=sdb.database.params.kmer_format)
         assert gv.size == ov.size
         gm_ = gv != BLANK
         om_ = ((oq >> np.uint64(32)) & np.uint64(0x1FFFFFFF)) != 0

@@ -23,7 +23,7 @@ echo "== ncu full (merge kernel, FULL bench workload; score kernel, reduced work
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:merge_kernel -s 1 -c 1 -o gpurun_out/merge_prof -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_run.log 2>&1
 tail -2 gpurun_out/ncu_full_run.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_kernel -s 2 -c 1 -o gpurun_out/score_prof -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_ -s 4 -c 4 -o gpurun_out/score_prof -f \
     python bench.py --db-gib 1 --reads 2000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_score_run.log 2>&1
 tail -1 gpurun_out/ncu_score_run.log | cut -c1-200
 ls -la gpurun_out
