@@ -28,11 +28,11 @@ void sort_kmers(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, u
     result_in_b = k.selector;
 }
 
-void sort_kmers_idx(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b, size_t n,
+void sort_kmers_idx(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b, size_t n, int begin_bit,
                     int& result_in_b, cudaStream_t st) {
     cub::DoubleBuffer<uint64_t> k(key_a, key_b);
     cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
-    MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 24, 64, st));
+    MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, begin_bit, 64, st));
     result_in_b = k.selector;
 }
 

@@ -132,6 +132,17 @@ jumbo_decode_kernel(const uint16_t* __restrict__ diff, const Tile* __restrict__ 
     }
 }
 
+// How coarse may the query sort be?  With queries ordered on value >> b only, a tile receives every query whose prefix lies
+// in [prefix(first k-mer), prefix(last k-mer)]; that is (nearly) free when a tile spans many prefixes and wasteful when whole
+// tiles sit inside one prefix.  cnt[0] / cnt[1] = tiles whose first and last k-mer share the 24-bit / 32-bit prefix.
+__global__ void tile_prefix_kernel(const Tile* __restrict__ tiles, uint64_t n_tiles, unsigned long long* __restrict__ cnt) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles || tiles[t].n_kmers == 0) return;
+    const uint64_t lo = tiles[t].first_aa << 24, hi = tiles[t].last_value;
+    if ((lo >> 40) == (hi >> 40)) atomicAdd(cnt, 1ull);
+    if ((lo >> 32) == (hi >> 32)) atomicAdd(cnt + 1, 1ull);
+}
+
 // -------------------------------------------------------------------------------------------------
 void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
                           cudaStream_t st, TileDirectory& dir) {
@@ -200,8 +211,12 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
         jumbo_decode_kernel<<<(unsigned)std::min<uint64_t>(dir.n_tiles, (uint64_t)sm_count * 8), kWarps * 32, 0, st>>>(
             d_diff, dir.tiles, dir.n_tiles, dir.cell_k, dir.cell_v, dir.jumbo_vals);
     }
+    MBL_CUDA(cudaMemsetAsync(d_cnt, 0, 16, st));
+    tile_prefix_kernel<<<(unsigned)((dir.n_tiles + 255) / 256), 256, 0, st>>>(dir.tiles, dir.n_tiles, d_cnt);
+    MBL_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
     MBL_CUDA(cudaStreamSynchronize(st));
     MBL_CUDA(cudaGetLastError());
+    dir.sort_begin_bit = h_cnt[0] * 32 <= dir.n_tiles ? 40 : h_cnt[1] * 32 <= dir.n_tiles ? 32 : 24;
     cudaFree(cell_cnt); cudaFree(cell_sum); cudaFree(b_kidx); cudaFree(b_off); cudaFree(b_base); cudaFree(b_aa);
     cudaFree(cand); cudaFree(flag); cudaFree(rank); cudaFree(tmp); cudaFree(d_cnt);
 }

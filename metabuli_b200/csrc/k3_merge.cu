@@ -6,20 +6,22 @@
 // collecting for every query the target k-mers with the same 40-bit amino-acid part, then keeps the
 // candidates whose codon-level Hamming sum is <= min(2*min, 7).
 //
-// B200: the index lives in HBM behind a tile directory (k3_index.cu).  A persistent CTA pulls work
-// items (tile, query slice):
-//   1. stage   two 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) bring the tile's fragments
-//              and taxids into shared memory;
-//   2. decode  eight warps decode the tile's cells independently from their checkpoints
-//              (delta_decode.cuh) into a sorted value array; every k-mer that starts an amino-acid group is
-//              entered into a tagged bucket table (bucket = monotone hash of the 40-bit amino-acid part, entry =
-//              {group start, 18-bit tag, collision flag}) so a query misses in ~12 instructions and one LDS;
-//   3. match   a warp looks up 32 queries per iteration and queues the hits; 32 queued hits are processed one
-//              per lane: a scan of the group finds its size and whether the query's exact value is present
-//              (Hamming sum 0 <=> identical DNA part, so the survivors are exactly the equal values and no
-//              table lookups are needed); only the remaining hits run the min / select Hamming passes over a
-//              8 KiB two-codon table.  Output slots come from one atomicAdd per 32 hits.
-// HBM traffic per launch = index once + 8 B per query (+ 8 B qinfo per matching query) + 24 B per match.
+// B200: the index lives in HBM behind a tile directory (k3_index.cu).  A persistent CTA pulls work items (a tile and
+// a slice of its queries; the item carries the tile geometry, fetched into shared memory with cp.async one item ahead):
+//   1. stage   two 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) bring the tile's fragments and taxids
+//              into shared memory; the fragments of the next tile are requested as soon as this one is decoded;
+//   2. decode  all eight warps decode the tile together (delta_decode.cuh: one 16-byte octet per thread, shuffle scan
+//              of (count, sum), one barrier per 2048 fragments) into a value array; a second, k-mer-parallel pass
+//              marks the first k-mer of every amino-acid group in a bitmap (one ballot per 32 k-mers) and enters it
+//              into a bucketed hash table keyed by the 40-bit amino-acid part;
+//   3. match   a warp looks up 32 queries per iteration (the next 32 are already in flight) and queues the hits;
+//              the slot index of a hit (payload of the K2 sort) is fetched straight into the queue record with
+//              cp.async.  32 queued hits are expanded into their (query, candidate) pairs, spread evenly over the lanes:
+//              sweep 1 finds every hit's minimum Hamming sum over an 8 KiB two-codon table while the hits' qinfo words
+//              are in flight (cp.async again), sweep 2 keeps the candidates with sum <= min(2*min, 7), assembles their
+//              Match rows in a per-warp staging buffer and writes them as contiguous 8-byte words (whole sectors).
+//              Output slots come from warp-private chunks of 1024 (one global atomic per chunk).
+// HBM traffic per launch = index once + 8 B per query + (4 B slot + 8 B qinfo, sector granular) per hit + 24 B per match.
 #include "delta_decode.cuh"
 #include "kernels.cuh"
 
@@ -42,19 +44,21 @@ __device__ __forceinline__ uint32_t aa_hash(uint64_t aa40) { return (uint32_t)((
 
 // dynamic shared memory layout (sizes depend on the tile geometry chosen at load time)
 struct SmemLayout {
-    uint32_t off_scan, off_ham, off_queue, off_own, off_bits, off_frag0, off_frag1, off_info, off_vals, off_tab, total;
+    uint32_t off_rec, off_scan, off_ham, off_queue, off_own, off_qinfo, off_stage, off_bits, off_frag, off_info, off_vals, off_tab, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets) {
     SmemLayout l;
-    uint32_t o = 64;                                   // three mbarriers + two item slots
+    uint32_t o = 64;                                   // two mbarriers + two item slots
+    l.off_rec = o;    o += 2 * 64;                     // work item records: current / next
     l.off_scan = o;   o += 2 * 2 * kWarps * 8;         // block_decode cross-warp scan
     l.off_ham = o;    o += 8192;                       // two-codon table: sum | plain nibble | reversed nibble (u16)
-    l.off_queue = o;  o += kWarps * kQueue * 12;       // per-warp hit queues {group start, query dna, query offset}
+    l.off_queue = o;  o += kWarps * kQueue * 12;       // per-warp hit queues {group start, query dna, slot / query offset}
     l.off_own = o;    o += kWarps * 32 * 4;            // per-warp, per-hit minimum Hamming sum of the current round
+    l.off_qinfo = o;  o += kWarps * 32 * 8;            // per-warp, per-hit qinfo word of the current round
+    l.off_stage = o;  o += kWarps * 32 * 24;           // per-warp staging of up to 32 Match rows
     l.off_bits = o;   o += ((max_kmers + 63) / 32) * 4;   // bitmap: k-mer starts an amino-acid group
     o = (o + 15) & ~15u;
-    l.off_frag0 = o;  o += (max_u16 + 16) * 2;         // fragment tile, double buffered: the next item's tile is
-    l.off_frag1 = o;  o += (max_u16 + 16) * 2;         // in flight (TMA) while the current one is being matched
+    l.off_frag = o;   o += (max_u16 + 16) * 2;         // fragment tile (the next tile streams in once this one is decoded)
     l.off_info = o;   o += (max_kmers + 8) * 4;        // taxids of the current tile
     o = (o + 15) & ~15u;
     l.off_vals = o;   o += max_kmers * 8;
@@ -94,6 +98,19 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
     return v;
 }
 
+// Ampere-style asynchronous copies of single words: the gathers a hit needs (slot index, qinfo) land in shared memory
+// without a register round trip, so nothing waits on them until the data is used
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // codon-level Hamming distances of two 24-bit DNA parts: four lookups in the two-codon table, whose
 // entries hold {sum:4, plain nibble:4, reversed nibble:4}; the four entries are kept so the per-codon fields
 // of a surviving candidate cost no further lookups
@@ -115,10 +132,6 @@ __device__ __forceinline__ uint32_t ham_fields(const HamQuad& h, uint32_t q, uin
     const uint32_t qc = plain ? (q >> 21) & 7u : q & 7u, tc = plain ? (t >> 21) & 7u : t & 7u;
     if ((qc & 6u) == 4u && tc >= 6u) f |= 0x4000u;
     return f;
-}
-
-__device__ __forceinline__ uint64_t load_qinfo(const MergeArgs& a, uint64_t sorted_pos) {
-    return a.q_info[a.q_idx ? (uint64_t)a.q_idx[sorted_pos] : sorted_pos];
 }
 
 // Output slots: a single global cursor would serialise ~10^7 atomics per launch, so every warp reserves kOutChunk
@@ -146,36 +159,31 @@ __device__ __forceinline__ uint64_t slot_of(const Reservation& r, uint32_t i) {
     return i < r.rem ? r.old_base + r.old_used + i : r.new_base + (i - r.rem);
 }
 
-// one 24-byte Match record (Match.h:9-26 without the vptr); Q2: taxid 0 / unmapped species raise the error flag
-__device__ __forceinline__ void emit_match(const MergeArgs& a, uint64_t slot, uint64_t qinfo, int32_t raw_taxid, uint32_t td,
-                                           uint32_t field, uint32_t sum) {
-    const int32_t taxid = (int32_t)((uint32_t)raw_taxid & a.info_mask);
-    const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
-    if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);
-    if (slot < a.out_cap) {
-        uint64_t* w = reinterpret_cast<uint64_t*>(a.out + slot);
-        w[0] = qinfo;
-        w[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
-        w[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
-    }
-}
-
 }  // namespace
 
 // ---- work planning ---------------------------------------------------------------------------------
 // q_lo[t] = first query whose amino-acid part is >= the tile's first amino-acid part
+// The queries are radix-sorted on value >> prefix_shift only (k2_sort.cu), which is all the merge needs: a tile takes
+// every query whose prefix lies between the prefixes of its first and last k-mer and the per-tile hash table rejects
+// the ones that belong to a neighbour (tiles are amino-acid-group aligned, so a query can hit in one tile only).
 __global__ void merge_partition_kernel(const Tile* __restrict__ tiles, uint64_t n_tiles, const uint64_t* __restrict__ q_value,
-                                       uint64_t n_query, uint64_t* __restrict__ q_lo) {
+                                       uint64_t n_query, int prefix_shift, uint64_t* __restrict__ q_lo) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    if (t == n_tiles) { q_lo[t] = n_query; return; }
-    const uint64_t key = tiles[t].first_aa;
+    if (t >= n_tiles) return;
+    const uint64_t key_lo = (tiles[t].first_aa << 24) >> prefix_shift;
+    const uint64_t key_hi = tiles[t].last_value >> prefix_shift;
     uint64_t lo = 0, hi = n_query;
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
-        if (aa_part(q_value[mid]) < key) lo = mid + 1; else hi = mid;
+        if ((q_value[mid] >> prefix_shift) < key_lo) lo = mid + 1; else hi = mid;
     }
-    q_lo[t] = lo;
+    q_lo[2 * t] = lo;
+    hi = n_query;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if ((q_value[mid] >> prefix_shift) <= key_hi) lo = mid + 1; else hi = mid;
+    }
+    q_lo[2 * t + 1] = lo;
 }
 __global__ void merge_item_count_kernel(const Tile* __restrict__ tiles, uint64_t n_tiles, const uint64_t* __restrict__ q_lo,
                                         uint32_t* __restrict__ item_cnt) {
@@ -183,22 +191,26 @@ __global__ void merge_item_count_kernel(const Tile* __restrict__ tiles, uint64_t
     if (t > n_tiles) return;
     uint32_t c = 0;
     if (t < n_tiles && tiles[t].n_kmers > 0) {
-        uint64_t nq = q_lo[t + 1] - q_lo[t];
+        uint64_t nq = q_lo[2 * t + 1] - q_lo[2 * t];
         c = (uint32_t)((nq + kItemQueries - 1) / kItemQueries);
     }
     item_cnt[t] = c;
 }
-__global__ void merge_item_fill_kernel(uint64_t n_tiles, const uint64_t* __restrict__ q_lo, const uint32_t* __restrict__ item_cnt,
-                                       const uint32_t* __restrict__ item_off, MergeItem* __restrict__ items, uint64_t items_cap) {
+__global__ void merge_item_fill_kernel(const Tile* __restrict__ tiles, uint64_t n_tiles, const uint64_t* __restrict__ q_lo,
+                                       const uint32_t* __restrict__ item_cnt, const uint32_t* __restrict__ item_off,
+                                       MergeItem* __restrict__ items, uint64_t items_cap) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     const uint32_t c = item_cnt[t];
-    const uint64_t b = q_lo[t], e = q_lo[t + 1];
+    if (!c) return;
+    const uint64_t b = q_lo[2 * t], e = q_lo[2 * t + 1];
+    const Tile tl = tiles[t];
+    MergeItem it;
+    it.diff_begin = tl.diff_begin; it.info_begin = tl.info_begin; it.base_value = tl.base_value; it.jumbo_off = tl.jumbo_off;
+    it.n_u16 = tl.n_u16; it.n_kmers = tl.n_kmers; it.tile = (uint32_t)t; it.pad = 0;
     for (uint32_t i = 0; i < c; ++i) {
         uint64_t slot = (uint64_t)item_off[t] + i;
         if (slot >= items_cap) return;
-        MergeItem it;
-        it.tile = (uint32_t)t; it.pad = 0;
         it.q_begin = b + (uint64_t)i * kItemQueries;
         it.q_end = min(e, it.q_begin + kItemQueries);
         items[slot] = it;
@@ -210,110 +222,138 @@ __global__ void __launch_bounds__(kThreads, 3)
 merge_kernel(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = smem_layout(a.max_u16, a.max_kmers, a.n_buckets);
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);          // [0],[1] fragments, [2] taxids
-    unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 32);                 // [2]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);          // [0] fragments, [1] taxids
+    unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 32);                 // [2] claimed item numbers
+    MergeItem* s_rec = reinterpret_cast<MergeItem*>(smem + L.off_rec);                 // [2] their records
     uint64_t* s_scan = reinterpret_cast<uint64_t*>(smem + L.off_scan);
     uint16_t* s_ham = reinterpret_cast<uint16_t*>(smem + L.off_ham);
     uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + L.off_queue);
     uint32_t* s_own = reinterpret_cast<uint32_t*>(smem + L.off_own);
+    uint64_t* s_qinfo = reinterpret_cast<uint64_t*>(smem + L.off_qinfo);
+    uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem + L.off_stage);
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.off_bits);
-    uint16_t* s_frag0 = reinterpret_cast<uint16_t*>(smem + L.off_frag0);
-    const uint32_t frag_stride = (L.off_frag1 - L.off_frag0) / 2;                      // in u16
+    uint16_t* s_frag = reinterpret_cast<uint16_t*>(smem + L.off_frag);
     int32_t* s_info = reinterpret_cast<int32_t*>(smem + L.off_info);
     uint64_t* s_vals = reinterpret_cast<uint64_t*>(smem + L.off_vals);
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + L.off_tab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 4096; i += kThreads) s_ham[i] = a.ham_pair[i];
-    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); mbar_init(mbar + 2, 1); }
-    __syncthreads();
+    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
     unsigned parity_bits = 0u;                        // bit b = phase parity of mbarrier b
-    const uint32_t n_items = a.item_off[a.n_tiles];
+    const uint32_t n_items_all = a.item_off[a.n_tiles];
+    const uint32_t n_items = (uint32_t)min((uint64_t)n_items_all, a.items_cap);
+    if (n_items_all > n_items && blockIdx.x == 0 && tid == 0) atomicOr(a.error_flag, 2u);   // work list too short: host retries
     const bool fmt2 = a.kmer_format == 2;
+    const bool via_idx = a.q_idx != nullptr;
     const uint32_t bucket_mask = a.n_buckets / 2 - 1;
     const int hash_shift = 32 - (31 - __clz(a.n_buckets / 2));
-    const uint32_t bit_words = (a.max_kmers + 63) / 32;
     uint32_t* my_queue = s_queue + warp * kQueue * 3;
     uint32_t* my_own = s_own + warp * 32;
+    uint64_t* my_qinfo = s_qinfo + warp * 32;
+    uint64_t* my_stage = s_stage + warp * 96;
     unsigned long long my_matches = 0;
     OutChunk chunk;
 
-    // thread 0: start the TMA copy of an item's fragment tile into buffer `buf`
-    auto stage = [&](uint32_t item, int buf) {
-        if (item >= n_items) return;
-        const Tile t = a.tiles[a.items[item].tile];
-        if (t.jumbo_off != kNone) return;
-        const uint64_t d0 = t.diff_begin, d1 = t.diff_begin + t.n_u16;
+    // thread 0: start the TMA copy of a tile's fragments
+    auto stage_frag = [&](const MergeItem& r) {
+        if (r.jumbo_off != kNone) return;
+        const uint64_t d0 = r.diff_begin, d1 = r.diff_begin + r.n_u16;
         const uint64_t a0 = d0 & ~7ull, a1 = (d1 + 7ull) & ~7ull;
         fence_proxy_async();
-        mbar_expect_tx(mbar + buf, (unsigned)((a1 - a0) * 2));
-        tma_load_1d(s_frag0 + (uint32_t)buf * frag_stride, a.diff + a0, (unsigned)((a1 - a0) * 2), mbar + buf);
+        mbar_expect_tx(mbar, (unsigned)((a1 - a0) * 2));
+        tma_load_1d(s_frag, a.diff + a0, (unsigned)((a1 - a0) * 2), mbar);
     };
 
-    if (tid == 0) { s_item[0] = atomicAdd(a.item_cursor, 1u); stage(s_item[0], 0); }
+    // prologue: claim two items; the first one's record is fetched synchronously
+    if (tid == 0) {
+        s_item[0] = atomicAdd(a.item_cursor, 1u);
+        s_item[1] = atomicAdd(a.item_cursor, 1u);
+        if (s_item[0] < n_items) { s_rec[0] = a.items[s_item[0]]; }
+    }
     __syncthreads();
     uint32_t item = s_item[0];
-    int buf = 0;
+    int slot = 0;
+    if (tid == 0 && item < n_items) stage_frag(s_rec[0]);
+    // every warp keeps its next 32 queries in flight
+    uint64_t qv_next = kBlank;
+    if (item < n_items) {
+        const uint64_t qi = s_rec[0].q_begin + (uint64_t)warp * 32 + lane;
+        if (qi < s_rec[0].q_end) qv_next = ld_stream_u64(a.q_value + qi);
+    }
 
     while (item < n_items) {
-        const MergeItem it = a.items[item];
-        const Tile tl = a.tiles[it.tile];
-        const uint32_t nk = tl.n_kmers;
-        const bool jumbo = tl.jumbo_off != kNone;
+        const MergeItem it = s_rec[slot];
+        const uint32_t nk = it.n_kmers;
+        const uint32_t nw = (nk + 31) >> 5;
+        const bool jumbo = it.jumbo_off != kNone;
+        const uint32_t next_item = s_item[slot ^ 1];
         const uint64_t* vals;
         const int32_t* infos;
-        // claim the next item, clear the hash table and the group-start bitmap (the previous item's lookups ended at the
-        // barrier that closes the loop body), request this tile's taxids
+        unsigned int pending = 0;
         if (tid == 0) {
-            s_item[buf ^ 1] = atomicAdd(a.item_cursor, 1u);
-            if (!jumbo) {
-                const uint64_t i0 = tl.info_begin & ~3ull, i1 = (tl.info_begin + nk + 3ull) & ~3ull;
+            pending = atomicAdd(a.item_cursor, 1u);           // the item after next; published at the end of this one
+            if (!jumbo) {                                     // this tile's taxids (buffer idle since the last barrier)
+                const uint64_t i0 = it.info_begin & ~3ull, i1 = (it.info_begin + nk + 3ull) & ~3ull;
                 fence_proxy_async();
-                mbar_expect_tx(mbar + 2, (unsigned)((i1 - i0) * 4));
-                tma_load_1d(s_info, a.info + i0, (unsigned)((i1 - i0) * 4), mbar + 2);
+                mbar_expect_tx(mbar + 1, (unsigned)((i1 - i0) * 4));
+                tma_load_1d(s_info, a.info + i0, (unsigned)((i1 - i0) * 4), mbar + 1);
             }
         }
-        for (uint32_t x = tid; x < a.n_buckets; x += kThreads) s_tab[x] = kEmpty;
-        for (uint32_t x = tid; x < bit_words; x += kThreads) s_bits[x] = 0u;
-        __syncthreads();
-        const uint32_t next_item = s_item[buf ^ 1];
-        if (tid == 0) stage(next_item, buf ^ 1);             // its tile streams in while this item is decoded and matched
+        if (warp == 1 && lane < 4 && next_item < n_items)     // next item's record, four 16-byte words
+            cp_async16(reinterpret_cast<unsigned char*>(s_rec + (slot ^ 1)) + 16 * lane,
+                       reinterpret_cast<const unsigned char*>(a.items + next_item) + 16 * lane);
         if (!jumbo) {
+            for (uint32_t x = tid; x < a.n_buckets; x += kThreads) s_tab[x] = kEmpty;
             // -- 1. the tile's fragments were requested one item ago
-            const uint64_t d0 = tl.diff_begin, d1 = tl.diff_begin + tl.n_u16;
+            const uint64_t d0 = it.diff_begin, d1 = it.diff_begin + it.n_u16;
             const uint64_t a0 = d0 & ~7ull;
-            mbar_wait(mbar + buf, (parity_bits >> buf) & 1u);
-            parity_bits ^= 1u << buf;
-            // -- 2. block-wide decode; every k-mer that starts an amino-acid group is flagged in the bitmap and entered
-            //       into the hash table
-            uint64_t v = tl.base_value, k = tl.info_begin;
-            const uint64_t kb = tl.info_begin;
-            block_decode<kThreads>(s_frag0 + (uint32_t)buf * frag_stride, (int)(d0 - a0), (int)(d0 - a0), (int)(d1 - a0), v, k,
-                                   s_scan, [&](uint64_t kk, uint64_t val, uint64_t delta) {
+            mbar_wait(mbar, parity_bits & 1u);
+            parity_bits ^= 1u;
+            // -- 2. block-wide decode into the value array
+            uint64_t v = it.base_value, k = it.info_begin;
+            const uint64_t kb = it.info_begin;
+            block_decode<kThreads>(s_frag, (int)(d0 - a0), (int)(d0 - a0), (int)(d1 - a0), v, k, s_scan,
+                                   [&](uint64_t kk, uint64_t val, uint64_t) {
                 const uint64_t rel = kk - kb;
-                if (rel >= nk) return;
-                s_vals[rel] = val;
-                const uint64_t aa = val >> 24;
-                if (rel == 0 || ((val - delta) >> 24) != aa) {
-                    atomicOr(&s_bits[rel >> 5], 1u << (rel & 31));
+                if (rel < nk) s_vals[rel] = val;
+            });
+            if (warp == 1 && lane < 4) cp_async_wait_all();
+            __syncthreads();
+            if (tid == 0 && next_item < n_items) stage_frag(s_rec[slot ^ 1]);      // streams in during the match phase
+            // -- 2b. amino-acid group starts: bitmap + hash table (the table was cleared before the decode barriers)
+            for (uint32_t base = (uint32_t)warp * 32; base < nw * 32; base += kThreads) {
+                const uint32_t rel = base + lane;
+                bool start = false;
+                uint64_t aa = 0;
+                if (rel < nk) {
+                    aa = s_vals[rel] >> 24;
+                    start = rel == 0 || (s_vals[rel - 1] >> 24) != aa;
+                }
+                const uint32_t b = __ballot_sync(kFull, start);
+                if (lane == 0) s_bits[base >> 5] = b;
+                if (start) {
                     const uint32_t h = aa_hash(aa);
-                    const uint32_t entry = ((uint32_t)rel << 19) | (h & 0x7FFFFu);
-                    uint32_t slot = 2u * (h >> hash_shift);
+                    const uint32_t entry = (rel << 19) | (h & 0x7FFFFu);
+                    uint32_t bs = 2u * (h >> hash_shift);
                     while (true) {
-                        if (atomicCAS(&s_tab[slot], kEmpty, entry) == kEmpty) break;
-                        if (atomicCAS(&s_tab[slot + 1], kEmpty, entry) == kEmpty) break;
-                        slot = (slot + 2) & (2u * bucket_mask + 1u);
+                        if (atomicCAS(&s_tab[bs], kEmpty, entry) == kEmpty) break;
+                        if (atomicCAS(&s_tab[bs + 1], kEmpty, entry) == kEmpty) break;
+                        bs = (bs + 2) & (2u * bucket_mask + 1u);
                     }
                 }
-            });
-            mbar_wait(mbar + 2, (parity_bits >> 2) & 1u);
-            parity_bits ^= 4u;
+            }
+            mbar_wait(mbar + 1, (parity_bits >> 1) & 1u);
+            parity_bits ^= 2u;
             __syncthreads();
             vals = s_vals;
-            infos = s_info + (tl.info_begin & 3ull);
+            infos = s_info + (it.info_begin & 3ull);
         } else {
-            vals = a.jumbo_vals + tl.jumbo_off;
-            infos = a.info + tl.info_begin;
+            if (warp == 1 && lane < 4) cp_async_wait_all();
+            __syncthreads();
+            if (tid == 0 && next_item < n_items) stage_frag(s_rec[slot ^ 1]);
+            vals = a.jumbo_vals + it.jumbo_off;
+            infos = a.info + it.info_begin;
         }
 
         // -- 3. stream the query slice.  A warp looks up 32 queries per iteration and appends the ones that found
@@ -324,10 +364,12 @@ merge_kernel(MergeArgs a) {
         uint32_t q_head = 0, q_count = 0;
         auto process_hits = [&](uint32_t m) {
             const bool valid = (uint32_t)lane < m;
+            cp_async_wait_all();                                                    // slot indices of the queued hits
+            __syncwarp();
             const uint32_t* rec = my_queue + 3u * ((q_head + lane) & (kQueue - 1));
             const uint32_t g0 = valid ? rec[0] : 0u;                                // group start inside the tile
             const uint32_t qd = valid ? rec[1] : 0u;                                // query DNA part
-            const uint32_t qoff = valid ? rec[2] : 0u;                              // query index relative to the item
+            if (valid) cp_async8(my_qinfo + lane, a.q_info + (via_idx ? (uint64_t)rec[2] : it.q_begin + rec[2]));
             q_head = (q_head + m) & (kQueue - 1);
             q_count -= m;
             // group size = distance to the next group start
@@ -335,8 +377,8 @@ merge_kernel(MergeArgs a) {
             if (valid) {
                 if (!jumbo) {
                     uint32_t w = (g0 + 1) >> 5;
-                    uint32_t bits = w < bit_words ? s_bits[w] & (0xffffffffu << ((g0 + 1) & 31)) : 0u;
-                    while (!bits && ++w < bit_words) bits = s_bits[w];
+                    uint32_t bits = w < nw ? s_bits[w] & (0xffffffffu << ((g0 + 1) & 31)) : 0u;
+                    while (!bits && ++w < nw) bits = s_bits[w];
                     const uint32_t nxt = bits ? (w << 5) + (uint32_t)__ffs(bits) - 1u : nk;
                     n = min(nxt, nk) - g0;
                 } else {
@@ -363,14 +405,14 @@ merge_kernel(MergeArgs a) {
                 o &= 31u;
                 const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
                 const uint32_t oq = __shfl_sync(kFull, qd, o);
-                uint32_t sum = 255u;
                 if (pv) {
                     const uint32_t td = (uint32_t)vals[j] & 0xFFFFFFu;
-                    sum = td == oq ? 0u : ham_sum(ham_lookup(s_ham, oq, td));
+                    const uint32_t sum = td == oq ? 0u : ham_sum(ham_lookup(s_ham, oq, td));
+                    atomicMin(&my_own[o], sum);
                 }
-                if (pv) atomicMin(&my_own[o], sum);
-                __syncwarp();
             }
+            cp_async_wait_all();                                                    // qinfo words
+            __syncwarp();
             // sweep 2: survivors
             for (uint32_t pb = 0; pb < total; pb += 32) {
                 const uint32_t p = pb + lane;
@@ -381,7 +423,6 @@ merge_kernel(MergeArgs a) {
                 o &= 31u;
                 const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
                 const uint32_t oq = __shfl_sync(kFull, qd, o);
-                const uint32_t ooff = __shfl_sync(kFull, qoff, o);
                 uint32_t td = 0, sum = 255u;
                 HamQuad hq{0u, 0u, 0u, 0u};
                 if (pv) {
@@ -391,21 +432,37 @@ merge_kernel(MergeArgs a) {
                 const bool sel = pv && sum <= min(my_own[o] * 2u, 7u);                  // KmerMatcher.cpp:1136
                 const uint32_t bal = __ballot_sync(kFull, sel);
                 if (!bal) continue;
-                const Reservation rs = reserve(chunk, __popc(bal), a.out_count, lane);
+                const uint32_t cnt = __popc(bal);
+                const Reservation rs = reserve(chunk, cnt, a.out_count, lane);
                 if (sel) {
-                    const uint64_t qinfo = load_qinfo(a, it.q_begin + ooff);
+                    // one 24-byte Match record (Match.h:9-26 without the vptr); Q2: taxid 0 / unmapped species raise the flag
+                    const uint64_t qinfo = my_qinfo[o];
                     const bool plain = !((qi_frame(qinfo) < 3) ^ fmt2);                 // KmerMatcher.cpp:1140
-                    emit_match(a, slot_of(rs, __popc(bal & ((1u << lane) - 1))), qinfo, infos[j], td, sum ? ham_fields(hq, oq, td, plain) : 0u, sum);
+                    const int32_t taxid = (int32_t)((uint32_t)infos[j] & a.info_mask);
+                    const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
+                    if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);
+                    const uint32_t field = sum ? ham_fields(hq, oq, td, plain) : 0u;
+                    uint64_t* w = my_stage + 3u * (uint32_t)__popc(bal & ((1u << lane) - 1));
+                    w[0] = qinfo;
+                    w[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
+                    w[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
                 }
-                my_matches += __popc(bal);
+                __syncwarp();
+                for (uint32_t w = lane; w < 3u * cnt; w += 32) {                        // contiguous 8-byte words
+                    const uint32_t r = w / 3u;
+                    const uint64_t sl = slot_of(rs, r);
+                    if (sl < a.out_cap) reinterpret_cast<uint64_t*>(a.out + sl)[w - 3u * r] = my_stage[w];
+                }
+                __syncwarp();
+                my_matches += cnt;
             }
-            __syncwarp();
         };
 
         for (uint64_t qb = it.q_begin + (uint64_t)warp * 32; qb < it.q_end; qb += kThreads) {
             const uint64_t qi = qb + lane;
             const bool active = qi < it.q_end;
-            const uint64_t qv = active ? ld_stream_u64(a.q_value + qi) : kBlank;
+            const uint64_t qv = qv_next;
+            qv_next = qi + kThreads < it.q_end ? ld_stream_u64(a.q_value + qi + kThreads) : kBlank;
             const uint64_t q40 = qv >> 24;
             uint32_t g0 = 0;
             bool hit = false;
@@ -432,7 +489,8 @@ merge_kernel(MergeArgs a) {
             if (bal) {
                 if (hit) {
                     uint32_t* rec = my_queue + 3u * ((q_head + q_count + __popc(bal & ((1u << lane) - 1))) & (kQueue - 1));
-                    rec[0] = g0; rec[1] = (uint32_t)qv & 0xFFFFFFu; rec[2] = (uint32_t)(qi - it.q_begin);
+                    rec[0] = g0; rec[1] = (uint32_t)qv & 0xFFFFFFu;
+                    if (via_idx) cp_async4(rec + 2, a.q_idx + qi); else rec[2] = (uint32_t)(qi - it.q_begin);
                 }
                 q_count += __popc(bal);
                 __syncwarp();
@@ -440,16 +498,23 @@ merge_kernel(MergeArgs a) {
             }
         }
         if (q_count) process_hits(q_count);
+        // first queries of the next item (its record arrived before the decode barrier)
+        if (next_item < n_items) {
+            const MergeItem* nr = s_rec + (slot ^ 1);
+            const uint64_t qi = nr->q_begin + (uint64_t)warp * 32 + lane;
+            qv_next = qi < nr->q_end ? ld_stream_u64(a.q_value + qi) : kBlank;
+        }
+        if (tid == 0) s_item[slot] = pending;
         __syncthreads();
         item = next_item;
-        buf ^= 1;
+        slot ^= 1;
     }
     // blank out the unused tail of the warp's last chunk (seqID 0 == not a match)
     if (chunk.used < kOutChunk) {
         for (uint32_t w = chunk.used + lane; w < kOutChunk; w += 32) {
-            const uint64_t slot = chunk.base + w;
-            if (slot < a.out_cap) {
-                uint64_t* o = reinterpret_cast<uint64_t*>(a.out + slot);
+            const uint64_t sl = chunk.base + w;
+            if (sl < a.out_cap) {
+                uint64_t* o = reinterpret_cast<uint64_t*>(a.out + sl);
                 o[0] = 0; o[1] = 0; o[2] = 0;
             }
         }
@@ -461,10 +526,10 @@ size_t merge_smem_bytes(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets
 
 void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
     const unsigned blocks = (unsigned)((a.n_tiles + 1 + 255) / 256);
-    merge_partition_kernel<<<blocks, 256, 0, st>>>(a.tiles, a.n_tiles, a.q_value, a.n_query, a.q_lo);
+    merge_partition_kernel<<<blocks, 256, 0, st>>>(a.tiles, a.n_tiles, a.q_value, a.n_query, a.prefix_shift, a.q_lo);
     merge_item_count_kernel<<<blocks, 256, 0, st>>>(a.tiles, a.n_tiles, a.q_lo, a.item_cnt);
     exclusive_sum_u32(a.scan_tmp, a.scan_tmp_bytes, a.item_cnt, a.item_off, a.n_tiles + 1, st);
-    merge_item_fill_kernel<<<blocks, 256, 0, st>>>(a.n_tiles, a.q_lo, a.item_cnt, a.item_off, a.items, a.items_cap);
+    merge_item_fill_kernel<<<blocks, 256, 0, st>>>(a.tiles, a.n_tiles, a.q_lo, a.item_cnt, a.item_off, a.items, a.items_cap);
 }
 
 void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st) {

@@ -16,6 +16,9 @@ struct TileDirectory {
     // geometry chosen at load time: nominal tile = tile_cells cells; tiles with more than max_u16 fragments or
     // max_kmers k-mers are jumbo (pre-decoded in HBM)
     uint32_t tile_cells = 4, max_u16 = 0, max_kmers = 0;
+    // lowest value bit the query sort must cover so that almost no tile lies inside a single sort bucket (40, 32 or 24;
+    // see tile_sort_bit in k3_index.cu) — the merge only needs queries grouped per tile, not fully ordered
+    int sort_begin_bit = 24;
     uint64_t n_kmers_decoded = 0;   // number of end flags in the stream (must equal the info count)
 };
 
@@ -48,7 +51,7 @@ size_t sort_kmers_temp_bytes(size_t n);
 void sort_kmers(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint64_t* val_a, uint64_t* val_b, size_t n,
                 int& result_in_b, cudaStream_t st);
 // pipeline variant: the payload is the 32-bit slot index; qinfo stays where K1 wrote it and is gathered for hits only
-void sort_kmers_idx(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b, size_t n,
+void sort_kmers_idx(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b, size_t n, int begin_bit,
                     int& result_in_b, cudaStream_t st);
 size_t scan_temp_bytes(size_t n);
 void exclusive_sum_u64(void* tmp, size_t tmp_bytes, const uint64_t* in, uint64_t* out, size_t n, cudaStream_t st);
@@ -94,7 +97,8 @@ struct MergeArgs {
     unsigned long long* out_count;  // total matches found (may exceed out_cap => overflow)
     unsigned int* error_flag;       // Q2
     // work list
-    uint64_t* q_lo;                 // [n_tiles + 1]
+    uint64_t* q_lo;                 // [2 * (n_tiles + 1)]: per tile first query / one past the last query of its prefix range
+    int prefix_shift;               // queries are ordered by value >> prefix_shift only
     uint32_t* item_cnt;             // [n_tiles + 1]
     uint32_t* item_off;             // [n_tiles + 1]
     MergeItem* items;

@@ -48,6 +48,7 @@ struct mbl_ctx {
     uint16_t* d_ham_pair = nullptr;
     uint8_t* d_ham_single = nullptr;
     uint32_t tile_cells = 4;
+    int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // index
     uint16_t* d_diff = nullptr;
     int32_t* d_info = nullptr;
@@ -79,6 +80,9 @@ struct mbl_ctx {
 };
 
 namespace {
+
+// blank tails of the merge kernel's warp-private output chunks (k3_merge.cu: kOutChunk = 1024 slots, <= 4 CTAs x 8 warps per SM)
+uint64_t out_slack(const mbl_ctx* c) { return (uint64_t)c->sm_count * 4 * 8 * 1024 + 65536; }
 
 int fail(mbl_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
@@ -222,7 +226,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         uint64_t *va = ar, *vb = ar + S8;
         uint32_t *ia = reinterpret_cast<uint32_t*>(ar + 3 * S8), *ib = ia + S8;
         int in_b = 0;
-        if (S) sort_kmers_idx(c->cub_tmp.p, c->cub_tmp.cap, va, vb, ia, ib, S, in_b, st);
+        if (S) sort_kmers_idx(c->cub_tmp.p, c->cub_tmp.cap, va, vb, ia, ib, S, c->dir.sort_begin_bit, in_b, st);
         qv = in_b ? vb : va;
         qidx = in_b ? ib : ia;
         qi = ar + 2 * S8;
@@ -235,7 +239,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     c->stats.n_query_kmers += n_query;
 
     // ---- K3 ------------------------------------------------------------------------------------------
-    uint64_t cap = (uint64_t)((double)S * std::max(c->match_ratio * 1.25, 0.125 * (double)std::max(1, c->cfg.match_per_kmer))) + (1u << 16);
+    uint64_t cap = (uint64_t)((double)S * std::max(c->match_ratio * 1.25, 0.125 * (double)std::max(1, c->cfg.match_per_kmer))) + out_slack(c);
     uint64_t reserved = 0, n_match = 0;
     MergeArgs ma{};
     ma.diff = c->d_diff; ma.info = c->d_info;
@@ -250,7 +254,8 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     ma.out_count = counters + 1;
     ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
     ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
-    ma.q_lo = c->q_lo.get<uint64_t>(c->dir.n_tiles + 2);
+    ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
+    ma.prefix_shift = c->dir.sort_begin_bit;
     ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
     ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
     ma.items_cap = c->dir.n_tiles + n_query / kItemQueries + 2;
@@ -281,6 +286,15 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         MBL_CUDA(cudaGetLastError());
         reserved = h_cnt[1]; n_match = h_cnt[2];
         if ((uint32_t)h_cnt[3] & 1u) return fail(c, MBL_E_BAD_DB, "target k-mer with taxid 0 or unmapped species (reference exits, KmerMatcher.cpp:292-300)");
+        if ((uint32_t)h_cnt[3] & 2u) {          // overlapping prefix ranges produced more work items than planned for
+            uint32_t need = 0;
+            MBL_CUDA(cudaMemcpy(&need, ma.item_off + c->dir.n_tiles, 4, cudaMemcpyDeviceToHost));
+            ma.items_cap = (uint64_t)need + 2;
+            ma.items = c->items.get<MergeItem>(ma.items_cap);
+            c->stats.overflow_retries += 1;
+            if (attempt > 4) return fail(c, MBL_E_MATCH_OVERFLOW, "merge work list overflow persists");
+            continue;
+        }
         if (reserved <= cap) break;
         // Classifier.cpp:127-130: the reference bumps matchPerKmer and restarts; here only the merge is redone
         c->stats.overflow_retries += 1;
@@ -427,6 +441,7 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         c->d_codon = upload(c, t.codon, 512);
         c->d_ham_pair = upload(c, t.ham_pair, 4096);
         c->d_ham_single = upload(c, t.ham_sum, 64);
+        if (const char* e = getenv("MBL_SORT_BIT")) { int v = atoi(e); if (v == 24 || v == 32 || v == 40) c->force_sort_bit = v; }
         if (const char* e = getenv("MBL_TILE_CELLS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->tile_cells = (uint32_t)v; }
         MBL_CUDA(cudaStreamSynchronize(c->st));
     } catch (const CudaError& e) {
@@ -476,6 +491,7 @@ int mbl_load_db(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx) {
         c->tax.max_taxid = tx->max_taxid; c->tax.M_k = tx->M_k; c->tax.eukaryota = tx->eukaryota; c->tax.max_nodes = (uint32_t)N;
         MBL_CUDA(cudaStreamSynchronize(c->st));
         build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->tile_cells, c->st, c->dir);
+        if (c->force_sort_bit) c->dir.sort_begin_bit = c->force_sort_bit;
         // the k-mer count implied by the end flags must agree with the info file
         if (c->dir.n_kmers_decoded != c->n_kmers) {
             char msg[256];
@@ -683,14 +699,15 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
         ma.out_count = counters + 1;
         ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
         ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
-        ma.q_lo = c->q_lo.get<uint64_t>(c->dir.n_tiles + 2);
+        ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
+        ma.prefix_shift = 24;                // the stage API takes fully ordered queries; any coarser grouping is valid too
         ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
         ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
         ma.items_cap = c->dir.n_tiles + nq / kItemQueries + 2;
         ma.items = c->items.get<MergeItem>(ma.items_cap);
         ma.scan_tmp = c->cub_tmp.get<uint8_t>(scan_temp_bytes(c->dir.n_tiles + 2));
         ma.scan_tmp_bytes = c->cub_tmp.cap;
-        uint64_t dcap = cap + 148ull * 8 * 3 * 256 + 65536;
+        uint64_t dcap = cap + out_slack(c);
         unsigned long long h_cnt[4];
         std::vector<mbl_match_rec> host;
         for (int attempt = 0;; ++attempt) {

@@ -49,11 +49,14 @@ struct Tile {
     uint64_t last_value;     // value of the tile's last k-mer (bucket geometry of the merge kernel)
 };
 
-struct MergeItem {           // one unit of merge work: a tile and a slice of its queries
-    uint32_t tile;
-    uint32_t pad;
-    uint64_t q_begin, q_end;
+struct alignas(16) MergeItem {   // one unit of merge work: a slice of the queries of one tile, with the tile's
+    uint64_t q_begin, q_end;     // geometry copied in so the merge kernel needs a single 64-byte fetch per item
+    uint64_t diff_begin, info_begin;
+    uint64_t base_value, jumbo_off;
+    uint32_t n_u16, n_kmers;
+    uint32_t tile, pad;
 };
+static_assert(sizeof(MergeItem) == 64, "MergeItem is fetched as four 16-byte words");
 
 // ---- error handling ------------------------------------------------------------------------------
 struct CudaError {

@@ -78,3 +78,21 @@ def test_empty_and_tiny_batches():
         assert list(res["is_classified"]) == [0, 0] and list(res["query_length"]) == [21, 147]
     finally:
         clf.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sort_bit", [24, 32, 40])
+def test_query_sort_granularity(sort_bit, golden_dir, monkeypatch):
+    """The merge only needs the queries grouped per tile: every supported coarseness of the K2 sort (MBL_SORT_BIT, normally
+    chosen at load time) must give the reference's TSV."""
+    from metabuli_b200 import Classifier, ClassifyOptions
+    monkeypatch.setenv("MBL_SORT_BIT", str(sort_bit))
+    for name in ("multi_se", "format1_pe"):
+        sdb, reads, seq_mode = synth_cases.build(name)
+        clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
+        try:
+            res, pairs = clf.classify_batch(*reads)
+            tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
+            assert tsv == gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
+        finally:
+            clf.close()

@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-echo "== pytest -m gpu"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+echo "== pytest -m gpu"; timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
 echo "== tune"; timeout 600 python tools/tune_merge.py --cells 1,2,4 2>&1 | tail -8 | tee gpurun_out/tune.jsonl
 BEST=$(tail -1 gpurun_out/tune.jsonl | python -c "import json,sys; print(json.loads(sys.stdin.read()).get('best_tile_cells',4))" 2>/dev/null || echo 4)
@@ -14,7 +14,7 @@ echo "== bench full"; timeout 900 python bench.py --steps 3 --warmup 3 2>&1 | ta
 if [ "${1:-}" != "quick" ]; then
 echo "== bench reference arm"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -2 | tee gpurun_out/bench_reference.json
 fi
-KRE='regex:(merge_|extract_kernel|read_meta|score_kernel|segment_kernel|match_.*kernel|taxcnt|RadixSort|DeviceScan)'
+KRE='regex:(merge_|extract_kernel|read_meta|score_|segment_kernel|match_|seq_bounds|taxcnt|RadixSort|DeviceScan|DeviceSelect)'
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --db-gib 1 --reads 2000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_run.log 2>&1
