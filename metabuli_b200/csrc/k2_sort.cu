@@ -84,7 +84,9 @@ __global__ void match_gather_kernel(const mbl_match_rec* __restrict__ in, const 
     uint64_t a = s[0], b = s[1], c = s[2];
     d[0] = a; d[1] = b; d[2] = c;
 }
-// single-pass key: seqID | species | frame | pos
+// single-pass key: seqID | species | frame | pos / 3.  Inside one (read, frame) the k-mer positions advance in codon steps
+// (and the second mate starts beyond the first), so two distinct positions differ by at least 3 and pos / 3 orders them
+// like pos does with ~1.6 fewer key bits — in the benchmark shape that is one radix pass less.
 __global__ void match_fullkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, int sp_bits, int pos_bits, uint64_t* __restrict__ key,
                                      uint32_t* __restrict__ idx) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,7 +95,7 @@ __global__ void match_fullkey_kernel(const mbl_match_rec* __restrict__ m, size_t
     uint64_t k = (uint64_t)qi_seq(q);
     k = (k << sp_bits) | (uint64_t)(uint32_t)m[i].species_id;
     k = (k << 3) | (uint64_t)qi_frame(q);
-    k = (k << pos_bits) | (uint64_t)qi_pos(q);
+    k = (k << pos_bits) | (uint64_t)(qi_pos(q) / 3u);
     key[i] = k;
     idx[i] = (uint32_t)i;
 }
@@ -194,11 +196,12 @@ void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
     const int pos_bits = bits_for(max_pos);
     const int sp_bits = bits_for((uint64_t)(uint32_t)max_taxid);
     const int seq_bits = bits_for(n_reads);
-    if (seq_bits + sp_bits + 3 + pos_bits <= 64) {
-        match_fullkey_kernel<<<blocks, 256, 0, st>>>(in, n, sp_bits, pos_bits, key_a, idx_a);
+    const int pos3_bits = bits_for(max_pos / 3u);
+    if (seq_bits + sp_bits + 3 + pos3_bits <= 64) {
+        match_fullkey_kernel<<<blocks, 256, 0, st>>>(in, n, sp_bits, pos3_bits, key_a, idx_a);
         cub::DoubleBuffer<uint64_t> k(key_a, key_b);
         cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
-        MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, seq_bits + sp_bits + 3 + pos_bits, st));
+        MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, seq_bits + sp_bits + 3 + pos3_bits, st));
         match_gather_kernel<<<blocks, 256, 0, st>>>(in, v.Current(), n, out);
         match_fix_runs_kernel<<<blocks, 256, 0, st>>>(out, n);
         return;

@@ -138,7 +138,7 @@ jumbo_decode_kernel(const uint16_t* __restrict__ diff, const Tile* __restrict__ 
 __global__ void tile_prefix_kernel(const Tile* __restrict__ tiles, uint64_t n_tiles, unsigned long long* __restrict__ cnt) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles || tiles[t].n_kmers == 0) return;
-    const uint64_t lo = tiles[t].first_aa << 24, hi = tiles[t].last_value;
+    const uint64_t lo = tiles[t].first_aa, hi = tiles[t].last_value;     // first_aa = value with the DNA bits cleared
     if ((lo >> 40) == (hi >> 40)) atomicAdd(cnt, 1ull);
     if ((lo >> 32) == (hi >> 32)) atomicAdd(cnt + 1, 1ull);
 }

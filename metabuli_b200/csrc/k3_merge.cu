@@ -170,7 +170,7 @@ __global__ void merge_partition_kernel(const Tile* __restrict__ tiles, uint64_t 
                                        uint64_t n_query, int prefix_shift, uint64_t* __restrict__ q_lo) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    const uint64_t key_lo = (tiles[t].first_aa << 24) >> prefix_shift;
+    const uint64_t key_lo = tiles[t].first_aa >> prefix_shift;          // first_aa = value with the DNA bits cleared
     const uint64_t key_hi = tiles[t].last_value >> prefix_shift;
     uint64_t lo = 0, hi = n_query;
     while (lo < hi) {
@@ -253,6 +253,9 @@ merge_kernel(MergeArgs a) {
     uint64_t* my_qinfo = s_qinfo + warp * 32;
     uint64_t* my_stage = s_stage + warp * 96;
     unsigned long long my_matches = 0;
+#ifdef MBL_DEBUG_ITEMS
+    unsigned long long dbg_prev = 0;
+#endif
     OutChunk chunk;
 
     // thread 0: start the TMA copy of a tile's fragments
@@ -498,6 +501,9 @@ merge_kernel(MergeArgs a) {
             }
         }
         if (q_count) process_hits(q_count);
+#ifdef MBL_DEBUG_ITEMS
+        { unsigned long long d = my_matches - dbg_prev; dbg_prev = my_matches; if (lane == 0 && d) atomicAdd(&a.items[item].pad, (unsigned)d); }
+#endif
         // first queries of the next item (its record arrived before the decode barrier)
         if (next_item < n_items) {
             const MergeItem* nr = s_rec + (slot ^ 1);

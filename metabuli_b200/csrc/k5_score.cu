@@ -28,7 +28,18 @@ __global__ void score_mark_kernel(const mbl_match_rec* __restrict__ m, uint64_t 
     flag_sp[i - begin] = sp;
     flag_fg[i - begin] = fg;
 }
-__global__ void __launch_bounds__(128, 4) score_fg_kernel(ScoreArgs a) {
+// Frame groups differ a lot in length (the true species in the true frame holds tens of matches, chance hits one or
+// two), so one group per thread in list order leaves most lanes of a warp idle.  Tasks are therefore ordered by length,
+// longest first: key = 255 - min(length, 255), one 8-bit radix pass.
+__global__ void fg_len_key_kernel(const uint32_t* __restrict__ fg_list, uint32_t n_fg, uint64_t match_end, uint8_t* __restrict__ key,
+                                  uint32_t* __restrict__ idx) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_fg) return;
+    const uint64_t len = (g + 1 < n_fg ? (uint64_t)fg_list[g + 1] : match_end) - fg_list[g];
+    key[g] = (uint8_t)(255u - (uint32_t)min(len, (uint64_t)255));
+    idx[g] = g;
+}
+__global__ void __launch_bounds__(128, 8) score_fg_kernel(ScoreArgs a) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < a.n_fg) score_task_frame_group(a, g);
 }
@@ -41,7 +52,11 @@ size_t score_flat_temp_bytes(size_t n) {
     size_t bytes = 0;
     cub::DeviceSelect::Flagged(nullptr, bytes, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)nullptr, (uint32_t*)nullptr,
                                (uint32_t*)nullptr, (long long)n);
-    return bytes;
+    size_t sb = 0;
+    cub::DoubleBuffer<uint8_t> k(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, sb, k, v, (long long)n, 0, 8);
+    return bytes > sb ? bytes : sb;
 }
 
 void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch& s, cudaStream_t st) {
@@ -60,6 +75,15 @@ void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch
         MBL_CUDA(cudaStreamSynchronize(st));
     }
     a.fg_list = s.fg_list; a.n_fg = h_counts[0]; a.sp_list = s.sp_list; a.n_sp = h_counts[1];
+    a.fg_order = nullptr;
+    if (a.n_fg > 1) {
+        fg_len_key_kernel<<<(a.n_fg + 255) / 256, 256, 0, st>>>(s.fg_list, a.n_fg, a.match_end, s.flags_fg, s.fg_ord);
+        cub::DoubleBuffer<uint8_t> k(s.flags_fg, s.flags_sp);
+        cub::DoubleBuffer<uint32_t> v(s.fg_ord, s.fg_ord + n);
+        size_t tb = s.cub_tmp_bytes;
+        MBL_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tb, k, v, (long long)a.n_fg, 0, 8, st));
+        a.fg_order = v.Current();
+    }
     if (a.n_fg) score_fg_kernel<<<(a.n_fg + 127) / 128, 128, 0, st>>>(a);
     if (a.n_sp) score_sp_kernel<<<(a.n_sp + 127) / 128, 128, 0, st>>>(a);
     score_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);

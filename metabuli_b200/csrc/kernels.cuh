@@ -131,6 +131,7 @@ struct ScoreArgs {
     int32_t* c_start; int32_t* c_end; float* s_score;
     // flat task lists (first match index of every (species, frame) group / (read, species) group); optional
     const uint32_t* fg_list; uint32_t n_fg; const uint32_t* sp_list; uint32_t n_sp; uint32_t* g_np; uint64_t match_end;
+    const uint32_t* fg_order;           // optional: permutation of the frame-group tasks (similar lengths per warp)
     // scratch, per quotient
     int32_t* q_tax; uint8_t* q_ham; uint8_t* q_has;
     // outputs
@@ -139,7 +140,12 @@ struct ScoreArgs {
 };
 void launch_score(const ScoreArgs& a, cudaStream_t st);
 // flat pipeline over the matches [match_begin, a.match_end) of the reads [a.read_begin, +a.n_reads)
-struct ScoreFlatScratch { uint8_t* flags_fg; uint8_t* flags_sp; uint32_t* fg_list; uint32_t* sp_list; uint32_t* counts; void* cub_tmp; size_t cub_tmp_bytes; };
+struct ScoreFlatScratch {
+    uint8_t* flags_fg; uint8_t* flags_sp;       // per match; reused as the length keys of the frame-group ordering
+    uint32_t* fg_list; uint32_t* sp_list;
+    uint32_t* fg_ord;                           // [2 * matches]: frame-group task order, double buffered
+    uint32_t* counts; void* cub_tmp; size_t cub_tmp_bytes;
+};
 size_t score_flat_temp_bytes(size_t n_matches);
 void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch& s, cudaStream_t st);
 void launch_compact_taxcnt(const mbl_read_result* results, uint32_t n_reads, const uint32_t* quot_off,

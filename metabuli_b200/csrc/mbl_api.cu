@@ -66,7 +66,7 @@ struct mbl_ctx {
     // workspace
     Buf cov1, cov2, w1, w2, slots, slot_off, quot_cnt, quot_off, seg_b, seg_e, res_sub, tax_len, tax_off;
     Buf val_a, val_b, qi_a, qi_b, cub_tmp;
-    Buf arena, chunk_bounds, order_keys, g_np, flag_fg, flag_sp, fg_list, sp_list, flat_tmp;     // phase 1: k-mer keys/payloads (32 B per slot); phase 2: match sort buffers
+    Buf arena, chunk_bounds, order_keys, g_np, flag_fg, flag_sp, fg_list, sp_list, fg_ord, flat_tmp;     // phase 1: k-mer keys/payloads (32 B per slot); phase 2: match sort buffers
     Buf m_raw, m_sorted, key_a, key_b, idx_a, idx_b;
     Buf l_score, l_start, l_ham, l_depth, l_smatch, l_conn, p_start, p_end, p_score, p_ham, p_depth, p_smatch, p_ematch,
         c_start, c_end, s_score;
@@ -371,6 +371,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         ScoreFlatScratch flat{};
         flat.flags_fg = c->flag_fg.get<uint8_t>(Mp); flat.flags_sp = c->flag_sp.get<uint8_t>(Mp);
         flat.fg_list = c->fg_list.get<uint32_t>(Mp); flat.sp_list = c->sp_list.get<uint32_t>(Mp);
+        flat.fg_ord = c->fg_ord.get<uint32_t>(2 * Mp);
         flat.counts = reinterpret_cast<uint32_t*>(c->counters.get<unsigned long long>(8)) + 12;
         flat.cub_tmp = c->flat_tmp.get<uint8_t>(score_flat_temp_bytes(Mp)); flat.cub_tmp_bytes = c->flat_tmp.cap;
         for (uint32_t k = 0; k < n_chunks; ++k) {
@@ -384,7 +385,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
             sa.g_np = g_np - f;
             sa.match_end = bounds[k + 1];
             launch_score_flat(sa, f, flat, st);
-            c->stats.kernel_launches += 4;
+            c->stats.kernel_launches += 6;
         }
         // compact the (taxid,count) lists behind the pairs of earlier sub-batches
         uint32_t *tl = c->tax_len.get<uint32_t>(n + 1), *to = c->tax_off.get<uint32_t>(n + 1);
@@ -460,7 +461,7 @@ void mbl_destroy(mbl_ctx* c) {
     free_db(c);
     for (Buf* b : {&c->bases1, &c->bases2, &c->off1, &c->off2, &c->cov1, &c->cov2, &c->w1, &c->w2, &c->slots, &c->slot_off, &c->quot_cnt,
                    &c->quot_off, &c->seg_b, &c->seg_e, &c->res_sub, &c->tax_len, &c->tax_off, &c->val_a, &c->val_b, &c->qi_a, &c->qi_b,
-                   &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->order_keys, &c->g_np, &c->flag_fg, &c->flag_sp, &c->fg_list, &c->sp_list, &c->flat_tmp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
+                   &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->order_keys, &c->g_np, &c->flag_fg, &c->flag_sp, &c->fg_list, &c->sp_list, &c->fg_ord, &c->flat_tmp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
                    &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score, &c->p_ham, &c->p_depth, &c->p_smatch,
                    &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw, &c->q_lo,
                    &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs})
@@ -723,6 +724,22 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
             if (attempt > 3) return fail(c, MBL_E_MATCH_OVERFLOW, "match buffer overflow persists");
             dcap = h_cnt[1] + 65536;
         }
+#ifdef MBL_DEBUG_ITEMS
+        {
+            uint32_t ni = 0;
+            cudaMemcpy(&ni, ma.item_off + c->dir.n_tiles, 4, cudaMemcpyDeviceToHost);
+            std::vector<MergeItem> hi(ni);
+            cudaMemcpy(hi.data(), ma.items, sizeof(MergeItem) * ni, cudaMemcpyDeviceToHost);
+            std::vector<uint64_t> ql(2 * c->dir.n_tiles + 2);
+            cudaMemcpy(ql.data(), ma.q_lo, 8 * ql.size(), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "items %u (cap %llu) tiles %llu nq %llu\n", ni, (unsigned long long)ma.items_cap, (unsigned long long)c->dir.n_tiles, (unsigned long long)nq);
+            for (uint32_t i = 0; i < ni; ++i)
+                fprintf(stderr, "item %u tile %u q [%llu,%llu) d0 %llu nu %u k0 %llu nk %u base %llx jumbo %lld found %u\n", i, hi[i].tile,
+                        (unsigned long long)hi[i].q_begin, (unsigned long long)hi[i].q_end, (unsigned long long)hi[i].diff_begin, hi[i].n_u16,
+                        (unsigned long long)hi[i].info_begin, hi[i].n_kmers, (unsigned long long)hi[i].base_value, (long long)hi[i].jumbo_off, hi[i].pad);
+            for (uint64_t t = 0; t < c->dir.n_tiles; ++t) fprintf(stderr, "tile %llu q_lo %llu q_hi %llu\n", (unsigned long long)t, (unsigned long long)ql[2*t], (unsigned long long)ql[2*t+1]);
+        }
+#endif
         *n_match = h_cnt[2];
         if (h_cnt[2] > cap || !out) return fail(c, MBL_E_MATCH_OVERFLOW, "match buffer too small");
         host.resize(h_cnt[1]);

@@ -42,7 +42,7 @@ struct Tile {
     uint64_t diff_begin;     // u16 index of the first fragment of the tile's first k-mer
     uint64_t info_begin;     // k-mer index of the tile's first k-mer
     uint64_t base_value;     // value of the k-mer preceding the tile (0 at the stream start)
-    uint64_t first_aa;       // amino-acid part of the tile's first k-mer
+    uint64_t first_aa;       // amino-acid part of the tile's first k-mer, in place (value with the DNA bits cleared)
     uint32_t n_u16;          // fragments in the tile
     uint32_t n_kmers;        // k-mers in the tile (after the Q1 trim of the very last k-mer)
     uint64_t jumbo_off;      // offset into the pre-decoded value array, or ~0 when not jumbo

@@ -181,14 +181,7 @@ struct DpCell { float score; int32_t start, ham, depth; uint32_t smatch, idx, dn
 
 MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge, int min_depth, uint64_t pbase, uint32_t& np) {
     const mbl_match_rec* ml = a.matches;
-    // pre-scan: widest position of the group
-    {
-        uint32_t run = 1;
-        for (uint64_t i = gs + 1; i < ge; ++i) {
-            run = qi_pos(ml[i].qinfo) == qi_pos(ml[i - 1].qinfo) ? run + 1 : 1;
-            if (run > (uint32_t)kDpWidth) return false;
-        }
-    }
+    const uint32_t np_in = np;                       // a position wider than kDpWidth: undo and let the caller fall back
     const bool forward = qi_frame(ml[gs].qinfo) < 3;
     const bool fmt2 = a.par.kmer_format == 2;
     DpCell bufA[kDpWidth], bufB[kDpWidth];
@@ -210,12 +203,19 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
     };
     uint64_t i = gs;
     uint64_t curPos = qi_pos(ml[gs].qinfo);
-    while (i < ge && qi_pos(ml[i].qinfo) == curPos) { load(bufA[ncur++], i); ++i; }
+    bool wide = false;                               // keep going on overflow (results are discarded), no extra control flow
+    while (i < ge && qi_pos(ml[i].qinfo) == curPos) {
+        if (ncur < kDpWidth) load(bufA[ncur++], i); else wide = true;
+        ++i;
+    }
     // one DP step: `cur` holds the paths ending at curPos, `nxt` receives those ending at the next position
     auto step = [&](DpCell* cur, DpCell* nxt) {
         const uint32_t nextPos = qi_pos(ml[i].qinfo);
         nnxt = 0;
-        while (i < ge && qi_pos(ml[i].qinfo) == nextPos) { load(nxt[nnxt++], i); ++i; }
+        while (i < ge && qi_pos(ml[i].qinfo) == nextPos) {
+            if (nnxt < kDpWidth) load(nxt[nnxt++], i); else wide = true;
+            ++i;
+        }
         const int shift = (int)(((uint64_t)nextPos - curPos) / 3);
         if (shift == 1) {
             const uint32_t lowMask = (1u << 21) - 1;
@@ -262,6 +262,7 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
         if (i >= ge) break;
         step(bufB, bufA);
     }
+    if (wide) { np = np_in; return false; }
     return true;
 }
 
@@ -405,7 +406,8 @@ MBL_HD uint32_t list_lower_bound(const uint32_t* list, uint32_t n, uint64_t key)
     return lo;
 }
 
-MBL_HD void score_task_frame_group(const ScoreArgs& a, uint32_t g) {
+MBL_HD void score_task_frame_group(const ScoreArgs& a, uint32_t t) {
+    const uint32_t g = a.fg_order ? a.fg_order[t] : t;             // tasks ordered by group length (k5_score.cu)
     const uint64_t gs = a.fg_list[g];
     const uint64_t ge = g + 1 < a.n_fg ? a.fg_list[g + 1] : a.match_end;
     uint32_t np = 0;

@@ -4,7 +4,8 @@
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-echo "== pytest -m gpu"; timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+echo "== pytest -m gpu"; timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; RC=$?; tail -15 gpurun_out/pytest.log
+if [ $RC -ne 0 ]; then echo "== GPU TESTS FAILED (rc=$RC): stopping here"; tail -60 gpurun_out/pytest.log; exit 1; fi
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
 echo "== tune"; timeout 600 python tools/tune_merge.py --cells 1,2,4 2>&1 | tail -8 | tee gpurun_out/tune.jsonl
 BEST=$(tail -1 gpurun_out/tune.jsonl | python -c "import json,sys; print(json.loads(sys.stdin.read()).get('best_tile_cells',4))" 2>/dev/null || echo 4)
