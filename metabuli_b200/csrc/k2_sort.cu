@@ -87,15 +87,15 @@ __global__ void match_gather_kernel(const mbl_match_rec* __restrict__ in, const 
 // single-pass key: seqID | species | frame | pos / 3.  Inside one (read, frame) the k-mer positions advance in codon steps
 // (and the second mate starts beyond the first), so two distinct positions differ by at least 3 and pos / 3 orders them
 // like pos does with ~1.6 fewer key bits — in the benchmark shape that is one radix pass less.
-__global__ void match_fullkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, int sp_bits, int pos_bits, uint64_t* __restrict__ key,
-                                     uint32_t* __restrict__ idx) {
+__global__ void match_fullkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, int sp_bits, int pos_bits, uint32_t pos_div,
+                                     uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t q = m[i].qinfo;
     uint64_t k = (uint64_t)qi_seq(q);
     k = (k << sp_bits) | (uint64_t)(uint32_t)m[i].species_id;
     k = (k << 3) | (uint64_t)qi_frame(q);
-    k = (k << pos_bits) | (uint64_t)(qi_pos(q) / 3u);
+    k = (k << pos_bits) | (uint64_t)(qi_pos(q) / pos_div);
     key[i] = k;
     idx[i] = (uint32_t)i;
 }
@@ -189,16 +189,17 @@ size_t sort_matches_temp_bytes(size_t n) {
 }
 
 void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
-                  int32_t max_taxid, uint32_t max_pos, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b,
-                  cudaStream_t st) {
+                  int32_t max_taxid, uint32_t max_pos, bool codon_spaced, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a,
+                  uint32_t* idx_b, cudaStream_t st) {
     if (!n) return;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     const int pos_bits = bits_for(max_pos);
     const int sp_bits = bits_for((uint64_t)(uint32_t)max_taxid);
     const int seq_bits = bits_for(n_reads);
-    const int pos3_bits = bits_for(max_pos / 3u);
+    const uint32_t pos_div = codon_spaced ? 3u : 1u;     // true for matches produced by K3 (see match_fullkey_kernel)
+    const int pos3_bits = bits_for(max_pos / pos_div);
     if (seq_bits + sp_bits + 3 + pos3_bits <= 64) {
-        match_fullkey_kernel<<<blocks, 256, 0, st>>>(in, n, sp_bits, pos3_bits, key_a, idx_a);
+        match_fullkey_kernel<<<blocks, 256, 0, st>>>(in, n, sp_bits, pos3_bits, pos_div, key_a, idx_a);
         cub::DoubleBuffer<uint64_t> k(key_a, key_b);
         cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
         MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, seq_bits + sp_bits + 3 + pos3_bits, st));

@@ -224,6 +224,7 @@ merge_kernel(MergeArgs a) {
     const SmemLayout L = smem_layout(a.max_u16, a.max_kmers, a.n_buckets);
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);          // [0] fragments, [1] taxids
     unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 32);                 // [2] claimed item numbers
+    unsigned int* s_chunk = reinterpret_cast<unsigned int*>(smem + 40);                // query chunk cursor of the current item
     MergeItem* s_rec = reinterpret_cast<MergeItem*>(smem + L.off_rec);                 // [2] their records
     uint64_t* s_scan = reinterpret_cast<uint64_t*>(smem + L.off_scan);
     uint16_t* s_ham = reinterpret_cast<uint16_t*>(smem + L.off_ham);
@@ -296,6 +297,7 @@ merge_kernel(MergeArgs a) {
         unsigned int pending = 0;
         if (tid == 0) {
             pending = atomicAdd(a.item_cursor, 1u);           // the item after next; published at the end of this one
+            *s_chunk = kWarps;                                // chunks 0..kWarps-1 are taken (one per warp)
             if (!jumbo) {                                     // this tile's taxids (buffer idle since the last barrier)
                 const uint64_t i0 = it.info_begin & ~3ull, i1 = (it.info_begin + nk + 3ull) & ~3ull;
                 fence_proxy_async();
@@ -365,6 +367,42 @@ merge_kernel(MergeArgs a) {
         //       hit's minimum Hamming sum, sweep 2 keeps the candidates with sum <= min(2*min, 7) (KmerMatcher.cpp:1117-
         //       1146) and writes them, ballot-compacted, as coalesced 24-byte Match rows.
         uint32_t q_head = 0, q_count = 0;
+        // ballot-compact the selected lanes' Match rows (Match.h:9-26 without the vptr) into the staging buffer and write them
+        // as contiguous 8-byte words; Q2: taxid 0 / unmapped species raise the error flag
+        auto emit = [&](bool sel, uint32_t o, uint32_t j, uint32_t oq, uint32_t td, uint32_t sum, const HamQuad& hq) {
+            const uint32_t bal = __ballot_sync(kFull, sel);
+            if (!bal) return;
+            const uint32_t cnt = __popc(bal);
+            const Reservation rs = reserve(chunk, cnt, a.out_count, lane);
+            if (sel) {
+                const uint64_t qinfo = my_qinfo[o];
+                const int32_t taxid = (int32_t)((uint32_t)infos[j] & a.info_mask);
+                const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
+                if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);
+                uint32_t field = 0u;
+                if (sum) field = ham_fields(hq, oq, td, !((qi_frame(qinfo) < 3) ^ fmt2));   // KmerMatcher.cpp:1140
+                uint64_t* w = my_stage + 3u * (uint32_t)__popc(bal & ((1u << lane) - 1));
+                w[0] = qinfo;
+                w[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
+                w[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
+            }
+            __syncwarp();
+            if (cnt <= rs.rem) {                                                    // one contiguous run of slots (the usual case)
+                const uint64_t s0 = rs.old_base + rs.old_used;
+                if (s0 + cnt <= a.out_cap) {
+                    uint64_t* dst = reinterpret_cast<uint64_t*>(a.out + s0);
+                    for (uint32_t w = lane; w < 3u * cnt; w += 32) dst[w] = my_stage[w];
+                }
+            } else {
+                for (uint32_t w = lane; w < 3u * cnt; w += 32) {
+                    const uint32_t r = w / 3u;
+                    const uint64_t sl = slot_of(rs, r);
+                    if (sl < a.out_cap) reinterpret_cast<uint64_t*>(a.out + sl)[w - 3u * r] = my_stage[w];
+                }
+            }
+            __syncwarp();
+            my_matches += cnt;
+        };
         auto process_hits = [&](uint32_t m) {
             const bool valid = (uint32_t)lane < m;
             cp_async_wait_all();                                                    // slot indices of the queued hits
@@ -396,76 +434,72 @@ merge_kernel(MergeArgs a) {
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
             const uint32_t total = __shfl_sync(kFull, incl, 31);
             const uint32_t excl = incl - n;
-            my_own[lane] = 255u;
+            my_own[lane] = 1u;
             __syncwarp();
-            // sweep 1: per-hit minimum (an identical DNA part is the only way to distance 0)
+            // A Hamming sum of 0 needs an identical DNA part, and then min(2*min, 7) = 0 keeps exactly the identical candidates
+            // (KmerMatcher.cpp:1117-1146).  Sweep 1 looks for identical candidates — a compare, no table lookups; sweep 2 emits
+            // them.  Only the hits without one (a few per cent) go through the Hamming tables below.
             for (uint32_t pb = 0; pb < total; pb += 32) {
                 const uint32_t p = pb + lane;
-                const bool pv = p < total;
                 uint32_t o = 0;
 #pragma unroll
                 for (int st = 16; st > 0; st >>= 1) { const uint32_t t = __shfl_sync(kFull, incl, (o + st - 1) & 31); if (t <= p) o += st; }
                 o &= 31u;
                 const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
                 const uint32_t oq = __shfl_sync(kFull, qd, o);
-                if (pv) {
-                    const uint32_t td = (uint32_t)vals[j] & 0xFFFFFFu;
-                    const uint32_t sum = td == oq ? 0u : ham_sum(ham_lookup(s_ham, oq, td));
-                    atomicMin(&my_own[o], sum);
-                }
+                if (p < total && ((uint32_t)vals[j] & 0xFFFFFFu) == oq) my_own[o] = 0u;
             }
             cp_async_wait_all();                                                    // qinfo words
             __syncwarp();
-            // sweep 2: survivors
+            const HamQuad none{0u, 0u, 0u, 0u};
             for (uint32_t pb = 0; pb < total; pb += 32) {
                 const uint32_t p = pb + lane;
-                const bool pv = p < total;
                 uint32_t o = 0;
 #pragma unroll
                 for (int st = 16; st > 0; st >>= 1) { const uint32_t t = __shfl_sync(kFull, incl, (o + st - 1) & 31); if (t <= p) o += st; }
                 o &= 31u;
                 const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
                 const uint32_t oq = __shfl_sync(kFull, qd, o);
-                uint32_t td = 0, sum = 255u;
-                HamQuad hq{0u, 0u, 0u, 0u};
-                if (pv) {
-                    td = (uint32_t)vals[j] & 0xFFFFFFu;
-                    if (td == oq) sum = 0u; else { hq = ham_lookup(s_ham, oq, td); sum = ham_sum(hq); }
+                const bool sel = p < total && ((uint32_t)vals[j] & 0xFFFFFFu) == oq;
+                emit(sel, o, j, oq, oq, 0u, none);
+            }
+            // hits without an identical candidate: the warp takes them one at a time, one candidate per lane
+            uint32_t slow = __ballot_sync(kFull, valid && my_own[lane] != 0u);
+            while (slow) {
+                const int h = __ffs(slow) - 1;
+                slow &= slow - 1u;
+                const uint32_t hg = __shfl_sync(kFull, g0, h), hn = __shfl_sync(kFull, n, h), oq = __shfl_sync(kFull, qd, h);
+                uint32_t mn = 255u;
+                for (uint32_t c = lane; c < hn; c += 32)
+                    mn = min(mn, ham_sum(ham_lookup(s_ham, oq, (uint32_t)vals[hg + c] & 0xFFFFFFu)));
+                mn = __reduce_min_sync(kFull, mn);
+                const uint32_t thr = min(mn * 2u, 7u);                              // KmerMatcher.cpp:1136
+                for (uint32_t cb = 0; cb < hn; cb += 32) {
+                    const uint32_t c = cb + lane;
+                    uint32_t td = 0, sum = 255u;
+                    HamQuad hq{0u, 0u, 0u, 0u};
+                    if (c < hn) { td = (uint32_t)vals[hg + c] & 0xFFFFFFu; hq = ham_lookup(s_ham, oq, td); sum = ham_sum(hq); }
+                    emit(c < hn && sum <= thr, (uint32_t)h, hg + c, oq, td, sum, hq);
                 }
-                const bool sel = pv && sum <= min(my_own[o] * 2u, 7u);                  // KmerMatcher.cpp:1136
-                const uint32_t bal = __ballot_sync(kFull, sel);
-                if (!bal) continue;
-                const uint32_t cnt = __popc(bal);
-                const Reservation rs = reserve(chunk, cnt, a.out_count, lane);
-                if (sel) {
-                    // one 24-byte Match record (Match.h:9-26 without the vptr); Q2: taxid 0 / unmapped species raise the flag
-                    const uint64_t qinfo = my_qinfo[o];
-                    const bool plain = !((qi_frame(qinfo) < 3) ^ fmt2);                 // KmerMatcher.cpp:1140
-                    const int32_t taxid = (int32_t)((uint32_t)infos[j] & a.info_mask);
-                    const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
-                    if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);
-                    const uint32_t field = sum ? ham_fields(hq, oq, td, plain) : 0u;
-                    uint64_t* w = my_stage + 3u * (uint32_t)__popc(bal & ((1u << lane) - 1));
-                    w[0] = qinfo;
-                    w[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
-                    w[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
-                }
-                __syncwarp();
-                for (uint32_t w = lane; w < 3u * cnt; w += 32) {                        // contiguous 8-byte words
-                    const uint32_t r = w / 3u;
-                    const uint64_t sl = slot_of(rs, r);
-                    if (sl < a.out_cap) reinterpret_cast<uint64_t*>(a.out + sl)[w - 3u * r] = my_stage[w];
-                }
-                __syncwarp();
-                my_matches += cnt;
             }
         };
 
-        for (uint64_t qb = it.q_begin + (uint64_t)warp * 32; qb < it.q_end; qb += kThreads) {
-            const uint64_t qi = qb + lane;
+        // 32-query chunks: the first round is fixed (chunk = warp, already in flight), later chunks are claimed from a
+        // shared counter so that no warp idles at the closing barrier for long
+        const uint32_t n_chunks = (uint32_t)((it.q_end - it.q_begin + 31) >> 5);
+        uint32_t ch = (uint32_t)warp;
+        while (ch < n_chunks) {
+            uint32_t ch_next = 0;
+            if (lane == 0) ch_next = atomicAdd(s_chunk, 1u);
+            ch_next = __shfl_sync(kFull, ch_next, 0);
+            const uint64_t qi = it.q_begin + (uint64_t)ch * 32 + lane;
             const bool active = qi < it.q_end;
             const uint64_t qv = qv_next;
-            qv_next = qi + kThreads < it.q_end ? ld_stream_u64(a.q_value + qi + kThreads) : kBlank;
+            {
+                const uint64_t nqi = it.q_begin + (uint64_t)ch_next * 32 + lane;
+                qv_next = (ch_next < n_chunks && nqi < it.q_end) ? ld_stream_u64(a.q_value + nqi) : kBlank;
+            }
+            ch = ch_next;
             const uint64_t q40 = qv >> 24;
             uint32_t g0 = 0;
             bool hit = false;

@@ -59,8 +59,8 @@ void exclusive_sum_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t
 // full reference order (seqID, species, frame, pos, hamming, dna): sorted copy of `in` in `out`
 size_t sort_matches_temp_bytes(size_t n);
 void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
-                  int32_t max_taxid, uint32_t max_pos, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b,
-                  cudaStream_t st);
+                  int32_t max_taxid, uint32_t max_pos, bool codon_spaced, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a,
+                  uint32_t* idx_b, cudaStream_t st);
 size_t order_reads_temp_bytes(size_t n);
 const uint32_t* order_reads_by_matches(void* tmp, size_t tmp_bytes, const uint64_t* seg_b, const uint64_t* seg_e, uint32_t n,
                                        uint32_t chunk_reads, uint32_t* key_a, uint32_t* key_b, uint32_t* idx_a, uint32_t* idx_b, cudaStream_t st);

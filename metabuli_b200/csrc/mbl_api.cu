@@ -321,7 +321,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         StageTimer t(c, MBL_STAGE_MSORT);
         const size_t sm_bytes = sort_matches_temp_bytes(M);
         void* tmp = c->cub_tmp.get<uint8_t>(std::max(sm_bytes, std::max(scan_bytes, sortk_bytes)));
-        sort_matches(tmp, c->cub_tmp.cap, (const mbl_match_rec*)c->m_raw.p, sorted, M, n, c->tax.max_taxid, sb.max_pos, key_a, key_b,
+        sort_matches(tmp, c->cub_tmp.cap, (const mbl_match_rec*)c->m_raw.p, sorted, M, n, c->tax.max_taxid, sb.max_pos, true, key_a, key_b,
                      idx_a, idx_b, st);
         launch_segments(sorted, M, n, seg_b, seg_e, st);
         c->stats.kernel_launches += M ? 4 : 0;
@@ -771,7 +771,7 @@ int mbl_sort_matches(mbl_ctx* c, mbl_match_rec* m, size_t n) {
         mbl_match_rec* sorted = c->m_sorted.get<mbl_match_rec>(n + 1);
         MBL_CUDA(cudaMemcpyAsync(raw, m, sizeof(mbl_match_rec) * n, cudaMemcpyHostToDevice, st));
         void* tmp = c->cub_tmp.get<uint8_t>(sort_matches_temp_bytes(n));
-        sort_matches(tmp, c->cub_tmp.cap, raw, sorted, n, max_seq, max_sp, max_pos, c->key_a.get<uint64_t>(n + 1),
+        sort_matches(tmp, c->cub_tmp.cap, raw, sorted, n, max_seq, max_sp, max_pos, false, c->key_a.get<uint64_t>(n + 1),
                      c->key_b.get<uint64_t>(n + 1), c->idx_a.get<uint32_t>(n + 1), c->idx_b.get<uint32_t>(n + 1), st);
         MBL_CUDA(cudaMemcpyAsync(m, sorted, sizeof(mbl_match_rec) * n, cudaMemcpyDeviceToHost, st));
         MBL_CUDA(cudaStreamSynchronize(st));
