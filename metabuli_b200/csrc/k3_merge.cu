@@ -434,53 +434,43 @@ merge_kernel(MergeArgs a) {
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
             const uint32_t total = __shfl_sync(kFull, incl, 31);
             const uint32_t excl = incl - n;
-            my_own[lane] = 1u;
+            my_own[lane] = 255u;
             __syncwarp();
-            // A Hamming sum of 0 needs an identical DNA part, and then min(2*min, 7) = 0 keeps exactly the identical candidates
-            // (KmerMatcher.cpp:1117-1146).  Sweep 1 looks for identical candidates — a compare, no table lookups; sweep 2 emits
-            // them.  Only the hits without one (a few per cent) go through the Hamming tables below.
+            // sweep 1: per-hit minimum (an identical DNA part is the only way to distance 0)
             for (uint32_t pb = 0; pb < total; pb += 32) {
                 const uint32_t p = pb + lane;
+                const bool pv = p < total;
                 uint32_t o = 0;
 #pragma unroll
                 for (int st = 16; st > 0; st >>= 1) { const uint32_t t = __shfl_sync(kFull, incl, (o + st - 1) & 31); if (t <= p) o += st; }
                 o &= 31u;
                 const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
                 const uint32_t oq = __shfl_sync(kFull, qd, o);
-                if (p < total && ((uint32_t)vals[j] & 0xFFFFFFu) == oq) my_own[o] = 0u;
+                if (pv) {
+                    const uint32_t td = (uint32_t)vals[j] & 0xFFFFFFu;
+                    const uint32_t sum = td == oq ? 0u : ham_sum(ham_lookup(s_ham, oq, td));
+                    atomicMin(&my_own[o], sum);
+                }
             }
             cp_async_wait_all();                                                    // qinfo words
             __syncwarp();
-            const HamQuad none{0u, 0u, 0u, 0u};
+            // sweep 2: survivors
             for (uint32_t pb = 0; pb < total; pb += 32) {
                 const uint32_t p = pb + lane;
+                const bool pv = p < total;
                 uint32_t o = 0;
 #pragma unroll
                 for (int st = 16; st > 0; st >>= 1) { const uint32_t t = __shfl_sync(kFull, incl, (o + st - 1) & 31); if (t <= p) o += st; }
                 o &= 31u;
                 const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
                 const uint32_t oq = __shfl_sync(kFull, qd, o);
-                const bool sel = p < total && ((uint32_t)vals[j] & 0xFFFFFFu) == oq;
-                emit(sel, o, j, oq, oq, 0u, none);
-            }
-            // hits without an identical candidate: the warp takes them one at a time, one candidate per lane
-            uint32_t slow = __ballot_sync(kFull, valid && my_own[lane] != 0u);
-            while (slow) {
-                const int h = __ffs(slow) - 1;
-                slow &= slow - 1u;
-                const uint32_t hg = __shfl_sync(kFull, g0, h), hn = __shfl_sync(kFull, n, h), oq = __shfl_sync(kFull, qd, h);
-                uint32_t mn = 255u;
-                for (uint32_t c = lane; c < hn; c += 32)
-                    mn = min(mn, ham_sum(ham_lookup(s_ham, oq, (uint32_t)vals[hg + c] & 0xFFFFFFu)));
-                mn = __reduce_min_sync(kFull, mn);
-                const uint32_t thr = min(mn * 2u, 7u);                              // KmerMatcher.cpp:1136
-                for (uint32_t cb = 0; cb < hn; cb += 32) {
-                    const uint32_t c = cb + lane;
-                    uint32_t td = 0, sum = 255u;
-                    HamQuad hq{0u, 0u, 0u, 0u};
-                    if (c < hn) { td = (uint32_t)vals[hg + c] & 0xFFFFFFu; hq = ham_lookup(s_ham, oq, td); sum = ham_sum(hq); }
-                    emit(c < hn && sum <= thr, (uint32_t)h, hg + c, oq, td, sum, hq);
+                uint32_t td = 0, sum = 255u;
+                HamQuad hq{0u, 0u, 0u, 0u};
+                if (pv) {
+                    td = (uint32_t)vals[j] & 0xFFFFFFu;
+                    if (td == oq) sum = 0u; else { hq = ham_lookup(s_ham, oq, td); sum = ham_sum(hq); }
                 }
+                emit(pv && sum <= min(my_own[o] * 2u, 7u), o, j, oq, td, sum, hq);      // KmerMatcher.cpp:1136
             }
         };
 
@@ -490,8 +480,12 @@ merge_kernel(MergeArgs a) {
         uint32_t ch = (uint32_t)warp;
         while (ch < n_chunks) {
             uint32_t ch_next = 0;
-            if (lane == 0) ch_next = atomicAdd(s_chunk, 1u);
-            ch_next = __shfl_sync(kFull, ch_next, 0);
+            if (a.dyn_chunks) {
+                if (lane == 0) ch_next = atomicAdd(s_chunk, 1u);
+                ch_next = __shfl_sync(kFull, ch_next, 0);
+            } else {
+                ch_next = ch + kWarps;
+            }
             const uint64_t qi = it.q_begin + (uint64_t)ch * 32 + lane;
             const bool active = qi < it.q_end;
             const uint64_t qv = qv_next;

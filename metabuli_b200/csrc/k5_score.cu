@@ -96,7 +96,7 @@ __global__ void taxcnt_len_kernel(const mbl_read_result* __restrict__ res, uint3
 }
 
 __global__ void compact_taxcnt_kernel(const mbl_read_result* __restrict__ res, uint32_t n, const uint32_t* __restrict__ quot_off,
-                                      const int32_t* __restrict__ pairs_in, const uint32_t* __restrict__ out_off,
+                                      const int32_t* __restrict__ pairs_in, const uint32_t* __restrict__ out_off, uint32_t pair_base,
                                       int32_t* __restrict__ pairs_out, mbl_read_result* __restrict__ res_out) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -104,7 +104,7 @@ __global__ void compact_taxcnt_kernel(const mbl_read_result* __restrict__ res, u
     const int32_t* src = pairs_in + 2ull * quot_off[r];
     int32_t* dst = pairs_out + 2ull * out_off[r];
     for (uint32_t k = 0; k < 2 * x.taxcnt_len; ++k) dst[k] = src[k];
-    x.taxcnt_begin = out_off[r];
+    x.taxcnt_begin = pair_base + out_off[r];         // batch-global: pairs of earlier sub-batches come first
     res_out[r] = x;
 }
 
@@ -116,9 +116,9 @@ void launch_taxcnt_len(const mbl_read_result* results, uint32_t n_reads, uint32_
     taxcnt_len_kernel<<<(n_reads + 1 + 255) / 256, 256, 0, st>>>(results, n_reads, len);
 }
 void launch_compact_taxcnt(const mbl_read_result* results, uint32_t n_reads, const uint32_t* quot_off, const int32_t* pairs_in,
-                           const uint32_t* out_off, int32_t* pairs_out, mbl_read_result* results_out, cudaStream_t st) {
+                           const uint32_t* out_off, uint32_t pair_base, int32_t* pairs_out, mbl_read_result* results_out, cudaStream_t st) {
     if (!n_reads) return;
-    compact_taxcnt_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(results, n_reads, quot_off, pairs_in, out_off, pairs_out, results_out);
+    compact_taxcnt_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(results, n_reads, quot_off, pairs_in, out_off, pair_base, pairs_out, results_out);
 }
 
 }  // namespace mbl

@@ -99,6 +99,7 @@ struct MergeArgs {
     // work list
     uint64_t* q_lo;                 // [2 * (n_tiles + 1)]: per tile first query / one past the last query of its prefix range
     int prefix_shift;               // queries are ordered by value >> prefix_shift only
+    int dyn_chunks;                 // 1: warps claim 32-query chunks from a shared counter, 0: fixed striding
     uint32_t* item_cnt;             // [n_tiles + 1]
     uint32_t* item_off;             // [n_tiles + 1]
     MergeItem* items;
@@ -149,8 +150,8 @@ struct ScoreFlatScratch {
 size_t score_flat_temp_bytes(size_t n_matches);
 void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch& s, cudaStream_t st);
 void launch_compact_taxcnt(const mbl_read_result* results, uint32_t n_reads, const uint32_t* quot_off,
-                           const int32_t* pairs_in, const uint32_t* out_off, int32_t* pairs_out, mbl_read_result* results_out,
-                           cudaStream_t st);
+                           const int32_t* pairs_in, const uint32_t* out_off, uint32_t pair_base, int32_t* pairs_out,
+                           mbl_read_result* results_out, cudaStream_t st);
 void launch_taxcnt_len(const mbl_read_result* results, uint32_t n_reads, uint32_t* len, cudaStream_t st);
 
 }  // namespace mbl

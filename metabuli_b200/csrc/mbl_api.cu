@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -48,6 +49,7 @@ struct mbl_ctx {
     uint16_t* d_ham_pair = nullptr;
     uint8_t* d_ham_single = nullptr;
     uint32_t tile_cells = 4;
+    int dyn_chunks = 1;                 // MBL_DYN_CHUNKS
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // index
     uint16_t* d_diff = nullptr;
@@ -136,8 +138,7 @@ void free_db(mbl_ctx* c) {
 // QueryIndexer.cpp:30-147, with the HBM budget in place of --max-ram)
 void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
     c->subs.clear();
-    SubBatch cur{0, 0, 0, 0, 0};
-    for (uint32_t r = 0; r < b->n_reads; ++r) {
+    auto read_cost = [&](uint32_t r, uint64_t& s, uint64_t& q, uint32_t& mp) {
         int l1 = (int)(b->offsets[r + 1] - b->offsets[r]);
         int w1 = windows_per_frame(l1), c1 = max_covered_length(l1), w2 = 0, c2 = 0;
         if (b->offsets2) {
@@ -145,15 +146,47 @@ void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
             w2 = windows_per_frame(l2); c2 = max_covered_length(l2);
         }
         bool empty = w1 < 1 || (b->offsets2 && w2 < 1);
-        uint64_t s = empty ? 0 : 6ull * (uint64_t)(w1 + w2);
+        s = empty ? 0 : 6ull * (uint64_t)(w1 + w2);
         int ql = c1 + c2;
-        uint64_t q = ql + 3 > 0 ? (uint64_t)((ql + 3) / 3 + 1) : 1;
+        q = ql + 3 > 0 ? (uint64_t)((ql + 3) / 3 + 1) : 1;
+        mp = (uint32_t)std::max(0, c1 + 3 + c2 + 8);
+    };
+    // common case first: the whole batch fits one sub-batch — totals over a few host threads (this runs while the reads are
+    // still on their way to the device)
+    const uint32_t n = b->n_reads;
+    const unsigned T = n > (1u << 18) ? 8u : 1u;
+    std::vector<SubBatch> part(T, SubBatch{0, 0, 0, 0, 0});
+    auto work = [&](unsigned t) {
+        const uint32_t r0 = (uint32_t)((uint64_t)n * t / T), r1 = (uint32_t)((uint64_t)n * (t + 1) / T);
+        SubBatch acc{r0, r1, 0, 0, 0};
+        for (uint32_t r = r0; r < r1; ++r) {
+            uint64_t s, q; uint32_t mp;
+            read_cost(r, s, q, mp);
+            acc.slots += s; acc.quots += q; acc.max_pos = std::max(acc.max_pos, mp);
+        }
+        part[t] = acc;
+    };
+    if (T > 1) {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    } else {
+        work(0);
+    }
+    SubBatch all{0, n, 0, 0, 0};
+    for (const SubBatch& p : part) { all.slots += p.slots; all.quots += p.quots; all.max_pos = std::max(all.max_pos, p.max_pos); }
+    if (n == 0) return;
+    if (all.slots <= max_slots && all.quots <= 0xF0000000ull) { c->subs.push_back(all); return; }
+    SubBatch cur{0, 0, 0, 0, 0};
+    for (uint32_t r = 0; r < n; ++r) {
+        uint64_t s, q; uint32_t mp;
+        read_cost(r, s, q, mp);
         if (cur.r1 > cur.r0 && (cur.slots + s > max_slots || cur.quots + q > 0xF0000000ull)) {
             c->subs.push_back(cur);
             cur = SubBatch{r, r, 0, 0, 0};
         }
         cur.r1 = r + 1; cur.slots += s; cur.quots += q;
-        uint32_t mp = (uint32_t)std::max(0, c1 + 3 + c2 + 8);
         cur.max_pos = std::max(cur.max_pos, mp);
     }
     if (cur.r1 > cur.r0) c->subs.push_back(cur);
@@ -256,6 +289,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
     ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
     ma.prefix_shift = c->dir.sort_begin_bit;
+    ma.dyn_chunks = c->dyn_chunks;
     ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
     ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
     ma.items_cap = c->dir.n_tiles + n_query / kItemQueries + 2;
@@ -403,7 +437,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
             c->pairs.release();
             c->pairs = nb;
         }
-        launch_compact_taxcnt(sa.results, n, quot_off, sa.taxcnt_pairs, to, (int32_t*)c->pairs.p + 2 * c->n_pairs,
+        launch_compact_taxcnt(sa.results, n, quot_off, sa.taxcnt_pairs, to, (uint32_t)c->n_pairs, (int32_t*)c->pairs.p + 2 * c->n_pairs,
                               (mbl_read_result*)c->results.p + sb.r0, st);
         c->stats.kernel_launches += 3;
         t.stop();
@@ -442,6 +476,7 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         c->d_codon = upload(c, t.codon, 512);
         c->d_ham_pair = upload(c, t.ham_pair, 4096);
         c->d_ham_single = upload(c, t.ham_sum, 64);
+        if (const char* e = getenv("MBL_DYN_CHUNKS")) c->dyn_chunks = atoi(e) != 0;
         if (const char* e = getenv("MBL_SORT_BIT")) { int v = atoi(e); if (v == 24 || v == 32 || v == 40) c->force_sort_bit = v; }
         if (const char* e = getenv("MBL_TILE_CELLS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->tile_cells = (uint32_t)v; }
         MBL_CUDA(cudaStreamSynchronize(c->st));
@@ -528,8 +563,8 @@ int mbl_upload_batch(mbl_ctx* c, const mbl_batch* b) {
             MBL_CUDA(cudaMemcpyAsync(d2, b->bases2, nb2, cudaMemcpyHostToDevice, c->st));
             MBL_CUDA(cudaMemcpyAsync(c->off2.get<uint64_t>(n + 1), b->offsets2, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->st));
         }
+        plan_sub_batches(c, b, slots_budget(c));             // host work overlaps the copies
         t.stop();
-        plan_sub_batches(c, b, slots_budget(c));
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
     }
@@ -568,13 +603,6 @@ int mbl_download_results(mbl_ctx* c, mbl_read_result* out, int32_t* taxcnt_pairs
         if (c->n_reads) MBL_CUDA(cudaMemcpyAsync(out, c->results.p, sizeof(mbl_read_result) * (size_t)c->n_reads, cudaMemcpyDeviceToHost, c->st));
         if (c->n_pairs && taxcnt_pairs) MBL_CUDA(cudaMemcpyAsync(taxcnt_pairs, c->pairs.p, 8 * c->n_pairs, cudaMemcpyDeviceToHost, c->st));
         t.stop();
-        // taxcnt_begin is relative to the sub-batch's first pair: make it batch-global
-        uint64_t base = 0;
-        for (const SubBatch& sb : c->subs) {
-            uint64_t cnt = 0;
-            for (uint32_t r = sb.r0; r < sb.r1; ++r) { out[r].taxcnt_begin += (uint32_t)base; cnt += out[r].taxcnt_len; }
-            base += cnt;
-        }
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
     }
@@ -701,6 +729,7 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
         ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
         ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
         ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
+        ma.dyn_chunks = c->dyn_chunks;
         ma.prefix_shift = 24;                // the stage API takes fully ordered queries; any coarser grouping is valid too
         ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
         ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
@@ -836,7 +865,7 @@ int mbl_score(mbl_ctx* c, const mbl_match_rec* sorted_h, size_t M, uint32_t n, c
         if (total > cap_pairs) return fail(c, MBL_E_CAPACITY, "taxcnt_pairs too small");
         int32_t* pc = c->pairs.get<int32_t>(2 * (size_t)total + 2);
         mbl_read_result* rc = c->results.get<mbl_read_result>(n + 1);
-        launch_compact_taxcnt(sa.results, n, quot_off, sa.taxcnt_pairs, to, pc, rc, st);
+        launch_compact_taxcnt(sa.results, n, quot_off, sa.taxcnt_pairs, to, 0u, pc, rc, st);
         MBL_CUDA(cudaMemcpyAsync(out, rc, sizeof(mbl_read_result) * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (total && taxcnt_pairs) MBL_CUDA(cudaMemcpyAsync(taxcnt_pairs, pc, 8 * (size_t)total, cudaMemcpyDeviceToHost, st));
         MBL_CUDA(cudaStreamSynchronize(st));

@@ -7,6 +7,7 @@ export PYTHONUNBUFFERED=1
 echo "== pytest -m gpu"; timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; RC=$?; tail -15 gpurun_out/pytest.log
 if [ $RC -ne 0 ]; then echo "== GPU TESTS FAILED (rc=$RC): stopping here"; tail -60 gpurun_out/pytest.log; exit 1; fi
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
+if [ "${1:-}" = "tune" ]; then echo "== tune only"; timeout 600 python tools/tune_merge.py --cells ${TUNE_CELLS:-2} --env "${TUNE_ENV:-MBL_DYN_CHUNKS=0,1}" 2>&1 | tail -8 | cut -c1-400; exit 0; fi
 echo "== tune"; timeout 600 python tools/tune_merge.py --cells 1,2,4 2>&1 | tail -8 | tee gpurun_out/tune.jsonl
 BEST=$(tail -1 gpurun_out/tune.jsonl | python -c "import json,sys; print(json.loads(sys.stdin.read()).get('best_tile_cells',4))" 2>/dev/null || echo 4)
 export MBL_TILE_CELLS=${MBL_TILE_CELLS_FORCE:-$BEST}
