@@ -108,6 +108,14 @@ __global__ void compact_taxcnt_kernel(const mbl_read_result* __restrict__ res, u
     res_out[r] = x;
 }
 
+__global__ void shift_taxcnt_kernel(mbl_read_result* __restrict__ res, uint32_t n, uint32_t delta) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) res[r].taxcnt_begin += delta;
+}
+void launch_shift_taxcnt(mbl_read_result* results, uint32_t n_reads, uint32_t delta, cudaStream_t st) {
+    if (n_reads) shift_taxcnt_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(results, n_reads, delta);
+}
+
 void launch_score(const ScoreArgs& a, cudaStream_t st) {
     if (!a.n_reads) return;
     score_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);

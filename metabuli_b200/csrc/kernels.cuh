@@ -152,6 +152,8 @@ void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch
 void launch_compact_taxcnt(const mbl_read_result* results, uint32_t n_reads, const uint32_t* quot_off,
                            const int32_t* pairs_in, const uint32_t* out_off, uint32_t pair_base, int32_t* pairs_out,
                            mbl_read_result* results_out, cudaStream_t st);
+// taxcnt_begin += delta (mod 2^32) for a range of reads: re-bases a sub-batch's pair offsets inside the batch's pair array
+void launch_shift_taxcnt(mbl_read_result* results, uint32_t n_reads, uint32_t delta, cudaStream_t st);
 void launch_taxcnt_len(const mbl_read_result* results, uint32_t n_reads, uint32_t* len, cudaStream_t st);
 
 }  // namespace mbl

@@ -49,7 +49,7 @@ struct mbl_ctx {
     uint16_t* d_ham_pair = nullptr;
     uint8_t* d_ham_single = nullptr;
     uint32_t tile_cells = 4;
-    int dyn_chunks = 1;                 // MBL_DYN_CHUNKS
+    int dyn_chunks = 0;                 // MBL_DYN_CHUNKS (measured: no gain over fixed striding)
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // index
     uint16_t* d_diff = nullptr;
@@ -75,8 +75,17 @@ struct mbl_ctx {
     Buf q_tax, q_ham, q_has, pairs_raw;
     Buf q_lo, item_cnt, item_off, items, counters;
     // results of the whole batch
-    Buf results, pairs;
-    uint64_t n_pairs = 0;
+    Buf results, pairs, pairs_final;
+    uint64_t n_pairs = 0;               // pairs written by this lane
+    const void* pairs_out = nullptr;    // what mbl_download_results copies (pairs, or pairs_final after a two-lane run)
+    uint64_t n_pairs_total = 0;
+    // second pipeline lane: a context with its own stream and workspace that shares the index, the tables, the resident
+    // reads and the result array.  Sub-batches alternate between the lanes (two host threads), so the latency-bound
+    // scoring kernels of one sub-batch overlap the bandwidth-bound sorts of the other.
+    mbl_ctx* shadow = nullptr;
+    bool is_shadow = false;
+    int pipeline = 1;                   // MBL_PIPELINE=0 switches the second lane off
+    uint32_t pipeline_min_reads = 1u << 21;   // MBL_PIPELINE_MIN_READS: smaller batches stay on one lane
     double match_ratio = 0.0;   // matches per slot seen so far (sizes the match buffer)
     mbl_stats stats{};
 };
@@ -154,7 +163,8 @@ void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
     // common case first: the whole batch fits one sub-batch — totals over a few host threads (this runs while the reads are
     // still on their way to the device)
     const uint32_t n = b->n_reads;
-    const unsigned T = n > (1u << 18) ? 8u : 1u;
+    const bool may_split = c->pipeline && n >= c->pipeline_min_reads && n >= 16;
+    const unsigned T = (n > (1u << 18) || may_split) ? 8u : 1u;
     std::vector<SubBatch> part(T, SubBatch{0, 0, 0, 0, 0});
     auto work = [&](unsigned t) {
         const uint32_t r0 = (uint32_t)((uint64_t)n * t / T), r1 = (uint32_t)((uint64_t)n * (t + 1) / T);
@@ -177,7 +187,23 @@ void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
     SubBatch all{0, n, 0, 0, 0};
     for (const SubBatch& p : part) { all.slots += p.slots; all.quots += p.quots; all.max_pos = std::max(all.max_pos, p.max_pos); }
     if (n == 0) return;
-    if (all.slots <= max_slots && all.quots <= 0xF0000000ull) { c->subs.push_back(all); return; }
+    // large batches are cut in (at least) two so that the two pipeline lanes overlap (mbl_classify_resident); each lane then
+    // owns half of the workspace budget
+    const bool split = may_split;
+    if (!split && all.slots <= max_slots && all.quots <= 0xF0000000ull) { c->subs.push_back(all); return; }
+    if (split) {
+        max_slots /= 2;
+        SubBatch h[2] = {SubBatch{0, 0, 0, 0, 0}, SubBatch{0, 0, 0, 0, 0}};
+        for (unsigned t = 0; t < T; ++t) {
+            SubBatch& d = h[t >= T / 2];
+            if (d.r1 == d.r0) d.r0 = part[t].r0;
+            d.r1 = part[t].r1; d.slots += part[t].slots; d.quots += part[t].quots; d.max_pos = std::max(d.max_pos, part[t].max_pos);
+        }
+        if (h[0].slots <= max_slots && h[1].slots <= max_slots && h[0].quots <= 0xF0000000ull && h[1].quots <= 0xF0000000ull) {
+            c->subs.push_back(h[0]); c->subs.push_back(h[1]);
+            return;
+        }
+    }
     SubBatch cur{0, 0, 0, 0, 0};
     for (uint32_t r = 0; r < n; ++r) {
         uint64_t s, q; uint32_t mp;
@@ -477,6 +503,8 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         c->d_ham_pair = upload(c, t.ham_pair, 4096);
         c->d_ham_single = upload(c, t.ham_sum, 64);
         if (const char* e = getenv("MBL_DYN_CHUNKS")) c->dyn_chunks = atoi(e) != 0;
+        if (const char* e = getenv("MBL_PIPELINE")) c->pipeline = atoi(e) != 0;
+        if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }
         if (const char* e = getenv("MBL_SORT_BIT")) { int v = atoi(e); if (v == 24 || v == 32 || v == 40) c->force_sort_bit = v; }
         if (const char* e = getenv("MBL_TILE_CELLS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->tile_cells = (uint32_t)v; }
         MBL_CUDA(cudaStreamSynchronize(c->st));
@@ -489,21 +517,60 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
     return MBL_OK;
 }
 
+namespace {
+void release_lane(mbl_ctx* c) {
+    if (c->is_shadow) {             // borrowed from the owning context
+        for (Buf* b : {&c->bases1, &c->bases2, &c->off1, &c->off2, &c->results}) { b->p = nullptr; b->cap = 0; }
+    }
+    for (Buf* b : {&c->bases1, &c->bases2, &c->off1, &c->off2, &c->cov1, &c->cov2, &c->w1, &c->w2, &c->slots, &c->slot_off, &c->quot_cnt,
+                   &c->quot_off, &c->seg_b, &c->seg_e, &c->res_sub, &c->tax_len, &c->tax_off, &c->val_a, &c->val_b, &c->qi_a, &c->qi_b,
+                   &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->order_keys, &c->g_np, &c->flag_fg, &c->flag_sp, &c->fg_list, &c->sp_list,
+                   &c->fg_ord, &c->flat_tmp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start,
+                   &c->l_ham, &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score, &c->p_ham, &c->p_depth,
+                   &c->p_smatch, &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw,
+                   &c->q_lo, &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs, &c->pairs_final})
+        b->release();
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->st) cudaStreamDestroy(c->st);
+}
+
+// the second lane: shares everything that is read-only during a batch
+mbl_ctx* ensure_shadow(mbl_ctx* c) {
+    if (!c->shadow) {
+        mbl_ctx* s = new mbl_ctx();
+        s->is_shadow = true;
+        s->cfg = c->cfg; s->sm_count = c->sm_count;
+        MBL_CUDA(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+        for (auto& e : s->ev) MBL_CUDA(cudaEventCreate(&e));
+        c->shadow = s;
+    }
+    mbl_ctx* s = c->shadow;
+    s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
+    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks;
+    s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
+    s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded;
+    s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed
+    s->n_reads = c->n_reads; s->paired = c->paired;
+    s->match_ratio = c->match_ratio;
+    s->n_pairs = 0;
+    s->stats = mbl_stats{};
+    return s;
+}
+}  // namespace
+
 void mbl_destroy(mbl_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->st);
+    if (c->shadow) {
+        cudaStreamSynchronize(c->shadow->st);
+        release_lane(c->shadow);
+        delete c->shadow;
+        c->shadow = nullptr;
+    }
     free_db(c);
-    for (Buf* b : {&c->bases1, &c->bases2, &c->off1, &c->off2, &c->cov1, &c->cov2, &c->w1, &c->w2, &c->slots, &c->slot_off, &c->quot_cnt,
-                   &c->quot_off, &c->seg_b, &c->seg_e, &c->res_sub, &c->tax_len, &c->tax_off, &c->val_a, &c->val_b, &c->qi_a, &c->qi_b,
-                   &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->order_keys, &c->g_np, &c->flag_fg, &c->flag_sp, &c->fg_list, &c->sp_list, &c->fg_ord, &c->flat_tmp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start, &c->l_ham,
-                   &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score, &c->p_ham, &c->p_depth, &c->p_smatch,
-                   &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw, &c->q_lo,
-                   &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs})
-        b->release();
     cudaFree(c->d_base_code); cudaFree(c->d_codon); cudaFree(c->d_ham_pair); cudaFree(c->d_ham_single);
-    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
-    if (c->st) cudaStreamDestroy(c->st);
+    release_lane(c);
     delete c;
 }
 
@@ -582,9 +649,68 @@ int mbl_classify_resident(mbl_ctx* c) {
         c->n_pairs = 0;
         c->results.get<mbl_read_result>(c->n_reads + 1);
         c->stats.sub_batches = (uint32_t)c->subs.size();
-        for (const SubBatch& sb : c->subs) {
-            int rc = run_sub_batch(c, sb);
-            if (rc != MBL_OK) return rc;
+        struct SubDone { int lane; uint64_t lane_off, count; };
+        std::vector<SubDone> done(c->subs.size(), SubDone{0, 0, 0});
+        const bool two = c->pipeline && c->subs.size() >= 2;
+        mbl_ctx* s = two ? ensure_shadow(c) : nullptr;
+        int rc1 = MBL_OK;
+        std::thread lane1;
+        if (two) {
+            lane1 = std::thread([&] {
+                cudaSetDevice(c->cfg.device);
+                try {
+                    for (size_t k = 1; k < c->subs.size(); k += 2) {
+                        const uint64_t off = s->n_pairs;
+                        rc1 = run_sub_batch(s, c->subs[k]);
+                        if (rc1 != MBL_OK) break;
+                        done[k] = SubDone{1, off, s->n_pairs - off};
+                    }
+                } catch (const CudaError& e) {
+                    rc1 = fail_cuda(s, e);
+                }
+            });
+        }
+        int rc0 = MBL_OK;
+        try {
+            for (size_t k = 0; k < c->subs.size(); k += two ? 2 : 1) {
+                const uint64_t off = c->n_pairs;
+                rc0 = run_sub_batch(c, c->subs[k]);
+                if (rc0 != MBL_OK) break;
+                done[k] = SubDone{0, off, c->n_pairs - off};
+            }
+        } catch (const CudaError& e) {
+            rc0 = fail_cuda(c, e);
+        }
+        if (two) lane1.join();
+        if (rc0 != MBL_OK) return rc0;
+        if (rc1 != MBL_OK) { c->err = s->err; return rc1; }
+        c->pairs_out = c->pairs.p;
+        c->n_pairs_total = c->n_pairs;
+        if (two) {
+            // per-stage times of the two lanes add up (they overlap in wall-clock time); counts add up
+            for (int i = 0; i < 7; ++i) if (i != MBL_STAGE_H2D) c->stats.ms[i] += s->stats.ms[i];
+            c->stats.merge_kernel_ms += s->stats.merge_kernel_ms; c->stats.n_query_kmers += s->stats.n_query_kmers;
+            c->stats.n_matches += s->stats.n_matches; c->stats.merge_bytes += s->stats.merge_bytes;
+            c->stats.merge_launches += s->stats.merge_launches; c->stats.kernel_launches += s->stats.kernel_launches;
+            c->stats.overflow_retries += s->stats.overflow_retries;
+            c->match_ratio = std::max(c->match_ratio, s->match_ratio);
+            // the batch's pair array: the sub-batches' pairs in sub-batch order
+            uint64_t total = 0;
+            for (const SubDone& d : done) total += d.count;
+            int32_t* fin = c->pairs_final.get<int32_t>(2 * total + 2);
+            uint64_t base = 0;
+            for (size_t k = 0; k < done.size(); ++k) {
+                const SubDone& d = done[k];
+                const mbl_ctx* src = d.lane ? s : c;
+                if (d.count) MBL_CUDA(cudaMemcpyAsync(fin + 2 * base, (const int32_t*)src->pairs.p + 2 * d.lane_off, 8 * d.count, cudaMemcpyDeviceToDevice, c->st));
+                if (base != d.lane_off)
+                    launch_shift_taxcnt((mbl_read_result*)c->results.p + c->subs[k].r0, c->subs[k].r1 - c->subs[k].r0,
+                                        (uint32_t)(base - d.lane_off), c->st);
+                base += d.count;
+            }
+            c->pairs_out = fin;
+            c->n_pairs_total = total;
+            c->stats.kernel_launches += (uint32_t)done.size();
         }
         MBL_CUDA(cudaStreamSynchronize(c->st));
     } catch (const CudaError& e) {
@@ -597,11 +723,11 @@ int mbl_download_results(mbl_ctx* c, mbl_read_result* out, int32_t* taxcnt_pairs
     if (!c || !out) return fail(c, MBL_E_BAD_ARG, "null argument");
     try {
         MBL_CUDA(cudaSetDevice(c->cfg.device));
-        if (used_pairs) *used_pairs = c->n_pairs;
-        if (c->n_pairs > cap_pairs) return fail(c, MBL_E_CAPACITY, "taxcnt_pairs too small");
+        if (used_pairs) *used_pairs = c->n_pairs_total;
+        if (c->n_pairs_total > cap_pairs) return fail(c, MBL_E_CAPACITY, "taxcnt_pairs too small");
         StageTimer t(c, MBL_STAGE_D2H);
         if (c->n_reads) MBL_CUDA(cudaMemcpyAsync(out, c->results.p, sizeof(mbl_read_result) * (size_t)c->n_reads, cudaMemcpyDeviceToHost, c->st));
-        if (c->n_pairs && taxcnt_pairs) MBL_CUDA(cudaMemcpyAsync(taxcnt_pairs, c->pairs.p, 8 * c->n_pairs, cudaMemcpyDeviceToHost, c->st));
+        if (c->n_pairs_total && taxcnt_pairs) MBL_CUDA(cudaMemcpyAsync(taxcnt_pairs, c->pairs_out, 8 * c->n_pairs_total, cudaMemcpyDeviceToHost, c->st));
         t.stop();
     } catch (const CudaError& e) {
         return fail_cuda(c, e);

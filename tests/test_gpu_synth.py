@@ -96,3 +96,22 @@ def test_query_sort_granularity(sort_bit, golden_dir, monkeypatch):
             assert tsv == gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
         finally:
             clf.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["multi_se", "multi_pe", "ragged_se"])
+def test_two_lane_pipeline(name, golden_dir, monkeypatch):
+    """Large batches are cut in two and run on two pipeline lanes (two host threads, two streams, shared index); forcing
+    that path on a small batch must still give the reference's TSV, including the per-read (taxid, count) lists."""
+    from metabuli_b200 import Classifier, ClassifyOptions
+    monkeypatch.setenv("MBL_PIPELINE_MIN_READS", "64")
+    sdb, reads, seq_mode = synth_cases.build(name)
+    clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
+    try:
+        for _ in range(2):          # second call reuses both workspaces
+            res, pairs = clf.classify_batch(*reads)
+            assert clf.stats()["sub_batches"] == 2
+            tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
+            assert tsv == gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
+    finally:
+        clf.close()
