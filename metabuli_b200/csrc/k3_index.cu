@@ -144,8 +144,12 @@ __global__ void tile_prefix_kernel(const Tile* __restrict__ tiles, uint64_t n_ti
 }
 
 // -------------------------------------------------------------------------------------------------
+namespace { struct AddU64 { __host__ __device__ uint64_t operator()(uint64_t a, uint64_t b) const { return a + b; } }; }
+
+// base_value: value the first delta of the stream is relative to (0 for a whole diffIdx file, the preceding k-mer's value for a
+// shard that starts inside the file, mbl_plan_shards); holds_db_tail: the stream ends with the numerically last k-mer of the DB (Q1)
 void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
-                          cudaStream_t st, TileDirectory& dir) {
+                          cudaStream_t st, TileDirectory& dir, uint64_t base_value, bool holds_db_tail) {
     dir = TileDirectory();
     if (tile_cells < 1) tile_cells = 1;
     dir.tile_cells = tile_cells;
@@ -154,7 +158,7 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
     if (n_u16 == 0 || n_kmers == 0) return;
     const uint64_t n_cells = (n_u16 + kCellU16 - 1) / kCellU16;
     const uint64_t n_grid = (n_cells + tile_cells - 1) / tile_cells;
-    const uint64_t n_kmers_eff = n_kmers - 1;                       // Q1
+    const uint64_t n_kmers_eff = n_kmers - (holds_db_tail ? 1 : 0);   // Q1
     uint64_t *cell_cnt, *cell_sum, *b_kidx, *b_off, *b_base, *b_aa, *cand;
     uint32_t *flag, *rank;
     MBL_CUDA(cudaMalloc(&cell_cnt, 8 * (n_cells + 1)));
@@ -174,10 +178,12 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cell_cnt, dir.cell_k, n_cells, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb2, flag, rank, n_grid + 1, st);
     tmp_bytes = std::max(tmp_bytes, tb2);
+    cub::DeviceScan::ExclusiveScan(nullptr, tb2, cell_sum, dir.cell_v, AddU64(), base_value, n_cells, st);
+    tmp_bytes = std::max(tmp_bytes, tb2);
     void* tmp;
     MBL_CUDA(cudaMalloc(&tmp, tmp_bytes));
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cell_cnt, dir.cell_k, n_cells, st);
-    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cell_sum, dir.cell_v, n_cells, st);
+    cub::DeviceScan::ExclusiveScan(tmp, tmp_bytes, cell_sum, dir.cell_v, AddU64(), base_value, n_cells, st);
     cell_boundary_kernel<<<blocks, kWarps * 32, 0, st>>>(d_diff, n_u16, n_cells, dir.cell_k, dir.cell_v, b_kidx, b_off, b_base, b_aa);
     tile_candidate_kernel<<<(unsigned)((n_grid + 255) / 256), 256, 0, st>>>(b_kidx, n_cells, n_grid, tile_cells, cand);
     MBL_CUDA(cudaMemsetAsync(flag, 0, 4 * (n_grid + 1), st));

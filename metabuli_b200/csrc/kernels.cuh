@@ -69,7 +69,7 @@ void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, ui
 
 // K3 directory (load time)
 void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
-                          cudaStream_t st, TileDirectory& dir);
+                          cudaStream_t st, TileDirectory& dir, uint64_t base_value = 0, bool holds_db_tail = true);
 void free_tile_directory(TileDirectory& dir);
 
 // K3 merge (per batch)

@@ -48,7 +48,7 @@ struct mbl_ctx {
     uint8_t *d_base_code = nullptr, *d_codon = nullptr;
     uint16_t* d_ham_pair = nullptr;
     uint8_t* d_ham_single = nullptr;
-    uint32_t tile_cells = 4;
+    uint32_t tile_cells = 2;            // MBL_TILE_CELLS (measured best on the 8 GiB benchmark index: 3 CTAs per SM)
     int dyn_chunks = 0;                 // MBL_DYN_CHUNKS (measured: no gain over fixed striding)
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // index
@@ -84,7 +84,7 @@ struct mbl_ctx {
     // scoring kernels of one sub-batch overlap the bandwidth-bound sorts of the other.
     mbl_ctx* shadow = nullptr;
     bool is_shadow = false;
-    int pipeline = 1;                   // MBL_PIPELINE=0 switches the second lane off
+    int pipeline = 0;                   // MBL_PIPELINE=1 switches the second lane on (measured slower: the lanes contend and the index is streamed twice)
     uint32_t pipeline_min_reads = 1u << 21;   // MBL_PIPELINE_MIN_READS: smaller batches stay on one lane
     double match_ratio = 0.0;   // matches per slot seen so far (sizes the match buffer)
     mbl_stats stats{};
@@ -239,8 +239,11 @@ uint64_t slots_budget(mbl_ctx* c) {
     return s;
 }
 
-// the pipeline over one sub-batch of resident reads
-int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
+// ---- the pipeline over one sub-batch of resident reads, in three stages -------------------------------------------------
+// (the index-sharded mode runs the same stages with an exchange between them, see mbl_shard_* below)
+
+// K1: per-read metadata + metamer extraction into the phase-1 arena (value A | value B | qinfo | slot idx A | slot idx B)
+void stage_extract(mbl_ctx* c, const SubBatch& sb) {
     cudaStream_t st = c->st;
     const uint32_t n = sb.r1 - sb.r0;
     const uint64_t S = sb.slots;
@@ -249,15 +252,12 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     const uint8_t* bases2 = c->paired ? (const uint8_t*)c->bases2.p : nullptr;
     const uint64_t* off1 = (const uint64_t*)c->off1.p + sb.r0;
     const uint64_t* off2 = c->paired ? (const uint64_t*)c->off2.p + sb.r0 : nullptr;
-
     int32_t *cov1 = c->cov1.get<int32_t>(n), *cov2 = c->cov2.get<int32_t>(n), *w1 = c->w1.get<int32_t>(n), *w2 = c->w2.get<int32_t>(n);
     uint64_t *slots = c->slots.get<uint64_t>(n + 1), *slot_off = c->slot_off.get<uint64_t>(n + 1);
     uint32_t *quot_cnt = c->quot_cnt.get<uint32_t>(n + 1), *quot_off = c->quot_off.get<uint32_t>(n + 1);
     const size_t scan_bytes = std::max(scan_temp_bytes(n + 1), scan_temp_bytes(c->dir.n_tiles + 2));
     const size_t sortk_bytes = sort_kmers_temp_bytes(S);
     unsigned long long* counters = c->counters.get<unsigned long long>(8);   // [0] n_valid [1] reserved [2] matches [3] err|cursor
-
-    // ---- K1 ------------------------------------------------------------------------------------------
     {
         StageTimer t(c, MBL_STAGE_EXTRACT);
         MBL_CUDA(cudaMemsetAsync(counters, 0, 64, st));
@@ -276,11 +276,21 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         c->stats.kernel_launches += 2;
         t.stop();
     }
-    // ---- K2 ------------------------------------------------------------------------------------------
-    uint64_t *qv = nullptr, *qi = nullptr;
+}
+
+// K2 + K3: sort the S slots in the phase-1 arena (keys in `value A`, slot indices in `slot idx A`) and merge them against the
+// resident index; q_info is the array the slot indices point into.  -> rows written to m_raw (blank tails included), matches
+int stage_sort_merge(mbl_ctx* c, uint64_t S, const uint64_t* q_info, bool count_valid_on_device, uint64_t* reserved_out, uint64_t* n_match_out) {
+    cudaStream_t st = c->st;
+    const uint64_t S8 = (S + 31) & ~31ull;
+    const size_t scan_bytes = scan_temp_bytes(c->dir.n_tiles + 2);
+    const size_t sortk_bytes = sort_kmers_temp_bytes(S);
+    unsigned long long* counters = c->counters.get<unsigned long long>(8);
+    uint64_t *qv = nullptr;
     uint32_t* qidx = nullptr;
     {
         StageTimer t(c, MBL_STAGE_SORT);
+        c->cub_tmp.get<uint8_t>(std::max(scan_bytes, sortk_bytes));
         uint64_t* ar = (uint64_t*)c->arena.p;
         uint64_t *va = ar, *vb = ar + S8;
         uint32_t *ia = reinterpret_cast<uint32_t*>(ar + 3 * S8), *ib = ia + S8;
@@ -288,13 +298,16 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
         if (S) sort_kmers_idx(c->cub_tmp.p, c->cub_tmp.cap, va, vb, ia, ib, S, c->dir.sort_begin_bit, in_b, st);
         qv = in_b ? vb : va;
         qidx = in_b ? ib : ia;
-        qi = ar + 2 * S8;
         t.stop();
     }
+    const uint64_t* qi = q_info;
     unsigned long long h_cnt[4] = {0, 0, 0, 0};
-    MBL_CUDA(cudaMemcpyAsync(h_cnt, counters, 8, cudaMemcpyDeviceToHost, st));
-    MBL_CUDA(cudaStreamSynchronize(st));
-    const uint64_t n_query = h_cnt[0];
+    uint64_t n_query = S;                          // exchange buffers hold no blanks
+    if (count_valid_on_device) {
+        MBL_CUDA(cudaMemcpyAsync(h_cnt, counters, 8, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        n_query = h_cnt[0];
+    }
     c->stats.n_query_kmers += n_query;
 
     // ---- K3 ------------------------------------------------------------------------------------------
@@ -365,10 +378,18 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     c->stats.merge_bytes += 2 * c->n_u16 + 4 * c->n_kmers + 16 * n_query + 24 * n_match;
     if (S) c->match_ratio = std::max(c->match_ratio, (double)reserved / (double)S);
     if (reserved >= (1ull << 32)) return fail(c, MBL_E_UNSUPPORTED, "more than 2^32 matches in one sub-batch");
+    *reserved_out = reserved; *n_match_out = n_match;
+    return MBL_OK;
+}
 
-    // ---- K4 ------------------------------------------------------------------------------------------
+// K4 + K5: order the M rows in m_raw (blank rows allowed) and score the sub-batch's reads
+int stage_sort_score(mbl_ctx* c, const SubBatch& sb, uint64_t M) {
+    cudaStream_t st = c->st;
+    const uint32_t n = sb.r1 - sb.r0;
+    const size_t scan_bytes = std::max(scan_temp_bytes(n + 1), scan_temp_bytes(c->dir.n_tiles + 2));
+    int32_t *cov1 = (int32_t*)c->cov1.p, *cov2 = (int32_t*)c->cov2.p;
+    uint32_t* quot_off = (uint32_t*)c->quot_off.p;
     // the k-mer buffers are dead now: phase-2 layout of the arena = sorted matches | key A | key B | idx A | idx B
-    const uint64_t M = reserved;
     const uint64_t M8 = (M + 32) & ~31ull;
     uint8_t* ar2 = c->arena.get<uint8_t>(48 * M8 + 256);
     mbl_match_rec* sorted = reinterpret_cast<mbl_match_rec*>(ar2);
@@ -380,7 +401,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     {
         StageTimer t(c, MBL_STAGE_MSORT);
         const size_t sm_bytes = sort_matches_temp_bytes(M);
-        void* tmp = c->cub_tmp.get<uint8_t>(std::max(sm_bytes, std::max(scan_bytes, sortk_bytes)));
+        void* tmp = c->cub_tmp.get<uint8_t>(std::max(sm_bytes, scan_bytes));
         sort_matches(tmp, c->cub_tmp.cap, (const mbl_match_rec*)c->m_raw.p, sorted, M, n, c->tax.max_taxid, sb.max_pos, true, key_a, key_b,
                      idx_a, idx_b, st);
         launch_segments(sorted, M, n, seg_b, seg_e, st);
@@ -471,6 +492,15 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     }
     MBL_CUDA(cudaGetLastError());
     return MBL_OK;
+}
+
+int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
+    stage_extract(c, sb);
+    const uint64_t S8 = (sb.slots + 31) & ~31ull;
+    uint64_t reserved = 0, n_match = 0;
+    int rc = stage_sort_merge(c, sb.slots, (const uint64_t*)c->arena.p + 2 * S8, true, &reserved, &n_match);
+    if (rc != MBL_OK) return rc;
+    return stage_sort_score(c, sb, reserved);
 }
 
 }  // namespace
