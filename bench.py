@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--db-gib", type=float, default=8.0, help="target size of diffIdx+info")
     ap.add_argument("--ref-reads", type=int, default=1_000_000, help="reads per step of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="replica", choices=["replica", "sharded"],
+                    help="N>1: replica = index replicated, reads sharded, no collective (default; the 8 GiB index fits one GPU); "
+                         "sharded = index range-partitioned over the GPUs, metamers / matches exchanged with two NCCL all-to-alls")
+    ap.add_argument("--sharded-reads", type=int, default=4_000_000, help="reads per step and GPU in --mode sharded (HBM budget)")
     return ap.parse_args()
 
 
@@ -154,6 +158,92 @@ def cpu_arm(sdb, reads, n_sample, threads, steps, warmup):
     return n, secs
 
 
+def sharded_arm(args, rank, local_rank, world, dist):
+    """--mode sharded: the index is range-partitioned over the ranks (mbl_plan_shards), every step moves the metamers to the
+    owning shard and the matches back with two NCCL all-to-alls (metabuli_b200/sharded.py).  Every step starts from host
+    buffers and ends with the per-read results on the host, so value and e2e are the same measurement here."""
+    import torch
+    from metabuli_b200 import ClassifyOptions, sharded
+    args.reads = args.sharded_reads
+    device = f"cuda:{local_rank}"
+    sdb, reads, winfo = build_workload(args, device, seed_reads=4 + rank)
+    bases, offs = np.ascontiguousarray(reads[0]), np.ascontiguousarray(reads[1])
+    n_reads = offs.size - 1
+    shards = sharded.plan_shards(sdb.database, world)
+    t0 = time.time()
+    sc = sharded.ShardedClassifier(sdb.database, ClassifyOptions(seq_mode=1, device=local_rank), shards, rank)
+    winfo["db_load_s"] = round(time.time() - t0, 1)
+    lib = sc.lib
+    lib.mbl_host_register(bases.ctypes.data_as(C.c_void_p), bases.nbytes)
+    lib.mbl_host_register(offs.ctypes.data_as(C.c_void_p), offs.nbytes)
+    ex = sharded.DistExchange(dist, device) if world > 1 else sharded.SelfExchange()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res, pairs = sharded.classify_index_sharded(sc, ex, bases, offs)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    tm, stage_ms = {}, {}
+    merge_ms = merge_bytes = launches = merge_launches = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res, pairs = sharded.classify_index_sharded(sc, ex, bases, offs, timings=tm)
+        st = sc.clf.stats()
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+        merge_ms += st["ms_merge_kernel"]; merge_bytes += st["merge_bytes"]; launches += st["kernel_launches"]
+        merge_launches += st["merge_launches"]
+    barrier()
+    t_step = time.perf_counter() - t0
+    clocks = sampler.stop()
+    last = sc.clf.stats()
+    if dist is not None:
+        t = torch.tensor([t_step], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_step = float(t[0])
+    total_reads = n_reads * world * args.steps
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = (merge_bytes / 1e9) / (merge_ms / 1e3) if merge_ms > 0 else 0.0
+        sh = shards[rank]
+        line = {
+            "metric": METRIC, "value": total_reads / t_step, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * t_step / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": f"{n_reads} synthetic {args.read_len} bp SE reads per GPU per step vs {winfo['index_gib']} GiB synthetic index "
+                                   f"range-partitioned over {world} GPU(s) (BASELINE configs[1] index, configs[2] exchange pattern)",
+                       "l2": "inputs_exceed_l2",
+                       "parallelism": f"index-sharded x{world}: all-to-all #1 metamers (16 B) to the owning shard, all-to-all #2 matches (24 B) to the read owner",
+                       **winfo, "shard0_gib": round((2 * (sh.diff_end - sh.diff_begin) + 4 * (sh.info_end - sh.info_begin)) / (1 << 30), 3),
+                       "rank0_received_kmers_per_step": last["n_query_kmers"], "rank0_matches_per_step": last["n_matches"],
+                       "classified_rank0": int(res["is_classified"].sum()),
+                       "rank0_a2a_kmer_gb_per_step": tm.get("a2a_kmer_bytes", 0) / args.steps / 1e9,
+                       "rank0_a2a_match_gb_per_step": tm.get("a2a_match_bytes", 0) / args.steps / 1e9},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "kernel": "merge_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": merge_bytes / max(1, merge_launches), "ms_per_launch": merge_ms / max(1, merge_launches)},
+            "cpu_baseline": None,
+            "e2e": {"value": total_reads / t_step, "unit": "reads/s", "h2d_bytes_per_step": int(bases.nbytes + offs.nbytes),
+                    "d2h_bytes_per_step": int(res.nbytes + pairs.nbytes), "ms_per_step": 1000 * t_step / args.steps},
+            "gpu_launches": launches, "clocks": clocks,
+            "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+            "phases_ms_per_step_rank0": {k: 1000 * v / args.steps for k, v in tm.items() if k.startswith("s_")},
+        }
+        print(json.dumps(line))
+    for a in (bases, offs):
+        lib.mbl_host_unregister(a.ctypes.data_as(C.c_void_p))
+    sc.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -196,6 +286,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     from metabuli_b200 import Classifier, ClassifyOptions, _ffi
+
+    if args.mode == "sharded":
+        return sharded_arm(args, rank, local_rank, world, dist)
 
     sdb, reads, winfo = build_workload(args, f"cuda:{local_rank}", seed_reads=4 + rank)
     bases, offs = np.ascontiguousarray(reads[0]), np.ascontiguousarray(reads[1])

@@ -142,6 +142,42 @@ int  mbl_score(mbl_ctx* ctx, const mbl_match_rec* sorted, size_t n_match, uint32
                const int32_t* cov_len1, const int32_t* cov_len2, mbl_read_result* out,
                int32_t* taxcnt_pairs, size_t taxcnt_cap_pairs, size_t* taxcnt_used_pairs);
 
+/* ---- index-sharded mode ------------------------------------------------------------ */
+/* The reference's OpenMP threads all walk one diffIdx (KmerMatcher.cpp:156-217, one DiffIdxSplit checkpoint per thread,
+ * Kmer.h:111-119).  Across GPUs the same checkpoints cut the index into contiguous value ranges, one per GPU/context; query
+ * metamers travel to the shard that owns their amino-acid part, matches travel back to the rank that owns the read.  The three
+ * phases below are what one rank runs around the two exchanges (all-to-all #1: value + qinfo, #2: 24-byte match rows); the
+ * exchange itself is the caller's (NCCL through torch.distributed in metabuli_b200/sharded.py).  Device pointers returned by a
+ * phase stay valid until the context's next call. */
+typedef struct {
+    uint64_t first_value;      /* amino-acid-group-aligned lower bound of the shard's value range (0 for shard 0,
+                                  UINT64_MAX for an empty trailing shard)                                         */
+    uint64_t base_value;       /* value the shard's first delta is relative to (DiffIdxSplit::ADkmer of the
+                                  preceding k-mer; 0 at the file start)                                           */
+    uint64_t diff_begin, diff_end;   /* u16 range of <db>/diffIdx                                                 */
+    uint64_t info_begin, info_end;   /* k-mer range of <db>/info                                                  */
+    int32_t  holds_db_tail;    /* the shard ends with the numerically last k-mer of the DB (Q1 applies here only) */
+    int32_t  pad;
+} mbl_shard;
+#define MBL_MAX_SHARDS 64
+/* Host only (no device needed): cut the index into n_shards value ranges of near-equal diffIdx+info bytes at amino-acid-group
+ * starts, from the `split` checkpoints (IndexCreator.cpp:817-872) or, when those are too few, from one scan of the stream. */
+int  mbl_plan_shards(const mbl_db* db, uint32_t n_shards, mbl_shard* out);
+/* mbl_load_db for one shard: uploads diffIdx[diff_begin, diff_end) and info[info_begin, info_end) only. */
+int  mbl_load_db_shard(mbl_ctx* ctx, const mbl_db* db, const mbl_taxonomy* tax, const mbl_shard* shard);
+/* Phase 1, read owner: upload + extract (A0-A3') and bucket the metamers by owning shard.  seq_base = index of the batch's
+ * first read among the reads of all ranks (seqIDs are global on the wire); shard_first_value[n_shards] from mbl_plan_shards.
+ * -> send_counts[n_shards] and the contiguous send buffers (bucket s starts at sum(send_counts[0..s))). */
+int  mbl_shard_extract(mbl_ctx* ctx, const mbl_batch* batch, uint64_t seq_base, uint32_t n_shards, const uint64_t* shard_first_value,
+                       uint64_t* send_counts, const uint64_t** d_send_value, const uint64_t** d_send_qinfo);
+/* Phase 2, shard owner: sort (A4) and merge (A5-A8) the received metamers (device pointers) against the resident shard, then
+ * bucket the matches by read owner: owner o holds the reads [owner_first_read[o], owner_first_read[o+1]). */
+int  mbl_shard_match(mbl_ctx* ctx, const uint64_t* d_value, const uint64_t* d_qinfo, uint64_t n, uint32_t n_owners,
+                     const uint64_t* owner_first_read, uint64_t* send_counts, const mbl_match_rec** d_send_match);
+/* Phase 3, read owner: sort (A9) and score (A10-A12) the received matches (device pointer) of the batch given to phase 1;
+ * fetch with mbl_download_results. */
+int  mbl_shard_score(mbl_ctx* ctx, const mbl_match_rec* d_match, uint64_t n_match);
+
 /* Pin / unpin a caller buffer (cudaHostRegister) so the copies inside mbl_classify_batch run at PCIe
  * speed; purely an optimisation, pageable buffers work too. */
 int  mbl_host_register(void* ptr, size_t bytes);
@@ -166,6 +202,8 @@ typedef struct {
     uint32_t kernel_launches;         /* launches of this library's own kernels in the last call        */
     uint32_t overflow_retries;
     uint32_t sub_batches;
+    float    ms_bucket_kmers;         /* sharded mode: bucketing + packing of the metamers / of the matches    */
+    float    ms_bucket_matches;
 } mbl_stats;
 int  mbl_get_stats(const mbl_ctx* ctx, mbl_stats* out);
 

@@ -61,7 +61,12 @@ class ReadResult(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms", C.c_float * 7), ("merge_kernel_ms", C.c_float), ("n_query_kmers", C.c_uint64), ("n_matches", C.c_uint64), ("merge_bytes", C.c_uint64),
                 ("merge_launches", C.c_uint32), ("kernel_launches", C.c_uint32), ("overflow_retries", C.c_uint32),
-                ("sub_batches", C.c_uint32)]
+                ("sub_batches", C.c_uint32), ("ms_bucket_kmers", C.c_float), ("ms_bucket_matches", C.c_float)]
+
+
+class Shard(C.Structure):
+    _fields_ = [("first_value", C.c_uint64), ("base_value", C.c_uint64), ("diff_begin", C.c_uint64), ("diff_end", C.c_uint64),
+                ("info_begin", C.c_uint64), ("info_end", C.c_uint64), ("holds_db_tail", C.c_int32), ("pad", C.c_int32)]
 
 
 class DbInfo(C.Structure):
@@ -81,7 +86,8 @@ assert MATCH_DTYPE.itemsize == 24
 
 EXPORTS = ["mbl_create", "mbl_destroy", "mbl_last_error", "mbl_load_db", "mbl_classify_batch", "mbl_upload_batch",
            "mbl_classify_resident", "mbl_download_results", "mbl_extract", "mbl_sort_kmers", "mbl_match", "mbl_sort_matches",
-           "mbl_score", "mbl_get_stats", "mbl_get_db_info", "mbl_host_register", "mbl_host_unregister"]
+           "mbl_score", "mbl_get_stats", "mbl_get_db_info", "mbl_host_register", "mbl_host_unregister",
+           "mbl_plan_shards", "mbl_load_db_shard", "mbl_shard_extract", "mbl_shard_match", "mbl_shard_score"]
 
 _lib = None
 
@@ -113,6 +119,11 @@ def load_library() -> C.CDLL:
     lib.mbl_score.argtypes = [vp, vp, sz, C.c_uint32, vp, vp, vp, vp, sz, C.POINTER(sz)]
     lib.mbl_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.mbl_get_db_info.argtypes = [vp, C.POINTER(DbInfo)]
+    lib.mbl_plan_shards.argtypes = [C.POINTER(Db), C.c_uint32, C.POINTER(Shard)]
+    lib.mbl_load_db_shard.argtypes = [vp, C.POINTER(Db), C.POINTER(Taxonomy), C.POINTER(Shard)]
+    lib.mbl_shard_extract.argtypes = [vp, C.POINTER(Batch), C.c_uint64, C.c_uint32, vp, vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.mbl_shard_match.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, vp, vp, C.POINTER(vp)]
+    lib.mbl_shard_score.argtypes = [vp, vp, C.c_uint64]
     lib.mbl_host_register.argtypes = [vp, sz]
     lib.mbl_host_unregister.argtypes = [vp]
     for name in EXPORTS:

@@ -39,7 +39,8 @@ def _ptr(a):
 class Classifier:
     """Classifier(par): loads the DB (loadDbParameters, loadTaxonomy, KmerMatcher::loadTaxIdList) onto the GPU."""
 
-    def __init__(self, db_dir: str | None, opt: ClassifyOptions | None = None, database: Database | None = None):
+    def __init__(self, db_dir: str | None, opt: ClassifyOptions | None = None, database: Database | None = None, shard=None):
+        """shard: an _ffi.Shard from sharded.plan_shards -> only that value range of the index is uploaded (mbl_load_db_shard)."""
         self.opt = opt or ClassifyOptions()
         self.lib = _ffi.load_library()
         self.db = database if database is not None else load_database(db_dir)
@@ -66,7 +67,10 @@ class Classifier:
         tx = _ffi.Taxonomy(t.max_nodes, t.max_taxid, t.eukaryota, _ptr(t.D), _ptr(t.E), _ptr(t.L), _ptr(t.H), _ptr(t.M), t.M_k,
                            _ptr(t.node_taxid), _ptr(t.node_parent), _ptr(t.node_prune), _ptr(t.node_rank),
                            _ptr(self.db.taxid2species))
-        self._check(self.lib.mbl_load_db(self.ctx, C.byref(dbs), C.byref(tx)))
+        if shard is None:
+            self._check(self.lib.mbl_load_db(self.ctx, C.byref(dbs), C.byref(tx)))
+        else:
+            self._check(self.lib.mbl_load_db_shard(self.ctx, C.byref(dbs), C.byref(tx), C.byref(shard)))
 
     # ---------------------------------------------------------------------------------------------
     def _check(self, rc: int):
@@ -93,6 +97,8 @@ class Classifier:
         batch = _ffi.Batch(_ptr(b1), _ptr(o1), _ptr(b2), _ptr(o2), o1.size - 1)
         return batch, (b1, o1, b2, o2)
 
+    _n_resident = 0
+
     # ---- whole path -----------------------------------------------------------------------------
     def classify_batch(self, bases1, off1, bases2=None, off2=None):
         """One QuerySplit through extract/sort/match/sort/score.  -> (results[n], taxcnt_pairs[k,2])"""
@@ -111,13 +117,29 @@ class Classifier:
             del keep
             return out, pairs[: used.value]
 
+    def download_results(self):
+        """mbl_download_results of the resident batch -> (results[n], taxcnt_pairs[k,2])"""
+        n = int(self._n_resident)
+        out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+        cap = max(16, 4 * n)
+        while True:
+            pairs = np.zeros((cap, 2), dtype=np.int32)
+            used = C.c_size_t(0)
+            rc = self.lib.mbl_download_results(self.ctx, _ptr(out), _ptr(pairs), cap, C.byref(used))
+            if rc == _ffi.MBL_E_CAPACITY:
+                cap = int(used.value) + 16
+                continue
+            self._check(rc)
+            return out, pairs[: used.value]
+
     def stats(self) -> dict:
         s = _ffi.Stats()
         self.lib.mbl_get_stats(self.ctx, C.byref(s))
         d = {f"ms_{n}": float(s.ms[i]) for i, n in enumerate(_ffi.STAGE_NAMES)}
         d.update(ms_merge_kernel=float(s.merge_kernel_ms), n_query_kmers=int(s.n_query_kmers), n_matches=int(s.n_matches), merge_bytes=int(s.merge_bytes),
                  merge_launches=int(s.merge_launches), kernel_launches=int(s.kernel_launches),
-                 overflow_retries=int(s.overflow_retries), sub_batches=int(s.sub_batches))
+                 overflow_retries=int(s.overflow_retries), sub_batches=int(s.sub_batches), ms_bucket_kmers=float(s.ms_bucket_kmers),
+                 ms_bucket_matches=float(s.ms_bucket_matches))
         return d
 
     def db_info(self) -> dict:

@@ -156,4 +156,22 @@ void launch_compact_taxcnt(const mbl_read_result* results, uint32_t n_reads, con
 void launch_shift_taxcnt(mbl_read_result* results, uint32_t n_reads, uint32_t delta, cudaStream_t st);
 void launch_taxcnt_len(const mbl_read_result* results, uint32_t n_reads, uint32_t* len, cudaStream_t st);
 
+// K6 exchange staging of the index-sharded mode (k6_shard.cu)
+constexpr uint32_t kMaxShards = 64;
+struct ShardBounds {                // ascending lower bounds of the buckets: shard first values (amino-acid part) / owners' first reads
+    uint32_t n;
+    uint64_t bound[kMaxShards];
+};
+size_t bucket_sort_temp_bytes(size_t n);
+// stable partition by bucket; return the permutation (idx_a or idx_b); d_begin[0..b.n] = bucket starts, d_begin[b.n] = elements kept
+const uint32_t* bucket_kmers(void* tmp, size_t tmp_bytes, const uint64_t* value, uint64_t n, const ShardBounds& b, uint8_t* key_a, uint8_t* key_b,
+                             uint32_t* idx_a, uint32_t* idx_b, uint64_t* d_begin, cudaStream_t st);
+const uint32_t* bucket_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* m, uint64_t n, const ShardBounds& b, uint8_t* key_a,
+                               uint8_t* key_b, uint32_t* idx_a, uint32_t* idx_b, uint64_t* d_begin, cudaStream_t st);
+void gather_kmers(const uint32_t* idx, uint64_t n_send, const uint64_t* value, const uint64_t* qinfo, uint64_t seq_add, uint64_t* out_value,
+                  uint64_t* out_qinfo, cudaStream_t st);
+void gather_matches(const uint32_t* idx, uint64_t n_send, const mbl_match_rec* in, mbl_match_rec* out, cudaStream_t st);
+void localize_matches(const mbl_match_rec* in, uint64_t n, uint64_t seq_sub, mbl_match_rec* out, cudaStream_t st);
+void launch_iota(uint32_t* idx, uint64_t n, cudaStream_t st);
+
 }  // namespace mbl

@@ -2,6 +2,7 @@
 // and the batch pipeline  K1 extract -> K2 sort -> K3 merge -> K4 match sort -> K5 score
 // (reference: Classifier::startClassify, src/commons/Classifier.cpp:44-164).
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -74,6 +75,11 @@ struct mbl_ctx {
         c_start, c_end, s_score;
     Buf q_tax, q_ham, q_has, pairs_raw;
     Buf q_lo, item_cnt, item_off, items, counters;
+    // index-sharded mode (mbl_shard_*): bucket keys / permutations, send buffers, bucket starts
+    Buf sh_key_a, sh_key_b, sh_idx_a, sh_idx_b, sh_begin, send_value, send_qinfo, send_match, sh_tmp;
+    uint64_t seq_base = 0;              // index of the resident batch's first read among all ranks' reads
+    mbl_shard shard{};                  // the value range this context holds (whole index: first_value 0)
+    bool is_shard = false;
     // results of the whole batch
     Buf results, pairs, pairs_final;
     uint64_t n_pairs = 0;               // pairs written by this lane
@@ -558,7 +564,9 @@ void release_lane(mbl_ctx* c) {
                    &c->fg_ord, &c->flat_tmp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start,
                    &c->l_ham, &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score, &c->p_ham, &c->p_depth,
                    &c->p_smatch, &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw,
-                   &c->q_lo, &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs, &c->pairs_final})
+                   &c->q_lo, &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs, &c->pairs_final,
+                   &c->sh_key_a, &c->sh_key_b, &c->sh_idx_a, &c->sh_idx_b, &c->sh_begin, &c->send_value, &c->send_qinfo, &c->send_match,
+                   &c->sh_tmp})
         b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
@@ -606,14 +614,18 @@ void mbl_destroy(mbl_ctx* c) {
 
 const char* mbl_last_error(const mbl_ctx* c) { return c ? c->err.c_str() : "no context"; }
 
-int mbl_load_db(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx) {
+namespace {
+int load_db_range(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx, const mbl_shard& sh, bool is_shard) {
     if (!c || !db || !tx || !db->diff_idx || !db->info) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (sh.diff_begin > sh.diff_end || sh.diff_end > db->n_u16 || sh.info_begin > sh.info_end || sh.info_end > db->n_kmers)
+        return fail(c, MBL_E_BAD_ARG, "shard range outside the index");
     try {
         MBL_CUDA(cudaSetDevice(c->cfg.device));
         free_db(c);
-        c->n_u16 = db->n_u16; c->n_kmers = db->n_kmers;
-        c->d_diff = upload(c, db->diff_idx, db->n_u16, 64);
-        c->d_info = upload(c, db->info, db->n_kmers, 64);
+        c->shard = sh; c->is_shard = is_shard;
+        c->n_u16 = sh.diff_end - sh.diff_begin; c->n_kmers = sh.info_end - sh.info_begin;
+        c->d_diff = upload(c, db->diff_idx + sh.diff_begin, c->n_u16, 64);
+        c->d_info = upload(c, db->info + sh.info_begin, c->n_kmers, 64);
         auto up = [&](auto* h, size_t n) { auto* d = upload(c, h, n); c->tax_allocs.push_back((void*)d); return d; };
         const size_t N = tx->max_nodes, T = (size_t)tx->max_taxid + 1;
         c->tax.D = up(tx->D, T); c->tax.E = up(tx->E, 2 * N); c->tax.L = up(tx->L, 2 * N); c->tax.H = up(tx->H, N);
@@ -623,7 +635,7 @@ int mbl_load_db(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx) {
         c->tax.taxid2species = up(tx->taxid2species, T);
         c->tax.max_taxid = tx->max_taxid; c->tax.M_k = tx->M_k; c->tax.eukaryota = tx->eukaryota; c->tax.max_nodes = (uint32_t)N;
         MBL_CUDA(cudaStreamSynchronize(c->st));
-        build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->tile_cells, c->st, c->dir);
+        build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->tile_cells, c->st, c->dir, sh.base_value, sh.holds_db_tail != 0);
         if (c->force_sort_bit) c->dir.sort_begin_bit = c->force_sort_bit;
         // the k-mer count implied by the end flags must agree with the info file
         if (c->dir.n_kmers_decoded != c->n_kmers) {
@@ -637,6 +649,113 @@ int mbl_load_db(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx) {
         c->db_loaded = true;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+// one k-mer's delta: 15 payload bits per fragment, most significant group first (KmerMatcher.h:282-297)
+inline uint64_t decode_delta(const uint16_t* d, uint64_t b, uint64_t e) {
+    uint64_t v = 0;
+    for (uint64_t i = b; i < e; ++i) v = (v << 15) | (uint64_t)(d[i] & 0x7FFFu);
+    return v;
+}
+struct ShardCut { uint64_t first_value, base_value, diff_begin, info_begin; };
+}  // namespace
+
+int mbl_load_db(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx) {
+    if (!c || !db) return fail(c, MBL_E_BAD_ARG, "null argument");
+    mbl_shard whole{};
+    whole.first_value = 0; whole.base_value = 0; whole.diff_begin = 0; whole.diff_end = db->n_u16; whole.info_begin = 0;
+    whole.info_end = db->n_kmers; whole.holds_db_tail = 1;
+    return load_db_range(c, db, tx, whole, false);
+}
+
+int mbl_load_db_shard(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx, const mbl_shard* shard) {
+    if (!c || !shard) return fail(c, MBL_E_BAD_ARG, "null argument");
+    return load_db_range(c, db, tx, *shard, true);
+}
+
+int mbl_plan_shards(const mbl_db* db, uint32_t n_shards, mbl_shard* out) {
+    if (!db || !out || n_shards < 1 || n_shards > MBL_MAX_SHARDS || (db->n_u16 && !db->diff_idx)) return MBL_E_BAD_ARG;
+    const uint16_t* d = db->diff_idx;
+    const uint64_t NU = db->n_u16, NK = db->n_kmers;
+    const long double total = 2.0L * NU + 4.0L * NK;
+    auto bytes_at = [](const ShardCut& c) { return 2.0L * c.diff_begin + 4.0L * c.info_begin; };
+    std::vector<ShardCut> cuts;                     // chosen boundaries, ascending; shard s+1 starts at cuts[s]
+    if (n_shards > 1 && NU && NK) {
+        // candidates from the split checkpoints: entry = {ADkmer = first k-mer of a new amino-acid group, u16 index just after it,
+        // its info index + 1} (IndexCreator.cpp:849-857)
+        std::vector<ShardCut> cand;
+        if (db->split) {
+            uint64_t last_info = 0;
+            for (size_t k = 1; k < db->n_split; ++k) {
+                const uint64_t ad = db->split[3 * k], doff = db->split[3 * k + 1], ioff = db->split[3 * k + 2];
+                if (ad == 0 || ad == ~0ull || doff < 1 || doff > NU || ioff < 2 || ioff > NK || ioff - 1 <= last_info) continue;
+                if (!(d[doff - 1] & 0x8000u)) continue;
+                uint64_t b = doff - 1;
+                while (b > 0 && !(d[b - 1] & 0x8000u) && doff - b < 5) --b;
+                if (b > 0 && !(d[b - 1] & 0x8000u)) continue;               // more than 5 fragments: not a k-mer boundary
+                const uint64_t delta = decode_delta(d, b, doff);
+                if (delta > ad || ((ad - delta) & kAaMask) == (ad & kAaMask)) continue;   // must start an amino-acid group
+                cand.push_back(ShardCut{ad, ad - delta, b, ioff - 1});
+                last_info = ioff - 1;
+            }
+        }
+        auto choose = [&](const std::vector<ShardCut>& cs) {
+            std::vector<ShardCut> pick;
+            size_t from = 0;
+            for (uint32_t s = 1; s < n_shards && from < cs.size(); ++s) {
+                const long double target = total * s / n_shards;
+                size_t best = from;
+                for (size_t i = from; i < cs.size(); ++i) {
+                    if (fabsl(bytes_at(cs[i]) - target) < fabsl(bytes_at(cs[best]) - target)) best = i;
+                    if (bytes_at(cs[i]) > target) break;
+                }
+                pick.push_back(cs[best]);
+                from = best + 1;
+            }
+            return pick;
+        };
+        cuts = choose(cand);
+        auto largest = [&](const std::vector<ShardCut>& cs) {
+            long double prev = 0, worst = 0;
+            for (const ShardCut& c : cs) { worst = std::max(worst, bytes_at(c) - prev); prev = bytes_at(c); }
+            return std::max(worst, total - prev);
+        };
+        if (cuts.size() + 1 < n_shards || largest(cuts) > 1.25L * total / n_shards) {
+            const std::vector<ShardCut> from_split = cuts;
+            // too few usable checkpoints (small or hand-made DBs): one sequential pass over the stream, taking the first
+            // amino-acid-group start at or after every byte target
+            cuts.clear();
+            uint64_t v = 0, k = 0, p = 0;
+            uint32_t s = 1;
+            while (p < NU && s < n_shards) {
+                uint64_t e = p;
+                while (e < NU && !(d[e] & 0x8000u)) ++e;
+                if (e >= NU) break;                                          // truncated tail: ignored, the loader reports it
+                const uint64_t nv = v + decode_delta(d, p, e + 1);
+                if (k > 0 && (nv & kAaMask) != (v & kAaMask) && 2.0L * p + 4.0L * k >= total * s / n_shards) {
+                    cuts.push_back(ShardCut{nv, v, p, k});
+                    ++s;
+                }
+                v = nv; ++k; p = e + 1;
+            }
+            if (from_split.size() + 1 == n_shards && (cuts.size() + 1 < n_shards || largest(from_split) <= largest(cuts))) cuts = from_split;
+        }
+    }
+    for (uint32_t s = 0; s < n_shards; ++s) {
+        mbl_shard& o = out[s];
+        o = mbl_shard{};
+        const bool has_begin = s == 0 || s - 1 < cuts.size();
+        const bool has_end = s < cuts.size();
+        if (!has_begin) {                       // empty trailing shard
+            o.first_value = ~0ull; o.base_value = 0; o.diff_begin = o.diff_end = NU; o.info_begin = o.info_end = NK;
+            continue;
+        }
+        if (s > 0) { const ShardCut& b = cuts[s - 1]; o.first_value = b.first_value; o.base_value = b.base_value; o.diff_begin = b.diff_begin; o.info_begin = b.info_begin; }
+        o.diff_end = has_end ? cuts[s].diff_begin : NU;
+        o.info_end = has_end ? cuts[s].info_begin : NK;
+        o.holds_db_tail = (!has_end && o.info_end > o.info_begin) ? 1 : 0;
     }
     return MBL_OK;
 }
@@ -773,6 +892,136 @@ int mbl_classify_batch(mbl_ctx* c, const mbl_batch* b, mbl_read_result* out, int
     rc = mbl_classify_resident(c);
     if (rc != MBL_OK) return rc;
     return mbl_download_results(c, out, taxcnt_pairs, cap_pairs, used_pairs);
+}
+
+// ---- index-sharded mode: the three phases one rank runs around the two exchanges (include/metabuli_b200.h) ----------------
+int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_t n_shards, const uint64_t* shard_first_value,
+                      uint64_t* send_counts, const uint64_t** d_send_value, const uint64_t** d_send_qinfo) {
+    if (!c || !b || !shard_first_value || !send_counts || !d_send_value || !d_send_qinfo) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (n_shards < 1 || n_shards > kMaxShards) return fail(c, MBL_E_BAD_ARG, "1..64 shards");
+    if (seq_base + b->n_reads >= (1ull << 29)) return fail(c, MBL_E_BAD_ARG, "global read index exceeds the 29-bit sequenceID (Kmer.h:13)");
+    c->stats.ms[MBL_STAGE_H2D] = 0;
+    const int pipeline = c->pipeline;
+    c->pipeline = 0;                                   // one sub-batch: the exchange works on whole batches
+    int rc = mbl_upload_batch(c, b);
+    c->pipeline = pipeline;
+    if (rc != MBL_OK) return rc;
+    if (c->subs.size() > 1) return fail(c, MBL_E_CAPACITY, "batch too large for one sharded pass: split it on the caller's side");
+    try {
+        cudaStream_t st = c->st;
+        float h2d = c->stats.ms[MBL_STAGE_H2D];
+        c->stats = mbl_stats{};
+        c->stats.ms[MBL_STAGE_H2D] = h2d;
+        c->stats.sub_batches = 1;
+        c->n_pairs = 0; c->n_pairs_total = 0;
+        c->seq_base = seq_base;
+        c->results.get<mbl_read_result>(c->n_reads + 1);
+        for (uint32_t s = 0; s < n_shards; ++s) send_counts[s] = 0;
+        *d_send_value = nullptr; *d_send_qinfo = nullptr;
+        if (c->subs.empty()) return MBL_OK;
+        const SubBatch sb = c->subs[0];
+        stage_extract(c, sb);
+        const uint64_t S = sb.slots, S8 = (S + 31) & ~31ull;
+        const uint64_t* va = (const uint64_t*)c->arena.p;
+        const uint64_t* qa = va + 2 * S8;
+        const float ms_k1 = c->stats.ms[MBL_STAGE_EXTRACT];
+        StageTimer t(c, MBL_STAGE_EXTRACT);
+        ShardBounds sbnd{};
+        sbnd.n = n_shards;
+        for (uint32_t s = 0; s < n_shards; ++s) sbnd.bound[s] = shard_first_value[s];
+        uint8_t *ka = c->sh_key_a.get<uint8_t>(S + 16), *kb = c->sh_key_b.get<uint8_t>(S + 16);
+        uint32_t *ia = c->sh_idx_a.get<uint32_t>(S + 16), *ib = c->sh_idx_b.get<uint32_t>(S + 16);
+        uint64_t* d_begin = c->sh_begin.get<uint64_t>(kMaxShards + 2);
+        void* tmp = c->sh_tmp.get<uint8_t>(bucket_sort_temp_bytes(S));
+        const uint32_t* perm = bucket_kmers(tmp, c->sh_tmp.cap, va, S, sbnd, ka, kb, ia, ib, d_begin, st);
+        uint64_t h_begin[kMaxShards + 2];
+        MBL_CUDA(cudaMemcpyAsync(h_begin, d_begin, 8 * (size_t)(n_shards + 1), cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        const uint64_t n_send = h_begin[n_shards];
+        for (uint32_t s = 0; s < n_shards; ++s) send_counts[s] = h_begin[s + 1] - h_begin[s];
+        uint64_t *sv = c->send_value.get<uint64_t>(n_send + 16), *sq = c->send_qinfo.get<uint64_t>(n_send + 16);
+        gather_kmers(perm, n_send, va, qa, seq_base, sv, sq, st);
+        c->stats.kernel_launches += 4;
+        t.stop();
+        c->stats.ms_bucket_kmers = c->stats.ms[MBL_STAGE_EXTRACT] - ms_k1;
+        MBL_CUDA(cudaGetLastError());
+        *d_send_value = sv; *d_send_qinfo = sq;
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_shard_match(mbl_ctx* c, const uint64_t* d_value, const uint64_t* d_qinfo, uint64_t n, uint32_t n_owners,
+                    const uint64_t* owner_first_read, uint64_t* send_counts, const mbl_match_rec** d_send_match) {
+    if (!c || !owner_first_read || !send_counts || !d_send_match || (n && (!d_value || !d_qinfo))) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (!c->db_loaded) return fail(c, MBL_E_BAD_ARG, "mbl_load_db[_shard] has not been called");
+    if (n_owners < 1 || n_owners > kMaxShards) return fail(c, MBL_E_BAD_ARG, "1..64 owners");
+    if (n >= 4000000000ull) return fail(c, MBL_E_CAPACITY, "more than 4e9 received metamers in one pass");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        cudaStream_t st = c->st;
+        for (uint32_t o = 0; o < n_owners; ++o) send_counts[o] = 0;
+        *d_send_match = nullptr;
+        // the received metamers become the phase-1 arena of this context: keys in `value A`, their positions in `slot idx A`
+        const uint64_t S8 = (n + 31) & ~31ull;
+        uint64_t* ar = c->arena.get<uint64_t>(4 * S8 + 64);
+        uint32_t* ia = reinterpret_cast<uint32_t*>(ar + 3 * S8);
+        if (n) MBL_CUDA(cudaMemcpyAsync(ar, d_value, 8 * n, cudaMemcpyDeviceToDevice, st));
+        launch_iota(ia, n, st);
+        uint64_t reserved = 0, n_match = 0;
+        int rc = stage_sort_merge(c, n, d_qinfo, false, &reserved, &n_match);
+        if (rc != MBL_OK) return rc;
+        const float ms_before = c->stats.ms[MBL_STAGE_MSORT];
+        StageTimer t(c, MBL_STAGE_MSORT);
+        ShardBounds ob{};
+        ob.n = n_owners;
+        for (uint32_t o = 0; o < n_owners; ++o) ob.bound[o] = owner_first_read[o];
+        const uint64_t R = reserved;
+        uint8_t *ka = c->sh_key_a.get<uint8_t>(R + 16), *kb = c->sh_key_b.get<uint8_t>(R + 16);
+        uint32_t *xa = c->sh_idx_a.get<uint32_t>(R + 16), *xb = c->sh_idx_b.get<uint32_t>(R + 16);
+        uint64_t* d_begin = c->sh_begin.get<uint64_t>(kMaxShards + 2);
+        void* tmp = c->sh_tmp.get<uint8_t>(bucket_sort_temp_bytes(R));
+        const uint32_t* perm = bucket_matches(tmp, c->sh_tmp.cap, (const mbl_match_rec*)c->m_raw.p, R, ob, ka, kb, xa, xb, d_begin, st);
+        uint64_t h_begin[kMaxShards + 2];
+        MBL_CUDA(cudaMemcpyAsync(h_begin, d_begin, 8 * (size_t)(n_owners + 1), cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        const uint64_t n_send = h_begin[n_owners];
+        if (n_send != n_match) return fail(c, MBL_E_CUDA, "internal: bucketed match count differs from the merge count");
+        for (uint32_t o = 0; o < n_owners; ++o) send_counts[o] = h_begin[o + 1] - h_begin[o];
+        mbl_match_rec* sm = c->send_match.get<mbl_match_rec>(n_send + 16);
+        gather_matches(perm, n_send, (const mbl_match_rec*)c->m_raw.p, sm, st);
+        c->stats.kernel_launches += 5;
+        t.stop();
+        c->stats.ms_bucket_matches += c->stats.ms[MBL_STAGE_MSORT] - ms_before;
+        MBL_CUDA(cudaGetLastError());
+        *d_send_match = sm;
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_shard_score(mbl_ctx* c, const mbl_match_rec* d_match, uint64_t n_match) {
+    if (!c || (n_match && !d_match)) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (!c->db_loaded) return fail(c, MBL_E_BAD_ARG, "mbl_load_db[_shard] has not been called");
+    if (n_match >= (1ull << 32)) return fail(c, MBL_E_UNSUPPORTED, "more than 2^32 matches in one pass");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        c->pairs_out = c->pairs.p; c->n_pairs_total = 0;
+        if (c->subs.empty()) return MBL_OK;
+        mbl_match_rec* raw = c->m_raw.get<mbl_match_rec>(n_match + 64);
+        localize_matches(d_match, n_match, c->seq_base, raw, c->st);
+        c->stats.kernel_launches += 1;
+        int rc = stage_sort_score(c, c->subs[0], n_match);
+        if (rc != MBL_OK) return rc;
+        c->pairs_out = c->pairs.p;
+        c->n_pairs_total = c->n_pairs;
+        MBL_CUDA(cudaStreamSynchronize(c->st));
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
 }
 
 int mbl_host_register(void* ptr, size_t bytes) {

@@ -1,0 +1,44 @@
+"""TEST INFRASTRUCTURE: an in-process all-to-all between threads, so several ranks of the index-sharded mode can run on ONE
+GPU (each rank = a thread with its own mbl context holding one shard).  Same interface as sharded.DistExchange."""
+import threading
+
+import torch
+
+
+class LocalWorld:
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.box = [[None] * world for _ in range(world)]      # box[src][dst]
+
+    def exchange(self, rank):
+        return LocalExchange(self, rank)
+
+
+class LocalExchange:
+    def __init__(self, w, rank):
+        self.w, self.rank, self.world = w, rank, w.world
+
+    def _a2a(self, parts):
+        w = self.w
+        for dst in range(self.world):
+            w.box[self.rank][dst] = parts[dst]
+        w.barrier.wait()
+        got = [w.box[src][self.rank] for src in range(self.world)]
+        w.barrier.wait()
+        return got
+
+    def counts(self, send_counts):
+        return [int(x) for x in self._a2a([int(x) for x in send_counts])]
+
+    def all_gather_int(self, v):
+        return self.counts([int(v)] * self.world)
+
+    def rows(self, send, send_counts, recv_counts):
+        parts = list(torch.split(send, [int(x) for x in send_counts], dim=0))
+        got = self._a2a([p.clone() for p in parts])
+        assert [int(g.shape[0]) for g in got] == [int(x) for x in recv_counts]
+        out = torch.cat(got, dim=0) if got else send[:0]
+        if out.is_cuda:
+            torch.cuda.synchronize(out.device)
+        return out

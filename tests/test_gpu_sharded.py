@@ -1,0 +1,66 @@
+"""GPU parity of the index-sharded mode: several ranks on ONE GPU (a thread and an mbl context per rank, each holding one
+shard of the index; tests/local_exchange.py stands in for NCCL), every compute phase through the C-ABI.  The per-read
+results must equal the oracle's on the whole index, bit for bit, for every rank's reads."""
+import threading
+
+import numpy as np
+import pytest
+
+import synth_cases
+from test_sharded_gloo import _expected, _same
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,world", [("multi_se", 2), ("multi_se", 3), ("multi_pe", 2), ("ragged_se", 4), ("format1_pe", 2), ("long", 2)])
+def test_sharded_equals_whole_index(name, world):
+    from local_exchange import LocalWorld
+    from metabuli_b200 import ClassifyOptions, multigpu, sharded
+    sdb, reads, seq_mode = synth_cases.build(name)
+    shards = sharded.plan_shards(sdb.database, world)
+    want_res, want_pairs = _expected(sdb, reads, seq_mode)
+    lw = LocalWorld(world)
+    n = reads[1].size - 1
+    ok = [None] * world
+    stats = [None] * world
+    errors = []
+
+    def run(rank):
+        try:
+            sc = sharded.ShardedClassifier(sdb.database, ClassifyOptions(seq_mode=seq_mode), shards, rank)
+            lo, hi = multigpu.shard_range(n, rank, world)
+            b1, o1 = multigpu.slice_batch(reads[0], reads[1], lo, hi)
+            b2, o2 = multigpu.slice_batch(reads[2], reads[3], lo, hi) if len(reads) > 2 and reads[2] is not None else (None, None)
+            for _ in range(2):                      # twice: workspace reuse across batches
+                res, pairs = sharded.classify_index_sharded(sc, lw.exchange(rank), b1, o1, b2, o2)
+            ok[rank] = _same(res, pairs, want_res, want_pairs, lo, hi)
+            stats[rank] = sc.clf.stats()
+            sc.close()
+        except Exception as e:  # a dead rank must not leave the others waiting at the barrier
+            errors.append(e)
+            lw.barrier.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    assert not errors, errors
+    assert ok == [True] * world
+    assert all(s["kernel_launches"] > 0 for s in stats)
+    assert sum(s["n_matches"] for s in stats) > 0
+
+
+def test_shard_of_one_is_the_whole_index():
+    """world = 1 through the sharded entry points == mbl_classify_batch."""
+    from local_exchange import LocalWorld
+    from metabuli_b200 import Classifier, ClassifyOptions, sharded
+    sdb, reads, seq_mode = synth_cases.build("multi_se")
+    shards = sharded.plan_shards(sdb.database, 1)
+    sc = sharded.ShardedClassifier(sdb.database, ClassifyOptions(seq_mode=seq_mode), shards, 0)
+    res, pairs = sharded.classify_index_sharded(sc, LocalWorld(1).exchange(0), reads[0], reads[1])
+    sc.close()
+    clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
+    r2, p2 = clf.classify_batch(reads[0], reads[1])
+    clf.close()
+    assert np.array_equal(res, r2) and np.array_equal(pairs, p2)

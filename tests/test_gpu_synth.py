@@ -104,6 +104,7 @@ def test_two_lane_pipeline(name, golden_dir, monkeypatch):
     """Large batches are cut in two and run on two pipeline lanes (two host threads, two streams, shared index); forcing
     that path on a small batch must still give the reference's TSV, including the per-read (taxid, count) lists."""
     from metabuli_b200 import Classifier, ClassifyOptions
+    monkeypatch.setenv("MBL_PIPELINE", "1")            # off by default (profiles/r01_v10_config_sweep.md)
     monkeypatch.setenv("MBL_PIPELINE_MIN_READS", "64")
     sdb, reads, seq_mode = synth_cases.build(name)
     clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
