@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--mode", default="replica", choices=["replica", "sharded"],
                     help="N>1: replica = index replicated, reads sharded, no collective (default; the 8 GiB index fits one GPU); "
                          "sharded = index range-partitioned over the GPUs, metamers / matches exchanged with two NCCL all-to-alls")
+    ap.add_argument("--transport", default="peer", choices=["peer", "collective"],
+                    help="--mode sharded: peer = gather kernels store into the receivers' buffers over NVLink; collective = NCCL all_to_all")
     ap.add_argument("--sharded-reads", type=int, default=4_000_000, help="reads per step and GPU in --mode sharded (HBM budget)")
     return ap.parse_args()
 
@@ -185,14 +187,14 @@ def sharded_arm(args, rank, local_rank, world, dist):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        res, pairs = sharded.classify_index_sharded(sc, ex, bases, offs)
+        res, pairs = sharded.classify_index_sharded(sc, ex, bases, offs, transport=args.transport)
     barrier()
     sampler = ClockSampler(local_rank)
     tm, stage_ms = {}, {}
     merge_ms = merge_bytes = launches = merge_launches = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res, pairs = sharded.classify_index_sharded(sc, ex, bases, offs, timings=tm)
+        res, pairs = sharded.classify_index_sharded(sc, ex, bases, offs, timings=tm, transport=args.transport)
         st = sc.clf.stats()
         for k, v in st.items():
             if k.startswith("ms_"):
@@ -219,7 +221,8 @@ def sharded_arm(args, rank, local_rank, world, dist):
             "config": {"workload": f"{n_reads} synthetic {args.read_len} bp SE reads per GPU per step vs {winfo['index_gib']} GiB synthetic index "
                                    f"range-partitioned over {world} GPU(s) (BASELINE configs[1] index, configs[2] exchange pattern)",
                        "l2": "inputs_exceed_l2",
-                       "parallelism": f"index-sharded x{world}: all-to-all #1 metamers (16 B) to the owning shard, all-to-all #2 matches (24 B) to the read owner",
+                       "parallelism": f"index-sharded x{world}: all-to-all #1 metamers (16 B) to the owning shard, all-to-all #2 matches (24 B) to the read owner; "
+                                      + ("transport = peer-memory stores from the gather kernels over NVLink" if args.transport == "peer" else "transport = NCCL all_to_all_single"),
                        **winfo, "shard0_gib": round((2 * (sh.diff_end - sh.diff_begin) + 4 * (sh.info_end - sh.info_begin)) / (1 << 30), 3),
                        "rank0_received_kmers_per_step": last["n_query_kmers"], "rank0_matches_per_step": last["n_matches"],
                        "classified_rank0": int(res["is_classified"].sum()),

@@ -146,9 +146,10 @@ int  mbl_score(mbl_ctx* ctx, const mbl_match_rec* sorted, size_t n_match, uint32
 /* The reference's OpenMP threads all walk one diffIdx (KmerMatcher.cpp:156-217, one DiffIdxSplit checkpoint per thread,
  * Kmer.h:111-119).  Across GPUs the same checkpoints cut the index into contiguous value ranges, one per GPU/context; query
  * metamers travel to the shard that owns their amino-acid part, matches travel back to the rank that owns the read.  The three
- * phases below are what one rank runs around the two exchanges (all-to-all #1: value + qinfo, #2: 24-byte match rows); the
- * exchange itself is the caller's (NCCL through torch.distributed in metabuli_b200/sharded.py).  Device pointers returned by a
- * phase stay valid until the context's next call. */
+ * phases below are what one rank runs around the two exchanges (all-to-all #1: value + qinfo, #2: 24-byte match rows).  The
+ * exchange is either the caller's collective (NCCL through torch.distributed, metabuli_b200/sharded.py) fed by mbl_shard_pack_*,
+ * or the library's own peer-memory stores (mbl_shard_push_*).  Device pointers returned by a call stay valid until the
+ * context's next phase. */
 typedef struct {
     uint64_t first_value;      /* amino-acid-group-aligned lower bound of the shard's value range (0 for shard 0,
                                   UINT64_MAX for an empty trailing shard)                                         */
@@ -167,16 +168,37 @@ int  mbl_plan_shards(const mbl_db* db, uint32_t n_shards, mbl_shard* out);
 int  mbl_load_db_shard(mbl_ctx* ctx, const mbl_db* db, const mbl_taxonomy* tax, const mbl_shard* shard);
 /* Phase 1, read owner: upload + extract (A0-A3') and bucket the metamers by owning shard.  seq_base = index of the batch's
  * first read among the reads of all ranks (seqIDs are global on the wire); shard_first_value[n_shards] from mbl_plan_shards.
- * -> send_counts[n_shards] and the contiguous send buffers (bucket s starts at sum(send_counts[0..s))). */
+ * -> send_counts[n_shards]: metamers bound for every shard. */
 int  mbl_shard_extract(mbl_ctx* ctx, const mbl_batch* batch, uint64_t seq_base, uint32_t n_shards, const uint64_t* shard_first_value,
-                       uint64_t* send_counts, const uint64_t** d_send_value, const uint64_t** d_send_qinfo);
+                       uint64_t* send_counts);
 /* Phase 2, shard owner: sort (A4) and merge (A5-A8) the received metamers (device pointers) against the resident shard, then
- * bucket the matches by read owner: owner o holds the reads [owner_first_read[o], owner_first_read[o+1]). */
+ * bucket the matches by read owner: owner o holds the reads [owner_first_read[o], owner_first_read[o+1]).
+ * -> send_counts[n_owners]: matches bound for every owner. */
 int  mbl_shard_match(mbl_ctx* ctx, const uint64_t* d_value, const uint64_t* d_qinfo, uint64_t n, uint32_t n_owners,
-                     const uint64_t* owner_first_read, uint64_t* send_counts, const mbl_match_rec** d_send_match);
+                     const uint64_t* owner_first_read, uint64_t* send_counts);
 /* Phase 3, read owner: sort (A9) and score (A10-A12) the received matches (device pointer) of the batch given to phase 1;
  * fetch with mbl_download_results. */
 int  mbl_shard_score(mbl_ctx* ctx, const mbl_match_rec* d_match, uint64_t n_match);
+
+/* Transport A (collective library): pack the buckets of the last phase 1 / phase 2 into contiguous send buffers (bucket b
+ * starts at sum(send_counts[0..b))) for a variable-count all-to-all (NCCL). */
+int  mbl_shard_pack_kmers(mbl_ctx* ctx, const uint64_t** d_send_value, const uint64_t** d_send_qinfo);
+int  mbl_shard_pack_matches(mbl_ctx* ctx, const mbl_match_rec** d_send_match);
+
+/* Transport B (peer memory, fused gather + all-to-all): every rank owns two receive buffers that its peers' gather kernels
+ * store into directly over NVLink.  mbl_shard_recv_buffers allocates them (kmer_rows x 16 B laid out as values | qinfo,
+ * match_rows x 24 B) and returns CUDA IPC handles; mbl_shard_attach_peer maps a peer's buffers from its handles (other
+ * process) or takes raw device pointers (same process, or the rank itself).  mbl_shard_push_* then replace pack + all-to-all:
+ * bucket b's rows land at row dst_row_offset[b] of peer b's buffer; dst_total_rows[b] = rows peer b receives from all ranks
+ * (start of its qinfo half).  The caller orders a push before the receiver's next phase with a barrier. */
+#define MBL_IPC_HANDLE_BYTES 64
+int  mbl_shard_recv_buffers(mbl_ctx* ctx, uint64_t kmer_rows, uint64_t match_rows, void** d_kmers, void** d_matches,
+                            uint8_t* handle_kmers, uint8_t* handle_matches);
+int  mbl_shard_attach_peer(mbl_ctx* ctx, uint32_t peer, const uint8_t* handle_kmers, const uint8_t* handle_matches,
+                           void* raw_kmers, void* raw_matches);
+int  mbl_shard_detach_peers(mbl_ctx* ctx);      /* unmap every peer buffer (before the owners re-allocate theirs) */
+int  mbl_shard_push_kmers(mbl_ctx* ctx, const uint64_t* dst_row_offset, const uint64_t* dst_total_rows);
+int  mbl_shard_push_matches(mbl_ctx* ctx, const uint64_t* dst_row_offset);
 
 /* Pin / unpin a caller buffer (cudaHostRegister) so the copies inside mbl_classify_batch run at PCIe
  * speed; purely an optimisation, pageable buffers work too. */

@@ -20,6 +20,7 @@ MBL_E_BAD_ARG = -3
 MBL_E_BAD_DB = -4
 MBL_E_UNSUPPORTED = -5
 
+IPC_HANDLE_BYTES = 64
 STAGE_NAMES = ["h2d", "extract", "sort", "merge", "match_sort", "score", "d2h"]
 
 
@@ -87,7 +88,9 @@ assert MATCH_DTYPE.itemsize == 24
 EXPORTS = ["mbl_create", "mbl_destroy", "mbl_last_error", "mbl_load_db", "mbl_classify_batch", "mbl_upload_batch",
            "mbl_classify_resident", "mbl_download_results", "mbl_extract", "mbl_sort_kmers", "mbl_match", "mbl_sort_matches",
            "mbl_score", "mbl_get_stats", "mbl_get_db_info", "mbl_host_register", "mbl_host_unregister",
-           "mbl_plan_shards", "mbl_load_db_shard", "mbl_shard_extract", "mbl_shard_match", "mbl_shard_score"]
+           "mbl_plan_shards", "mbl_load_db_shard", "mbl_shard_extract", "mbl_shard_match", "mbl_shard_score",
+           "mbl_shard_pack_kmers", "mbl_shard_pack_matches", "mbl_shard_recv_buffers", "mbl_shard_attach_peer", "mbl_shard_detach_peers", "mbl_shard_push_kmers",
+           "mbl_shard_push_matches"]
 
 _lib = None
 
@@ -121,9 +124,16 @@ def load_library() -> C.CDLL:
     lib.mbl_get_db_info.argtypes = [vp, C.POINTER(DbInfo)]
     lib.mbl_plan_shards.argtypes = [C.POINTER(Db), C.c_uint32, C.POINTER(Shard)]
     lib.mbl_load_db_shard.argtypes = [vp, C.POINTER(Db), C.POINTER(Taxonomy), C.POINTER(Shard)]
-    lib.mbl_shard_extract.argtypes = [vp, C.POINTER(Batch), C.c_uint64, C.c_uint32, vp, vp, C.POINTER(vp), C.POINTER(vp)]
-    lib.mbl_shard_match.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, vp, vp, C.POINTER(vp)]
+    lib.mbl_shard_extract.argtypes = [vp, C.POINTER(Batch), C.c_uint64, C.c_uint32, vp, vp]
+    lib.mbl_shard_match.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint32, vp, vp]
     lib.mbl_shard_score.argtypes = [vp, vp, C.c_uint64]
+    lib.mbl_shard_pack_kmers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    lib.mbl_shard_pack_matches.argtypes = [vp, C.POINTER(vp)]
+    lib.mbl_shard_recv_buffers.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(vp), C.POINTER(vp), vp, vp]
+    lib.mbl_shard_attach_peer.argtypes = [vp, C.c_uint32, vp, vp, vp, vp]
+    lib.mbl_shard_detach_peers.argtypes = [vp]
+    lib.mbl_shard_push_kmers.argtypes = [vp, vp, vp]
+    lib.mbl_shard_push_matches.argtypes = [vp, vp]
     lib.mbl_host_register.argtypes = [vp, sz]
     lib.mbl_host_unregister.argtypes = [vp]
     for name in EXPORTS:

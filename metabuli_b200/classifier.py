@@ -79,6 +79,7 @@ class Classifier:
 
     def close(self):
         if getattr(self, "ctx", None) and self.ctx.value:
+            self._dl_free()
             self.lib.mbl_destroy(self.ctx)
             self.ctx = C.c_void_p()
 
@@ -118,19 +119,34 @@ class Classifier:
             return out, pairs[: used.value]
 
     def download_results(self):
-        """mbl_download_results of the resident batch -> (results[n], taxcnt_pairs[k,2])"""
+        """mbl_download_results of the resident batch -> (results[n], taxcnt_pairs[k,2]).  The arrays are views of two pinned
+        buffers owned by this object and are overwritten by the next call."""
         n = int(self._n_resident)
-        out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
-        cap = max(16, 4 * n)
+        if self._dl_out is None or self._dl_out.size < n:
+            self._dl_free()
+            self._dl_out = np.zeros(max(16, n + n // 8), dtype=_ffi.RESULT_DTYPE)
+            self._dl_pairs = np.zeros((max(16, 5 * n), 2), dtype=np.int32)
+            for a in (self._dl_out, self._dl_pairs):
+                self.lib.mbl_host_register(_ptr(a), a.nbytes)
         while True:
-            pairs = np.zeros((cap, 2), dtype=np.int32)
             used = C.c_size_t(0)
-            rc = self.lib.mbl_download_results(self.ctx, _ptr(out), _ptr(pairs), cap, C.byref(used))
+            rc = self.lib.mbl_download_results(self.ctx, _ptr(self._dl_out), _ptr(self._dl_pairs), self._dl_pairs.shape[0], C.byref(used))
             if rc == _ffi.MBL_E_CAPACITY:
-                cap = int(used.value) + 16
+                self.lib.mbl_host_unregister(_ptr(self._dl_pairs))
+                self._dl_pairs = np.zeros((int(used.value) + int(used.value) // 8 + 16, 2), dtype=np.int32)
+                self.lib.mbl_host_register(_ptr(self._dl_pairs), self._dl_pairs.nbytes)
                 continue
             self._check(rc)
-            return out, pairs[: used.value]
+            return self._dl_out[:n], self._dl_pairs[: used.value]
+
+    _dl_out = None
+    _dl_pairs = None
+
+    def _dl_free(self):
+        for a in (self._dl_out, self._dl_pairs):
+            if a is not None:
+                self.lib.mbl_host_unregister(_ptr(a))
+        self._dl_out = self._dl_pairs = None
 
     def stats(self) -> dict:
         s = _ffi.Stats()

@@ -86,6 +86,35 @@ __global__ void match_localize_kernel(const uint64_t* __restrict__ in, uint64_t 
     out[w] = x;
 }
 
+// fused bucket-gather + all-to-all: every row goes straight into the receive buffer of the rank that owns its bucket (a
+// cudaMalloc'd buffer mapped through CUDA IPC, written over NVLink; the local bucket is an ordinary store).  Lanes of a warp
+// write consecutive 8-byte words of one destination except at a bucket boundary, so the peer traffic is full 32-byte sectors.
+__device__ __forceinline__ uint32_t bucket_of(const PushDst& d, uint64_t i) {
+    uint32_t b = 0;
+    while (b + 1 < d.n && d.begin[b + 1] <= i) ++b;
+    return b;
+}
+__global__ void kmer_push_kernel(const uint32_t* __restrict__ idx, uint64_t n_send, const uint64_t* __restrict__ value,
+                                 const uint64_t* __restrict__ qinfo, uint64_t seq_add, const __grid_constant__ PushDst d) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_send) return;
+    const uint32_t b = bucket_of(d, i);
+    const uint32_t s = idx[i];
+    uint64_t* dst = reinterpret_cast<uint64_t*>(d.base[b]);
+    const uint64_t row = d.row_off[b] + (i - d.begin[b]);
+    dst[row] = value[s];                                        // receiver layout: values [0, total) | qinfo [total, 2 total)
+    dst[d.total[b] + row] = qinfo[s] + (seq_add << 32);
+}
+__global__ void match_push_kernel(const uint32_t* __restrict__ idx, uint64_t n_send, const uint64_t* __restrict__ in,
+                                  const __grid_constant__ PushDst d) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= 3 * n_send) return;
+    const uint64_t i = w / 3;
+    const uint32_t b = bucket_of(d, i);
+    uint64_t* dst = reinterpret_cast<uint64_t*>(d.base[b]);
+    dst[3 * (d.row_off[b] + (i - d.begin[b])) + (w - 3 * i)] = in[3ull * idx[i] + (w - 3 * i)];
+}
+
 __global__ void iota_kernel(uint32_t* __restrict__ idx, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) idx[i] = (uint32_t)i;
@@ -139,6 +168,15 @@ void gather_matches(const uint32_t* idx, uint64_t n_send, const mbl_match_rec* i
 
 void localize_matches(const mbl_match_rec* in, uint64_t n, uint64_t seq_sub, mbl_match_rec* out, cudaStream_t st) {
     if (n) match_localize_kernel<<<blocks_for(3 * n), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(in), n, seq_sub, reinterpret_cast<uint64_t*>(out));
+}
+
+void push_kmers(const uint32_t* idx, uint64_t n_send, const uint64_t* value, const uint64_t* qinfo, uint64_t seq_add, const PushDst& d,
+                cudaStream_t st) {
+    if (n_send) kmer_push_kernel<<<blocks_for(n_send), 256, 0, st>>>(idx, n_send, value, qinfo, seq_add, d);
+}
+
+void push_matches(const uint32_t* idx, uint64_t n_send, const mbl_match_rec* in, const PushDst& d, cudaStream_t st) {
+    if (n_send) match_push_kernel<<<blocks_for(3 * n_send), 256, 0, st>>>(idx, n_send, reinterpret_cast<const uint64_t*>(in), d);
 }
 
 void launch_iota(uint32_t* idx, uint64_t n, cudaStream_t st) {

@@ -162,6 +162,16 @@ struct ShardBounds {                // ascending lower bounds of the buckets: sh
     uint32_t n;
     uint64_t bound[kMaxShards];
 };
+struct PushDst {                    // where the rows of bucket b go: rows [begin[b], begin[b+1]) of the send order land at
+    uint32_t n;                     // base[b] + row_off[b] (peer-mapped or local memory); total[b] = rows the receiver gets
+    uint64_t begin[kMaxShards + 1];
+    void* base[kMaxShards];
+    uint64_t row_off[kMaxShards];
+    uint64_t total[kMaxShards];
+};
+void push_kmers(const uint32_t* idx, uint64_t n_send, const uint64_t* value, const uint64_t* qinfo, uint64_t seq_add, const PushDst& d,
+                cudaStream_t st);
+void push_matches(const uint32_t* idx, uint64_t n_send, const mbl_match_rec* in, const PushDst& d, cudaStream_t st);
 size_t bucket_sort_temp_bytes(size_t n);
 // stable partition by bucket; return the permutation (idx_a or idx_b); d_begin[0..b.n] = bucket starts, d_begin[b.n] = elements kept
 const uint32_t* bucket_kmers(void* tmp, size_t tmp_bytes, const uint64_t* value, uint64_t n, const ShardBounds& b, uint8_t* key_a, uint8_t* key_b,

@@ -78,6 +78,15 @@ struct mbl_ctx {
     // index-sharded mode (mbl_shard_*): bucket keys / permutations, send buffers, bucket starts
     Buf sh_key_a, sh_key_b, sh_idx_a, sh_idx_b, sh_begin, send_value, send_qinfo, send_match, sh_tmp;
     uint64_t seq_base = 0;              // index of the resident batch's first read among all ranks' reads
+    const uint32_t* sh_perm = nullptr;  // bucket permutation of the last mbl_shard_extract / mbl_shard_match
+    uint32_t sh_n = 0;                  // its bucket count
+    uint64_t sh_begin_h[kMaxShards + 2] = {};   // its bucket starts
+    // peer-memory transport: this rank's receive buffers and the peers' (IPC-mapped or same-process pointers)
+    void *recv_kmers = nullptr, *recv_matches = nullptr;
+    uint64_t recv_kmer_rows = 0, recv_match_rows = 0;
+    void* peer_kmers[kMaxShards] = {};
+    void* peer_matches[kMaxShards] = {};
+    bool peer_opened[kMaxShards][2] = {};
     mbl_shard shard{};                  // the value range this context holds (whole index: first_value 0)
     bool is_shard = false;
     // results of the whole batch
@@ -607,6 +616,11 @@ void mbl_destroy(mbl_ctx* c) {
         c->shadow = nullptr;
     }
     free_db(c);
+    for (uint32_t p = 0; p < kMaxShards; ++p) {
+        if (c->peer_opened[p][0] && c->peer_kmers[p]) cudaIpcCloseMemHandle(c->peer_kmers[p]);
+        if (c->peer_opened[p][1] && c->peer_matches[p]) cudaIpcCloseMemHandle(c->peer_matches[p]);
+    }
+    cudaFree(c->recv_kmers); cudaFree(c->recv_matches);
     cudaFree(c->d_base_code); cudaFree(c->d_codon); cudaFree(c->d_ham_pair); cudaFree(c->d_ham_single);
     release_lane(c);
     delete c;
@@ -894,10 +908,10 @@ int mbl_classify_batch(mbl_ctx* c, const mbl_batch* b, mbl_read_result* out, int
     return mbl_download_results(c, out, taxcnt_pairs, cap_pairs, used_pairs);
 }
 
-// ---- index-sharded mode: the three phases one rank runs around the two exchanges (include/metabuli_b200.h) ----------------
+// ---- index-sharded mode: the phases one rank runs around the two exchanges (include/metabuli_b200.h) ---------------------
 int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_t n_shards, const uint64_t* shard_first_value,
-                      uint64_t* send_counts, const uint64_t** d_send_value, const uint64_t** d_send_qinfo) {
-    if (!c || !b || !shard_first_value || !send_counts || !d_send_value || !d_send_qinfo) return fail(c, MBL_E_BAD_ARG, "null argument");
+                      uint64_t* send_counts) {
+    if (!c || !b || !shard_first_value || !send_counts) return fail(c, MBL_E_BAD_ARG, "null argument");
     if (n_shards < 1 || n_shards > kMaxShards) return fail(c, MBL_E_BAD_ARG, "1..64 shards");
     if (seq_base + b->n_reads >= (1ull << 29)) return fail(c, MBL_E_BAD_ARG, "global read index exceeds the 29-bit sequenceID (Kmer.h:13)");
     c->stats.ms[MBL_STAGE_H2D] = 0;
@@ -917,13 +931,13 @@ int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_
         c->seq_base = seq_base;
         c->results.get<mbl_read_result>(c->n_reads + 1);
         for (uint32_t s = 0; s < n_shards; ++s) send_counts[s] = 0;
-        *d_send_value = nullptr; *d_send_qinfo = nullptr;
+        c->sh_n = n_shards; c->sh_perm = nullptr;
+        for (uint32_t s = 0; s <= n_shards; ++s) c->sh_begin_h[s] = 0;
         if (c->subs.empty()) return MBL_OK;
         const SubBatch sb = c->subs[0];
         stage_extract(c, sb);
-        const uint64_t S = sb.slots, S8 = (S + 31) & ~31ull;
+        const uint64_t S = sb.slots;
         const uint64_t* va = (const uint64_t*)c->arena.p;
-        const uint64_t* qa = va + 2 * S8;
         const float ms_k1 = c->stats.ms[MBL_STAGE_EXTRACT];
         StageTimer t(c, MBL_STAGE_EXTRACT);
         ShardBounds sbnd{};
@@ -933,17 +947,35 @@ int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_
         uint32_t *ia = c->sh_idx_a.get<uint32_t>(S + 16), *ib = c->sh_idx_b.get<uint32_t>(S + 16);
         uint64_t* d_begin = c->sh_begin.get<uint64_t>(kMaxShards + 2);
         void* tmp = c->sh_tmp.get<uint8_t>(bucket_sort_temp_bytes(S));
-        const uint32_t* perm = bucket_kmers(tmp, c->sh_tmp.cap, va, S, sbnd, ka, kb, ia, ib, d_begin, st);
-        uint64_t h_begin[kMaxShards + 2];
-        MBL_CUDA(cudaMemcpyAsync(h_begin, d_begin, 8 * (size_t)(n_shards + 1), cudaMemcpyDeviceToHost, st));
-        MBL_CUDA(cudaStreamSynchronize(st));
-        const uint64_t n_send = h_begin[n_shards];
-        for (uint32_t s = 0; s < n_shards; ++s) send_counts[s] = h_begin[s + 1] - h_begin[s];
-        uint64_t *sv = c->send_value.get<uint64_t>(n_send + 16), *sq = c->send_qinfo.get<uint64_t>(n_send + 16);
-        gather_kmers(perm, n_send, va, qa, seq_base, sv, sq, st);
-        c->stats.kernel_launches += 4;
+        c->sh_perm = bucket_kmers(tmp, c->sh_tmp.cap, va, S, sbnd, ka, kb, ia, ib, d_begin, st);
+        MBL_CUDA(cudaMemcpyAsync(c->sh_begin_h, d_begin, 8 * (size_t)(n_shards + 1), cudaMemcpyDeviceToHost, st));
+        c->stats.kernel_launches += 3;
         t.stop();
         c->stats.ms_bucket_kmers = c->stats.ms[MBL_STAGE_EXTRACT] - ms_k1;
+        for (uint32_t s = 0; s < n_shards; ++s) send_counts[s] = c->sh_begin_h[s + 1] - c->sh_begin_h[s];
+        MBL_CUDA(cudaGetLastError());
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_shard_pack_kmers(mbl_ctx* c, const uint64_t** d_send_value, const uint64_t** d_send_qinfo) {
+    if (!c || !d_send_value || !d_send_qinfo) return fail(c, MBL_E_BAD_ARG, "null argument");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        *d_send_value = nullptr; *d_send_qinfo = nullptr;
+        const uint64_t n_send = c->sh_begin_h[c->sh_n];
+        if (!n_send || c->subs.empty()) return MBL_OK;
+        const uint64_t S8 = (c->subs[0].slots + 31) & ~31ull;
+        const uint64_t* va = (const uint64_t*)c->arena.p;
+        const float ms_before = c->stats.ms[MBL_STAGE_EXTRACT];
+        StageTimer t(c, MBL_STAGE_EXTRACT);
+        uint64_t *sv = c->send_value.get<uint64_t>(n_send + 16), *sq = c->send_qinfo.get<uint64_t>(n_send + 16);
+        gather_kmers(c->sh_perm, n_send, va, va + 2 * S8, c->seq_base, sv, sq, c->st);
+        c->stats.kernel_launches += 1;
+        t.stop();
+        c->stats.ms_bucket_kmers += c->stats.ms[MBL_STAGE_EXTRACT] - ms_before;
         MBL_CUDA(cudaGetLastError());
         *d_send_value = sv; *d_send_qinfo = sq;
     } catch (const CudaError& e) {
@@ -953,8 +985,8 @@ int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_
 }
 
 int mbl_shard_match(mbl_ctx* c, const uint64_t* d_value, const uint64_t* d_qinfo, uint64_t n, uint32_t n_owners,
-                    const uint64_t* owner_first_read, uint64_t* send_counts, const mbl_match_rec** d_send_match) {
-    if (!c || !owner_first_read || !send_counts || !d_send_match || (n && (!d_value || !d_qinfo))) return fail(c, MBL_E_BAD_ARG, "null argument");
+                    const uint64_t* owner_first_read, uint64_t* send_counts) {
+    if (!c || !owner_first_read || !send_counts || (n && (!d_value || !d_qinfo))) return fail(c, MBL_E_BAD_ARG, "null argument");
     if (!c->db_loaded) return fail(c, MBL_E_BAD_ARG, "mbl_load_db[_shard] has not been called");
     if (n_owners < 1 || n_owners > kMaxShards) return fail(c, MBL_E_BAD_ARG, "1..64 owners");
     if (n >= 4000000000ull) return fail(c, MBL_E_CAPACITY, "more than 4e9 received metamers in one pass");
@@ -962,7 +994,8 @@ int mbl_shard_match(mbl_ctx* c, const uint64_t* d_value, const uint64_t* d_qinfo
         MBL_CUDA(cudaSetDevice(c->cfg.device));
         cudaStream_t st = c->st;
         for (uint32_t o = 0; o < n_owners; ++o) send_counts[o] = 0;
-        *d_send_match = nullptr;
+        c->sh_n = n_owners; c->sh_perm = nullptr;
+        for (uint32_t o = 0; o <= n_owners; ++o) c->sh_begin_h[o] = 0;
         // the received metamers become the phase-1 arena of this context: keys in `value A`, their positions in `slot idx A`
         const uint64_t S8 = (n + 31) & ~31ull;
         uint64_t* ar = c->arena.get<uint64_t>(4 * S8 + 64);
@@ -982,20 +1015,151 @@ int mbl_shard_match(mbl_ctx* c, const uint64_t* d_value, const uint64_t* d_qinfo
         uint32_t *xa = c->sh_idx_a.get<uint32_t>(R + 16), *xb = c->sh_idx_b.get<uint32_t>(R + 16);
         uint64_t* d_begin = c->sh_begin.get<uint64_t>(kMaxShards + 2);
         void* tmp = c->sh_tmp.get<uint8_t>(bucket_sort_temp_bytes(R));
-        const uint32_t* perm = bucket_matches(tmp, c->sh_tmp.cap, (const mbl_match_rec*)c->m_raw.p, R, ob, ka, kb, xa, xb, d_begin, st);
-        uint64_t h_begin[kMaxShards + 2];
-        MBL_CUDA(cudaMemcpyAsync(h_begin, d_begin, 8 * (size_t)(n_owners + 1), cudaMemcpyDeviceToHost, st));
-        MBL_CUDA(cudaStreamSynchronize(st));
-        const uint64_t n_send = h_begin[n_owners];
-        if (n_send != n_match) return fail(c, MBL_E_CUDA, "internal: bucketed match count differs from the merge count");
-        for (uint32_t o = 0; o < n_owners; ++o) send_counts[o] = h_begin[o + 1] - h_begin[o];
+        c->sh_perm = bucket_matches(tmp, c->sh_tmp.cap, (const mbl_match_rec*)c->m_raw.p, R, ob, ka, kb, xa, xb, d_begin, st);
+        MBL_CUDA(cudaMemcpyAsync(c->sh_begin_h, d_begin, 8 * (size_t)(n_owners + 1), cudaMemcpyDeviceToHost, st));
+        c->stats.kernel_launches += 4;
+        t.stop();
+        c->stats.ms_bucket_matches += c->stats.ms[MBL_STAGE_MSORT] - ms_before;
+        if (c->sh_begin_h[n_owners] != n_match) return fail(c, MBL_E_CUDA, "internal: bucketed match count differs from the merge count");
+        for (uint32_t o = 0; o < n_owners; ++o) send_counts[o] = c->sh_begin_h[o + 1] - c->sh_begin_h[o];
+        MBL_CUDA(cudaGetLastError());
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_shard_pack_matches(mbl_ctx* c, const mbl_match_rec** d_send_match) {
+    if (!c || !d_send_match) return fail(c, MBL_E_BAD_ARG, "null argument");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        *d_send_match = nullptr;
+        const uint64_t n_send = c->sh_begin_h[c->sh_n];
+        if (!n_send) return MBL_OK;
+        const float ms_before = c->stats.ms[MBL_STAGE_MSORT];
+        StageTimer t(c, MBL_STAGE_MSORT);
         mbl_match_rec* sm = c->send_match.get<mbl_match_rec>(n_send + 16);
-        gather_matches(perm, n_send, (const mbl_match_rec*)c->m_raw.p, sm, st);
-        c->stats.kernel_launches += 5;
+        gather_matches(c->sh_perm, n_send, (const mbl_match_rec*)c->m_raw.p, sm, c->st);
+        c->stats.kernel_launches += 1;
         t.stop();
         c->stats.ms_bucket_matches += c->stats.ms[MBL_STAGE_MSORT] - ms_before;
         MBL_CUDA(cudaGetLastError());
         *d_send_match = sm;
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+// ---- peer-memory transport: the bucket-gather kernels store straight into the receivers' buffers over NVLink ---------------
+int mbl_shard_recv_buffers(mbl_ctx* c, uint64_t kmer_rows, uint64_t match_rows, void** d_kmers, void** d_matches,
+                           uint8_t* handle_kmers, uint8_t* handle_matches) {
+    if (!c || !d_kmers || !d_matches) return fail(c, MBL_E_BAD_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MBL_IPC_HANDLE_BYTES, "handle size");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        // plain cudaMalloc allocations of their own (IPC handles name whole allocations)
+        for (void** p : {&c->recv_kmers, &c->recv_matches}) { if (*p) cudaFree(*p); *p = nullptr; }
+        MBL_CUDA(cudaMalloc(&c->recv_kmers, 16 * kmer_rows + 256));
+        MBL_CUDA(cudaMalloc(&c->recv_matches, 24 * match_rows + 256));
+        c->recv_kmer_rows = kmer_rows; c->recv_match_rows = match_rows;
+        if (handle_kmers) MBL_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_kmers), c->recv_kmers));
+        if (handle_matches) MBL_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_matches), c->recv_matches));
+        *d_kmers = c->recv_kmers; *d_matches = c->recv_matches;
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_shard_attach_peer(mbl_ctx* c, uint32_t peer, const uint8_t* handle_kmers, const uint8_t* handle_matches, void* raw_kmers,
+                          void* raw_matches) {
+    if (!c || peer >= kMaxShards) return fail(c, MBL_E_BAD_ARG, "bad peer");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        for (int k = 0; k < 2; ++k) {
+            void*& slot = k ? c->peer_matches[peer] : c->peer_kmers[peer];
+            bool& opened = k ? c->peer_opened[peer][1] : c->peer_opened[peer][0];
+            if (opened && slot) cudaIpcCloseMemHandle(slot);
+            opened = false; slot = nullptr;
+            void* raw = k ? raw_matches : raw_kmers;
+            const uint8_t* h = k ? handle_matches : handle_kmers;
+            if (raw) { slot = raw; continue; }                       // same process (or this rank itself)
+            if (!h) return fail(c, MBL_E_BAD_ARG, "neither a handle nor a pointer for the peer buffer");
+            cudaIpcMemHandle_t hh;
+            memcpy(&hh, h, sizeof hh);
+            MBL_CUDA(cudaIpcOpenMemHandle(&slot, hh, cudaIpcMemLazyEnablePeerAccess));
+            opened = true;
+        }
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_shard_detach_peers(mbl_ctx* c) {
+    if (!c) return MBL_E_BAD_ARG;
+    cudaSetDevice(c->cfg.device);
+    for (uint32_t p = 0; p < kMaxShards; ++p) {
+        if (c->peer_opened[p][0] && c->peer_kmers[p]) cudaIpcCloseMemHandle(c->peer_kmers[p]);
+        if (c->peer_opened[p][1] && c->peer_matches[p]) cudaIpcCloseMemHandle(c->peer_matches[p]);
+        c->peer_opened[p][0] = c->peer_opened[p][1] = false;
+        c->peer_kmers[p] = c->peer_matches[p] = nullptr;
+    }
+    cudaGetLastError();
+    return MBL_OK;
+}
+
+int mbl_shard_push_kmers(mbl_ctx* c, const uint64_t* dst_row_offset, const uint64_t* dst_total_rows) {
+    if (!c || !dst_row_offset || !dst_total_rows) return fail(c, MBL_E_BAD_ARG, "null argument");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        const uint64_t n_send = c->sh_begin_h[c->sh_n];
+        if (!n_send || c->subs.empty()) return MBL_OK;
+        PushDst d{};
+        d.n = c->sh_n;
+        for (uint32_t s = 0; s < c->sh_n; ++s) {
+            d.begin[s] = c->sh_begin_h[s];
+            d.base[s] = c->peer_kmers[s]; d.row_off[s] = dst_row_offset[s]; d.total[s] = dst_total_rows[s];
+            if (c->sh_begin_h[s + 1] > c->sh_begin_h[s] && !d.base[s]) return fail(c, MBL_E_BAD_ARG, "peer buffer not attached");
+        }
+        d.begin[c->sh_n] = n_send;
+        const uint64_t S8 = (c->subs[0].slots + 31) & ~31ull;
+        const uint64_t* va = (const uint64_t*)c->arena.p;
+        const float ms_before = c->stats.ms[MBL_STAGE_EXTRACT];
+        StageTimer t(c, MBL_STAGE_EXTRACT);
+        push_kmers(c->sh_perm, n_send, va, va + 2 * S8, c->seq_base, d, c->st);
+        c->stats.kernel_launches += 1;
+        t.stop();
+        c->stats.ms_bucket_kmers += c->stats.ms[MBL_STAGE_EXTRACT] - ms_before;
+        MBL_CUDA(cudaGetLastError());
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_shard_push_matches(mbl_ctx* c, const uint64_t* dst_row_offset) {
+    if (!c || !dst_row_offset) return fail(c, MBL_E_BAD_ARG, "null argument");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        const uint64_t n_send = c->sh_begin_h[c->sh_n];
+        if (!n_send) return MBL_OK;
+        PushDst d{};
+        d.n = c->sh_n;
+        for (uint32_t s = 0; s < c->sh_n; ++s) {
+            d.begin[s] = c->sh_begin_h[s];
+            d.base[s] = c->peer_matches[s]; d.row_off[s] = dst_row_offset[s]; d.total[s] = 0;
+            if (c->sh_begin_h[s + 1] > c->sh_begin_h[s] && !d.base[s]) return fail(c, MBL_E_BAD_ARG, "peer buffer not attached");
+        }
+        d.begin[c->sh_n] = n_send;
+        const float ms_before = c->stats.ms[MBL_STAGE_MSORT];
+        StageTimer t(c, MBL_STAGE_MSORT);
+        push_matches(c->sh_perm, n_send, (const mbl_match_rec*)c->m_raw.p, d, c->st);
+        c->stats.kernel_launches += 1;
+        t.stop();
+        c->stats.ms_bucket_matches += c->stats.ms[MBL_STAGE_MSORT] - ms_before;
+        MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
     }

@@ -7,6 +7,10 @@ The reference has no counterpart: its OpenMP threads share one diffIdx and start
 
     rank r:  phase_extract(own reads)  --a2a #1: (value, qinfo)-->  phase_match(own shard)  --a2a #2: 24-B rows-->  phase_score
 
+Two transports for the exchanges: "peer" — the library's bucket-gather kernels store every row straight into the receiving
+rank's buffer over NVLink (CUDA-IPC-mapped peer memory; gather and all-to-all are ONE kernel, then a barrier) — and
+"collective" — pack into send buffers + all_to_all_single (NCCL; gloo in the CPU tests).
+
 `classify_index_sharded` drives one batch through the phases; `phases` is any object with the three phase methods
 (ShardedClassifier = the CUDA path; the CPU tests plug in an oracle-backed stand-in to exercise the exchange logic over gloo).
 """
@@ -42,6 +46,7 @@ def shard_first_values(shards) -> np.ndarray:
 # ---- exchanges ------------------------------------------------------------------------------------------------------
 class DistExchange:
     """Variable-count all-to-all over a torch.distributed process group (NCCL on GPUs, gloo in the CPU tests)."""
+    same_process = False
 
     def __init__(self, dist, device):
         self.dist = dist
@@ -49,15 +54,21 @@ class DistExchange:
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
 
-    def counts(self, send_counts):
+    def count_matrix(self, send_counts) -> np.ndarray:
+        """M[src][dst] = rows rank src sends to rank dst (every rank learns the whole matrix)."""
         import torch
         s = torch.tensor([int(x) for x in send_counts], dtype=torch.int64, device=self.device)
-        r = torch.zeros(self.world, dtype=torch.int64, device=self.device)
-        self.dist.all_to_all_single(r, s)
-        return [int(x) for x in r.tolist()]
+        parts = [torch.zeros(self.world, dtype=torch.int64, device=self.device) for _ in range(self.world)]
+        self.dist.all_gather(parts, s)
+        return np.array([[int(x) for x in p.tolist()] for p in parts], dtype=np.int64)
 
-    def all_gather_int(self, v: int):
-        return self.counts([int(v)] * self.world)       # every rank sends its number to every rank
+    def all_gather_bytes(self, b: bytes):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, bytes(b))
+        return out
+
+    def barrier(self):
+        self.dist.barrier()
 
     def rows(self, send, send_counts, recv_counts):
         """send: tensor whose dim 0 is split by send_counts -> tensor of sum(recv_counts) rows."""
@@ -70,9 +81,26 @@ class DistExchange:
         return recv
 
 
+class SelfExchange:
+    """world_size 1: the exchanges are the identity (single-GPU runs of the sharded entry points)."""
+    world, rank, same_process = 1, 0, True
+
+    def count_matrix(self, send_counts):
+        return np.array([[int(x) for x in send_counts]], dtype=np.int64)
+
+    def all_gather_bytes(self, b):
+        return [bytes(b)]
+
+    def barrier(self):
+        pass
+
+    def rows(self, send, send_counts, recv_counts):
+        return send
+
+
 # ---- the CUDA phases ------------------------------------------------------------------------------------------------
 class _DevArray:
-    """Zero-copy view of library-owned device memory for torch (valid until the context's next call)."""
+    """Zero-copy view of library-owned device memory for torch (valid until the context's next phase)."""
 
     def __init__(self, ptr: int, shape, typestr="<i8"):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
@@ -92,6 +120,8 @@ class ShardedClassifier:
         self.ctx = self.clf.ctx
         self.device = f"cuda:{opt.device}"
         self._keep = None
+        self.peer_rows = (0, 0)            # capacity (k-mer rows, match rows) of every rank's receive buffers
+        self._recv = (0, 0)                # this rank's receive buffers (device pointers)
 
     def close(self):
         self.clf.close()
@@ -103,53 +133,96 @@ class ShardedClassifier:
             return torch.empty(tuple(shape), dtype=torch.int64, device=self.device)
         return torch.as_tensor(_DevArray(ptr, shape), device=self.device)
 
+    # -- phases ---------------------------------------------------------------------------------------------------
     def phase_extract(self, bases1, off1, bases2, off2, seq_base: int):
         batch, self._keep = self.clf.make_batch(bases1, off1, bases2, off2)
         self.clf._n_resident = int(batch.n_reads)
         n = len(self.shards)
         counts = np.zeros(n, dtype=np.uint64)
-        pv, pq = C.c_void_p(), C.c_void_p()
         self.clf._check(self.lib.mbl_shard_extract(self.ctx, C.byref(batch), int(seq_base), n, self.first_values.ctypes.data_as(C.c_void_p),
-                                                   counts.ctypes.data_as(C.c_void_p), C.byref(pv), C.byref(pq)))
-        total = int(counts.sum())
-        return self._tensor(pv.value, (total,)), self._tensor(pq.value, (total,)), [int(x) for x in counts]
+                                                   counts.ctypes.data_as(C.c_void_p)))
+        return [int(x) for x in counts]
 
     def phase_match(self, recv_value, recv_qinfo, owner_first_read):
         own = np.ascontiguousarray(owner_first_read, dtype=np.uint64)
         n_owners = own.size - 1
         counts = np.zeros(n_owners, dtype=np.uint64)
-        pm = C.c_void_p()
         n = int(recv_value.numel())
         self.clf._check(self.lib.mbl_shard_match(self.ctx, recv_value.data_ptr() if n else None, recv_qinfo.data_ptr() if n else None, n, n_owners,
-                                                 own.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), C.byref(pm)))
-        total = int(counts.sum())
-        return self._tensor(pm.value, (total, 3)), [int(x) for x in counts]
+                                                 own.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)))
+        return [int(x) for x in counts]
 
     def phase_score(self, recv_match):
         n = int(recv_match.shape[0])
         self.clf._check(self.lib.mbl_shard_score(self.ctx, recv_match.data_ptr() if n else None, n))
         return self.clf.download_results()
 
+    # -- transport A: contiguous send buffers for a collective ----------------------------------------------------
+    def pack_kmers(self, total: int):
+        pv, pq = C.c_void_p(), C.c_void_p()
+        self.clf._check(self.lib.mbl_shard_pack_kmers(self.ctx, C.byref(pv), C.byref(pq)))
+        return self._tensor(pv.value, (total,)), self._tensor(pq.value, (total,))
 
-class SelfExchange:
-    """world_size 1: the exchanges are the identity (single-GPU runs of the sharded entry points)."""
-    world, rank = 1, 0
+    def pack_matches(self, total: int):
+        pm = C.c_void_p()
+        self.clf._check(self.lib.mbl_shard_pack_matches(self.ctx, C.byref(pm)))
+        return self._tensor(pm.value, (total, 3))
 
-    def counts(self, send_counts):
-        return [int(x) for x in send_counts]
+    # -- transport B: peers store into this rank's receive buffers ----------------------------------------------------
+    supports_push = True
 
-    def all_gather_int(self, v: int):
-        return [int(v)]
+    def setup_peer_buffers(self, exchange, kmer_rows: int, match_rows: int):
+        """Collective: every rank (re)allocates its receive buffers with the same capacity and maps everybody else's."""
+        lib = self.lib
+        exchange.barrier()
+        lib.mbl_shard_detach_peers(self.ctx)
+        exchange.barrier()
+        dk, dm = C.c_void_p(), C.c_void_p()
+        hk = (C.c_uint8 * _ffi.IPC_HANDLE_BYTES)()
+        hm = (C.c_uint8 * _ffi.IPC_HANDLE_BYTES)()
+        self.clf._check(lib.mbl_shard_recv_buffers(self.ctx, int(kmer_rows), int(match_rows), C.byref(dk), C.byref(dm), hk, hm))
+        self._recv = (int(dk.value), int(dm.value))
+        mine = bytes(hk) + bytes(hm) + int(dk.value).to_bytes(8, "little") + int(dm.value).to_bytes(8, "little")
+        everyone = exchange.all_gather_bytes(mine)
+        H = _ffi.IPC_HANDLE_BYTES
+        for peer, blob in enumerate(everyone):
+            raw_k = int.from_bytes(blob[2 * H:2 * H + 8], "little")
+            raw_m = int.from_bytes(blob[2 * H + 8:2 * H + 16], "little")
+            if peer == exchange.rank or exchange.same_process:
+                rc = lib.mbl_shard_attach_peer(self.ctx, peer, None, None, raw_k, raw_m)
+            else:
+                bk = (C.c_uint8 * H).from_buffer_copy(blob[:H])
+                bm = (C.c_uint8 * H).from_buffer_copy(blob[H:2 * H])
+                rc = lib.mbl_shard_attach_peer(self.ctx, peer, bk, bm, None, None)
+            self.clf._check(rc)
+        self.peer_rows = (int(kmer_rows), int(match_rows))
+        exchange.barrier()
 
-    def rows(self, send, send_counts, recv_counts):
-        return send
+    def push_kmers(self, row_off, totals):
+        ro = np.ascontiguousarray(row_off, dtype=np.uint64)
+        tt = np.ascontiguousarray(totals, dtype=np.uint64)
+        self.clf._check(self.lib.mbl_shard_push_kmers(self.ctx, ro.ctypes.data_as(C.c_void_p), tt.ctypes.data_as(C.c_void_p)))
+
+    def push_matches(self, row_off):
+        ro = np.ascontiguousarray(row_off, dtype=np.uint64)
+        self.clf._check(self.lib.mbl_shard_push_matches(self.ctx, ro.ctypes.data_as(C.c_void_p)))
+
+    def received_kmers(self, total: int):
+        return self._tensor(self._recv[0], (total,)), self._tensor(self._recv[0] + 8 * total if total else 0, (total,))
+
+    def received_matches(self, total: int):
+        return self._tensor(self._recv[1], (total, 3))
 
 
 # ---- one batch through the sharded path ------------------------------------------------------------------------------
-def classify_index_sharded(phases, exchange, bases1, off1, bases2=None, off2=None, timings: dict | None = None):
+def classify_index_sharded(phases, exchange, bases1, off1, bases2=None, off2=None, timings: dict | None = None, transport: str = "auto"):
     """Every rank calls this with ITS reads; returns (results, taxcnt_pairs) for those reads, bit-identical to a
-    single-GPU classify of the same reads against the whole index.  timings (optional) receives wall-clock seconds of the
-    phases and exchanges (every phase and exchange ends synchronised) and the bytes this rank put on the wire."""
+    single-GPU classify of the same reads against the whole index.
+
+    transport: "peer" = the gather kernels store into the receivers' buffers over NVLink (fused gather + all-to-all),
+    "collective" = pack + all_to_all_single (NCCL / gloo), "auto" = peer when the phases support it.
+    timings (optional) receives wall-clock seconds of the phases and exchanges (each ends synchronised) and the bytes this rank
+    put on the wire."""
     import time
     t = [time.perf_counter()]
 
@@ -158,29 +231,54 @@ def classify_index_sharded(phases, exchange, bases1, off1, bases2=None, off2=Non
         if timings is not None:
             timings[key] = timings.get(key, 0.0) + (t[-1] - t[-2])
 
+    rank, world = exchange.rank, exchange.world
+    use_peer = transport == "peer" or (transport == "auto" and getattr(phases, "supports_push", False))
     n_reads = int(off1.size - 1)
-    per_rank = exchange.all_gather_int(n_reads)
+    per_rank = exchange.count_matrix([n_reads] * world)[:, rank]
     owner_first_read = np.concatenate([[0], np.cumsum(per_rank)]).astype(np.uint64)
-    seq_base = int(owner_first_read[exchange.rank])
+    seq_base = int(owner_first_read[rank])
+
     # phase 1 + all-to-all #1: metamers to the shard that owns their amino-acid part
-    sv, sq, kc = phases.phase_extract(bases1, off1, bases2, off2, seq_base)
+    kc = phases.phase_extract(bases1, off1, bases2, off2, seq_base)
+    K = exchange.count_matrix(kc)                       # K[src][dst]
     lap("s_extract")
-    rc = exchange.counts(kc)
-    rv = exchange.rows(sv, kc, rc)
-    rq = exchange.rows(sq, kc, rc)
+    k_tot = K.sum(axis=0)
+    if use_peer and int(k_tot.max()) > phases.peer_rows[0]:
+        # receive buffers sized from the traffic seen (same decision on every rank: it depends on the shared matrix only)
+        phases.setup_peer_buffers(exchange, int(1.25 * k_tot.max()) + 4096, max(phases.peer_rows[1], int(0.6 * k_tot.max()) + 4096))
+    if use_peer:
+        phases.push_kmers(K[:rank].sum(axis=0), k_tot)
+        exchange.barrier()
+        rv, rq = phases.received_kmers(int(k_tot[rank]))
+    else:
+        sv, sq = phases.pack_kmers(int(sum(kc)))
+        rv = exchange.rows(sv, kc, K[:, rank])
+        rq = exchange.rows(sq, kc, K[:, rank])
+        del sv, sq
     lap("s_a2a_kmers")
+
     # phase 2 + all-to-all #2: matches back to the rank that owns the read
-    sm, mc = phases.phase_match(rv, rq, owner_first_read)
-    del rv, rq, sv, sq
+    mc = phases.phase_match(rv, rq, owner_first_read)
+    del rv, rq
+    Mx = exchange.count_matrix(mc)
     lap("s_match")
-    rmc = exchange.counts(mc)
-    rm = exchange.rows(sm, mc, rmc)
+    m_tot = Mx.sum(axis=0)
+    if use_peer and int(m_tot.max()) > phases.peer_rows[1]:
+        phases.setup_peer_buffers(exchange, phases.peer_rows[0], int(1.25 * m_tot.max()) + 4096)
+    if use_peer:
+        phases.push_matches(Mx[:rank].sum(axis=0))
+        exchange.barrier()
+        rm = phases.received_matches(int(m_tot[rank]))
+    else:
+        sm = phases.pack_matches(int(sum(mc)))
+        rm = exchange.rows(sm, mc, Mx[:, rank])
+        del sm
     lap("s_a2a_matches")
+
     # phase 3
     out = phases.phase_score(rm)
     lap("s_score")
     if timings is not None:
-        off_rank = lambda c: int(sum(c)) - int(c[exchange.rank])
-        timings["a2a_kmer_bytes"] = timings.get("a2a_kmer_bytes", 0) + 16 * off_rank(kc)
-        timings["a2a_match_bytes"] = timings.get("a2a_match_bytes", 0) + 24 * off_rank(mc)
+        timings["a2a_kmer_bytes"] = timings.get("a2a_kmer_bytes", 0) + 16 * (int(sum(kc)) - int(kc[rank]))
+        timings["a2a_match_bytes"] = timings.get("a2a_match_bytes", 0) + 24 * (int(sum(mc)) - int(mc[rank]))
     return out

@@ -28,11 +28,18 @@ class LocalExchange:
         w.barrier.wait()
         return got
 
-    def counts(self, send_counts):
-        return [int(x) for x in self._a2a([int(x) for x in send_counts])]
+    same_process = True
 
-    def all_gather_int(self, v):
-        return self.counts([int(v)] * self.world)
+    def count_matrix(self, send_counts):
+        import numpy as np
+        rows = self._a2a([[int(x) for x in send_counts]] * self.world)
+        return np.array(rows, dtype=np.int64)
+
+    def all_gather_bytes(self, b):
+        return self._a2a([bytes(b)] * self.world)
+
+    def barrier(self):
+        self.w.barrier.wait()
 
     def rows(self, send, send_counts, recv_counts):
         parts = list(torch.split(send, [int(x) for x in send_counts], dim=0))

@@ -87,14 +87,20 @@ class OraclePhases:
         sid = np.searchsorted(self.first, v & AA_MASK, side="right") - 1
         order = np.argsort(sid, kind="stable")
         counts = np.bincount(sid, minlength=len(self.shards)).tolist()
-        return (torch.from_numpy(v[order].view(np.int64).copy()), torch.from_numpy(q[order].view(np.int64).copy()), counts)
+        self._packed = (torch.from_numpy(v[order].view(np.int64).copy()), torch.from_numpy(q[order].view(np.int64).copy()))
+        return counts
+
+    def pack_kmers(self, total):
+        assert int(self._packed[0].numel()) == total
+        return self._packed
 
     def phase_match(self, rv, rq, owner_first_read):
         v = rv.numpy().view(np.uint64)
         q = rq.numpy().view(np.uint64)
         n_owners = len(owner_first_read) - 1
         if v.size == 0 or self.odb is None:
-            return torch.zeros((0, 3), dtype=torch.int64), [0] * n_owners
+            self._packed_m = torch.zeros((0, 3), dtype=torch.int64)
+            return [0] * n_owners
         sv, sq = oracle.sort_kmers(v, q)
         m = self.odb.match(sv, sq)
         seq = ((m["qinfo"] >> np.uint64(32)) & SEQ_MASK).astype(np.int64) - 1
@@ -102,7 +108,12 @@ class OraclePhases:
         order = np.argsort(own, kind="stable")
         counts = np.bincount(own, minlength=n_owners).tolist()
         rows = np.ascontiguousarray(m[order]).view(np.int64).reshape(-1, 3)
-        return torch.from_numpy(rows.copy()), counts
+        self._packed_m = torch.from_numpy(rows.copy())
+        return counts
+
+    def pack_matches(self, total):
+        assert int(self._packed_m.shape[0]) == total
+        return self._packed_m
 
     def phase_score(self, rm):
         m = rm.numpy().reshape(-1).view(oracle.MATCH_DTYPE).copy()

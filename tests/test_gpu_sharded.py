@@ -12,8 +12,10 @@ from test_sharded_gloo import _expected, _same
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,world", [("multi_se", 2), ("multi_se", 3), ("multi_pe", 2), ("ragged_se", 4), ("format1_pe", 2), ("long", 2)])
-def test_sharded_equals_whole_index(name, world):
+@pytest.mark.parametrize("name,world,transport", [("multi_se", 2, "peer"), ("multi_se", 3, "collective"), ("multi_pe", 2, "collective"),
+                                                  ("multi_pe", 3, "peer"), ("ragged_se", 4, "peer"), ("format1_pe", 2, "peer"),
+                                                  ("long", 2, "collective"), ("long", 3, "peer")])
+def test_sharded_equals_whole_index(name, world, transport):
     from local_exchange import LocalWorld
     from metabuli_b200 import ClassifyOptions, multigpu, sharded
     sdb, reads, seq_mode = synth_cases.build(name)
@@ -32,7 +34,7 @@ def test_sharded_equals_whole_index(name, world):
             b1, o1 = multigpu.slice_batch(reads[0], reads[1], lo, hi)
             b2, o2 = multigpu.slice_batch(reads[2], reads[3], lo, hi) if len(reads) > 2 and reads[2] is not None else (None, None)
             for _ in range(2):                      # twice: workspace reuse across batches
-                res, pairs = sharded.classify_index_sharded(sc, lw.exchange(rank), b1, o1, b2, o2)
+                res, pairs = sharded.classify_index_sharded(sc, lw.exchange(rank), b1, o1, b2, o2, transport=transport)
             ok[rank] = _same(res, pairs, want_res, want_pairs, lo, hi)
             stats[rank] = sc.clf.stats()
             sc.close()
