@@ -125,6 +125,15 @@ int  mbl_classify_resident(mbl_ctx* ctx);
 int  mbl_download_results(mbl_ctx* ctx, mbl_read_result* out, int32_t* taxcnt_pairs,
                           size_t taxcnt_cap_pairs, size_t* taxcnt_used_pairs);
 
+/* Streaming over many batches (the QuerySplit loop, Classifier.cpp:81-140, with the next split's reads on their way while
+ * the current split is classified): mbl_prefetch_batch starts the asynchronous upload of a batch into a staging buffer on a
+ * copy stream and returns; mbl_classify_prefetched makes the staged batch resident, starts the upload of `next` (may be
+ * NULL) and classifies.  Host buffers of a prefetched batch must stay valid (and should be pinned) until the
+ * mbl_classify_prefetched call that consumes it returns. */
+int  mbl_prefetch_batch(mbl_ctx* ctx, const mbl_batch* batch);
+int  mbl_classify_prefetched(mbl_ctx* ctx, const mbl_batch* next, mbl_read_result* out, int32_t* taxcnt_pairs,
+                             size_t taxcnt_cap_pairs, size_t* taxcnt_used_pairs);
+
 /* ---- stage-level entry points (parity tests against the oracle) -------------------------------- */
 /* KmerExtractor::fillQueryKmerBufferParallel[_paired] (KmerExtractor.cpp:83-290): fills every reserved
  * slot; blank slots (N windows) are value = UINT64_MAX, qinfo = 0.  *n = number of slots. */

@@ -86,7 +86,7 @@ assert RESULT_DTYPE.itemsize == C.sizeof(ReadResult) == 28
 assert MATCH_DTYPE.itemsize == 24
 
 EXPORTS = ["mbl_create", "mbl_destroy", "mbl_last_error", "mbl_load_db", "mbl_classify_batch", "mbl_upload_batch",
-           "mbl_classify_resident", "mbl_download_results", "mbl_extract", "mbl_sort_kmers", "mbl_match", "mbl_sort_matches",
+           "mbl_classify_resident", "mbl_download_results", "mbl_prefetch_batch", "mbl_classify_prefetched", "mbl_extract", "mbl_sort_kmers", "mbl_match", "mbl_sort_matches",
            "mbl_score", "mbl_get_stats", "mbl_get_db_info", "mbl_host_register", "mbl_host_unregister",
            "mbl_plan_shards", "mbl_load_db_shard", "mbl_shard_extract", "mbl_shard_match", "mbl_shard_score",
            "mbl_shard_pack_kmers", "mbl_shard_pack_matches", "mbl_shard_recv_buffers", "mbl_shard_attach_peer", "mbl_shard_detach_peers", "mbl_shard_push_kmers",
@@ -113,6 +113,8 @@ def load_library() -> C.CDLL:
     lib.mbl_load_db.argtypes = [vp, C.POINTER(Db), C.POINTER(Taxonomy)]
     lib.mbl_classify_batch.argtypes = [vp, C.POINTER(Batch), vp, vp, sz, C.POINTER(sz)]
     lib.mbl_upload_batch.argtypes = [vp, C.POINTER(Batch)]
+    lib.mbl_prefetch_batch.argtypes = [vp, C.POINTER(Batch)]
+    lib.mbl_classify_prefetched.argtypes = [vp, C.POINTER(Batch), vp, vp, sz, C.POINTER(sz)]
     lib.mbl_classify_resident.argtypes = [vp]
     lib.mbl_download_results.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     lib.mbl_extract.argtypes = [vp, C.POINTER(Batch), vp, vp, sz, C.POINTER(sz)]

@@ -118,6 +118,33 @@ class Classifier:
             del keep
             return out, pairs[: used.value]
 
+    def classify_stream(self, batches):
+        """The QuerySplit loop over many batches: yields (results, taxcnt_pairs) per batch of `batches` (an iterable of
+        (bases1, off1[, bases2, off2]) tuples) while the NEXT batch's reads are already on their way to the device
+        (mbl_prefetch_batch / mbl_classify_prefetched)."""
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        cur_b, cur_keep = self.make_batch(*cur)
+        self._check(self.lib.mbl_prefetch_batch(self.ctx, C.byref(cur_b)))
+        while cur is not None:
+            nxt = next(it, None)
+            nxt_b, nxt_keep = self.make_batch(*nxt) if nxt is not None else (None, None)
+            n = cur_b.n_reads
+            out = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+            cap = max(1 << 16, 5 * n)
+            used = C.c_size_t(0)
+            pairs = np.zeros((cap, 2), dtype=np.int32)
+            rc = self.lib.mbl_classify_prefetched(self.ctx, C.byref(nxt_b) if nxt_b is not None else None, _ptr(out), _ptr(pairs), cap, C.byref(used))
+            if rc == _ffi.MBL_E_CAPACITY:             # the batch is classified and resident: only the download is repeated
+                cap = int(used.value) + 16
+                pairs = np.zeros((cap, 2), dtype=np.int32)
+                rc = self.lib.mbl_download_results(self.ctx, _ptr(out), _ptr(pairs), cap, C.byref(used))
+            self._check(rc)
+            yield out, pairs[: used.value]
+            cur, cur_b, cur_keep = nxt, nxt_b, nxt_keep
+
     def download_results(self):
         """mbl_download_results of the resident batch -> (results[n], taxcnt_pairs[k,2]).  The arrays are views of two pinned
         buffers owned by this object and are overwritten by the next call."""

@@ -29,8 +29,8 @@ namespace mbl {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+// CTA shapes: 256 threads x 3 CTAs per SM (76 registers) or 512 threads x 2 CTAs per SM (64 registers, 32 warps per SM);
+// MergeArgs::cta_threads selects one at launch
 constexpr uint32_t kQueue = 64;              // per-warp hit queue (power of two, >= 63)
 constexpr uint32_t kOutChunk = 1024;         // match slots a warp reserves from the global cursor at a time
 constexpr uint64_t kNone = ~0ull;
@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t aa_hash(uint64_t aa40) { return (uint32_t)((
 struct SmemLayout {
     uint32_t off_rec, off_scan, off_ham, off_queue, off_own, off_qinfo, off_stage, off_bits, off_frag, off_info, off_vals, off_tab, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets) {
+__host__ __device__ inline SmemLayout smem_layout(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets, uint32_t kWarps) {
     SmemLayout l;
     uint32_t o = 64;                                   // two mbarriers + two item slots
     l.off_rec = o;    o += 2 * 64;                     // work item records: current / next
@@ -218,10 +218,12 @@ __global__ void merge_item_fill_kernel(const Tile* __restrict__ tiles, uint64_t 
 }
 
 // ---- the merge kernel ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 3)
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 3 : 2)
 merge_kernel(MergeArgs a) {
+    constexpr int kWarps = kThreads / 32;
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout L = smem_layout(a.max_u16, a.max_kmers, a.n_buckets);
+    const SmemLayout L = smem_layout(a.max_u16, a.max_kmers, a.n_buckets, kWarps);
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);          // [0] fragments, [1] taxids
     unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 32);                 // [2] claimed item numbers
     unsigned int* s_chunk = reinterpret_cast<unsigned int*>(smem + 40);                // query chunk cursor of the current item
@@ -556,7 +558,9 @@ merge_kernel(MergeArgs a) {
     if (lane == 0 && my_matches) atomicAdd(a.out_count + 1, my_matches);
 }
 
-size_t merge_smem_bytes(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets) { return smem_layout(max_u16, max_kmers, n_buckets).total; }
+size_t merge_smem_bytes(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets, int cta_threads) {
+    return smem_layout(max_u16, max_kmers, n_buckets, (uint32_t)cta_threads / 32).total;
+}
 
 void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
     const unsigned blocks = (unsigned)((a.n_tiles + 1 + 255) / 256);
@@ -566,17 +570,23 @@ void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
     merge_item_fill_kernel<<<blocks, 256, 0, st>>>(a.tiles, a.n_tiles, a.q_lo, a.item_cnt, a.item_off, a.items, a.items_cap);
 }
 
-void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st) {
+template <int kThreads>
+static void launch_merge_t(const MergeArgs& a, int sm_count, cudaStream_t st) {
     static size_t attr_smem = 0;
-    const size_t smem = smem_layout(a.max_u16, a.max_kmers, a.n_buckets).total;
+    const size_t smem = smem_layout(a.max_u16, a.max_kmers, a.n_buckets, kThreads / 32).total;
     if (attr_smem != smem) {
-        MBL_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MBL_CUDA(cudaFuncSetAttribute(merge_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
     int per_sm = 0;
-    MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel, kThreads, smem));
+    MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel<kThreads>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    merge_kernel<<<(unsigned)(sm_count * per_sm), kThreads, smem, st>>>(a);
+    merge_kernel<kThreads><<<(unsigned)(sm_count * per_sm), kThreads, smem, st>>>(a);
+}
+
+void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st) {
+    if (a.cta_threads == 512) launch_merge_t<512>(a, sm_count, st);
+    else launch_merge_t<256>(a, sm_count, st);
 }
 
 }  // namespace mbl

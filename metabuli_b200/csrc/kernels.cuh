@@ -100,6 +100,7 @@ struct MergeArgs {
     uint64_t* q_lo;                 // [2 * (n_tiles + 1)]: per tile first query / one past the last query of its prefix range
     int prefix_shift;               // queries are ordered by value >> prefix_shift only
     int dyn_chunks;                 // 1: warps claim 32-query chunks from a shared counter, 0: fixed striding
+    int cta_threads;                // 256 (3 CTAs per SM) or 512 (2 CTAs per SM)
     uint32_t* item_cnt;             // [n_tiles + 1]
     uint32_t* item_off;             // [n_tiles + 1]
     MergeItem* items;
@@ -110,7 +111,7 @@ struct MergeArgs {
 };
 void launch_merge_plan(const MergeArgs& a, cudaStream_t st);      // partition + work items
 void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st);
-size_t merge_smem_bytes(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets);
+size_t merge_smem_bytes(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets, int cta_threads);
 
 // K5
 struct ScoreArgs {

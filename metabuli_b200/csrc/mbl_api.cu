@@ -51,6 +51,7 @@ struct mbl_ctx {
     uint8_t* d_ham_single = nullptr;
     uint32_t tile_cells = 2;            // MBL_TILE_CELLS (measured best on the 8 GiB benchmark index: 3 CTAs per SM)
     int dyn_chunks = 0;                 // MBL_DYN_CHUNKS (measured: no gain over fixed striding)
+    int merge_threads = 256;            // MBL_MERGE_THREADS: 256 (3 CTAs per SM) or 512 (2 CTAs per SM, 32 warps)
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // index
     uint16_t* d_diff = nullptr;
@@ -66,6 +67,13 @@ struct mbl_ctx {
     uint32_t n_reads = 0;
     bool paired = false;
     std::vector<SubBatch> subs;
+    // staging copy of the NEXT batch (mbl_prefetch_batch): uploaded on its own stream while the resident batch is classified
+    Buf stage_bases1, stage_bases2, stage_off1, stage_off2;
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t copy_ev[2] = {};
+    bool staged = false, staged_paired = false;
+    uint32_t staged_reads = 0;
+    std::vector<SubBatch> staged_subs;
     // workspace
     Buf cov1, cov2, w1, w2, slots, slot_off, quot_cnt, quot_off, seg_b, seg_e, res_sub, tax_len, tax_off;
     Buf val_a, val_b, qi_a, qi_b, cub_tmp;
@@ -160,8 +168,8 @@ void free_db(mbl_ctx* c) {
 
 // host-side planning of sub-batches from the read lengths (QueryIndexer::indexQueryFile analogue,
 // QueryIndexer.cpp:30-147, with the HBM budget in place of --max-ram)
-void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
-    c->subs.clear();
+void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots, std::vector<SubBatch>& subs) {
+    subs.clear();
     auto read_cost = [&](uint32_t r, uint64_t& s, uint64_t& q, uint32_t& mp) {
         int l1 = (int)(b->offsets[r + 1] - b->offsets[r]);
         int w1 = windows_per_frame(l1), c1 = max_covered_length(l1), w2 = 0, c2 = 0;
@@ -205,7 +213,7 @@ void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
     // large batches are cut in (at least) two so that the two pipeline lanes overlap (mbl_classify_resident); each lane then
     // owns half of the workspace budget
     const bool split = may_split;
-    if (!split && all.slots <= max_slots && all.quots <= 0xF0000000ull) { c->subs.push_back(all); return; }
+    if (!split && all.slots <= max_slots && all.quots <= 0xF0000000ull) { subs.push_back(all); return; }
     if (split) {
         max_slots /= 2;
         SubBatch h[2] = {SubBatch{0, 0, 0, 0, 0}, SubBatch{0, 0, 0, 0, 0}};
@@ -215,7 +223,7 @@ void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
             d.r1 = part[t].r1; d.slots += part[t].slots; d.quots += part[t].quots; d.max_pos = std::max(d.max_pos, part[t].max_pos);
         }
         if (h[0].slots <= max_slots && h[1].slots <= max_slots && h[0].quots <= 0xF0000000ull && h[1].quots <= 0xF0000000ull) {
-            c->subs.push_back(h[0]); c->subs.push_back(h[1]);
+            subs.push_back(h[0]); subs.push_back(h[1]);
             return;
         }
     }
@@ -224,13 +232,13 @@ void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots) {
         uint64_t s, q; uint32_t mp;
         read_cost(r, s, q, mp);
         if (cur.r1 > cur.r0 && (cur.slots + s > max_slots || cur.quots + q > 0xF0000000ull)) {
-            c->subs.push_back(cur);
+            subs.push_back(cur);
             cur = SubBatch{r, r, 0, 0, 0};
         }
         cur.r1 = r + 1; cur.slots += s; cur.quots += q;
         cur.max_pos = std::max(cur.max_pos, mp);
     }
-    if (cur.r1 > cur.r0) c->subs.push_back(cur);
+    if (cur.r1 > cur.r0) subs.push_back(cur);
 }
 
 uint64_t slots_budget(mbl_ctx* c) {
@@ -344,6 +352,7 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, const uint64_t* q_info, bool count_
     ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
     ma.prefix_shift = c->dir.sort_begin_bit;
     ma.dyn_chunks = c->dyn_chunks;
+    ma.cta_threads = c->merge_threads;
     ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
     ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
     ma.items_cap = c->dir.n_tiles + n_query / kItemQueries + 2;
@@ -549,6 +558,7 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         c->d_ham_single = upload(c, t.ham_sum, 64);
         if (const char* e = getenv("MBL_DYN_CHUNKS")) c->dyn_chunks = atoi(e) != 0;
         if (const char* e = getenv("MBL_PIPELINE")) c->pipeline = atoi(e) != 0;
+        if (const char* e = getenv("MBL_MERGE_THREADS")) { int v = atoi(e); if (v == 256 || v == 512) c->merge_threads = v; }
         if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }
         if (const char* e = getenv("MBL_SORT_BIT")) { int v = atoi(e); if (v == 24 || v == 32 || v == 40) c->force_sort_bit = v; }
         if (const char* e = getenv("MBL_TILE_CELLS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->tile_cells = (uint32_t)v; }
@@ -577,6 +587,9 @@ void release_lane(mbl_ctx* c) {
                    &c->sh_key_a, &c->sh_key_b, &c->sh_idx_a, &c->sh_idx_b, &c->sh_begin, &c->send_value, &c->send_qinfo, &c->send_match,
                    &c->sh_tmp})
         b->release();
+    for (Buf* b : {&c->stage_bases1, &c->stage_bases2, &c->stage_off1, &c->stage_off2}) b->release();
+    for (auto& e : c->copy_ev) if (e) cudaEventDestroy(e);
+    if (c->copy_st) cudaStreamDestroy(c->copy_st);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
 }
@@ -593,7 +606,7 @@ mbl_ctx* ensure_shadow(mbl_ctx* c) {
     }
     mbl_ctx* s = c->shadow;
     s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
-    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks;
+    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads;
     s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
     s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded;
     s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed
@@ -793,7 +806,7 @@ int mbl_upload_batch(mbl_ctx* c, const mbl_batch* b) {
             MBL_CUDA(cudaMemcpyAsync(d2, b->bases2, nb2, cudaMemcpyHostToDevice, c->st));
             MBL_CUDA(cudaMemcpyAsync(c->off2.get<uint64_t>(n + 1), b->offsets2, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->st));
         }
-        plan_sub_batches(c, b, slots_budget(c));             // host work overlaps the copies
+        plan_sub_batches(c, b, slots_budget(c), c->subs);    // host work overlaps the copies
         t.stop();
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
@@ -904,6 +917,65 @@ int mbl_classify_batch(mbl_ctx* c, const mbl_batch* b, mbl_read_result* out, int
     int rc = mbl_upload_batch(c, b);
     if (rc != MBL_OK) return rc;
     rc = mbl_classify_resident(c);
+    if (rc != MBL_OK) return rc;
+    return mbl_download_results(c, out, taxcnt_pairs, cap_pairs, used_pairs);
+}
+
+// ---- streaming: the next batch is uploaded while the current one is classified ------------------------------------------
+int mbl_prefetch_batch(mbl_ctx* c, const mbl_batch* b) {
+    if (!c || !b || !b->bases || !b->offsets) return fail(c, MBL_E_BAD_ARG, "null argument");
+    if (b->n_reads >= (1u << 29)) return fail(c, MBL_E_BAD_ARG, "at most 2^29-1 reads per batch (29-bit sequenceID, Kmer.h:13)");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        if (!c->copy_st) {
+            MBL_CUDA(cudaStreamCreateWithFlags(&c->copy_st, cudaStreamNonBlocking));
+            for (auto& e : c->copy_ev) MBL_CUDA(cudaEventCreate(&e));
+        }
+        const uint32_t n = b->n_reads;
+        c->staged_reads = n;
+        c->staged_paired = b->bases2 != nullptr && b->offsets2 != nullptr;
+        MBL_CUDA(cudaEventRecord(c->copy_ev[0], c->copy_st));
+        const uint64_t nb1 = b->offsets[n];
+        MBL_CUDA(cudaMemcpyAsync(c->stage_bases1.get<uint8_t>(nb1 + 64), b->bases, nb1, cudaMemcpyHostToDevice, c->copy_st));
+        MBL_CUDA(cudaMemcpyAsync(c->stage_off1.get<uint64_t>(n + 1), b->offsets, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->copy_st));
+        if (c->staged_paired) {
+            const uint64_t nb2 = b->offsets2[n];
+            MBL_CUDA(cudaMemcpyAsync(c->stage_bases2.get<uint8_t>(nb2 + 64), b->bases2, nb2, cudaMemcpyHostToDevice, c->copy_st));
+            MBL_CUDA(cudaMemcpyAsync(c->stage_off2.get<uint64_t>(n + 1), b->offsets2, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->copy_st));
+        }
+        MBL_CUDA(cudaEventRecord(c->copy_ev[1], c->copy_st));
+        plan_sub_batches(c, b, slots_budget(c), c->staged_subs);
+        c->staged = true;
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
+int mbl_classify_prefetched(mbl_ctx* c, const mbl_batch* next, mbl_read_result* out, int32_t* taxcnt_pairs, size_t cap_pairs,
+                            size_t* used_pairs) {
+    if (!c) return MBL_E_BAD_ARG;
+    if (!c->staged) return fail(c, MBL_E_BAD_ARG, "mbl_prefetch_batch has not been called");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        // the staged batch becomes the resident one; what was resident is free (the previous classify has returned)
+        MBL_CUDA(cudaEventSynchronize(c->copy_ev[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->copy_ev[0], c->copy_ev[1]);
+        std::swap(c->bases1, c->stage_bases1); std::swap(c->bases2, c->stage_bases2);
+        std::swap(c->off1, c->stage_off1); std::swap(c->off2, c->stage_off2);
+        c->subs.swap(c->staged_subs);
+        c->n_reads = c->staged_reads; c->paired = c->staged_paired;
+        c->staged = false;
+        c->stats.ms[MBL_STAGE_H2D] = ms;
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    if (next) {
+        int rc = mbl_prefetch_batch(c, next);
+        if (rc != MBL_OK) return rc;
+    }
+    int rc = mbl_classify_resident(c);
     if (rc != MBL_OK) return rc;
     return mbl_download_results(c, out, taxcnt_pairs, cap_pairs, used_pairs);
 }
@@ -1299,6 +1371,7 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
         ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
         ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
         ma.dyn_chunks = c->dyn_chunks;
+        ma.cta_threads = c->merge_threads;
         ma.prefix_shift = 24;                // the stage API takes fully ordered queries; any coarser grouping is valid too
         ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
         ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);

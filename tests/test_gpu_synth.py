@@ -116,3 +116,26 @@ def test_two_lane_pipeline(name, golden_dir, monkeypatch):
             assert tsv == gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
     finally:
         clf.close()
+
+
+def test_streaming_prefetch_equals_batch_calls():
+    """classify_stream (next batch uploaded while the current one is classified) == one classify_batch per batch."""
+    from metabuli_b200 import Classifier, ClassifyOptions, multigpu
+    sdb, reads, seq_mode = synth_cases.build("multi_pe")
+    n = reads[1].size - 1
+    cuts = [0, n // 5, n // 5, n // 2, n]                      # includes an empty batch
+    batches = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        b1, o1 = multigpu.slice_batch(reads[0], reads[1], lo, hi)
+        b2, o2 = multigpu.slice_batch(reads[2], reads[3], lo, hi)
+        batches.append((b1, o1, b2, o2))
+    clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
+    try:
+        want = [clf.classify_batch(*b) for b in batches]
+        got = list(clf.classify_stream(batches))
+        assert len(got) == len(want)
+        for (r1, p1), (r2, p2) in zip(got, want):
+            assert np.array_equal(r1, r2) and np.array_equal(p1, p2)
+        assert sum(int(r["is_classified"].sum()) for r, _ in got) > 500
+    finally:
+        clf.close()
