@@ -99,27 +99,44 @@ __global__ void match_fullkey_kernel(const mbl_match_rec* __restrict__ m, size_t
     key[i] = k;
     idx[i] = (uint32_t)i;
 }
-// order the run of records that share (seqID, species, frame, pos) by (hamming, dna): the thread that owns
-// the first record of a run insertion-sorts it in place (runs are 1-3 records long in practice)
-__global__ void match_fix_runs_kernel(mbl_match_rec* __restrict__ m, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Fused tail of the single-key path: gather the 24-byte rows through the sorted permutation, order the short runs that
+// share a key by (hamming, dna) and record every read's segment — all decided from the sorted KEYS (coalesced), so the rows
+// are touched exactly once (random read, coalesced write).  Equal keys <=> equal (seqID, species, frame, position); key 0 is
+// a blank row (seqID 0).  The thread of a run's first element places the whole run.
+__global__ void match_gather_fix_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restrict__ idx,
+                                        const uint64_t* __restrict__ key, size_t n, int seq_shift, uint32_t n_reads,
+                                        mbl_match_rec* __restrict__ out, uint64_t* __restrict__ seg_begin, uint64_t* __restrict__ seg_end) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t q = m[i].qinfo;
-    const int32_t sp = m[i].species_id;
-    if (qi_seq(q) == 0) return;                                                   // blank chunk tails
-    if (i > 0 && m[i - 1].qinfo == q && m[i - 1].species_id == sp) return;      // not a run start
-    size_t e = i + 1;
-    while (e < n && m[e].qinfo == q && m[e].species_id == sp) ++e;
-    if (e - i < 2) return;
-    auto less = [](const mbl_match_rec& a, const mbl_match_rec& b) {
-        if (a.hamming != b.hamming) return a.hamming < b.hamming;
-        return a.dna_encoding < b.dna_encoding;
+    const uint64_t k = key[i];
+    const uint64_t kp = i > 0 ? key[i - 1] : ~k, kn = i + 1 < n ? key[i + 1] : ~k;
+    const uint64_t seq = k >> seq_shift;
+    if (seg_begin && seq != 0 && seq <= n_reads) {
+        if ((kp >> seq_shift) != seq) seg_begin[seq - 1] = i;
+        if ((kn >> seq_shift) != seq) seg_end[seq - 1] = i + 1;
+    }
+    auto copy = [&](size_t from, size_t to) {
+        const uint64_t* s = reinterpret_cast<const uint64_t*>(in + from);
+        uint64_t* d = reinterpret_cast<uint64_t*>(out + to);
+        const uint64_t a = s[0], b = s[1], c = s[2];
+        d[0] = a; d[1] = b; d[2] = c;
     };
-    for (size_t a = i + 1; a < e; ++a) {
-        mbl_match_rec v = m[a];
-        size_t b = a;
-        while (b > i && less(v, m[b - 1])) { m[b] = m[b - 1]; --b; }
-        m[b] = v;
+    if (k == 0 || (k != kp && k != kn)) { copy(idx[i], i); return; }      // blank row or a run of one
+    if (k == kp) return;                                                 // placed by the run's first thread
+    size_t e = i + 2;
+    while (e < n && key[e] == k) ++e;
+    // selection by rank: row r of the run goes to i + (number of rows of the run that order before it)
+    for (size_t r = i; r < e; ++r) {
+        const mbl_match_rec x = in[idx[r]];
+        size_t rank = 0;
+        for (size_t q = i; q < e; ++q) {
+            if (q == r) continue;
+            const mbl_match_rec y = in[idx[q]];
+            const bool before = y.hamming != x.hamming ? y.hamming < x.hamming
+                              : (y.dna_encoding != x.dna_encoding ? y.dna_encoding < x.dna_encoding : q < r);
+            rank += before ? 1 : 0;
+        }
+        copy(idx[r], i + rank);
     }
 }
 // seg_begin/seg_end per read from the sorted match list (Classifier.cpp:174-185 MatchBlocks)
@@ -188,10 +205,10 @@ size_t sort_matches_temp_bytes(size_t n) {
     return bytes;
 }
 
-void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
+bool sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
                   int32_t max_taxid, uint32_t max_pos, bool codon_spaced, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a,
-                  uint32_t* idx_b, cudaStream_t st) {
-    if (!n) return;
+                  uint32_t* idx_b, cudaStream_t st, uint64_t* seg_begin, uint64_t* seg_end) {
+    if (!n) return false;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     const int pos_bits = bits_for(max_pos);
     const int sp_bits = bits_for((uint64_t)(uint32_t)max_taxid);
@@ -203,9 +220,13 @@ void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
         cub::DoubleBuffer<uint64_t> k(key_a, key_b);
         cub::DoubleBuffer<uint32_t> v(idx_a, idx_b);
         MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, seq_bits + sp_bits + 3 + pos3_bits, st));
-        match_gather_kernel<<<blocks, 256, 0, st>>>(in, v.Current(), n, out);
-        match_fix_runs_kernel<<<blocks, 256, 0, st>>>(out, n);
-        return;
+        if (seg_begin && seg_end) {
+            MBL_CUDA(cudaMemsetAsync(seg_begin, 0, 8 * (size_t)n_reads, st));
+            MBL_CUDA(cudaMemsetAsync(seg_end, 0, 8 * (size_t)n_reads, st));
+        }
+        match_gather_fix_kernel<<<blocks, 256, 0, st>>>(in, v.Current(), k.Current(), n, sp_bits + 3 + pos3_bits, n_reads, out,
+                                                        seg_begin && seg_end ? seg_begin : nullptr, seg_end);
+        return seg_begin && seg_end;
     }
     match_lowkey_kernel<<<blocks, 256, 0, st>>>(in, n, pos_bits, key_a, idx_a);
     cub::DoubleBuffer<uint64_t> k(key_a, key_b);
@@ -220,6 +241,7 @@ void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
     cub::DoubleBuffer<uint32_t> v2(perm1, v.Alternate());
     MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k2, v2, (long long)n, 0, seq_bits + sp_bits, st));
     match_gather_kernel<<<blocks, 256, 0, st>>>(in, v2.Current(), n, out);
+    return false;
 }
 
 void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, uint64_t* seg_begin, uint64_t* seg_end, cudaStream_t st) {

@@ -58,9 +58,11 @@ void exclusive_sum_u64(void* tmp, size_t tmp_bytes, const uint64_t* in, uint64_t
 void exclusive_sum_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st);
 // full reference order (seqID, species, frame, pos, hamming, dna): sorted copy of `in` in `out`
 size_t sort_matches_temp_bytes(size_t n);
-void sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
+// seg_begin / seg_end (optional, [n_reads]): when given and the single-key path is taken, the per-read segments are written by
+// the same kernel that gathers the rows; returns true in that case (the caller then skips launch_segments)
+bool sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_match_rec* out, size_t n, uint32_t n_reads,
                   int32_t max_taxid, uint32_t max_pos, bool codon_spaced, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a,
-                  uint32_t* idx_b, cudaStream_t st);
+                  uint32_t* idx_b, cudaStream_t st, uint64_t* seg_begin = nullptr, uint64_t* seg_end = nullptr);
 size_t order_reads_temp_bytes(size_t n);
 const uint32_t* order_reads_by_matches(void* tmp, size_t tmp_bytes, const uint64_t* seg_b, const uint64_t* seg_e, uint32_t n,
                                        uint32_t chunk_reads, uint32_t* key_a, uint32_t* key_b, uint32_t* idx_a, uint32_t* idx_b, cudaStream_t st);

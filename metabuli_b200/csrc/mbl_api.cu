@@ -426,9 +426,9 @@ int stage_sort_score(mbl_ctx* c, const SubBatch& sb, uint64_t M) {
         StageTimer t(c, MBL_STAGE_MSORT);
         const size_t sm_bytes = sort_matches_temp_bytes(M);
         void* tmp = c->cub_tmp.get<uint8_t>(std::max(sm_bytes, scan_bytes));
-        sort_matches(tmp, c->cub_tmp.cap, (const mbl_match_rec*)c->m_raw.p, sorted, M, n, c->tax.max_taxid, sb.max_pos, true, key_a, key_b,
-                     idx_a, idx_b, st);
-        launch_segments(sorted, M, n, seg_b, seg_e, st);
+        const bool have_segments = sort_matches(tmp, c->cub_tmp.cap, (const mbl_match_rec*)c->m_raw.p, sorted, M, n, c->tax.max_taxid, sb.max_pos,
+                                                true, key_a, key_b, idx_a, idx_b, st, seg_b, seg_e);
+        if (!have_segments) launch_segments(sorted, M, n, seg_b, seg_e, st);
         c->stats.kernel_launches += M ? 4 : 0;
         t.stop();
     }

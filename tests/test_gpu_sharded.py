@@ -66,3 +66,39 @@ def test_shard_of_one_is_the_whole_index():
     r2, p2 = clf.classify_batch(reads[0], reads[1])
     clf.close()
     assert np.array_equal(res, r2) and np.array_equal(pairs, p2)
+
+
+@pytest.mark.parametrize("transport", ["peer", "collective"])
+def test_rank_without_reads_and_empty_shard(transport):
+    """3 ranks, rank 1 brings no reads; 5 shards over a 2-group index leave trailing shards empty (covered by plan tests) —
+    here: uneven read counts, one rank idle on the read side but still serving its shard."""
+    from local_exchange import LocalWorld
+    from metabuli_b200 import ClassifyOptions, multigpu, sharded
+    sdb, reads, seq_mode = synth_cases.build("multi_se")
+    world = 3
+    shards = sharded.plan_shards(sdb.database, world)
+    want_res, want_pairs = _expected(sdb, reads, seq_mode)
+    n = reads[1].size - 1
+    cuts = [0, n // 3, n // 3, n]
+    lw = LocalWorld(world)
+    ok, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            sc = sharded.ShardedClassifier(sdb.database, ClassifyOptions(seq_mode=seq_mode), shards, rank)
+            lo, hi = cuts[rank], cuts[rank + 1]
+            b1, o1 = multigpu.slice_batch(reads[0], reads[1], lo, hi)
+            res, pairs = sharded.classify_index_sharded(sc, lw.exchange(rank), b1, o1, transport=transport)
+            ok[rank] = res.size == hi - lo and _same(res, pairs, want_res, want_pairs, lo, hi)
+            sc.close()
+        except Exception as e:
+            errors.append(e)
+            lw.barrier.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    assert not errors, errors
+    assert ok == [True] * world

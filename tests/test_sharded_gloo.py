@@ -85,8 +85,8 @@ def test_world_size_2_gloo_index_sharded():
     assert sum(g[2] for g in got) > 1000
 
 
-@pytest.mark.parametrize("name,world", [("multi_se", 3), ("ragged_se", 4)])
-def test_in_process_ranks(name, world):
+@pytest.mark.parametrize("name,world,idle", [("multi_se", 3, None), ("ragged_se", 4, None), ("multi_se", 3, 1)])
+def test_in_process_ranks(name, world, idle):
     import shard_oracle
     import synth_cases
     from local_exchange import LocalWorld
@@ -101,9 +101,13 @@ def test_in_process_ranks(name, world):
     def run(rank):
         phases = shard_oracle.OraclePhases(sdb, shards, rank, seq_mode)
         lo, hi = multigpu.shard_range(n, rank, world)
+        if idle is not None:                        # one rank brings no reads but still serves its shard
+            cuts = [0] + [n * (r + 1) // world for r in range(world)]
+            cuts[idle + 1] = cuts[idle]
+            lo, hi = cuts[rank], cuts[rank + 1] if rank + 1 < world else n
         b1, o1 = multigpu.slice_batch(reads[0], reads[1], lo, hi)
         res, pairs = sharded.classify_index_sharded(phases, lw.exchange(rank), b1, o1)
-        ok[rank] = _same(res, pairs, want_res, want_pairs, lo, hi)
+        ok[rank] = res.size == hi - lo and _same(res, pairs, want_res, want_pairs, lo, hi)
 
     th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
     for t in th:
