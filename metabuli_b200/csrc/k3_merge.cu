@@ -441,12 +441,7 @@ merge_kernel(MergeArgs a) {
             const uint32_t excl = incl - n;
             my_own[lane] = 255u;
             __syncwarp();
-            cp_async_wait_all();                                                    // qinfo words
-            __syncwarp();
-            // sweep E: a candidate with the query's own DNA part has Hamming sum 0 and survives whatever else is in the group;
-            // it also pins the hit's threshold min(2*min, 7) to 0, so nothing but the identical candidates survives.  One pass
-            // of plain compares therefore settles every hit that has an identical candidate (94 % of the hits in the benchmark
-            // workload) — no table lookups, no second sweep.
+            // sweep 1: per-hit minimum (an identical DNA part is the only way to distance 0)
             for (uint32_t pb = 0; pb < total; pb += 32) {
                 const uint32_t p = pb + lane;
                 const bool pv = p < total;
@@ -456,37 +451,31 @@ merge_kernel(MergeArgs a) {
                 o &= 31u;
                 const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
                 const uint32_t oq = __shfl_sync(kFull, qd, o);
-                uint32_t td = 0;
-                bool eq = false;
+                if (pv) {
+                    const uint32_t td = (uint32_t)vals[j] & 0xFFFFFFu;
+                    const uint32_t sum = td == oq ? 0u : ham_sum(ham_lookup(s_ham, oq, td));
+                    atomicMin(&my_own[o], sum);
+                }
+            }
+            cp_async_wait_all();                                                    // qinfo words
+            __syncwarp();
+            // sweep 2: survivors
+            for (uint32_t pb = 0; pb < total; pb += 32) {
+                const uint32_t p = pb + lane;
+                const bool pv = p < total;
+                uint32_t o = 0;
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1) { const uint32_t t = __shfl_sync(kFull, incl, (o + st - 1) & 31); if (t <= p) o += st; }
+                o &= 31u;
+                const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
+                const uint32_t oq = __shfl_sync(kFull, qd, o);
+                uint32_t td = 0, sum = 255u;
+                HamQuad hq{0u, 0u, 0u, 0u};
                 if (pv) {
                     td = (uint32_t)vals[j] & 0xFFFFFFu;
-                    eq = td == oq;
-                    if (eq) my_own[o] = 0u;
+                    if (td == oq) sum = 0u; else { hq = ham_lookup(s_ham, oq, td); sum = ham_sum(hq); }
                 }
-                emit(eq, o, j, oq, td, 0u, HamQuad{0u, 0u, 0u, 0u});
-            }
-            __syncwarp();
-            // hits without an identical candidate: the warp takes them one at a time, a lane per candidate — Hamming sums
-            // from the two-codon table, warp-wide minimum, then the candidates with sum <= min(2*min, 7) (KmerMatcher.cpp:1136)
-            uint32_t need = __ballot_sync(kFull, valid && n > 0 && my_own[lane] != 0u);
-            while (need) {
-                const uint32_t h = (uint32_t)__ffs(need) - 1u;
-                need &= need - 1u;
-                const uint32_t hg = __shfl_sync(kFull, g0, h), hn = __shfl_sync(kFull, n, h), hq_dna = __shfl_sync(kFull, qd, h);
-                uint32_t best = 255u;
-                for (uint32_t base = 0; base < hn; base += 32) {
-                    uint32_t sum = 255u;
-                    if (base + lane < hn) sum = ham_sum(ham_lookup(s_ham, hq_dna, (uint32_t)vals[hg + base + lane] & 0xFFFFFFu));
-                    best = min(best, __reduce_min_sync(kFull, sum));
-                }
-                const uint32_t limit = min(best * 2u, 7u);
-                for (uint32_t base = 0; base < hn; base += 32) {
-                    const bool pv = base + lane < hn;
-                    uint32_t td = 0, sum = 255u;
-                    HamQuad hq{0u, 0u, 0u, 0u};
-                    if (pv) { td = (uint32_t)vals[hg + base + lane] & 0xFFFFFFu; hq = ham_lookup(s_ham, hq_dna, td); sum = ham_sum(hq); }
-                    emit(pv && sum <= limit, h, hg + base + lane, hq_dna, td, sum, hq);
-                }
+                emit(pv && sum <= min(my_own[o] * 2u, 7u), o, j, oq, td, sum, hq);      // KmerMatcher.cpp:1136
             }
         };
 
