@@ -226,7 +226,7 @@ int  mbl_host_unregister(void* ptr);
 typedef struct {
     float    ms[MBL_STAGE_COUNT];     /* CUDA-event time of each stage in the last classify call       */
     float    merge_kernel_ms;         /* the merge kernel launches alone, CUDA events on their stream   */
-    uint64_t n_query_kmers;           /* non-blank                                                      */
+    uint64_t n_query_kmers;           /* non-blank metamers extracted                                   */
     uint64_t n_matches;
     uint64_t merge_bytes;             /* algorithmic bytes of the merge launches: S_diff+4K+16Nq+24Nm   */
     uint32_t merge_launches;
@@ -235,6 +235,7 @@ typedef struct {
     uint32_t sub_batches;
     float    ms_bucket_kmers;         /* sharded mode: bucketing + packing of the metamers / of the matches    */
     float    ms_bucket_matches;
+    uint64_t n_merge_queries;         /* metamers that reached the sort and the merge (after the amino-acid presence filter) */
 } mbl_stats;
 int  mbl_get_stats(const mbl_ctx* ctx, mbl_stats* out);
 

@@ -65,14 +65,24 @@ __global__ void read_meta_kernel(const uint64_t* __restrict__ off1, const uint64
     quot_cnt[r] = ql + 3 > 0 ? (uint32_t)((ql + 3) / 3 + 1) : 1u;
 }
 
-template <int FORMAT>
+// probe of the amino-acid presence filter (mbl_common.cuh): both bits live in one 32-byte sector
+__device__ __forceinline__ bool aa_filter_pass(const AaFilter& f, uint64_t value) {
+    const uint64_t h = aa_filter_hash(value);
+    const uint32_t* blk = f.words + (size_t)aa_filter_block(h, f.n_blocks) * 8;
+    const uint32_t b1 = aa_filter_bit1(h), b2 = aa_filter_bit2(h);
+    const uint32_t w1 = __ldg(blk + (b1 >> 5)), w2 = __ldg(blk + (b2 >> 5));
+    return ((w1 >> (b1 & 31)) & (w2 >> (b2 & 31)) & 1u) != 0u;
+}
+
+template <int FORMAT, bool FILTER>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ off1,
                const uint8_t* __restrict__ bases2, const uint64_t* __restrict__ off2, uint32_t n_reads,
                const int32_t* __restrict__ cov1, const int32_t* __restrict__ w1, const int32_t* __restrict__ w2,
                const uint64_t* __restrict__ slot_off, const uint8_t* __restrict__ g_base_code,
                const uint8_t* __restrict__ g_codon, uint64_t* __restrict__ value, uint64_t* __restrict__ qinfo,
-               uint32_t* __restrict__ slot_idx, unsigned long long* __restrict__ n_valid) {
+               uint32_t* __restrict__ slot_idx, unsigned long long* __restrict__ n_valid, const AaFilter filter,
+               unsigned long long* __restrict__ out_cursor, const uint64_t out_cap) {
     __shared__ uint8_t s_code[256];
     __shared__ uint8_t s_codon[512];
     __shared__ WarpScratch s_warp[kWarpsPerBlock];
@@ -83,6 +93,10 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = s_warp[warp];
     unsigned valid_cnt = 0;
+    // FILTER: survivors are packed from slot 0 upwards; a warp owns a chunk of kExtractChunk slots at a time
+    uint64_t chunk_base = 0;
+    uint32_t chunk_used = kExtractChunk;
+    unsigned pass_cnt = 0;
     for (uint32_t r = blockIdx.x * kWarpsPerBlock + warp; r < n_reads; r += gridDim.x * kWarpsPerBlock) {
         const int wa = w1[r], wb = w2[r];
         if (wa + wb == 0) continue;
@@ -116,28 +130,57 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
                 }
                 __syncwarp();
                 // 3. one forward and one reverse metamer per leftmost position
-                for (int i = lane; i < cnt; i += 32) {
-                    const int x = x0 + i;
+                for (int i0 = 0; i0 < cnt; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool active = i < cnt;
+                    if (!FILTER && !active) continue;
+                    const int x = x0 + (active ? i : 0);
                     uint64_t aaF = 0, aaR = 0;
                     uint32_t dnaF = 0, dnaR = 0;
                     unsigned badF = 0, badR = 0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         unsigned f, rv;
-                        if (FORMAT == 2) { f = ws.fwd[i + 3 * k]; rv = ws.rev[i + 21 - 3 * k]; }
-                        else             { f = ws.fwd[i + 21 - 3 * k]; rv = ws.rev[i + 3 * k]; }
+                        const int ii = active ? i : 0;
+                        if (FORMAT == 2) { f = ws.fwd[ii + 3 * k]; rv = ws.rev[ii + 21 - 3 * k]; }
+                        else             { f = ws.fwd[ii + 21 - 3 * k]; rv = ws.rev[ii + 3 * k]; }
                         badF |= (f == 0xFFu); badR |= (rv == 0xFFu);
                         if (FORMAT == 2) { aaF = (aaF << 5) | (f >> 3); aaR = (aaR << 5) | (rv >> 3); }
                         else             { aaF = aaF * 21 + (f >> 3); aaR = aaR * 21 + (rv >> 3); }
                         dnaF = (dnaF << 3) | (f & 7); dnaR = (dnaR << 3) | (rv & 7);
                     }
-                    const bool okF = !badF, okR = !badR;
+                    const bool okF = active && !badF, okR = active && !badR;
                     const uint32_t res = (uint32_t)(x % 3);
                     const uint32_t frameF = res;
                     const uint32_t frameR = 3u + (uint32_t)((lmod - (int)res + 3) % 3);
                     const uint64_t sF = slot_base + (uint64_t)x;
                     const uint64_t sR = slot_base + (uint64_t)npos + (uint64_t)x;
                     const uint32_t pos = (uint32_t)x + pos_off;
+                    if (FILTER) {
+                        const uint64_t vF = (aaF << 24) | (dnaF & 0xFFFFFFu), vR = (aaR << 24) | (dnaR & 0xFFFFFFu);
+                        const bool pF = okF && aa_filter_pass(filter, vF), pR = okR && aa_filter_pass(filter, vR);
+                        const uint32_t bF = __ballot_sync(0xffffffffu, pF), bR = __ballot_sync(0xffffffffu, pR);
+                        const uint32_t nF = __popc(bF), nR = __popc(bR), need = nF + nR;
+                        valid_cnt += (unsigned)okF + (unsigned)okR;
+                        if (need) {
+                            if (chunk_used + need > kExtractChunk) {          // blank out the rest of the old chunk, take a new one
+                                if (chunk_base + kExtractChunk <= out_cap)
+                                    for (uint32_t w = chunk_used + lane; w < kExtractChunk; w += 32) { value[chunk_base + w] = kBlank; qinfo[chunk_base + w] = 0ull; slot_idx[chunk_base + w] = (uint32_t)(chunk_base + w); }
+                                unsigned long long nb = 0;
+                                if (lane == 0) nb = atomicAdd(out_cursor, (unsigned long long)kExtractChunk);
+                                chunk_base = __shfl_sync(0xffffffffu, nb, 0);
+                                chunk_used = 0;
+                            }
+                            const uint32_t lt = (1u << lane) - 1u;
+                            const bool room = chunk_base + kExtractChunk <= out_cap;   // else: capacity guess too small, the host redoes K1
+                            if (!room) { chunk_used += need; continue; }
+                            if (pF) { const uint64_t s = chunk_base + chunk_used + __popc(bF & lt); value[s] = vF; qinfo[s] = pack_qinfo(r + 1, pos, frameF); slot_idx[s] = (uint32_t)s; }
+                            if (pR) { const uint64_t s = chunk_base + chunk_used + nF + __popc(bR & lt); value[s] = vR; qinfo[s] = pack_qinfo(r + 1, pos, frameR); slot_idx[s] = (uint32_t)s; }
+                            chunk_used += need;
+                            pass_cnt += (lane == 0) ? need : 0u;
+                        }
+                        continue;
+                    }
                     value[sF] = okF ? ((aaF << 24) | (dnaF & 0xFFFFFFu)) : kBlank;
                     qinfo[sF] = okF ? pack_qinfo(r + 1, pos, frameF) : 0ull;
                     value[sR] = okR ? ((aaR << 24) | (dnaR & 0xFFFFFFu)) : kBlank;
@@ -151,6 +194,14 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
         }
     }
     for (int o = 16; o > 0; o >>= 1) valid_cnt += __shfl_xor_sync(0xffffffffu, valid_cnt, o);
+    if (FILTER) {
+        // n_valid[0] = metamers that passed the filter (what the sort and the merge see), n_valid[5] = valid metamers extracted
+        if (chunk_used < kExtractChunk && chunk_used > 0 && chunk_base + kExtractChunk <= out_cap)
+            for (uint32_t w = chunk_used + lane; w < kExtractChunk; w += 32) { value[chunk_base + w] = kBlank; qinfo[chunk_base + w] = 0ull; slot_idx[chunk_base + w] = (uint32_t)(chunk_base + w); }
+        if (lane == 0 && pass_cnt) atomicAdd(n_valid, (unsigned long long)pass_cnt);
+        if (lane == 0 && valid_cnt) atomicAdd(n_valid + 5, (unsigned long long)valid_cnt);
+        return;
+    }
     if (lane == 0 && valid_cnt) atomicAdd(n_valid, (unsigned long long)valid_cnt);
 }
 
@@ -160,20 +211,28 @@ void launch_read_meta(const uint64_t* off1, const uint64_t* off2, uint32_t n_rea
     read_meta_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(off1, off2, n_reads, cov1, cov2, w1, w2, slots, quot_cnt);
 }
 
+uint64_t extract_filtered_capacity(uint64_t slots, int sm_count) {
+    // every warp can leave one chunk partly used, and a chunk switch can strand up to 63 slots
+    const uint64_t warps = (uint64_t)sm_count * 64u * kWarpsPerBlock;
+    return slots + slots / 7 + warps * kExtractChunk + 4096;
+}
+
 void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2,
                     uint32_t n_reads, const int32_t* cov1, const int32_t* w1, const int32_t* w2, const uint64_t* slot_off,
                     const uint8_t* base_code, const uint8_t* codon, uint64_t* value, uint64_t* qinfo, uint32_t* slot_idx,
-                    unsigned long long* n_valid, int sm_count, cudaStream_t st) {
+                    unsigned long long* n_valid, int sm_count, cudaStream_t st, AaFilter filter, unsigned long long* out_cursor,
+                    uint64_t out_cap) {
     if (!n_reads) return;
     unsigned blocks = (n_reads + kWarpsPerBlock - 1) / kWarpsPerBlock;
     unsigned cap = (unsigned)sm_count * 64u;          // grid-stride beyond a few waves
     if (blocks > cap) blocks = cap;
-    if (format == 2)
-        extract_kernel<2><<<blocks, kWarpsPerBlock * 32, 0, st>>>(bases1, off1, bases2, off2, n_reads, cov1, w1, w2,
-                                                                 slot_off, base_code, codon, value, qinfo, slot_idx, n_valid);
-    else
-        extract_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, st>>>(bases1, off1, bases2, off2, n_reads, cov1, w1, w2,
-                                                                 slot_off, base_code, codon, value, qinfo, slot_idx, n_valid);
+    const bool filtered = filter.words != nullptr && out_cursor != nullptr && slot_idx != nullptr;
+#define MBL_LAUNCH_EXTRACT(F, B)                                                                                             \
+    extract_kernel<F, B><<<blocks, kWarpsPerBlock * 32, 0, st>>>(bases1, off1, bases2, off2, n_reads, cov1, w1, w2, slot_off, \
+                                                                 base_code, codon, value, qinfo, slot_idx, n_valid, filter, out_cursor, out_cap)
+    if (format == 2) { if (filtered) MBL_LAUNCH_EXTRACT(2, true); else MBL_LAUNCH_EXTRACT(2, false); }
+    else             { if (filtered) MBL_LAUNCH_EXTRACT(1, true); else MBL_LAUNCH_EXTRACT(1, false); }
+#undef MBL_LAUNCH_EXTRACT
 }
 
 }  // namespace mbl

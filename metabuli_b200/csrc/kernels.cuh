@@ -20,6 +20,8 @@ struct TileDirectory {
     // see tile_sort_bit in k3_index.cu) — the merge only needs queries grouped per tile, not fully ordered
     int sort_begin_bit = 24;
     uint64_t n_kmers_decoded = 0;   // number of end flags in the stream (must equal the info count)
+    uint32_t* filter = nullptr;     // amino-acid presence filter over every k-mer of the stream (AaFilter), or null
+    uint32_t filter_blocks = 0;
 };
 
 struct DeviceTaxonomy {             // reference arrays as stored in taxonomyDB
@@ -44,7 +46,13 @@ void launch_read_meta(const uint64_t* off1, const uint64_t* off2, uint32_t n_rea
 void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2,
                     uint32_t n_reads, const int32_t* cov1, const int32_t* w1, const int32_t* w2, const uint64_t* slot_off,
                     const uint8_t* base_code, const uint8_t* codon, uint64_t* value, uint64_t* qinfo, uint32_t* slot_idx,
-                    unsigned long long* n_valid, int sm_count, cudaStream_t st);
+                    unsigned long long* n_valid, int sm_count, cudaStream_t st, AaFilter filter = AaFilter(),
+                    unsigned long long* out_cursor = nullptr, uint64_t out_cap = 0);
+// filtered extraction packs the surviving metamers from slot 0 upwards in per-warp chunks of kExtractChunk slots (unused chunk
+// tails are blank) and never writes at or beyond out_cap (a cursor beyond out_cap tells the host to redo it with more room);
+// extract_filtered_capacity = the slots it can need when `pass` of the `slots` reserved slots survive
+constexpr uint32_t kExtractChunk = 512;
+uint64_t extract_filtered_capacity(uint64_t pass, int sm_count);
 
 // K2 / K4 (radix sorts) and scans
 size_t sort_kmers_temp_bytes(size_t n);
@@ -70,8 +78,10 @@ void launch_seq_bounds(const mbl_match_rec* sorted, size_t n, uint32_t chunk_rea
 void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, uint64_t* seg_begin, uint64_t* seg_end, cudaStream_t st);
 
 // K3 directory (load time)
+// filter_bits_per_kmer > 0: also build the amino-acid presence filter (about that many bits per k-mer of the stream)
 void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
-                          cudaStream_t st, TileDirectory& dir, uint64_t base_value = 0, bool holds_db_tail = true);
+                          cudaStream_t st, TileDirectory& dir, uint64_t base_value = 0, bool holds_db_tail = true,
+                          int filter_bits_per_kmer = 0);
 void free_tile_directory(TileDirectory& dir);
 
 // K3 merge (per batch)

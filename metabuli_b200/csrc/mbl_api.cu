@@ -51,6 +51,8 @@ struct mbl_ctx {
     uint8_t* d_ham_single = nullptr;
     uint32_t tile_cells = 2;            // MBL_TILE_CELLS (measured best on the 8 GiB benchmark index: 3 CTAs per SM)
     int dyn_chunks = 0;                 // MBL_DYN_CHUNKS (measured: no gain over fixed striding)
+    int filter_bits = 16;               // MBL_FILTER_BITS: bits per index k-mer of the amino-acid presence filter, 0 = no filter
+    uint64_t arena_S8 = 0;              // slot stride of the phase-1 arena layout (set by whoever fills it)
     int merge_threads = 256;            // MBL_MERGE_THREADS: 256 (3 CTAs per SM) or 512 (2 CTAs per SM, 32 warps)
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // index
@@ -110,6 +112,7 @@ struct mbl_ctx {
     int pipeline = 0;                   // MBL_PIPELINE=1 switches the second lane on (measured slower: the lanes contend and the index is streamed twice)
     uint32_t pipeline_min_reads = 1u << 21;   // MBL_PIPELINE_MIN_READS: smaller batches stay on one lane
     double match_ratio = 0.0;   // matches per slot seen so far (sizes the match buffer)
+    double pass_ratio = 0.0;    // slots the packed (filtered) extraction used per reserved slot, seen so far
     mbl_stats stats{};
 };
 
@@ -253,7 +256,9 @@ uint64_t slots_budget(mbl_ctx* c) {
     // per slot: 32 B keys+payloads (arena; reused by the match sort: 48 B per match) + 24 B per raw match + ~4 B per-read tables;
     // fixed: scoring scratch of one chunk + results
     const double r = std::max(0.5, c->match_ratio * 1.3);
-    const double per_slot = std::max(32.0, 48.0 * r) + 24.0 * r + 4.0;
+    // with the presence filter the phase-1 arena only holds the survivors (the guess of run_sub_batch)
+    const double kept = c->dir.filter ? std::min(1.0, c->pass_ratio > 0 ? 1.3 * c->pass_ratio + 0.05 : 0.45) : 1.0;
+    const double per_slot = std::max(32.0 * kept, 48.0 * r) + 24.0 * r + 4.0;
     double budget = 0.88 * (double)(free_b + held) - 10.0e9;
     uint64_t s = budget > 0 ? (uint64_t)(budget / per_slot) : 0;
     s = std::min<uint64_t>(s, (uint64_t)(3.9e9 / r));            // 32-bit match permutation
@@ -266,11 +271,15 @@ uint64_t slots_budget(mbl_ctx* c) {
 // (the index-sharded mode runs the same stages with an exchange between them, see mbl_shard_* below)
 
 // K1: per-read metadata + metamer extraction into the phase-1 arena (value A | value B | qinfo | slot idx A | slot idx B)
-void stage_extract(mbl_ctx* c, const SubBatch& sb) {
+// use_filter: metamers whose amino-acid part is not in the index are dropped and the survivors packed from slot 0 (K1 + filter)
+// filter_pass: expected number of survivors (sizes the packed buffers; a too small guess is detected and redone by the caller)
+void stage_extract(mbl_ctx* c, const SubBatch& sb, bool use_filter, uint64_t filter_pass = 0) {
     cudaStream_t st = c->st;
     const uint32_t n = sb.r1 - sb.r0;
     const uint64_t S = sb.slots;
-    const uint64_t S8 = (S + 31) & ~31ull;
+    use_filter = use_filter && c->dir.filter != nullptr;
+    const uint64_t S8 = ((use_filter ? extract_filtered_capacity(std::min(filter_pass, S), c->sm_count) : S) + 31) & ~31ull;
+    c->arena_S8 = S8;
     const uint8_t* bases1 = (const uint8_t*)c->bases1.p;
     const uint8_t* bases2 = c->paired ? (const uint8_t*)c->bases2.p : nullptr;
     const uint64_t* off1 = (const uint64_t*)c->off1.p + sb.r0;
@@ -294,8 +303,10 @@ void stage_extract(mbl_ctx* c, const SubBatch& sb) {
         uint64_t* ar = c->arena.get<uint64_t>(4 * S8 + 64);
         uint64_t *va = ar, *qa = ar + 2 * S8;
         uint32_t* ia = reinterpret_cast<uint32_t*>(ar + 3 * S8);
+        AaFilter flt;
+        if (use_filter) { flt.words = c->dir.filter; flt.n_blocks = c->dir.filter_blocks; }
         launch_extract(c->cfg.kmer_format, bases1, off1, bases2, off2, n, cov1, w1, w2, slot_off, c->d_base_code, c->d_codon,
-                       va, qa, ia, counters, c->sm_count, st);
+                       va, qa, ia, counters, c->sm_count, st, flt, counters + 4, S8);
         c->stats.kernel_launches += 2;
         t.stop();
     }
@@ -303,9 +314,10 @@ void stage_extract(mbl_ctx* c, const SubBatch& sb) {
 
 // K2 + K3: sort the S slots in the phase-1 arena (keys in `value A`, slot indices in `slot idx A`) and merge them against the
 // resident index; q_info is the array the slot indices point into.  -> rows written to m_raw (blank tails included), matches
-int stage_sort_merge(mbl_ctx* c, uint64_t S, const uint64_t* q_info, bool count_valid_on_device, uint64_t* reserved_out, uint64_t* n_match_out) {
+int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, const uint64_t* q_info, bool count_valid_on_device, uint64_t* reserved_out,
+                     uint64_t* n_match_out) {
     cudaStream_t st = c->st;
-    const uint64_t S8 = (S + 31) & ~31ull;
+    const uint64_t S8 = c->arena_S8;
     const size_t scan_bytes = scan_temp_bytes(c->dir.n_tiles + 2);
     const size_t sortk_bytes = sort_kmers_temp_bytes(S);
     unsigned long long* counters = c->counters.get<unsigned long long>(8);
@@ -331,10 +343,10 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, const uint64_t* q_info, bool count_
         MBL_CUDA(cudaStreamSynchronize(st));
         n_query = h_cnt[0];
     }
-    c->stats.n_query_kmers += n_query;
+    c->stats.n_merge_queries += n_query;
 
     // ---- K3 ------------------------------------------------------------------------------------------
-    uint64_t cap = (uint64_t)((double)S * std::max(c->match_ratio * 1.25, 0.125 * (double)std::max(1, c->cfg.match_per_kmer))) + out_slack(c);
+    uint64_t cap = (uint64_t)((double)cap_basis * std::max(c->match_ratio * 1.25, 0.125 * (double)std::max(1, c->cfg.match_per_kmer))) + out_slack(c);
     uint64_t reserved = 0, n_match = 0;
     MergeArgs ma{};
     ma.diff = c->d_diff; ma.info = c->d_info;
@@ -400,7 +412,7 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, const uint64_t* q_info, bool count_
     }
     c->stats.n_matches += n_match;
     c->stats.merge_bytes += 2 * c->n_u16 + 4 * c->n_kmers + 16 * n_query + 24 * n_match;
-    if (S) c->match_ratio = std::max(c->match_ratio, (double)reserved / (double)S);
+    if (cap_basis) c->match_ratio = std::max(c->match_ratio, (double)reserved / (double)cap_basis);
     if (reserved >= (1ull << 32)) return fail(c, MBL_E_UNSUPPORTED, "more than 2^32 matches in one sub-batch");
     *reserved_out = reserved; *n_match_out = n_match;
     return MBL_OK;
@@ -519,10 +531,32 @@ int stage_sort_score(mbl_ctx* c, const SubBatch& sb, uint64_t M) {
 }
 
 int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
-    stage_extract(c, sb);
-    const uint64_t S8 = (sb.slots + 31) & ~31ull;
+    const bool filtered = c->dir.filter != nullptr;
+    uint64_t n_sort = sb.slots;
+    unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+    if (filtered) {
+        // the packed buffers are sized from the survivor fraction seen so far (40 % before the first batch); K1 never writes
+        // beyond them, and a cursor past the end means the guess was too small: redo with room for every slot
+        uint64_t guess = (uint64_t)((double)sb.slots * std::min(1.0, c->pass_ratio > 0 ? 1.3 * c->pass_ratio + 0.02 : 0.4)) + 4096;
+        for (int attempt = 0;; ++attempt) {
+            stage_extract(c, sb, true, guess);
+            MBL_CUDA(cudaMemcpyAsync(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost, c->st));
+            MBL_CUDA(cudaStreamSynchronize(c->st));
+            if (h[4] <= c->arena_S8 || attempt > 0) break;
+            c->stats.overflow_retries += 1;
+            guess = sb.slots;
+        }
+        if (h[4] > c->arena_S8) return fail(c, MBL_E_CUDA, "internal: packed extraction overflow");
+        n_sort = h[4];                              // slots handed out by the packed extraction
+        c->stats.n_query_kmers += h[5];             // valid metamers before the filter
+        if (sb.slots) c->pass_ratio = std::max(c->pass_ratio, (double)h[4] / (double)sb.slots);
+    } else {
+        stage_extract(c, sb, false);
+    }
     uint64_t reserved = 0, n_match = 0;
-    int rc = stage_sort_merge(c, sb.slots, (const uint64_t*)c->arena.p + 2 * S8, true, &reserved, &n_match);
+    const uint64_t nq_before = c->stats.n_merge_queries;
+    int rc = stage_sort_merge(c, n_sort, sb.slots, (const uint64_t*)c->arena.p + 2 * c->arena_S8, true, &reserved, &n_match);
+    if (!filtered) c->stats.n_query_kmers += c->stats.n_merge_queries - nq_before;
     if (rc != MBL_OK) return rc;
     return stage_sort_score(c, sb, reserved);
 }
@@ -558,6 +592,7 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         c->d_ham_single = upload(c, t.ham_sum, 64);
         if (const char* e = getenv("MBL_DYN_CHUNKS")) c->dyn_chunks = atoi(e) != 0;
         if (const char* e = getenv("MBL_PIPELINE")) c->pipeline = atoi(e) != 0;
+        if (const char* e = getenv("MBL_FILTER_BITS")) { int v = atoi(e); if (v >= 0 && v <= 64) c->filter_bits = v; }
         if (const char* e = getenv("MBL_MERGE_THREADS")) { int v = atoi(e); if (v == 256 || v == 512) c->merge_threads = v; }
         if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }
         if (const char* e = getenv("MBL_SORT_BIT")) { int v = atoi(e); if (v == 24 || v == 32 || v == 40) c->force_sort_bit = v; }
@@ -606,12 +641,12 @@ mbl_ctx* ensure_shadow(mbl_ctx* c) {
     }
     mbl_ctx* s = c->shadow;
     s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
-    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads;
+    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->filter_bits = c->filter_bits;
     s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
     s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded;
     s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed
     s->n_reads = c->n_reads; s->paired = c->paired;
-    s->match_ratio = c->match_ratio;
+    s->match_ratio = c->match_ratio; s->pass_ratio = c->pass_ratio;
     s->n_pairs = 0;
     s->stats = mbl_stats{};
     return s;
@@ -662,7 +697,9 @@ int load_db_range(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx, const mb
         c->tax.taxid2species = up(tx->taxid2species, T);
         c->tax.max_taxid = tx->max_taxid; c->tax.M_k = tx->M_k; c->tax.eukaryota = tx->eukaryota; c->tax.max_nodes = (uint32_t)N;
         MBL_CUDA(cudaStreamSynchronize(c->st));
-        build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->tile_cells, c->st, c->dir, sh.base_value, sh.holds_db_tail != 0);
+        // the presence filter must cover every k-mer a query could match, so a shard (which sees only its own range) builds none
+        build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->tile_cells, c->st, c->dir, sh.base_value, sh.holds_db_tail != 0,
+                             is_shard ? 0 : c->filter_bits);
         if (c->force_sort_bit) c->dir.sort_begin_bit = c->force_sort_bit;
         // the k-mer count implied by the end flags must agree with the info file
         if (c->dir.n_kmers_decoded != c->n_kmers) {
@@ -672,7 +709,8 @@ int load_db_range(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx, const mb
             free_db(c);
             return fail(c, MBL_E_BAD_DB, msg);
         }
-        c->db_bytes = 2 * c->n_u16 + 4 * c->n_kmers + sizeof(Tile) * c->dir.n_tiles + 16 * c->dir.n_cells + 8 * c->dir.n_jumbo_kmers;
+        c->db_bytes = 2 * c->n_u16 + 4 * c->n_kmers + sizeof(Tile) * c->dir.n_tiles + 16 * c->dir.n_cells + 8 * c->dir.n_jumbo_kmers +
+                      32 * (size_t)c->dir.filter_blocks;
         c->db_loaded = true;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
@@ -866,10 +904,12 @@ int mbl_classify_resident(mbl_ctx* c) {
             // per-stage times of the two lanes add up (they overlap in wall-clock time); counts add up
             for (int i = 0; i < 7; ++i) if (i != MBL_STAGE_H2D) c->stats.ms[i] += s->stats.ms[i];
             c->stats.merge_kernel_ms += s->stats.merge_kernel_ms; c->stats.n_query_kmers += s->stats.n_query_kmers;
+            c->stats.n_merge_queries += s->stats.n_merge_queries;
             c->stats.n_matches += s->stats.n_matches; c->stats.merge_bytes += s->stats.merge_bytes;
             c->stats.merge_launches += s->stats.merge_launches; c->stats.kernel_launches += s->stats.kernel_launches;
             c->stats.overflow_retries += s->stats.overflow_retries;
             c->match_ratio = std::max(c->match_ratio, s->match_ratio);
+            c->pass_ratio = std::max(c->pass_ratio, s->pass_ratio);
             // the batch's pair array: the sub-batches' pairs in sub-batch order
             uint64_t total = 0;
             for (const SubDone& d : done) total += d.count;
@@ -1007,7 +1047,7 @@ int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_
         for (uint32_t s = 0; s <= n_shards; ++s) c->sh_begin_h[s] = 0;
         if (c->subs.empty()) return MBL_OK;
         const SubBatch sb = c->subs[0];
-        stage_extract(c, sb);
+        stage_extract(c, sb, false);
         const uint64_t S = sb.slots;
         const uint64_t* va = (const uint64_t*)c->arena.p;
         const float ms_k1 = c->stats.ms[MBL_STAGE_EXTRACT];
@@ -1075,7 +1115,9 @@ int mbl_shard_match(mbl_ctx* c, const uint64_t* d_value, const uint64_t* d_qinfo
         if (n) MBL_CUDA(cudaMemcpyAsync(ar, d_value, 8 * n, cudaMemcpyDeviceToDevice, st));
         launch_iota(ia, n, st);
         uint64_t reserved = 0, n_match = 0;
-        int rc = stage_sort_merge(c, n, d_qinfo, false, &reserved, &n_match);
+        c->arena_S8 = S8;
+        int rc = stage_sort_merge(c, n, n, d_qinfo, false, &reserved, &n_match);
+        c->stats.n_query_kmers = c->stats.n_merge_queries;
         if (rc != MBL_OK) return rc;
         const float ms_before = c->stats.ms[MBL_STAGE_MSORT];
         StageTimer t(c, MBL_STAGE_MSORT);

@@ -25,6 +25,23 @@ MBL_HD uint32_t qi_pos(uint64_t q) { return (uint32_t)q; }
 MBL_HD uint32_t qi_seq(uint64_t q) { return (uint32_t)((q >> 32) & 0x1FFFFFFFu); }
 MBL_HD uint32_t qi_frame(uint64_t q) { return (uint32_t)(q >> 61); }
 
+// ---- amino-acid presence filter (k3_index.cu builds it, K1 probes it) ---------------------------------
+// Blocked Bloom filter over the 40-bit amino-acid parts of the index: a 256-bit block (one 32-byte sector) per key, two bits
+// inside it.  A query whose amino-acid part is not in the filter cannot have a candidate (KmerMatcher.cpp:363-375 would skip
+// it), so K1 drops it before the sort; false positives only cost work.
+struct AaFilter {
+    const uint32_t* words = nullptr;   // n_blocks x 8 words
+    uint32_t n_blocks = 0;
+};
+MBL_HD uint64_t aa_filter_hash(uint64_t value) {
+    uint64_t h = (value >> 24) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32;
+    return h * 0xD6E8FEB86659FD93ull;
+}
+MBL_HD uint32_t aa_filter_block(uint64_t h, uint32_t n_blocks) { return (uint32_t)(((h >> 32) * (uint64_t)n_blocks) >> 32); }
+MBL_HD uint32_t aa_filter_bit1(uint64_t h) { return (uint32_t)(h >> 8) & 255u; }
+MBL_HD uint32_t aa_filter_bit2(uint64_t h) { return (uint32_t)(h >> 20) & 255u; }
+
 // LocalUtil.h:46-60
 MBL_HD int max_covered_length(int len) {
     int r = len % 3;
