@@ -179,6 +179,7 @@ def sharded_arm(args, rank, local_rank, world, dist):
     lib.mbl_host_register(bases.ctypes.data_as(C.c_void_p), bases.nbytes)
     lib.mbl_host_register(offs.ctypes.data_as(C.c_void_p), offs.nbytes)
     ex = sharded.DistExchange(dist, device) if world > 1 else sharded.SelfExchange()
+    winfo["presence_filter"] = bool(sc.merge_filters(ex))
 
     def barrier():
         torch.cuda.synchronize()

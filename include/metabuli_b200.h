@@ -175,6 +175,12 @@ typedef struct {
 int  mbl_plan_shards(const mbl_db* db, uint32_t n_shards, mbl_shard* out);
 /* mbl_load_db for one shard: uploads diffIdx[diff_begin, diff_end) and info[info_begin, info_end) only. */
 int  mbl_load_db_shard(mbl_ctx* ctx, const mbl_db* db, const mbl_taxonomy* tax, const mbl_shard* shard);
+/* Presence filter in sharded mode: a shard's filter covers only its own value range, so phase 1 may use it only after the ranks
+ * have merged their parts.  mbl_shard_filter returns this rank's part (device pointer, same size on every rank);
+ * mbl_shard_filter_or ORs another rank's part into it (d_other may be NULL) and, with complete != 0, declares the filter
+ * whole.  Without this step phase 1 simply sends every metamer. */
+int  mbl_shard_filter(mbl_ctx* ctx, void** d_words, uint64_t* n_bytes);
+int  mbl_shard_filter_or(mbl_ctx* ctx, const void* d_other, uint64_t n_bytes, int complete);
 /* Phase 1, read owner: upload + extract (A0-A3') and bucket the metamers by owning shard.  seq_base = index of the batch's
  * first read among the reads of all ranks (seqIDs are global on the wire); shard_first_value[n_shards] from mbl_plan_shards.
  * -> send_counts[n_shards]: metamers bound for every shard. */

@@ -167,7 +167,8 @@ namespace { struct AddU64 { __host__ __device__ uint64_t operator()(uint64_t a, 
 // base_value: value the first delta of the stream is relative to (0 for a whole diffIdx file, the preceding k-mer's value for a
 // shard that starts inside the file, mbl_plan_shards); holds_db_tail: the stream ends with the numerically last k-mer of the DB (Q1)
 void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
-                          cudaStream_t st, TileDirectory& dir, uint64_t base_value, bool holds_db_tail, int filter_bits_per_kmer) {
+                          cudaStream_t st, TileDirectory& dir, uint64_t base_value, bool holds_db_tail, int filter_bits_per_kmer,
+                          uint64_t filter_total_kmers) {
     dir = TileDirectory();
     if (tile_cells < 1) tile_cells = 1;
     dir.tile_cells = tile_cells;
@@ -204,7 +205,8 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
     cub::DeviceScan::ExclusiveScan(tmp, tmp_bytes, cell_sum, dir.cell_v, AddU64(), base_value, n_cells, st);
     cell_boundary_kernel<<<blocks, kWarps * 32, 0, st>>>(d_diff, n_u16, n_cells, dir.cell_k, dir.cell_v, b_kidx, b_off, b_base, b_aa);
     if (filter_bits_per_kmer > 0) {
-        const uint64_t want = (n_kmers * (uint64_t)filter_bits_per_kmer + 255) / 256 + 1;
+        // a shard sizes its filter for the whole index: the ranks OR their filters together (mbl_shard_filter_or)
+        const uint64_t want = (std::max(n_kmers, filter_total_kmers) * (uint64_t)filter_bits_per_kmer + 255) / 256 + 1;
         dir.filter_blocks = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull);
         MBL_CUDA(cudaMalloc(&dir.filter, 32 * (size_t)dir.filter_blocks));
         MBL_CUDA(cudaMemsetAsync(dir.filter, 0, 32 * (size_t)dir.filter_blocks, st));
@@ -250,6 +252,18 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
     dir.sort_begin_bit = h_cnt[0] * 32 <= dir.n_tiles ? 40 : h_cnt[1] * 32 <= dir.n_tiles ? 32 : 24;
     cudaFree(cell_cnt); cudaFree(cell_sum); cudaFree(b_kidx); cudaFree(b_off); cudaFree(b_base); cudaFree(b_aa);
     cudaFree(cand); cudaFree(flag); cudaFree(rank); cudaFree(tmp); cudaFree(d_cnt);
+}
+
+__global__ void filter_or_kernel(uint4* __restrict__ w, const uint4* __restrict__ o, uint64_t n16) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 a = w[i];
+        const uint4 b = o[i];
+        a.x |= b.x; a.y |= b.y; a.z |= b.z; a.w |= b.w;
+        w[i] = a;
+    }
+}
+void launch_filter_or(uint32_t* words, const uint32_t* other, uint64_t n_words, cudaStream_t st) {
+    if (n_words) filter_or_kernel<<<148 * 16, 256, 0, st>>>(reinterpret_cast<uint4*>(words), reinterpret_cast<const uint4*>(other), n_words / 4);
 }
 
 void free_tile_directory(TileDirectory& dir) {

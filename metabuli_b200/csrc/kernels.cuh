@@ -81,7 +81,9 @@ void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, ui
 // filter_bits_per_kmer > 0: also build the amino-acid presence filter (about that many bits per k-mer of the stream)
 void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
                           cudaStream_t st, TileDirectory& dir, uint64_t base_value = 0, bool holds_db_tail = true,
-                          int filter_bits_per_kmer = 0);
+                          int filter_bits_per_kmer = 0, uint64_t filter_total_kmers = 0);
+// words |= other (merging the shards' presence filters)
+void launch_filter_or(uint32_t* words, const uint32_t* other, uint64_t n_words, cudaStream_t st);
 void free_tile_directory(TileDirectory& dir);
 
 // K3 merge (per batch)

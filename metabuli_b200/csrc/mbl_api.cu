@@ -90,6 +90,7 @@ struct mbl_ctx {
     uint64_t seq_base = 0;              // index of the resident batch's first read among all ranks' reads
     const uint32_t* sh_perm = nullptr;  // bucket permutation of the last mbl_shard_extract / mbl_shard_match
     uint32_t sh_n = 0;                  // its bucket count
+    uint64_t sh_S8 = 0;                 // arena layout of the last mbl_shard_extract
     uint64_t sh_begin_h[kMaxShards + 2] = {};   // its bucket starts
     // peer-memory transport: this rank's receive buffers and the peers' (IPC-mapped or same-process pointers)
     void *recv_kmers = nullptr, *recv_matches = nullptr;
@@ -99,6 +100,7 @@ struct mbl_ctx {
     bool peer_opened[kMaxShards][2] = {};
     mbl_shard shard{};                  // the value range this context holds (whole index: first_value 0)
     bool is_shard = false;
+    bool filter_complete = false;       // the presence filter covers the whole index (always for mbl_load_db; shards: after the OR)
     // results of the whole batch
     Buf results, pairs, pairs_final;
     uint64_t n_pairs = 0;               // pairs written by this lane
@@ -257,7 +259,7 @@ uint64_t slots_budget(mbl_ctx* c) {
     // fixed: scoring scratch of one chunk + results
     const double r = std::max(0.5, c->match_ratio * 1.3);
     // with the presence filter the phase-1 arena only holds the survivors (the guess of run_sub_batch)
-    const double kept = c->dir.filter ? std::min(1.0, c->pass_ratio > 0 ? 1.3 * c->pass_ratio + 0.05 : 0.45) : 1.0;
+    const double kept = (c->dir.filter && c->filter_complete) ? std::min(1.0, c->pass_ratio > 0 ? 1.3 * c->pass_ratio + 0.05 : 0.45) : 1.0;
     const double per_slot = std::max(32.0 * kept, 48.0 * r) + 24.0 * r + 4.0;
     double budget = 0.88 * (double)(free_b + held) - 10.0e9;
     uint64_t s = budget > 0 ? (uint64_t)(budget / per_slot) : 0;
@@ -530,26 +532,33 @@ int stage_sort_score(mbl_ctx* c, const SubBatch& sb, uint64_t M) {
     return MBL_OK;
 }
 
-int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
-    const bool filtered = c->dir.filter != nullptr;
-    uint64_t n_sort = sb.slots;
+// K1 through the presence filter: -> slots the packed extraction handed out (what the sort / the bucketing walks).  The packed
+// buffers are sized from the survivor fraction seen so far (40 % before the first batch); K1 never writes beyond them, and a
+// cursor past the end means the guess was too small: redo with room for every slot.
+int extract_filtered(mbl_ctx* c, const SubBatch& sb, uint64_t* n_slots_used) {
     unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t guess = (uint64_t)((double)sb.slots * std::min(1.0, c->pass_ratio > 0 ? 1.3 * c->pass_ratio + 0.02 : 0.4)) + 4096;
+    for (int attempt = 0;; ++attempt) {
+        stage_extract(c, sb, true, guess);
+        MBL_CUDA(cudaMemcpyAsync(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost, c->st));
+        MBL_CUDA(cudaStreamSynchronize(c->st));
+        if (h[4] <= c->arena_S8 || attempt > 0) break;
+        c->stats.overflow_retries += 1;
+        guess = sb.slots;
+    }
+    if (h[4] > c->arena_S8) return fail(c, MBL_E_CUDA, "internal: packed extraction overflow");
+    *n_slots_used = h[4];
+    c->stats.n_query_kmers += h[5];             // valid metamers before the filter
+    if (sb.slots) c->pass_ratio = std::max(c->pass_ratio, (double)h[4] / (double)sb.slots);
+    return MBL_OK;
+}
+
+int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
+    const bool filtered = c->dir.filter != nullptr && c->filter_complete;
+    uint64_t n_sort = sb.slots;
     if (filtered) {
-        // the packed buffers are sized from the survivor fraction seen so far (40 % before the first batch); K1 never writes
-        // beyond them, and a cursor past the end means the guess was too small: redo with room for every slot
-        uint64_t guess = (uint64_t)((double)sb.slots * std::min(1.0, c->pass_ratio > 0 ? 1.3 * c->pass_ratio + 0.02 : 0.4)) + 4096;
-        for (int attempt = 0;; ++attempt) {
-            stage_extract(c, sb, true, guess);
-            MBL_CUDA(cudaMemcpyAsync(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost, c->st));
-            MBL_CUDA(cudaStreamSynchronize(c->st));
-            if (h[4] <= c->arena_S8 || attempt > 0) break;
-            c->stats.overflow_retries += 1;
-            guess = sb.slots;
-        }
-        if (h[4] > c->arena_S8) return fail(c, MBL_E_CUDA, "internal: packed extraction overflow");
-        n_sort = h[4];                              // slots handed out by the packed extraction
-        c->stats.n_query_kmers += h[5];             // valid metamers before the filter
-        if (sb.slots) c->pass_ratio = std::max(c->pass_ratio, (double)h[4] / (double)sb.slots);
+        int rc = extract_filtered(c, sb, &n_sort);
+        if (rc != MBL_OK) return rc;
     } else {
         stage_extract(c, sb, false);
     }
@@ -643,7 +652,7 @@ mbl_ctx* ensure_shadow(mbl_ctx* c) {
     s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
     s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->filter_bits = c->filter_bits;
     s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
-    s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded;
+    s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded; s->filter_complete = c->filter_complete;
     s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed
     s->n_reads = c->n_reads; s->paired = c->paired;
     s->match_ratio = c->match_ratio; s->pass_ratio = c->pass_ratio;
@@ -697,9 +706,11 @@ int load_db_range(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx, const mb
         c->tax.taxid2species = up(tx->taxid2species, T);
         c->tax.max_taxid = tx->max_taxid; c->tax.M_k = tx->M_k; c->tax.eukaryota = tx->eukaryota; c->tax.max_nodes = (uint32_t)N;
         MBL_CUDA(cudaStreamSynchronize(c->st));
-        // the presence filter must cover every k-mer a query could match, so a shard (which sees only its own range) builds none
+        // the presence filter must cover every k-mer a query could match: a shard builds its part, sized for the whole index, and
+        // the filter is only used once the ranks have OR-ed their parts together (mbl_shard_filter / mbl_shard_filter_or)
         build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->tile_cells, c->st, c->dir, sh.base_value, sh.holds_db_tail != 0,
-                             is_shard ? 0 : c->filter_bits);
+                             c->filter_bits, db->n_kmers);
+        c->filter_complete = !is_shard;
         if (c->force_sort_bit) c->dir.sort_begin_bit = c->force_sort_bit;
         // the k-mer count implied by the end flags must agree with the info file
         if (c->dir.n_kmers_decoded != c->n_kmers) {
@@ -1021,6 +1032,29 @@ int mbl_classify_prefetched(mbl_ctx* c, const mbl_batch* next, mbl_read_result* 
 }
 
 // ---- index-sharded mode: the phases one rank runs around the two exchanges (include/metabuli_b200.h) ---------------------
+int mbl_shard_filter(mbl_ctx* c, void** d_words, uint64_t* n_bytes) {
+    if (!c || !d_words || !n_bytes) return fail(c, MBL_E_BAD_ARG, "null argument");
+    *d_words = c->dir.filter;
+    *n_bytes = 32ull * c->dir.filter_blocks;
+    return MBL_OK;
+}
+
+int mbl_shard_filter_or(mbl_ctx* c, const void* d_other, uint64_t n_bytes, int complete) {
+    if (!c) return MBL_E_BAD_ARG;
+    if (!c->dir.filter) { c->filter_complete = false; return MBL_OK; }          // MBL_FILTER_BITS=0
+    if (d_other && n_bytes != 32ull * c->dir.filter_blocks) return fail(c, MBL_E_BAD_ARG, "filter sizes differ between the ranks");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        if (d_other) launch_filter_or(c->dir.filter, (const uint32_t*)d_other, n_bytes / 4, c->st);
+        MBL_CUDA(cudaStreamSynchronize(c->st));
+        MBL_CUDA(cudaGetLastError());
+        if (complete) c->filter_complete = true;
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    }
+    return MBL_OK;
+}
+
 int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_t n_shards, const uint64_t* shard_first_value,
                       uint64_t* send_counts) {
     if (!c || !b || !shard_first_value || !send_counts) return fail(c, MBL_E_BAD_ARG, "null argument");
@@ -1047,8 +1081,14 @@ int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_
         for (uint32_t s = 0; s <= n_shards; ++s) c->sh_begin_h[s] = 0;
         if (c->subs.empty()) return MBL_OK;
         const SubBatch sb = c->subs[0];
-        stage_extract(c, sb, false);
-        const uint64_t S = sb.slots;
+        uint64_t S = sb.slots;
+        if (c->dir.filter && c->filter_complete) {
+            int rc2 = extract_filtered(c, sb, &S);
+            if (rc2 != MBL_OK) return rc2;
+        } else {
+            stage_extract(c, sb, false);
+        }
+        c->sh_S8 = c->arena_S8;
         const uint64_t* va = (const uint64_t*)c->arena.p;
         const float ms_k1 = c->stats.ms[MBL_STAGE_EXTRACT];
         StageTimer t(c, MBL_STAGE_EXTRACT);
@@ -1079,7 +1119,7 @@ int mbl_shard_pack_kmers(mbl_ctx* c, const uint64_t** d_send_value, const uint64
         *d_send_value = nullptr; *d_send_qinfo = nullptr;
         const uint64_t n_send = c->sh_begin_h[c->sh_n];
         if (!n_send || c->subs.empty()) return MBL_OK;
-        const uint64_t S8 = (c->subs[0].slots + 31) & ~31ull;
+        const uint64_t S8 = c->sh_S8;
         const uint64_t* va = (const uint64_t*)c->arena.p;
         const float ms_before = c->stats.ms[MBL_STAGE_EXTRACT];
         StageTimer t(c, MBL_STAGE_EXTRACT);
@@ -1238,7 +1278,7 @@ int mbl_shard_push_kmers(mbl_ctx* c, const uint64_t* dst_row_offset, const uint6
             if (c->sh_begin_h[s + 1] > c->sh_begin_h[s] && !d.base[s]) return fail(c, MBL_E_BAD_ARG, "peer buffer not attached");
         }
         d.begin[c->sh_n] = n_send;
-        const uint64_t S8 = (c->subs[0].slots + 31) & ~31ull;
+        const uint64_t S8 = c->sh_S8;
         const uint64_t* va = (const uint64_t*)c->arena.p;
         const float ms_before = c->stats.ms[MBL_STAGE_EXTRACT];
         StageTimer t(c, MBL_STAGE_EXTRACT);

@@ -70,6 +70,14 @@ class DistExchange:
     def barrier(self):
         self.dist.barrier()
 
+    def all_gather_tensor(self, t):
+        import torch
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t)
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+        return parts
+
     def rows(self, send, send_counts, recv_counts):
         """send: tensor whose dim 0 is split by send_counts -> tensor of sum(recv_counts) rows."""
         import torch
@@ -93,6 +101,9 @@ class SelfExchange:
 
     def barrier(self):
         pass
+
+    def all_gather_tensor(self, t):
+        return [t]
 
     def rows(self, send, send_counts, recv_counts):
         return send
@@ -132,6 +143,21 @@ class ShardedClassifier:
         if n == 0 or not ptr:
             return torch.empty(tuple(shape), dtype=torch.int64, device=self.device)
         return torch.as_tensor(_DevArray(ptr, shape), device=self.device)
+
+    def merge_filters(self, exchange):
+        """Collective, once after loading: OR the ranks' parts of the amino-acid presence filter together so that phase 1 can
+        drop the metamers no shard can match before they are bucketed and sent (4-5x less exchange traffic)."""
+        p, nb = C.c_void_p(), C.c_uint64(0)
+        self.clf._check(self.lib.mbl_shard_filter(self.ctx, C.byref(p), C.byref(nb)))
+        if not p.value or nb.value == 0:
+            return False
+        mine = self._tensor(p.value, (nb.value // 8,))
+        for r, part in enumerate(exchange.all_gather_tensor(mine)):
+            if r != exchange.rank:
+                self.clf._check(self.lib.mbl_shard_filter_or(self.ctx, part.data_ptr(), nb.value, 0))
+        self.clf._check(self.lib.mbl_shard_filter_or(self.ctx, None, nb.value, 1))
+        exchange.barrier()
+        return True
 
     # -- phases ---------------------------------------------------------------------------------------------------
     def phase_extract(self, bases1, off1, bases2, off2, seq_base: int):

@@ -41,6 +41,9 @@ class LocalExchange:
     def barrier(self):
         self.w.barrier.wait()
 
+    def all_gather_tensor(self, t):
+        return self._a2a([t] * self.world)
+
     def rows(self, send, send_counts, recv_counts):
         parts = list(torch.split(send, [int(x) for x in send_counts], dim=0))
         got = self._a2a([p.clone() for p in parts])
