@@ -114,6 +114,7 @@ struct mbl_ctx {
     int pipeline = 0;                   // MBL_PIPELINE=1 switches the second lane on (measured slower: the lanes contend and the index is streamed twice)
     uint32_t pipeline_min_reads = 1u << 21;   // MBL_PIPELINE_MIN_READS: smaller batches stay on one lane
     double match_ratio = 0.0;   // matches per slot seen so far (sizes the match buffer)
+    double shard_match_ratio = 0.0;   // sharded phase 2: matches per received metamer
     double pass_ratio = 0.0;    // slots the packed (filtered) extraction used per reserved slot, seen so far
     mbl_stats stats{};
 };
@@ -316,8 +317,9 @@ void stage_extract(mbl_ctx* c, const SubBatch& sb, bool use_filter, uint64_t fil
 
 // K2 + K3: sort the S slots in the phase-1 arena (keys in `value A`, slot indices in `slot idx A`) and merge them against the
 // resident index; q_info is the array the slot indices point into.  -> rows written to m_raw (blank tails included), matches
-int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, const uint64_t* q_info, bool count_valid_on_device, uint64_t* reserved_out,
-                     uint64_t* n_match_out) {
+// ratio: matches per cap_basis slot seen so far on this kind of input (sizes the match buffer; updated)
+int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, double* ratio, const uint64_t* q_info, bool count_valid_on_device,
+                     uint64_t* reserved_out, uint64_t* n_match_out) {
     cudaStream_t st = c->st;
     const uint64_t S8 = c->arena_S8;
     const size_t scan_bytes = scan_temp_bytes(c->dir.n_tiles + 2);
@@ -348,7 +350,7 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, const uint64_t*
     c->stats.n_merge_queries += n_query;
 
     // ---- K3 ------------------------------------------------------------------------------------------
-    uint64_t cap = (uint64_t)((double)cap_basis * std::max(c->match_ratio * 1.25, 0.125 * (double)std::max(1, c->cfg.match_per_kmer))) + out_slack(c);
+    uint64_t cap = (uint64_t)((double)cap_basis * std::max(*ratio * 1.25, 0.125 * (double)std::max(1, c->cfg.match_per_kmer))) + out_slack(c);
     uint64_t reserved = 0, n_match = 0;
     MergeArgs ma{};
     ma.diff = c->d_diff; ma.info = c->d_info;
@@ -414,7 +416,7 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, const uint64_t*
     }
     c->stats.n_matches += n_match;
     c->stats.merge_bytes += 2 * c->n_u16 + 4 * c->n_kmers + 16 * n_query + 24 * n_match;
-    if (cap_basis) c->match_ratio = std::max(c->match_ratio, (double)reserved / (double)cap_basis);
+    if (cap_basis) *ratio = std::max(*ratio, (double)reserved / (double)cap_basis);
     if (reserved >= (1ull << 32)) return fail(c, MBL_E_UNSUPPORTED, "more than 2^32 matches in one sub-batch");
     *reserved_out = reserved; *n_match_out = n_match;
     return MBL_OK;
@@ -564,7 +566,7 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     }
     uint64_t reserved = 0, n_match = 0;
     const uint64_t nq_before = c->stats.n_merge_queries;
-    int rc = stage_sort_merge(c, n_sort, sb.slots, (const uint64_t*)c->arena.p + 2 * c->arena_S8, true, &reserved, &n_match);
+    int rc = stage_sort_merge(c, n_sort, sb.slots, &c->match_ratio, (const uint64_t*)c->arena.p + 2 * c->arena_S8, true, &reserved, &n_match);
     if (!filtered) c->stats.n_query_kmers += c->stats.n_merge_queries - nq_before;
     if (rc != MBL_OK) return rc;
     return stage_sort_score(c, sb, reserved);
@@ -1156,7 +1158,7 @@ int mbl_shard_match(mbl_ctx* c, const uint64_t* d_value, const uint64_t* d_qinfo
         launch_iota(ia, n, st);
         uint64_t reserved = 0, n_match = 0;
         c->arena_S8 = S8;
-        int rc = stage_sort_merge(c, n, n, d_qinfo, false, &reserved, &n_match);
+        int rc = stage_sort_merge(c, n, n, &c->shard_match_ratio, d_qinfo, false, &reserved, &n_match);
         c->stats.n_query_kmers = c->stats.n_merge_queries;
         if (rc != MBL_OK) return rc;
         const float ms_before = c->stats.ms[MBL_STAGE_MSORT];
