@@ -11,8 +11,9 @@ Legs of our arm, both timed over exactly K steps after W warm-up steps:
   value : reads resident in HBM, mbl_classify_resident() per step (device pipeline only)
   e2e   : per step the reads go up from pinned host buffers and the per-read results come back, all inside the timed
           region; the upload of step i+1 overlaps the classification of step i (mbl_prefetch_batch / mbl_classify_prefetched)
-`roofline` is the merge kernel: algorithmic bytes (S_diff + 4K + 16Nq + 24Nm) over its
-CUDA-event time, against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
+`roofline` is the merge kernel: algorithmic bytes (S_diff + 4K + 16Nq + 24Nm; Nq = the metamers that reach the
+merge, i.e. after the amino-acid presence filter of K1) over its CUDA-event time, against the measured HBM copy bandwidth of
+MEASURED_PEAKS.json.
 """
 from __future__ import annotations
 
@@ -387,7 +388,8 @@ def main():
             "config": {"workload": f"{n_reads} synthetic {args.read_len} bp SE reads per GPU per step vs {winfo['index_gib']} GiB synthetic "
                                    f"index replicated per GPU (BASELINE configs[1])", "l2": "inputs_exceed_l2",
                        "parallelism": f"replica x{world}: reads sharded, index replicated, no data-path collective", **winfo,
-                       "query_kmers_per_step": last["n_query_kmers"], "matches_per_step": last["n_matches"],
+                       "query_kmers_per_step": last["n_query_kmers"], "merge_queries_per_step": last["n_merge_queries"],
+                       "presence_filter": last["n_merge_queries"] < last["n_query_kmers"], "matches_per_step": last["n_matches"],
                        "classified_per_step": classified, "sub_batches": last["sub_batches"], "overflow_retries": last["overflow_retries"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": ncu_traffic(), "kernel": "merge_kernel", "peak_source": peak_src,

@@ -1068,7 +1068,17 @@ int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_
     int rc = mbl_upload_batch(c, b);
     c->pipeline = pipeline;
     if (rc != MBL_OK) return rc;
-    if (c->subs.size() > 1) return fail(c, MBL_E_CAPACITY, "batch too large for one sharded pass: split it on the caller's side");
+    if (c->subs.size() > 1) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        uint64_t slots = 0;
+        for (const SubBatch& x : c->subs) slots += x.slots;
+        char msg[320];
+        snprintf(msg, sizeof msg, "batch too large for one sharded pass (%llu slots, budget %llu slots, %.1f of %.1f GB free, match ratio %.3f, "
+                 "pass ratio %.3f): split it on the caller's side", (unsigned long long)slots, (unsigned long long)slots_budget(c), free_b / 1e9,
+                 total_b / 1e9, c->match_ratio, c->pass_ratio);
+        return fail(c, MBL_E_CAPACITY, msg);
+    }
     try {
         cudaStream_t st = c->st;
         float h2d = c->stats.ms[MBL_STAGE_H2D];
