@@ -10,6 +10,7 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -17,9 +18,11 @@
 #include <fstream>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/metabuli_b200.h"
+#include "fastx_tsv.hpp"
 
 namespace {
 
@@ -136,53 +139,8 @@ struct TaxonomyHost {
     }
 };
 
-// ---- FASTA/FASTQ with kseq semantics -------------------------------------------------------------------------
-struct ReadFile {
-    std::vector<std::string> names;
-    std::vector<char> bases;
-    std::vector<uint64_t> offsets{0};
-    void load(const std::string& path) {
-        gzFile g = gzopen(path.c_str(), "rb");
-        if (!g) die("cannot open " + path);
-        gzbuffer(g, 1 << 20);
-        std::string data;
-        std::vector<char> buf(1 << 22);
-        int got;
-        while ((got = gzread(g, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)got);
-        gzclose(g);
-        size_t i = 0, n = data.size();
-        auto line = [&](size_t& b, size_t& e) { b = i; while (i < n && data[i] != '\n') ++i; e = i; if (i < n) ++i; if (e > b && data[e - 1] == '\r') --e; };
-        size_t b, e, entry = 0;
-        while (i < n) {
-            while (i < n && data[i] != '>' && data[i] != '@') line(b, e);
-            if (i >= n) break;
-            char tag = data[i];
-            line(b, e);
-            size_t p = b + 1;
-            while (p < e && !isspace((unsigned char)data[p])) ++p;
-            names.emplace_back(data, b + 1, p - (b + 1));
-            size_t start = bases.size();
-            while (i < n && data[i] != '>' && data[i] != '@' && data[i] != '+') {
-                line(b, e);
-                for (size_t x = b; x < e; ++x) if (isgraph((unsigned char)data[x])) bases.push_back(data[x]);
-            }
-            if (tag == '@' && i < n && data[i] == '+') {
-                line(b, e);
-                size_t ql = 0, sl = bases.size() - start;
-                while (i < n && ql < sl) { line(b, e); ql += e - b; }
-            }
-            ++entry;
-            if (bases.size() == start || names.back().empty()) {   // QueryIndexer.cpp:50-53
-                printf("%zuth entry has no sequence or name.\n", entry);
-                exit(1);
-            }
-            offsets.push_back(bases.size());
-        }
-    }
-};
-
 struct Params {
-    int seqMode = 2, threads = 1, accessionLevel = 0, minConsCnt = 4, minConsCntEuk = 9, matchPerKmer = 4, device = 0;
+    int seqMode = 2, threads = 0, accessionLevel = 0, minConsCnt = 4, minConsCntEuk = 9, matchPerKmer = 4, device = 0;
     float minScore = 0.f, minSpScore = 0.f, tieRatio = 0.95f;
     size_t batchReads = 0;
     std::vector<std::string> files;
@@ -266,60 +224,94 @@ int classify(int argc, char** argv) {
     rc = mbl_load_db(ctx, &db, &tx);
     if (rc != MBL_OK) die(std::string("mbl_load_db: ") + mbl_last_error(ctx));
 
-    ReadFile r1, r2;
-    r1.load(q1);
+    // reads: parsed by all host threads (fastx_tsv.hpp), kept in memory as the SoA the library takes
+    const unsigned T = par.threads > 0 ? (unsigned)par.threads : std::max(1u, std::thread::hardware_concurrency());
+    mblhost::ReadSet r1, r2;
+    std::string perr;
+    auto tl0 = std::chrono::steady_clock::now();
+    if (!mblhost::load_fastx(q1, r1, T, &perr)) die(perr);
     if (par.seqMode == 2) {
-        r2.load(q2);
-        if (r1.names.size() != r2.names.size()) die("The number of reads in the two files are not equal.");
+        if (!mblhost::load_fastx(q2, r2, T, &perr)) die(perr);
+        if (r1.size() != r2.size()) die("The number of reads in the two files are not equal.");
     }
-    const size_t total = r1.names.size();
+    const size_t total = r1.size();
     printf("--------------------\nTotal read count : %zu\nTotal read length: %zunt\n--------------------\n", total,
            r1.bases.size() + r2.bases.size());
+    printf("Reads loaded in %.3f s (%u threads)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tl0).count(), T);
+    if (!r1.bases.empty()) mbl_host_register(r1.bases.data(), r1.bases.size());
+    if (!r2.bases.empty()) mbl_host_register(r2.bases.data(), r2.bases.size());
 
     const std::string tsvPath = outDir + "/" + jobId + "_classifications.tsv";
     FILE* out = fopen(tsvPath.c_str(), "wb");
     if (!out) die("cannot write " + tsvPath);
     fputs("#is_classified\tname\ttaxID\tquery_length\tscore\trank\ttaxID:match_count\n", out);      // Reporter.cpp:37-41
-    const size_t step = par.batchReads ? par.batchReads : (total ? total : 1);
-    std::vector<mbl_read_result> res;
-    std::vector<int32_t> pairs;
+
+    // batches (the reference's QuerySplits, Classifier.cpp:81-140): batch i+1 is uploaded while batch i is classified
+    // (mbl_prefetch_batch / mbl_classify_prefetched) and batch i-1 is formatted and written by the host threads
+    const size_t step = par.batchReads ? par.batchReads : (size_t)8000000;
+    // inputs and outputs rotate separately: while batch i is on the GPU, the offsets of batch i+1 are being prepared / uploaded
+    // and the rows of batch i-1 are being formatted
+    struct In { std::vector<uint64_t> off1, off2; mbl_batch b{}; size_t r0 = 0, n = 0; } in[2];
+    struct Out { std::vector<mbl_read_result> res; std::vector<int32_t> pairs; size_t used = 0, r0 = 0, n = 0; } outb[2];
+    auto fill = [&](In& s, size_t r0) {
+        s.r0 = r0; s.n = std::min(step, total - r0);
+        auto rebase = [&](const mblhost::ReadSet& r, std::vector<uint64_t>& off) {
+            off.resize(s.n + 1);
+            const uint64_t base = r.offsets[r0];
+            for (size_t k = 0; k <= s.n; ++k) off[k] = r.offsets[r0 + k] - base;
+            return r.bases.data() + base;
+        };
+        s.b = mbl_batch{};
+        s.b.bases = rebase(r1, s.off1); s.b.offsets = s.off1.data(); s.b.n_reads = (uint32_t)s.n;
+        if (par.seqMode == 2) { s.b.bases2 = rebase(r2, s.off2); s.b.offsets2 = s.off2.data(); }
+    };
+    struct TaxView {
+        const TaxonomyHost& t;
+        int32_t original(int32_t x) const { return t.original(x); }
+        const char* rank_name(int32_t x) const { return t.str(t.rankIdx[t.D[x]]); }
+    } tv{tax};
     uint64_t kmers = 0, matches = 0;
     auto t0 = std::chrono::steady_clock::now();
-    for (size_t r0 = 0; r0 < total; r0 += step) {
-        const size_t n = std::min(step, total - r0);
-        mbl_batch b{};
-        b.bases = r1.bases.data(); b.offsets = r1.offsets.data() + r0; b.n_reads = (uint32_t)n;
-        if (par.seqMode == 2) { b.bases2 = r2.bases.data(); b.offsets2 = r2.offsets.data() + r0; }
-        res.assign(n, mbl_read_result{});
-        size_t cap = pairs.size() / 2, used = 0;
-        rc = mbl_classify_batch(ctx, &b, res.data(), pairs.data(), cap, &used);
-        if (rc == MBL_E_CAPACITY) {
-            pairs.assign(2 * (used + 16), 0);
-            rc = mbl_classify_batch(ctx, &b, res.data(), pairs.data(), used + 16, &used);
+    std::thread writer;
+    if (total) {
+        fill(in[0], 0);
+        rc = mbl_prefetch_batch(ctx, &in[0].b);
+        if (rc != MBL_OK) die(std::string("mbl_prefetch_batch: ") + mbl_last_error(ctx));
+    }
+    int cur = 0;
+    for (size_t r0 = 0; r0 < total; r0 += step, cur ^= 1) {
+        In& s = in[cur];
+        Out& o = outb[cur];
+        const bool has_next = r0 + step < total;
+        if (has_next) fill(in[cur ^ 1], r0 + step);
+        o.r0 = s.r0; o.n = s.n;
+        o.res.assign(s.n, mbl_read_result{});
+        if (o.pairs.size() < 10 * s.n + 32) o.pairs.assign(10 * s.n + 32, 0);
+        rc = mbl_classify_prefetched(ctx, has_next ? &in[cur ^ 1].b : nullptr, o.res.data(), o.pairs.data(), o.pairs.size() / 2, &o.used);
+        if (rc == MBL_E_CAPACITY) {                       // the batch is classified and resident: only the download is repeated
+            o.pairs.assign(2 * (o.used + 16), 0);
+            rc = mbl_download_results(ctx, o.res.data(), o.pairs.data(), o.pairs.size() / 2, &o.used);
         }
-        if (rc != MBL_OK) die(std::string("mbl_classify_batch: ") + mbl_last_error(ctx));
+        if (rc != MBL_OK) die(std::string("mbl_classify_prefetched: ") + mbl_last_error(ctx));
         mbl_stats st;
         mbl_get_stats(ctx, &st);
         kmers += st.n_query_kmers; matches += st.n_matches;
-        // Reporter::writeReadClassification (Reporter.cpp:43-79)
-        for (size_t i = 0; i < n; ++i) {
-            const mbl_read_result& q = res[i];
-            if (q.is_classified) {
-                fprintf(out, "1\t%s\t%d\t%d\t%g\t%s\t", r1.names[r0 + i].c_str(), tax.original(q.classification), q.query_length,
-                        (double)q.score, tax.str(tax.rankIdx[tax.D[q.classification]]));
-                for (uint32_t k = q.taxcnt_begin; k < q.taxcnt_begin + q.taxcnt_len; ++k)
-                    fprintf(out, "%d:%d ", tax.original(pairs[2 * k]), pairs[2 * k + 1]);
-                fputc('\n', out);
-            } else {
-                fprintf(out, "0\t%s\t%d\t%d\t%g\t-\t-\t\n", r1.names[r0 + i].c_str(), tax.original(q.classification), q.query_length, (double)q.score);
-            }
-        }
-        printf("Processed read count   : %zu (%g)\n", r0 + n, (double)(r0 + n) / (double)total);
+        if (writer.joinable()) writer.join();             // rows of batch i-1 are out before batch i+1 reuses that buffer
+        writer = std::thread([&, cur] {
+            const Out& w = outb[cur];
+            std::vector<std::string> rows;
+            mblhost::format_rows(tv, r1.names, w.r0, w.n, w.res.data(), w.pairs.data(), T, rows);
+            for (const std::string& x : rows) fwrite(x.data(), 1, x.size(), out);
+        });
+        printf("Processed read count   : %zu (%g)\n", r0 + s.n, (double)(r0 + s.n) / (double)total);
     }
+    if (writer.joinable()) writer.join();
     fclose(out);
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     printf("Query k-mer number     : %llu\nTotal k-mer match count: %llu\nTaxonomic classification completed. (%.3f s)\n",
            (unsigned long long)kmers, (unsigned long long)matches, sec);
+    if (!r1.bases.empty()) mbl_host_unregister(r1.bases.data());
+    if (!r2.bases.empty()) mbl_host_unregister(r2.bases.data());
     mbl_destroy(ctx);
     return 0;
 }

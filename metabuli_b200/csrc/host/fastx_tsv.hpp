@@ -1,0 +1,228 @@
+// Host I/O of the classify path: FASTA/FASTQ reading with kseq semantics (reference: lib/mmseqs KSeqWrapper as used by
+// KmerExtractor::loadChunkOfReads, KmerExtractor.cpp:429-481, and QueryIndexer::indexQueryFile, QueryIndexer.cpp:30-147) and
+// the per-read TSV rows of Reporter::writeReadClassification (Reporter.cpp:35-80).
+//
+// The reference parses on one thread (its master thread is the bottleneck at 8 threads, SURVEY §8 A3') and formats on one
+// thread; at tens of millions of reads per second from the GPU both have to be parallel.  The file is cut at record starts
+// into one range per thread, every range is parsed with the same sequential grammar, and the rows of a batch are formatted
+// by all threads into per-thread strings that are written in order.
+#pragma once
+#include <zlib.h>
+
+#include <cctype>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/metabuli_b200.h"
+
+namespace mblhost {
+
+struct ReadSet {                       // SoA layout of mbl_batch + the names the Reporter prints
+    std::vector<std::string> names;
+    std::vector<char> bases;
+    std::vector<uint64_t> offsets{0};
+    size_t size() const { return names.size(); }
+};
+
+// whole file into memory (gz or plain; gzread handles both)
+inline bool slurp_maybe_gz(const std::string& path, std::string& data) {
+    gzFile g = gzopen(path.c_str(), "rb");
+    if (!g) return false;
+    gzbuffer(g, 1 << 20);
+    std::vector<char> buf(1 << 24);
+    int got;
+    while ((got = gzread(g, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)got);
+    gzclose(g);
+    return true;
+}
+
+// sequential kseq grammar over data[i0, i1): a record starts at a line whose first character is '>' or '@'; name = first
+// whitespace-delimited token; sequence = the graphic characters of the following lines up to a line starting with '>', '@'
+// or '+'; a FASTQ record then skips the '+' line and as many quality characters as it has bases.
+// Returns false on an entry without a sequence or a name (QueryIndexer.cpp:50-53); *bad = its ordinal in the range.
+inline bool parse_range(const std::string& data, size_t i0, size_t i1, ReadSet& out, size_t* bad) {
+    size_t i = i0;
+    const size_t n = i1;
+    const char* d = data.data();
+    auto line = [&](size_t& b, size_t& e) {
+        b = i;
+        const void* nl = i < n ? memchr(d + i, '\n', n - i) : nullptr;
+        e = nl ? (size_t)((const char*)nl - d) : n;
+        i = nl ? e + 1 : n;
+        if (e > b && d[e - 1] == '\r') --e;
+    };
+    size_t b, e, entry = 0;
+    while (i < n) {
+        while (i < n && d[i] != '>' && d[i] != '@') line(b, e);
+        if (i >= n) break;
+        const char tag = d[i];
+        line(b, e);
+        size_t p = b + 1;
+        while (p < e && !isspace((unsigned char)d[p])) ++p;
+        out.names.emplace_back(d + b + 1, p - (b + 1));
+        const size_t start = out.bases.size();
+        while (i < n && d[i] != '>' && d[i] != '@' && d[i] != '+') {
+            line(b, e);
+            const size_t at = out.bases.size();
+            out.bases.insert(out.bases.end(), d + b, d + e);
+            bool clean = true;
+            for (size_t x = at; x < out.bases.size(); ++x) clean &= isgraph((unsigned char)out.bases[x]) != 0;
+            if (!clean) {                                    // rare: blanks or control characters inside a sequence line
+                size_t w = at;
+                for (size_t x = at; x < out.bases.size(); ++x) if (isgraph((unsigned char)out.bases[x])) out.bases[w++] = out.bases[x];
+                out.bases.resize(w);
+            }
+        }
+        if (tag == '@' && i < n && d[i] == '+') {
+            line(b, e);
+            size_t ql = 0;
+            const size_t sl = out.bases.size() - start;
+            while (i < n && ql < sl) { line(b, e); ql += e - b; }
+        }
+        ++entry;
+        if (out.bases.size() == start || out.names.back().empty()) { if (bad) *bad = entry; return false; }
+        out.offsets.push_back(out.bases.size());
+    }
+    return true;
+}
+
+// record starts at or after `from` that are safe cut points: FASTA: a line starting with '>'; FASTQ: a line starting with
+// '@' whose second-next line starts with '+' (a quality line that starts with '@' is followed by a header, then bases)
+inline size_t next_record_start(const std::string& data, size_t from, bool fastq) {
+    const size_t n = data.size();
+    const char* d = data.data();
+    size_t i = from;
+    if (i > 0) {                                              // move to a line start
+        const void* nl = memchr(d + i - 1, '\n', n - (i - 1));
+        if (!nl) return n;
+        i = (size_t)((const char*)nl - d) + 1;
+    }
+    while (i < n) {
+        if (!fastq && d[i] == '>') return i;
+        if (fastq && d[i] == '@') {
+            const void* l1 = memchr(d + i, '\n', n - i);
+            const void* l2 = l1 ? memchr((const char*)l1 + 1, '\n', n - ((const char*)l1 + 1 - d)) : nullptr;
+            if (l2 && (size_t)((const char*)l2 + 1 - d) < n && ((const char*)l2)[1] == '+') return i;
+        }
+        const void* nl = memchr(d + i, '\n', n - i);
+        if (!nl) return n;
+        i = (size_t)((const char*)nl - d) + 1;
+    }
+    return n;
+}
+
+// Parallel load.  Returns false with *err set on unreadable files or an entry without sequence / name.
+inline bool load_fastx(const std::string& path, ReadSet& out, unsigned threads, std::string* err) {
+    std::string data;
+    if (!slurp_maybe_gz(path, data)) { if (err) *err = "cannot open " + path; return false; }
+    size_t first = 0;
+    while (first < data.size() && data[first] != '>' && data[first] != '@') {
+        const void* nl = memchr(data.data() + first, '\n', data.size() - first);
+        if (!nl) { first = data.size(); break; }
+        first = (size_t)((const char*)nl - data.data()) + 1;
+    }
+    const bool fastq = first < data.size() && data[first] == '@';
+    unsigned T = threads ? threads : 1;
+    if (data.size() < (1u << 22)) T = 1;
+    std::vector<size_t> cut(T + 1, data.size());
+    cut[0] = 0;
+    for (unsigned t = 1; t < T; ++t) cut[t] = next_record_start(data, data.size() / T * t, fastq);
+    for (unsigned t = 1; t <= T; ++t) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+    std::vector<ReadSet> part(T);
+    std::vector<size_t> bad(T, 0);
+    std::vector<char> ok(T, 1);
+    auto work = [&](unsigned t) {
+        part[t].bases.reserve((cut[t + 1] - cut[t]) / (fastq ? 2 : 1) + 64);
+        ok[t] = parse_range(data, cut[t], cut[t + 1], part[t], &bad[t]) ? 1 : 0;
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    size_t n_reads = 0, n_bases = 0;
+    for (unsigned t = 0; t < T; ++t) {
+        if (!ok[t]) {
+            if (err) *err = std::to_string(n_reads + bad[t]) + "th entry has no sequence or name.";
+            return false;
+        }
+        n_reads += part[t].size(); n_bases += part[t].bases.size();
+    }
+    out.names.clear(); out.bases.clear(); out.offsets.assign(1, 0);
+    out.names.reserve(n_reads); out.bases.resize(n_bases); out.offsets.reserve(n_reads + 1);
+    std::vector<size_t> base_at(T + 1, 0);
+    for (unsigned t = 0; t < T; ++t) base_at[t + 1] = base_at[t] + part[t].bases.size();
+    for (unsigned t = 0; t < T; ++t) {
+        for (auto& s : part[t].names) out.names.emplace_back(std::move(s));
+        for (size_t k = 1; k < part[t].offsets.size(); ++k) out.offsets.push_back(base_at[t] + part[t].offsets[k]);
+    }
+    auto copy = [&](unsigned t) { if (!part[t].bases.empty()) memcpy(out.bases.data() + base_at[t], part[t].bases.data(), part[t].bases.size()); };
+    th.clear();
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(copy, t);
+    copy(0);
+    for (auto& x : th) x.join();
+    return true;
+}
+
+// ---- Reporter::writeReadClassification rows (Reporter.cpp:43-79, printLineage 0) ------------------------------------------
+// `ostream << float` prints like %g (6 significant digits, Q12).
+inline void append_int(std::string& s, long long v) {
+    char buf[24];
+    int n = 0;
+    bool neg = v < 0;
+    unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (neg) s.push_back('-');
+    while (n) s.push_back(buf[--n]);
+}
+
+// Tax must provide: int32_t original(int32_t) const; const char* rank_name(int32_t internal_taxid) const
+template <class Tax>
+void format_rows(const Tax& tax, const std::vector<std::string>& names, size_t name0, size_t n, const mbl_read_result* res,
+                 const int32_t* pairs, unsigned threads, std::vector<std::string>& out) {
+    unsigned T = threads ? threads : 1;
+    if (n < 4096) T = 1;
+    out.assign(T, std::string());
+    auto work = [&](unsigned t) {
+        const size_t a = n * t / T, b = n * (t + 1) / T;
+        std::string& s = out[t];
+        s.reserve((b - a) * 96);
+        char num[48];
+        for (size_t i = a; i < b; ++i) {
+            const mbl_read_result& q = res[i];
+            s.push_back(q.is_classified ? '1' : '0');
+            s.push_back('\t');
+            s += names[name0 + i];
+            s.push_back('\t');
+            append_int(s, tax.original(q.classification));
+            s.push_back('\t');
+            append_int(s, q.query_length);
+            s.push_back('\t');
+            s.append(num, (size_t)snprintf(num, sizeof num, "%g", (double)q.score));
+            s.push_back('\t');
+            if (q.is_classified) {
+                s += tax.rank_name(q.classification);
+                s.push_back('\t');
+                for (uint32_t k = q.taxcnt_begin; k < q.taxcnt_begin + q.taxcnt_len; ++k) {
+                    append_int(s, tax.original(pairs[2 * (size_t)k]));
+                    s.push_back(':');
+                    append_int(s, pairs[2 * (size_t)k + 1]);
+                    s.push_back(' ');
+                }
+                s.push_back('\n');
+            } else {
+                s += "-\t-\t\n";
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+}  // namespace mblhost

@@ -1,0 +1,39 @@
+// TEST HARNESS for metabuli_b200/csrc/host/fastx_tsv.hpp (the C++ host's parallel FASTA/FASTQ reader and TSV row formatter):
+// C entry points so the CPU tests can compare them with the Python mirror (metabuli_b200/fastx.py, Classifier.format_tsv).
+#include "../../metabuli_b200/csrc/host/fastx_tsv.hpp"
+
+namespace {
+mblhost::ReadSet g_reads;
+std::string g_text;
+struct Tax {
+    const int32_t* orig; const char* const* ranks;
+    int32_t original(int32_t x) const { return orig[x]; }
+    const char* rank_name(int32_t x) const { return ranks[x]; }
+};
+}  // namespace
+
+extern "C" {
+// -> number of reads, or -1 (error text via hio_text)
+long long hio_load(const char* path, unsigned threads) {
+    std::string err;
+    if (!mblhost::load_fastx(path, g_reads, threads, &err)) { g_text = err; return -1; }
+    return (long long)g_reads.size();
+}
+unsigned long long hio_total_bases() { return g_reads.bases.size(); }
+void hio_copy(char* bases, unsigned long long* offsets) {
+    if (!g_reads.bases.empty()) memcpy(bases, g_reads.bases.data(), g_reads.bases.size());
+    memcpy(offsets, g_reads.offsets.data(), 8 * g_reads.offsets.size());
+}
+const char* hio_name(unsigned long long i) { return g_reads.names[i].c_str(); }
+// formats rows [0, n) of the loaded reads' names; -> length of the text (hio_text)
+unsigned long long hio_format(unsigned long long n, const mbl_read_result* res, const int32_t* pairs, const int32_t* orig,
+                              const char* const* ranks, unsigned threads) {
+    Tax t{orig, ranks};
+    std::vector<std::string> rows;
+    mblhost::format_rows(t, g_reads.names, 0, (size_t)n, res, pairs, threads, rows);
+    g_text.clear();
+    for (auto& r : rows) g_text += r;
+    return g_text.size();
+}
+const char* hio_text() { return g_text.c_str(); }
+}

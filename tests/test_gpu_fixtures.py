@@ -90,3 +90,24 @@ def test_end_to_end_tsv_matches_reference(case, golden_dir):
     known = {("in", "se"): (1229412, 174845), ("in", "pe"): (2458568, 349237), ("ex", "se"): (1229412, 77545), ("ex", "pe"): (2458568, 154365)}
     assert (st["n_query_kmers"], st["n_matches"]) == known[(db, mode)]
     assert st["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("db,mode,batch", [("in", "pe", 0), ("in", "se", 1500), ("ex", "pe", 777)])
+def test_cpp_host_cli_writes_the_reference_tsv(db, mode, batch, fixtures_dir, golden_dir, tmp_path):
+    """The C++ host (`metabuli-b200 classify`, same command line as the reference): parallel FASTA reader, streamed batches
+    (next batch uploads while the current one is classified), parallel TSV writer -> the reference binary's TSV, byte for byte."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "metabuli_b200", "_lib", "metabuli-b200")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    reads = [os.path.join(fixtures_dir, "reads", f"ERR9594652_5000_{k}.fna.gz") for k in ((1, 2) if mode == "pe" else (1,))]
+    cmd = [exe, "classify", "--seq-mode", "2" if mode == "pe" else "1", "--threads", "4"]
+    if batch:
+        cmd += ["--batch-reads", str(batch)]
+    cmd += reads + [os.path.join(fixtures_dir, f"db_{db}"), str(tmp_path), "job"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    got = open(tmp_path / "job_classifications.tsv", "rb").read()
+    golden = gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_classifications.tsv.gz"), "rb").read()
+    assert got == golden
+    assert "Total read count : 5000" in r.stdout

@@ -1,0 +1,114 @@
+"""The C++ host's parallel FASTA/FASTQ reader and TSV formatter (metabuli_b200/csrc/host/fastx_tsv.hpp) against the Python
+mirror of the reference semantics (kseq: KmerExtractor.cpp:429-481; Reporter.cpp:35-80).  CPU only."""
+import ctypes as C
+import gzip
+import os
+import subprocess
+import types
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host", "host_io_test.cpp")
+HDR = os.path.join(ROOT, "metabuli_b200", "csrc", "host", "fastx_tsv.hpp")
+OUT = os.path.join(ROOT, "tests", "host", "_build", "libhost_io.so")
+
+
+@pytest.fixture(scope="module")
+def hio():
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in (SRC, HDR)):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", OUT, SRC, "-lz", "-lpthread"])
+    L = C.CDLL(OUT)
+    L.hio_load.argtypes = [C.c_char_p, C.c_uint]
+    L.hio_load.restype = C.c_longlong
+    L.hio_total_bases.restype = C.c_ulonglong
+    L.hio_copy.argtypes = [C.c_void_p, C.c_void_p]
+    L.hio_name.argtypes = [C.c_ulonglong]
+    L.hio_name.restype = C.c_char_p
+    L.hio_format.argtypes = [C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+    L.hio_format.restype = C.c_ulonglong
+    L.hio_text.restype = C.c_char_p
+    return L
+
+
+def _load(hio, path, threads):
+    n = hio.hio_load(path.encode(), threads)
+    assert n >= 0, hio.hio_text()
+    bases = np.zeros(hio.hio_total_bases(), dtype=np.uint8)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    hio.hio_copy(bases.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p))
+    return [hio.hio_name(i).decode() for i in range(n)], bases, offs
+
+
+def _write_cases(tmp_path):
+    rng = np.random.default_rng(9)
+    letters = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    n = 60000
+    lens = rng.integers(30, 260, n)
+    seqs = [bytes(letters[rng.integers(0, 5, int(l))]) for l in lens]
+    quals = [bytes(rng.integers(33, 74, int(l)).astype(np.uint8)) for l in lens]      # '!'..'I': lines may start with '@' or '+'
+    fq = tmp_path / "reads.fastq"
+    with open(fq, "wb") as f:
+        for i, (s, q) in enumerate(zip(seqs, quals)):
+            f.write(b"@r%d some comment\n%s\n+\n%s\n" % (i, s, q))
+    fa = tmp_path / "reads.fna"
+    with open(fa, "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b">s%d\tdesc\r\n" % i)
+            for k in range(0, len(s), 70):                                            # multi-line FASTA with CRLF
+                f.write(s[k:k + 70] + b"\r\n")
+    gz = tmp_path / "reads.fq.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(open(fq, "rb").read())
+    return [str(fq), str(fa), str(gz)]
+
+
+@pytest.mark.parametrize("threads", [1, 7])
+def test_parallel_reader_matches_python_mirror(hio, tmp_path, fixtures_dir, threads):
+    from metabuli_b200.fastx import read_fastx
+    paths = _write_cases(tmp_path) + [os.path.join(fixtures_dir, "reads", "ERR9594652_5000_1.fna.gz")]
+    for p in paths:
+        names, bases, offs = _load(hio, p, threads)
+        wn, wb, wo = read_fastx(p)
+        assert names == wn, p
+        assert np.array_equal(offs, wo) and np.array_equal(bases, wb), p
+
+
+def test_reader_rejects_empty_entries(hio, tmp_path):
+    p = tmp_path / "bad.fna"
+    p.write_bytes(b">a\nACGT\n>b\n>c\nAC\n")
+    assert hio.hio_load(str(p).encode(), 1) == -1
+    assert b"2th entry has no sequence or name." in hio.hio_text()
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_rows_match_python_formatter(hio, tmp_path, threads):
+    from metabuli_b200 import _ffi
+    from metabuli_b200.classifier import Classifier
+    n = 20000
+    fa = tmp_path / "names.fna"
+    with open(fa, "wb") as f:
+        for i in range(n):
+            f.write(b">read_%d/1 x\nACGT\n" % i)
+    names, _, _ = _load(hio, str(fa), threads)
+    rng = np.random.default_rng(3)
+    res = np.zeros(n, dtype=_ffi.RESULT_DTYPE)
+    res["is_classified"] = rng.integers(0, 2, n)
+    res["classification"] = np.where(res["is_classified"] == 1, rng.integers(1, 50, n), 0)
+    res["query_length"] = rng.integers(24, 300, n)
+    scores = np.concatenate([rng.random(n - 6).astype(np.float32), np.float32([0, 1, 0.5, 1e-5, 0.123456789, 0.0000123])])
+    res["score"] = np.where(res["is_classified"] == 1, scores, np.float32(0))
+    res["taxcnt_len"] = np.where(res["is_classified"] == 1, rng.integers(1, 5, n), 0)
+    res["taxcnt_begin"] = np.concatenate([[0], np.cumsum(res["taxcnt_len"])[:-1]])
+    pairs = np.stack([rng.integers(1, 50, int(res["taxcnt_len"].sum())), rng.integers(1, 40, int(res["taxcnt_len"].sum()))], 1).astype(np.int32)
+    orig = (np.arange(50, dtype=np.int32) * 7 + 1000)
+    rank_names = [b"no rank", b"species", b"genus", b"subspecies", b""]
+    ranks = (C.c_char_p * 50)(*[rank_names[i % 5] for i in range(50)])
+    length = hio.hio_format(n, res.ctypes.data_as(C.c_void_p), pairs.ctypes.data_as(C.c_void_p), orig.ctypes.data_as(C.c_void_p), ranks, threads)
+    got = hio.hio_text()[:length].decode()
+    tax = types.SimpleNamespace(original=lambda t: int(orig[t]), rank_of=lambda t: rank_names[t % 5].decode())
+    fake = types.SimpleNamespace(db=types.SimpleNamespace(tax=tax))
+    want = Classifier.format_tsv(fake, names, res, pairs, header=False)
+    assert got == want
