@@ -20,6 +20,7 @@ G = os.path.join(ROOT, "gpurun_out")
 
 
 def short(name):
+    name = name.replace("(anonymous namespace)::", "").replace("void ", "")
     name = re.sub(r"\(.*", "", name)
     name = re.sub(r"<.*", "", name)
     return name.split("::")[-1][:60]
@@ -51,40 +52,41 @@ if os.path.exists(launch_csv):
             f.write(f"| {k} | {agg[k][0]} | {agg[k][1] / 1e6:.3f} | {100 * agg[k][1] / total:.1f}% |\n")
     print("wrote", f"{tag}_launches.md", len(rows), "rows")
 
-rep = os.path.join(G, "merge_prof.ncu-rep")
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units, data = rows[0], rows[1], rows[2:]
-    want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-            "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-            "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size",
-            "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum", "smsp__cycles_active.avg",
-            "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
-            "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
-            "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
-            "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
-            "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct"]
-    idx = {h: i for i, h in enumerate(hdr)}
-    with open(os.path.join(out_dir, f"{tag}_merge_ncu.md"), "w") as f:
-        f.write(f"# {tag}: ncu --set full on merge_kernel (per launch)\n\n")
-        dram = []
-        for li, d in enumerate(data):
-            f.write(f"## launch {li}\n\n| metric | value | unit |\n|---|---|---|\n")
-            for w in want:
-                if w in idx:
-                    f.write(f"| {w} | {d[idx[w]]} | {units[idx[w]]} |\n")
-            f.write("\n")
-            try:
-                def to_bytes(name):
-                    v = float(d[idx[name]].replace(",", ""))
-                    u = units[idx[name]].lower()
-                    return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-                dram.append(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
-            except Exception:
-                pass
-    if dram:
-        json.dump({"dram_bytes_per_launch": sum(dram) / len(dram), "launches": len(dram), "source": f"profiles/{tag}_merge_ncu.md",
-                   "note": "ncu workload = bench.py default workload (10M reads vs ~8 GiB index), one merge launch"},
-                  open(os.path.join(out_dir, "merge_ncu_summary.json"), "w"))
-    print("wrote", f"{tag}_merge_ncu.md", len(data), "launches")
+for kname in ["merge"] + sys.argv[2:]:
+  rep = os.path.join(G, f"{kname}_prof.ncu-rep")
+  if os.path.exists(rep):
+      raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+      rows = list(csv.reader(io.StringIO(raw)))
+      hdr, units, data = rows[0], rows[1], rows[2:]
+      want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+              "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+              "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size",
+              "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum", "smsp__cycles_active.avg",
+              "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+              "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+              "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+              "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+              "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct"]
+      idx = {h: i for i, h in enumerate(hdr)}
+      with open(os.path.join(out_dir, f"{tag}_{kname}_ncu.md"), "w") as f:
+          f.write(f"# {tag}: ncu --set full on {kname} kernel (per launch)\n\n")
+          dram = []
+          for li, d in enumerate(data):
+              f.write(f"## launch {li}\n\n| metric | value | unit |\n|---|---|---|\n")
+              for w in want:
+                  if w in idx:
+                      f.write(f"| {w} | {d[idx[w]]} | {units[idx[w]]} |\n")
+              f.write("\n")
+              try:
+                  def to_bytes(name):
+                      v = float(d[idx[name]].replace(",", ""))
+                      u = units[idx[name]].lower()
+                      return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+                  dram.append(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
+              except Exception:
+                  pass
+      if dram and kname == "merge":
+          json.dump({"dram_bytes_per_launch": sum(dram) / len(dram), "launches": len(dram), "source": f"profiles/{tag}_merge_ncu.md",
+                     "note": "ncu workload = bench.py default workload (10M reads vs ~8 GiB index), one merge launch"},
+                    open(os.path.join(out_dir, "merge_ncu_summary.json"), "w"))
+      print("wrote", f"{tag}_{kname}_ncu.md", len(data), "launches")
