@@ -603,6 +603,12 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         c->d_ham_single = upload(c, t.ham_sum, 64);
         if (const char* e = getenv("MBL_DYN_CHUNKS")) c->dyn_chunks = atoi(e) != 0;
         if (const char* e = getenv("MBL_PIPELINE")) c->pipeline = atoi(e) != 0;
+        // L2 fetch granularity on a DRAM miss (32, 64 or 128 bytes; the default fetches 128): the presence-filter probes of K1 and
+        // the qinfo gathers of K3 are random 32-byte sector reads, and ncu shows 126 bytes of DRAM traffic per probe with the default
+        if (const char* e = getenv("MBL_L2_FETCH")) {
+            int v = atoi(e);
+            if (v == 32 || v == 64 || v == 128) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v); cudaGetLastError(); }
+        }
         if (const char* e = getenv("MBL_FILTER_BITS")) { int v = atoi(e); if (v >= 0 && v <= 64) c->filter_bits = v; }
         if (const char* e = getenv("MBL_MERGE_THREADS")) { int v = atoi(e); if (v == 256 || v == 512) c->merge_threads = v; }
         if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }

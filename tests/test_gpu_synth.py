@@ -139,3 +139,25 @@ def test_streaming_prefetch_equals_batch_calls():
         assert sum(int(r["is_classified"].sum()) for r, _ in got) > 500
     finally:
         clf.close()
+
+
+def test_very_long_ragged_reads_vs_oracle():
+    """BASELINE configs[3]/[4] shape in miniature: ragged long reads up to 50 kbp (seq-mode 3, denominator 1000), 8 % substitutions,
+    some Ns — the CUDA path against the oracle on every read (positions beyond 2^15, thousands of windows per frame)."""
+    from metabuli_b200 import Classifier, ClassifyOptions, synth
+    sdb = synth.make_db(genera=3, species_per_genus=3, strains_per_species=2, codons=20000, seed=41)
+    reads = synth.make_reads(sdb, 48, 50000, seed=42, sub_rate=0.08, n_rate=0.0005, length_jitter=47000)
+    odb = oracle.OracleDb.from_synth(sdb)
+    clf = Classifier(None, ClassifyOptions(seq_mode=3), database=sdb.database)
+    try:
+        res, pairs = clf.classify_batch(*reads)
+        _, ores, nk, nm = odb.classify_arrays(*reads, seq_mode=3, threads=2)
+        st = clf.stats()
+        assert st["n_matches"] == nm and nm > 10000
+        for f in ("classification", "query_length", "taxcnt_len", "is_classified"):
+            assert np.array_equal(res[f], ores[f]), f
+        assert np.array_equal(res["score"].view(np.uint32), ores["score"].view(np.uint32))
+        assert int(res["is_classified"].sum()) > 20
+    finally:
+        clf.close()
+        odb.close()

@@ -20,7 +20,7 @@ G = os.path.join(ROOT, "gpurun_out")
 
 
 def short(name):
-    name = name.replace("(anonymous namespace)::", "").replace("void ", "")
+    name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", "")
     name = re.sub(r"\(.*", "", name)
     name = re.sub(r"<.*", "", name)
     return name.split("::")[-1][:60]
