@@ -65,12 +65,12 @@ __global__ void read_meta_kernel(const uint64_t* __restrict__ off1, const uint64
     quot_cnt[r] = ql + 3 > 0 ? (uint32_t)((ql + 3) / 3 + 1) : 1u;
 }
 
-// probe of the amino-acid presence filter (mbl_common.cuh): both bits live in one 32-byte sector
+// probe of the amino-acid presence filter (mbl_common.cuh): both bits live in one 128-byte line
 __device__ __forceinline__ bool aa_filter_pass(const AaFilter& f, uint64_t value) {
     const uint64_t h = aa_filter_hash(value);
-    const uint32_t* blk = f.words + (size_t)aa_filter_block(h, f.n_blocks) * 8;
+    const uint32_t* line = f.words + (size_t)aa_filter_line(value, h, f.n_lines, f.minimizer) * 32;
     const uint32_t b1 = aa_filter_bit1(h), b2 = aa_filter_bit2(h);
-    const uint32_t w1 = __ldg(blk + (b1 >> 5)), w2 = __ldg(blk + (b2 >> 5));
+    const uint32_t w1 = __ldg(line + (b1 >> 5)), w2 = __ldg(line + (b2 >> 5));
     return ((w1 >> (b1 & 31)) & (w2 >> (b2 & 31)) & 1u) != 0u;
 }
 

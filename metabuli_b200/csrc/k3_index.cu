@@ -55,17 +55,17 @@ cell_boundary_kernel(const uint16_t* __restrict__ diff, uint64_t n_u16, uint64_t
     }
 }
 
-// amino-acid presence filter: two bits per k-mer in the 256-bit block its amino-acid part hashes to
+// amino-acid presence filter: two bits per amino-acid group in the 1024-bit line it maps to (mbl_common.cuh)
 __global__ void __launch_bounds__(kWarps * 32)
 filter_build_kernel(const uint16_t* __restrict__ diff, uint64_t n_u16, uint64_t n_cells, const uint64_t* __restrict__ cell_k,
-                    const uint64_t* __restrict__ cell_v, uint32_t* __restrict__ words, uint32_t n_blocks) {
+                    const uint64_t* __restrict__ cell_v, uint32_t* __restrict__ words, uint32_t n_lines, int minimizer) {
     for (uint64_t c = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); c < n_cells; c += (uint64_t)gridDim.x * kWarps) {
         long long s = (long long)(c * kCellU16), e = (long long)min((c + 1) * (uint64_t)kCellU16, n_u16);
         uint64_t v = cell_v[c], k = cell_k[c];
         warp_decode(diff, 0, s, e, v, k, [&](uint64_t kk, uint64_t val, uint64_t delta, long long) {
             if (kk != 0 && aa_part(val) == aa_part(val - delta)) return;           // same group as its predecessor: bits are set
             const uint64_t h = aa_filter_hash(val);
-            uint32_t* blk = words + (size_t)aa_filter_block(h, n_blocks) * 8;
+            uint32_t* blk = words + (size_t)aa_filter_line(val, h, n_lines, minimizer) * 32;
             const uint32_t b1 = aa_filter_bit1(h), b2 = aa_filter_bit2(h);
             atomicOr(blk + (b1 >> 5), 1u << (b1 & 31));
             atomicOr(blk + (b2 >> 5), 1u << (b2 & 31));
@@ -168,7 +168,7 @@ namespace { struct AddU64 { __host__ __device__ uint64_t operator()(uint64_t a, 
 // shard that starts inside the file, mbl_plan_shards); holds_db_tail: the stream ends with the numerically last k-mer of the DB (Q1)
 void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
                           cudaStream_t st, TileDirectory& dir, uint64_t base_value, bool holds_db_tail, int filter_bits_per_kmer,
-                          uint64_t filter_total_kmers) {
+                          uint64_t filter_total_kmers, int filter_minimizer) {
     dir = TileDirectory();
     if (tile_cells < 1) tile_cells = 1;
     dir.tile_cells = tile_cells;
@@ -206,11 +206,13 @@ void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kme
     cell_boundary_kernel<<<blocks, kWarps * 32, 0, st>>>(d_diff, n_u16, n_cells, dir.cell_k, dir.cell_v, b_kidx, b_off, b_base, b_aa);
     if (filter_bits_per_kmer > 0) {
         // a shard sizes its filter for the whole index: the ranks OR their filters together (mbl_shard_filter_or)
-        const uint64_t want = (std::max(n_kmers, filter_total_kmers) * (uint64_t)filter_bits_per_kmer + 255) / 256 + 1;
-        dir.filter_blocks = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull);
-        MBL_CUDA(cudaMalloc(&dir.filter, 32 * (size_t)dir.filter_blocks));
-        MBL_CUDA(cudaMemsetAsync(dir.filter, 0, 32 * (size_t)dir.filter_blocks, st));
-        filter_build_kernel<<<blocks, kWarps * 32, 0, st>>>(d_diff, n_u16, n_cells, dir.cell_k, dir.cell_v, dir.filter, dir.filter_blocks);
+        const uint64_t want = (std::max(n_kmers, filter_total_kmers) * (uint64_t)filter_bits_per_kmer + 1023) / 1024 + 1;
+        dir.filter_lines = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull);
+        dir.filter_minimizer = filter_minimizer;
+        MBL_CUDA(cudaMalloc(&dir.filter, 128 * (size_t)dir.filter_lines));
+        MBL_CUDA(cudaMemsetAsync(dir.filter, 0, 128 * (size_t)dir.filter_lines, st));
+        filter_build_kernel<<<blocks, kWarps * 32, 0, st>>>(d_diff, n_u16, n_cells, dir.cell_k, dir.cell_v, dir.filter, dir.filter_lines,
+                                                            filter_minimizer);
     }
     tile_candidate_kernel<<<(unsigned)((n_grid + 255) / 256), 256, 0, st>>>(b_kidx, n_cells, n_grid, tile_cells, cand);
     MBL_CUDA(cudaMemsetAsync(flag, 0, 4 * (n_grid + 1), st));

@@ -21,7 +21,8 @@ struct TileDirectory {
     int sort_begin_bit = 24;
     uint64_t n_kmers_decoded = 0;   // number of end flags in the stream (must equal the info count)
     uint32_t* filter = nullptr;     // amino-acid presence filter over every k-mer of the stream (AaFilter), or null
-    uint32_t filter_blocks = 0;
+    uint32_t filter_lines = 0;      // 128-byte lines
+    int filter_minimizer = 0;
 };
 
 struct DeviceTaxonomy {             // reference arrays as stored in taxonomyDB
@@ -81,7 +82,7 @@ void launch_segments(const mbl_match_rec* sorted, size_t n, uint32_t n_reads, ui
 // filter_bits_per_kmer > 0: also build the amino-acid presence filter (about that many bits per k-mer of the stream)
 void build_tile_directory(const uint16_t* d_diff, uint64_t n_u16, uint64_t n_kmers, int sm_count, uint32_t tile_cells,
                           cudaStream_t st, TileDirectory& dir, uint64_t base_value = 0, bool holds_db_tail = true,
-                          int filter_bits_per_kmer = 0, uint64_t filter_total_kmers = 0);
+                          int filter_bits_per_kmer = 0, uint64_t filter_total_kmers = 0, int filter_minimizer = 0);
 // words |= other (merging the shards' presence filters)
 void launch_filter_or(uint32_t* words, const uint32_t* other, uint64_t n_words, cudaStream_t st);
 void free_tile_directory(TileDirectory& dir);

@@ -51,6 +51,7 @@ struct mbl_ctx {
     uint8_t* d_ham_single = nullptr;
     uint32_t tile_cells = 2;            // MBL_TILE_CELLS (measured best on the 8 GiB benchmark index: 3 CTAs per SM)
     int dyn_chunks = 0;                 // MBL_DYN_CHUNKS (measured: no gain over fixed striding)
+    int filter_minimizer = 1;           // MBL_FILTER_MINIMIZER=0: filter line from the whole amino-acid part instead of its minimizer
     int filter_bits = 16;               // MBL_FILTER_BITS: bits per index k-mer of the amino-acid presence filter, 0 = no filter
     uint64_t arena_S8 = 0;              // slot stride of the phase-1 arena layout (set by whoever fills it)
     int merge_threads = 256;            // MBL_MERGE_THREADS: 256 (3 CTAs per SM) or 512 (2 CTAs per SM, 32 warps)
@@ -307,7 +308,7 @@ void stage_extract(mbl_ctx* c, const SubBatch& sb, bool use_filter, uint64_t fil
         uint64_t *va = ar, *qa = ar + 2 * S8;
         uint32_t* ia = reinterpret_cast<uint32_t*>(ar + 3 * S8);
         AaFilter flt;
-        if (use_filter) { flt.words = c->dir.filter; flt.n_blocks = c->dir.filter_blocks; }
+        if (use_filter) { flt.words = c->dir.filter; flt.n_lines = c->dir.filter_lines; flt.minimizer = c->dir.filter_minimizer; }
         launch_extract(c->cfg.kmer_format, bases1, off1, bases2, off2, n, cov1, w1, w2, slot_off, c->d_base_code, c->d_codon,
                        va, qa, ia, counters, c->sm_count, st, flt, counters + 4, S8);
         c->stats.kernel_launches += 2;
@@ -609,6 +610,7 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
             int v = atoi(e);
             if (v == 32 || v == 64 || v == 128) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v); cudaGetLastError(); }
         }
+        if (const char* e = getenv("MBL_FILTER_MINIMIZER")) c->filter_minimizer = atoi(e) != 0;
         if (const char* e = getenv("MBL_FILTER_BITS")) { int v = atoi(e); if (v >= 0 && v <= 64) c->filter_bits = v; }
         if (const char* e = getenv("MBL_MERGE_THREADS")) { int v = atoi(e); if (v == 256 || v == 512) c->merge_threads = v; }
         if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }
@@ -658,7 +660,7 @@ mbl_ctx* ensure_shadow(mbl_ctx* c) {
     }
     mbl_ctx* s = c->shadow;
     s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
-    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->filter_bits = c->filter_bits;
+    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
     s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
     s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded; s->filter_complete = c->filter_complete;
     s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed
@@ -717,7 +719,7 @@ int load_db_range(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx, const mb
         // the presence filter must cover every k-mer a query could match: a shard builds its part, sized for the whole index, and
         // the filter is only used once the ranks have OR-ed their parts together (mbl_shard_filter / mbl_shard_filter_or)
         build_tile_directory(c->d_diff, c->n_u16, c->n_kmers, c->sm_count, c->tile_cells, c->st, c->dir, sh.base_value, sh.holds_db_tail != 0,
-                             c->filter_bits, db->n_kmers);
+                             c->filter_bits, db->n_kmers, c->cfg.kmer_format == 2 && c->filter_minimizer);
         c->filter_complete = !is_shard;
         if (c->force_sort_bit) c->dir.sort_begin_bit = c->force_sort_bit;
         // the k-mer count implied by the end flags must agree with the info file
@@ -729,7 +731,7 @@ int load_db_range(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx, const mb
             return fail(c, MBL_E_BAD_DB, msg);
         }
         c->db_bytes = 2 * c->n_u16 + 4 * c->n_kmers + sizeof(Tile) * c->dir.n_tiles + 16 * c->dir.n_cells + 8 * c->dir.n_jumbo_kmers +
-                      32 * (size_t)c->dir.filter_blocks;
+                      128 * (size_t)c->dir.filter_lines;
         c->db_loaded = true;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
@@ -1043,14 +1045,14 @@ int mbl_classify_prefetched(mbl_ctx* c, const mbl_batch* next, mbl_read_result* 
 int mbl_shard_filter(mbl_ctx* c, void** d_words, uint64_t* n_bytes) {
     if (!c || !d_words || !n_bytes) return fail(c, MBL_E_BAD_ARG, "null argument");
     *d_words = c->dir.filter;
-    *n_bytes = 32ull * c->dir.filter_blocks;
+    *n_bytes = 128ull * c->dir.filter_lines;
     return MBL_OK;
 }
 
 int mbl_shard_filter_or(mbl_ctx* c, const void* d_other, uint64_t n_bytes, int complete) {
     if (!c) return MBL_E_BAD_ARG;
     if (!c->dir.filter) { c->filter_complete = false; return MBL_OK; }          // MBL_FILTER_BITS=0
-    if (d_other && n_bytes != 32ull * c->dir.filter_blocks) return fail(c, MBL_E_BAD_ARG, "filter sizes differ between the ranks");
+    if (d_other && n_bytes != 128ull * c->dir.filter_lines) return fail(c, MBL_E_BAD_ARG, "filter sizes differ between the ranks");
     try {
         MBL_CUDA(cudaSetDevice(c->cfg.device));
         if (d_other) launch_filter_or(c->dir.filter, (const uint32_t*)d_other, n_bytes / 4, c->st);

@@ -26,21 +26,42 @@ MBL_HD uint32_t qi_seq(uint64_t q) { return (uint32_t)((q >> 32) & 0x1FFFFFFFu);
 MBL_HD uint32_t qi_frame(uint64_t q) { return (uint32_t)(q >> 61); }
 
 // ---- amino-acid presence filter (k3_index.cu builds it, K1 probes it) ---------------------------------
-// Blocked Bloom filter over the 40-bit amino-acid parts of the index: a 256-bit block (one 32-byte sector) per key, two bits
-// inside it.  A query whose amino-acid part is not in the filter cannot have a candidate (KmerMatcher.cpp:363-375 would skip
-// it), so K1 drops it before the sort; false positives only cost work.
+// Blocked Bloom filter over the 40-bit amino-acid parts of the index: one 128-byte line per key (what one DRAM access brings
+// in anyway — ncu shows 126 bytes of DRAM traffic per random 32-byte probe), two bits inside it.  A query whose amino-acid part
+// is not in the filter cannot have a candidate (KmerMatcher.cpp:363-375 would skip it), so K1 drops it before the sort; false
+// positives only cost work.
+// Line choice (format-2 k-mers: eight 5-bit residues): by the MINIMIZER of the 8-mer — the smallest hash among its three
+// 6-residue sub-words.  Consecutive windows of a frame share seven residues and, about half of the time, the minimizer, so
+// the ~10 windows per frame a K1 warp handles at once fall into ~5 lines instead of 10: fewer DRAM lines per read.  Format-1
+// k-mers (base-21 amino-acid part) hash the whole part.
 struct AaFilter {
-    const uint32_t* words = nullptr;   // n_blocks x 8 words
-    uint32_t n_blocks = 0;
+    const uint32_t* words = nullptr;   // n_lines x 32 words
+    uint32_t n_lines = 0;
+    int minimizer = 0;                 // 1: line from the 6-residue minimizer (kmer_format 2)
 };
+MBL_HD uint32_t aa_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
 MBL_HD uint64_t aa_filter_hash(uint64_t value) {
     uint64_t h = (value >> 24) * 0x9E3779B97F4A7C15ull;
     h ^= h >> 32;
     return h * 0xD6E8FEB86659FD93ull;
 }
-MBL_HD uint32_t aa_filter_block(uint64_t h, uint32_t n_blocks) { return (uint32_t)(((h >> 32) * (uint64_t)n_blocks) >> 32); }
-MBL_HD uint32_t aa_filter_bit1(uint64_t h) { return (uint32_t)(h >> 8) & 255u; }
-MBL_HD uint32_t aa_filter_bit2(uint64_t h) { return (uint32_t)(h >> 20) & 255u; }
+// line of a k-mer value; h = aa_filter_hash(value)
+MBL_HD uint32_t aa_filter_line(uint64_t value, uint64_t h, uint32_t n_lines, int minimizer) {
+    uint32_t key = (uint32_t)(h >> 32);
+    if (minimizer) {
+        const uint64_t aa = value >> 24;
+        const uint32_t m0 = aa_mix32((uint32_t)(aa >> 10) & 0x3FFFFFFFu), m1 = aa_mix32((uint32_t)(aa >> 5) & 0x3FFFFFFFu),
+                       m2 = aa_mix32((uint32_t)aa & 0x3FFFFFFFu);
+        key = m0 < m1 ? (m0 < m2 ? m0 : m2) : (m1 < m2 ? m1 : m2);
+    }
+    return (uint32_t)(((uint64_t)key * (uint64_t)n_lines) >> 32);
+}
+// both bits sit in the same 32-byte sector of the line (bits 8-9 pick the sector), so a probe is one sector request
+MBL_HD uint32_t aa_filter_bit1(uint64_t h) { return ((uint32_t)(h >> 8) & 0x300u) | ((uint32_t)(h >> 12) & 255u); }
+MBL_HD uint32_t aa_filter_bit2(uint64_t h) { return ((uint32_t)(h >> 8) & 0x300u) | ((uint32_t)(h >> 22) & 255u); }
 
 // LocalUtil.h:46-60
 MBL_HD int max_covered_length(int len) {
