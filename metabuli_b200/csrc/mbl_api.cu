@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -112,6 +114,7 @@ struct mbl_ctx {
     // scoring kernels of one sub-batch overlap the bandwidth-bound sorts of the other.
     mbl_ctx* shadow = nullptr;
     bool is_shadow = false;
+    int pipeline_parts = 2;             // MBL_PIPELINE_PARTS: sub-batches a large batch is cut into when the lanes are on
     int pipeline = 0;                   // MBL_PIPELINE=1 switches the second lane on (measured slower: the lanes contend and the index is streamed twice)
     uint32_t pipeline_min_reads = 1u << 21;   // MBL_PIPELINE_MIN_READS: smaller batches stay on one lane
     double match_ratio = 0.0;   // matches per slot seen so far (sizes the match buffer)
@@ -194,7 +197,8 @@ void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots, std::v
     // still on their way to the device)
     const uint32_t n = b->n_reads;
     const bool may_split = c->pipeline && n >= c->pipeline_min_reads && n >= 16;
-    const unsigned T = (n > (1u << 18) || may_split) ? 8u : 1u;
+    const unsigned P = may_split ? (unsigned)std::max(2, c->pipeline_parts) : 1u;       // sub-batches of a split batch
+    const unsigned T = may_split ? P * ((8u + P - 1) / P) : (n > (1u << 18) ? 8u : 1u);
     std::vector<SubBatch> part(T, SubBatch{0, 0, 0, 0, 0});
     auto work = [&](unsigned t) {
         const uint32_t r0 = (uint32_t)((uint64_t)n * t / T), r1 = (uint32_t)((uint64_t)n * (t + 1) / T);
@@ -222,15 +226,17 @@ void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots, std::v
     const bool split = may_split;
     if (!split && all.slots <= max_slots && all.quots <= 0xF0000000ull) { subs.push_back(all); return; }
     if (split) {
-        max_slots /= 2;
-        SubBatch h[2] = {SubBatch{0, 0, 0, 0, 0}, SubBatch{0, 0, 0, 0, 0}};
+        max_slots /= 2;                                   // two lanes share the workspace budget
+        std::vector<SubBatch> h(P, SubBatch{0, 0, 0, 0, 0});
+        bool fits = true;
         for (unsigned t = 0; t < T; ++t) {
-            SubBatch& d = h[t >= T / 2];
+            SubBatch& d = h[t / (T / P)];
             if (d.r1 == d.r0) d.r0 = part[t].r0;
             d.r1 = part[t].r1; d.slots += part[t].slots; d.quots += part[t].quots; d.max_pos = std::max(d.max_pos, part[t].max_pos);
         }
-        if (h[0].slots <= max_slots && h[1].slots <= max_slots && h[0].quots <= 0xF0000000ull && h[1].quots <= 0xF0000000ull) {
-            subs.push_back(h[0]); subs.push_back(h[1]);
+        for (const SubBatch& d : h) fits = fits && d.slots <= max_slots && d.quots <= 0xF0000000ull;
+        if (fits) {
+            for (const SubBatch& d : h) if (d.r1 > d.r0) subs.push_back(d);
             return;
         }
     }
@@ -556,7 +562,8 @@ int extract_filtered(mbl_ctx* c, const SubBatch& sb, uint64_t* n_slots_used) {
     return MBL_OK;
 }
 
-int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
+// front half of a sub-batch: K1 (+ presence filter), K2, K3 -> rows in m_raw
+int sub_front(mbl_ctx* c, const SubBatch& sb, uint64_t* reserved_out) {
     const bool filtered = c->dir.filter != nullptr && c->filter_complete;
     uint64_t n_sort = sb.slots;
     if (filtered) {
@@ -565,12 +572,20 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
     } else {
         stage_extract(c, sb, false);
     }
-    uint64_t reserved = 0, n_match = 0;
+    uint64_t n_match = 0;
     const uint64_t nq_before = c->stats.n_merge_queries;
-    int rc = stage_sort_merge(c, n_sort, sb.slots, &c->match_ratio, (const uint64_t*)c->arena.p + 2 * c->arena_S8, true, &reserved, &n_match);
+    int rc = stage_sort_merge(c, n_sort, sb.slots, &c->match_ratio, (const uint64_t*)c->arena.p + 2 * c->arena_S8, true, reserved_out, &n_match);
     if (!filtered) c->stats.n_query_kmers += c->stats.n_merge_queries - nq_before;
+    return rc;
+}
+// back half: K4, K5
+int sub_back(mbl_ctx* c, const SubBatch& sb, uint64_t reserved) { return stage_sort_score(c, sb, reserved); }
+
+int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
+    uint64_t reserved = 0;
+    int rc = sub_front(c, sb, &reserved);
     if (rc != MBL_OK) return rc;
-    return stage_sort_score(c, sb, reserved);
+    return sub_back(c, sb, reserved);
 }
 
 }  // namespace
@@ -603,7 +618,8 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         c->d_ham_pair = upload(c, t.ham_pair, 4096);
         c->d_ham_single = upload(c, t.ham_sum, 64);
         if (const char* e = getenv("MBL_DYN_CHUNKS")) c->dyn_chunks = atoi(e) != 0;
-        if (const char* e = getenv("MBL_PIPELINE")) c->pipeline = atoi(e) != 0;
+        if (const char* e = getenv("MBL_PIPELINE")) { int v = atoi(e); c->pipeline = v < 0 ? 0 : (v > 2 ? 2 : v); }
+        if (const char* e = getenv("MBL_PIPELINE_PARTS")) { int v = atoi(e); if (v >= 2 && v <= 16) c->pipeline_parts = v; }
         // L2 fetch granularity on a DRAM miss (32, 64 or 128 bytes; the default fetches 128): the presence-filter probes of K1 and
         // the qinfo gathers of K3 are random 32-byte sector reads, and ncu shows 126 bytes of DRAM traffic per probe with the default
         if (const char* e = getenv("MBL_L2_FETCH")) {
@@ -887,10 +903,57 @@ int mbl_classify_resident(mbl_ctx* c) {
         struct SubDone { int lane; uint64_t lane_off, count; };
         std::vector<SubDone> done(c->subs.size(), SubDone{0, 0, 0});
         const bool two = c->pipeline && c->subs.size() >= 2;
+        const bool staggered = two && c->pipeline == 2;
         mbl_ctx* s = two ? ensure_shadow(c) : nullptr;
         int rc1 = MBL_OK;
         std::thread lane1;
-        if (two) {
+        if (staggered) {
+            // Sub-batch k runs on lane k & 1.  One thread walks the FRONT halves (K1-K3: DRAM- and issue-bound), this thread the
+            // BACK halves (K4-K5: radix passes and latency-bound scoring), so back(k) overlaps front(k+1) on the other lane's
+            // stream; front(k+2) waits for back(k) because it reuses that lane's workspace.
+            mbl_ctx* lanes[2] = {c, s};
+            const size_t n = c->subs.size();
+            std::vector<uint64_t> reserved(n, 0);
+            std::vector<char> fdone(n, 0), bdone(n, 0);
+            std::mutex mu;
+            std::condition_variable cv;
+            bool stop = false;
+            lane1 = std::thread([&] {
+                cudaSetDevice(c->cfg.device);
+                for (size_t k = 0; k < n; ++k) {
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return stop || k < 2 || bdone[k - 2]; });
+                        if (stop) return;
+                    }
+                    int rc = MBL_OK;
+                    try { rc = sub_front(lanes[k & 1], c->subs[k], &reserved[k]); } catch (const CudaError& e) { rc = fail_cuda(lanes[k & 1], e); }
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (rc != MBL_OK) { rc1 = rc; c->err = lanes[k & 1]->err; stop = true; cv.notify_all(); return; }
+                    fdone[k] = 1;
+                    cv.notify_all();
+                }
+            });
+            int rcb = MBL_OK;
+            for (size_t k = 0; k < n; ++k) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return stop || fdone[k]; });
+                    if (stop) break;
+                }
+                mbl_ctx* L = lanes[k & 1];
+                const uint64_t off = L->n_pairs;
+                try { rcb = sub_back(L, c->subs[k], reserved[k]); } catch (const CudaError& e) { rcb = fail_cuda(L, e); }
+                std::lock_guard<std::mutex> lk(mu);
+                if (rcb != MBL_OK) { if (L != c) c->err = L->err; stop = true; cv.notify_all(); break; }
+                done[k] = SubDone{(int)(k & 1), off, L->n_pairs - off};
+                bdone[k] = 1;
+                cv.notify_all();
+            }
+            lane1.join();
+            if (rcb != MBL_OK) return rcb;
+            if (rc1 != MBL_OK) return rc1;
+        } else if (two) {
             lane1 = std::thread([&] {
                 cudaSetDevice(c->cfg.device);
                 try {
@@ -906,7 +969,7 @@ int mbl_classify_resident(mbl_ctx* c) {
             });
         }
         int rc0 = MBL_OK;
-        try {
+        if (!staggered) try {
             for (size_t k = 0; k < c->subs.size(); k += two ? 2 : 1) {
                 const uint64_t off = c->n_pairs;
                 rc0 = run_sub_batch(c, c->subs[k]);
@@ -916,7 +979,7 @@ int mbl_classify_resident(mbl_ctx* c) {
         } catch (const CudaError& e) {
             rc0 = fail_cuda(c, e);
         }
-        if (two) lane1.join();
+        if (two && !staggered) lane1.join();
         if (rc0 != MBL_OK) return rc0;
         if (rc1 != MBL_OK) { c->err = s->err; return rc1; }
         c->pairs_out = c->pairs.p;

@@ -99,19 +99,23 @@ def test_query_sort_granularity(sort_bit, golden_dir, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["multi_se", "multi_pe", "ragged_se"])
-def test_two_lane_pipeline(name, golden_dir, monkeypatch):
-    """Large batches are cut in two and run on two pipeline lanes (two host threads, two streams, shared index); forcing
-    that path on a small batch must still give the reference's TSV, including the per-read (taxid, count) lists."""
+@pytest.mark.parametrize("name,mode,parts", [("multi_se", 1, 2), ("multi_pe", 1, 2), ("ragged_se", 1, 2), ("multi_se", 2, 2), ("multi_pe", 2, 3),
+                                             ("ragged_se", 2, 5), ("format1_pe", 2, 4)])
+def test_two_lane_pipeline(name, mode, parts, golden_dir, monkeypatch):
+    """Large batches are cut into sub-batches that run on two pipeline lanes (two host threads, two streams, shared index):
+    mode 1 = the lanes take alternate sub-batches whole, mode 2 = staggered (the back half K4-K5 of sub-batch k overlaps the
+    front half K1-K3 of sub-batch k+1).  Forcing those paths on a small batch must still give the reference's TSV, including
+    the per-read (taxid, count) lists."""
     from metabuli_b200 import Classifier, ClassifyOptions
-    monkeypatch.setenv("MBL_PIPELINE", "1")            # off by default (profiles/r01_v10_config_sweep.md)
+    monkeypatch.setenv("MBL_PIPELINE", str(mode))      # off by default (profiles/r01_v10_config_sweep.md)
+    monkeypatch.setenv("MBL_PIPELINE_PARTS", str(parts))
     monkeypatch.setenv("MBL_PIPELINE_MIN_READS", "64")
     sdb, reads, seq_mode = synth_cases.build(name)
     clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
     try:
         for _ in range(2):          # second call reuses both workspaces
             res, pairs = clf.classify_batch(*reads)
-            assert clf.stats()["sub_batches"] == 2
+            assert clf.stats()["sub_batches"] == parts
             tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
             assert tsv == gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
     finally:
