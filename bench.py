@@ -387,6 +387,8 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"{n_reads} synthetic {args.read_len} bp SE reads per GPU per step vs {winfo['index_gib']} GiB synthetic "
                                    f"index replicated per GPU (BASELINE configs[1])", "l2": "inputs_exceed_l2",
+                       "timing": "host clock between device-synchronised points (every library call ends with a synchronise of its own "
+                                 "stream; stage and merge-kernel times are CUDA events on that stream), max over ranks",
                        "parallelism": f"replica x{world}: reads sharded, index replicated, no data-path collective", **winfo,
                        "query_kmers_per_step": last["n_query_kmers"], "merge_queries_per_step": last["n_merge_queries"],
                        "presence_filter": last["n_merge_queries"] < last["n_query_kmers"], "matches_per_step": last["n_matches"],
