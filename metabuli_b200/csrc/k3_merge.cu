@@ -575,12 +575,9 @@ void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
 
 template <int kThreads>
 static void launch_merge_t(const MergeArgs& a, int sm_count, cudaStream_t st) {
-    static size_t attr_smem = 0;
     const size_t smem = smem_layout(a.max_u16, a.max_kmers, a.n_buckets, kThreads / 32).total;
-    if (attr_smem != smem) {
-        MBL_CUDA(cudaFuncSetAttribute(merge_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    // set on every launch (microseconds): two pipeline lanes may launch from two host threads
+    MBL_CUDA(cudaFuncSetAttribute(merge_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel<kThreads>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
