@@ -217,9 +217,11 @@ class SynthDb:
             f.write(self.taxonomy_blob)
         with open(os.path.join(path, "taxID_list"), "w") as f:
             f.write("".join(f"{int(t)}\n" for t in self.taxid_list))
+        p = self.database.params
         with open(os.path.join(path, "db.parameters"), "w") as f:
             f.write("DB_name\tsynthetic\nCreation_date\t2026-1-1\nReduced_alphabet\t0\nAccession_level\t0\nMask_mode\t0\n"
-                    "Mask_prob\t0.900000\nSkip_redundancy\t1\nSyncmer\t0\nKmer_format\t%d\n" % self.database.params.kmer_format)
+                    "Mask_prob\t0.900000\nSkip_redundancy\t1\nSyncmer\t%d\n%sKmer_format\t%d\n"
+                    % (p.syncmer, ("S-mer_len\t%d\n" % p.smer_len) if p.syncmer else "", p.kmer_format))    # IndexCreator.cpp:1258-1270
 
 
 def encode_index(values_i64: torch.Tensor, split_num: int = 4096):
@@ -269,7 +271,24 @@ def encode_index(values_i64: torch.Tensor, split_num: int = 4096):
     return diff, split
 
 
-def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, chunk_rows: int = 4096, kmer_format: int = 2) -> SynthDb:
+def syncmer_mask(values_i64: torch.Tensor, smer_len: int) -> torch.Tensor:
+    """Closed-syncmer predicate of format-2 metamers (SyncmerScanner.h:36-74): the smallest of the 8 - s + 1 s-mers of the
+    8-residue window (leftmost on ties) sits at the first or at the last s-mer position."""
+    aa = (values_i64 >> 24) & ((1 << 40) - 1)
+    n = 8 - smer_len + 1
+    mask = (1 << (5 * smer_len)) - 1
+    sm = [(aa >> (5 * (n - 1 - j))) & mask for j in range(n)]
+    first = torch.ones_like(aa, dtype=torch.bool)
+    for j in range(1, n):
+        first &= sm[0] <= sm[j]
+    last = torch.ones_like(aa, dtype=torch.bool)
+    for j in range(n - 1):
+        last &= sm[n - 1] < sm[j]
+    return first | last
+
+
+def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, chunk_rows: int = 4096, kmer_format: int = 2,
+             syncmer: int = 0, smer_len: int = 5) -> SynthDb:
     dev = genomes.device
     strain_t = torch.as_tensor(tx.strain_ids.astype(np.int64), device=dev)
     species_t = torch.as_tensor(tx.species_of_strain.astype(np.int64), device=dev)
@@ -277,9 +296,15 @@ def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, ch
     for r0 in range(0, genomes.shape[0], chunk_rows):
         g = genomes[r0:r0 + chunk_rows]
         v = _metamers(g, kmer_format)
+        t_ = strain_t[r0:r0 + chunk_rows, None].expand_as(v)
+        s_ = species_t[r0:r0 + chunk_rows, None].expand_as(v)
+        if syncmer:                                  # IndexCreator.cpp:940 / 1052: the index holds syncmers only
+            keep = syncmer_mask(v, smer_len)
+            vals.append(v[keep]); tids.append(t_[keep]); sps.append(s_[keep])
+            continue
         vals.append(v.flatten())
-        tids.append(strain_t[r0:r0 + chunk_rows, None].expand_as(v).flatten())
-        sps.append(species_t[r0:r0 + chunk_rows, None].expand_as(v).flatten())
+        tids.append(t_.flatten())
+        sps.append(s_.flatten())
     val = torch.cat(vals); tid = torch.cat(tids); sp = torch.cat(sps)
     del vals, tids, sps
     # order by (value unsigned, species, taxid): three stable sorts, least significant key first
@@ -309,16 +334,16 @@ def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, ch
     taxdb = TaxonomyDB(tmp)
     os.remove(tmp)
     taxid_list = np.concatenate([tx.strain_ids, tx.species_ids]).astype(np.int32)
-    params = DbParameters(kmer_format=kmer_format, skip_redundancy=1)
+    params = DbParameters(kmer_format=kmer_format, skip_redundancy=1, syncmer=1 if syncmer else 0, smer_len=smer_len)
     db = Database(params, diff, info.cpu().numpy(), split, taxdb, taxdb.build_taxid2species(taxid_list))
     return SynthDb(db, tx, genomes, blob, taxid_list)
 
 
 def make_db(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, species_div=0.12, strain_div=0.01, seed=3,
-            eukaryote_genera=0, device="cpu", split_num=4096, kmer_format=2) -> SynthDb:
+            eukaryote_genera=0, device="cpu", split_num=4096, kmer_format=2, syncmer=0, smer_len=5) -> SynthDb:
     tx = make_taxonomy(genera, species_per_genus, strains_per_species, eukaryote_genera)
     genomes = make_genomes(tx, codons, species_div, strain_div, seed, device)
-    return build_db(tx, genomes, split_num, kmer_format=kmer_format)
+    return build_db(tx, genomes, split_num, kmer_format=kmer_format, syncmer=syncmer, smer_len=smer_len)
 
 
 # ---- reads ---------------------------------------------------------------------------------------------------------

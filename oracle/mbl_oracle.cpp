@@ -176,6 +176,65 @@ struct Scanner {
         return false;
     }
     int nq = 0;
+
+    // ---- SyncmerScanner (SyncmerScanner.h:9-103): format-2 metamers whose smallest s-mer (s residues, leftmost on ties)
+    // sits at the first or the last s-mer position of the 8-residue window ("closed syncmers")
+    int smerLen = 0;                     // 0 = every window (MetamerScanner)
+    struct SmerAt { uint64_t value; int pos; };
+    std::vector<SmerAt> dq;              // monotone deque (front = minimum), SyncmerScanner.h:17
+    size_t dqHead = 0;
+    int smerCnt = 0, loadedChar = 0, prevPos = -8;
+    uint64_t smer = 0;
+    void init_syncmer() { dq.clear(); dqHead = 0; smerCnt = 0; loadedChar = 0; prevPos = -8; smer = 0; }
+    bool next_syncmer(uint64_t &value, uint32_t &pos) {
+        const uint64_t smerMask = (1ull << (5 * smerLen)) - 1;
+        bool found = false;
+        while (posStart <= aaLen - 8 && !found) {
+            bool sawN = false;
+            smerCnt -= (smerCnt > 0);
+            while (smerCnt < 8 - smerLen + 1) {
+                loadedChar -= (loadedChar == smerLen);
+                while (loadedChar < smerLen) {
+                    int aa, id;
+                    codon(posStart + smerCnt + loadedChar, aa, id);
+                    if (aa < 0) { sawN = true; break; }
+                    smer = (smer << 5) | (uint64_t)aa;
+                    ++loadedChar;
+                }
+                if (sawN) break;
+                smer &= smerMask;
+                while (dq.size() > dqHead && dq.back().value > smer) dq.pop_back();
+                dq.push_back(SmerAt{smer, posStart + smerCnt});
+                ++smerCnt;
+            }
+            if (sawN) {                                           // SyncmerScanner.h:62-69
+                posStart += smerCnt + loadedChar + 1;
+                prevPos = posStart - 8;
+                dq.clear(); dqHead = 0;
+                smerCnt = loadedChar = 0;
+                smer = 0;
+                continue;
+            }
+            if (dq.size() > dqHead && dq[dqHead].pos < posStart) ++dqHead;
+            const int anchor1 = posStart, anchor2 = posStart + (8 - smerLen);
+            if (dq.size() > dqHead && (dq[dqHead].pos == anchor1 || dq[dqHead].pos == anchor2)) {
+                const int shifts = posStart - prevPos;
+                for (int i = 0; i < shifts; ++i) {                // SyncmerScanner.h:75-88
+                    int aa, id;
+                    codon(prevPos + 8 + i, aa, id);
+                    aaPart = (aaPart << 5) | (uint64_t)aa;
+                    dnaPart = (dnaPart << 3) | (uint64_t)id;
+                }
+                prevPos = posStart;
+                found = true;
+            }
+            ++posStart;
+        }
+        if (!found) return false;
+        value = (aaPart << 24) | (dnaPart & 0xFFFFFFull);
+        pos = fwd ? (uint32_t)(seqStart + prevPos * 3) : (uint32_t)(seqEnd - (prevPos + 8) * 3 + 1);
+        return true;
+    }
 };
 
 }  // namespace
@@ -190,12 +249,17 @@ static void fill_query_kmers(Scanner &sc, const std::string &seq, Kmer *out, siz
         if (begin < 0) begin += 3;
         sc.init(seq.c_str(), begin, begin + usedLen - 1, fwd);
         uint64_t v; uint32_t p;
+        if (sc.smerLen > 0) {
+            sc.init_syncmer();
+            while (sc.next_syncmer(v, p)) out[w++] = Kmer{v, pack_qinfo(seqId, p + offset, (uint32_t)frame)};
+            continue;
+        }
         while (sc.next(v, p)) out[w++] = Kmer{v, pack_qinfo(seqId, p + offset, (uint32_t)frame)};
     }
 }
 
 void extract_kmers(const std::vector<Read> &m1, const std::vector<Read> *m2, int kmerFormat,
-                   std::vector<QueryInfo> &queries, std::vector<Kmer> &kmers) {
+                   std::vector<QueryInfo> &queries, std::vector<Kmer> &kmers, int syncmer, int smerLen) {
     size_t n = m1.size();
     queries.assign(n, QueryInfo());
     std::vector<uint8_t> empty(n, 0);
@@ -224,7 +288,8 @@ void extract_kmers(const std::vector<Read> &m1, const std::vector<Read> *m2, int
     kmers.assign(total, Kmer{0, 0});                      // Buffer::init memset (common.h:170-175)
 #pragma omp parallel
     {
-        Scanner sc(kmerFormat);
+        Scanner sc(syncmer ? 2 : kmerFormat);            // KmerExtractor.cpp:18-20: SyncmerScanner is a MetamerScanner
+        sc.smerLen = syncmer ? smerLen : 0;
 #pragma omp for schedule(dynamic, 256)
         for (long long ii = 0; ii < (long long)n; ++ii) {
             size_t i = (size_t)ii;
@@ -734,12 +799,13 @@ struct Scorer {
     const Database &db;
     const Options &opt;
     int kmerFormat, denominator;
-    const int maxCodonShift = 1, dnaShift = 3;                         // Taxonomer.cpp:38-42 (no syncmer)
+    int maxCodonShift = 1, dnaShift = 3;                               // Taxonomer.cpp:34-42
     std::vector<Path> paths, combined, local;
     std::vector<uint8_t> connected;
 
     Scorer(const Database &d, const Options &o) : db(d), opt(o) {
         kmerFormat = d.params.kmerFormat;
+        if (d.params.syncmer) { dnaShift = (8 - d.params.smerLen) * 3; maxCodonShift = 8 - d.params.smerLen; }
         denominator = (o.seqMode == 1 || o.seqMode == 2) ? 100 : 1000;  // Taxonomer.cpp:44-48
     }
 
@@ -1035,7 +1101,7 @@ bool classify_files(const std::string &q1, const std::string &q2, const std::str
     }
     std::vector<QueryInfo> queries;
     std::vector<Kmer> kmers;
-    extract_kmers(m1, paired ? &m2 : nullptr, db.params.kmerFormat, queries, kmers);
+    extract_kmers(m1, paired ? &m2 : nullptr, db.params.kmerFormat, queries, kmers, db.params.syncmer, db.params.smerLen);
     sort_kmers(kmers, opt.threads);
     if (nKmers) { size_t b = 0; while (b < kmers.size() && qi_seq(kmers[b].qinfo) == 0) ++b; *nKmers = kmers.size() - b; }
     std::vector<Match> matches;

@@ -128,8 +128,9 @@ int max_covered_length(int len);                               // LocalUtil.h:51
 int query_kmer_number(int len);                                // LocalUtil.h:46-49 (spaceNum 0, k 8)
 // A2/A3/A3': six-frame metamer extraction of one batch.  kmers gets exactly sum(kmerCnt[+kmerCnt2])
 // slots in the reference's reservation order; unused slots are all-zero (seqID 0 == blank).
+// syncmer != 0: only closed syncmers with s = smerLen are emitted (SyncmerScanner.h:9-103; KmerExtractor.cpp:18-20)
 void extract_kmers(const std::vector<Read> &m1, const std::vector<Read> *m2, int kmerFormat,
-                   std::vector<QueryInfo> &queries, std::vector<Kmer> &kmers);
+                   std::vector<QueryInfo> &queries, std::vector<Kmer> &kmers, int syncmer = 0, int smerLen = 5);
 void sort_kmers(std::vector<Kmer> &kmers, int threads);        // A4 (Kmer.h:89-94)
 // A5-A8: linear merge.  Returns false on Q2 (taxid 0 / unmapped species).
 bool match_kmers(const Database &db, const std::vector<Kmer> &sortedKmers, std::vector<Match> &out,

@@ -47,17 +47,28 @@ void* orc_db_from_arrays(const uint16_t* diff, size_t n_u16, const int32_t* info
     return db;
 }
 void orc_db_close(void* db) { delete (Database*)db; }
+// Syncmer / S-mer_len of db.parameters for databases built from arrays (common.cpp:117-125)
+void orc_db_set_syncmer(void* db, int syncmer, int smer_len) { ((Database*)db)->params.syncmer = syncmer; ((Database*)db)->params.smerLen = smer_len; }
+int orc_db_syncmer(void* db) { return ((Database*)db)->params.syncmer ? ((Database*)db)->params.smerLen : 0; }
 int orc_db_kmer_format(void* db) { return ((Database*)db)->params.kmerFormat; }
 
 // A0-A3': returns the number of slots (reference reservation order, blanks all-zero)
+int orc_extract2(const uint8_t* bases1, const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2, uint32_t n,
+                 int kmer_format, int syncmer, int smer_len, uint64_t* value, uint64_t* qinfo, size_t cap, size_t* n_out, int32_t* cov1,
+                 int32_t* cov2);
 int orc_extract(const uint8_t* bases1, const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2, uint32_t n,
                 int kmer_format, uint64_t* value, uint64_t* qinfo, size_t cap, size_t* n_out, int32_t* cov1, int32_t* cov2) {
+    return orc_extract2(bases1, off1, bases2, off2, n, kmer_format, 0, 5, value, qinfo, cap, n_out, cov1, cov2);
+}
+int orc_extract2(const uint8_t* bases1, const uint64_t* off1, const uint8_t* bases2, const uint64_t* off2, uint32_t n,
+                 int kmer_format, int syncmer, int smer_len, uint64_t* value, uint64_t* qinfo, size_t cap, size_t* n_out, int32_t* cov1,
+                 int32_t* cov2) {
     std::vector<Read> m1, m2;
     make_reads(bases1, off1, n, m1);
     if (bases2) make_reads(bases2, off2, n, m2);
     std::vector<QueryInfo> q;
     std::vector<Kmer> k;
-    extract_kmers(m1, bases2 ? &m2 : nullptr, kmer_format, q, k);
+    extract_kmers(m1, bases2 ? &m2 : nullptr, kmer_format, q, k, syncmer, smer_len);
     *n_out = k.size();
     for (uint32_t i = 0; i < n; ++i) { if (cov1) cov1[i] = q[i].queryLength; if (cov2) cov2[i] = q[i].queryLength2; }
     if (k.size() > cap) return 2;
@@ -130,7 +141,7 @@ double orc_classify_arrays(void* dbp, int seq_mode, int threads, const uint8_t* 
     auto t0 = std::chrono::steady_clock::now();
     std::vector<QueryInfo> q;
     std::vector<Kmer> k;
-    extract_kmers(m1, bases2 ? &m2 : nullptr, db.params.kmerFormat, q, k);
+    extract_kmers(m1, bases2 ? &m2 : nullptr, db.params.kmerFormat, q, k, db.params.syncmer, db.params.smerLen);
     sort_kmers(k, threads);
     std::vector<Match> m;
     std::string err;

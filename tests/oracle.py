@@ -33,6 +33,9 @@ def lib():
         L.orc_db_from_arrays.restype = vp
         L.orc_db_kmer_format.argtypes = [vp]
         L.orc_extract.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_int, vp, vp, sz, C.POINTER(sz), vp, vp]
+        L.orc_extract2.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_int, vp, vp, sz, C.POINTER(sz), vp, vp]
+        L.orc_db_set_syncmer.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_db_syncmer.argtypes = [vp]
         L.orc_sort_kmers.argtypes = [vp, vp, sz, C.c_int]
         L.orc_match.argtypes = [vp, vp, vp, sz, vp, sz, C.POINTER(sz), C.c_int]
         L.orc_sort_matches.argtypes = [vp, sz, C.c_int]
@@ -70,6 +73,7 @@ class OracleDb:
             if not self.h:
                 raise RuntimeError(err.value.decode())
         self.kmer_format = lib().orc_db_kmer_format(self.h)
+        self.smer_len = lib().orc_db_syncmer(self.h)            # 0 = not a syncmer database
 
     @classmethod
     def from_synth(cls, sdb):
@@ -83,6 +87,7 @@ class OracleDb:
                                      _p(tl), tl.size, d.params.kmer_format, d.params.skip_redundancy, err, 512)
         if not h:
             raise RuntimeError(err.value.decode())
+        lib().orc_db_set_syncmer(h, int(d.params.syncmer), int(d.params.smer_len))
         return cls(None, handle=h)
 
     def close(self):
@@ -136,7 +141,7 @@ class OracleDb:
         return sec, res, nk.value, nm.value
 
 
-def extract(bases1, off1, bases2=None, off2=None, kmer_format=2):
+def extract(bases1, off1, bases2=None, off2=None, kmer_format=2, syncmer=0, smer_len=5):
     b1 = np.ascontiguousarray(bases1, dtype=np.uint8)
     o1 = np.ascontiguousarray(off1, dtype=np.uint64)
     b2 = np.ascontiguousarray(bases2, dtype=np.uint8) if bases2 is not None else None
@@ -145,11 +150,11 @@ def extract(bases1, off1, bases2=None, off2=None, kmer_format=2):
     cov1 = np.zeros(n, dtype=np.int32)
     cov2 = np.zeros(n, dtype=np.int32)
     cnt = C.c_size_t(0)
-    lib().orc_extract(_p(b1), _p(o1), _p(b2), _p(o2), n, kmer_format, None, None, 0, C.byref(cnt), _p(cov1), _p(cov2))
+    lib().orc_extract2(_p(b1), _p(o1), _p(b2), _p(o2), n, kmer_format, syncmer, smer_len, None, None, 0, C.byref(cnt), _p(cov1), _p(cov2))
     value = np.zeros(cnt.value, dtype=np.uint64)
     qinfo = np.zeros(cnt.value, dtype=np.uint64)
-    rc = lib().orc_extract(_p(b1), _p(o1), _p(b2), _p(o2), n, kmer_format, _p(value), _p(qinfo), cnt.value, C.byref(cnt),
-                           _p(cov1), _p(cov2))
+    rc = lib().orc_extract2(_p(b1), _p(o1), _p(b2), _p(o2), n, kmer_format, syncmer, smer_len, _p(value), _p(qinfo), cnt.value,
+                            C.byref(cnt), _p(cov1), _p(cov2))
     assert rc == 0
     return value, qinfo, cov1, cov2
 

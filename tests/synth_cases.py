@@ -19,6 +19,12 @@ CASES = {
     # format-1 database (OldMetamerScanner: base-21 amino-acid part, reversed codon order)
     "format1_pe": (dict(genera=4, species_per_genus=4, strains_per_species=2, codons=2500, seed=17, species_div=0.05, kmer_format=1),
                    dict(n_reads=3000, length=150, seed=18, n_rate=0.002, sub_rate=0.02, paired=True), 2),
+    # syncmer databases (SyncmerScanner.h: only closed syncmers are indexed and queried; paths may skip up to 8 - s codons;
+    # SURVEY §8f N3 — the reference's current default DB type)
+    "sync_se": (dict(genera=6, species_per_genus=4, strains_per_species=2, codons=3000, seed=23, eukaryote_genera=1, syncmer=1, smer_len=5),
+                dict(n_reads=4000, length=150, seed=24, n_rate=0.002, sub_rate=0.02), 1),
+    "sync_pe": (dict(genera=4, species_per_genus=4, strains_per_species=2, codons=2500, seed=27, species_div=0.05, syncmer=1, smer_len=6),
+                dict(n_reads=3000, length=151, seed=28, n_rate=0.003, sub_rate=0.02, paired=True), 2),
     # long reads (seq-mode 3: denominator 1000)
     "long": (dict(genera=3, species_per_genus=3, strains_per_species=2, codons=6000, seed=13),
              dict(n_reads=300, length=6000, seed=14, sub_rate=0.05), 3),
