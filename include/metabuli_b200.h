@@ -37,8 +37,8 @@ typedef struct {
     int   kmer_format;        /* 1|2 (Kmer_format; classify.cpp:13 default 1)                         */
     int   reduced_aa;         /* must be 0 (ReducedKmerMatcher is out of scope)         */
     int   skip_redundancy;    /* Skip_redundancy: 0 => info & ~(1<<31) (KmerMatcher.cpp:204-205)       */
-    int   syncmer;            /* must be 0                                             */
-    int   smer_len;
+    int   syncmer;            /* Syncmer: 1 = only closed syncmers are queries (SyncmerScanner.h:9-103), needs    */
+    int   smer_len;           /* kmer_format 2; S-mer_len (2..7): paths may skip up to 8 - s codons (Taxonomer.cpp:34-42) */
     int   seq_mode;           /* 1 SE, 2 PE, 3 long (denominator 100/100/1000, Taxonomer.cpp:44-48)    */
     float min_score;          /* --min-score                                                           */
     float min_sp_score;       /* --min-sp-score                                                        */

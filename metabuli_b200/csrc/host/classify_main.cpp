@@ -206,7 +206,7 @@ int classify(int argc, char** argv) {
             }
         }
     }
-    if (cfg.reduced_aa || cfg.syncmer) die("reduced-alphabet and syncmer databases are not supported by the B200 path yet");
+    if (cfg.reduced_aa) die("reduced-alphabet databases are not supported by the B200 path yet");
 
     TaxonomyHost tax;
     tax.load(dbDir + "/taxonomyDB");

@@ -74,6 +74,22 @@ __device__ __forceinline__ bool aa_filter_pass(const AaFilter& f, uint64_t value
     return ((w1 >> (b1 & 31)) & (w2 >> (b2 & 31)) & 1u) != 0u;
 }
 
+// closed-syncmer test of a format-2 amino-acid part (SyncmerScanner.h:36-74): of the 9 - s s-mers of the 8-residue window the
+// smallest one (leftmost on ties: the reference's deque only evicts strictly larger values) is the first or the last.  The
+// window is decided by its own residues alone, so it fits the one-thread-per-window shape of this kernel.
+__device__ __forceinline__ bool is_closed_syncmer(uint64_t aa40, int s) {
+    const int n = 9 - s;
+    const uint64_t mask = (1ull << (5 * s)) - 1;
+    const uint64_t first = (aa40 >> (5 * (n - 1))) & mask, last = aa40 & mask;
+    bool first_min = first <= last, last_min = last < first;
+    for (int j = 1; j < n - 1; ++j) {
+        const uint64_t m = (aa40 >> (5 * (n - 1 - j))) & mask;
+        first_min = first_min && first <= m;
+        last_min = last_min && last < m;
+    }
+    return first_min || last_min;
+}
+
 template <int FORMAT, bool FILTER>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ off1,
@@ -82,7 +98,7 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
                const uint64_t* __restrict__ slot_off, const uint8_t* __restrict__ g_base_code,
                const uint8_t* __restrict__ g_codon, uint64_t* __restrict__ value, uint64_t* __restrict__ qinfo,
                uint32_t* __restrict__ slot_idx, unsigned long long* __restrict__ n_valid, const AaFilter filter,
-               unsigned long long* __restrict__ out_cursor, const uint64_t out_cap) {
+               unsigned long long* __restrict__ out_cursor, const uint64_t out_cap, const int smer_len) {
     __shared__ uint8_t s_code[256];
     __shared__ uint8_t s_codon[512];
     __shared__ WarpScratch s_warp[kWarpsPerBlock];
@@ -149,7 +165,11 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
                         else             { aaF = aaF * 21 + (f >> 3); aaR = aaR * 21 + (rv >> 3); }
                         dnaF = (dnaF << 3) | (f & 7); dnaR = (dnaR << 3) | (rv & 7);
                     }
-                    const bool okF = active && !badF, okR = active && !badR;
+                    bool okF = active && !badF, okR = active && !badR;
+                    if (FORMAT == 2 && smer_len > 0) {                 // syncmer databases: only closed syncmers are queries
+                        okF = okF && is_closed_syncmer(aaF, smer_len);
+                        okR = okR && is_closed_syncmer(aaR, smer_len);
+                    }
                     const uint32_t res = (uint32_t)(x % 3);
                     const uint32_t frameF = res;
                     const uint32_t frameR = 3u + (uint32_t)((lmod - (int)res + 3) % 3);
@@ -221,7 +241,7 @@ void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, con
                     uint32_t n_reads, const int32_t* cov1, const int32_t* w1, const int32_t* w2, const uint64_t* slot_off,
                     const uint8_t* base_code, const uint8_t* codon, uint64_t* value, uint64_t* qinfo, uint32_t* slot_idx,
                     unsigned long long* n_valid, int sm_count, cudaStream_t st, AaFilter filter, unsigned long long* out_cursor,
-                    uint64_t out_cap) {
+                    uint64_t out_cap, int smer_len) {
     if (!n_reads) return;
     unsigned blocks = (n_reads + kWarpsPerBlock - 1) / kWarpsPerBlock;
     unsigned cap = (unsigned)sm_count * 64u;          // grid-stride beyond a few waves
@@ -229,7 +249,7 @@ void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, con
     const bool filtered = filter.words != nullptr && out_cursor != nullptr && slot_idx != nullptr;
 #define MBL_LAUNCH_EXTRACT(F, B)                                                                                             \
     extract_kernel<F, B><<<blocks, kWarpsPerBlock * 32, 0, st>>>(bases1, off1, bases2, off2, n_reads, cov1, w1, w2, slot_off, \
-                                                                 base_code, codon, value, qinfo, slot_idx, n_valid, filter, out_cursor, out_cap)
+                                                                 base_code, codon, value, qinfo, slot_idx, n_valid, filter, out_cursor, out_cap, smer_len)
     if (format == 2) { if (filtered) MBL_LAUNCH_EXTRACT(2, true); else MBL_LAUNCH_EXTRACT(2, false); }
     else             { if (filtered) MBL_LAUNCH_EXTRACT(1, true); else MBL_LAUNCH_EXTRACT(1, false); }
 #undef MBL_LAUNCH_EXTRACT

@@ -38,6 +38,7 @@ struct DeviceTaxonomy {             // reference arrays as stored in taxonomyDB
 struct ScoreParams {
     float min_score, min_sp_score, tie_ratio;
     int min_cons_cnt, min_cons_cnt_euk, accession_level, denominator, kmer_format;
+    int max_codon_shift, dna_shift;   // Taxonomer.cpp:34-42: 1 / 3, or (8 - s) / 3 (8 - s) for syncmer databases
     int force_scratch_dp;      // tests only: skip the register-resident DP fast path
 };
 
@@ -48,7 +49,7 @@ void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, con
                     uint32_t n_reads, const int32_t* cov1, const int32_t* w1, const int32_t* w2, const uint64_t* slot_off,
                     const uint8_t* base_code, const uint8_t* codon, uint64_t* value, uint64_t* qinfo, uint32_t* slot_idx,
                     unsigned long long* n_valid, int sm_count, cudaStream_t st, AaFilter filter = AaFilter(),
-                    unsigned long long* out_cursor = nullptr, uint64_t out_cap = 0);
+                    unsigned long long* out_cursor = nullptr, uint64_t out_cap = 0, int smer_len = 0);
 // filtered extraction packs the surviving metamers from slot 0 upwards in per-warp chunks of kExtractChunk slots (unused chunk
 // tails are blank) and never writes at or beyond out_cap (a cursor beyond out_cap tells the host to redo it with more room);
 // extract_filtered_capacity = the slots it can need when `pass` of the `slots` reserved slots survive

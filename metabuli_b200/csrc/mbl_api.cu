@@ -316,7 +316,7 @@ void stage_extract(mbl_ctx* c, const SubBatch& sb, bool use_filter, uint64_t fil
         AaFilter flt;
         if (use_filter) { flt.words = c->dir.filter; flt.n_lines = c->dir.filter_lines; flt.minimizer = c->dir.filter_minimizer; }
         launch_extract(c->cfg.kmer_format, bases1, off1, bases2, off2, n, cov1, w1, w2, slot_off, c->d_base_code, c->d_codon,
-                       va, qa, ia, counters, c->sm_count, st, flt, counters + 4, S8);
+                       va, qa, ia, counters, c->sm_count, st, flt, counters + 4, S8, c->cfg.syncmer ? c->cfg.smer_len : 0);
         c->stats.kernel_launches += 2;
         t.stop();
     }
@@ -467,6 +467,8 @@ int stage_sort_score(mbl_ctx* c, const SubBatch& sb, uint64_t M) {
         sa.par.accession_level = c->cfg.accession_level;
         sa.par.denominator = (c->cfg.seq_mode == 1 || c->cfg.seq_mode == 2) ? 100 : 1000;      // Taxonomer.cpp:44-48
         sa.par.kmer_format = c->cfg.kmer_format;
+        sa.par.max_codon_shift = c->cfg.syncmer ? 8 - c->cfg.smer_len : 1;               // Taxonomer.cpp:34-42
+        sa.par.dna_shift = 3 * sa.par.max_codon_shift;
         sa.q_tax = c->q_tax.get<int32_t>(sb.quots + 1); sa.q_ham = c->q_ham.get<uint8_t>(sb.quots + 1); sa.q_has = c->q_has.get<uint8_t>(sb.quots + 1);
         sa.taxcnt_pairs = c->pairs_raw.get<int32_t>(2 * (sb.quots + 1));
         sa.results = c->res_sub.get<mbl_read_result>(n);
@@ -604,8 +606,10 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
     mbl_ctx* c = new mbl_ctx();
     c->cfg = *cfg;
     try {
-        if (cfg->reduced_aa || cfg->syncmer) { delete c; return MBL_E_UNSUPPORTED; }
+        if (cfg->reduced_aa) { delete c; return MBL_E_UNSUPPORTED; }
         if (cfg->kmer_format != 1 && cfg->kmer_format != 2) { delete c; return MBL_E_UNSUPPORTED; }
+        // syncmer databases (SyncmerScanner is a MetamerScanner, KmerExtractor.cpp:18-20): format-2 k-mers, 2 <= s <= 7
+        if (cfg->syncmer && (cfg->kmer_format != 2 || cfg->smer_len < 2 || cfg->smer_len > 7)) { delete c; return MBL_E_UNSUPPORTED; }
         MBL_CUDA(cudaSetDevice(cfg->device));
         cudaDeviceProp prop;
         MBL_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
@@ -1476,7 +1480,7 @@ int mbl_extract(mbl_ctx* c, const mbl_batch* b, uint64_t* value, uint64_t* qinfo
         uint64_t *va = c->val_a.get<uint64_t>(total), *qa = c->qi_a.get<uint64_t>(total);
         launch_extract(c->cfg.kmer_format, (const uint8_t*)c->bases1.p, (const uint64_t*)c->off1.p,
                        c->paired ? (const uint8_t*)c->bases2.p : nullptr, off2, n, cov1, w1, w2, slot_off, c->d_base_code,
-                       c->d_codon, va, qa, nullptr, counters, c->sm_count, st);
+                       c->d_codon, va, qa, nullptr, counters, c->sm_count, st, AaFilter(), nullptr, 0, c->cfg.syncmer ? c->cfg.smer_len : 0);
         MBL_CUDA(cudaMemcpyAsync(value, va, 8 * total, cudaMemcpyDeviceToHost, st));
         MBL_CUDA(cudaMemcpyAsync(qinfo, qa, 8 * total, cudaMemcpyDeviceToHost, st));
         MBL_CUDA(cudaStreamSynchronize(st));
@@ -1651,6 +1655,8 @@ int mbl_score(mbl_ctx* c, const mbl_match_rec* sorted_h, size_t M, uint32_t n, c
         sa.par.accession_level = c->cfg.accession_level;
         sa.par.denominator = (c->cfg.seq_mode == 1 || c->cfg.seq_mode == 2) ? 100 : 1000;
         sa.par.kmer_format = c->cfg.kmer_format;
+        sa.par.max_codon_shift = c->cfg.syncmer ? 8 - c->cfg.smer_len : 1;
+        sa.par.dna_shift = 3 * sa.par.max_codon_shift;
         const size_t Mp = M + 1;
         sa.l_score = c->l_score.get<float>(Mp); sa.l_start = c->l_start.get<int32_t>(Mp); sa.l_ham = c->l_ham.get<int32_t>(Mp);
         sa.l_depth = c->l_depth.get<int32_t>(Mp); sa.l_smatch = c->l_smatch.get<uint32_t>(Mp); sa.l_conn = c->l_conn.get<uint8_t>(Mp);

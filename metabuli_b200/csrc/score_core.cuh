@@ -217,20 +217,22 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
             ++i;
         }
         const int shift = (int)(((uint64_t)nextPos - curPos) / 3);
-        if (shift == 1) {
-            const uint32_t lowMask = (1u << 21) - 1;
+        if (shift > 0 && shift <= a.par.max_codon_shift) {              // maxCodonShift: 1, or 8 - s with syncmers (Taxonomer.cpp:34-42)
+            const uint32_t lowMask = (1u << (24 - 3 * shift)) - 1;
 #pragma unroll
             for (int nx = 0; nx < kDpWidth; ++nx) {
                 if (nx >= nnxt) break;
-                const int h = ml[gs + nxt[nx].idx].right_end_hamming & 3;
-                const float inc = codon_score(h);
+                const uint32_t reh = ml[gs + nxt[nx].idx].right_end_hamming;
+                int h = 0;                                               // calHammingDistIncrement / calScoreIncrement (:650-669)
+                float inc = 0.f;
+                for (int sft = 0; sft < shift; ++sft) { const int d = (reh >> (2 * sft)) & 3; h += d; inc += codon_score(d); }
                 int best = -1;
                 float bestScore = 0.f;
 #pragma unroll
                 for (int cu = 0; cu < kDpWidth; ++cu) {
                     if (cu >= ncur) break;
                     const uint32_t m1 = forward ? cur[cu].dna : nxt[nx].dna, m2 = forward ? nxt[nx].dna : cur[cu].dna;
-                    const bool cons = fmt2 ? ((m1 & lowMask) == (m2 >> 3)) : ((m1 >> 3) == (m2 & lowMask));
+                    const bool cons = fmt2 ? ((m1 & lowMask) == (m2 >> (3 * shift))) : ((m1 >> (3 * shift)) == (m2 & lowMask));
                     if (cons) {
                         cur[cu].conn = true;
                         if (cur[cu].score > bestScore) { best = cu; bestScore = cur[cu].score; }
@@ -241,7 +243,7 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
                     for (int cu = 0; cu < kDpWidth; ++cu)
                         if (cu == best) {
                             nxt[nx].start = cur[cu].start; nxt[nx].score = cur[cu].score + inc; nxt[nx].ham = cur[cu].ham + h;
-                            nxt[nx].depth = cur[cu].depth + 1; nxt[nx].smatch = cur[cu].smatch;
+                            nxt[nx].depth = cur[cu].depth + shift; nxt[nx].smatch = cur[cu].smatch;
                         }
                 }
             }
@@ -300,11 +302,13 @@ MBL_HD void score_frame_group(const ScoreArgs& a, uint64_t gs, uint64_t ge, int 
         while (i < ge && qi_pos(ml[i].qinfo) == nextPos) { init(i); ++i; }
         const uint64_t nxtE = i;
         const int shift = (int)(((uint64_t)nextPos - curPos) / 3);
-        if (shift > 0 && shift <= 1) {                                   // maxCodonShift = 1 without syncmers
+        if (shift > 0 && shift <= a.par.max_codon_shift) {              // maxCodonShift = 1 without syncmers, 8 - s with
             const uint32_t lowMask = (1u << (24 - 3 * shift)) - 1;
             for (uint64_t nx = nxtS; nx < nxtE; ++nx) {
-                const int h = ml[nx].right_end_hamming & 3;              // calScoreIncrement / calHammingDistIncrement
-                const float inc = codon_score(h);
+                const uint32_t reh = ml[nx].right_end_hamming;
+                int h = 0;                                               // calScoreIncrement / calHammingDistIncrement
+                float inc = 0.f;
+                for (int sft = 0; sft < shift; ++sft) { const int d = (reh >> (2 * sft)) & 3; h += d; inc += codon_score(d); }
                 const uint32_t ndna = ml[nx].dna_encoding;
                 int64_t best = -1;
                 float bestScore = 0.f;
@@ -538,7 +542,7 @@ MBL_HD void score_read(const ScoreArgs& a, uint32_t r) {
     const uint32_t q0 = a.quot_off[r], nq = a.quot_off[r + 1] - q0;
     for (uint32_t k = 0; k < nq; ++k) a.q_has[q0 + k] = 0;
     for (uint64_t k = bestS; k < bestE; ++k) {
-        const uint32_t quo = qi_pos(ml[k].qinfo) / 3u;
+        const uint32_t quo = qi_pos(ml[k].qinfo) / (uint32_t)a.par.dna_shift;      // Taxonomer.cpp:217 (dnaShift: 3, or 3 (8 - s) with syncmers)
         if (quo >= nq) continue;
         const uint8_t h = ml[k].hamming;
         if (!a.q_has[q0 + quo] || h < a.q_ham[q0 + quo]) { a.q_has[q0 + quo] = 1; a.q_tax[q0 + quo] = ml[k].target_id; a.q_ham[q0 + quo] = h; }

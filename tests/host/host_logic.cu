@@ -9,6 +9,9 @@
 
 using namespace mbl;
 
+static int g_smer_len = 0;     // syncmer database: s-mer length (0 = none); set with ht_set_syncmer
+extern "C" void ht_set_syncmer(int smer_len) { g_smer_len = smer_len; }
+
 extern "C" {
 
 // comparator of combineMatchPaths: (score desc, hamming asc, start desc)
@@ -54,6 +57,7 @@ int ht_score(const mbl_match_rec* matches, size_t n_match, uint32_t n_reads, con
     a.par.min_score = min_score; a.par.min_sp_score = min_sp_score; a.par.tie_ratio = tie_ratio; a.par.min_cons_cnt = min_cons;
     a.par.min_cons_cnt_euk = min_cons_euk; a.par.accession_level = accession_level;
     a.par.denominator = (seq_mode == 1 || seq_mode == 2) ? 100 : 1000; a.par.kmer_format = kmer_format; a.par.force_scratch_dp = force_scratch_dp;
+    a.par.max_codon_shift = g_smer_len ? 8 - g_smer_len : 1; a.par.dna_shift = 3 * a.par.max_codon_shift;   // Taxonomer.cpp:34-42
     a.l_score = l_score.data(); a.l_start = l_start.data(); a.l_ham = l_ham.data(); a.l_depth = l_depth.data();
     a.l_smatch = l_smatch.data(); a.l_conn = l_conn.data(); a.p_start = p_start.data(); a.p_end = p_end.data();
     a.p_score = p_score.data(); a.p_ham = p_ham.data(); a.p_depth = p_depth.data(); a.p_smatch = p_smatch.data();

@@ -35,7 +35,8 @@ def test_synthetic_case(name, golden_dir, tmp_path):
         sdb.write(db_dir)
         odb = oracle.OracleDb(db_dir)
         gv, gq = clf.extract(*reads)
-        ov, oq, cov1, cov2 = oracle.extract(*reads, kmer_format=sdb.database.params.kmer_format)
+        ov, oq, cov1, cov2 = oracle.extract(*reads, kmer_format=sdb.database.params.kmer_format, syncmer=sdb.database.params.syncmer,
+                                            smer_len=sdb.database.params.smer_len)
         assert gv.size == ov.size
         gm_ = gv != BLANK
         om_ = ((oq >> np.uint64(32)) & np.uint64(0x1FFFFFFF)) != 0

@@ -54,12 +54,13 @@ def test_sort_replays_std_sort(hl):
 
 @pytest.mark.parametrize("flat", [0, 1])
 @pytest.mark.parametrize("force_scratch", [0, 1])
-@pytest.mark.parametrize("name", ["multi_pe", "ties_se", "long"])
+@pytest.mark.parametrize("name", ["multi_pe", "ties_se", "long", "sync_se", "sync_pe"])
 def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
     from metabuli_b200 import _ffi
     sdb, reads, seq_mode = synth_cases.build(name)
     odb = oracle.OracleDb.from_synth(sdb)
-    ov, oq, cov1, cov2 = oracle.extract(*reads, kmer_format=2)
+    hl.ht_set_syncmer(odb.smer_len)                 # syncmer databases: paths may skip up to 8 - s codons, votes per 3 (8 - s) nt
+    ov, oq, cov1, cov2 = oracle.extract(*reads, kmer_format=2, syncmer=1 if odb.smer_len else 0, smer_len=odb.smer_len or 5)
     sv, sq = oracle.sort_kmers(ov, oq)
     m = oracle.sort_matches(odb.match(sv, sq))
     c2 = cov2 if seq_mode == 2 else None
