@@ -87,3 +87,27 @@ def test_oracle_matches_shard_by_shard(name, n_shards):
     assert np.array_equal(np.sort(got, order=order), np.sort(want, order=order))
     assert want.size > 1000
     full.close()
+
+
+@pytest.mark.parametrize("db,n_shards", [("in", 2), ("in", 8), ("ex", 3)])
+def test_cuts_on_the_reference_built_fixture(db, n_shards, fixtures_dir):
+    """The regression fixture databases were written by the reference's own `build` (diffIdx, info and the 4096-entry `split`
+    file): the planner must produce valid cuts from those checkpoints too, and the oracle must find the same matches shard by
+    shard as on the whole index."""
+    import os
+    from metabuli_b200 import load_database, read_fastx, sharded
+    d = load_database(os.path.join(fixtures_dir, f"db_{db}"))
+    shards = sharded.plan_shards(d, n_shards)
+    vals, starts = shard_oracle.decode_stream(np.asarray(d.diff_idx))
+    assert vals.size == d.info.size
+    non_empty = [s for s in shards if s.info_end > s.info_begin]
+    assert len(non_empty) == n_shards
+    assert non_empty[0].info_begin == 0 and non_empty[-1].info_end == d.info.size and non_empty[-1].diff_end == d.diff_idx.size
+    for a, b in zip(non_empty[:-1], non_empty[1:]):
+        assert a.diff_end == b.diff_begin and a.info_end == b.info_begin
+    for s in non_empty[1:]:
+        k = int(s.info_begin)
+        assert int(starts[k]) == s.diff_begin and int(vals[k]) == s.first_value and int(vals[k - 1]) == s.base_value
+        assert (vals[k] & AA) != (vals[k - 1] & AA)
+    sizes = [2 * (s.diff_end - s.diff_begin) + 4 * (s.info_end - s.info_begin) for s in shards]
+    assert max(sizes) < 1.3 * sum(sizes) / n_shards
