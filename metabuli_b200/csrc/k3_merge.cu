@@ -256,9 +256,6 @@ merge_kernel(MergeArgs a) {
     uint64_t* my_qinfo = s_qinfo + warp * 32;
     uint64_t* my_stage = s_stage + warp * 96;
     unsigned long long my_matches = 0;
-#ifdef MBL_DEBUG_ITEMS
-    unsigned long long dbg_prev = 0;
-#endif
     OutChunk chunk;
 
     // thread 0: start the TMA copy of a tile's fragments
@@ -534,9 +531,6 @@ merge_kernel(MergeArgs a) {
             }
         }
         if (q_count) process_hits(q_count);
-#ifdef MBL_DEBUG_ITEMS
-        { unsigned long long d = my_matches - dbg_prev; dbg_prev = my_matches; if (lane == 0 && d) atomicAdd(&a.items[item].pad, (unsigned)d); }
-#endif
         // first queries of the next item (its record arrived before the decode barrier)
         if (next_item < n_items) {
             const MergeItem* nr = s_rec + (slot ^ 1);

@@ -1564,22 +1564,6 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
             if (attempt > 3) return fail(c, MBL_E_MATCH_OVERFLOW, "match buffer overflow persists");
             dcap = h_cnt[1] + 65536;
         }
-#ifdef MBL_DEBUG_ITEMS
-        {
-            uint32_t ni = 0;
-            cudaMemcpy(&ni, ma.item_off + c->dir.n_tiles, 4, cudaMemcpyDeviceToHost);
-            std::vector<MergeItem> hi(ni);
-            cudaMemcpy(hi.data(), ma.items, sizeof(MergeItem) * ni, cudaMemcpyDeviceToHost);
-            std::vector<uint64_t> ql(2 * c->dir.n_tiles + 2);
-            cudaMemcpy(ql.data(), ma.q_lo, 8 * ql.size(), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "items %u (cap %llu) tiles %llu nq %llu\n", ni, (unsigned long long)ma.items_cap, (unsigned long long)c->dir.n_tiles, (unsigned long long)nq);
-            for (uint32_t i = 0; i < ni; ++i)
-                fprintf(stderr, "item %u tile %u q [%llu,%llu) d0 %llu nu %u k0 %llu nk %u base %llx jumbo %lld found %u\n", i, hi[i].tile,
-                        (unsigned long long)hi[i].q_begin, (unsigned long long)hi[i].q_end, (unsigned long long)hi[i].diff_begin, hi[i].n_u16,
-                        (unsigned long long)hi[i].info_begin, hi[i].n_kmers, (unsigned long long)hi[i].base_value, (long long)hi[i].jumbo_off, hi[i].pad);
-            for (uint64_t t = 0; t < c->dir.n_tiles; ++t) fprintf(stderr, "tile %llu q_lo %llu q_hi %llu\n", (unsigned long long)t, (unsigned long long)ql[2*t], (unsigned long long)ql[2*t+1]);
-        }
-#endif
         *n_match = h_cnt[2];
         if (h_cnt[2] > cap || !out) return fail(c, MBL_E_MATCH_OVERFLOW, "match buffer too small");
         host.resize(h_cnt[1]);
