@@ -348,7 +348,7 @@ def make_db(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, s
 
 # ---- reads ---------------------------------------------------------------------------------------------------------
 def make_reads(sdb: SynthDb, n_reads: int, length: int = 150, seed: int = 4, random_frac: float = 0.3, sub_rate: float = 0.01,
-               n_rate: float = 0.0, paired: bool = False, insert: int = 350, length_jitter: int = 0):
+               n_rate: float = 0.0, paired: bool = False, insert: int = 350, length_jitter: int = 0, mate2_jitter: int = 0):
     """Reads drawn from the strain genomes (either strand, any phase) with substitutions, plus random reads.
     -> (bases1 u8, offsets1 u64[, bases2, offsets2]) as numpy arrays (SoA of mbl_batch)."""
     dev = sdb.genomes.device
@@ -394,5 +394,8 @@ def make_reads(sdb: SynthDb, n_reads: int, length: int = 150, seed: int = 4, ran
     if not paired:
         return b1, o1
     mate2 = comp[frag_seq.flip(1).long()][:, :length]
-    b2, o2 = pack(mate2, lens)
+    lens2 = lens
+    if mate2_jitter > 0:                 # mates of different lengths (drawn last, so every other output is unchanged)
+        lens2 = (lens - torch.randint(0, mate2_jitter + 1, (n_reads,), generator=gen, device=dev)).clamp_(min=1)
+    b2, o2 = pack(mate2, lens2)
     return b1, o1, b2, o2

@@ -31,9 +31,17 @@ CASES = {
 }
 
 
+# cases checked on the CPU only so far (oracle vs the reference binary's TSV); to be promoted to CASES (GPU parity) next
+CPU_CASES = {
+    # mates of different, partly too short lengths: a pair counts only when BOTH mates hold a k-mer (KmerExtractor.cpp:436-471)
+    "ragged_pe": (dict(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, seed=31),
+                  dict(n_reads=3000, length=150, seed=32, n_rate=0.004, paired=True, length_jitter=118, mate2_jitter=30), 2),
+}
+
+
 def build(name):
     from metabuli_b200 import synth
-    dbkw, rkw, seq_mode = CASES[name]
+    dbkw, rkw, seq_mode = (CASES.get(name) or CPU_CASES[name])
     sdb = synth.make_db(**dbkw)
     reads = synth.make_reads(sdb, **rkw)
     return sdb, reads, seq_mode
