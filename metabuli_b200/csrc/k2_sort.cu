@@ -28,6 +28,13 @@ void sort_kmers(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, u
     result_in_b = k.selector;
 }
 
+void sort_kmers_qinfo(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint64_t* val_a, uint64_t* val_b, size_t n, int begin_bit,
+                      int& result_in_b, cudaStream_t st) {
+    cub::DoubleBuffer<uint64_t> k(key_a, key_b), v(val_a, val_b);
+    MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, begin_bit, 64, st));
+    result_in_b = k.selector;
+}
+
 void sort_kmers_idx(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b, size_t n, int begin_bit,
                     int& result_in_b, cudaStream_t st) {
     cub::DoubleBuffer<uint64_t> k(key_a, key_b);

@@ -218,7 +218,9 @@ __global__ void merge_item_fill_kernel(const Tile* __restrict__ tiles, uint64_t 
 }
 
 // ---- the merge kernel ------------------------------------------------------------------------------
-template <int kThreads>
+// kDirect (MergeArgs::direct, experimental): the query's qinfo travels with its value through the sort, and a lane settles its
+// own query — group minimum, then its surviving candidates — instead of the queue + pair sweeps below.
+template <int kThreads, bool kDirect>
 __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 3 : 2)
 merge_kernel(MergeArgs a) {
     constexpr int kWarps = kThreads / 32;
@@ -360,6 +362,97 @@ merge_kernel(MergeArgs a) {
             infos = a.info + it.info_begin;
         }
 
+        if (kDirect) {
+            // -- 3'. lane per query.  With the presence filter three quarters of the queries that get here have their group, so
+            //        the lanes are busy without a hit queue.  Pass 1 walks the group for the minimum Hamming sum (a candidate
+            //        equal to its predecessor — the same k-mer in a sister species — reuses the predecessor's sum; the sums of the
+            //        first 16 candidates are kept, 4 bits each), pass 2 lets every lane step to its next surviving candidate and
+            //        the warp writes those rows together (ballot-ranked slots, rows straight from registers).
+            const uint32_t n_chunks_d = (uint32_t)((it.q_end - it.q_begin + 31) >> 5);
+            const uint32_t lt = (1u << lane) - 1u;
+            for (uint32_t ch = (uint32_t)warp; ch < n_chunks_d; ch += kWarps) {
+                const uint64_t qi = it.q_begin + (uint64_t)ch * 32 + lane;
+                const bool active = qi < it.q_end;
+                const uint64_t qv = active ? ld_stream_u64(a.q_value + qi) : kBlank;
+                const uint64_t qinfo = active ? ld_stream_u64(a.q_info + qi) : 0ull;
+                const uint64_t q40 = qv >> 24;
+                const uint32_t qd = (uint32_t)qv & 0xFFFFFFu;
+                uint32_t g0 = 0;
+                bool hit = false;
+                if (!jumbo) {
+                    if (active) {
+                        const uint32_t h = aa_hash(q40);
+                        const uint32_t tag = h & 0x7FFFFu;
+                        uint32_t bkt = h >> hash_shift;
+                        while (true) {
+                            const uint2 e = *reinterpret_cast<const uint2*>(s_tab + 2u * bkt);
+                            if (e.x == kEmpty) break;
+                            if ((e.x & 0x7FFFFu) == tag && (vals[e.x >> 19] >> 24) == q40) { g0 = e.x >> 19; hit = true; break; }
+                            if (e.y == kEmpty) break;
+                            if ((e.y & 0x7FFFFu) == tag && (vals[e.y >> 19] >> 24) == q40) { g0 = e.y >> 19; hit = true; break; }
+                            bkt = (bkt + 1) & bucket_mask;
+                        }
+                    }
+                } else if (active) {
+                    uint32_t lo = 0, hi = nk;
+                    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((vals[mid] >> 24) < q40) lo = mid + 1; else hi = mid; }
+                    if (lo < nk && (vals[lo] >> 24) == q40) { g0 = lo; hit = true; }
+                }
+                if (!__any_sync(kFull, hit)) continue;
+                // pass 1: group end and minimum
+                uint32_t end = g0, best = 255u;
+                uint64_t packed = 0;                                       // sums of candidates g0 .. g0+15, 4 bits each
+                if (hit) {
+                    uint32_t prev_td = 0xFFFFFFFFu, prev_sum = 0;
+                    while (end < nk && (vals[end] >> 24) == q40) {
+                        const uint32_t td = (uint32_t)vals[end] & 0xFFFFFFu;
+                        const uint32_t sum = td == prev_td ? prev_sum : (td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td)));
+                        prev_td = td; prev_sum = sum;
+                        best = min(best, sum);
+                        if (end - g0 < 16u) packed |= (uint64_t)min(sum, 15u) << (4u * (end - g0));
+                        ++end;
+                    }
+                }
+                const uint32_t limit = min(best * 2u, 7u);                 // KmerMatcher.cpp:1136
+                // pass 2: survivors
+                uint32_t j = g0;
+                while (true) {
+                    uint32_t td = 0, sum = 255u;
+                    while (j < end) {                                      // this lane's next surviving candidate
+                        td = (uint32_t)vals[j] & 0xFFFFFFu;
+                        sum = (j - g0 < 16u) ? (uint32_t)(packed >> (4u * (j - g0))) & 15u : (td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td)));
+                        if (sum <= limit) break;
+                        ++j;
+                    }
+                    const bool sel = j < end;
+                    const uint32_t bal = __ballot_sync(kFull, sel);
+                    if (!bal) break;
+                    const uint32_t cnt = __popc(bal);
+                    const Reservation rs = reserve(chunk, cnt, a.out_count, lane);
+                    if (sel) {
+                        const int32_t taxid = (int32_t)((uint32_t)infos[j] & a.info_mask);
+                        const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
+                        if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);              // Q2
+                        uint32_t field = 0u;
+                        if (sum) field = ham_fields(ham_lookup(s_ham, qd, td), qd, td, !((qi_frame(qinfo) < 3) ^ fmt2));
+                        const uint64_t sl = slot_of(rs, (uint32_t)__popc(bal & lt));
+                        if (sl < a.out_cap) {
+                            uint64_t* o = reinterpret_cast<uint64_t*>(a.out + sl);
+                            o[0] = qinfo;
+                            o[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
+                            o[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
+                        }
+                        ++j;
+                    }
+                    my_matches += cnt;
+                }
+            }
+            if (tid == 0) s_item[slot] = pending;
+            __syncthreads();
+            item = next_item;
+            slot ^= 1;
+            continue;
+        }
         // -- 3. stream the query slice.  A warp looks up 32 queries per iteration and appends the ones that found
         //       their amino-acid group ("hits") to its private queue.  32 queued hits are expanded into their
         //       (query, candidate) pairs, which are spread evenly over the lanes in batches of 32: sweep 1 finds every
@@ -567,20 +660,25 @@ void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
     merge_item_fill_kernel<<<blocks, 256, 0, st>>>(a.tiles, a.n_tiles, a.q_lo, a.item_cnt, a.item_off, a.items, a.items_cap);
 }
 
-template <int kThreads>
+template <int kThreads, bool kDirect>
 static void launch_merge_t(const MergeArgs& a, int sm_count, cudaStream_t st) {
     const size_t smem = smem_layout(a.max_u16, a.max_kmers, a.n_buckets, kThreads / 32).total;
     // set on every launch (microseconds): two pipeline lanes may launch from two host threads
-    MBL_CUDA(cudaFuncSetAttribute(merge_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MBL_CUDA(cudaFuncSetAttribute(merge_kernel<kThreads, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel<kThreads>, kThreads, smem));
+    MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel<kThreads, kDirect>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    merge_kernel<kThreads><<<(unsigned)(sm_count * per_sm), kThreads, smem, st>>>(a);
+    merge_kernel<kThreads, kDirect><<<(unsigned)(sm_count * per_sm), kThreads, smem, st>>>(a);
 }
 
 void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st) {
-    if (a.cta_threads == 512) launch_merge_t<512>(a, sm_count, st);
-    else launch_merge_t<256>(a, sm_count, st);
+    if (a.direct) {                                   // q_info is sorted alongside q_value, no q_idx
+        if (a.cta_threads == 512) launch_merge_t<512, true>(a, sm_count, st);
+        else launch_merge_t<256, true>(a, sm_count, st);
+        return;
+    }
+    if (a.cta_threads == 512) launch_merge_t<512, false>(a, sm_count, st);
+    else launch_merge_t<256, false>(a, sm_count, st);
 }
 
 }  // namespace mbl

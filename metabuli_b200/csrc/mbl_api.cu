@@ -56,6 +56,7 @@ struct mbl_ctx {
     int filter_minimizer = 1;           // MBL_FILTER_MINIMIZER=0: filter line from the whole amino-acid part instead of its minimizer
     int filter_bits = 16;               // MBL_FILTER_BITS: bits per index k-mer of the amino-acid presence filter, 0 = no filter
     uint64_t arena_S8 = 0;              // slot stride of the phase-1 arena layout (set by whoever fills it)
+    int merge_direct = 0;               // MBL_MERGE_DIRECT=1: experimental lane-per-query match stage with qinfo sorted alongside the value
     int merge_threads = 256;            // MBL_MERGE_THREADS: 256 (3 CTAs per SM) or 512 (2 CTAs per SM, 32 warps)
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // index
@@ -334,6 +335,7 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, double* ratio, 
     unsigned long long* counters = c->counters.get<unsigned long long>(8);
     uint64_t *qv = nullptr;
     uint32_t* qidx = nullptr;
+    bool direct = false;
     {
         StageTimer t(c, MBL_STAGE_SORT);
         c->cub_tmp.get<uint8_t>(std::max(scan_bytes, sortk_bytes));
@@ -341,9 +343,18 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, double* ratio, 
         uint64_t *va = ar, *vb = ar + S8;
         uint32_t *ia = reinterpret_cast<uint32_t*>(ar + 3 * S8), *ib = ia + S8;
         int in_b = 0;
-        if (S) sort_kmers_idx(c->cub_tmp.p, c->cub_tmp.cap, va, vb, ia, ib, S, c->dir.sort_begin_bit, in_b, st);
+        // experimental direct merge: qinfo travels through the sort with the value (only when it sits in the arena, i.e. not for the
+        // receive buffer of the sharded mode); its second buffer is the region of the two slot-index arrays
+        direct = c->merge_direct && q_info == ar + 2 * S8;
+        if (direct) {
+            uint64_t *qa = ar + 2 * S8, *qb = ar + 3 * S8;
+            if (S) sort_kmers_qinfo(c->cub_tmp.p, c->cub_tmp.cap, va, vb, qa, qb, S, c->dir.sort_begin_bit, in_b, st);
+            q_info = in_b ? qb : qa;
+        } else if (S) {
+            sort_kmers_idx(c->cub_tmp.p, c->cub_tmp.cap, va, vb, ia, ib, S, c->dir.sort_begin_bit, in_b, st);
+        }
         qv = in_b ? vb : va;
-        qidx = in_b ? ib : ia;
+        qidx = direct ? nullptr : (in_b ? ib : ia);
         t.stop();
     }
     const uint64_t* qi = q_info;
@@ -376,6 +387,7 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, double* ratio, 
     ma.prefix_shift = c->dir.sort_begin_bit;
     ma.dyn_chunks = c->dyn_chunks;
     ma.cta_threads = c->merge_threads;
+    ma.direct = direct ? 1 : 0;
     ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
     ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
     ma.items_cap = c->dir.n_tiles + n_query / kItemQueries + 2;
@@ -632,6 +644,7 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         }
         if (const char* e = getenv("MBL_FILTER_MINIMIZER")) c->filter_minimizer = atoi(e) != 0;
         if (const char* e = getenv("MBL_FILTER_BITS")) { int v = atoi(e); if (v >= 0 && v <= 64) c->filter_bits = v; }
+        if (const char* e = getenv("MBL_MERGE_DIRECT")) c->merge_direct = atoi(e) != 0;
         if (const char* e = getenv("MBL_MERGE_THREADS")) { int v = atoi(e); if (v == 256 || v == 512) c->merge_threads = v; }
         if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }
         if (const char* e = getenv("MBL_SORT_BIT")) { int v = atoi(e); if (v == 24 || v == 32 || v == 40) c->force_sort_bit = v; }
@@ -680,7 +693,7 @@ mbl_ctx* ensure_shadow(mbl_ctx* c) {
     }
     mbl_ctx* s = c->shadow;
     s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
-    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
+    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->merge_direct = c->merge_direct; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
     s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
     s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded; s->filter_complete = c->filter_complete;
     s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed

@@ -166,3 +166,27 @@ def test_very_long_ragged_reads_vs_oracle():
     finally:
         clf.close()
         odb.close()
+
+
+@pytest.mark.skipif(os.environ.get("MBL_TEST_EXPERIMENTAL") != "1", reason="experimental kernels are opt-in (MBL_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("name", ["multi_se", "multi_pe", "ties_se", "format1_pe", "sync_se", "long"])
+def test_experimental_direct_merge(name, golden_dir):
+    """MBL_MERGE_DIRECT=1: lane-per-query match stage with qinfo sorted alongside the value (written at the end of round 1 without
+    a GPU at hand).  Runs in a subprocess so that a faulting kernel cannot poison this process's CUDA context."""
+    import subprocess
+    import sys
+    code = f"""
+import gzip, os, sys
+sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r}); sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import synth_cases
+from metabuli_b200 import Classifier, ClassifyOptions
+sdb, reads, seq_mode = synth_cases.build({name!r})
+clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
+res, pairs = clf.classify_batch(*reads)
+tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
+golden = gzip.open(os.path.join({golden_dir!r}, "synth", {name!r} + ".tsv.gz"), "rb").read()
+sys.exit(0 if tsv == golden else 3)
+"""
+    env = dict(os.environ, MBL_MERGE_DIRECT="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, timeout=300, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
