@@ -26,6 +26,8 @@ for name in list(synth_cases.CASES) + list(synth_cases.CPU_CASES):
     else:
         args += ["--seq-mode", str(seq_mode), q1]
     args += [db_dir, work, name, "--threads", "4", "--max-ram", "8"]
+    for k, v in synth_cases.FLAGS.get(name, {}).items():
+        args += [k, str(v)]
     r = subprocess.run(args, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     tsv = open(os.path.join(work, name + "_classifications.tsv"), "rb").read()

@@ -54,7 +54,7 @@ def test_sort_replays_std_sort(hl):
 
 @pytest.mark.parametrize("flat", [0, 1])
 @pytest.mark.parametrize("force_scratch", [0, 1])
-@pytest.mark.parametrize("name", ["multi_pe", "ties_se", "long", "sync_se", "sync_pe"])
+@pytest.mark.parametrize("name", ["multi_pe", "ties_se", "long", "sync_se", "sync_pe", "flags_se", "ragged_pe"])
 def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
     from metabuli_b200 import _ffi
     sdb, reads, seq_mode = synth_cases.build(name)
@@ -64,7 +64,8 @@ def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
     sv, sq = oracle.sort_kmers(ov, oq)
     m = oracle.sort_matches(odb.match(sv, sq))
     c2 = cov2 if seq_mode == 2 else None
-    ores, opairs = odb.score(m, cov1, c2, seq_mode=seq_mode)
+    fl = synth_cases.oracle_flags(name)
+    ores, opairs = odb.score(m, cov1, c2, seq_mode=seq_mode, **fl)
     t = sdb.database.tax
     t2s = np.ascontiguousarray(sdb.database.taxid2species)
     tx = _ffi.Taxonomy(t.max_nodes, t.max_taxid, t.eukaryota, _p(t.D), _p(t.E), _p(t.L), _p(t.H), _p(t.M), t.M_k, _p(t.node_taxid),
@@ -76,7 +77,8 @@ def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
     hl.ht_score.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
                             C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     mm = np.ascontiguousarray(m)
-    rc = hl.ht_score(_p(mm), mm.size, n, _p(cov1), _p(c2), C.byref(tx), seq_mode, 0.0, 0.0, 0.95, 4, 9, 0, 2, force_scratch, flat, _p(res), _p(pairs),
+    rc = hl.ht_score(_p(mm), mm.size, n, _p(cov1), _p(c2), C.byref(tx), seq_mode, fl["min_score"], fl["min_sp_score"], fl["tie_ratio"],
+                     fl["min_cons"], fl["min_cons_euk"], 0, 2, force_scratch, flat, _p(res), _p(pairs),
                      pairs.shape[0], C.byref(used))
     assert rc == 0
     for f in ("classification", "query_length", "taxcnt_len", "is_classified", "taxcnt_begin"):

@@ -24,6 +24,6 @@ def test_oracle_matches_reference_on_synthetic(name, golden_dir, tmp_path):
         q2 = str(tmp_path / "r2.fna")
         synth_cases.write_fasta(q2, reads[2], reads[3])
     out = str(tmp_path / "o.tsv")
-    oracle.classify_files(q1, q2, db_dir, seq_mode, out, threads=3)
+    oracle.classify_files(q1, q2, db_dir, seq_mode, out, threads=3, **synth_cases.oracle_flags(name))
     golden = gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
     assert open(out, "rb").read() == golden
