@@ -74,7 +74,10 @@ class SynthTaxonomy:
     genus_of_species: np.ndarray
 
 
-def make_taxonomy(genera: int, species_per_genus: int, strains_per_species: int, eukaryote_genera: int = 0) -> SynthTaxonomy:
+def make_taxonomy(genera: int, species_per_genus: int, strains_per_species: int, eukaryote_genera: int = 0,
+                  accession_leaves: bool = False) -> SynthTaxonomy:
+    """accession_leaves: every strain gets one child of rank "accession" that carries the k-mers (databases built with
+    --accession-level 1, IndexCreator / Taxonomer.cpp:256-267)."""
     # internal taxid 1 must not carry k-mers (getTaxIdAtRank returns 0 for it, TaxonomyWrapper.cpp:480)
     parent, rank, name = [0, 1], ["", "no rank"], ["", "root"]
 
@@ -92,6 +95,8 @@ def make_taxonomy(genera: int, species_per_genus: int, strains_per_species: int,
             species_ids.append(sid); genus_of_species.append(gid)
             for t in range(strains_per_species):
                 tid = add(sid, "subspecies", f"Genus{g} species{s} strain{t}")
+                if accession_leaves:
+                    tid = add(tid, "accession", f"ACC_{g}_{s}_{t}.1")
                 strain_ids.append(tid); species_of_strain.append(sid)
     return SynthTaxonomy(np.array(parent, dtype=np.int32), rank, name, np.array(strain_ids, dtype=np.int32),
                          np.array(species_of_strain, dtype=np.int32), np.array(species_ids, dtype=np.int32),
@@ -219,7 +224,7 @@ class SynthDb:
             f.write("".join(f"{int(t)}\n" for t in self.taxid_list))
         p = self.database.params
         with open(os.path.join(path, "db.parameters"), "w") as f:
-            f.write("DB_name\tsynthetic\nCreation_date\t2026-1-1\nReduced_alphabet\t0\nAccession_level\t0\nMask_mode\t0\n"
+            f.write("DB_name\tsynthetic\nCreation_date\t2026-1-1\nReduced_alphabet\t0\nAccession_level\t%d\nMask_mode\t0\n" % (1 if p.accession_level_db == 1 else 0) +
                     "Mask_prob\t0.900000\nSkip_redundancy\t1\nSyncmer\t%d\n%sKmer_format\t%d\n"
                     % (p.syncmer, ("S-mer_len\t%d\n" % p.smer_len) if p.syncmer else "", p.kmer_format))    # IndexCreator.cpp:1258-1270
 
@@ -340,10 +345,13 @@ def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, ch
 
 
 def make_db(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, species_div=0.12, strain_div=0.01, seed=3,
-            eukaryote_genera=0, device="cpu", split_num=4096, kmer_format=2, syncmer=0, smer_len=5) -> SynthDb:
-    tx = make_taxonomy(genera, species_per_genus, strains_per_species, eukaryote_genera)
+            eukaryote_genera=0, device="cpu", split_num=4096, kmer_format=2, syncmer=0, smer_len=5, accession_leaves=False) -> SynthDb:
+    tx = make_taxonomy(genera, species_per_genus, strains_per_species, eukaryote_genera, accession_leaves)
     genomes = make_genomes(tx, codons, species_div, strain_div, seed, device)
-    return build_db(tx, genomes, split_num, kmer_format=kmer_format, syncmer=syncmer, smer_len=smer_len)
+    sdb = build_db(tx, genomes, split_num, kmer_format=kmer_format, syncmer=syncmer, smer_len=smer_len)
+    if accession_leaves:
+        sdb.database.params.accession_level_db = 1
+    return sdb
 
 
 # ---- reads ---------------------------------------------------------------------------------------------------------

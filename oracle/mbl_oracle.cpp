@@ -1099,6 +1099,10 @@ bool classify_files(const std::string &q1, const std::string &q2, const std::str
         if (!read_fastx(q2, m2, err)) return false;
         if (m1.size() != m2.size()) { if (err) *err = "The number of reads in the two files are not equal."; return false; }
     }
+    // loadDbParameters (common.cpp:101-108): the database's Accession_level adjusts --accession-level
+    Options o = opt;
+    if (db.params.accessionLevelDb == 0 && o.accessionLevel == 1) o.accessionLevel = 0;
+    if (db.params.accessionLevelDb == 1 && o.accessionLevel == 0) o.accessionLevel = 2;
     std::vector<QueryInfo> queries;
     std::vector<Kmer> kmers;
     extract_kmers(m1, paired ? &m2 : nullptr, db.params.kmerFormat, queries, kmers, db.params.syncmer, db.params.smerLen);
@@ -1108,7 +1112,7 @@ bool classify_files(const std::string &q1, const std::string &q2, const std::str
     if (!match_kmers(db, kmers, matches, opt.threads, err)) return false;
     if (nMatches) *nMatches = matches.size();
     sort_matches(matches, opt.threads);
-    score_reads(db, opt, matches, queries, opt.threads);
+    score_reads(db, o, matches, queries, opt.threads);
     tsv.clear();
     write_tsv_header(tsv);
     write_tsv_rows(db, m1, queries, tsv);

@@ -164,11 +164,11 @@ double orc_classify_arrays(void* dbp, int seq_mode, int threads, const uint8_t* 
 }
 
 // classify flags for orc_classify_files (classify.cpp:10-37 defaults until set): --min-score, --min-sp-score, --tie-ratio,
-// --min-cons-cnt, --min-cons-cnt-euk
+// --min-cons-cnt, --min-cons-cnt-euk, --accession-level
 static Options g_flags;
-void orc_set_flags(float min_score, float min_sp_score, float tie_ratio, int min_cons, int min_cons_euk) {
+void orc_set_flags(float min_score, float min_sp_score, float tie_ratio, int min_cons, int min_cons_euk, int accession_level) {
     g_flags.minScore = min_score; g_flags.minSpScore = min_sp_score; g_flags.tieRatio = tie_ratio;
-    g_flags.minConsCnt = min_cons; g_flags.minConsCntEuk = min_cons_euk;
+    g_flags.minConsCnt = min_cons; g_flags.minConsCntEuk = min_cons_euk; g_flags.accessionLevel = accession_level;
 }
 
 int orc_classify_files(const char* q1, const char* q2, const char* db_dir, int seq_mode, int threads, const char* out_path,

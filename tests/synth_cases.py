@@ -38,6 +38,12 @@ CPU_CASES = {
     "flags_se": (dict(genera=4, species_per_genus=5, strains_per_species=2, codons=2500, seed=37, species_div=0.03, strain_div=0.006,
                       eukaryote_genera=2),
                  dict(n_reads=4000, length=150, seed=38, sub_rate=0.03, n_rate=0.001), 1),
+    # accession-level databases (Accession_level 1 in db.parameters): by default the "accession" leaves are pruned from the clade
+    # descent (Taxonomer.cpp:256-267, accessionLevel 2); with --accession-level 1 reads go down to the accession
+    "acc_prune_se": (dict(genera=4, species_per_genus=3, strains_per_species=3, codons=2500, seed=43, strain_div=0.03, accession_leaves=True),
+                     dict(n_reads=3000, length=150, seed=44, sub_rate=0.01), 1),
+    "acc_lvl1_se": (dict(genera=4, species_per_genus=3, strains_per_species=3, codons=2500, seed=43, strain_div=0.03, accession_leaves=True),
+                    dict(n_reads=3000, length=150, seed=44, sub_rate=0.01), 1),
     "ragged_pe": (dict(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, seed=31),
                   dict(n_reads=3000, length=150, seed=32, n_rate=0.004, paired=True, length_jitter=118, mate2_jitter=30), 2),
 }
@@ -46,13 +52,15 @@ CPU_CASES = {
 # classify flags of a case (reference spelling -> value); cases without an entry run the defaults
 FLAGS = {
     "flags_se": {"--min-score": 0.3, "--min-sp-score": 0.6, "--tie-ratio": 0.9, "--min-cons-cnt": 6, "--min-cons-cnt-euk": 11},
+    "acc_lvl1_se": {"--accession-level": 1},
 }
 
 
 def oracle_flags(name):
     f = FLAGS.get(name, {})
     return dict(min_score=f.get("--min-score", 0.0), min_sp_score=f.get("--min-sp-score", 0.0), tie_ratio=f.get("--tie-ratio", 0.95),
-                min_cons=f.get("--min-cons-cnt", 4), min_cons_euk=f.get("--min-cons-cnt-euk", 9))
+                min_cons=f.get("--min-cons-cnt", 4), min_cons_euk=f.get("--min-cons-cnt-euk", 9),
+                accession_level=f.get("--accession-level", 0))
 
 
 def build(name):

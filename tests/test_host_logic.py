@@ -54,7 +54,7 @@ def test_sort_replays_std_sort(hl):
 
 @pytest.mark.parametrize("flat", [0, 1])
 @pytest.mark.parametrize("force_scratch", [0, 1])
-@pytest.mark.parametrize("name", ["multi_pe", "ties_se", "long", "sync_se", "sync_pe", "flags_se", "ragged_pe"])
+@pytest.mark.parametrize("name", ["multi_pe", "ties_se", "long", "sync_se", "sync_pe", "flags_se", "ragged_pe", "acc_prune_se", "acc_lvl1_se"])
 def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
     from metabuli_b200 import _ffi
     sdb, reads, seq_mode = synth_cases.build(name)
@@ -65,6 +65,12 @@ def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
     m = oracle.sort_matches(odb.match(sv, sq))
     c2 = cov2 if seq_mode == 2 else None
     fl = synth_cases.oracle_flags(name)
+    acc = fl["accession_level"]                         # loadDbParameters (common.cpp:101-108)
+    if sdb.database.params.accession_level_db == 1 and acc == 0:
+        acc = 2
+    if sdb.database.params.accession_level_db != 1 and acc == 1:
+        acc = 0
+    fl["accession_level"] = acc
     ores, opairs = odb.score(m, cov1, c2, seq_mode=seq_mode, **fl)
     t = sdb.database.tax
     t2s = np.ascontiguousarray(sdb.database.taxid2species)
@@ -78,7 +84,7 @@ def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
                             C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     mm = np.ascontiguousarray(m)
     rc = hl.ht_score(_p(mm), mm.size, n, _p(cov1), _p(c2), C.byref(tx), seq_mode, fl["min_score"], fl["min_sp_score"], fl["tie_ratio"],
-                     fl["min_cons"], fl["min_cons_euk"], 0, 2, force_scratch, flat, _p(res), _p(pairs),
+                     fl["min_cons"], fl["min_cons_euk"], acc, 2, force_scratch, flat, _p(res), _p(pairs),
                      pairs.shape[0], C.byref(used))
     assert rc == 0
     for f in ("classification", "query_length", "taxcnt_len", "is_classified", "taxcnt_begin"):
