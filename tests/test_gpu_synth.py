@@ -190,3 +190,22 @@ sys.exit(0 if tsv == golden else 3)
     env = dict(os.environ, MBL_MERGE_DIRECT="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, timeout=300, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(os.environ.get("MBL_TEST_EXPERIMENTAL") != "1", reason="not yet run on a GPU (MBL_TEST_EXPERIMENTAL=1 to try)")
+@pytest.mark.parametrize("name", list(synth_cases.CPU_CASES))
+def test_cpu_pinned_cases_on_gpu(name, golden_dir):
+    """The cases of synth_cases.CPU_CASES (asymmetric mates, non-default flags, accession-level databases) end to end on the CUDA
+    path against the reference binary's TSV.  Written after the GPU budget of round 1 was spent: promote to CASES once green."""
+    from metabuli_b200 import Classifier, ClassifyOptions
+    sdb, reads, seq_mode = synth_cases.build(name)
+    f = synth_cases.oracle_flags(name)
+    opt = ClassifyOptions(seq_mode=seq_mode, min_score=f["min_score"], min_sp_score=f["min_sp_score"], tie_ratio=f["tie_ratio"],
+                          min_cons_cnt=f["min_cons"], min_cons_cnt_euk=f["min_cons_euk"], accession_level=f["accession_level"])
+    clf = Classifier(None, opt, database=sdb.database)
+    try:
+        res, pairs = clf.classify_batch(*reads)
+        tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
+        assert tsv == gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
+    finally:
+        clf.close()
