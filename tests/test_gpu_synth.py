@@ -209,3 +209,26 @@ def test_cpu_pinned_cases_on_gpu(name, golden_dir):
         assert tsv == gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
     finally:
         clf.close()
+
+
+@pytest.mark.skipif(os.environ.get("MBL_TEST_EXPERIMENTAL") != "1", reason="not yet run on a GPU (MBL_TEST_EXPERIMENTAL=1 to try)")
+def test_batch_without_any_kmer():
+    """Every read shorter than one k-mer window (and a batch of Ns): all rows come back unclassified with the covered length the
+    reference prints (Q8), nothing is sorted or merged."""
+    from metabuli_b200 import Classifier, ClassifyOptions
+    sdb, _, _ = synth_cases.build("multi_se")
+    clf = Classifier(None, ClassifyOptions(seq_mode=1), database=sdb.database)
+    try:
+        lens = np.array([1, 5, 23, 26, 20, 2], dtype=np.uint64)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        bases = np.frombuffer(b"ACGT" * 64, dtype=np.uint8)[: int(off[-1])].copy()
+        res, pairs = clf.classify_batch(bases, off)
+        assert not res["is_classified"].any() and pairs.shape[0] == 0
+        want = [orc_len for orc_len in (oracle.lib().orc_max_covered_length(int(x)) for x in lens)]
+        assert res["query_length"].tolist() == want
+        n_reads = 64
+        off = (np.arange(n_reads + 1, dtype=np.uint64) * 150)
+        res, pairs = clf.classify_batch(np.full(int(off[-1]), ord("N"), dtype=np.uint8), off)
+        assert not res["is_classified"].any() and clf.stats()["n_query_kmers"] == 0
+    finally:
+        clf.close()
