@@ -169,10 +169,12 @@ def test_very_long_ragged_reads_vs_oracle():
 
 
 @pytest.mark.skipif(os.environ.get("MBL_TEST_EXPERIMENTAL") != "1", reason="experimental kernels are opt-in (MBL_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("knob", ["MBL_MERGE_DIRECT", "MBL_SCORE_WARP"])
 @pytest.mark.parametrize("name", ["multi_se", "multi_pe", "ties_se", "format1_pe", "sync_se", "long"])
-def test_experimental_direct_merge(name, golden_dir):
-    """MBL_MERGE_DIRECT=1: lane-per-query match stage with qinfo sorted alongside the value (written at the end of round 1 without
-    a GPU at hand).  Runs in a subprocess so that a faulting kernel cannot poison this process's CUDA context."""
+def test_experimental_kernels(name, knob, golden_dir):
+    """Kernels written at the end of round 1 without a GPU at hand, off by default: MBL_MERGE_DIRECT=1 (lane-per-query match
+    stage with qinfo sorted alongside the value) and MBL_SCORE_WARP=1 (warp-per-read scoring over rows staged in shared memory).
+    Runs in a subprocess so that a faulting kernel cannot poison this process's CUDA context."""
     import subprocess
     import sys
     code = f"""
@@ -187,7 +189,7 @@ tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
 golden = gzip.open(os.path.join({golden_dir!r}, "synth", {name!r} + ".tsv.gz"), "rb").read()
 sys.exit(0 if tsv == golden else 3)
 """
-    env = dict(os.environ, MBL_MERGE_DIRECT="1")
+    env = dict(os.environ, **{knob: "1"})
     r = subprocess.run([sys.executable, "-c", code], env=env, timeout=300, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
 
