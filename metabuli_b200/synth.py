@@ -225,8 +225,8 @@ class SynthDb:
         p = self.database.params
         with open(os.path.join(path, "db.parameters"), "w") as f:
             f.write("DB_name\tsynthetic\nCreation_date\t2026-1-1\nReduced_alphabet\t0\nAccession_level\t%d\nMask_mode\t0\n" % (1 if p.accession_level_db == 1 else 0) +
-                    "Mask_prob\t0.900000\nSkip_redundancy\t1\nSyncmer\t%d\n%sKmer_format\t%d\n"
-                    % (p.syncmer, ("S-mer_len\t%d\n" % p.smer_len) if p.syncmer else "", p.kmer_format))    # IndexCreator.cpp:1258-1270
+                    "Mask_prob\t0.900000\nSkip_redundancy\t%d\nSyncmer\t%d\n%sKmer_format\t%d\n"
+                    % (p.skip_redundancy, p.syncmer, ("S-mer_len\t%d\n" % p.smer_len) if p.syncmer else "", p.kmer_format))    # IndexCreator.cpp:1258-1270
 
 
 def encode_index(values_i64: torch.Tensor, split_num: int = 4096):

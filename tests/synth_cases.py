@@ -44,6 +44,13 @@ CPU_CASES = {
                      dict(n_reads=3000, length=150, seed=44, sub_rate=0.01), 1),
     "acc_lvl1_se": (dict(genera=4, species_per_genus=3, strains_per_species=3, codons=2500, seed=43, strain_div=0.03, accession_leaves=True),
                     dict(n_reads=3000, length=150, seed=44, sub_rate=0.01), 1),
+    # long ragged reads (BASELINE configs[3]/[4] shape in miniature): 3-46 kbp, 8 % substitutions, seq-mode 3
+    "ont_ragged": (dict(genera=3, species_per_genus=3, strains_per_species=2, codons=20000, seed=41),
+                   dict(n_reads=48, length=50000, seed=42, sub_rate=0.08, n_rate=0.0005, length_jitter=47000), 3),
+    # database written without Skip_redundancy (older builds): bit 31 of an info entry is a flag that classify masks away
+    # (KmerMatcher.cpp:204-205, 381); the case sets it on every third entry
+    "redund_se": (dict(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, seed=47),
+                  dict(n_reads=3000, length=150, seed=48, sub_rate=0.02), 1),
     "ragged_pe": (dict(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, seed=31),
                   dict(n_reads=3000, length=150, seed=32, n_rate=0.004, paired=True, length_jitter=118, mate2_jitter=30), 2),
 }
@@ -67,6 +74,9 @@ def build(name):
     from metabuli_b200 import synth
     dbkw, rkw, seq_mode = (CASES.get(name) or CPU_CASES[name])
     sdb = synth.make_db(**dbkw)
+    if name == "redund_se":
+        sdb.database.info[::3] |= np.int32(-2147483648)           # bit 31
+        sdb.database.params.skip_redundancy = 0
     reads = synth.make_reads(sdb, **rkw)
     return sdb, reads, seq_mode
 

@@ -54,7 +54,7 @@ def test_sort_replays_std_sort(hl):
 
 @pytest.mark.parametrize("flat", [0, 1])
 @pytest.mark.parametrize("force_scratch", [0, 1])
-@pytest.mark.parametrize("name", ["multi_pe", "ties_se", "long", "sync_se", "sync_pe", "flags_se", "ragged_pe", "acc_prune_se", "acc_lvl1_se"])
+@pytest.mark.parametrize("name", ["multi_pe", "ties_se", "long", "sync_se", "sync_pe", "flags_se", "ragged_pe", "acc_prune_se", "acc_lvl1_se", "ont_ragged", "redund_se"])
 def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
     from metabuli_b200 import _ffi
     sdb, reads, seq_mode = synth_cases.build(name)
