@@ -181,6 +181,8 @@ def sharded_arm(args, rank, local_rank, world, dist):
     lib.mbl_host_register(offs.ctypes.data_as(C.c_void_p), offs.nbytes)
     ex = sharded.DistExchange(dist, device) if world > 1 else sharded.SelfExchange()
     winfo["presence_filter"] = bool(sc.merge_filters(ex))
+    sc.clf.release_host_index()                    # every rank built the whole index on the host to cut its shard out of it
+    sdb = None
 
     def barrier():
         torch.cuda.synchronize()
@@ -302,6 +304,9 @@ def main():
     clf = Classifier(None, ClassifyOptions(seq_mode=1, device=local_rank), database=sdb.database)
     winfo["db_load_s"] = round(time.time() - t0, 1)
     winfo.update({"db_" + k: v for k, v in clf.db_info().items() if k in ("n_tiles", "n_jumbo")})
+    if world > 1 or args.no_cpu_baseline:          # the host copy of the index is only needed by the CPU baseline (rank 0, N = 1)
+        clf.release_host_index()
+        sdb = None
     lib = clf.lib
     lib.mbl_host_register(bases.ctypes.data_as(C.c_void_p), bases.nbytes)
     lib.mbl_host_register(offs.ctypes.data_as(C.c_void_p), offs.nbytes)

@@ -145,6 +145,13 @@ class Classifier:
             yield out, pairs[: used.value]
             cur, cur_b, cur_keep = nxt, nxt_b, nxt_keep
 
+    def release_host_index(self):
+        """Drop this object's references to the host copies of diffIdx / info (they are only read by mbl_load_db); several ranks
+        on one node would otherwise each keep ~the index size in host memory."""
+        self._keep = None
+        self.db.diff_idx = np.zeros(0, dtype=np.uint16)
+        self.db.info = np.zeros(0, dtype=np.int32)
+
     def download_results(self):
         """mbl_download_results of the resident batch -> (results[n], taxcnt_pairs[k,2]).  The arrays are views of two pinned
         buffers owned by this object and are overwritten by the next call."""
