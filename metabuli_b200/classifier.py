@@ -254,11 +254,12 @@ class Classifier:
             return out, pairs[: used.value]
 
     # ---- Reporter::writeReadClassification (Reporter.cpp:35-80, printLineage 0) --------------------
-    def format_tsv(self, names, results, pairs, header=True) -> str:
+    def format_tsv(self, names, results, pairs, header=True, lineage=False) -> str:
+        """lineage: --lineage 1 (an extra column with TaxonomyWrapper::taxLineage2 of the classification, Reporter.cpp:37-79)"""
         t = self.db.tax
         rows = []
         if header:
-            rows.append("#is_classified\tname\ttaxID\tquery_length\tscore\trank\ttaxID:match_count\n")
+            rows.append("#is_classified\tname\ttaxID\tquery_length\tscore\trank" + ("\tlineage" if lineage else "") + "\ttaxID:match_count\n")
         for i, name in enumerate(names):
             r = results[i]
             score = "%g" % float(r["score"])                     # ostream << float, precision 6 (Q12)
@@ -266,9 +267,10 @@ class Classifier:
             if r["is_classified"]:
                 b, ln = int(r["taxcnt_begin"]), int(r["taxcnt_len"])
                 cnt = "".join(f"{t.original(int(pairs[k, 0]))}:{int(pairs[k, 1])} " for k in range(b, b + ln))
-                rows.append(f"1\t{name}\t{t.original(cls)}\t{int(r['query_length'])}\t{score}\t{t.rank_of(cls)}\t{cnt}\n")
+                lin = (t.lineage(cls) + "\t") if lineage else ""
+                rows.append(f"1\t{name}\t{t.original(cls)}\t{int(r['query_length'])}\t{score}\t{t.rank_of(cls)}\t{lin}{cnt}\n")
             else:
-                rows.append(f"0\t{name}\t{t.original(cls)}\t{int(r['query_length'])}\t{score}\t-\t-\t\n")
+                rows.append(f"0\t{name}\t{t.original(cls)}\t{int(r['query_length'])}\t{score}\t-\t{'-' + chr(9) if lineage else ''}-\t\n")
         return "".join(rows)
 
     def classify_files(self, q1: str, q2: str | None = None) -> str:

@@ -113,6 +113,24 @@ struct TaxonomyHost {
         for (size_t i = 0; i < maxNodes; ++i)
             if (nameIdx[i] != 0 && strcmp(str(nameIdx[i]), "Eukaryota") == 0) { eukaryota = nodeTaxId[i]; break; }
     }
+    std::string lineage(int32_t taxId) const {        // TaxonomyWrapper::taxLineage2 (TaxonomyWrapper.cpp:431-454)
+        static const std::map<std::string, std::string> shortRanks = {     // ExtendedShortRanks (TaxonomyWrapper.h:9-26)
+            {"subspecies", "ss"}, {"species", "s"}, {"subgenus", "sg"}, {"genus", "g"}, {"subfamily", "sf"}, {"family", "f"},
+            {"suborder", "so"}, {"order", "o"}, {"subclass", "sc"}, {"class", "c"}, {"subphylum", "sp"}, {"phylum", "p"},
+            {"subkingdom", "sk"}, {"kingdom", "k"}, {"superkingdom", "d"}, {"domain", "d"}, {"realm", "r"}};
+        std::vector<int> chain;
+        int node = D[taxId];
+        do { chain.push_back(node); node = D[nodeParent[node]]; } while (nodeParent[node] != nodeTaxId[node]);
+        std::string out;
+        for (int i = (int)chain.size() - 1; i >= 0; --i) {
+            auto it = shortRanks.find(str(rankIdx[chain[(size_t)i]]));
+            out += it == shortRanks.end() ? "-" : it->second;
+            out += '_';
+            out += str(nameIdx[chain[(size_t)i]]);
+            if (i > 0) out += ';';
+        }
+        return out;
+    }
     bool exists(int32_t t) const { return t <= maxTaxID && D[t] != -1; }
     int32_t original(int32_t t) const { return internalIds ? i2o[t] : t; }
     int32_t atSpecies(int32_t taxId) const {          // TaxonomyWrapper.cpp:479-498 with rank "species"
@@ -140,6 +158,7 @@ struct TaxonomyHost {
 };
 
 struct Params {
+    int lineage = 0;
     int seqMode = 2, threads = 0, accessionLevel = 0, minConsCnt = 4, minConsCntEuk = 9, matchPerKmer = 4, device = 0;
     float minScore = 0.f, minSpScore = 0.f, tieRatio = 0.95f;
     size_t batchReads = 0;
@@ -162,8 +181,9 @@ int classify(int argc, char** argv) {
         else if (a == "--match-per-kmer") par.matchPerKmer = atoi(val());
         else if (a == "--device") par.device = atoi(val());
         else if (a == "--batch-reads") par.batchReads = (size_t)atoll(val());
+        else if (a == "--lineage") par.lineage = atoi(val());
         else if (a == "--max-ram" || a == "--mask" || a == "--mask-prob" || a == "-v" || a == "--hamming-margin" ||
-                 a == "--validate-input" || a == "--validate-db" || a == "--lineage" || a == "--taxonomy-path") val();
+                 a == "--validate-input" || a == "--validate-db" || a == "--taxonomy-path") val();
         else if (a.rfind("--", 0) == 0) die("unknown flag " + a);
         else par.files.push_back(a);
     }
@@ -244,7 +264,8 @@ int classify(int argc, char** argv) {
     const std::string tsvPath = outDir + "/" + jobId + "_classifications.tsv";
     FILE* out = fopen(tsvPath.c_str(), "wb");
     if (!out) die("cannot write " + tsvPath);
-    fputs("#is_classified\tname\ttaxID\tquery_length\tscore\trank\ttaxID:match_count\n", out);      // Reporter.cpp:37-41
+    fputs(par.lineage ? "#is_classified\tname\ttaxID\tquery_length\tscore\trank\tlineage\ttaxID:match_count\n"
+                      : "#is_classified\tname\ttaxID\tquery_length\tscore\trank\ttaxID:match_count\n", out);      // Reporter.cpp:37-41
 
     // batches (the reference's QuerySplits, Classifier.cpp:81-140): batch i+1 is uploaded while batch i is classified
     // (mbl_prefetch_batch / mbl_classify_prefetched) and batch i-1 is formatted and written by the host threads
@@ -269,6 +290,7 @@ int classify(int argc, char** argv) {
         const TaxonomyHost& t;
         int32_t original(int32_t x) const { return t.original(x); }
         const char* rank_name(int32_t x) const { return t.str(t.rankIdx[t.D[x]]); }
+        std::string lineage(int32_t x) const { return t.lineage(x); }
     } tv{tax};
     uint64_t kmers = 0, matches = 0;
     auto t0 = std::chrono::steady_clock::now();
@@ -300,7 +322,7 @@ int classify(int argc, char** argv) {
         writer = std::thread([&, cur] {
             const Out& w = outb[cur];
             std::vector<std::string> rows;
-            mblhost::format_rows(tv, r1.names, w.r0, w.n, w.res.data(), w.pairs.data(), T, rows);
+            mblhost::format_rows(tv, r1.names, w.r0, w.n, w.res.data(), w.pairs.data(), T, rows, par.lineage != 0);
             for (const std::string& x : rows) fwrite(x.data(), 1, x.size(), out);
         });
         printf("Processed read count   : %zu (%g)\n", r0 + s.n, (double)(r0 + s.n) / (double)total);
@@ -321,7 +343,8 @@ int classify(int argc, char** argv) {
 int main(int argc, char** argv) {
     if (argc < 2 || strcmp(argv[1], "classify") != 0) {
         fprintf(stderr, "usage: %s classify [--seq-mode 1|2|3] [--min-score F] [--min-sp-score F] [--tie-ratio F] [--min-cons-cnt N]\n"
-                        "          [--min-cons-cnt-euk N] [--accession-level N] [--match-per-kmer N] [--device N] [--batch-reads N]\n"
+                        "          [--min-cons-cnt-euk N] [--accession-level N] [--lineage 0|1] [--match-per-kmer N] [--device N]\n"
+                        "          [--batch-reads N] [--threads N]\n"
                         "          <fastx> [<fastx2>] <dbdir> <outdir> <jobid>\n", argv[0]);
         return 2;
     }

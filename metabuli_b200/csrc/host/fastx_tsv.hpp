@@ -180,10 +180,11 @@ inline void append_int(std::string& s, long long v) {
     while (n) s.push_back(buf[--n]);
 }
 
-// Tax must provide: int32_t original(int32_t) const; const char* rank_name(int32_t internal_taxid) const
+// Tax must provide: int32_t original(int32_t) const; const char* rank_name(int32_t internal_taxid) const; and, for
+// lineage = true (--lineage 1), std::string lineage(int32_t internal_taxid) const (TaxonomyWrapper::taxLineage2)
 template <class Tax>
 void format_rows(const Tax& tax, const std::vector<std::string>& names, size_t name0, size_t n, const mbl_read_result* res,
-                 const int32_t* pairs, unsigned threads, std::vector<std::string>& out) {
+                 const int32_t* pairs, unsigned threads, std::vector<std::string>& out, bool lineage = false) {
     unsigned T = threads ? threads : 1;
     if (n < 4096) T = 1;
     out.assign(T, std::string());
@@ -207,6 +208,7 @@ void format_rows(const Tax& tax, const std::vector<std::string>& names, size_t n
             if (q.is_classified) {
                 s += tax.rank_name(q.classification);
                 s.push_back('\t');
+                if (lineage) { s += tax.lineage(q.classification); s.push_back('\t'); }
                 for (uint32_t k = q.taxcnt_begin; k < q.taxcnt_begin + q.taxcnt_len; ++k) {
                     append_int(s, tax.original(pairs[2 * (size_t)k]));
                     s.push_back(':');
@@ -215,7 +217,7 @@ void format_rows(const Tax& tax, const std::vector<std::string>& names, size_t n
                 }
                 s.push_back('\n');
             } else {
-                s += "-\t-\t\n";
+                s += lineage ? "-\t-\t-\t\n" : "-\t-\t\n";
             }
         }
     };

@@ -129,6 +129,23 @@ class TaxonomyDB:
     def rank_of(self, taxid: int) -> str:
         return self.node_rank_name[int(self.D[taxid])]
 
+    # ExtendedShortRanks (TaxonomyWrapper.h:9-26)
+    SHORT_RANKS = {"subspecies": "ss", "species": "s", "subgenus": "sg", "genus": "g", "subfamily": "sf", "family": "f", "suborder": "so",
+                   "order": "o", "subclass": "sc", "class": "c", "subphylum": "sp", "phylum": "p", "subkingdom": "sk", "kingdom": "k",
+                   "superkingdom": "d", "domain": "d", "realm": "r"}
+
+    def lineage(self, taxid: int) -> str:
+        """TaxonomyWrapper::taxLineage2 (TaxonomyWrapper.cpp:431-454): short rank '_' name of every node from below the root
+        down to the taxon, ';'-separated; the walk stops at the node that is its own parent."""
+        chain = []
+        node = int(self.D[taxid])
+        while True:
+            chain.append(node)
+            node = int(self.D[self.node_parent[node]])
+            if self.node_parent[node] == self.node_taxid[node]:
+                break
+        return ";".join(self.SHORT_RANKS.get(self.node_rank_name[n], "-") + "_" + self.string(int(self.node_name_idx[n])) for n in reversed(chain))
+
     def taxid_at_rank(self, taxid: int, rank: str) -> int:  # TaxonomyWrapper.cpp:479-498
         if taxid == 0 or not self.node_exists(taxid) or taxid == 1:
             return 0

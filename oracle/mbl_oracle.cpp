@@ -1059,7 +1059,34 @@ void score_reads(const Database &db, const Options &opt, const std::vector<Match
 // =================================================================================================
 // A13  Reporter::writeReadClassification (Reporter.cpp:35-80)
 // =================================================================================================
-void write_tsv_header(std::string &out) { out += "#is_classified\tname\ttaxID\tquery_length\tscore\trank\ttaxID:match_count\n"; }
+void write_tsv_header(std::string &out, bool lineage) {
+    out += "#is_classified\tname\ttaxID\tquery_length\tscore\trank";
+    if (lineage) out += "\tlineage";
+    out += "\ttaxID:match_count\n";
+}
+
+// TaxonomyWrapper::taxLineage2 (TaxonomyWrapper.cpp:431-454) with ExtendedShortRanks (TaxonomyWrapper.h:9-26)
+std::string Taxonomy::lineage(int32_t taxId) const {
+    static const std::map<std::string, std::string> shortRanks = {
+        {"subspecies", "ss"}, {"species", "s"}, {"subgenus", "sg"}, {"genus", "g"}, {"subfamily", "sf"}, {"family", "f"},
+        {"suborder", "so"}, {"order", "o"}, {"subclass", "sc"}, {"class", "c"}, {"subphylum", "sp"}, {"phylum", "p"},
+        {"subkingdom", "sk"}, {"kingdom", "k"}, {"superkingdom", "d"}, {"domain", "d"}, {"realm", "r"}};
+    std::vector<int> chain;
+    int node = D[taxId];
+    do {
+        chain.push_back(node);
+        node = D[nodeParent[node]];
+    } while (nodeParent[node] != nodeTaxId[node]);
+    std::string out;
+    for (int i = (int)chain.size() - 1; i >= 0; --i) {
+        auto it = shortRanks.find(str(nodeRankIdx[chain[(size_t)i]]));
+        out += it == shortRanks.end() ? "-" : it->second;
+        out += '_';
+        out += str(nodeNameIdx[chain[(size_t)i]]);
+        if (i > 0) out += ';';
+    }
+    return out;
+}
 
 static void append_float(std::string &out, float v) {   // ostream << float, default precision 6 (Q12)
     char buf[64];
@@ -1067,7 +1094,7 @@ static void append_float(std::string &out, float v) {   // ostream << float, def
     out += buf;
 }
 
-void write_tsv_rows(const Database &db, const std::vector<Read> &m1, const std::vector<QueryInfo> &qs, std::string &out) {
+void write_tsv_rows(const Database &db, const std::vector<Read> &m1, const std::vector<QueryInfo> &qs, std::string &out, bool lineage) {
     for (size_t i = 0; i < qs.size(); ++i) {
         const QueryInfo &q = qs[i];
         out += q.isClassified ? "1\t" : "0\t";
@@ -1077,10 +1104,11 @@ void write_tsv_rows(const Database &db, const std::vector<Read> &m1, const std::
         append_float(out, q.score); out += '\t';
         if (q.isClassified) {
             out += db.tax.rankOf(q.classification); out += '\t';
+            if (lineage) { out += db.tax.lineage(q.classification); out += '\t'; }
             for (auto &t : q.taxCnt) { out += std::to_string(db.tax.original(t.first)); out += ':'; out += std::to_string(t.second); out += ' '; }
             out += '\n';
         } else {
-            out += "-\t-\t\n";
+            out += lineage ? "-\t-\t-\t\n" : "-\t-\t\n";
         }
     }
 }
@@ -1114,8 +1142,8 @@ bool classify_files(const std::string &q1, const std::string &q2, const std::str
     sort_matches(matches, opt.threads);
     score_reads(db, o, matches, queries, opt.threads);
     tsv.clear();
-    write_tsv_header(tsv);
-    write_tsv_rows(db, m1, queries, tsv);
+    write_tsv_header(tsv, opt.printLineage != 0);
+    write_tsv_rows(db, m1, queries, tsv, opt.printLineage != 0);
     return true;
 }
 

@@ -81,6 +81,7 @@ struct Taxonomy {
     int32_t original(int32_t internal) const { return internalIds ? internal2org[internal] : internal; }
     int32_t parentOf(int32_t t) const { return nodeParent[D[t]]; }
     const char *rankOf(int32_t t) const { return str(nodeRankIdx[D[t]]); }
+    std::string lineage(int32_t taxId) const;        // TaxonomyWrapper::taxLineage2
 };
 int rank_index(const char *rank);   // NcbiTaxonomy.h:52-80 / NcbiTaxonomy.cpp:374-380
 
@@ -107,6 +108,7 @@ struct Options {
     int minConsCnt = 4, minConsCntEuk = 9;
     int accessionLevel = 0;
     int threads = 1;
+    int printLineage = 0;            // --lineage
 };
 
 // ---- Reads ----------------------------------------------------------------------------------
@@ -138,9 +140,9 @@ bool match_kmers(const Database &db, const std::vector<Kmer> &sortedKmers, std::
 void sort_matches(std::vector<Match> &m, int threads);         // A9 (KmerMatcher.cpp:1149-1166)
 void score_reads(const Database &db, const Options &opt, const std::vector<Match> &sortedMatches,
                  std::vector<QueryInfo> &queries, int threads);  // A10-A12
-// A13 Reporter.cpp:35-80 (printLineage 0)
-void write_tsv_header(std::string &out);
-void write_tsv_rows(const Database &db, const std::vector<Read> &m1, const std::vector<QueryInfo> &q, std::string &out);
+// A13 Reporter.cpp:35-80; lineage = --lineage 1 (TaxonomyWrapper::taxLineage2, TaxonomyWrapper.cpp:431-454)
+void write_tsv_header(std::string &out, bool lineage = false);
+void write_tsv_rows(const Database &db, const std::vector<Read> &m1, const std::vector<QueryInfo> &q, std::string &out, bool lineage = false);
 
 // delta codec (A6) — exposed for tests
 uint64_t next_target_kmer(uint64_t prev, const uint16_t *diff, size_t &idx);   // KmerMatcher.h:282-297

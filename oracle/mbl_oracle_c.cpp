@@ -170,6 +170,7 @@ void orc_set_flags(float min_score, float min_sp_score, float tie_ratio, int min
     g_flags.minScore = min_score; g_flags.minSpScore = min_sp_score; g_flags.tieRatio = tie_ratio;
     g_flags.minConsCnt = min_cons; g_flags.minConsCntEuk = min_cons_euk; g_flags.accessionLevel = accession_level;
 }
+void orc_set_lineage(int print_lineage) { g_flags.printLineage = print_lineage; }
 
 int orc_classify_files(const char* q1, const char* q2, const char* db_dir, int seq_mode, int threads, const char* out_path,
                        size_t* n_kmers, size_t* n_matches, char* err, size_t errlen) {

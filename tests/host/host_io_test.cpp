@@ -6,9 +6,10 @@ namespace {
 mblhost::ReadSet g_reads;
 std::string g_text;
 struct Tax {
-    const int32_t* orig; const char* const* ranks;
+    const int32_t* orig; const char* const* ranks; const char* const* lineages;
     int32_t original(int32_t x) const { return orig[x]; }
     const char* rank_name(int32_t x) const { return ranks[x]; }
+    std::string lineage(int32_t x) const { return lineages ? lineages[x] : ""; }
 };
 }  // namespace
 
@@ -27,10 +28,10 @@ void hio_copy(char* bases, unsigned long long* offsets) {
 const char* hio_name(unsigned long long i) { return g_reads.names[i].c_str(); }
 // formats rows [0, n) of the loaded reads' names; -> length of the text (hio_text)
 unsigned long long hio_format(unsigned long long n, const mbl_read_result* res, const int32_t* pairs, const int32_t* orig,
-                              const char* const* ranks, unsigned threads) {
-    Tax t{orig, ranks};
+                              const char* const* ranks, unsigned threads, const char* const* lineages) {
+    Tax t{orig, ranks, lineages};
     std::vector<std::string> rows;
-    mblhost::format_rows(t, g_reads.names, 0, (size_t)n, res, pairs, threads, rows);
+    mblhost::format_rows(t, g_reads.names, 0, (size_t)n, res, pairs, threads, rows, lineages != nullptr);
     g_text.clear();
     for (auto& r : rows) g_text += r;
     return g_text.size();

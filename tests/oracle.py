@@ -46,6 +46,7 @@ def lib():
         L.orc_classify_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(sz),
                                          C.POINTER(sz), C.c_char_p, sz]
         L.orc_set_flags.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_set_lineage.argtypes = [C.c_int]
         L.orc_next_target_kmer.argtypes = [C.c_uint64, vp, C.POINTER(sz)]
         L.orc_next_target_kmer.restype = C.c_uint64
         L.orc_hamming_sum.argtypes = [C.c_uint64, C.c_uint64]
@@ -174,8 +175,9 @@ def sort_matches(m, threads=4):
 
 
 def classify_files(q1, q2, db_dir, seq_mode, out_path, threads=1, min_score=0.0, min_sp_score=0.0, tie_ratio=0.95, min_cons=4,
-                   min_cons_euk=9, accession_level=0):
+                   min_cons_euk=9, accession_level=0, lineage=0):
     lib().orc_set_flags(min_score, min_sp_score, tie_ratio, min_cons, min_cons_euk, accession_level)
+    lib().orc_set_lineage(lineage)
     err = C.create_string_buffer(512)
     nk, nm = C.c_size_t(0), C.c_size_t(0)
     rc = lib().orc_classify_files(q1.encode(), q2.encode() if q2 else None, db_dir.encode(), seq_mode, threads, out_path.encode(),

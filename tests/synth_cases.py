@@ -51,6 +51,9 @@ CPU_CASES = {
     # (KmerMatcher.cpp:204-205, 381); the case sets it on every third entry
     "redund_se": (dict(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, seed=47),
                   dict(n_reads=3000, length=150, seed=48, sub_rate=0.02), 1),
+    # --lineage 1: an extra column with the lineage of the classification (Reporter.cpp:37-79, TaxonomyWrapper::taxLineage2)
+    "lineage_se": (dict(genera=5, species_per_genus=3, strains_per_species=2, codons=1500, seed=53, eukaryote_genera=1),
+                   dict(n_reads=1500, length=150, seed=54, sub_rate=0.02, n_rate=0.002), 1),
     "ragged_pe": (dict(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, seed=31),
                   dict(n_reads=3000, length=150, seed=32, n_rate=0.004, paired=True, length_jitter=118, mate2_jitter=30), 2),
 }
@@ -60,6 +63,7 @@ CPU_CASES = {
 FLAGS = {
     "flags_se": {"--min-score": 0.3, "--min-sp-score": 0.6, "--tie-ratio": 0.9, "--min-cons-cnt": 6, "--min-cons-cnt-euk": 11},
     "acc_lvl1_se": {"--accession-level": 1},
+    "lineage_se": {"--lineage": 1},
 }
 
 
@@ -67,7 +71,7 @@ def oracle_flags(name):
     f = FLAGS.get(name, {})
     return dict(min_score=f.get("--min-score", 0.0), min_sp_score=f.get("--min-sp-score", 0.0), tie_ratio=f.get("--tie-ratio", 0.95),
                 min_cons=f.get("--min-cons-cnt", 4), min_cons_euk=f.get("--min-cons-cnt-euk", 9),
-                accession_level=f.get("--accession-level", 0))
+                accession_level=f.get("--accession-level", 0), lineage=f.get("--lineage", 0))
 
 
 def build(name):

@@ -27,7 +27,7 @@ def hio():
     L.hio_copy.argtypes = [C.c_void_p, C.c_void_p]
     L.hio_name.argtypes = [C.c_ulonglong]
     L.hio_name.restype = C.c_char_p
-    L.hio_format.argtypes = [C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+    L.hio_format.argtypes = [C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
     L.hio_format.restype = C.c_ulonglong
     L.hio_text.restype = C.c_char_p
     return L
@@ -83,8 +83,9 @@ def test_reader_rejects_empty_entries(hio, tmp_path):
     assert b"2th entry has no sequence or name." in hio.hio_text()
 
 
+@pytest.mark.parametrize("lineage", [False, True])
 @pytest.mark.parametrize("threads", [1, 5])
-def test_rows_match_python_formatter(hio, tmp_path, threads):
+def test_rows_match_python_formatter(hio, tmp_path, threads, lineage):
     from metabuli_b200 import _ffi
     from metabuli_b200.classifier import Classifier
     n = 20000
@@ -106,9 +107,29 @@ def test_rows_match_python_formatter(hio, tmp_path, threads):
     orig = (np.arange(50, dtype=np.int32) * 7 + 1000)
     rank_names = [b"no rank", b"species", b"genus", b"subspecies", b""]
     ranks = (C.c_char_p * 50)(*[rank_names[i % 5] for i in range(50)])
-    length = hio.hio_format(n, res.ctypes.data_as(C.c_void_p), pairs.ctypes.data_as(C.c_void_p), orig.ctypes.data_as(C.c_void_p), ranks, threads)
+    lin = (C.c_char_p * 50)(*[b"d_Bacteria;g_G%d;s_G%d sp" % (i, i) for i in range(50)])
+    length = hio.hio_format(n, res.ctypes.data_as(C.c_void_p), pairs.ctypes.data_as(C.c_void_p), orig.ctypes.data_as(C.c_void_p), ranks, threads,
+                            lin if lineage else None)
     got = hio.hio_text()[:length].decode()
-    tax = types.SimpleNamespace(original=lambda t: int(orig[t]), rank_of=lambda t: rank_names[t % 5].decode())
+    tax = types.SimpleNamespace(original=lambda t: int(orig[t]), rank_of=lambda t: rank_names[t % 5].decode(),
+                                lineage=lambda t: "d_Bacteria;g_G%d;s_G%d sp" % (t, t))
     fake = types.SimpleNamespace(db=types.SimpleNamespace(tax=tax))
-    want = Classifier.format_tsv(fake, names, res, pairs, header=False)
+    want = Classifier.format_tsv(fake, names, res, pairs, header=False, lineage=lineage)
     assert got == want
+
+
+def test_python_formatter_with_lineage_matches_reference(golden_dir):
+    """Classifier.format_tsv(lineage=True) over the oracle's results == the reference binary's TSV with --lineage 1."""
+    import types as _t
+    import oracle
+    import synth_cases
+    from metabuli_b200.classifier import Classifier
+    sdb, reads, seq_mode = synth_cases.build("lineage_se")
+    odb = oracle.OracleDb.from_synth(sdb)
+    v, q, cov1, cov2 = oracle.extract(*reads)
+    sv, sq = oracle.sort_kmers(v, q)
+    res, pairs = odb.score(oracle.sort_matches(odb.match(sv, sq)), cov1, None, seq_mode=seq_mode)
+    fake = _t.SimpleNamespace(db=sdb.database)
+    tsv = Classifier.format_tsv(fake, synth_cases.names(reads[1].size - 1), res, pairs, lineage=True).encode()
+    assert tsv == gzip.open(os.path.join(golden_dir, "synth", "lineage_se.tsv.gz"), "rb").read()
+    odb.close()
