@@ -207,7 +207,7 @@ def test_cpu_pinned_cases_on_gpu(name, golden_dir):
     clf = Classifier(None, opt, database=sdb.database)
     try:
         res, pairs = clf.classify_batch(*reads)
-        tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
+        tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs, lineage=bool(f["lineage"])).encode()
         assert tsv == gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
     finally:
         clf.close()

@@ -65,6 +65,7 @@ def test_score_core_matches_oracle(hl, name, force_scratch, flat, tmp_path):
     m = oracle.sort_matches(odb.match(sv, sq))
     c2 = cov2 if seq_mode == 2 else None
     fl = synth_cases.oracle_flags(name)
+    fl.pop("lineage", None)                             # a column of the TSV, not a scoring flag
     acc = fl["accession_level"]                         # loadDbParameters (common.cpp:101-108)
     if sdb.database.params.accession_level_db == 1 and acc == 0:
         acc = 2
