@@ -292,6 +292,12 @@ int classify(int argc, char** argv) {
         const char* rank_name(int32_t x) const { return t.str(t.rankIdx[t.D[x]]); }
         std::string lineage(int32_t x) const { return t.lineage(x); }
     } tv{tax};
+    // taxonomy in the shape mblhost::write_report takes (Reporter::writeReportFile, Reporter.cpp:117-193)
+    std::vector<const char*> nodeRankStr(tax.maxNodes), nodeNameStr(tax.maxNodes);
+    for (size_t i = 0; i < tax.maxNodes; ++i) { nodeRankStr[i] = tax.str(tax.rankIdx[i]); nodeNameStr[i] = tax.str(tax.nameIdx[i]); }
+    mblhost::ArrayTax rt{tax.maxNodes, tax.maxTaxID, tax.nodeTaxId.data(), tax.nodeParent.data(), tax.D,
+                         tax.internalIds ? tax.i2o : nullptr, nodeRankStr.data(), nodeNameStr.data()};
+    std::vector<uint64_t> taxCounts((size_t)tax.maxTaxID + 1, 0);           // Classifier.cpp:196-203: ++taxCounts[classification]
     uint64_t kmers = 0, matches = 0;
     auto t0 = std::chrono::steady_clock::now();
     std::thread writer;
@@ -324,11 +330,20 @@ int classify(int argc, char** argv) {
             std::vector<std::string> rows;
             mblhost::format_rows(tv, r1.names, w.r0, w.n, w.res.data(), w.pairs.data(), T, rows, par.lineage != 0);
             for (const std::string& x : rows) fwrite(x.data(), 1, x.size(), out);
+            for (size_t i = 0; i < w.n; ++i) ++taxCounts[(size_t)w.res[i].classification];
         });
         printf("Processed read count   : %zu (%g)\n", r0 + s.n, (double)(r0 + s.n) / (double)total);
     }
     if (writer.joinable()) writer.join();
     fclose(out);
+    {                                                           // <jobid>_report.tsv (Reporter.cpp:19, :117-137)
+        std::string report;
+        mblhost::write_report(rt, taxCounts, total, report);
+        FILE* rf = fopen((outDir + "/" + jobId + "_report.tsv").c_str(), "wb");
+        if (!rf) die("cannot write " + outDir + "/" + jobId + "_report.tsv");
+        fwrite(report.data(), 1, report.size(), rf);
+        fclose(rf);
+    }
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     printf("Query k-mer number     : %llu\nTotal k-mer match count: %llu\nTaxonomic classification completed. (%.3f s)\n",
            (unsigned long long)kmers, (unsigned long long)matches, sec);

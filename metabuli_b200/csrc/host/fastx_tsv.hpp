@@ -9,6 +9,7 @@
 #pragma once
 #include <zlib.h>
 
+#include <algorithm>
 #include <cctype>
 #include <cstdint>
 #include <cstdio>
@@ -225,6 +226,76 @@ void format_rows(const Tax& tax, const std::vector<std::string>& names, size_t n
     for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
     work(0);
     for (auto& x : th) x.join();
+}
+
+// ---- Reporter::writeReportFile / writeReport (Reporter.cpp:117-193) with NcbiTaxonomy::getParentToChildren / getCladeCounts
+// (NcbiTaxonomy.cpp:504-545): the Kraken-style <jobid>_report.tsv.  counts[t] = reads classified to internal taxid t
+// (counts[0] = unclassified).  Children keep node order and are ordered by clade count with std::sort, as the reference does
+// (SORT_SERIAL), so ties fall the same way; the walk starts at internal taxid 1 whatever the root is (Q11).
+// Tax must provide: size_t n_nodes(); int32_t node_taxid(size_t i), node_parent(size_t i); bool exists(int32_t t);
+// int32_t parent_of(int32_t t); int32_t max_taxid(); original(t); rank_name(t); const char* name(t).
+// the taxonomy arrays of taxonomyDB in the shape write_report wants (per node: taxid, parent taxid, rank and name strings;
+// D = taxid -> node, orig = internal -> original taxid or null)
+struct ArrayTax {
+    size_t nn; int32_t maxt; const int32_t *ntax, *npar, *D, *orig; const char* const* rank; const char* const* nm;
+    size_t n_nodes() const { return nn; }
+    int32_t node_taxid(size_t i) const { return ntax[i]; }
+    int32_t node_parent(size_t i) const { return npar[i]; }
+    int32_t max_taxid() const { return maxt; }
+    bool exists(int32_t t) const { return t >= 0 && t <= maxt && D[t] != -1; }
+    int32_t parent_of(int32_t t) const { return npar[D[t]]; }
+    int32_t original(int32_t t) const { return orig ? orig[t] : t; }
+    const char* rank_name(int32_t t) const { return rank[D[t]]; }
+    const char* name(int32_t t) const { return nm[D[t]]; }
+};
+
+template <class Tax>
+void write_report(const Tax& tax, const std::vector<uint64_t>& counts, uint64_t total_reads, std::string& out) {
+    const size_t T = (size_t)tax.max_taxid() + 1;
+    std::vector<uint64_t> clade(T, 0), own(T, 0);
+    std::vector<char> present(T, 0);
+    for (size_t t = 0; t < counts.size() && t < T; ++t) {
+        if (!counts[t]) continue;
+        own[t] = counts[t]; clade[t] += counts[t]; present[t] = 1;
+        if (tax.exists((int32_t)t)) {
+            int32_t x = (int32_t)t;
+            while (tax.parent_of(x) != x && tax.exists(tax.parent_of(x))) {
+                x = tax.parent_of(x);
+                clade[(size_t)x] += counts[t]; present[(size_t)x] = 1;
+            }
+        }
+    }
+    std::vector<std::vector<int32_t>> children(T);
+    for (size_t i = 0; i < tax.n_nodes(); ++i)
+        if (tax.node_parent(i) != tax.node_taxid(i)) children[(size_t)tax.node_parent(i)].push_back(tax.node_taxid(i));
+    char line[512];
+    out += "#clade_proportion\tclade_count\ttaxon_count\trank\ttaxID\tname\n";
+    if (clade[0] > 0) {
+        snprintf(line, sizeof line, "%.4f\t%i\t%i\tno rank\t0\tunclassified\n", 100 * clade[0] / double(total_reads), (int)clade[0], (int)own[0]);
+        out += line;
+    }
+    struct Frame { int32_t t; int depth; };
+    // explicit stack: children are pushed in reverse so that they are written in sorted order
+    std::vector<Frame> stack;
+    if (T > 1) stack.push_back(Frame{1, 0});
+    while (!stack.empty()) {
+        const Frame f = stack.back();
+        stack.pop_back();
+        if (!present[(size_t)f.t] || clade[(size_t)f.t] == 0) continue;
+        snprintf(line, sizeof line, "%.4f\t%i\t%i\t%s\t%i\t", 100 * clade[(size_t)f.t] / double(total_reads), (int)clade[(size_t)f.t],
+                 (int)own[(size_t)f.t], tax.rank_name(f.t), (int)tax.original(f.t));
+        out += line;
+        out.append((size_t)(2 * f.depth), ' ');
+        out += tax.name(f.t);
+        out.push_back('\n');
+        std::vector<int32_t> ch = children[(size_t)f.t];
+        std::sort(ch.begin(), ch.end(), [&](int a, int b) {
+            return (present[(size_t)a] ? clade[(size_t)a] : 0) > (present[(size_t)b] ? clade[(size_t)b] : 0);
+        });
+        size_t keep = 0;
+        while (keep < ch.size() && present[(size_t)ch[keep]]) ++keep;          // the reference stops at the first child without reads
+        for (size_t k = keep; k > 0; --k) stack.push_back(Frame{ch[k - 1], f.depth + 1});
+    }
 }
 
 }  // namespace mblhost

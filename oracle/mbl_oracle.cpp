@@ -1114,10 +1114,67 @@ void write_tsv_rows(const Database &db, const std::vector<Read> &m1, const std::
 }
 
 // =================================================================================================
+// Reporter::writeReportFile (Reporter.cpp:117-137), writeReport (:166-193), NcbiTaxonomy::getParentToChildren / getCladeCounts
+// (NcbiTaxonomy.cpp:504-545)
+// =================================================================================================
+namespace {
+struct CladeCnt { unsigned taxCount = 0, cladeCount = 0; std::vector<int32_t> children; };
+void report_node(const Database &db, const std::unordered_map<int32_t, CladeCnt> &cc, unsigned long total, int32_t taxId, int depth,
+                 std::string &out) {
+    auto it = cc.find(taxId);
+    const unsigned cladeCount = it == cc.end() ? 0 : it->second.cladeCount, taxCount = it == cc.end() ? 0 : it->second.taxCount;
+    char line[512];
+    if (taxId == 0) {
+        if (cladeCount > 0) {
+            snprintf(line, sizeof line, "%.4f\t%i\t%i\tno rank\t0\tunclassified\n", 100 * cladeCount / double(total), cladeCount, taxCount);
+            out += line;
+        }
+        report_node(db, cc, total, 1, 0, out);
+        return;
+    }
+    if (cladeCount == 0) return;
+    const int node = db.tax.D[taxId];
+    snprintf(line, sizeof line, "%.4f\t%i\t%i\t%s\t%i\t%s%s\n", 100 * cladeCount / double(total), cladeCount, taxCount,
+             db.tax.str(db.tax.nodeRankIdx[(size_t)node]), db.tax.original(taxId), std::string((size_t)(2 * depth), ' ').c_str(),
+             db.tax.str(db.tax.nodeNameIdx[(size_t)node]));
+    out += line;
+    std::vector<int32_t> children = it->second.children;
+    auto val = [&](int32_t k) { auto f = cc.find(k); return f == cc.end() ? 0u : f->second.cladeCount; };
+    std::sort(children.begin(), children.end(), [&](int a, int b) { return val(a) > val(b); });     // SORT_SERIAL = std::sort
+    for (int32_t c : children) {
+        if (cc.count(c)) report_node(db, cc, total, c, depth + 1, out); else break;
+    }
+}
+}  // namespace
+
+void write_report(const Database &db, const std::vector<QueryInfo> &qs, std::string &out) {
+    std::unordered_map<int32_t, unsigned> taxCnt;                       // Classifier.cpp:196-203
+    for (const QueryInfo &q : qs) ++taxCnt[q.classification];
+    std::unordered_map<int32_t, std::vector<int32_t>> p2c;
+    for (size_t i = 0; i < db.tax.maxNodes; ++i)
+        if (db.tax.nodeParent[i] != db.tax.nodeTaxId[i]) p2c[db.tax.nodeParent[i]].push_back(db.tax.nodeTaxId[i]);
+    std::unordered_map<int32_t, CladeCnt> cc;
+    for (auto &kv : taxCnt) {
+        cc[kv.first].taxCount = kv.second;
+        cc[kv.first].cladeCount += kv.second;
+        if (db.tax.nodeExists(kv.first)) {
+            int node = db.tax.D[kv.first];
+            while (db.tax.nodeParent[(size_t)node] != db.tax.nodeTaxId[(size_t)node] && db.tax.nodeExists(db.tax.nodeParent[(size_t)node])) {
+                node = db.tax.D[db.tax.nodeParent[(size_t)node]];
+                cc[db.tax.nodeTaxId[(size_t)node]].cladeCount += kv.second;
+            }
+        }
+    }
+    for (auto &kv : cc) { auto f = p2c.find(kv.first); if (f != p2c.end()) kv.second.children = f->second; }
+    out += "#clade_proportion\tclade_count\ttaxon_count\trank\ttaxID\tname\n";
+    report_node(db, cc, (unsigned long)qs.size(), 0, 0, out);
+}
+
+// =================================================================================================
 // whole path
 // =================================================================================================
 bool classify_files(const std::string &q1, const std::string &q2, const std::string &dbDir, const Options &opt,
-                    std::string &tsv, std::string *err, size_t *nKmers, size_t *nMatches) {
+                    std::string &tsv, std::string *err, size_t *nKmers, size_t *nMatches, std::string *report) {
     Database db;
     if (!db.load(dbDir, err)) return false;
     std::vector<Read> m1, m2;
@@ -1144,6 +1201,7 @@ bool classify_files(const std::string &q1, const std::string &q2, const std::str
     tsv.clear();
     write_tsv_header(tsv, opt.printLineage != 0);
     write_tsv_rows(db, m1, queries, tsv, opt.printLineage != 0);
+    if (report) { report->clear(); write_report(db, queries, *report); }
     return true;
 }
 

@@ -144,6 +144,9 @@ void score_reads(const Database &db, const Options &opt, const std::vector<Match
 void write_tsv_header(std::string &out, bool lineage = false);
 void write_tsv_rows(const Database &db, const std::vector<Read> &m1, const std::vector<QueryInfo> &q, std::string &out, bool lineage = false);
 
+// Reporter::writeReportFile / writeReport (Reporter.cpp:117-193): text of <jobid>_report.tsv from the per-read classifications
+void write_report(const Database &db, const std::vector<QueryInfo> &q, std::string &out);
+
 // delta codec (A6) — exposed for tests
 uint64_t next_target_kmer(uint64_t prev, const uint16_t *diff, size_t &idx);   // KmerMatcher.h:282-297
 void encode_delta(uint64_t delta, std::vector<uint16_t> &out);                // IndexCreator.cpp:874-892
@@ -154,6 +157,6 @@ uint16_t hammings_rev(uint64_t a, uint64_t b);                                 /
 // whole path, file to TSV text (Classifier.cpp:44-164 minus batching, which does not change results)
 bool classify_files(const std::string &q1, const std::string &q2, const std::string &dbDir,
                     const Options &opt, std::string &tsv, std::string *err,
-                    size_t *nKmers = nullptr, size_t *nMatches = nullptr);
+                    size_t *nKmers = nullptr, size_t *nMatches = nullptr, std::string *report = nullptr);
 
 }  // namespace orc

@@ -176,11 +176,13 @@ int orc_classify_files(const char* q1, const char* q2, const char* db_dir, int s
                        size_t* n_kmers, size_t* n_matches, char* err, size_t errlen) {
     Options opt = g_flags;
     opt.seqMode = seq_mode; opt.threads = threads;
-    std::string tsv, e;
-    if (!classify_files(q1, q2 ? q2 : "", db_dir, opt, tsv, &e, n_kmers, n_matches)) { set_err(err, errlen, e); return -1; }
+    std::string tsv, e, report;
+    if (!classify_files(q1, q2 ? q2 : "", db_dir, opt, tsv, &e, n_kmers, n_matches, &report)) { set_err(err, errlen, e); return -1; }
     std::ofstream f(out_path, std::ios::binary);
     f << tsv;
-    return f.good() ? 0 : -1;
+    std::ofstream r(std::string(out_path) + ".report", std::ios::binary);      // <out_path>.report = text of <jobid>_report.tsv
+    r << report;
+    return f.good() && r.good() ? 0 : -1;
 }
 
 // primitives for unit tests

@@ -33,6 +33,9 @@ for name in list(synth_cases.CASES) + list(synth_cases.CPU_CASES):
     tsv = open(os.path.join(work, name + "_classifications.tsv"), "rb").read()
     with open(os.path.join(out_dir, name + ".tsv.gz"), "wb") as f:
         f.write(gzip.compress(tsv, 9, mtime=0))
+    rep = open(os.path.join(work, name + "_report.tsv"), "rb").read()          # Reporter::writeReportFile
+    with open(os.path.join(out_dir, name + ".report.gz"), "wb") as f:
+        f.write(gzip.compress(rep, 9, mtime=0))
     with open(os.path.join(out_dir, name + ".md5"), "w") as f:
         f.write(synth_cases.fingerprint(sdb, reads) + "\n")
     stats = [l for l in r.stdout.split("\n") if "match count" in l or "k-mer number" in l]

@@ -36,5 +36,16 @@ unsigned long long hio_format(unsigned long long n, const mbl_read_result* res, 
     for (auto& r : rows) g_text += r;
     return g_text.size();
 }
+// <jobid>_report.tsv from per-read classifications (internal taxids) and the taxonomy arrays
+unsigned long long hio_report(unsigned long long n_reads, const int32_t* classification, unsigned long long n_nodes, int32_t max_taxid,
+                              const int32_t* node_taxid, const int32_t* node_parent, const int32_t* D, const int32_t* orig,
+                              const char* const* node_rank, const char* const* node_name) {
+    mblhost::ArrayTax t{(size_t)n_nodes, max_taxid, node_taxid, node_parent, D, orig, node_rank, node_name};
+    std::vector<uint64_t> counts((size_t)max_taxid + 1, 0);
+    for (unsigned long long i = 0; i < n_reads; ++i) ++counts[(size_t)classification[i]];
+    g_text.clear();
+    mblhost::write_report(t, counts, n_reads, g_text);
+    return g_text.size();
+}
 const char* hio_text() { return g_text.c_str(); }
 }

@@ -111,3 +111,6 @@ def test_cpp_host_cli_writes_the_reference_tsv(db, mode, batch, fixtures_dir, go
     golden = gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_classifications.tsv.gz"), "rb").read()
     assert got == golden
     assert "Total read count : 5000" in r.stdout
+    # the Kraken-style report (Reporter::writeReportFile)
+    report = gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_report.tsv.gz"), "rb").read()
+    assert open(tmp_path / "job_report.tsv", "rb").read() == report

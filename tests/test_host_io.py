@@ -30,6 +30,8 @@ def hio():
     L.hio_format.argtypes = [C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
     L.hio_format.restype = C.c_ulonglong
     L.hio_text.restype = C.c_char_p
+    L.hio_report.argtypes = [C.c_ulonglong, C.c_void_p, C.c_ulonglong, C.c_int32] + [C.c_void_p] * 6
+    L.hio_report.restype = C.c_ulonglong
     return L
 
 
@@ -133,3 +135,52 @@ def test_python_formatter_with_lineage_matches_reference(golden_dir):
     tsv = Classifier.format_tsv(fake, synth_cases.names(reads[1].size - 1), res, pairs, lineage=True).encode()
     assert tsv == gzip.open(os.path.join(golden_dir, "synth", "lineage_se.tsv.gz"), "rb").read()
     odb.close()
+
+
+@pytest.mark.parametrize("name", ["multi_se", "ties_se", "multi_pe", "acc_prune_se", "flags_se"])
+def test_cpp_report_matches_reference(hio, name, golden_dir):
+    """mblhost::write_report (the C++ host's <jobid>_report.tsv) over the oracle's per-read classifications == the reference
+    binary's report, ties between equally large clades included (children keep node order, std::sort as in the reference)."""
+    import oracle
+    import synth_cases
+    sdb, reads, seq_mode = synth_cases.build(name)
+    odb = oracle.OracleDb.from_synth(sdb)
+    fl = synth_cases.oracle_flags(name)
+    fl.pop("lineage", None)
+    if sdb.database.params.accession_level_db == 1 and fl["accession_level"] == 0:
+        fl["accession_level"] = 2
+    v, q, cov1, cov2 = oracle.extract(*reads, kmer_format=sdb.database.params.kmer_format)
+    sv, sq = oracle.sort_kmers(v, q)
+    res, _ = odb.score(oracle.sort_matches(odb.match(sv, sq)), cov1, cov2 if seq_mode == 2 else None, seq_mode=seq_mode, **fl)
+    t = sdb.database.tax
+    cls = np.ascontiguousarray(res["classification"], dtype=np.int32)
+    n = t.max_nodes
+    ranks = (C.c_char_p * n)(*[t.node_rank_name[i].encode() for i in range(n)])
+    names = (C.c_char_p * n)(*[t.string(int(t.node_name_idx[i])).encode() for i in range(n)])
+    orig = np.ascontiguousarray(t.internal2org, dtype=np.int32) if t.internal_ids else None
+    length = hio.hio_report(cls.size, cls.ctypes.data_as(C.c_void_p), n, t.max_taxid, t.node_taxid.ctypes.data_as(C.c_void_p),
+                            t.node_parent.ctypes.data_as(C.c_void_p), t.D.ctypes.data_as(C.c_void_p),
+                            orig.ctypes.data_as(C.c_void_p) if orig is not None else None, ranks, names)
+    got = hio.hio_text()[:length]
+    assert got == gzip.open(os.path.join(golden_dir, "synth", name + ".report.gz"), "rb").read()
+    odb.close()
+
+
+@pytest.mark.parametrize("db", ["in", "ex"])
+def test_cpp_report_on_the_reference_fixture(hio, db, fixtures_dir, golden_dir):
+    """Same on the regression fixture database (original taxids differ from internal ones, the report walk starts at internal
+    taxid 1 = Viruses rather than at the root, Q11): per-read classifications parsed back from the reference's own TSV."""
+    from metabuli_b200 import load_database
+    d = load_database(os.path.join(fixtures_dir, f"db_{db}"))
+    t = d.tax
+    org2int = {int(o): i for i, o in enumerate(t.internal2org) if t.D[i] != -1} if t.internal_ids else None
+    rows = gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_se_classifications.tsv.gz"), "rt").read().split("\n")[1:]
+    cls = np.array([(org2int[int(r.split("\t")[2])] if org2int and int(r.split("\t")[2]) else int(r.split("\t")[2])) for r in rows if r], dtype=np.int32)
+    n = t.max_nodes
+    ranks = (C.c_char_p * n)(*[t.node_rank_name[i].encode() for i in range(n)])
+    names = (C.c_char_p * n)(*[t.string(int(t.node_name_idx[i])).encode() for i in range(n)])
+    orig = np.ascontiguousarray(t.internal2org, dtype=np.int32) if t.internal_ids else None
+    length = hio.hio_report(cls.size, cls.ctypes.data_as(C.c_void_p), n, t.max_taxid, t.node_taxid.ctypes.data_as(C.c_void_p),
+                            t.node_parent.ctypes.data_as(C.c_void_p), t.D.ctypes.data_as(C.c_void_p),
+                            orig.ctypes.data_as(C.c_void_p) if orig is not None else None, ranks, names)
+    assert hio.hio_text()[:length] == gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_se_report.tsv.gz"), "rb").read()

@@ -31,6 +31,9 @@ def test_oracle_matches_reference_tsv(db, mode, fixtures_dir, golden_dir, tmp_pa
     assert hashlib.md5(data).hexdigest() == want_md5
     golden = gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_classifications.tsv.gz"), "rb").read()
     assert data == golden
+    # <jobid>_report.tsv: walked from internal taxid 1, which is not the root in this taxonomy (Q11)
+    report = gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_report.tsv.gz"), "rb").read()
+    assert open(out + ".report", "rb").read() == report
 
 
 def test_oracle_thread_invariance(fixtures_dir, tmp_path):

@@ -27,3 +27,6 @@ def test_oracle_matches_reference_on_synthetic(name, golden_dir, tmp_path):
     oracle.classify_files(q1, q2, db_dir, seq_mode, out, threads=3, **synth_cases.oracle_flags(name))
     golden = gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
     assert open(out, "rb").read() == golden
+    # <jobid>_report.tsv (Reporter::writeReportFile): clade counts walked from internal taxid 1, children by clade count (std::sort)
+    want_report = gzip.open(os.path.join(golden_dir, "synth", name + ".report.gz"), "rb").read()
+    assert open(out + ".report", "rb").read() == want_report
