@@ -92,15 +92,16 @@ def test_end_to_end_tsv_matches_reference(case, golden_dir):
     assert st["kernel_launches"] > 0
 
 
-@pytest.mark.parametrize("db,mode,batch", [("in", "pe", 0), ("in", "se", 1500), ("ex", "pe", 777)])
-def test_cpp_host_cli_writes_the_reference_tsv(db, mode, batch, fixtures_dir, golden_dir, tmp_path):
+@pytest.mark.parametrize("db,mode,batch,ext", [("in", "pe", 0, "fna.gz"), ("in", "se", 1500, "fna.gz"), ("ex", "pe", 777, "fna.gz"),
+                                               ("ex", "se", 0, "fq.gz")])
+def test_cpp_host_cli_writes_the_reference_tsv(db, mode, batch, ext, fixtures_dir, golden_dir, tmp_path):
     """The C++ host (`metabuli-b200 classify`, same command line as the reference): parallel FASTA reader, streamed batches
     (next batch uploads while the current one is classified), parallel TSV writer -> the reference binary's TSV, byte for byte."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "metabuli_b200", "_lib", "metabuli-b200")
     assert os.path.exists(exe), "run __graft_entry__.build() first"
-    reads = [os.path.join(fixtures_dir, "reads", f"ERR9594652_5000_{k}.fna.gz") for k in ((1, 2) if mode == "pe" else (1,))]
+    reads = [os.path.join(fixtures_dir, "reads", f"ERR9594652_5000_{k}.{ext}") for k in ((1, 2) if mode == "pe" else (1,))]
     cmd = [exe, "classify", "--seq-mode", "2" if mode == "pe" else "1", "--threads", "4"]
     if batch:
         cmd += ["--batch-reads", str(batch)]

@@ -70,7 +70,8 @@ def _write_cases(tmp_path):
 @pytest.mark.parametrize("threads", [1, 7])
 def test_parallel_reader_matches_python_mirror(hio, tmp_path, fixtures_dir, threads):
     from metabuli_b200.fastx import read_fastx
-    paths = _write_cases(tmp_path) + [os.path.join(fixtures_dir, "reads", "ERR9594652_5000_1.fna.gz")]
+    paths = _write_cases(tmp_path) + [os.path.join(fixtures_dir, "reads", "ERR9594652_5000_1.fna.gz"),
+                                      os.path.join(fixtures_dir, "reads", "ERR9594652_5000_2.fq.gz")]
     for p in paths:
         names, bases, offs = _load(hio, p, threads)
         wn, wb, wo = read_fastx(p)
