@@ -5,7 +5,8 @@
 #  1. builds the unmodified reference out of tree in /tmp (SURVEY.md §8c command; the reference needs its
 #     own cmake build + generated sources, so it is NOT shipped as oracle/_ref — see DESIGN.md),
 #  2. runs `metabuli classify` on the regression fixtures (4 configs) -> tests/golden/ref_tsv/*.tsv.gz,
-#  3. runs it on the seeded synthetic cases of tests/synth_cases.py  -> tests/golden/synth/<case>.tsv.gz
+#  3. runs it on the seeded synthetic cases of tests/synth_cases.py (CASES and CPU_CASES, with the flags of FLAGS)
+#     -> tests/golden/synth/<case>.tsv.gz, <case>.report.gz
 #     (+ <case>.md5 = fingerprint of the generated inputs, so a test can tell "inputs differ" from "bug").
 set -euo pipefail
 REPO=$(cd "$(dirname "$0")/../.." && pwd)
@@ -22,7 +23,10 @@ mkdir -p $REPO/tests/golden/ref_tsv $REPO/tests/golden/synth
 for db in in ex; do
   $BIN classify --seq-mode 1 $D/reads/ERR9594652_5000_1.fna $D/reference/$db $OUT ${db}_se --threads 1 --max-ram 6 >/dev/null
   $BIN classify $D/reads/ERR9594652_5000_1.fna $D/reads/ERR9594652_5000_2.fna $D/reference/$db $OUT ${db}_pe --threads 1 --max-ram 6 >/dev/null
-  for m in se pe; do gzip -9 -n -c $OUT/${db}_${m}_classifications.tsv > $REPO/tests/golden/ref_tsv/${db}_${m}_classifications.tsv.gz; done
+  for m in se pe; do
+    gzip -9 -n -c $OUT/${db}_${m}_classifications.tsv > $REPO/tests/golden/ref_tsv/${db}_${m}_classifications.tsv.gz
+    gzip -9 -n -c $OUT/${db}_${m}_report.tsv > $REPO/tests/golden/ref_tsv/${db}_${m}_report.tsv.gz
+  done
 done
 cd $REPO && python tests/golden/gen_synth_golden.py $BIN $OUT
 rm -rf $OUT
