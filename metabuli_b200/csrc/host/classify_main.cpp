@@ -182,8 +182,17 @@ int classify(int argc, char** argv) {
         else if (a == "--device") par.device = atoi(val());
         else if (a == "--batch-reads") par.batchReads = (size_t)atoll(val());
         else if (a == "--lineage") par.lineage = atoi(val());
-        else if (a == "--max-ram" || a == "--mask" || a == "--mask-prob" || a == "-v" || a == "--hamming-margin" ||
-                 a == "--validate-input" || a == "--validate-db" || a == "--taxonomy-path") val();
+        // flags that change the reference's output and are not implemented here must fail, never be dropped silently:
+        // --mask 1 masks low-complexity regions before extraction (KmerExtractor.cpp:308-314, SeqIterator.cpp:154-175),
+        // --taxonomy-path replaces the database's taxonomy (classify.cpp / TaxonomyWrapper)
+        else if (a == "--mask") { if (atoi(val()) != 0) die("--mask 1 (tantan masking of the queries) is not supported by the B200 path; run with --mask 0 (the default)"); }
+        else if (a == "--taxonomy-path") { if (std::string(val()) != "") die("--taxonomy-path is not supported by the B200 path: the taxonomy is read from <dbdir>/taxonomyDB"); }
+        else if (a == "--reduced-aa") { if (atoi(val()) != 0) die("--reduced-aa 1 is not supported by the B200 path"); }
+        // flags without influence on the classifications: --max-ram only sizes the reference's query splits (here: HBM budget),
+        // --mask-prob is read by --mask 1 only, --hamming-margin is parsed but unused by the reference (KmerMatcher.cpp:1117-1146), -v is verbosity
+        else if (a == "--max-ram" || a == "--mask-prob" || a == "-v" || a == "--hamming-margin") val();
+        // the validators only check the inputs and exit on malformed files; on valid inputs the output is unchanged
+        else if (a == "--validate-input" || a == "--validate-db") { if (atoi(val()) != 0) fprintf(stderr, "warning: %s is ignored by the B200 path (inputs are not validated)\n", a.c_str()); }
         else if (a.rfind("--", 0) == 0) die("unknown flag " + a);
         else par.files.push_back(a);
     }

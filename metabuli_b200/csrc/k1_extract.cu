@@ -185,7 +185,7 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
                         if (need) {
                             if (chunk_used + need > kExtractChunk) {          // blank out the rest of the old chunk, take a new one
                                 if (chunk_base + kExtractChunk <= out_cap)
-                                    for (uint32_t w = chunk_used + lane; w < kExtractChunk; w += 32) { value[chunk_base + w] = kBlank; qinfo[chunk_base + w] = 0ull; slot_idx[chunk_base + w] = (uint32_t)(chunk_base + w); }
+                                    for (uint32_t w = chunk_used + lane; w < kExtractChunk; w += 32) { value[chunk_base + w] = kBlank; qinfo[chunk_base + w] = 0ull; }
                                 unsigned long long nb = 0;
                                 if (lane == 0) nb = atomicAdd(out_cursor, (unsigned long long)kExtractChunk);
                                 chunk_base = __shfl_sync(0xffffffffu, nb, 0);
@@ -194,8 +194,8 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
                             const uint32_t lt = (1u << lane) - 1u;
                             const bool room = chunk_base + kExtractChunk <= out_cap;   // else: capacity guess too small, the host redoes K1
                             if (!room) { chunk_used += need; continue; }
-                            if (pF) { const uint64_t s = chunk_base + chunk_used + __popc(bF & lt); value[s] = vF; qinfo[s] = pack_qinfo(r + 1, pos, frameF); slot_idx[s] = (uint32_t)s; }
-                            if (pR) { const uint64_t s = chunk_base + chunk_used + nF + __popc(bR & lt); value[s] = vR; qinfo[s] = pack_qinfo(r + 1, pos, frameR); slot_idx[s] = (uint32_t)s; }
+                            if (pF) { const uint64_t s = chunk_base + chunk_used + __popc(bF & lt); value[s] = vF; qinfo[s] = pack_qinfo(r + 1, pos, frameF); }
+                            if (pR) { const uint64_t s = chunk_base + chunk_used + nF + __popc(bR & lt); value[s] = vR; qinfo[s] = pack_qinfo(r + 1, pos, frameR); }
                             chunk_used += need;
                             pass_cnt += (lane == 0) ? need : 0u;
                         }
@@ -217,7 +217,7 @@ extract_kernel(const uint8_t* __restrict__ bases1, const uint64_t* __restrict__ 
     if (FILTER) {
         // n_valid[0] = metamers that passed the filter (what the sort and the merge see), n_valid[5] = valid metamers extracted
         if (chunk_used < kExtractChunk && chunk_used > 0 && chunk_base + kExtractChunk <= out_cap)
-            for (uint32_t w = chunk_used + lane; w < kExtractChunk; w += 32) { value[chunk_base + w] = kBlank; qinfo[chunk_base + w] = 0ull; slot_idx[chunk_base + w] = (uint32_t)(chunk_base + w); }
+            for (uint32_t w = chunk_used + lane; w < kExtractChunk; w += 32) { value[chunk_base + w] = kBlank; qinfo[chunk_base + w] = 0ull; }
         if (lane == 0 && pass_cnt) atomicAdd(n_valid, (unsigned long long)pass_cnt);
         if (lane == 0 && valid_cnt) atomicAdd(n_valid + 5, (unsigned long long)valid_cnt);
         return;
@@ -246,7 +246,7 @@ void launch_extract(int format, const uint8_t* bases1, const uint64_t* off1, con
     unsigned blocks = (n_reads + kWarpsPerBlock - 1) / kWarpsPerBlock;
     unsigned cap = (unsigned)sm_count * 64u;          // grid-stride beyond a few waves
     if (blocks > cap) blocks = cap;
-    const bool filtered = filter.words != nullptr && out_cursor != nullptr && slot_idx != nullptr;
+    const bool filtered = filter.words != nullptr && out_cursor != nullptr;
 #define MBL_LAUNCH_EXTRACT(F, B)                                                                                             \
     extract_kernel<F, B><<<blocks, kWarpsPerBlock * 32, 0, st>>>(bases1, off1, bases2, off2, n_reads, cov1, w1, w2, slot_off, \
                                                                  base_code, codon, value, qinfo, slot_idx, n_valid, filter, out_cursor, out_cap, smer_len)

@@ -218,9 +218,8 @@ __global__ void merge_item_fill_kernel(const Tile* __restrict__ tiles, uint64_t 
 }
 
 // ---- the merge kernel ------------------------------------------------------------------------------
-// kDirect (MergeArgs::direct, experimental): the query's qinfo travels with its value through the sort, and a lane settles its
-// own query — group minimum, then its surviving candidates — instead of the queue + pair sweeps below.
-template <int kThreads, bool kDirect>
+// v1 (MBL_MERGE_V1=1): warp-private hit queues + two pair sweeps per 32 hits.
+template <int kThreads>
 __global__ void __launch_bounds__(kThreads, kThreads == 256 ? 3 : 2)
 merge_kernel(MergeArgs a) {
     constexpr int kWarps = kThreads / 32;
@@ -362,97 +361,6 @@ merge_kernel(MergeArgs a) {
             infos = a.info + it.info_begin;
         }
 
-        if (kDirect) {
-            // -- 3'. lane per query.  With the presence filter three quarters of the queries that get here have their group, so
-            //        the lanes are busy without a hit queue.  Pass 1 walks the group for the minimum Hamming sum (a candidate
-            //        equal to its predecessor — the same k-mer in a sister species — reuses the predecessor's sum; the sums of the
-            //        first 16 candidates are kept, 4 bits each), pass 2 lets every lane step to its next surviving candidate and
-            //        the warp writes those rows together (ballot-ranked slots, rows straight from registers).
-            const uint32_t n_chunks_d = (uint32_t)((it.q_end - it.q_begin + 31) >> 5);
-            const uint32_t lt = (1u << lane) - 1u;
-            for (uint32_t ch = (uint32_t)warp; ch < n_chunks_d; ch += kWarps) {
-                const uint64_t qi = it.q_begin + (uint64_t)ch * 32 + lane;
-                const bool active = qi < it.q_end;
-                const uint64_t qv = active ? ld_stream_u64(a.q_value + qi) : kBlank;
-                const uint64_t qinfo = active ? ld_stream_u64(a.q_info + qi) : 0ull;
-                const uint64_t q40 = qv >> 24;
-                const uint32_t qd = (uint32_t)qv & 0xFFFFFFu;
-                uint32_t g0 = 0;
-                bool hit = false;
-                if (!jumbo) {
-                    if (active) {
-                        const uint32_t h = aa_hash(q40);
-                        const uint32_t tag = h & 0x7FFFFu;
-                        uint32_t bkt = h >> hash_shift;
-                        while (true) {
-                            const uint2 e = *reinterpret_cast<const uint2*>(s_tab + 2u * bkt);
-                            if (e.x == kEmpty) break;
-                            if ((e.x & 0x7FFFFu) == tag && (vals[e.x >> 19] >> 24) == q40) { g0 = e.x >> 19; hit = true; break; }
-                            if (e.y == kEmpty) break;
-                            if ((e.y & 0x7FFFFu) == tag && (vals[e.y >> 19] >> 24) == q40) { g0 = e.y >> 19; hit = true; break; }
-                            bkt = (bkt + 1) & bucket_mask;
-                        }
-                    }
-                } else if (active) {
-                    uint32_t lo = 0, hi = nk;
-                    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((vals[mid] >> 24) < q40) lo = mid + 1; else hi = mid; }
-                    if (lo < nk && (vals[lo] >> 24) == q40) { g0 = lo; hit = true; }
-                }
-                if (!__any_sync(kFull, hit)) continue;
-                // pass 1: group end and minimum
-                uint32_t end = g0, best = 255u;
-                uint64_t packed = 0;                                       // sums of candidates g0 .. g0+15, 4 bits each
-                if (hit) {
-                    uint32_t prev_td = 0xFFFFFFFFu, prev_sum = 0;
-                    while (end < nk && (vals[end] >> 24) == q40) {
-                        const uint32_t td = (uint32_t)vals[end] & 0xFFFFFFu;
-                        const uint32_t sum = td == prev_td ? prev_sum : (td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td)));
-                        prev_td = td; prev_sum = sum;
-                        best = min(best, sum);
-                        if (end - g0 < 16u) packed |= (uint64_t)min(sum, 15u) << (4u * (end - g0));
-                        ++end;
-                    }
-                }
-                const uint32_t limit = min(best * 2u, 7u);                 // KmerMatcher.cpp:1136
-                // pass 2: survivors
-                uint32_t j = g0;
-                while (true) {
-                    uint32_t td = 0, sum = 255u;
-                    while (j < end) {                                      // this lane's next surviving candidate
-                        td = (uint32_t)vals[j] & 0xFFFFFFu;
-                        sum = (j - g0 < 16u) ? (uint32_t)(packed >> (4u * (j - g0))) & 15u : (td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td)));
-                        if (sum <= limit) break;
-                        ++j;
-                    }
-                    const bool sel = j < end;
-                    const uint32_t bal = __ballot_sync(kFull, sel);
-                    if (!bal) break;
-                    const uint32_t cnt = __popc(bal);
-                    const Reservation rs = reserve(chunk, cnt, a.out_count, lane);
-                    if (sel) {
-                        const int32_t taxid = (int32_t)((uint32_t)infos[j] & a.info_mask);
-                        const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
-                        if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);              // Q2
-                        uint32_t field = 0u;
-                        if (sum) field = ham_fields(ham_lookup(s_ham, qd, td), qd, td, !((qi_frame(qinfo) < 3) ^ fmt2));
-                        const uint64_t sl = slot_of(rs, (uint32_t)__popc(bal & lt));
-                        if (sl < a.out_cap) {
-                            uint64_t* o = reinterpret_cast<uint64_t*>(a.out + sl);
-                            o[0] = qinfo;
-                            o[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
-                            o[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
-                        }
-                        ++j;
-                    }
-                    my_matches += cnt;
-                }
-            }
-            if (tid == 0) s_item[slot] = pending;
-            __syncthreads();
-            item = next_item;
-            slot ^= 1;
-            continue;
-        }
         // -- 3. stream the query slice.  A warp looks up 32 queries per iteration and appends the ones that found
         //       their amino-acid group ("hits") to its private queue.  32 queued hits are expanded into their
         //       (query, candidate) pairs, which are spread evenly over the lanes in batches of 32: sweep 1 finds every
@@ -648,8 +556,406 @@ merge_kernel(MergeArgs a) {
     if (lane == 0 && my_matches) atomicAdd(a.out_count + 1, my_matches);
 }
 
+// ---- the merge kernel, v2 -------------------------------------------------------------------------------------------------
+// Same staging and decode as v1, but the match stage is balanced over the whole CTA instead of living in warp-private queues
+// (v1 left 17 % of the stall samples at the closing barrier of an item, waiting for the warp with the fullest queue, and paid
+// ~365 warp instructions per 32 (query, candidate) pairs for two shuffle-searched sweeps):
+//   probe   a thread looks up one query per step; a hit appends {group start | length, pair offset, minimum | query DNA, qinfo}
+//           to a CTA-wide hit list (one shared-memory atomic per warp and step), its qinfo word is loaded right there (it travels
+//           through the K2 sort next to the value, so this is a coalesced stream and not a gather), and the hit's thread writes
+//           its index into the owner slot of every (query, candidate) pair the hit expands to;
+//   pass 1  pairs are spread over all threads: Hamming sum over the 8 KiB two-codon table, one byte per pair kept, atomicMin
+//           into the hit's record;
+//   pass 2  pairs again: keep those with sum <= min(2 * minimum, 7) (KmerMatcher.cpp:1136), ballot-compact the warp's
+//           survivors into its staging buffer and write the rows out as contiguous 8-byte words.
+// A round takes up to 2 * kThreads queries and 8 * kThreads pairs; a round with more pairs (a hot amino-acid group) walks the
+// pair range in windows and recomputes the sums in pass 2.  Jumbo items (an amino-acid group larger than a shared-memory tile:
+// values pre-decoded in HBM) take a plain lane-per-query path.
+struct SmemLayout2 {
+    uint32_t off_rec, off_scan, off_ham, off_hg, off_hp, off_hm, off_hq, off_owner, off_psum, off_stage, off_bits, off_frag, off_info, off_vals,
+        off_tab, total;
+};
+__host__ __device__ inline SmemLayout2 smem_layout2(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets, uint32_t kThreads) {
+    const uint32_t kWarps = kThreads / 32, kQR = 2 * kThreads, kPC = 8 * kThreads;
+    SmemLayout2 l;
+    uint32_t o = 64;                                   // two mbarriers, two item slots, hit / pair counters
+    l.off_rec = o;    o += 2 * 64;                     // work item records: current / next
+    l.off_scan = o;   o += 2 * 2 * kWarps * 8;         // block_decode cross-warp scan
+    l.off_ham = o;    o += 8192;                       // two-codon table
+    l.off_hq = o;     o += kQR * 8;                    // hit list: qinfo
+    l.off_hg = o;     o += kQR * 4;                    //           group start | length << 16
+    l.off_hp = o;     o += kQR * 4;                    //           first pair of the hit
+    l.off_hm = o;     o += kQR * 4;                    //           minimum Hamming sum << 24 | query DNA part
+    l.off_owner = o;  o += kPC * 2;                    // pair -> hit
+    l.off_psum = o;   o += kPC;                        // pair -> Hamming sum
+    o = (o + 15) & ~15u;
+    l.off_stage = o;  o += kWarps * 32 * 24;           // per-warp staging of up to 32 Match rows
+    l.off_bits = o;   o += ((max_kmers + 63) / 32) * 4;
+    o = (o + 15) & ~15u;
+    l.off_frag = o;   o += (max_u16 + 16) * 2;
+    l.off_info = o;   o += (max_kmers + 8) * 4;
+    o = (o + 15) & ~15u;
+    l.off_vals = o;   o += max_kmers * 8;
+    l.off_tab = o;    o += n_buckets * 4;
+    l.total = (o + 15) & ~15u;
+    return l;
+}
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 2)
+merge_kernel_v2(MergeArgs a) {
+    constexpr int kWarps = kThreads / 32;
+    constexpr uint32_t kQR = 2 * kThreads;            // queries per round
+    constexpr uint32_t kPC = 8 * kThreads;            // pairs per window
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SmemLayout2 L = smem_layout2(a.max_u16, a.max_kmers, a.n_buckets, kThreads);
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);          // [0] fragments, [1] taxids
+    unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 32);                 // [2] claimed item numbers
+    unsigned int* s_nhit = reinterpret_cast<unsigned int*>(smem + 40);
+    unsigned int* s_npair = reinterpret_cast<unsigned int*>(smem + 44);
+    MergeItem* s_rec = reinterpret_cast<MergeItem*>(smem + L.off_rec);
+    uint64_t* s_scan = reinterpret_cast<uint64_t*>(smem + L.off_scan);
+    uint16_t* s_ham = reinterpret_cast<uint16_t*>(smem + L.off_ham);
+    uint64_t* s_hq = reinterpret_cast<uint64_t*>(smem + L.off_hq);
+    uint32_t* s_hg = reinterpret_cast<uint32_t*>(smem + L.off_hg);
+    uint32_t* s_hp = reinterpret_cast<uint32_t*>(smem + L.off_hp);
+    uint32_t* s_hm = reinterpret_cast<uint32_t*>(smem + L.off_hm);
+    uint16_t* s_owner = reinterpret_cast<uint16_t*>(smem + L.off_owner);
+    uint8_t* s_psum = smem + L.off_psum;
+    uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem + L.off_stage);
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.off_bits);
+    uint16_t* s_frag = reinterpret_cast<uint16_t*>(smem + L.off_frag);
+    int32_t* s_info = reinterpret_cast<int32_t*>(smem + L.off_info);
+    uint64_t* s_vals = reinterpret_cast<uint64_t*>(smem + L.off_vals);
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + L.off_tab);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int i = tid; i < 4096; i += kThreads) s_ham[i] = a.ham_pair[i];
+    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); *s_nhit = 0u; *s_npair = 0u; }
+    unsigned parity_bits = 0u;
+    const uint32_t n_items_all = a.item_off[a.n_tiles];
+    const uint32_t n_items = (uint32_t)min((uint64_t)n_items_all, a.items_cap);
+    if (n_items_all > n_items && blockIdx.x == 0 && tid == 0) atomicOr(a.error_flag, 2u);   // work list too short: host retries
+    const bool fmt2 = a.kmer_format == 2;
+    const bool via_idx = a.q_idx != nullptr;
+    const uint32_t bucket_mask = a.n_buckets / 2 - 1;
+    const int hash_shift = 32 - (31 - __clz(a.n_buckets / 2));
+    uint64_t* my_stage = s_stage + warp * 96;
+    unsigned long long my_matches = 0;
+    OutChunk chunk;
+
+    auto stage_frag = [&](const MergeItem& r) {
+        if (r.jumbo_off != kNone) return;
+        const uint64_t d0 = r.diff_begin, d1 = r.diff_begin + r.n_u16;
+        const uint64_t a0 = d0 & ~7ull, a1 = (d1 + 7ull) & ~7ull;
+        fence_proxy_async();
+        mbar_expect_tx(mbar, (unsigned)((a1 - a0) * 2));
+        tma_load_1d(s_frag, a.diff + a0, (unsigned)((a1 - a0) * 2), mbar);
+    };
+    // warp-collective: ballot-compact the selected lanes' Match rows (Match.h:9-26 without the vptr) into the warp's staging
+    // buffer and write them as contiguous 8-byte words; Q2: taxid 0 / unmapped species raise the error flag
+    auto emit = [&](bool sel, uint64_t qinfo, int32_t taxid_raw, uint32_t qd, uint32_t td, uint32_t sum) {
+        const uint32_t bal = __ballot_sync(kFull, sel);
+        if (!bal) return;
+        const uint32_t cnt = __popc(bal);
+        const Reservation rs = reserve(chunk, cnt, a.out_count, lane);
+        if (sel) {
+            const int32_t taxid = (int32_t)((uint32_t)taxid_raw & a.info_mask);
+            const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? __ldg(a.taxid2species + taxid) : 0;
+            uint32_t field = 0u;
+            if (sum) field = ham_fields(ham_lookup(s_ham, qd, td), qd, td, !((qi_frame(qinfo) < 3) ^ fmt2));   // KmerMatcher.cpp:1140
+            if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);
+            uint64_t* w = my_stage + 3u * (uint32_t)__popc(bal & lt);
+            w[0] = qinfo;
+            w[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
+            w[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
+        }
+        __syncwarp();
+        if (cnt <= rs.rem) {                                                    // one contiguous run of slots (the usual case)
+            const uint64_t s0 = rs.old_base + rs.old_used;
+            if (s0 + cnt <= a.out_cap) {
+                uint64_t* dst = reinterpret_cast<uint64_t*>(a.out + s0);
+                const uint32_t nw3 = 3u * cnt;                                  // <= 96 words: three predicated copies
+                if ((uint32_t)lane < nw3) dst[lane] = my_stage[lane];
+                if ((uint32_t)lane + 32u < nw3) dst[lane + 32] = my_stage[lane + 32];
+                if ((uint32_t)lane + 64u < nw3) dst[lane + 64] = my_stage[lane + 64];
+            }
+        } else {
+            for (uint32_t w = lane; w < 3u * cnt; w += 32) {
+                const uint32_t r = w / 3u;
+                const uint64_t sl = slot_of(rs, r);
+                if (sl < a.out_cap) reinterpret_cast<uint64_t*>(a.out + sl)[w - 3u * r] = my_stage[w];
+            }
+        }
+        __syncwarp();
+        my_matches += cnt;
+    };
+
+    if (tid == 0) {
+        s_item[0] = atomicAdd(a.item_cursor, 1u);
+        s_item[1] = atomicAdd(a.item_cursor, 1u);
+        if (s_item[0] < n_items) { s_rec[0] = a.items[s_item[0]]; }
+    }
+    __syncthreads();
+    uint32_t item = s_item[0];
+    int slot = 0;
+    if (tid == 0 && item < n_items) stage_frag(s_rec[0]);
+
+    while (item < n_items) {
+        const MergeItem it = s_rec[slot];
+        const uint32_t nk = it.n_kmers;
+        const uint32_t nw = (nk + 31) >> 5;
+        const bool jumbo = it.jumbo_off != kNone;
+        const uint32_t next_item = s_item[slot ^ 1];
+        if (tid == 0) {
+            s_item[slot] = atomicAdd(a.item_cursor, 1u);      // the item after next (this slot was read one iteration ago)
+            if (!jumbo) {                                     // this tile's taxids (buffer idle since the last barrier)
+                const uint64_t i0 = it.info_begin & ~3ull, i1 = (it.info_begin + nk + 3ull) & ~3ull;
+                fence_proxy_async();
+                mbar_expect_tx(mbar + 1, (unsigned)((i1 - i0) * 4));
+                tma_load_1d(s_info, a.info + i0, (unsigned)((i1 - i0) * 4), mbar + 1);
+            }
+        }
+        if (warp == 1 && lane < 4 && next_item < n_items)     // next item's record, four 16-byte words
+            cp_async16(reinterpret_cast<unsigned char*>(s_rec + (slot ^ 1)) + 16 * lane,
+                       reinterpret_cast<const unsigned char*>(a.items + next_item) + 16 * lane);
+        if (jumbo) {
+            if (warp == 1 && lane < 4) cp_async_wait_all();
+            __syncthreads();
+            if (tid == 0 && next_item < n_items) stage_frag(s_rec[slot ^ 1]);
+            // lane per query over the pre-decoded values in HBM: binary search for the group, one walk for the minimum, one for the
+            // survivors (every lane steps to its next surviving candidate, the warp writes those rows together)
+            const uint64_t* vals = a.jumbo_vals + it.jumbo_off;
+            const int32_t* infos = a.info + it.info_begin;
+            const uint32_t n_chunks = (uint32_t)((it.q_end - it.q_begin + 31) >> 5);
+            for (uint32_t ch = (uint32_t)warp; ch < n_chunks; ch += kWarps) {
+                const uint64_t qi = it.q_begin + (uint64_t)ch * 32 + lane;
+                const bool active = qi < it.q_end;
+                const uint64_t qv = active ? ld_stream_u64(a.q_value + qi) : kBlank;
+                const uint64_t q40 = qv >> 24;
+                const uint32_t qd = (uint32_t)qv & 0xFFFFFFu;
+                uint32_t g0 = 0;
+                bool hit = false;
+                if (active) {
+                    uint32_t lo = 0, hi = nk;
+                    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((vals[mid] >> 24) < q40) lo = mid + 1; else hi = mid; }
+                    if (lo < nk && (vals[lo] >> 24) == q40) { g0 = lo; hit = true; }
+                }
+                if (!__any_sync(kFull, hit)) continue;
+                uint64_t qinfo = 0;
+                uint32_t end = g0, best = 255u;
+                if (hit) {
+                    qinfo = via_idx ? a.q_info[a.q_idx[qi]] : a.q_info[qi];
+                    while (end < nk && (vals[end] >> 24) == q40) {
+                        const uint32_t td = (uint32_t)vals[end] & 0xFFFFFFu;
+                        best = min(best, td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td)));
+                        ++end;
+                    }
+                }
+                const uint32_t limit = min(best * 2u, 7u);                 // KmerMatcher.cpp:1136
+                uint32_t j = g0;
+                while (true) {
+                    uint32_t td = 0, sum = 255u;
+                    while (j < end) {                                      // this lane's next surviving candidate
+                        td = (uint32_t)vals[j] & 0xFFFFFFu;
+                        sum = td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td));
+                        if (sum <= limit) break;
+                        ++j;
+                    }
+                    const bool sel = j < end;
+                    if (!__any_sync(kFull, sel)) break;
+                    emit(sel, qinfo, sel ? infos[j] : 0, qd, td, sum);
+                    if (sel) ++j;
+                }
+            }
+            __syncthreads();
+            item = next_item;
+            slot ^= 1;
+            continue;
+        }
+        for (uint32_t x = tid; x < a.n_buckets; x += kThreads) s_tab[x] = kEmpty;
+        // -- 1. the tile's fragments were requested one item ago
+        const uint64_t d0 = it.diff_begin, d1 = it.diff_begin + it.n_u16;
+        const uint64_t a0 = d0 & ~7ull;
+        mbar_wait(mbar, parity_bits & 1u);
+        parity_bits ^= 1u;
+        // -- 2. block-wide decode into the value array
+        {
+            uint64_t v = it.base_value, k = it.info_begin;
+            const uint64_t kb = it.info_begin;
+            block_decode<kThreads>(s_frag, (int)(d0 - a0), (int)(d0 - a0), (int)(d1 - a0), v, k, s_scan,
+                                   [&](uint64_t kk, uint64_t val, uint64_t) {
+                const uint64_t rel = kk - kb;
+                if (rel < nk) s_vals[rel] = val;
+            });
+        }
+        if (warp == 1 && lane < 4) cp_async_wait_all();
+        __syncthreads();
+        if (tid == 0 && next_item < n_items) stage_frag(s_rec[slot ^ 1]);      // streams in during the match phase
+        // -- 2b. amino-acid group starts: bitmap + hash table (the table was cleared before the decode barriers)
+        for (uint32_t base = (uint32_t)warp * 32; base < nw * 32; base += kThreads) {
+            const uint32_t rel = base + lane;
+            bool start = false;
+            uint64_t aa = 0;
+            if (rel < nk) {
+                aa = s_vals[rel] >> 24;
+                start = rel == 0 || (s_vals[rel - 1] >> 24) != aa;
+            }
+            const uint32_t b = __ballot_sync(kFull, start);
+            if (lane == 0) s_bits[base >> 5] = b;
+            if (start) {
+                const uint32_t h = aa_hash(aa);
+                const uint32_t entry = (rel << 19) | (h & 0x7FFFFu);
+                uint32_t bs = 2u * (h >> hash_shift);
+                while (true) {
+                    if (atomicCAS(&s_tab[bs], kEmpty, entry) == kEmpty) break;
+                    if (atomicCAS(&s_tab[bs + 1], kEmpty, entry) == kEmpty) break;
+                    bs = (bs + 2) & (2u * bucket_mask + 1u);
+                }
+            }
+        }
+        mbar_wait(mbar + 1, (parity_bits >> 1) & 1u);
+        parity_bits ^= 2u;
+        __syncthreads();
+        const uint64_t* vals = s_vals;
+        const int32_t* infos = s_info + (it.info_begin & 3ull);
+
+        // -- 3. rounds of up to kQR queries
+        for (uint64_t r0 = it.q_begin; r0 < it.q_end; r0 += kQR) {
+            const uint32_t nq = (uint32_t)min((uint64_t)kQR, it.q_end - r0);
+            // probe: hit list + owner slots of the first pair window
+            for (uint32_t qb = (uint32_t)warp * 32; qb < nq; qb += kThreads) {
+                const uint32_t q = qb + lane;
+                const bool active = q < nq;
+                const uint64_t qi = r0 + q;
+                const uint64_t qv = active ? ld_stream_u64(a.q_value + qi) : kBlank;
+                const uint64_t q40 = qv >> 24;
+                uint32_t g0 = 0;
+                bool hit = false;
+                if (active) {
+                    const uint32_t h = aa_hash(q40);
+                    const uint32_t tag = h & 0x7FFFFu;
+                    uint32_t bkt = h >> hash_shift;
+                    while (true) {
+                        const uint2 e = *reinterpret_cast<const uint2*>(s_tab + 2u * bkt);
+                        if (e.x == kEmpty) break;
+                        if ((e.x & 0x7FFFFu) == tag && (vals[e.x >> 19] >> 24) == q40) { g0 = e.x >> 19; hit = true; break; }
+                        if (e.y == kEmpty) break;
+                        if ((e.y & 0x7FFFFu) == tag && (vals[e.y >> 19] >> 24) == q40) { g0 = e.y >> 19; hit = true; break; }
+                        bkt = (bkt + 1) & bucket_mask;
+                    }
+                }
+                const uint32_t bal = __ballot_sync(kFull, hit);
+                if (!bal) continue;
+                uint64_t qinfo = 0;
+                uint32_t len = 0;
+                if (hit) {
+                    qinfo = via_idx ? a.q_info[a.q_idx[qi]] : ld_stream_u64(a.q_info + qi);
+                    // group length = distance to the next group start
+                    uint32_t w = (g0 + 1) >> 5;
+                    uint32_t bits = w < nw ? s_bits[w] & (0xffffffffu << ((g0 + 1) & 31)) : 0u;
+                    while (!bits && ++w < nw) bits = s_bits[w];
+                    const uint32_t nxt = bits ? (w << 5) + (uint32_t)__ffs(bits) - 1u : nk;
+                    len = min(nxt, nk) - g0;
+                }
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+                const uint32_t total = __shfl_sync(kFull, incl, 31);
+                uint32_t hb = 0, pb = 0;
+                if (lane == 0) { hb = atomicAdd(s_nhit, (uint32_t)__popc(bal)); pb = atomicAdd(s_npair, total); }
+                hb = __shfl_sync(kFull, hb, 0);
+                pb = __shfl_sync(kFull, pb, 0);
+                if (hit) {
+                    const uint32_t h = hb + (uint32_t)__popc(bal & lt);
+                    const uint32_t pbase = pb + incl - len;
+                    s_hq[h] = qinfo;
+                    s_hg[h] = g0 | (len << 16);
+                    s_hp[h] = pbase;
+                    s_hm[h] = 0xFF000000u | ((uint32_t)qv & 0xFFFFFFu);
+                    for (uint32_t p = pbase, e = min(pbase + len, kPC); p < e; ++p) s_owner[p] = (uint16_t)h;
+                }
+            }
+            __syncthreads();
+            const uint32_t nh = *s_nhit, np = *s_npair;
+            // pair p of the window starting at w0 -> (hit o, candidate j)
+            auto fill = [&](uint32_t w0) {
+                for (uint32_t h = tid; h < nh; h += kThreads) {
+                    const uint32_t pbase = s_hp[h], len = s_hg[h] >> 16;
+                    const uint32_t b = max(pbase, w0), e = min(pbase + len, w0 + kPC);
+                    for (uint32_t p = b; p < e; ++p) s_owner[p - w0] = (uint16_t)h;
+                }
+            };
+            auto pass1 = [&](uint32_t w0, bool keep) {
+                const uint32_t wend = min(np, w0 + kPC);
+                for (uint32_t p = w0 + tid; p < wend; p += kThreads) {
+                    const uint32_t o = s_owner[p - w0];
+                    const uint32_t j = (s_hg[o] & 0xFFFFu) + (p - s_hp[o]);
+                    const uint32_t qd = s_hm[o] & 0xFFFFFFu;
+                    const uint32_t td = (uint32_t)vals[j] & 0xFFFFFFu;
+                    const uint32_t sum = td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td));
+                    if (keep) s_psum[p - w0] = (uint8_t)sum;
+                    atomicMin(&s_hm[o], (sum << 24) | qd);
+                }
+            };
+            auto pass2 = [&](uint32_t w0, bool kept) {
+                const uint32_t wend = min(np, w0 + kPC);
+                for (uint32_t p0 = w0 + (uint32_t)warp * 32; p0 < wend; p0 += kThreads) {
+                    const uint32_t p = p0 + lane;
+                    uint32_t o = 0, j = 0, qd = 0, td = 0, sum = 255u;
+                    bool sel = false;
+                    if (p < wend) {
+                        o = s_owner[p - w0];
+                        j = (s_hg[o] & 0xFFFFu) + (p - s_hp[o]);
+                        const uint32_t mq = s_hm[o];
+                        qd = mq & 0xFFFFFFu;
+                        td = (uint32_t)vals[j] & 0xFFFFFFu;
+                        sum = kept ? (uint32_t)s_psum[p - w0] : (td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td)));
+                        sel = sum <= min((mq >> 24) * 2u, 7u);                  // KmerMatcher.cpp:1136
+                    }
+                    emit(sel, sel ? s_hq[o] : 0ull, sel ? infos[j] : 0, qd, td, sum);
+                }
+            };
+            if (np != 0 && np <= kPC) {
+                pass1(0, true);
+                __syncthreads();
+                pass2(0, true);
+            } else if (np != 0) {
+                for (uint32_t w0 = 0; w0 < np; w0 += kPC) {
+                    __syncthreads();
+                    fill(w0);
+                    __syncthreads();
+                    pass1(w0, false);
+                }
+                for (uint32_t w0 = 0; w0 < np; w0 += kPC) {
+                    __syncthreads();
+                    fill(w0);
+                    __syncthreads();
+                    pass2(w0, false);
+                }
+            }
+            if (tid == 0) { *s_nhit = 0u; *s_npair = 0u; }
+            __syncthreads();
+        }
+        item = next_item;
+        slot ^= 1;
+    }
+    // blank out the unused tail of the warp's last chunk (seqID 0 == not a match)
+    if (chunk.used < kOutChunk) {
+        for (uint32_t w = chunk.used + lane; w < kOutChunk; w += 32) {
+            const uint64_t sl = chunk.base + w;
+            if (sl < a.out_cap) {
+                uint64_t* o = reinterpret_cast<uint64_t*>(a.out + sl);
+                o[0] = 0; o[1] = 0; o[2] = 0;
+            }
+        }
+    }
+    if (lane == 0 && my_matches) atomicAdd(a.out_count + 1, my_matches);
+}
+
 size_t merge_smem_bytes(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets, int cta_threads) {
-    return smem_layout(max_u16, max_kmers, n_buckets, (uint32_t)cta_threads / 32).total;
+    return smem_layout2(max_u16, max_kmers, n_buckets, (uint32_t)cta_threads).total;
 }
 
 void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
@@ -660,25 +966,34 @@ void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
     merge_item_fill_kernel<<<blocks, 256, 0, st>>>(a.tiles, a.n_tiles, a.q_lo, a.item_cnt, a.item_off, a.items, a.items_cap);
 }
 
-template <int kThreads, bool kDirect>
-static void launch_merge_t(const MergeArgs& a, int sm_count, cudaStream_t st) {
+template <int kThreads>
+static void launch_merge_v1(const MergeArgs& a, int sm_count, cudaStream_t st) {
     const size_t smem = smem_layout(a.max_u16, a.max_kmers, a.n_buckets, kThreads / 32).total;
     // set on every launch (microseconds): two pipeline lanes may launch from two host threads
-    MBL_CUDA(cudaFuncSetAttribute(merge_kernel<kThreads, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MBL_CUDA(cudaFuncSetAttribute(merge_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel<kThreads, kDirect>, kThreads, smem));
+    MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel<kThreads>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    merge_kernel<kThreads, kDirect><<<(unsigned)(sm_count * per_sm), kThreads, smem, st>>>(a);
+    merge_kernel<kThreads><<<(unsigned)(sm_count * per_sm), kThreads, smem, st>>>(a);
+}
+template <int kThreads>
+static void launch_merge_v2(const MergeArgs& a, int sm_count, cudaStream_t st) {
+    const size_t smem = smem_layout2(a.max_u16, a.max_kmers, a.n_buckets, kThreads).total;
+    MBL_CUDA(cudaFuncSetAttribute(merge_kernel_v2<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel_v2<kThreads>, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    merge_kernel_v2<kThreads><<<(unsigned)(sm_count * per_sm), kThreads, smem, st>>>(a);
 }
 
 void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st) {
-    if (a.direct) {                                   // q_info is sorted alongside q_value, no q_idx
-        if (a.cta_threads == 512) launch_merge_t<512, true>(a, sm_count, st);
-        else launch_merge_t<256, true>(a, sm_count, st);
+    if (a.version == 1) {                             // needs q_idx (qinfo gathered through the sort permutation) or sorted qinfo alike
+        if (a.cta_threads == 512) launch_merge_v1<512>(a, sm_count, st);
+        else launch_merge_v1<256>(a, sm_count, st);
         return;
     }
-    if (a.cta_threads == 512) launch_merge_t<512, false>(a, sm_count, st);
-    else launch_merge_t<256, false>(a, sm_count, st);
+    if (a.cta_threads == 256) launch_merge_v2<256>(a, sm_count, st);
+    else launch_merge_v2<512>(a, sm_count, st);
 }
 
 }  // namespace mbl

@@ -60,8 +60,8 @@ uint64_t extract_filtered_capacity(uint64_t pass, int sm_count);
 size_t sort_kmers_temp_bytes(size_t n);
 void sort_kmers(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint64_t* val_a, uint64_t* val_b, size_t n,
                 int& result_in_b, cudaStream_t st);
-// pipeline variant: the payload is the 32-bit slot index; qinfo stays where K1 wrote it and is gathered for hits only
-// experimental direct merge: the payload is the 64-bit qinfo itself (16 bytes per element through the passes)
+// pipeline: the payload is the 64-bit qinfo itself (16 bytes per element through the passes), so the merge reads it as a stream;
+// the index-sharded mode sorts (value, 32-bit position in the receive buffer) and gathers qinfo for hits only
 void sort_kmers_qinfo(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint64_t* val_a, uint64_t* val_b, size_t n, int begin_bit,
                       int& result_in_b, cudaStream_t st);
 void sort_kmers_idx(void* tmp, size_t tmp_bytes, uint64_t* key_a, uint64_t* key_b, uint32_t* idx_a, uint32_t* idx_b, size_t n, int begin_bit,
@@ -120,7 +120,7 @@ struct MergeArgs {
     int prefix_shift;               // queries are ordered by value >> prefix_shift only
     int dyn_chunks;                 // 1: warps claim 32-query chunks from a shared counter, 0: fixed striding
     int cta_threads;                // 256 (3 CTAs per SM) or 512 (2 CTAs per SM)
-    int direct;                     // experimental (MBL_MERGE_DIRECT=1): q_info is sorted like q_value, a lane settles its own query
+    int version;                    // 2 (default): CTA-wide balanced match stage; 1 (MBL_MERGE_V1=1): warp-private queues + pair sweeps
     uint32_t* item_cnt;             // [n_tiles + 1]
     uint32_t* item_off;             // [n_tiles + 1]
     MergeItem* items;

@@ -57,9 +57,13 @@ struct mbl_ctx {
     int filter_bits = 16;               // MBL_FILTER_BITS: bits per index k-mer of the amino-acid presence filter, 0 = no filter
     uint64_t arena_S8 = 0;              // slot stride of the phase-1 arena layout (set by whoever fills it)
     int score_warp = 0;                 // MBL_SCORE_WARP=1: experimental warp-per-read scoring over rows staged in shared memory
-    int merge_direct = 0;               // MBL_MERGE_DIRECT=1: experimental lane-per-query match stage with qinfo sorted alongside the value
-    int merge_threads = 256;            // MBL_MERGE_THREADS: 256 (3 CTAs per SM) or 512 (2 CTAs per SM, 32 warps)
+    int merge_version = 2;              // MBL_MERGE_V1=1: the round-1 match stage (warp-private hit queues, two pair sweeps)
+    int merge_threads = 0;              // MBL_MERGE_THREADS: 256 or 512 threads per merge CTA (default: 512 for v2, 256 for v1)
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
+    // test hooks: force the capacity guesses low so that the retry paths run on small inputs (tests/test_gpu_edge_paths.py)
+    uint64_t test_match_cap = 0;        // MBL_TEST_MATCH_CAP: first match-buffer capacity (rows) of a merge
+    uint64_t test_items_cap = 0;        // MBL_TEST_ITEMS_CAP: first work-list capacity of a merge
+    uint64_t test_pack_slots = 0;       // MBL_TEST_PACK_SLOTS: first capacity of the packed (filtered) extraction
     // index
     uint16_t* d_diff = nullptr;
     int32_t* d_info = nullptr;
@@ -282,15 +286,15 @@ uint64_t slots_budget(mbl_ctx* c) {
 // ---- the pipeline over one sub-batch of resident reads, in three stages -------------------------------------------------
 // (the index-sharded mode runs the same stages with an exchange between them, see mbl_shard_* below)
 
-// K1: per-read metadata + metamer extraction into the phase-1 arena (value A | value B | qinfo | slot idx A | slot idx B)
+// K1: per-read metadata + metamer extraction into the phase-1 arena (value A | value B | qinfo A | qinfo B)
 // use_filter: metamers whose amino-acid part is not in the index are dropped and the survivors packed from slot 0 (K1 + filter)
 // filter_pass: expected number of survivors (sizes the packed buffers; a too small guess is detected and redone by the caller)
-void stage_extract(mbl_ctx* c, const SubBatch& sb, bool use_filter, uint64_t filter_pass = 0) {
+void stage_extract(mbl_ctx* c, const SubBatch& sb, bool use_filter, uint64_t filter_pass = 0, uint64_t forced_cap = 0) {
     cudaStream_t st = c->st;
     const uint32_t n = sb.r1 - sb.r0;
     const uint64_t S = sb.slots;
     use_filter = use_filter && c->dir.filter != nullptr;
-    const uint64_t S8 = ((use_filter ? extract_filtered_capacity(std::min(filter_pass, S), c->sm_count) : S) + 31) & ~31ull;
+    const uint64_t S8 = ((use_filter ? (forced_cap ? forced_cap : extract_filtered_capacity(std::min(filter_pass, S), c->sm_count)) : S) + 31) & ~31ull;
     c->arena_S8 = S8;
     const uint8_t* bases1 = (const uint8_t*)c->bases1.p;
     const uint8_t* bases2 = c->paired ? (const uint8_t*)c->bases2.p : nullptr;
@@ -311,14 +315,13 @@ void stage_extract(mbl_ctx* c, const SubBatch& sb, bool use_filter, uint64_t fil
         void* tmp = c->cub_tmp.get<uint8_t>(std::max(scan_bytes, sortk_bytes));
         exclusive_sum_u64(tmp, c->cub_tmp.cap, slots, slot_off, n + 1, st);
         exclusive_sum_u32(tmp, c->cub_tmp.cap, quot_cnt, quot_off, n + 1, st);
-        // phase-1 layout of the arena (32 B per slot): value A | value B | qinfo (stays unsorted) | slot idx A | slot idx B
+        // phase-1 layout of the arena (32 B per slot): value A | value B | qinfo A | qinfo B (the sort's second buffers)
         uint64_t* ar = c->arena.get<uint64_t>(4 * S8 + 64);
         uint64_t *va = ar, *qa = ar + 2 * S8;
-        uint32_t* ia = reinterpret_cast<uint32_t*>(ar + 3 * S8);
         AaFilter flt;
         if (use_filter) { flt.words = c->dir.filter; flt.n_lines = c->dir.filter_lines; flt.minimizer = c->dir.filter_minimizer; }
         launch_extract(c->cfg.kmer_format, bases1, off1, bases2, off2, n, cov1, w1, w2, slot_off, c->d_base_code, c->d_codon,
-                       va, qa, ia, counters, c->sm_count, st, flt, counters + 4, S8, c->cfg.syncmer ? c->cfg.smer_len : 0);
+                       va, qa, nullptr, counters, c->sm_count, st, flt, counters + 4, S8, c->cfg.syncmer ? c->cfg.smer_len : 0);
         c->stats.kernel_launches += 2;
         t.stop();
     }
@@ -344,9 +347,9 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, double* ratio, 
         uint64_t *va = ar, *vb = ar + S8;
         uint32_t *ia = reinterpret_cast<uint32_t*>(ar + 3 * S8), *ib = ia + S8;
         int in_b = 0;
-        // experimental direct merge: qinfo travels through the sort with the value (only when it sits in the arena, i.e. not for the
-        // receive buffer of the sharded mode); its second buffer is the region of the two slot-index arrays
-        direct = c->merge_direct && q_info == ar + 2 * S8;
+        // qinfo travels through the sort with the value when it sits in the arena (i.e. not for the receive buffer of the sharded
+        // mode, which is sorted as (value, position) pairs); its second buffer is the region of the two slot-index arrays
+        direct = q_info == ar + 2 * S8;
         if (direct) {
             uint64_t *qa = ar + 2 * S8, *qb = ar + 3 * S8;
             if (S) sort_kmers_qinfo(c->cub_tmp.p, c->cub_tmp.cap, va, vb, qa, qb, S, c->dir.sort_begin_bit, in_b, st);
@@ -370,6 +373,7 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, double* ratio, 
 
     // ---- K3 ------------------------------------------------------------------------------------------
     uint64_t cap = (uint64_t)((double)cap_basis * std::max(*ratio * 1.25, 0.125 * (double)std::max(1, c->cfg.match_per_kmer))) + out_slack(c);
+    if (c->test_match_cap) cap = c->test_match_cap;
     uint64_t reserved = 0, n_match = 0;
     MergeArgs ma{};
     ma.diff = c->d_diff; ma.info = c->d_info;
@@ -387,11 +391,12 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, double* ratio, 
     ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
     ma.prefix_shift = c->dir.sort_begin_bit;
     ma.dyn_chunks = c->dyn_chunks;
-    ma.cta_threads = c->merge_threads;
-    ma.direct = direct ? 1 : 0;
+    ma.version = c->merge_version;
+    ma.cta_threads = c->merge_threads ? c->merge_threads : (c->merge_version == 1 ? 256 : 512);
     ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
     ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
     ma.items_cap = c->dir.n_tiles + n_query / kItemQueries + 2;
+    if (c->test_items_cap) ma.items_cap = c->test_items_cap;
     ma.items = c->items.get<MergeItem>(ma.items_cap);
     ma.scan_tmp = c->cub_tmp.p; ma.scan_tmp_bytes = c->cub_tmp.cap;
     for (int attempt = 0;; ++attempt) {
@@ -563,7 +568,7 @@ int extract_filtered(mbl_ctx* c, const SubBatch& sb, uint64_t* n_slots_used) {
     unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
     uint64_t guess = (uint64_t)((double)sb.slots * std::min(1.0, c->pass_ratio > 0 ? 1.3 * c->pass_ratio + 0.02 : 0.4)) + 4096;
     for (int attempt = 0;; ++attempt) {
-        stage_extract(c, sb, true, guess);
+        stage_extract(c, sb, true, guess, attempt == 0 ? c->test_pack_slots : 0);
         MBL_CUDA(cudaMemcpyAsync(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost, c->st));
         MBL_CUDA(cudaStreamSynchronize(c->st));
         if (h[4] <= c->arena_S8 || attempt > 0) break;
@@ -645,10 +650,13 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         }
         if (const char* e = getenv("MBL_FILTER_MINIMIZER")) c->filter_minimizer = atoi(e) != 0;
         if (const char* e = getenv("MBL_FILTER_BITS")) { int v = atoi(e); if (v >= 0 && v <= 64) c->filter_bits = v; }
-        if (const char* e = getenv("MBL_MERGE_DIRECT")) c->merge_direct = atoi(e) != 0;
+        if (const char* e = getenv("MBL_MERGE_V1")) c->merge_version = atoi(e) != 0 ? 1 : 2;
         if (const char* e = getenv("MBL_SCORE_WARP")) c->score_warp = atoi(e) != 0;
         if (const char* e = getenv("MBL_MERGE_THREADS")) { int v = atoi(e); if (v == 256 || v == 512) c->merge_threads = v; }
         if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }
+        if (const char* e = getenv("MBL_TEST_MATCH_CAP")) c->test_match_cap = strtoull(e, nullptr, 10);
+        if (const char* e = getenv("MBL_TEST_ITEMS_CAP")) c->test_items_cap = strtoull(e, nullptr, 10);
+        if (const char* e = getenv("MBL_TEST_PACK_SLOTS")) c->test_pack_slots = strtoull(e, nullptr, 10);
         if (const char* e = getenv("MBL_SORT_BIT")) { int v = atoi(e); if (v == 24 || v == 32 || v == 40) c->force_sort_bit = v; }
         if (const char* e = getenv("MBL_TILE_CELLS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->tile_cells = (uint32_t)v; }
         MBL_CUDA(cudaStreamSynchronize(c->st));
@@ -695,7 +703,7 @@ mbl_ctx* ensure_shadow(mbl_ctx* c) {
     }
     mbl_ctx* s = c->shadow;
     s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
-    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->merge_direct = c->merge_direct; s->score_warp = c->score_warp; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
+    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->merge_version = c->merge_version; s->score_warp = c->score_warp; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
     s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
     s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded; s->filter_complete = c->filter_complete;
     s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed
@@ -1555,7 +1563,8 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
         ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
         ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
         ma.dyn_chunks = c->dyn_chunks;
-        ma.cta_threads = c->merge_threads;
+        ma.version = c->merge_version;
+        ma.cta_threads = c->merge_threads ? c->merge_threads : (c->merge_version == 1 ? 256 : 512);
         ma.prefix_shift = 24;                // the stage API takes fully ordered queries; any coarser grouping is valid too
         ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
         ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);

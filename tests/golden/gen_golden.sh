@@ -2,21 +2,15 @@
 # Regenerates the golden vectors of tests/golden/ from the REFERENCE ITSELF.  Container-only: needs
 # /root/reference (read-only) and cmake; nothing here runs on the GPU box or in the test suite.
 #
-#  1. builds the unmodified reference out of tree in /tmp (SURVEY.md §8c command; the reference needs its
-#     own cmake build + generated sources, so it is NOT shipped as oracle/_ref — see DESIGN.md),
+#  1. builds the unmodified reference out of tree in /tmp into oracle/_ref/metabuli (oracle/build_ref.sh, SURVEY.md §8c recipe),
 #  2. runs `metabuli classify` on the regression fixtures (4 configs) -> tests/golden/ref_tsv/*.tsv.gz,
 #  3. runs it on the seeded synthetic cases of tests/synth_cases.py (CASES and CPU_CASES, with the flags of FLAGS)
 #     -> tests/golden/synth/<case>.tsv.gz, <case>.report.gz
 #     (+ <case>.md5 = fingerprint of the generated inputs, so a test can tell "inputs differ" from "bug").
 set -euo pipefail
 REPO=$(cd "$(dirname "$0")/../.." && pwd)
-W=/tmp/oracle
-if [ ! -x $W/build/src/metabuli ]; then
-  mkdir -p $W && cp -r /root/reference $W/src && chmod -R u+w $W/src && mkdir -p $W/build && cd $W/build
-  cmake -DCMAKE_BUILD_TYPE=Release -DCMAKE_C_COMPILER=/usr/bin/gcc -DCMAKE_CXX_COMPILER=/usr/bin/g++ ../src >/dev/null
-  make -j"$(nproc)" metabuli >/dev/null
-fi
-BIN=$W/build/src/metabuli
+bash $REPO/oracle/build_ref.sh
+BIN=$REPO/oracle/_ref/metabuli
 D=/root/reference/util/Metabuli-regression/data
 OUT=$(mktemp -d)
 mkdir -p $REPO/tests/golden/ref_tsv $REPO/tests/golden/synth
@@ -28,5 +22,5 @@ for db in in ex; do
     gzip -9 -n -c $OUT/${db}_${m}_report.tsv > $REPO/tests/golden/ref_tsv/${db}_${m}_report.tsv.gz
   done
 done
-cd $REPO && python tests/golden/gen_synth_golden.py $BIN $OUT
+cd $REPO && python tests/golden/gen_synth_golden.py $BIN $OUT "$@"
 rm -rf $OUT

@@ -12,7 +12,10 @@ import synth_cases  # noqa: E402
 binary, work = sys.argv[1], sys.argv[2]
 out_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "synth")
 os.makedirs(out_dir, exist_ok=True)
-for name in list(synth_cases.CASES) + list(synth_cases.CPU_CASES):
+only = set(sys.argv[3:])                                   # optional: case names to (re)generate
+for name in list(synth_cases.CASES) + list(synth_cases.CPU_CASES) + list(synth_cases.EDGE_CASES):
+    if only and name not in only:
+        continue
     sdb, reads, seq_mode = synth_cases.build(name)
     db_dir = os.path.join(work, "db_" + name)
     sdb.write(db_dir)

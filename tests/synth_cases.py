@@ -59,6 +59,52 @@ CPU_CASES = {
 }
 
 
+# Hand-made genomes that push the index decoder and the merge kernel off their common paths (code no test reached).
+# Built by _edge_db below: amino-acid stretches with independently drawn synonymous codons per strain give ONE amino-acid
+# group with thousands of distinct DNA parts; genomes restricted to two far-apart residue sets give 5-fragment deltas.
+EDGE_CASES = {
+    # poly-Leu (6 codons) stretch of 1000 codons x 8 strains: an amino-acid group of ~7.9 k k-mers, larger than a shared-memory
+    # tile (2048 k-mers) => a jumbo tile pre-decoded in HBM; a second, 200-codon poly-Ser stretch gives a 1.5 k group that stays
+    # in shared memory but expands to more (query, candidate) pairs than one pair window of the merge kernel holds
+    "jumbo_se": (dict(codons=2600, seed=61, stretches=(("L", 300, 1000), ("S", 1700, 200))),
+                 dict(n_reads=600, length=150, seed=62, sub_rate=0.01, random_frac=0.1), 1),
+    # every codon codes for one of {A, R} in the first half of a genome and one of {T, W, Y, V, stop} in the second: the first
+    # k-mer of the stream needs five 15-bit fragments (value >= 2^60) and so does the jump between the two populations
+    "fivefrag_se": (dict(codons=2400, seed=67, residue_sets=(("T", "W", "Y", "V", "X"), ("A", "R")), species_div=0.1),
+                    dict(n_reads=2000, length=150, seed=68, sub_rate=0.02), 1),
+    # only {T, W, Y, V, stop}: every value is >= 2^63, so the very first k-mer of the stream takes five fragments
+    "fivefrag_first_se": (dict(codons=2400, seed=71, residue_sets=(("T", "W", "Y", "V", "X"),), species_div=0.1),
+                          dict(n_reads=2000, length=150, seed=72, sub_rate=0.02), 1),
+}
+
+
+def _edge_db(codons, seed, stretches=(), residue_sets=(), species_div=0.12, strain_div=0.01):
+    import torch
+    from metabuli_b200 import synth
+    tx = synth.make_taxonomy(2, 2, 2)
+    genomes = synth.make_genomes(tx, codons, species_div, strain_div, seed)
+    gen = torch.Generator(); gen.manual_seed(seed + 1000)
+    aa_of = torch.as_tensor(synth._AA)
+
+    def codons_of(letters):
+        want = torch.as_tensor([synth._AA_ORDER.index(x) for x in letters])
+        return torch.nonzero((aa_of[:, None] == want[None, :]).any(1)).flatten().to(torch.uint8)
+    if residue_sets:
+        # position-wise residue classes: block b of the genome only uses codons of residue_sets[b]; redraw every codon inside its
+        # class, keeping the genus / species / strain relatedness (same random choice where the genomes agreed)
+        n_blocks = len(residue_sets)
+        edges = [codons * b // n_blocks for b in range(n_blocks + 1)]
+        for b, letters in enumerate(residue_sets):
+            pool = codons_of(letters)
+            blk = genomes[:, edges[b]:edges[b + 1]].long()
+            genomes[:, edges[b]:edges[b + 1]] = pool[blk % pool.numel()]
+    for letter, start, length in stretches:
+        pool = codons_of(letter)
+        pick = torch.randint(0, pool.numel(), (genomes.shape[0], length), generator=gen)
+        genomes[:, start:start + length] = pool[pick]
+    return synth.build_db(tx, genomes)
+
+
 # classify flags of a case (reference spelling -> value); cases without an entry run the defaults
 FLAGS = {
     "flags_se": {"--min-score": 0.3, "--min-sp-score": 0.6, "--tie-ratio": 0.9, "--min-cons-cnt": 6, "--min-cons-cnt-euk": 11},
@@ -76,6 +122,10 @@ def oracle_flags(name):
 
 def build(name):
     from metabuli_b200 import synth
+    if name in EDGE_CASES:
+        dbkw, rkw, seq_mode = EDGE_CASES[name]
+        sdb = _edge_db(**dbkw)
+        return sdb, synth.make_reads(sdb, **rkw), seq_mode
     dbkw, rkw, seq_mode = (CASES.get(name) or CPU_CASES[name])
     sdb = synth.make_db(**dbkw)
     if name == "redund_se":

@@ -54,3 +54,17 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(base, f), errors="replace").read()
                 assert "mbl_oracle" not in txt and "import oracle" not in txt and "/oracle/" not in txt, os.path.join(base, f)
+
+
+def test_cli_rejects_flags_that_would_change_the_output():
+    """`--mask 1`, `--taxonomy-path X`, `--reduced-aa 1` change the reference's classifications and are not implemented on the
+    B200 path: the C++ host must die with a message, not drop them (argument parsing needs no GPU)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metabuli_b200", "_lib", "metabuli-b200")
+    for flags in (["--mask", "1"], ["--taxonomy-path", "/some/where"], ["--reduced-aa", "1"], ["--no-such-flag", "1"]):
+        r = subprocess.run([exe, "classify", "--seq-mode", "1", *flags, "a.fna", "db", "out", "job"], capture_output=True, text=True)
+        assert r.returncode != 0 and "Error" in (r.stdout + r.stderr), flags
+    # harmless spellings are accepted up to the input checks
+    r = subprocess.run([exe, "classify", "--seq-mode", "1", "--mask", "0", "--max-ram", "8", "--hamming-margin", "1", "a.fna", "db", "out", "job"],
+                       capture_output=True, text=True)
+    assert "not supported" not in (r.stdout + r.stderr)

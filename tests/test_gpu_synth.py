@@ -168,37 +168,10 @@ def test_very_long_ragged_reads_vs_oracle():
         odb.close()
 
 
-@pytest.mark.skipif(os.environ.get("MBL_TEST_EXPERIMENTAL") != "1", reason="experimental kernels are opt-in (MBL_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("knob", ["MBL_MERGE_DIRECT", "MBL_SCORE_WARP"])
-@pytest.mark.parametrize("name", ["multi_se", "multi_pe", "ties_se", "format1_pe", "sync_se", "long"])
-def test_experimental_kernels(name, knob, golden_dir):
-    """Kernels written at the end of round 1 without a GPU at hand, off by default: MBL_MERGE_DIRECT=1 (lane-per-query match
-    stage with qinfo sorted alongside the value) and MBL_SCORE_WARP=1 (warp-per-read scoring over rows staged in shared memory).
-    Runs in a subprocess so that a faulting kernel cannot poison this process's CUDA context."""
-    import subprocess
-    import sys
-    code = f"""
-import gzip, os, sys
-sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r}); sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
-import synth_cases
-from metabuli_b200 import Classifier, ClassifyOptions
-sdb, reads, seq_mode = synth_cases.build({name!r})
-clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
-res, pairs = clf.classify_batch(*reads)
-tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
-golden = gzip.open(os.path.join({golden_dir!r}, "synth", {name!r} + ".tsv.gz"), "rb").read()
-sys.exit(0 if tsv == golden else 3)
-"""
-    env = dict(os.environ, **{knob: "1"})
-    r = subprocess.run([sys.executable, "-c", code], env=env, timeout=300, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-2000:]
-
-
-@pytest.mark.skipif(os.environ.get("MBL_TEST_EXPERIMENTAL") != "1", reason="not yet run on a GPU (MBL_TEST_EXPERIMENTAL=1 to try)")
 @pytest.mark.parametrize("name", list(synth_cases.CPU_CASES))
 def test_cpu_pinned_cases_on_gpu(name, golden_dir):
-    """The cases of synth_cases.CPU_CASES (asymmetric mates, non-default flags, accession-level databases) end to end on the CUDA
-    path against the reference binary's TSV.  Written after the GPU budget of round 1 was spent: promote to CASES once green."""
+    """The cases of synth_cases.CPU_CASES (asymmetric mates, non-default flags, accession-level databases, Skip_redundancy 0,
+    --lineage, 50 kbp ragged reads) end to end on the CUDA path against the reference binary's TSV (green on a B200 since round 2)."""
     from metabuli_b200 import Classifier, ClassifyOptions
     sdb, reads, seq_mode = synth_cases.build(name)
     f = synth_cases.oracle_flags(name)
@@ -213,7 +186,6 @@ def test_cpu_pinned_cases_on_gpu(name, golden_dir):
         clf.close()
 
 
-@pytest.mark.skipif(os.environ.get("MBL_TEST_EXPERIMENTAL") != "1", reason="not yet run on a GPU (MBL_TEST_EXPERIMENTAL=1 to try)")
 def test_batch_without_any_kmer():
     """Every read shorter than one k-mer window (and a batch of Ns): all rows come back unclassified with the covered length the
     reference prints (Q8), nothing is sorted or merged."""

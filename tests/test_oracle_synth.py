@@ -10,7 +10,7 @@ import oracle
 import synth_cases
 
 
-@pytest.mark.parametrize("name", list(synth_cases.CASES) + list(synth_cases.CPU_CASES))
+@pytest.mark.parametrize("name", list(synth_cases.CASES) + list(synth_cases.CPU_CASES) + list(synth_cases.EDGE_CASES))
 def test_oracle_matches_reference_on_synthetic(name, golden_dir, tmp_path):
     sdb, reads, seq_mode = synth_cases.build(name)
     want_fp = open(os.path.join(golden_dir, "synth", name + ".md5")).read().strip()
