@@ -114,77 +114,90 @@ __device__ __forceinline__ void warp_decode(const uint16_t* frag, long long lo, 
 template <int kThreadsDecode, class Emit>
 __device__ __forceinline__ void block_decode(const uint16_t* frag, int lo, int s, int e, uint64_t& v0, uint64_t& k0, uint64_t* scan, Emit emit) {
     constexpr int kW = kThreadsDecode / 32;
+    static_assert(kW <= 32, "one lane per warp in the cross-warp scan");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int flip = 0;
     for (int p0 = s & ~7; p0 < e; p0 += 8 * kThreadsDecode, flip ^= 1) {
         const int p = p0 + 8 * (int)threadIdx.x;
+        const bool warp_has_work = p0 + 256 * warp < e;     // warp-uniform: a 4 KiB tile keeps only the first 8 warps busy
         uint32_t w[4] = {0u, 0u, 0u, 0u};          // the octet as four pairs of fragments
         uint32_t l0 = 0x80008000u, l1 = 0x80008000u;   // look-back quartet (cuts when unavailable)
-        if (p < e) {
-            const uint4 v = *reinterpret_cast<const uint4*>(frag + p);
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            if (p >= 4 && p - 4 >= (lo & ~3)) { const uint2 b = *reinterpret_cast<const uint2*>(frag + p - 4); l0 = b.x; l1 = b.y; }
-        }
         const bool inner = p >= s && p + 8 <= e && p - 4 >= lo;
         uint64_t acc = 0;
-        uint32_t cnt = 0;
-        uint64_t sum = 0;
-        if (inner) {
-            // incoming partial delta: fragments after the last end flag of the look-back quartet
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t fr = ((j & 2 ? l1 : l0) >> (16 * (j & 1))) & 0xFFFFu;
-                acc = (fr & 0x8000u) ? 0ull : ((acc << 15) | fr);
+        uint32_t cnt = 0, icnt = 0;
+        uint64_t sum = 0, isum = 0;
+        if (warp_has_work) {
+            if (p < e) {
+                const uint4 v = *reinterpret_cast<const uint4*>(frag + p);
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                if (p >= 4 && p - 4 >= (lo & ~3)) { const uint2 b = *reinterpret_cast<const uint2*>(frag + p - 4); l0 = b.x; l1 = b.y; }
             }
-            uint64_t a = acc;
+            if (inner) {
+                // incoming partial delta: fragments after the last end flag of the look-back quartet
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t fr = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-                a = (a << 15) | (uint64_t)(fr & 0x7FFFu);
-                if (fr & 0x8000u) { ++cnt; sum += a; a = 0; }
-            }
-        } else if (p < e) {
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t fr = ((j & 2 ? l1 : l0) >> (16 * (j & 1))) & 0xFFFFu;
+                    acc = (fr & 0x8000u) ? 0ull : ((acc << 15) | fr);
+                }
+                uint64_t a = acc;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = p - 4 + j;
-                const uint32_t fr = ((j & 2 ? l1 : l0) >> (16 * (j & 1))) & 0xFFFFu;
-                const bool cut = (fr & 0x8000u) || idx < lo;
-                acc = cut ? 0ull : ((acc << 15) | fr);
-            }
-            uint64_t a = acc;
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t fr = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                    a = (a << 15) | (uint64_t)(fr & 0x7FFFu);
+                    if (fr & 0x8000u) { ++cnt; sum += a; a = 0; }
+                }
+            } else if (p < e) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int idx = p + j;
-                const uint32_t fr = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-                const bool dead = idx < lo;
-                a = dead ? 0ull : ((a << 15) | (uint64_t)(fr & 0x7FFFu));
-                if (!dead && (fr & 0x8000u)) {
-                    if (idx >= s && idx < e) { ++cnt; sum += a; }
-                    a = 0;
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = p - 4 + j;
+                    const uint32_t fr = ((j & 2 ? l1 : l0) >> (16 * (j & 1))) & 0xFFFFu;
+                    const bool cut = (fr & 0x8000u) || idx < lo;
+                    acc = cut ? 0ull : ((acc << 15) | fr);
+                }
+                uint64_t a = acc;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int idx = p + j;
+                    const uint32_t fr = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                    const bool dead = idx < lo;
+                    a = dead ? 0ull : ((a << 15) | (uint64_t)(fr & 0x7FFFu));
+                    if (!dead && (fr & 0x8000u)) {
+                        if (idx >= s && idx < e) { ++cnt; sum += a; }
+                        a = 0;
+                    }
                 }
             }
-        }
-        uint32_t icnt = cnt;
-        uint64_t isum = sum;
+            icnt = cnt;
+            isum = sum;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o);
-            const uint64_t s2 = __shfl_up_sync(0xffffffffu, isum, o);
-            if (lane >= o) { icnt += c2; isum += s2; }
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t c2 = __shfl_up_sync(0xffffffffu, icnt, o);
+                const uint64_t s2 = __shfl_up_sync(0xffffffffu, isum, o);
+                if (lane >= o) { icnt += c2; isum += s2; }
+            }
         }
         uint64_t* sc = scan + flip * 2 * kW;
         if (lane == 31) { sc[warp] = icnt; sc[kW + warp] = isum; }
         __syncthreads();
-        uint64_t wk = 0, wv = 0, tk = 0, tv = 0;
+        // cross-warp scan: lane x holds the totals of warp x, a shuffle scan gives this warp's offset and the block totals
+        uint32_t c = 0;
+        uint64_t v = 0;
+        if (lane < kW) { c = (uint32_t)sc[lane]; v = sc[kW + lane]; }
+        uint32_t ic = c;
+        uint64_t iv = v;
 #pragma unroll
-        for (int x = 0; x < kW; ++x) {
-            const uint64_t c = sc[x], v = sc[kW + x];
-            if (x < warp) { wk += c; wv += v; }
-            tk += c; tv += v;
+        for (int o = 1; o < kW; o <<= 1) {
+            const uint32_t c2 = __shfl_up_sync(0xffffffffu, ic, o);
+            const uint64_t s2 = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) { ic += c2; iv += s2; }
         }
-        uint64_t k = k0 + wk + (icnt - cnt);
-        uint64_t val = v0 + wv + (isum - sum);
+        const uint32_t wk = __shfl_sync(0xffffffffu, ic - c, warp);
+        const uint64_t wv = __shfl_sync(0xffffffffu, iv - v, warp);
+        const uint32_t tk = __shfl_sync(0xffffffffu, ic, kW - 1);
+        const uint64_t tv = __shfl_sync(0xffffffffu, iv, kW - 1);
         if (cnt) {
+            uint64_t k = k0 + wk + (icnt - cnt);
+            uint64_t val = v0 + wv + (isum - sum);
             uint64_t a = acc;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {

@@ -92,6 +92,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
     uint64_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -774,7 +775,14 @@ merge_kernel_v2(MergeArgs a) {
             slot ^= 1;
             continue;
         }
-        for (uint32_t x = tid; x < a.n_buckets; x += kThreads) s_tab[x] = kEmpty;
+        for (uint32_t x = tid; x < a.n_buckets / 4; x += kThreads) reinterpret_cast<uint4*>(s_tab)[x] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+        // the first round's queries: pull this thread's second query (and both qinfo words) towards L2 now, load the first one
+        // into a register after the decode — the probe then starts without a cold DRAM miss
+        {
+            const uint64_t q1 = it.q_begin + (uint64_t)tid;
+            if (q1 < it.q_end) { prefetch_l2(a.q_value + q1); if (!via_idx) prefetch_l2(a.q_info + q1); }
+            if (q1 + kThreads < it.q_end) { prefetch_l2(a.q_value + q1 + kThreads); if (!via_idx) prefetch_l2(a.q_info + q1 + kThreads); }
+        }
         // -- 1. the tile's fragments were requested one item ago
         const uint64_t d0 = it.diff_begin, d1 = it.diff_begin + it.n_u16;
         const uint64_t a0 = d0 & ~7ull;
@@ -793,6 +801,8 @@ merge_kernel_v2(MergeArgs a) {
         if (warp == 1 && lane < 4) cp_async_wait_all();
         __syncthreads();
         if (tid == 0 && next_item < n_items) stage_frag(s_rec[slot ^ 1]);      // streams in during the match phase
+        uint64_t qv_first = kBlank;
+        if (it.q_begin + (uint64_t)tid < it.q_end) qv_first = ld_stream_u64(a.q_value + it.q_begin + tid);
         // -- 2b. amino-acid group starts: bitmap + hash table (the table was cleared before the decode barriers)
         for (uint32_t base = (uint32_t)warp * 32; base < nw * 32; base += kThreads) {
             const uint32_t rel = base + lane;
@@ -829,7 +839,7 @@ merge_kernel_v2(MergeArgs a) {
                 const uint32_t q = qb + lane;
                 const bool active = q < nq;
                 const uint64_t qi = r0 + q;
-                const uint64_t qv = active ? ld_stream_u64(a.q_value + qi) : kBlank;
+                const uint64_t qv = (r0 == it.q_begin && qb == (uint32_t)warp * 32) ? qv_first : (active ? ld_stream_u64(a.q_value + qi) : kBlank);
                 const uint64_t q40 = qv >> 24;
                 uint32_t g0 = 0;
                 bool hit = false;

@@ -48,74 +48,6 @@ __global__ void __launch_bounds__(128, 4) score_sp_kernel(ScoreArgs a) {
     if (s < a.n_sp) score_task_species(a, s);
 }
 
-// ---- experimental: warp per read over rows staged in shared memory (MBL_SCORE_WARP=1) ---------------------------------------
-// The three flat passes above walk 24-byte rows from HBM one task per thread (uncoalesced; ncu: 2-3x the match list in DRAM
-// traffic, issue slots 8-14 % busy).  After K4 the rows of a read are contiguous, so a warp copies them into shared memory with
-// coalesced 8-byte loads, finds the (species, frame) and species group starts with two ballots per 32 rows, and runs the same
-// three steps — frame groups, species, read — lane per task on that copy.  Reads with more rows than fit stay in HBM.
-constexpr int kScoreWarps = 8;
-constexpr int kScoreMaxRows = 256;
-
-__global__ void __launch_bounds__(kScoreWarps * 32) score_warp_kernel(ScoreArgs a, uint64_t match_begin, uint32_t* __restrict__ fg_buf,
-                                                                       uint32_t* __restrict__ sp_buf) {
-    extern __shared__ __align__(16) unsigned char score_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t* rows64 = reinterpret_cast<uint64_t*>(score_smem) + (size_t)warp * kScoreMaxRows * 3;
-    const uint32_t lt = (1u << lane) - 1u;
-    for (uint32_t ri = blockIdx.x * kScoreWarps + warp; ri < a.n_reads; ri += gridDim.x * kScoreWarps) {
-        const uint32_t r = a.read_perm ? a.read_perm[a.read_begin + ri] : a.read_begin + ri;
-        const uint64_t ms = a.seg_begin[r], me = a.seg_end[r];
-        if (me <= ms) {
-            if (lane == 0) score_read(a, r);
-            continue;
-        }
-        const uint64_t n = me - ms;
-        ScoreArgs la = a;
-        __syncwarp();                                          // the previous read's rows are no longer in use
-        if (n <= (uint64_t)kScoreMaxRows) {
-            const uint64_t* src = reinterpret_cast<const uint64_t*>(a.matches + ms);
-            for (uint32_t w = lane; w < 3u * (uint32_t)n; w += 32) rows64[w] = src[w];
-            __syncwarp();
-            la.matches = reinterpret_cast<const mbl_match_rec*>(rows64) - ms;      // row i of the list sits at copy[i - ms]
-        }
-        const mbl_match_rec* ml = la.matches;
-        // group starts of this read (all rows share the seqID): ascending match indices, as the flat lists hold them
-        uint32_t* fgl = fg_buf + (ms - match_begin);
-        uint32_t* spl = sp_buf + (ms - match_begin);
-        uint32_t nfg = 0, nsp = 0;
-        for (uint64_t base = ms; base < me; base += 32) {
-            const uint64_t i = base + lane;
-            bool sp_start = false, fg_start = false;
-            if (i < me) {
-                sp_start = i == ms || ml[i].species_id != ml[i - 1].species_id;
-                fg_start = sp_start || qi_frame(ml[i].qinfo) != qi_frame(ml[i - 1].qinfo);
-            }
-            const uint32_t bs = __ballot_sync(0xffffffffu, sp_start), bf = __ballot_sync(0xffffffffu, fg_start);
-            if (sp_start) spl[nsp + __popc(bs & lt)] = (uint32_t)i;
-            if (fg_start) fgl[nfg + __popc(bf & lt)] = (uint32_t)i;
-            nsp += __popc(bs);
-            nfg += __popc(bf);
-        }
-        __syncwarp();
-        la.fg_list = fgl; la.n_fg = nfg; la.sp_list = spl; la.n_sp = nsp; la.match_end = me; la.fg_order = nullptr;
-        for (uint32_t t = lane; t < nfg; t += 32) score_task_frame_group(la, t);
-        __syncwarp();
-        for (uint32_t t = lane; t < nsp; t += 32) score_task_species(la, t);
-        __syncwarp();
-        if (lane == 0) score_read(la, r);
-    }
-}
-
-void launch_score_warp(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch& s, int sm_count, cudaStream_t st) {
-    if (a.n_reads == 0) return;
-    const size_t smem = (size_t)kScoreWarps * kScoreMaxRows * 24;
-    MBL_CUDA(cudaFuncSetAttribute(score_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unsigned blocks = (a.n_reads + kScoreWarps - 1) / kScoreWarps;
-    const unsigned cap = (unsigned)sm_count * 16u;
-    if (blocks > cap) blocks = cap;
-    score_warp_kernel<<<blocks, kScoreWarps * 32, smem, st>>>(a, match_begin, s.fg_list, s.sp_list);
-}
-
 size_t score_flat_temp_bytes(size_t n) {
     size_t bytes = 0;
     cub::DeviceSelect::Flagged(nullptr, bytes, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)nullptr, (uint32_t*)nullptr,

@@ -170,8 +170,6 @@ struct ScoreFlatScratch {
 };
 size_t score_flat_temp_bytes(size_t n_matches);
 void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch& s, cudaStream_t st);
-// experimental (MBL_SCORE_WARP=1): one warp per read over rows staged in shared memory; same results
-void launch_score_warp(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch& s, int sm_count, cudaStream_t st);
 void launch_compact_taxcnt(const mbl_read_result* results, uint32_t n_reads, const uint32_t* quot_off,
                            const int32_t* pairs_in, const uint32_t* out_off, uint32_t pair_base, int32_t* pairs_out,
                            mbl_read_result* results_out, cudaStream_t st);

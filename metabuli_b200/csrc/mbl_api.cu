@@ -56,7 +56,6 @@ struct mbl_ctx {
     int filter_minimizer = 1;           // MBL_FILTER_MINIMIZER=0: filter line from the whole amino-acid part instead of its minimizer
     int filter_bits = 16;               // MBL_FILTER_BITS: bits per index k-mer of the amino-acid presence filter, 0 = no filter
     uint64_t arena_S8 = 0;              // slot stride of the phase-1 arena layout (set by whoever fills it)
-    int score_warp = 0;                 // MBL_SCORE_WARP=1: experimental warp-per-read scoring over rows staged in shared memory
     int merge_version = 2;              // MBL_MERGE_V1=1: the round-1 match stage (warp-private hit queues, two pair sweeps)
     int merge_threads = 0;              // MBL_MERGE_THREADS: 256 or 512 threads per merge CTA (default: 512 for v2, 256 for v1)
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
@@ -532,8 +531,8 @@ int stage_sort_score(mbl_ctx* c, const SubBatch& sb, uint64_t M) {
             sa.s_score = s_score - f;
             sa.g_np = g_np - f;
             sa.match_end = bounds[k + 1];
-            if (c->score_warp) { launch_score_warp(sa, f, flat, c->sm_count, st); c->stats.kernel_launches += 1; }
-            else { launch_score_flat(sa, f, flat, st); c->stats.kernel_launches += 6; }
+            launch_score_flat(sa, f, flat, st);
+            c->stats.kernel_launches += 6;
         }
         // compact the (taxid,count) lists behind the pairs of earlier sub-batches
         uint32_t *tl = c->tax_len.get<uint32_t>(n + 1), *to = c->tax_off.get<uint32_t>(n + 1);
@@ -651,7 +650,6 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         if (const char* e = getenv("MBL_FILTER_MINIMIZER")) c->filter_minimizer = atoi(e) != 0;
         if (const char* e = getenv("MBL_FILTER_BITS")) { int v = atoi(e); if (v >= 0 && v <= 64) c->filter_bits = v; }
         if (const char* e = getenv("MBL_MERGE_V1")) c->merge_version = atoi(e) != 0 ? 1 : 2;
-        if (const char* e = getenv("MBL_SCORE_WARP")) c->score_warp = atoi(e) != 0;
         if (const char* e = getenv("MBL_MERGE_THREADS")) { int v = atoi(e); if (v == 256 || v == 512) c->merge_threads = v; }
         if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }
         if (const char* e = getenv("MBL_TEST_MATCH_CAP")) c->test_match_cap = strtoull(e, nullptr, 10);
@@ -703,7 +701,7 @@ mbl_ctx* ensure_shadow(mbl_ctx* c) {
     }
     mbl_ctx* s = c->shadow;
     s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
-    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->merge_version = c->merge_version; s->score_warp = c->score_warp; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
+    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->merge_version = c->merge_version; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
     s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
     s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded; s->filter_complete = c->filter_complete;
     s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed

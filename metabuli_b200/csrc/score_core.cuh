@@ -410,17 +410,26 @@ MBL_HD uint32_t list_lower_bound(const uint32_t* list, uint32_t n, uint64_t key)
     return lo;
 }
 
+// rows a (species, frame) group needs before getMatchPaths can emit anything: 2 (Q9); without syncmers depth == matches of the path
+MBL_HD int min_group_rows(const ScoreParams& p) {
+    if (p.max_codon_shift > 1) return 2;
+    const int m = p.min_cons_cnt < p.min_cons_cnt_euk ? p.min_cons_cnt : p.min_cons_cnt_euk;
+    return m > 2 ? m : 2;
+}
+
 MBL_HD void score_task_frame_group(const ScoreArgs& a, uint32_t t) {
     const uint32_t g = a.fg_order ? a.fg_order[t] : t;             // tasks ordered by group length (k5_score.cu)
     const uint64_t gs = a.fg_list[g];
     const uint64_t ge = g + 1 < a.n_fg ? a.fg_list[g + 1] : a.match_end;
+    // Q9 (a frame group with a single match contributes nothing, Taxonomer.cpp:342) and its generalisation: without syncmers a
+    // path's depth is its number of matches, so a group with fewer rows than the smaller minimum depth cannot emit a path — most
+    // groups (chance hits of one to three rows) end here without touching their rows; score_task_species skips them the same way
+    if (ge - gs < (uint64_t)min_group_rows(a.par)) return;
     uint32_t np = 0;
-    if (ge - gs > 1) {                                                            // Q9
-        const int32_t species = a.matches[gs].species_id;
-        int min_depth = a.par.min_cons_cnt;
-        if (tax_is_ancestor(a.tax, a.tax.eukaryota, species)) min_depth = a.par.min_cons_cnt_euk;
-        score_frame_group(a, gs, ge, min_depth, gs, np);
-    }
+    const int32_t species = a.matches[gs].species_id;
+    int min_depth = a.par.min_cons_cnt;
+    if (tax_is_ancestor(a.tax, a.tax.eukaryota, species)) min_depth = a.par.min_cons_cnt_euk;
+    score_frame_group(a, gs, ge, min_depth, gs, np);
     a.g_np[gs] = np;
 }
 
@@ -429,8 +438,11 @@ MBL_HD void score_task_species(const ScoreArgs& a, uint32_t sidx) {
     const uint64_t spE = sidx + 1 < a.n_sp ? a.sp_list[sidx + 1] : a.match_end;
     int32_t* perm = a.l_start + spS;
     uint32_t np = 0;
+    const uint64_t min_rows = (uint64_t)min_group_rows(a.par);
     for (uint32_t g = list_lower_bound(a.fg_list, a.n_fg, spS); g < a.n_fg && a.fg_list[g] < spE; ++g) {
         const uint64_t gs = a.fg_list[g];
+        const uint64_t ge = g + 1 < a.n_fg ? a.fg_list[g + 1] : a.match_end;
+        if (ge - gs < min_rows) continue;                                         // no paths, g_np not written (score_task_frame_group)
         const uint32_t cnt = a.g_np[gs];
         for (uint32_t k = 0; k < cnt; ++k) perm[np++] = (int32_t)(gs - spS + k);
     }

@@ -212,6 +212,9 @@ class SynthDb:
     genomes: torch.Tensor         # uint8 [n_strains, codons]
     taxonomy_blob: bytes
     taxid_list: np.ndarray
+    shard_first_value: int = 0    # build_db_parts(part=k): lower bound of the value range this stream covers
+    shard_is_tail: bool = True    #                        ... and whether it ends with the numerically last k-mer of the index
+    range_cuts: tuple = ()
 
     def write(self, path: str):
         os.makedirs(path, exist_ok=True)
@@ -229,11 +232,13 @@ class SynthDb:
                     % (p.skip_redundancy, p.syncmer, ("S-mer_len\t%d\n" % p.smer_len) if p.syncmer else "", p.kmer_format))    # IndexCreator.cpp:1258-1270
 
 
-def encode_index(values_i64: torch.Tensor, split_num: int = 4096):
-    """values: sorted uint64 bit patterns (int64 tensor).  -> (diffIdx u16 numpy, split u64 numpy[split_num*3])"""
+def encode_index(values_i64: torch.Tensor, split_num: int = 4096, prev: int = 0):
+    """values: sorted uint64 bit patterns (int64 tensor); prev: the value the first delta is relative to (0 at the start of a
+    stream).  -> (diffIdx u16 numpy, split u64 numpy[split_num*3])"""
     dev = values_i64.device
     n = values_i64.numel()
-    prev = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), values_i64[:-1]])
+    prev0 = torch.tensor([prev if prev < (1 << 63) else prev - (1 << 64)], dtype=torch.int64, device=dev)
+    prev = torch.cat([prev0, values_i64[:-1]])
     d = values_i64 - prev                      # wraps; only d[0] can exceed 2^63 (as unsigned)
     # number of 15-bit fragments; treat d as unsigned
     neg = d < 0
@@ -292,19 +297,34 @@ def syncmer_mask(values_i64: torch.Tensor, smer_len: int) -> torch.Tensor:
     return first | last
 
 
-def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, chunk_rows: int = 4096, kmer_format: int = 2,
-             syncmer: int = 0, smer_len: int = 5) -> SynthDb:
+def collect_range(tx: SynthTaxonomy, genomes: torch.Tensor, lo: int | None = None, hi: int | None = None, chunk_rows: int = 4096,
+                  kmer_format: int = 2, syncmer: int = 0, smer_len: int = 5):
+    """The index entries whose value lies in [lo, hi) (unsigned; None = open end), sorted by value: -> (values int64 bit patterns,
+    info int32).  One entry per (value, species) with taxid = the strain, or the species when several strains share the k-mer."""
     dev = genomes.device
     strain_t = torch.as_tensor(tx.strain_ids.astype(np.int64), device=dev)
     species_t = torch.as_tensor(tx.species_of_strain.astype(np.int64), device=dev)
+    lo_s = None if lo is None else torch.tensor(lo if lo < (1 << 63) else lo - (1 << 64), dtype=torch.int64, device=dev) ^ _TOP
+    hi_s = None if hi is None else torch.tensor(hi if hi < (1 << 63) else hi - (1 << 64), dtype=torch.int64, device=dev) ^ _TOP
     vals, tids, sps = [], [], []
+    chunk_rows = max(8, min(chunk_rows, (1 << 28) // max(1, genomes.shape[1])))      # <= 2 GiB of int64 metamers per step
     for r0 in range(0, genomes.shape[0], chunk_rows):
         g = genomes[r0:r0 + chunk_rows]
         v = _metamers(g, kmer_format)
         t_ = strain_t[r0:r0 + chunk_rows, None].expand_as(v)
         s_ = species_t[r0:r0 + chunk_rows, None].expand_as(v)
+        keep = None
         if syncmer:                                  # IndexCreator.cpp:940 / 1052: the index holds syncmers only
             keep = syncmer_mask(v, smer_len)
+        if lo_s is not None or hi_s is not None:
+            sv = v ^ _TOP                            # unsigned order as signed order
+            rng = torch.ones_like(v, dtype=torch.bool)
+            if lo_s is not None:
+                rng &= sv >= lo_s
+            if hi_s is not None:
+                rng &= sv < hi_s
+            keep = rng if keep is None else (keep & rng)
+        if keep is not None:
             vals.append(v[keep]); tids.append(t_[keep]); sps.append(s_[keep])
             continue
         vals.append(v.flatten())
@@ -312,6 +332,8 @@ def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, ch
         sps.append(s_.flatten())
     val = torch.cat(vals); tid = torch.cat(tids); sp = torch.cat(sps)
     del vals, tids, sps
+    if val.numel() == 0:
+        return val, torch.zeros(0, dtype=torch.int32, device=dev)
     # order by (value unsigned, species, taxid): three stable sorts, least significant key first
     o = torch.sort(tid, stable=True).indices
     val, tid, sp = val[o], tid[o], sp[o]
@@ -330,8 +352,27 @@ def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, ch
     uval = val[first]
     usp = sp[first]
     info = torch.where(tmin == tmax, tmin, usp).to(torch.int32)
-    del val, tid, sp, grp, first
-    diff, split = encode_index(uval, split_num)
+    return uval, info
+
+
+def range_cuts(genomes: torch.Tensor, n_parts: int, kmer_format: int = 2, sample_rows: int = 64) -> list:
+    """n_parts - 1 ascending cut values (unsigned ints with the DNA bits cleared, i.e. amino-acid-group aligned) that split the
+    metamers of these genomes into ranges of about equal size — quantiles of a sample of rows."""
+    if n_parts <= 1:
+        return []
+    rows = torch.linspace(0, genomes.shape[0] - 1, min(sample_rows, genomes.shape[0])).long().to(genomes.device)
+    v = torch.sort(_metamers(genomes[rows], kmer_format).flatten() ^ _TOP).values ^ _TOP
+    cuts = []
+    for k in range(1, n_parts):
+        x = int(v[(v.numel() * k) // n_parts].item()) & 0xFFFFFFFFFFFFFFFF
+        x &= ~0xFFFFFF
+        if cuts and x <= cuts[-1]:
+            continue
+        cuts.append(x)
+    return cuts
+
+
+def _finish_db(tx, genomes, diff, info_np, split, kmer_format, syncmer, smer_len) -> SynthDb:
     blob = taxonomy_db_bytes(tx)
     tmp = "/tmp/_mbl_synth_tax_%d" % os.getpid()
     with open(tmp, "wb") as f:
@@ -340,14 +381,66 @@ def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, ch
     os.remove(tmp)
     taxid_list = np.concatenate([tx.strain_ids, tx.species_ids]).astype(np.int32)
     params = DbParameters(kmer_format=kmer_format, skip_redundancy=1, syncmer=1 if syncmer else 0, smer_len=smer_len)
-    db = Database(params, diff, info.cpu().numpy(), split, taxdb, taxdb.build_taxid2species(taxid_list))
+    db = Database(params, diff, info_np, split, taxdb, taxdb.build_taxid2species(taxid_list))
     return SynthDb(db, tx, genomes, blob, taxid_list)
 
 
+def build_db(tx: SynthTaxonomy, genomes: torch.Tensor, split_num: int = 4096, chunk_rows: int = 4096, kmer_format: int = 2,
+             syncmer: int = 0, smer_len: int = 5) -> SynthDb:
+    uval, info = collect_range(tx, genomes, None, None, chunk_rows, kmer_format, syncmer, smer_len)
+    diff, split = encode_index(uval, split_num)
+    return _finish_db(tx, genomes, diff, info.cpu().numpy(), split, kmer_format, syncmer, smer_len)
+
+
+def build_db_parts(tx: SynthTaxonomy, genomes: torch.Tensor, n_parts: int, part: int | None = None, kmer_format: int = 2,
+                   chunk_rows: int = 4096) -> SynthDb:
+    """The same index as build_db, generated one value range at a time so that the generator's working set (three int64 per
+    metamer before de-duplication, plus sort scratch) stays at 1 / n_parts of a whole-index build — the 40 GiB configurations.
+    part = None: all ranges, concatenated on the host (split checkpoints are left empty: the shard planner then scans the stream).
+    part = k or (k0, k1): ONLY those ranges, encoded as a stream of its own whose first delta is relative to 0 — the shard of one
+    rank in the index-sharded benchmark (SynthDb.shard_first_value / shard_is_tail tell mbl_load_db_shard where it sits;
+    SynthDb.range_cuts are the cut values of all ranges, identical on every rank)."""
+    cuts = range_cuts(genomes, n_parts, kmer_format)
+    bounds = [None] + cuts + [None]
+    n_ranges = len(bounds) - 1
+    diffs, infos = [], []
+    prev = 0
+    first_value = 0
+    if part is None:
+        p_lo, p_hi = 0, n_ranges
+    elif isinstance(part, tuple):
+        p_lo, p_hi = min(part[0], n_ranges), min(part[1], n_ranges)
+    else:
+        p_lo, p_hi = min(part, n_ranges), min(part + 1, n_ranges)
+    for k in range(p_lo, p_hi):
+        uval, info = collect_range(tx, genomes, bounds[k], bounds[k + 1], chunk_rows, kmer_format)
+        if uval.numel() == 0:
+            continue
+        d, _ = encode_index(uval, 1, prev=prev)
+        if not diffs:
+            first_value = int(uval[0].item()) & 0xFFFFFFFFFFFFFFFF
+        prev = int(uval[-1].item()) & 0xFFFFFFFFFFFFFFFF
+        diffs.append(d); infos.append(info.cpu().numpy())
+        del uval, info
+        if genomes.device.type == "cuda":
+            torch.cuda.empty_cache()
+    diff = np.concatenate(diffs) if diffs else np.zeros(0, dtype=np.uint16)
+    info_np = np.concatenate(infos) if infos else np.zeros(0, dtype=np.int32)
+    sdb = _finish_db(tx, genomes, diff, info_np, np.zeros(3, dtype=np.uint64), kmer_format, 0, 5)
+    sdb.shard_first_value = (bounds[p_lo] or 0) if p_lo < n_ranges else 0xFFFFFFFFFFFFFFFF
+    sdb.shard_is_tail = p_hi >= n_ranges
+    sdb.range_cuts = tuple(cuts)
+    return sdb
+
+
 def make_db(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, species_div=0.12, strain_div=0.01, seed=3,
-            eukaryote_genera=0, device="cpu", split_num=4096, kmer_format=2, syncmer=0, smer_len=5, accession_leaves=False) -> SynthDb:
+            eukaryote_genera=0, device="cpu", split_num=4096, kmer_format=2, syncmer=0, smer_len=5, accession_leaves=False,
+            parts=1, part=None) -> SynthDb:
+    """parts > 1: build the index range by range (build_db_parts); part = k: only range k (one rank's shard)."""
     tx = make_taxonomy(genera, species_per_genus, strains_per_species, eukaryote_genera, accession_leaves)
     genomes = make_genomes(tx, codons, species_div, strain_div, seed, device)
+    if parts > 1:
+        return build_db_parts(tx, genomes, parts, part, kmer_format=kmer_format)
     sdb = build_db(tx, genomes, split_num, kmer_format=kmer_format, syncmer=syncmer, smer_len=smer_len)
     if accession_leaves:
         sdb.database.params.accession_level_db = 1
