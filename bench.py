@@ -53,7 +53,10 @@ def parse():
                          "sharded = index range-partitioned over the GPUs, metamers / matches exchanged with two NCCL all-to-alls")
     ap.add_argument("--transport", default="peer", choices=["peer", "collective"],
                     help="--mode sharded: peer = gather kernels store into the receivers' buffers over NVLink; collective = NCCL all_to_all")
-    ap.add_argument("--sharded-reads", type=int, default=4_000_000, help="reads per step and GPU in --mode sharded (HBM budget)")
+    ap.add_argument("--sharded-reads", type=int, default=10_000_000,
+                    help="N>1: read PAIRS per step over all GPUs of the index-sharded leg (configs[2]); --mode sharded: reads per step and GPU / 2.5")
+    ap.add_argument("--sharded-db-gib", type=float, default=40.0, help="N>1: index size of the index-sharded leg (configs[2])")
+    ap.add_argument("--no-sharded-leg", action="store_true", help="N>1: skip the index-sharded leg")
     return ap.parse_args()
 
 
@@ -67,22 +70,33 @@ def db_shape(db_gib: float):
     return genera, spg, 2, codons
 
 
-def build_workload(args, device, seed_reads):
+def gen_passes(db_gib: float) -> int:
+    """value ranges the index generator walks one at a time (bounds its working set; ~5 GiB of index per pass)."""
+    return max(1, int(np.ceil(db_gib / 5.0))) if db_gib > 12 else 1
+
+
+def build_workload(args, device, seed_reads, db_gib=None, n_reads=None, paired=False, parts=None, part=None):
     import torch
     from metabuli_b200 import synth
-    genera, spg, strains, codons = db_shape(args.db_gib)
+    db_gib = args.db_gib if db_gib is None else db_gib
+    n_reads = args.reads if n_reads is None else n_reads
+    genera, spg, strains, codons = db_shape(db_gib)
+    parts = gen_passes(db_gib) if parts is None else parts
     t0 = time.time()
-    sdb = synth.make_db(genera=genera, species_per_genus=spg, strains_per_species=strains, codons=codons, seed=3, device=device)
+    sdb = synth.make_db(genera=genera, species_per_genus=spg, strains_per_species=strains, codons=codons, seed=3, device=device,
+                        parts=parts, part=part)
     if device != "cpu":
         torch.cuda.synchronize()
     t1 = time.time()
-    reads = synth.make_reads(sdb, args.reads, args.read_len, seed=seed_reads, random_frac=0.3, sub_rate=0.01)
+    reads = synth.make_reads(sdb, n_reads, args.read_len, seed=seed_reads, random_frac=0.3, sub_rate=0.01, paired=paired)
     if device != "cpu":
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
     info = dict(db_gen_s=round(t1 - t0, 1), reads_gen_s=round(time.time() - t1, 1), genera=genera, species=genera * spg,
                 codons=codons, n_kmers=int(sdb.database.info.size), n_u16=int(sdb.database.diff_idx.size),
                 index_gib=round((2 * sdb.database.diff_idx.size + 4 * sdb.database.info.size) / (1 << 30), 3))
+    if parts > 1:
+        info["db_generator_passes"] = parts
     return sdb, reads, info
 
 
@@ -249,13 +263,146 @@ def parity_sample(clf, cpu, out, pairs):
     return {"reads": n, "equal": bool(equal), "checker": "oracle port (classification, score bits, query length, taxid-count list lengths)"}
 
 
+def nvlink_tx_rx_kib(index: int):
+    """(tx, rx) KiB summed over the links of one GPU from `nvidia-smi nvlink -gt d`, or None."""
+    try:
+        r = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20)
+        tx = rx = 0
+        seen = False
+        for ln in r.stdout.split("\n"):
+            ln = ln.strip()
+            if "Data Tx:" in ln:
+                tx += int(ln.split("Data Tx:")[1].split()[0]); seen = True
+            elif "Data Rx:" in ln:
+                rx += int(ln.split("Data Rx:")[1].split()[0]); seen = True
+        return (tx, rx) if seen else None
+    except Exception:
+        return None
+
+
+def sharded_leg(args, rank, local_rank, world, dist):
+    """BASELINE configs[2]: paired-end reads against a 40 GiB-class index range-partitioned over the GPUs of the box.  Every rank
+    GENERATES its own value range of the synthetic index (the same generator, restricted to the rank's amino-acid range; no rank
+    ever holds the whole index), loads it as its shard, and every step sends the metamers to the owning shard and the matches
+    back to the read owner (two exchanges over NVLink, metabuli_b200/sharded.py).  The batch is `--sharded-reads` pairs in total,
+    cut evenly over the ranks.  -> dict for the "sharded" key of the JSON line (rank 0) or None."""
+    import torch
+    from metabuli_b200 import ClassifyOptions, _ffi, sharded
+    device = f"cuda:{local_rank}"
+    per_rank_passes = max(1, int(np.ceil(gen_passes(args.sharded_db_gib) / world)))
+    parts = world * per_rank_passes
+    n_pairs = max(1, args.sharded_reads // world)
+    sdb, reads, winfo = build_workload(args, device, seed_reads=104 + rank, db_gib=args.sharded_db_gib, n_reads=n_pairs, paired=True,
+                                       parts=parts, part=(rank * per_rank_passes, (rank + 1) * per_rank_passes))
+    assert len(sdb.range_cuts) == parts - 1, "index generator produced fewer value ranges than ranks x passes"
+    sdb.genomes = None
+    torch.cuda.empty_cache()
+    b1, o1, b2, o2 = (np.ascontiguousarray(x) for x in reads)
+    n_local = int(sdb.database.info.size)
+    tot = torch.tensor([n_local, int(sdb.database.diff_idx.size)], dtype=torch.int64, device=device)
+    if dist is not None:
+        dist.all_reduce(tot)
+    total_kmers, total_u16 = int(tot[0]), int(tot[1])
+    shards = []
+    for r in range(world):
+        sh = _ffi.Shard()
+        sh.first_value = 0 if r == 0 else int(sdb.range_cuts[r * per_rank_passes - 1])
+        if r == rank:
+            sh.base_value = 0; sh.diff_begin = 0; sh.diff_end = int(sdb.database.diff_idx.size); sh.info_begin = 0; sh.info_end = n_local
+            sh.holds_db_tail = 1 if r == world - 1 else 0
+        shards.append(sh)
+    t0 = time.time()
+    sc = sharded.ShardedClassifier(sdb.database, ClassifyOptions(seq_mode=2, device=local_rank), shards, rank, total_kmers=total_kmers)
+    load_s = round(time.time() - t0, 1)
+    lib = sc.lib
+    pinned = [b1, o1, b2, o2]
+    for a in pinned:
+        lib.mbl_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes)
+    ex = sharded.DistExchange(dist, device) if world > 1 else sharded.SelfExchange()
+    have_filter = bool(sc.merge_filters(ex))
+    sc.clf.release_host_index()
+    sdb = None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res, pairs = sharded.classify_index_sharded(sc, ex, b1, o1, b2, o2, transport=args.transport)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    nv0 = nvlink_tx_rx_kib(local_rank) if rank == 0 else None
+    tm, stage_ms = {}, {}
+    merge_ms = merge_bytes = launches = merge_launches = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res, pairs = sharded.classify_index_sharded(sc, ex, b1, o1, b2, o2, timings=tm, transport=args.transport)
+        st = sc.clf.stats()
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+        merge_ms += st["ms_merge_kernel"]; merge_bytes += st["merge_bytes"]; launches += st["kernel_launches"]
+        merge_launches += st["merge_launches"]
+    barrier()
+    t_step = time.perf_counter() - t0
+    nv1 = nvlink_tx_rx_kib(local_rank) if rank == 0 else None
+    clocks = sampler.stop()
+    last = sc.clf.stats()
+    classified = int(res["is_classified"].sum())
+    if dist is not None:
+        t = torch.tensor([t_step], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_step = float(t[0])
+        cls = torch.tensor([classified], dtype=torch.int64, device=device)
+        dist.all_reduce(cls)
+        classified = int(cls[0])
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = (merge_bytes / 1e9) / (merge_ms / 1e3) if merge_ms > 0 else 0.0
+        total_pairs = n_pairs * world * args.steps
+        k_gb = tm.get("a2a_kmer_bytes", 0) / args.steps / 1e9
+        m_gb = tm.get("a2a_match_bytes", 0) / args.steps / 1e9
+        k_s = tm.get("s_a2a_kmers", 0) / args.steps
+        m_s = tm.get("s_a2a_matches", 0) / args.steps
+        out = {"metric": "read pairs/sec classified (2x150bp PE), index range-partitioned over the GPUs", "value": total_pairs / t_step,
+               "unit": "read pairs/s", "ms_per_step": 1000 * t_step / args.steps, "n_gpus": world, "scaling": "strong",
+               "workload": f"{n_pairs * world} synthetic 2x{args.read_len} bp read pairs per step ({n_pairs} per GPU) vs a "
+                           f"{round((2 * total_u16 + 4 * total_kmers) / (1 << 30), 2)} GiB synthetic index cut into {world} value ranges "
+                           f"(BASELINE configs[2]); each rank generates and holds only its range",
+               "transport": "peer-memory stores from the bucket kernels over NVLink" if args.transport == "peer" else "NCCL all_to_all_single",
+               "index_gib_total": round((2 * total_u16 + 4 * total_kmers) / (1 << 30), 3), "shard0_gib": winfo["index_gib"],
+               "index_kmers_total": total_kmers, "presence_filter": have_filter, "db_gen_s": winfo["db_gen_s"], "db_load_s": load_s,
+               "db_generator_passes_per_rank": per_rank_passes,
+               "classified_pairs_per_step": classified, "rank0_received_kmers_per_step": last["n_query_kmers"], "rank0_matches_per_step": last["n_matches"],
+               "phases_ms_per_step_rank0": {k: round(1000 * v / args.steps, 2) for k, v in tm.items() if k.startswith("s_")},
+               "a2a_rank0": {"kmer_gb_out_per_step": k_gb, "match_gb_out_per_step": m_gb,
+                             "kmer_exchange_gbs": k_gb / k_s if k_s > 0 else None, "match_exchange_gbs": m_gb / m_s if m_s > 0 else None,
+                             "note": "bytes this rank stores into its peers' buffers / wall time of the exchange phase (push kernel + count all-gather + barrier)"},
+               "nvlink_rank0": None if not (nv0 and nv1) else {"tx_gb_per_step": (nv1[0] - nv0[0]) * 1024 / 1e9 / args.steps,
+                                                              "rx_gb_per_step": (nv1[1] - nv0[1]) * 1024 / 1e9 / args.steps,
+                                                              "source": "nvidia-smi nvlink -gt d, GPU of rank 0, before/after the timed steps"},
+               "merge_roofline_rank0": {"achieved": achieved, "peak": peak, "frac": achieved / peak if peak else None, "unit": "GB/s",
+                                        "ms_per_launch": merge_ms / max(1, merge_launches)},
+               "stages_ms_per_step_rank0": {k: round(v / args.steps, 2) for k, v in stage_ms.items()},
+               "gpu_launches": launches, "clocks": clocks,
+               "h2d_bytes_per_step_per_rank": int(sum(a.nbytes for a in pinned)), "d2h_bytes_per_step_per_rank": int(res.nbytes + pairs.nbytes)}
+    for a in pinned:
+        lib.mbl_host_unregister(a.ctypes.data_as(C.c_void_p))
+    sc.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def sharded_arm(args, rank, local_rank, world, dist):
     """--mode sharded: the index is range-partitioned over the ranks (mbl_plan_shards), every step moves the metamers to the
     owning shard and the matches back with two NCCL all-to-alls (metabuli_b200/sharded.py).  Every step starts from host
     buffers and ends with the per-read results on the host, so value and e2e are the same measurement here."""
     import torch
     from metabuli_b200 import ClassifyOptions, sharded
-    args.reads = args.sharded_reads
+    args.reads = max(1, int(args.sharded_reads / 2.5))
     device = f"cuda:{local_rank}"
     sdb, reads, winfo = build_workload(args, device, seed_reads=4 + rank)
     bases, offs = np.ascontiguousarray(reads[0]), np.ascontiguousarray(reads[1])
@@ -474,6 +621,21 @@ def main():
         except Exception as e:  # the baseline is a reported number, never a reason to fail the bench
             cpu = {"value": None, "unit": "reads/s", "cores": threads, "kind": "reference" if os.path.exists(REF_BIN) else "port", "sample": f"failed: {e}"}
 
+    # N > 1: the north-star partitioning as a second leg of the same run (index range-partitioned, two exchanges per step)
+    sharded_out = None
+    if world > 1 and not args.no_sharded_leg:
+        for a in (bases, offs, out, pairs):
+            lib.mbl_host_unregister(a.ctypes.data_as(C.c_void_p))
+        clf.close()
+        clf = None
+        del batch, keep
+        torch.cuda.empty_cache()
+        try:
+            sharded_out = sharded_leg(args, rank, local_rank, world, dist)
+        except Exception as e:            # the replica numbers stand on their own; a failed second leg is reported, not fatal
+            import traceback
+            sharded_out = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = (merge_bytes / 1e9) / (merge_ms / 1e3) if merge_ms > 0 else 0.0
@@ -502,10 +664,13 @@ def main():
             "clocks": clocks,
             "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         }
+        if world > 1:
+            line["sharded"] = sharded_out
         print(json.dumps(line))
-    for a in (bases, offs, out, pairs):
-        lib.mbl_host_unregister(a.ctypes.data_as(C.c_void_p))
-    clf.close()
+    if clf is not None:
+        for a in (bases, offs, out, pairs):
+            lib.mbl_host_unregister(a.ctypes.data_as(C.c_void_p))
+        clf.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

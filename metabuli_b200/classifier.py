@@ -39,8 +39,11 @@ def _ptr(a):
 class Classifier:
     """Classifier(par): loads the DB (loadDbParameters, loadTaxonomy, KmerMatcher::loadTaxIdList) onto the GPU."""
 
-    def __init__(self, db_dir: str | None, opt: ClassifyOptions | None = None, database: Database | None = None, shard=None):
-        """shard: an _ffi.Shard from sharded.plan_shards -> only that value range of the index is uploaded (mbl_load_db_shard)."""
+    def __init__(self, db_dir: str | None, opt: ClassifyOptions | None = None, database: Database | None = None, shard=None,
+                 total_kmers: int | None = None):
+        """shard: an _ffi.Shard from sharded.plan_shards -> only that value range of the index is uploaded (mbl_load_db_shard).
+        total_kmers: k-mers of the WHOLE index when `database` holds one rank's part only (sizes the presence filter, which
+        every rank must lay out identically)."""
         self.opt = opt or ClassifyOptions()
         self.lib = _ffi.load_library()
         self.db = database if database is not None else load_database(db_dir)
@@ -62,8 +65,8 @@ class Classifier:
             raise _ffi.MblError(rc, "mbl_create failed (no usable CUDA device?)" if rc == _ffi.MBL_E_NO_DEVICE else "mbl_create failed")
         t = self.db.tax
         self._keep = [np.ascontiguousarray(self.db.diff_idx), np.ascontiguousarray(self.db.info), np.ascontiguousarray(self.db.split)]
-        dbs = _ffi.Db(_ptr(self._keep[0]), self._keep[0].size, _ptr(self._keep[1]), self._keep[1].size, _ptr(self._keep[2]),
-                      self._keep[2].size // 3)
+        dbs = _ffi.Db(_ptr(self._keep[0]), self._keep[0].size, _ptr(self._keep[1]), max(self._keep[1].size, int(total_kmers or 0)),
+                      _ptr(self._keep[2]), self._keep[2].size // 3)
         tx = _ffi.Taxonomy(t.max_nodes, t.max_taxid, t.eukaryota, _ptr(t.D), _ptr(t.E), _ptr(t.L), _ptr(t.H), _ptr(t.M), t.M_k,
                            _ptr(t.node_taxid), _ptr(t.node_parent), _ptr(t.node_prune), _ptr(t.node_rank),
                            _ptr(self.db.taxid2species))

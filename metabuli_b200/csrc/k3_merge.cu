@@ -603,7 +603,7 @@ __host__ __device__ inline SmemLayout2 smem_layout2(uint32_t max_u16, uint32_t m
 }
 
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 4 : 2)      // 64 registers either way: 32 warps per SM when shared memory allows
 merge_kernel_v2(MergeArgs a) {
     constexpr int kWarps = kThreads / 32;
     constexpr uint32_t kQR = 2 * kThreads;            // queries per round

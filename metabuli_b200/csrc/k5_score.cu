@@ -15,18 +15,30 @@ __global__ void __launch_bounds__(128, 4) score_kernel(ScoreArgs a) {
 }
 
 // ---- flat pipeline ---------------------------------------------------------------------------------------------
+// n_long counts the frame groups with at least min_rows rows — the only ones getMatchPaths can emit a path for (min_group_rows);
+// after the length ordering below they are the first n_long tasks, and only those get a thread
 __global__ void score_mark_kernel(const mbl_match_rec* __restrict__ m, uint64_t begin, uint64_t end, uint8_t* __restrict__ flag_fg,
-                                  uint8_t* __restrict__ flag_sp) {
+                                  uint8_t* __restrict__ flag_sp, uint32_t min_rows, uint32_t* __restrict__ n_long) {
     const uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= end) return;
-    bool sp = true, fg = true;
-    if (i > begin) {
-        const uint64_t q = m[i].qinfo, pq = m[i - 1].qinfo;
-        sp = qi_seq(q) != qi_seq(pq) || m[i].species_id != m[i - 1].species_id;
-        fg = sp || qi_frame(q) != qi_frame(pq);
+    bool is_long = false;
+    if (i < end) {
+        bool sp = true, fg = true;
+        const uint64_t q = m[i].qinfo;
+        const int32_t species = m[i].species_id;
+        if (i > begin) {
+            const uint64_t pq = m[i - 1].qinfo;
+            sp = qi_seq(q) != qi_seq(pq) || species != m[i - 1].species_id;
+            fg = sp || qi_frame(q) != qi_frame(pq);
+        }
+        flag_sp[i - begin] = sp;
+        flag_fg[i - begin] = fg;
+        if (fg && i + min_rows - 1 < end) {              // sorted by (read, species, frame): same group <=> same triple min_rows - 1 rows on
+            const uint64_t lq = m[i + min_rows - 1].qinfo;
+            is_long = qi_seq(lq) == qi_seq(q) && qi_frame(lq) == qi_frame(q) && m[i + min_rows - 1].species_id == species;
+        }
     }
-    flag_sp[i - begin] = sp;
-    flag_fg[i - begin] = fg;
+    const uint32_t bal = __ballot_sync(0xffffffffu, is_long);
+    if (bal && (threadIdx.x & 31) == 0) atomicAdd(n_long, (uint32_t)__popc(bal));
 }
 // Frame groups differ a lot in length (the true species in the true frame holds tens of matches, chance hits one or
 // two), so one group per thread in list order leaves most lanes of a warp idle.  Tasks are therefore ordered by length,
@@ -39,9 +51,9 @@ __global__ void fg_len_key_kernel(const uint32_t* __restrict__ fg_list, uint32_t
     key[g] = (uint8_t)(255u - (uint32_t)min(len, (uint64_t)255));
     idx[g] = g;
 }
-__global__ void __launch_bounds__(128, 8) score_fg_kernel(ScoreArgs a) {
+__global__ void __launch_bounds__(128, 8) score_fg_kernel(ScoreArgs a, uint32_t n_tasks) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < a.n_fg) score_task_frame_group(a, g);
+    if (g < n_tasks) score_task_frame_group(a, g);
 }
 __global__ void __launch_bounds__(128, 4) score_sp_kernel(ScoreArgs a) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,16 +74,18 @@ size_t score_flat_temp_bytes(size_t n) {
 void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch& s, cudaStream_t st) {
     const uint64_t n = a.match_end - match_begin;
     if (a.n_reads == 0) return;
-    uint32_t h_counts[2] = {0, 0};
+    uint32_t h_counts[3] = {0, 0, 0};
     if (n) {
-        score_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.matches, match_begin, a.match_end, s.flags_fg, s.flags_sp);
+        MBL_CUDA(cudaMemsetAsync(s.counts + 2, 0, 4, st));
+        score_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.matches, match_begin, a.match_end, s.flags_fg, s.flags_sp,
+                                                                      (uint32_t)min(min_group_rows(a.par), 255), s.counts + 2);   // 255: the length key saturates there
         size_t tb = s.cub_tmp_bytes;
         MBL_CUDA(cub::DeviceSelect::Flagged(s.cub_tmp, tb, cub::CountingInputIterator<uint32_t>((uint32_t)match_begin), s.flags_fg, s.fg_list,
                                             s.counts, (long long)n, st));
         tb = s.cub_tmp_bytes;
         MBL_CUDA(cub::DeviceSelect::Flagged(s.cub_tmp, tb, cub::CountingInputIterator<uint32_t>((uint32_t)match_begin), s.flags_sp, s.sp_list,
                                             s.counts + 1, (long long)n, st));
-        MBL_CUDA(cudaMemcpyAsync(h_counts, s.counts, 8, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaMemcpyAsync(h_counts, s.counts, 12, cudaMemcpyDeviceToHost, st));
         MBL_CUDA(cudaStreamSynchronize(st));
     }
     a.fg_list = s.fg_list; a.n_fg = h_counts[0]; a.sp_list = s.sp_list; a.n_sp = h_counts[1];
@@ -84,7 +98,9 @@ void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch
         MBL_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tb, k, v, (long long)a.n_fg, 0, 8, st));
         a.fg_order = v.Current();
     }
-    if (a.n_fg) score_fg_kernel<<<(a.n_fg + 127) / 128, 128, 0, st>>>(a);
+    // tasks are ordered longest group first, so the groups that can emit a path are the first n_long ones (a single group: no order)
+    const uint32_t n_tasks = a.fg_order ? (h_counts[2] < a.n_fg ? h_counts[2] : a.n_fg) : a.n_fg;
+    if (n_tasks) score_fg_kernel<<<(n_tasks + 127) / 128, 128, 0, st>>>(a, n_tasks);
     if (a.n_sp) score_sp_kernel<<<(a.n_sp + 127) / 128, 128, 0, st>>>(a);
     score_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);
 }

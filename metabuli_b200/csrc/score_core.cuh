@@ -439,6 +439,7 @@ MBL_HD void score_task_species(const ScoreArgs& a, uint32_t sidx) {
     int32_t* perm = a.l_start + spS;
     uint32_t np = 0;
     const uint64_t min_rows = (uint64_t)min_group_rows(a.par);
+    if (spE - spS < min_rows) { a.s_score[spS] = -3.0e38f; return; }              // not even one frame group long enough for a path
     for (uint32_t g = list_lower_bound(a.fg_list, a.n_fg, spS); g < a.n_fg && a.fg_list[g] < spE; ++g) {
         const uint64_t gs = a.fg_list[g];
         const uint64_t ge = g + 1 < a.n_fg ? a.fg_list[g + 1] : a.match_end;

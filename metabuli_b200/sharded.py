@@ -78,6 +78,12 @@ class DistExchange:
             torch.cuda.current_stream(t.device).synchronize()
         return parts
 
+    def broadcast_tensor(self, t, src: int):
+        import torch
+        self.dist.broadcast(t, src=src)
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+
     def rows(self, send, send_counts, recv_counts):
         """send: tensor whose dim 0 is split by send_counts -> tensor of sum(recv_counts) rows."""
         import torch
@@ -121,12 +127,14 @@ class _DevArray:
 class ShardedClassifier:
     """The classify path of one rank in index-sharded mode: a Classifier context that holds one shard of the index."""
 
-    def __init__(self, database, opt, shards, rank: int):
+    def __init__(self, database, opt, shards, rank: int, total_kmers: int | None = None):
+        """database: the whole index (shards[rank] is cut out of it), or — with total_kmers — only this rank's part as a stream of
+        its own (shards[rank] then spans it from 0; the other entries of `shards` only carry their first_value)."""
         from .classifier import Classifier
         self.rank = rank
         self.shards = shards
         self.first_values = shard_first_values(shards)
-        self.clf = Classifier(None, opt, database=database, shard=shards[rank])
+        self.clf = Classifier(None, opt, database=database, shard=shards[rank], total_kmers=total_kmers)
         self.lib = self.clf.lib
         self.ctx = self.clf.ctx
         self.device = f"cuda:{opt.device}"
@@ -152,9 +160,23 @@ class ShardedClassifier:
         if not p.value or nb.value == 0:
             return False
         mine = self._tensor(p.value, (nb.value // 8,))
-        for r, part in enumerate(exchange.all_gather_tensor(mine)):
-            if r != exchange.rank:
-                self.clf._check(self.lib.mbl_shard_filter_or(self.ctx, part.data_ptr(), nb.value, 0))
+        if hasattr(exchange, "broadcast_tensor"):
+            # one scratch buffer instead of world copies (the filter of a 40 GiB index is ~11 GB): rank r broadcasts what it
+            # has at its turn — possibly already OR-ed with earlier ranks' parts, which changes nothing (OR is idempotent)
+            import torch
+            tmp = torch.empty_like(mine)
+            for r in range(exchange.world):
+                if r == exchange.rank:
+                    exchange.broadcast_tensor(mine, r)
+                else:
+                    exchange.broadcast_tensor(tmp, r)
+                    self.clf._check(self.lib.mbl_shard_filter_or(self.ctx, tmp.data_ptr(), nb.value, 0))
+            del tmp
+            torch.cuda.empty_cache()
+        else:
+            for r, part in enumerate(exchange.all_gather_tensor(mine)):
+                if r != exchange.rank:
+                    self.clf._check(self.lib.mbl_shard_filter_or(self.ctx, part.data_ptr(), nb.value, 0))
         self.clf._check(self.lib.mbl_shard_filter_or(self.ctx, None, nb.value, 1))
         exchange.barrier()
         return True
