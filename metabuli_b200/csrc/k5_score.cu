@@ -37,9 +37,24 @@ __global__ void score_mark_kernel(const mbl_match_rec* __restrict__ m, uint64_t 
             is_long = qi_seq(lq) == qi_seq(q) && qi_frame(lq) == qi_frame(q) && m[i + min_rows - 1].species_id == species;
         }
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, is_long);
-    if (bal && (threadIdx.x & 31) == 0) atomicAdd(n_long, (uint32_t)__popc(bal));
+    const int cnt = __syncthreads_count(is_long);          // one atomic per block: ~10^9 rows must not queue up on one address
+    if (cnt && threadIdx.x == 0) atomicAdd(n_long, (uint32_t)cnt);
 }
+// first species task of every read that has matches (read_sp[seqID - 1]): spares score_read two binary searches over sp_list
+__global__ void read_first_species_kernel(const mbl_match_rec* __restrict__ m, const uint32_t* __restrict__ sp_list, uint32_t n_sp,
+                                          uint32_t* __restrict__ read_sp) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sp) return;
+    const uint32_t seq = qi_seq(m[sp_list[s]].qinfo);
+    if (s == 0 || qi_seq(m[sp_list[s - 1]].qinfo) != seq) read_sp[seq - 1] = s;
+}
+// flag of frame-group task g: it is the first one of its species group (both lists come from the same flags)
+struct SpeciesStartOfGroup {
+    const uint8_t* flag_sp;
+    const uint32_t* fg_list;
+    uint32_t match_begin;
+    __host__ __device__ uint8_t operator()(uint32_t g) const { return flag_sp[fg_list[g] - match_begin]; }
+};
 // Frame groups differ a lot in length (the true species in the true frame holds tens of matches, chance hits one or
 // two), so one group per thread in list order leaves most lanes of a warp idle.  Tasks are therefore ordered by length,
 // longest first: key = 255 - min(length, 255), one 8-bit radix pass.
@@ -77,7 +92,7 @@ void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch
     uint32_t h_counts[3] = {0, 0, 0};
     if (n) {
         MBL_CUDA(cudaMemsetAsync(s.counts + 2, 0, 4, st));
-        score_mark_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.matches, match_begin, a.match_end, s.flags_fg, s.flags_sp,
+        score_mark_kernel<<<(unsigned)((n + 1023) / 1024), 1024, 0, st>>>(a.matches, match_begin, a.match_end, s.flags_fg, s.flags_sp,
                                                                       (uint32_t)min(min_group_rows(a.par), 255), s.counts + 2);   // 255: the length key saturates there
         size_t tb = s.cub_tmp_bytes;
         MBL_CUDA(cub::DeviceSelect::Flagged(s.cub_tmp, tb, cub::CountingInputIterator<uint32_t>((uint32_t)match_begin), s.flags_fg, s.fg_list,
@@ -90,6 +105,17 @@ void launch_score_flat(ScoreArgs a, uint64_t match_begin, const ScoreFlatScratch
     }
     a.fg_list = s.fg_list; a.n_fg = h_counts[0]; a.sp_list = s.sp_list; a.n_sp = h_counts[1];
     a.fg_order = nullptr;
+    a.sp_fg = nullptr; a.read_sp = nullptr; a.sp_score = nullptr;
+    if (a.n_fg && a.n_sp && s.sp_fg && s.read_sp && s.sp_score) {
+        // direct maps instead of binary searches: species task -> its first frame-group task (a select over the frame-group tasks
+        // whose flag is "starts a species group"; must run before the flags are reused as sort keys), read -> its first species task
+        cub::TransformInputIterator<uint8_t, SpeciesStartOfGroup, cub::CountingInputIterator<uint32_t>> flags(
+            cub::CountingInputIterator<uint32_t>(0), SpeciesStartOfGroup{s.flags_sp, s.fg_list, (uint32_t)match_begin});
+        size_t tb = s.cub_tmp_bytes;
+        MBL_CUDA(cub::DeviceSelect::Flagged(s.cub_tmp, tb, cub::CountingInputIterator<uint32_t>(0), flags, s.sp_fg, s.counts + 3, (long long)a.n_fg, st));
+        read_first_species_kernel<<<(a.n_sp + 255) / 256, 256, 0, st>>>(a.matches, s.sp_list, a.n_sp, s.read_sp);
+        a.sp_fg = s.sp_fg; a.read_sp = s.read_sp; a.sp_score = s.sp_score;
+    }
     if (a.n_fg > 1) {
         fg_len_key_kernel<<<(a.n_fg + 255) / 256, 256, 0, st>>>(s.fg_list, a.n_fg, a.match_end, s.flags_fg, s.fg_ord);
         cub::DoubleBuffer<uint8_t> k(s.flags_fg, s.flags_sp);

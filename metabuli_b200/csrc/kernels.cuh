@@ -154,6 +154,10 @@ struct ScoreArgs {
     // flat task lists (first match index of every (species, frame) group / (read, species) group); optional
     const uint32_t* fg_list; uint32_t n_fg; const uint32_t* sp_list; uint32_t n_sp; uint32_t* g_np; uint64_t match_end;
     const uint32_t* fg_order;           // optional: permutation of the frame-group tasks (similar lengths per warp)
+    // optional direct maps of the CUDA pipeline (k5_score.cu) in place of binary searches over the task lists:
+    const uint32_t* sp_fg;              // [n_sp] index in fg_list of a species group's first frame group
+    const uint32_t* read_sp;            // [reads of the sub-batch] index in sp_list of a read's first species group
+    float* sp_score;                    // [n_sp] species scores by task index (dense) instead of s_score[first match]
     // scratch, per quotient
     int32_t* q_tax; uint8_t* q_ham; uint8_t* q_has;
     // outputs
@@ -166,6 +170,9 @@ struct ScoreFlatScratch {
     uint8_t* flags_fg; uint8_t* flags_sp;       // per match; reused as the length keys of the frame-group ordering
     uint32_t* fg_list; uint32_t* sp_list;
     uint32_t* fg_ord;                           // [2 * matches]: frame-group task order, double buffered
+    uint32_t* sp_fg;                            // [matches]: first frame-group task of every species task
+    uint32_t* read_sp;                          // [reads of the sub-batch]: first species task of every read
+    float* sp_score;                            // [matches]: species scores by task index
     uint32_t* counts; void* cub_tmp; size_t cub_tmp_bytes;
 };
 size_t score_flat_temp_bytes(size_t n_matches);

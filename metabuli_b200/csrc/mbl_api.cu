@@ -87,7 +87,7 @@ struct mbl_ctx {
     // workspace
     Buf cov1, cov2, w1, w2, slots, slot_off, quot_cnt, quot_off, seg_b, seg_e, res_sub, tax_len, tax_off;
     Buf val_a, val_b, qi_a, qi_b, cub_tmp;
-    Buf arena, chunk_bounds, order_keys, g_np, flag_fg, flag_sp, fg_list, sp_list, fg_ord, flat_tmp;     // phase 1: k-mer keys/payloads (32 B per slot); phase 2: match sort buffers
+    Buf arena, chunk_bounds, order_keys, g_np, flag_fg, flag_sp, fg_list, sp_list, fg_ord, flat_tmp, sp_fg, read_sp;     // phase 1: k-mer keys/payloads (32 B per slot); phase 2: match sort buffers
     Buf m_raw, m_sorted, key_a, key_b, idx_a, idx_b;
     Buf l_score, l_start, l_ham, l_depth, l_smatch, l_conn, p_start, p_end, p_score, p_ham, p_depth, p_smatch, p_ematch,
         c_start, c_end, s_score;
@@ -519,6 +519,9 @@ int stage_sort_score(mbl_ctx* c, const SubBatch& sb, uint64_t M) {
         flat.flags_fg = c->flag_fg.get<uint8_t>(Mp); flat.flags_sp = c->flag_sp.get<uint8_t>(Mp);
         flat.fg_list = c->fg_list.get<uint32_t>(Mp); flat.sp_list = c->sp_list.get<uint32_t>(Mp);
         flat.fg_ord = c->fg_ord.get<uint32_t>(2 * Mp);
+        flat.sp_fg = c->sp_fg.get<uint32_t>(Mp);
+        flat.read_sp = c->read_sp.get<uint32_t>(n + 1);
+        flat.sp_score = s_score;                    // the per-match array, indexed by species task (the flat passes use nothing else of it)
         flat.counts = reinterpret_cast<uint32_t*>(c->counters.get<unsigned long long>(8)) + 12;
         flat.cub_tmp = c->flat_tmp.get<uint8_t>(score_flat_temp_bytes(Mp)); flat.cub_tmp_bytes = c->flat_tmp.cap;
         for (uint32_t k = 0; k < n_chunks; ++k) {
@@ -675,7 +678,7 @@ void release_lane(mbl_ctx* c) {
     for (Buf* b : {&c->bases1, &c->bases2, &c->off1, &c->off2, &c->cov1, &c->cov2, &c->w1, &c->w2, &c->slots, &c->slot_off, &c->quot_cnt,
                    &c->quot_off, &c->seg_b, &c->seg_e, &c->res_sub, &c->tax_len, &c->tax_off, &c->val_a, &c->val_b, &c->qi_a, &c->qi_b,
                    &c->cub_tmp, &c->arena, &c->chunk_bounds, &c->order_keys, &c->g_np, &c->flag_fg, &c->flag_sp, &c->fg_list, &c->sp_list,
-                   &c->fg_ord, &c->flat_tmp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start,
+                   &c->fg_ord, &c->flat_tmp, &c->sp_fg, &c->read_sp, &c->m_raw, &c->m_sorted, &c->key_a, &c->key_b, &c->idx_a, &c->idx_b, &c->l_score, &c->l_start,
                    &c->l_ham, &c->l_depth, &c->l_smatch, &c->l_conn, &c->p_start, &c->p_end, &c->p_score, &c->p_ham, &c->p_depth,
                    &c->p_smatch, &c->p_ematch, &c->c_start, &c->c_end, &c->s_score, &c->q_tax, &c->q_ham, &c->q_has, &c->pairs_raw,
                    &c->q_lo, &c->item_cnt, &c->item_off, &c->items, &c->counters, &c->results, &c->pairs, &c->pairs_final,

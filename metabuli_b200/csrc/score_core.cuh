@@ -439,8 +439,9 @@ MBL_HD void score_task_species(const ScoreArgs& a, uint32_t sidx) {
     int32_t* perm = a.l_start + spS;
     uint32_t np = 0;
     const uint64_t min_rows = (uint64_t)min_group_rows(a.par);
-    if (spE - spS < min_rows) { a.s_score[spS] = -3.0e38f; return; }              // not even one frame group long enough for a path
-    for (uint32_t g = list_lower_bound(a.fg_list, a.n_fg, spS); g < a.n_fg && a.fg_list[g] < spE; ++g) {
+    float& result = a.sp_score ? a.sp_score[sidx] : a.s_score[spS];
+    if (spE - spS < min_rows) { result = -3.0e38f; return; }                      // not even one frame group long enough for a path
+    for (uint32_t g = a.sp_fg ? a.sp_fg[sidx] : list_lower_bound(a.fg_list, a.n_fg, spS); g < a.n_fg && a.fg_list[g] < spE; ++g) {
         const uint64_t gs = a.fg_list[g];
         const uint64_t ge = g + 1 < a.n_fg ? a.fg_list[g + 1] : a.match_end;
         if (ge - gs < min_rows) continue;                                         // no paths, g_np not written (score_task_frame_group)
@@ -454,7 +455,7 @@ MBL_HD void score_task_species(const ScoreArgs& a, uint32_t sidx) {
         score = fminf(score, 1.0f);
         if (!(score < a.par.min_score)) out = score;
     }
-    a.s_score[spS] = out;
+    result = out;
 }
 
 // ---- chooseBestTaxon for read r -----------------------------------------------------------------------
@@ -477,10 +478,10 @@ MBL_HD void score_read(const ScoreArgs& a, uint32_t r) {
     uint64_t i = ms;
     if (a.sp_list) {
         // flat pipeline: the species scores are already in s_score (tasks A and B)
-        for (uint32_t sidx = list_lower_bound(a.sp_list, a.n_sp, ms); sidx < a.n_sp && a.sp_list[sidx] < me; ++sidx) {
+        for (uint32_t sidx = a.read_sp ? a.read_sp[r] : list_lower_bound(a.sp_list, a.n_sp, ms); sidx < a.n_sp && a.sp_list[sidx] < me; ++sidx) {
             const uint64_t spS = a.sp_list[sidx];
             const uint64_t spE = sidx + 1 < a.n_sp && a.sp_list[sidx + 1] < me ? a.sp_list[sidx + 1] : me;
-            const float score = a.s_score[spS];
+            const float score = a.sp_score ? a.sp_score[sidx] : a.s_score[spS];
             if (score > -1.0e38f) {
                 if (score > 0.f) ++meaningful;
                 if (score > bestSpScore) { bestSpScore = score; bestS = spS; bestE = spE; }
@@ -519,13 +520,14 @@ MBL_HD void score_read(const ScoreArgs& a, uint32_t r) {
         int red = 0;
         bool haveRed = false;
         i = ms;
-        uint32_t sidx = a.sp_list ? list_lower_bound(a.sp_list, a.n_sp, ms) : 0;
+        uint32_t sidx = a.sp_list ? (a.read_sp ? a.read_sp[r] : list_lower_bound(a.sp_list, a.n_sp, ms)) : 0;
         while (i < me) {
             const int32_t species = ml[i].species_id;
             const uint64_t spS = i;
+            const uint32_t this_sidx = sidx;
             if (a.sp_list) { ++sidx; i = sidx < a.n_sp && a.sp_list[sidx] < me ? a.sp_list[sidx] : me; }
             else while (i < me && ml[i].species_id == species) ++i;
-            const float sc = a.s_score[spS];
+            const float sc = (a.sp_list && a.sp_score) ? a.sp_score[this_sidx] : a.s_score[spS];
             if (sc > -1.0e38f && sc >= thr) {
                 if (nMax == 0) taxId = species;
                 ++nMax;
