@@ -56,7 +56,9 @@ def parse():
     ap.add_argument("--sharded-reads", type=int, default=10_000_000,
                     help="N>1: read PAIRS per step over all GPUs of the index-sharded leg (configs[2]); --mode sharded: reads per step and GPU / 2.5")
     ap.add_argument("--sharded-db-gib", type=float, default=40.0, help="N>1: index size of the index-sharded leg (configs[2])")
+    ap.add_argument("--sharded-round-pairs", type=int, default=1_250_000, help="N>1: read pairs per rank per exchange round of the index-sharded leg")
     ap.add_argument("--no-sharded-leg", action="store_true", help="N>1: skip the index-sharded leg")
+    ap.add_argument("--sharded-leg-only", action="store_true", help="development: run only the index-sharded leg and print its dict")
     return ap.parse_args()
 
 
@@ -311,17 +313,21 @@ def sharded_leg(args, rank, local_rank, world, dist):
             sh.base_value = 0; sh.diff_begin = 0; sh.diff_end = int(sdb.database.diff_idx.size); sh.info_begin = 0; sh.info_end = n_local
             sh.holds_db_tail = 1 if r == world - 1 else 0
         shards.append(sh)
+    def note(msg):
+        if rank == 0:
+            free_b, total_b = torch.cuda.mem_get_info()
+            print(f"[sharded leg] {msg} (rank 0: {free_b / 1e9:.1f} of {total_b / 1e9:.1f} GB free)", file=sys.stderr, flush=True)
+    note(f"generated {winfo['index_gib']} GiB of {round((2 * total_u16 + 4 * total_kmers) / (1 << 30), 2)} GiB in {winfo['db_gen_s']} s, {n_pairs} pairs per rank")
     t0 = time.time()
     sc = sharded.ShardedClassifier(sdb.database, ClassifyOptions(seq_mode=2, device=local_rank), shards, rank, total_kmers=total_kmers)
     load_s = round(time.time() - t0, 1)
+    note(f"shard loaded in {load_s} s")
     lib = sc.lib
-    pinned = [b1, o1, b2, o2]
-    for a in pinned:
-        lib.mbl_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes)
     ex = sharded.DistExchange(dist, device) if world > 1 else sharded.SelfExchange()
     have_filter = bool(sc.merge_filters(ex))
     sc.clf.release_host_index()
     sdb = None
+    note(f"presence filter merged: {have_filter}")
 
     def barrier():
         torch.cuda.synchronize()
@@ -329,28 +335,55 @@ def sharded_leg(args, rank, local_rank, world, dist):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        res, pairs = sharded.classify_index_sharded(sc, ex, b1, o1, b2, o2, transport=args.transport)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    nv0 = nvlink_tx_rx_kib(local_rank) if rank == 0 else None
+    # a step = the rank's share of the batch, walked in exchange rounds of at most --sharded-round-pairs pairs per rank (the
+    # receive buffers, the bucket arrays and the match buffer of a round are sized by what ONE round moves; the reference's
+    # QuerySplit loop does the same against --max-ram)
+    from metabuli_b200 import multigpu
+    n_rounds = max(1, int(np.ceil(n_pairs / args.sharded_round_pairs)))
+    cuts = [n_pairs * k // n_rounds for k in range(n_rounds + 1)]
+    slices = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        s1, so1 = multigpu.slice_batch(b1, o1, lo, hi)
+        s2, so2 = multigpu.slice_batch(b2, o2, lo, hi)
+        slices.append((s1, so1, s2, so2))
+    pinned = [a for sl in slices for a in sl]
+    for a in pinned:
+        lib.mbl_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes)
     tm, stage_ms = {}, {}
     merge_ms = merge_bytes = launches = merge_launches = 0
+    d2h = 0
+
+    def one_step(timed):
+        nonlocal merge_ms, merge_bytes, launches, merge_launches, d2h
+        classified, recv_k, n_m = 0, 0, 0
+        d2h = 0
+        for sl in slices:
+            res, pairs = sharded.classify_index_sharded(sc, ex, *sl, timings=tm if timed else None, transport=args.transport)
+            classified += int(res["is_classified"].sum())
+            d2h += int(res.nbytes + pairs.nbytes)
+            st = sc.clf.stats()
+            recv_k += st["n_query_kmers"]; n_m += st["n_matches"]
+            if timed:
+                for k, v in st.items():
+                    if k.startswith("ms_"):
+                        stage_ms[k] = stage_ms.get(k, 0.0) + v
+                merge_ms += st["ms_merge_kernel"]; merge_bytes += st["merge_bytes"]; launches += st["kernel_launches"]
+                merge_launches += st["merge_launches"]
+        return classified, recv_k, n_m
+
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    note(f"warm-up done, {n_rounds} exchange round(s) per step")
+    sampler = ClockSampler(local_rank)
+    nv0 = nvlink_tx_rx_kib(local_rank) if rank == 0 else None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res, pairs = sharded.classify_index_sharded(sc, ex, b1, o1, b2, o2, timings=tm, transport=args.transport)
-        st = sc.clf.stats()
-        for k, v in st.items():
-            if k.startswith("ms_"):
-                stage_ms[k] = stage_ms.get(k, 0.0) + v
-        merge_ms += st["ms_merge_kernel"]; merge_bytes += st["merge_bytes"]; launches += st["kernel_launches"]
-        merge_launches += st["merge_launches"]
+        classified, recv_kmers, n_matches = one_step(True)
     barrier()
     t_step = time.perf_counter() - t0
     nv1 = nvlink_tx_rx_kib(local_rank) if rank == 0 else None
     clocks = sampler.stop()
-    last = sc.clf.stats()
-    classified = int(res["is_classified"].sum())
     if dist is not None:
         t = torch.tensor([t_step], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -376,7 +409,8 @@ def sharded_leg(args, rank, local_rank, world, dist):
                "index_gib_total": round((2 * total_u16 + 4 * total_kmers) / (1 << 30), 3), "shard0_gib": winfo["index_gib"],
                "index_kmers_total": total_kmers, "presence_filter": have_filter, "db_gen_s": winfo["db_gen_s"], "db_load_s": load_s,
                "db_generator_passes_per_rank": per_rank_passes,
-               "classified_pairs_per_step": classified, "rank0_received_kmers_per_step": last["n_query_kmers"], "rank0_matches_per_step": last["n_matches"],
+               "exchange_rounds_per_step": n_rounds,
+               "classified_pairs_per_step": classified, "rank0_received_kmers_per_step": recv_kmers, "rank0_matches_per_step": n_matches,
                "phases_ms_per_step_rank0": {k: round(1000 * v / args.steps, 2) for k, v in tm.items() if k.startswith("s_")},
                "a2a_rank0": {"kmer_gb_out_per_step": k_gb, "match_gb_out_per_step": m_gb,
                              "kmer_exchange_gbs": k_gb / k_s if k_s > 0 else None, "match_exchange_gbs": m_gb / m_s if m_s > 0 else None,
@@ -388,7 +422,7 @@ def sharded_leg(args, rank, local_rank, world, dist):
                                         "ms_per_launch": merge_ms / max(1, merge_launches)},
                "stages_ms_per_step_rank0": {k: round(v / args.steps, 2) for k, v in stage_ms.items()},
                "gpu_launches": launches, "clocks": clocks,
-               "h2d_bytes_per_step_per_rank": int(sum(a.nbytes for a in pinned)), "d2h_bytes_per_step_per_rank": int(res.nbytes + pairs.nbytes)}
+               "h2d_bytes_per_step_per_rank": int(sum(a.nbytes for a in pinned)), "d2h_bytes_per_step_per_rank": d2h}
     for a in pinned:
         lib.mbl_host_unregister(a.ctypes.data_as(C.c_void_p))
     sc.close()
@@ -533,6 +567,13 @@ def main():
 
     if args.mode == "sharded":
         return sharded_arm(args, rank, local_rank, world, dist)
+    if args.sharded_leg_only:
+        out = sharded_leg(args, rank, local_rank, world, dist)
+        if rank == 0:
+            print(json.dumps({"sharded": out}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
 
     sdb, reads, winfo = build_workload(args, f"cuda:{local_rank}", seed_reads=4 + rank)
     bases, offs = np.ascontiguousarray(reads[0]), np.ascontiguousarray(reads[1])

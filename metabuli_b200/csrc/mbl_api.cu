@@ -575,7 +575,9 @@ int extract_filtered(mbl_ctx* c, const SubBatch& sb, uint64_t* n_slots_used) {
         MBL_CUDA(cudaStreamSynchronize(c->st));
         if (h[4] <= c->arena_S8 || attempt > 0) break;
         c->stats.overflow_retries += 1;
-        guess = sb.slots;
+        // the cursor kept counting past the capacity, so it IS the room the packed output needs (chunk tails included); the same
+        // reads give the same survivors, only the chunk hand-out order differs between launches: a margin covers that
+        guess = std::min<uint64_t>(sb.slots, h[4] + h[4] / 8 + 65536);
     }
     if (h[4] > c->arena_S8) return fail(c, MBL_E_CUDA, "internal: packed extraction overflow");
     *n_slots_used = h[4];
@@ -1325,6 +1327,17 @@ int mbl_shard_recv_buffers(mbl_ctx* c, uint64_t kmer_rows, uint64_t match_rows, 
         MBL_CUDA(cudaSetDevice(c->cfg.device));
         // plain cudaMalloc allocations of their own (IPC handles name whole allocations)
         for (void** p : {&c->recv_kmers, &c->recv_matches}) { if (*p) cudaFree(*p); *p = nullptr; }
+        {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            if (16 * kmer_rows + 24 * match_rows + 512 > free_b) {
+                char msg[320];
+                snprintf(msg, sizeof msg, "receive buffers for %llu metamers + %llu matches need %.1f GB, %.1f of %.1f GB free (arena %.1f GB, index %.1f GB)",
+                         (unsigned long long)kmer_rows, (unsigned long long)match_rows, (16.0 * kmer_rows + 24.0 * match_rows) / 1e9, free_b / 1e9,
+                         total_b / 1e9, c->arena.cap / 1e9, c->db_bytes / 1e9);
+                return fail(c, MBL_E_CAPACITY, msg);
+            }
+        }
         MBL_CUDA(cudaMalloc(&c->recv_kmers, 16 * kmer_rows + 256));
         MBL_CUDA(cudaMalloc(&c->recv_matches, 24 * match_rows + 256));
         c->recv_kmer_rows = kmer_rows; c->recv_match_rows = match_rows;
