@@ -653,7 +653,10 @@ def main():
     total_reads = n_reads * world * args.steps
 
     cpu = parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and winfo["index_gib"] > 16:
+        cpu = {"value": None, "unit": "reads/s", "cores": threads, "kind": "reference" if os.path.exists(REF_BIN) else "port",
+               "sample": "skipped: the CPU arm writes the index to disk for the reference binary, not done for indexes above 16 GiB"}
+    elif rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             arm = cpu_arm(sdb, reads, args.ref_reads, threads, 1, 1, keep_results=True)
             cpu = {"value": arm["rate"], "unit": "reads/s", "cores": threads, "kind": arm["kind"], "sample": arm["sample"] + "; one warm-up pass, one timed pass"}

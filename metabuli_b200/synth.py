@@ -447,6 +447,26 @@ def make_db(genera=4, species_per_genus=3, strains_per_species=2, codons=2000, s
     return sdb
 
 
+def make_long_reads(sdb: SynthDb, n_reads: int, mean_len: float = 8000.0, sigma: float = 0.6, min_len: int = 200, max_len: int = 30000,
+                    seed: int = 4, random_frac: float = 0.1, sub_rate: float = 0.08, chunk: int = 8192):
+    """ONT-like reads (BASELINE configs[3]): log-normal lengths with the given mean, clipped to [min_len, max_len], substitutions
+    only.  Generated in chunks (a chunk is a [reads, max_len] matrix on the device) -> (bases u8, offsets u64) numpy SoA."""
+    rng = np.random.default_rng(seed)
+    mu = np.log(mean_len) - 0.5 * sigma * sigma
+    lens_all = np.clip(np.exp(rng.normal(mu, sigma, n_reads)), min_len, max_len).astype(np.int64)
+    bases, offs, total = [], [np.zeros(1, dtype=np.uint64)], 0
+    for c0 in range(0, n_reads, chunk):
+        lens = lens_all[c0:c0 + chunk]
+        L = int(lens.max())
+        b, o = make_reads(sdb, len(lens), L, seed=seed + 1 + c0, random_frac=random_frac, sub_rate=sub_rate)
+        mat = b.reshape(len(lens), L)
+        keep = np.arange(L)[None, :] < lens[:, None]
+        bases.append(mat[keep])
+        offs.append((np.cumsum(lens) + total).astype(np.uint64))
+        total += int(lens.sum())
+    return np.concatenate(bases), np.concatenate(offs)
+
+
 # ---- reads ---------------------------------------------------------------------------------------------------------
 def make_reads(sdb: SynthDb, n_reads: int, length: int = 150, seed: int = 4, random_frac: float = 0.3, sub_rate: float = 0.01,
                n_rate: float = 0.0, paired: bool = False, insert: int = 350, length_jitter: int = 0, mate2_jitter: int = 0):
