@@ -576,6 +576,8 @@ def main():
         return 0
 
     sdb, reads, winfo = build_workload(args, f"cuda:{local_rank}", seed_reads=4 + rank)
+    sdb.genomes = None                             # generator state on the device: not needed any more
+    torch.cuda.empty_cache()
     bases, offs = np.ascontiguousarray(reads[0]), np.ascontiguousarray(reads[1])
     n_reads = offs.size - 1
     t0 = time.time()

@@ -117,29 +117,21 @@ inline size_t next_record_start(const std::string& data, size_t from, bool fastq
     return n;
 }
 
-// Parallel load.  Returns false with *err set on unreadable files or an entry without sequence / name.
-inline bool load_fastx(const std::string& path, ReadSet& out, unsigned threads, std::string* err) {
-    std::string data;
-    if (!slurp_maybe_gz(path, data)) { if (err) *err = "cannot open " + path; return false; }
-    size_t first = 0;
-    while (first < data.size() && data[first] != '>' && data[first] != '@') {
-        const void* nl = memchr(data.data() + first, '\n', data.size() - first);
-        if (!nl) { first = data.size(); break; }
-        first = (size_t)((const char*)nl - data.data()) + 1;
-    }
-    const bool fastq = first < data.size() && data[first] == '@';
+// data[begin, end) — a whole number of records — parsed by up to T threads (record-aligned cuts, the sequential grammar per
+// range) and APPENDED to out.  Returns false on an entry without sequence / name; *bad = its ordinal among the entries of the range.
+inline bool parse_parallel(const std::string& data, size_t begin, size_t end, bool fastq, unsigned threads, ReadSet& out, size_t* bad) {
     unsigned T = threads ? threads : 1;
-    if (data.size() < (1u << 22)) T = 1;
-    std::vector<size_t> cut(T + 1, data.size());
-    cut[0] = 0;
-    for (unsigned t = 1; t < T; ++t) cut[t] = next_record_start(data, data.size() / T * t, fastq);
+    if (end - begin < (1u << 22)) T = 1;
+    std::vector<size_t> cut(T + 1, end);
+    cut[0] = begin;
+    for (unsigned t = 1; t < T; ++t) cut[t] = std::min(end, next_record_start(data, begin + (end - begin) / T * t, fastq));
     for (unsigned t = 1; t <= T; ++t) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
     std::vector<ReadSet> part(T);
-    std::vector<size_t> bad(T, 0);
+    std::vector<size_t> badv(T, 0);
     std::vector<char> ok(T, 1);
     auto work = [&](unsigned t) {
         part[t].bases.reserve((cut[t + 1] - cut[t]) / (fastq ? 2 : 1) + 64);
-        ok[t] = parse_range(data, cut[t], cut[t + 1], part[t], &bad[t]) ? 1 : 0;
+        ok[t] = parse_range(data, cut[t], cut[t + 1], part[t], &badv[t]) ? 1 : 0;
     };
     std::vector<std::thread> th;
     for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
@@ -147,15 +139,14 @@ inline bool load_fastx(const std::string& path, ReadSet& out, unsigned threads, 
     for (auto& x : th) x.join();
     size_t n_reads = 0, n_bases = 0;
     for (unsigned t = 0; t < T; ++t) {
-        if (!ok[t]) {
-            if (err) *err = std::to_string(n_reads + bad[t]) + "th entry has no sequence or name.";
-            return false;
-        }
+        if (!ok[t]) { if (bad) *bad = n_reads + badv[t]; return false; }
         n_reads += part[t].size(); n_bases += part[t].bases.size();
     }
-    out.names.clear(); out.bases.clear(); out.offsets.assign(1, 0);
-    out.names.reserve(n_reads); out.bases.resize(n_bases); out.offsets.reserve(n_reads + 1);
-    std::vector<size_t> base_at(T + 1, 0);
+    const size_t base0 = out.bases.size();
+    out.names.reserve(out.names.size() + n_reads);
+    out.bases.resize(base0 + n_bases);
+    out.offsets.reserve(out.offsets.size() + n_reads);
+    std::vector<size_t> base_at(T + 1, base0);
     for (unsigned t = 0; t < T; ++t) base_at[t + 1] = base_at[t] + part[t].bases.size();
     for (unsigned t = 0; t < T; ++t) {
         for (auto& s : part[t].names) out.names.emplace_back(std::move(s));
@@ -168,6 +159,111 @@ inline bool load_fastx(const std::string& path, ReadSet& out, unsigned threads, 
     for (auto& x : th) x.join();
     return true;
 }
+
+inline bool sniff_fastq(const std::string& data) {
+    size_t first = 0;
+    while (first < data.size() && data[first] != '>' && data[first] != '@') {
+        const void* nl = memchr(data.data() + first, '\n', data.size() - first);
+        if (!nl) return false;
+        first = (size_t)((const char*)nl - data.data()) + 1;
+    }
+    return first < data.size() && data[first] == '@';
+}
+
+// Whole-file parallel load (tests, small inputs).  Returns false with *err set on unreadable files or an entry without
+// sequence / name.
+inline bool load_fastx(const std::string& path, ReadSet& out, unsigned threads, std::string* err) {
+    std::string data;
+    if (!slurp_maybe_gz(path, data)) { if (err) *err = "cannot open " + path; return false; }
+    out.names.clear(); out.bases.clear(); out.offsets.assign(1, 0);
+    size_t bad = 0;
+    if (!parse_parallel(data, 0, data.size(), sniff_fastq(data), threads, out, &bad)) {
+        if (err) *err = std::to_string(bad) + "th entry has no sequence or name.";
+        return false;
+    }
+    return true;
+}
+
+// Streaming reader: the file is decompressed and parsed in bounded chunks, cut at record starts, and handed out in batches of
+// at most max_reads records — the reference's QuerySplit loop bounded by --max-ram (QueryIndexer.cpp:30-147,
+// KmerExtractor.cpp:429-481) instead of a whole-file load: what is held at any time is one raw chunk, the records parsed from
+// it that were not handed out yet, and the batches in flight.
+class FastxStream {
+public:
+    ~FastxStream() { if (g_) gzclose(g_); }
+    bool open(const std::string& path, std::string* err) {
+        g_ = gzopen(path.c_str(), "rb");
+        if (!g_) { if (err) *err = "cannot open " + path; return false; }
+        gzbuffer(g_, 1 << 20);
+        return true;
+    }
+    // out is cleared and receives the next min(max_reads, remaining) records; out.size() == 0 <=> end of file
+    bool next(ReadSet& out, size_t max_reads, unsigned threads, std::string* err, size_t chunk_bytes = (size_t)256 << 20) {
+        while (pend_.size() - pos_ < max_reads && !(eof_ && buf_.empty())) {
+            if (!eof_) {
+                const size_t old = buf_.size();
+                buf_.resize(old + chunk_bytes);
+                size_t got = 0;
+                while (got < chunk_bytes) {
+                    const int r = gzread(g_, &buf_[old + got], (unsigned)std::min<size_t>(chunk_bytes - got, 1u << 30));
+                    if (r <= 0) { eof_ = true; break; }
+                    got += (size_t)r;
+                }
+                buf_.resize(old + got);
+            }
+            if (!sniffed_ && !buf_.empty()) { fastq_ = sniff_fastq(buf_); sniffed_ = true; }
+            size_t cut = buf_.size();
+            if (!eof_) {                                     // keep the (possibly incomplete) last record for the next round
+                cut = last_record_start(buf_, fastq_);
+                if (cut == 0) continue;                       // a single record longer than the chunk: read on
+            }
+            size_t bad = 0;
+            if (!parse_parallel(buf_, 0, cut, fastq_, threads, pend_, &bad)) {
+                if (err) *err = std::to_string(parsed_ + bad) + "th entry has no sequence or name.";
+                return false;
+            }
+            parsed_ = pend_.size() + consumed_;
+            buf_.erase(0, cut);
+        }
+        out.names.clear(); out.bases.clear(); out.offsets.assign(1, 0);
+        const size_t n = std::min(max_reads, pend_.size() - pos_);
+        if (n) {
+            const uint64_t b0 = pend_.offsets[pos_], b1 = pend_.offsets[pos_ + n];
+            out.names.reserve(n);
+            for (size_t i = 0; i < n; ++i) out.names.emplace_back(std::move(pend_.names[pos_ + i]));
+            out.bases.assign(pend_.bases.begin() + (ptrdiff_t)b0, pend_.bases.begin() + (ptrdiff_t)b1);
+            out.offsets.reserve(n + 1);
+            for (size_t i = 1; i <= n; ++i) out.offsets.push_back(pend_.offsets[pos_ + i] - b0);
+            pos_ += n;
+            if (pos_ == pend_.size()) {                       // everything parsed so far is handed out
+                consumed_ += pos_;
+                pend_.names.clear(); pend_.bases.clear(); pend_.offsets.assign(1, 0);
+                pos_ = 0;
+            }
+        }
+        return true;
+    }
+
+private:
+    // the last safe record start of data (0 when there is none beyond the first)
+    static size_t last_record_start(const std::string& data, bool fastq) {
+        const size_t n = data.size();
+        for (size_t window = 1u << 16;; window <<= 2) {
+            const size_t from = n > window ? n - window : 1;
+            size_t p = next_record_start(data, from, fastq);
+            if (p < n) {
+                for (size_t q = next_record_start(data, p + 1, fastq); q < n; q = next_record_start(data, q + 1, fastq)) p = q;
+                return p;
+            }
+            if (from == 1) return 0;
+        }
+    }
+    gzFile g_ = nullptr;
+    std::string buf_;
+    bool eof_ = false, fastq_ = false, sniffed_ = false;
+    ReadSet pend_;
+    size_t pos_ = 0, consumed_ = 0, parsed_ = 0;
+};
 
 // ---- Reporter::writeReadClassification rows (Reporter.cpp:43-79, printLineage 0) ------------------------------------------
 // `ostream << float` prints like %g (6 significant digits, Q12).

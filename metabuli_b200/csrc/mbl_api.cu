@@ -36,7 +36,9 @@ struct Buf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct SubBatch { uint32_t r0, r1; uint64_t slots, quots; uint32_t max_pos; };
+struct SubBatch { uint32_t r0, r1; uint64_t slots, quots; uint32_t max_pos; uint32_t b0, b1; };   // reads [r0, r1) = blocks [b0, b1)
+struct ReadBlock { uint64_t slots, quots; uint32_t max_pos; };
+struct BatchSummary { uint32_t n_reads = 0, block_reads = 1; std::vector<ReadBlock> blocks; };
 constexpr uint32_t kScoreChunkReads = 1u << 20;   // reads scored per launch (bounds the per-match scratch)
 
 }  // namespace
@@ -58,6 +60,7 @@ struct mbl_ctx {
     uint64_t arena_S8 = 0;              // slot stride of the phase-1 arena layout (set by whoever fills it)
     int merge_version = 2;              // MBL_MERGE_V1=1: the round-1 match stage (warp-private hit queues, two pair sweeps)
     int merge_threads = 0;              // MBL_MERGE_THREADS: 256 or 512 threads per merge CTA (default: 512 for v2, 256 for v1)
+    bool no_probe = false;              // the index-sharded phases work on whole batches: no probe sub-batch
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // test hooks: force the capacity guesses low so that the retry paths run on small inputs (tests/test_gpu_edge_paths.py)
     uint64_t test_match_cap = 0;        // MBL_TEST_MATCH_CAP: first match-buffer capacity (rows) of a merge
@@ -77,6 +80,8 @@ struct mbl_ctx {
     uint32_t n_reads = 0;
     bool paired = false;
     std::vector<SubBatch> subs;
+    BatchSummary summary, staged_summary;   // per-block totals of the resident / the staged batch (plan_sub_batches)
+    bool probe_first = false, staged_probe_first = false;   // the plan starts with a small probe sub-batch; plan the rest again after it
     // staging copy of the NEXT batch (mbl_prefetch_batch): uploaded on its own stream while the resident batch is classified
     Buf stage_bases1, stage_bases2, stage_off1, stage_off2;
     cudaStream_t copy_st = nullptr;
@@ -181,82 +186,96 @@ void free_db(mbl_ctx* c) {
     c->db_bytes = 0;
 }
 
-// host-side planning of sub-batches from the read lengths (QueryIndexer::indexQueryFile analogue,
-// QueryIndexer.cpp:30-147, with the HBM budget in place of --max-ram)
-void plan_sub_batches(mbl_ctx* c, const mbl_batch* b, uint64_t max_slots, std::vector<SubBatch>& subs) {
-    subs.clear();
-    auto read_cost = [&](uint32_t r, uint64_t& s, uint64_t& q, uint32_t& mp) {
-        int l1 = (int)(b->offsets[r + 1] - b->offsets[r]);
-        int w1 = windows_per_frame(l1), c1 = max_covered_length(l1), w2 = 0, c2 = 0;
-        if (b->offsets2) {
-            int l2 = (int)(b->offsets2[r + 1] - b->offsets2[r]);
-            w2 = windows_per_frame(l2); c2 = max_covered_length(l2);
-        }
-        bool empty = w1 < 1 || (b->offsets2 && w2 < 1);
-        s = empty ? 0 : 6ull * (uint64_t)(w1 + w2);
-        int ql = c1 + c2;
-        q = ql + 3 > 0 ? (uint64_t)((ql + 3) / 3 + 1) : 1;
-        mp = (uint32_t)std::max(0, c1 + 3 + c2 + 8);
-    };
-    // common case first: the whole batch fits one sub-batch — totals over a few host threads (this runs while the reads are
-    // still on their way to the device)
+// host-side planning of sub-batches from the read lengths (QueryIndexer::indexQueryFile analogue, QueryIndexer.cpp:30-147, with
+// the HBM budget in place of --max-ram).  The reads are summarised once per batch in blocks of `block_reads` reads (slot and
+// quotient totals, largest position); sub-batches are runs of whole blocks, so the plan can be redone for the rest of a batch
+// when the first sub-batch has shown how many metamers survive the filter and how many matches a slot yields — the two ratios
+// the budget rests on, unknown before the first sub-batch against a new index (a 40 GiB index yields about twice the matches
+// per slot of an 8 GiB one) — and a sub-batch that still runs out of memory can be halved.
+void summarize_reads(const mbl_batch* b, BatchSummary& sum) {
     const uint32_t n = b->n_reads;
-    const bool may_split = c->pipeline && n >= c->pipeline_min_reads && n >= 16;
-    const unsigned P = may_split ? (unsigned)std::max(2, c->pipeline_parts) : 1u;       // sub-batches of a split batch
-    const unsigned T = may_split ? P * ((8u + P - 1) / P) : (n > (1u << 18) ? 8u : 1u);
-    std::vector<SubBatch> part(T, SubBatch{0, 0, 0, 0, 0});
-    auto work = [&](unsigned t) {
-        const uint32_t r0 = (uint32_t)((uint64_t)n * t / T), r1 = (uint32_t)((uint64_t)n * (t + 1) / T);
-        SubBatch acc{r0, r1, 0, 0, 0};
-        for (uint32_t r = r0; r < r1; ++r) {
-            uint64_t s, q; uint32_t mp;
-            read_cost(r, s, q, mp);
-            acc.slots += s; acc.quots += q; acc.max_pos = std::max(acc.max_pos, mp);
+    sum.n_reads = n;
+    sum.block_reads = std::max<uint32_t>(1, std::min<uint32_t>(4096, n / 256));
+    const size_t nb = ((size_t)n + sum.block_reads - 1) / sum.block_reads;
+    sum.blocks.assign(nb, ReadBlock{0, 0, 0});
+    auto work = [&](size_t b0, size_t b1) {
+        for (size_t k = b0; k < b1; ++k) {
+            ReadBlock acc{0, 0, 0};
+            const uint32_t r1 = (uint32_t)std::min<uint64_t>(n, (uint64_t)(k + 1) * sum.block_reads);
+            for (uint32_t r = (uint32_t)(k * sum.block_reads); r < r1; ++r) {
+                const int l1 = (int)(b->offsets[r + 1] - b->offsets[r]);
+                int w1 = windows_per_frame(l1), c1 = max_covered_length(l1), w2 = 0, c2 = 0;
+                if (b->offsets2) {
+                    const int l2 = (int)(b->offsets2[r + 1] - b->offsets2[r]);
+                    w2 = windows_per_frame(l2); c2 = max_covered_length(l2);
+                }
+                const bool empty = w1 < 1 || (b->offsets2 && w2 < 1);
+                acc.slots += empty ? 0 : 6ull * (uint64_t)(w1 + w2);
+                const int ql = c1 + c2;
+                acc.quots += ql + 3 > 0 ? (uint64_t)((ql + 3) / 3 + 1) : 1;
+                acc.max_pos = std::max(acc.max_pos, (uint32_t)std::max(0, c1 + 3 + c2 + 8));
+            }
+            sum.blocks[k] = acc;
         }
-        part[t] = acc;
     };
+    const unsigned T = n > (1u << 18) ? 8u : 1u;          // runs while the reads are still on their way to the device
     if (T > 1) {
         std::vector<std::thread> th;
-        for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
-        work(0);
+        for (unsigned t = 1; t < T; ++t) th.emplace_back(work, nb * t / T, nb * (t + 1) / T);
+        work(0, nb / T);
         for (auto& x : th) x.join();
     } else {
-        work(0);
+        work(0, nb);
     }
-    SubBatch all{0, n, 0, 0, 0};
-    for (const SubBatch& p : part) { all.slots += p.slots; all.quots += p.quots; all.max_pos = std::max(all.max_pos, p.max_pos); }
-    if (n == 0) return;
-    // large batches are cut in (at least) two so that the two pipeline lanes overlap (mbl_classify_resident); each lane then
-    // owns half of the workspace budget
-    const bool split = may_split;
-    if (!split && all.slots <= max_slots && all.quots <= 0xF0000000ull) { subs.push_back(all); return; }
-    if (split) {
-        max_slots /= 2;                                   // two lanes share the workspace budget
-        std::vector<SubBatch> h(P, SubBatch{0, 0, 0, 0, 0});
+}
+
+SubBatch sub_of_blocks(const BatchSummary& sum, size_t b0, size_t b1) {
+    SubBatch sb{(uint32_t)std::min<uint64_t>(sum.n_reads, (uint64_t)b0 * sum.block_reads),
+                (uint32_t)std::min<uint64_t>(sum.n_reads, (uint64_t)b1 * sum.block_reads), 0, 0, 0, (uint32_t)b0, (uint32_t)b1};
+    for (size_t k = b0; k < b1; ++k) { sb.slots += sum.blocks[k].slots; sb.quots += sum.blocks[k].quots; sb.max_pos = std::max(sb.max_pos, sum.blocks[k].max_pos); }
+    return sb;
+}
+
+// sub-batches over the blocks [first_block, end) appended to subs.  probe: the ratios behind max_slots are guesses (nothing has
+// run against this index yet) => a small first sub-batch, after which the caller plans the rest again
+void plan_sub_batches(mbl_ctx* c, const BatchSummary& sum, size_t first_block, uint64_t max_slots, bool probe, std::vector<SubBatch>& subs) {
+    const size_t nb = sum.blocks.size();
+    if (first_block >= nb) return;
+    const uint32_t n = sum.n_reads;
+    if (first_block == 0 && c->pipeline && n >= c->pipeline_min_reads && n >= 16) {
+        // large batches are cut in (at least) pipeline_parts pieces so that the two lanes overlap (mbl_classify_resident); each
+        // lane then owns half of the workspace budget
+        const unsigned P = (unsigned)std::max(2, c->pipeline_parts);
+        std::vector<SubBatch> h;
         bool fits = true;
-        for (unsigned t = 0; t < T; ++t) {
-            SubBatch& d = h[t / (T / P)];
-            if (d.r1 == d.r0) d.r0 = part[t].r0;
-            d.r1 = part[t].r1; d.slots += part[t].slots; d.quots += part[t].quots; d.max_pos = std::max(d.max_pos, part[t].max_pos);
+        for (unsigned p = 0; p < P; ++p) {
+            const size_t b0 = nb * p / P, b1 = nb * (p + 1) / P;
+            if (b1 == b0) continue;
+            h.push_back(sub_of_blocks(sum, b0, b1));
+            fits = fits && h.back().slots <= max_slots / 2 && h.back().quots <= 0xF0000000ull;
         }
-        for (const SubBatch& d : h) fits = fits && d.slots <= max_slots && d.quots <= 0xF0000000ull;
-        if (fits) {
-            for (const SubBatch& d : h) if (d.r1 > d.r0) subs.push_back(d);
-            return;
+        if (fits) { for (const SubBatch& d : h) subs.push_back(d); return; }
+        max_slots /= 2;
+    }
+    size_t b0 = first_block;
+    if (probe) {
+        const size_t pb = std::max<size_t>(1, (size_t)(262144 / sum.block_reads));
+        if (nb - first_block > 2 * pb) {
+            subs.push_back(sub_of_blocks(sum, first_block, first_block + pb));
+            b0 = first_block + pb;
         }
     }
-    SubBatch cur{0, 0, 0, 0, 0};
-    for (uint32_t r = 0; r < n; ++r) {
-        uint64_t s, q; uint32_t mp;
-        read_cost(r, s, q, mp);
-        if (cur.r1 > cur.r0 && (cur.slots + s > max_slots || cur.quots + q > 0xF0000000ull)) {
-            subs.push_back(cur);
-            cur = SubBatch{r, r, 0, 0, 0};
+    uint64_t slots = 0, quots = 0;
+    size_t start = b0;
+    for (size_t k = b0; k < nb; ++k) {
+        const ReadBlock& rb = sum.blocks[k];
+        if (k > start && (slots + rb.slots > max_slots || quots + rb.quots > 0xF0000000ull)) {
+            subs.push_back(sub_of_blocks(sum, start, k));
+            start = k; slots = 0; quots = 0;
         }
-        cur.r1 = r + 1; cur.slots += s; cur.quots += q;
-        cur.max_pos = std::max(cur.max_pos, mp);
+        slots += rb.slots; quots += rb.quots;
     }
-    if (cur.r1 > cur.r0) subs.push_back(cur);
+    subs.push_back(sub_of_blocks(sum, start, nb));
 }
 
 uint64_t slots_budget(mbl_ctx* c) {
@@ -911,7 +930,11 @@ int mbl_upload_batch(mbl_ctx* c, const mbl_batch* b) {
             MBL_CUDA(cudaMemcpyAsync(d2, b->bases2, nb2, cudaMemcpyHostToDevice, c->st));
             MBL_CUDA(cudaMemcpyAsync(c->off2.get<uint64_t>(n + 1), b->offsets2, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->st));
         }
-        plan_sub_batches(c, b, slots_budget(c), c->subs);    // host work overlaps the copies
+        summarize_reads(b, c->summary);                        // host work overlaps the copies
+        c->subs.clear();
+        c->probe_first = c->match_ratio == 0.0 && !c->no_probe;
+        plan_sub_batches(c, c->summary, 0, slots_budget(c), c->probe_first, c->subs);
+        c->probe_first = c->probe_first && c->subs.size() > 1;
         t.stop();
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
@@ -999,8 +1022,39 @@ int mbl_classify_resident(mbl_ctx* c) {
             });
         }
         int rc0 = MBL_OK;
-        if (!staggered) try {
-            for (size_t k = 0; k < c->subs.size(); k += two ? 2 : 1) {
+        if (!two) {
+            // one lane: sub-batches in order.  After a probe sub-batch the rest of the batch is planned again with the ratios
+            // it measured; a sub-batch that runs out of device memory all the same is halved (whole blocks) and redone
+            for (size_t k = 0; k < c->subs.size() && rc0 == MBL_OK; ++k) {
+                const uint64_t pairs_before = c->n_pairs;
+                const mbl_stats stats_before = c->stats;
+                try {
+                    rc0 = run_sub_batch(c, c->subs[k]);
+                } catch (const CudaError& e) {
+                    const SubBatch sb = c->subs[k];
+                    if (e.code != cudaErrorMemoryAllocation || sb.b1 - sb.b0 < 2) { rc0 = fail_cuda(c, e); break; }
+                    cudaGetLastError();
+                    MBL_CUDA(cudaStreamSynchronize(c->st));
+                    c->n_pairs = pairs_before;
+                    c->stats = stats_before;
+                    c->stats.overflow_retries += 1;
+                    for (Buf* b : {&c->arena, &c->m_raw, &c->cub_tmp}) b->release();     // regrown to what the halves need
+                    const uint32_t mid = sb.b0 + (sb.b1 - sb.b0) / 2;
+                    c->subs[k] = sub_of_blocks(c->summary, sb.b0, mid);
+                    c->subs.insert(c->subs.begin() + (ptrdiff_t)k + 1, sub_of_blocks(c->summary, mid, sb.b1));
+                    --k;
+                    continue;
+                }
+                if (rc0 == MBL_OK && k == 0 && c->probe_first) {
+                    const uint32_t next_block = c->subs[0].b1;
+                    c->subs.resize(1);
+                    plan_sub_batches(c, c->summary, next_block, slots_budget(c), false, c->subs);
+                    c->probe_first = false;
+                }
+            }
+            c->stats.sub_batches = (uint32_t)c->subs.size();
+        } else if (!staggered) try {
+            for (size_t k = 0; k < c->subs.size(); k += 2) {
                 const uint64_t off = c->n_pairs;
                 rc0 = run_sub_batch(c, c->subs[k]);
                 if (rc0 != MBL_OK) break;
@@ -1098,7 +1152,11 @@ int mbl_prefetch_batch(mbl_ctx* c, const mbl_batch* b) {
             MBL_CUDA(cudaMemcpyAsync(c->stage_off2.get<uint64_t>(n + 1), b->offsets2, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->copy_st));
         }
         MBL_CUDA(cudaEventRecord(c->copy_ev[1], c->copy_st));
-        plan_sub_batches(c, b, slots_budget(c), c->staged_subs);
+        summarize_reads(b, c->staged_summary);
+        c->staged_subs.clear();
+        c->staged_probe_first = c->match_ratio == 0.0 && !c->no_probe;
+        plan_sub_batches(c, c->staged_summary, 0, slots_budget(c), c->staged_probe_first, c->staged_subs);
+        c->staged_probe_first = c->staged_probe_first && c->staged_subs.size() > 1;
         c->staged = true;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
@@ -1119,6 +1177,8 @@ int mbl_classify_prefetched(mbl_ctx* c, const mbl_batch* next, mbl_read_result* 
         std::swap(c->bases1, c->stage_bases1); std::swap(c->bases2, c->stage_bases2);
         std::swap(c->off1, c->stage_off1); std::swap(c->off2, c->stage_off2);
         c->subs.swap(c->staged_subs);
+        std::swap(c->summary, c->staged_summary);
+        c->probe_first = c->staged_probe_first;
         c->n_reads = c->staged_reads; c->paired = c->staged_paired;
         c->staged = false;
         c->stats.ms[MBL_STAGE_H2D] = ms;
@@ -1166,8 +1226,10 @@ int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_
     c->stats.ms[MBL_STAGE_H2D] = 0;
     const int pipeline = c->pipeline;
     c->pipeline = 0;                                   // one sub-batch: the exchange works on whole batches
+    c->no_probe = true;
     int rc = mbl_upload_batch(c, b);
     c->pipeline = pipeline;
+    c->no_probe = false;
     if (rc != MBL_OK) return rc;
     if (c->subs.size() > 1) {
         size_t free_b = 0, total_b = 0;

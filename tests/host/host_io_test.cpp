@@ -20,6 +20,24 @@ long long hio_load(const char* path, unsigned threads) {
     if (!mblhost::load_fastx(path, g_reads, threads, &err)) { g_text = err; return -1; }
     return (long long)g_reads.size();
 }
+// the same file through the streaming reader in batches of batch_reads records and raw chunks of chunk_bytes, concatenated
+long long hio_load_stream(const char* path, unsigned threads, unsigned long long batch_reads, unsigned long long chunk_bytes) {
+    std::string err;
+    mblhost::FastxStream st;
+    if (!st.open(path, &err)) { g_text = err; return -1; }
+    g_reads = mblhost::ReadSet();
+    mblhost::ReadSet b;
+    while (true) {
+        if (!st.next(b, (size_t)batch_reads, threads, &err, (size_t)chunk_bytes)) { g_text = err; return -1; }
+        if (b.size() == 0) break;
+        if (b.size() > batch_reads) { g_text = "batch larger than requested"; return -1; }
+        const uint64_t base = g_reads.bases.size();
+        for (auto& n : b.names) g_reads.names.push_back(n);
+        g_reads.bases.insert(g_reads.bases.end(), b.bases.begin(), b.bases.end());
+        for (size_t k = 1; k < b.offsets.size(); ++k) g_reads.offsets.push_back(base + b.offsets[k]);
+    }
+    return (long long)g_reads.size();
+}
 unsigned long long hio_total_bases() { return g_reads.bases.size(); }
 void hio_copy(char* bases, unsigned long long* offsets) {
     if (!g_reads.bases.empty()) memcpy(bases, g_reads.bases.data(), g_reads.bases.size());

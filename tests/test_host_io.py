@@ -23,6 +23,8 @@ def hio():
     L = C.CDLL(OUT)
     L.hio_load.argtypes = [C.c_char_p, C.c_uint]
     L.hio_load.restype = C.c_longlong
+    L.hio_load_stream.argtypes = [C.c_char_p, C.c_uint, C.c_ulonglong, C.c_ulonglong]
+    L.hio_load_stream.restype = C.c_longlong
     L.hio_total_bases.restype = C.c_ulonglong
     L.hio_copy.argtypes = [C.c_void_p, C.c_void_p]
     L.hio_name.argtypes = [C.c_ulonglong]
@@ -79,10 +81,31 @@ def test_parallel_reader_matches_python_mirror(hio, tmp_path, fixtures_dir, thre
         assert np.array_equal(offs, wo) and np.array_equal(bases, wb), p
 
 
+@pytest.mark.parametrize("batch_reads,chunk_bytes", [(1000, 1 << 16), (7, 4096), (100000, 1 << 20), (5000, 300)])
+def test_streaming_reader_equals_whole_file_load(hio, tmp_path, fixtures_dir, batch_reads, chunk_bytes):
+    """FastxStream (bounded raw chunks cut at record starts, batches of at most N records, carry-over between chunks) must
+    deliver exactly the records of the whole-file reader, whatever the chunk and batch sizes — including chunks smaller than
+    one record and FASTQ quality lines that start with '@' or '+'."""
+    paths = _write_cases(tmp_path) + [os.path.join(fixtures_dir, "reads", "ERR9594652_5000_2.fq.gz")]
+    if chunk_bytes <= 4096:
+        paths = paths[:2] if batch_reads > 100 else paths[2:3] + paths[3:]
+    for p in paths:
+        want = _load(hio, p, 3)
+        n = hio.hio_load_stream(p.encode(), 3, batch_reads, chunk_bytes)
+        assert n == len(want[0]), hio.hio_text()
+        bases = np.zeros(hio.hio_total_bases(), dtype=np.uint8)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        hio.hio_copy(bases.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p))
+        assert [hio.hio_name(i).decode() for i in range(0, n, 997)] == want[0][::997]
+        assert np.array_equal(offs, want[2]) and np.array_equal(bases, want[1]), p
+
+
 def test_reader_rejects_empty_entries(hio, tmp_path):
     p = tmp_path / "bad.fna"
     p.write_bytes(b">a\nACGT\n>b\n>c\nAC\n")
     assert hio.hio_load(str(p).encode(), 1) == -1
+    assert b"2th entry has no sequence or name." in hio.hio_text()
+    assert hio.hio_load_stream(str(p).encode(), 1, 1, 8) == -1
     assert b"2th entry has no sequence or name." in hio.hio_text()
 
 

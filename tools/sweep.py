@@ -77,22 +77,30 @@ def main():
             clfs[mode] = Classifier(None, ClassifyOptions(seq_mode=mode, device=0), database=sdb.database)
         return clfs[mode]
 
+    # every read set is generated first (the generator works in multi-GB torch temporaries); the library's workspace then has
+    # the device to itself
+    cases = []
     for L in [int(x) for x in args.lens.split(",") if x]:
         n = max(1, int(args.gbp * 1e9 / L))
-        reads = synth.make_reads(sdb, n, L, seed=500 + L, random_frac=0.3, sub_rate=0.01 if L <= 500 else 0.05)
+        cases.append((L, synth.make_reads(sdb, n, L, seed=500 + L, random_frac=0.3, sub_rate=0.01 if L <= 500 else 0.05)))
         torch.cuda.empty_cache()
+    ont = None
+    if args.ont_reads > 0:
+        t0 = time.time()
+        ont = synth.make_long_reads(sdb, args.ont_reads, seed=900)
+        ont_gen_s = round(time.time() - t0, 1)
+    sdb.genomes = None
+    torch.cuda.empty_cache()
+    for L, reads in cases:
         r = run_case(clf_for(1 if L <= 500 else 3), reads, args.steps, args.warmup)
         r["read_len"] = L
         doc["sweep"].append(r)
         print(json.dumps(r), file=sys.stderr, flush=True)
-        del reads
-    if args.ont_reads > 0:
-        t0 = time.time()
-        reads = synth.make_long_reads(sdb, args.ont_reads, seed=900)
-        torch.cuda.empty_cache()
-        r = run_case(clf_for(3), reads, max(1, args.steps - 1), args.warmup)
+    del cases
+    if ont is not None:
+        r = run_case(clf_for(3), ont, max(1, args.steps - 1), args.warmup)
         r["read_len"] = "log-normal, mean %.0f bp (sigma 0.6, 200 bp - 30 kbp), 8 %% substitutions" % (r["bases"] / r["reads"])
-        r["reads_gen_s"] = round(time.time() - t0, 1)
+        r["reads_gen_s"] = ont_gen_s
         doc["ont"] = r
         print(json.dumps(r), file=sys.stderr, flush=True)
     for c in clfs.values():
