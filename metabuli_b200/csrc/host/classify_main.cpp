@@ -16,7 +16,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -162,6 +166,7 @@ struct Params {
     int seqMode = 2, threads = 0, accessionLevel = 0, minConsCnt = 4, minConsCntEuk = 9, matchPerKmer = 4, device = 0;
     float minScore = 0.f, minSpScore = 0.f, tieRatio = 0.95f;
     size_t batchReads = 0;
+    std::vector<int> devices;            // --gpus N (devices 0..N-1) or --devices a,b,c: one replica of the index per device
     std::vector<std::string> files;
 };
 
@@ -180,6 +185,8 @@ int classify(int argc, char** argv) {
         else if (a == "--accession-level") par.accessionLevel = atoi(val());
         else if (a == "--match-per-kmer") par.matchPerKmer = atoi(val());
         else if (a == "--device") par.device = atoi(val());
+        else if (a == "--gpus") { const int n = atoi(val()); if (n < 1 || n > 64) die("--gpus takes 1..64"); par.devices.clear(); for (int d = 0; d < n; ++d) par.devices.push_back(d); }
+        else if (a == "--devices") { par.devices.clear(); std::string v = val(); size_t p0 = 0; while (p0 <= v.size()) { size_t c = v.find(',', p0); if (c == std::string::npos) c = v.size(); if (c > p0) par.devices.push_back(atoi(v.substr(p0, c - p0).c_str())); p0 = c + 1; } if (par.devices.empty()) die("--devices takes a comma-separated list"); }
         else if (a == "--batch-reads") par.batchReads = (size_t)atoll(val());
         else if (a == "--lineage") par.lineage = atoi(val());
         // flags that change the reference's output and are not implemented here must fail, never be dropped silently:
@@ -244,57 +251,35 @@ int classify(int argc, char** argv) {
     std::vector<int32_t> info = slurp<int32_t>(dbDir + "/info");
     std::vector<uint64_t> split = slurp<uint64_t>(dbDir + "/split");
 
-    mbl_ctx* ctx = nullptr;
-    int rc = mbl_create(&cfg, &ctx);
-    if (rc != MBL_OK) die(rc == MBL_E_NO_DEVICE ? "no usable CUDA device (this build has no CPU fallback)" : "mbl_create failed");
+    // one context per device, each holding a replica of the index (the host arrays are shared)
+    if (par.devices.empty()) par.devices.push_back(par.device);
+    const size_t G = par.devices.size();
+    std::vector<mbl_ctx*> ctxs(G, nullptr);
     mbl_db db{diff.data(), diff.size(), info.data(), info.size(), split.data(), split.size() / 3};
     mbl_taxonomy tx{tax.maxNodes, tax.maxTaxID, tax.eukaryota, tax.D, tax.E, tax.L, tax.H, tax.M, tax.Mk,
                     tax.nodeTaxId.data(), tax.nodeParent.data(), tax.prune.data(), tax.rank.data(), t2s.data()};
-    rc = mbl_load_db(ctx, &db, &tx);
-    if (rc != MBL_OK) die(std::string("mbl_load_db: ") + mbl_last_error(ctx));
-
-    // reads: parsed by all host threads (fastx_tsv.hpp), kept in memory as the SoA the library takes
-    const unsigned T = par.threads > 0 ? (unsigned)par.threads : std::max(1u, std::thread::hardware_concurrency());
-    mblhost::ReadSet r1, r2;
-    std::string perr;
-    auto tl0 = std::chrono::steady_clock::now();
-    if (!mblhost::load_fastx(q1, r1, T, &perr)) die(perr);
-    if (par.seqMode == 2) {
-        if (!mblhost::load_fastx(q2, r2, T, &perr)) die(perr);
-        if (r1.size() != r2.size()) die("The number of reads in the two files are not equal.");
+    {
+        std::vector<std::thread> loaders;
+        std::vector<std::string> lerr(G);
+        for (size_t g = 0; g < G; ++g) loaders.emplace_back([&, g] {
+            mbl_config cg = cfg;
+            cg.device = par.devices[g];
+            int rc = mbl_create(&cg, &ctxs[g]);
+            if (rc != MBL_OK) { lerr[g] = rc == MBL_E_NO_DEVICE ? "no usable CUDA device " + std::to_string(cg.device) + " (this build has no CPU fallback)" : "mbl_create failed"; return; }
+            rc = mbl_load_db(ctxs[g], &db, &tx);
+            if (rc != MBL_OK) lerr[g] = std::string("mbl_load_db: ") + mbl_last_error(ctxs[g]);
+        });
+        for (auto& t : loaders) t.join();
+        for (size_t g = 0; g < G; ++g) if (!lerr[g].empty()) die(lerr[g]);
     }
-    const size_t total = r1.size();
-    printf("--------------------\nTotal read count : %zu\nTotal read length: %zunt\n--------------------\n", total,
-           r1.bases.size() + r2.bases.size());
-    printf("Reads loaded in %.3f s (%u threads)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tl0).count(), T);
-    if (!r1.bases.empty()) mbl_host_register(r1.bases.data(), r1.bases.size());
-    if (!r2.bases.empty()) mbl_host_register(r2.bases.data(), r2.bases.size());
 
+    const unsigned T = par.threads > 0 ? (unsigned)par.threads : std::max(1u, std::thread::hardware_concurrency());
     const std::string tsvPath = outDir + "/" + jobId + "_classifications.tsv";
     FILE* out = fopen(tsvPath.c_str(), "wb");
     if (!out) die("cannot write " + tsvPath);
     fputs(par.lineage ? "#is_classified\tname\ttaxID\tquery_length\tscore\trank\tlineage\ttaxID:match_count\n"
                       : "#is_classified\tname\ttaxID\tquery_length\tscore\trank\ttaxID:match_count\n", out);      // Reporter.cpp:37-41
 
-    // batches (the reference's QuerySplits, Classifier.cpp:81-140): batch i+1 is uploaded while batch i is classified
-    // (mbl_prefetch_batch / mbl_classify_prefetched) and batch i-1 is formatted and written by the host threads
-    const size_t step = par.batchReads ? par.batchReads : (size_t)8000000;
-    // inputs and outputs rotate separately: while batch i is on the GPU, the offsets of batch i+1 are being prepared / uploaded
-    // and the rows of batch i-1 are being formatted
-    struct In { std::vector<uint64_t> off1, off2; mbl_batch b{}; size_t r0 = 0, n = 0; } in[2];
-    struct Out { std::vector<mbl_read_result> res; std::vector<int32_t> pairs; size_t used = 0, r0 = 0, n = 0; } outb[2];
-    auto fill = [&](In& s, size_t r0) {
-        s.r0 = r0; s.n = std::min(step, total - r0);
-        auto rebase = [&](const mblhost::ReadSet& r, std::vector<uint64_t>& off) {
-            off.resize(s.n + 1);
-            const uint64_t base = r.offsets[r0];
-            for (size_t k = 0; k <= s.n; ++k) off[k] = r.offsets[r0 + k] - base;
-            return r.bases.data() + base;
-        };
-        s.b = mbl_batch{};
-        s.b.bases = rebase(r1, s.off1); s.b.offsets = s.off1.data(); s.b.n_reads = (uint32_t)s.n;
-        if (par.seqMode == 2) { s.b.bases2 = rebase(r2, s.off2); s.b.offsets2 = s.off2.data(); }
-    };
     struct TaxView {
         const TaxonomyHost& t;
         int32_t original(int32_t x) const { return t.original(x); }
@@ -307,58 +292,165 @@ int classify(int argc, char** argv) {
     mblhost::ArrayTax rt{tax.maxNodes, tax.maxTaxID, tax.nodeTaxId.data(), tax.nodeParent.data(), tax.D,
                          tax.internalIds ? tax.i2o : nullptr, nodeRankStr.data(), nodeNameStr.data()};
     std::vector<uint64_t> taxCounts((size_t)tax.maxTaxID + 1, 0);           // Classifier.cpp:196-203: ++taxCounts[classification]
+
+    // ---- the QuerySplit loop (Classifier.cpp:81-140) as a pipeline of batches --------------------------------------------
+    //   reader thread : FASTA/FASTQ(.gz) in bounded chunks -> batches of --batch-reads reads (mblhost::FastxStream)
+    //   device threads: one per context; batch i+1 of a device uploads while its batch i is classified
+    //                   (mbl_prefetch_batch / mbl_classify_prefetched)
+    //   writer thread : rows formatted by the host threads and written in batch order, taxon counts for the report
+    // Batch objects rotate through a free list, so their buffers (pinned once per growth) are reused and what is held in memory
+    // is bounded by the batches in flight, not by the size of the input (the reference bounds its splits by --max-ram).
+    struct Batch {
+        size_t index = 0;
+        mblhost::ReadSet r1, r2;
+        mbl_batch b{};
+        std::vector<mbl_read_result> res;
+        std::vector<int32_t> pairs;
+        size_t used = 0;
+        const void* pinned[2] = {nullptr, nullptr};
+        size_t pinned_cap[2] = {0, 0};
+    };
+    const size_t step = par.batchReads ? par.batchReads : (size_t)8000000;
+    const size_t n_batches_in_flight = 2 * G + 2;
+    std::vector<std::unique_ptr<Batch>> pool;
+    for (size_t i = 0; i < n_batches_in_flight; ++i) pool.emplace_back(new Batch());
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Batch*> free_list, ready;               // reader -> devices
+    std::map<size_t, Batch*> finished;                 // devices -> writer, by batch index
+    for (auto& p : pool) free_list.push_back(p.get());
+    bool reader_done = false, failed = false;
+    std::string fail_msg;
+    size_t n_batches = 0, total_reads = 0, total_bases = 0;
+    auto fail_with = [&](const std::string& m) { std::lock_guard<std::mutex> lk(mu); if (!failed) { failed = true; fail_msg = m; } cv.notify_all(); };
+    auto pin = [&](Batch* bt, int k, const std::vector<char>& v) {          // (re)register a batch buffer when it moved or grew
+        if (v.data() == bt->pinned[k] && v.capacity() == bt->pinned_cap[k]) return;
+        if (bt->pinned[k]) mbl_host_unregister(const_cast<void*>(bt->pinned[k]));
+        bt->pinned[k] = nullptr; bt->pinned_cap[k] = 0;
+        if (v.capacity() && mbl_host_register(const_cast<char*>(v.data()), v.capacity()) == MBL_OK) { bt->pinned[k] = v.data(); bt->pinned_cap[k] = v.capacity(); }
+    };
+    for (auto& p : pool) {
+        Batch* bt = p.get();
+        auto unpin = [bt](int k) { if (bt->pinned[k]) mbl_host_unregister(const_cast<void*>(bt->pinned[k])); bt->pinned[k] = nullptr; bt->pinned_cap[k] = 0; };
+        bt->r1.before_realloc = [unpin] { unpin(0); };
+        bt->r2.before_realloc = [unpin] { unpin(1); };
+    }
+    auto tl0 = std::chrono::steady_clock::now();
+
+    std::thread reader([&] {
+        mblhost::FastxStream s1, s2;
+        std::string err;
+        if (!s1.open(q1, &err) || (par.seqMode == 2 && !s2.open(q2, &err))) { fail_with(err); return; }
+        for (size_t index = 0;; ++index) {
+            Batch* bt = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || !free_list.empty(); });
+                if (failed) return;
+                bt = free_list.front(); free_list.pop_front();
+            }
+            if (!s1.next(bt->r1, step, T, &err)) { fail_with(err); return; }
+            if (par.seqMode == 2) {
+                if (!s2.next(bt->r2, step, T, &err)) { fail_with(err); return; }
+                if (bt->r1.size() != bt->r2.size()) { fail_with("The number of reads in the two files are not equal."); return; }
+            }
+            std::unique_lock<std::mutex> lk(mu);
+            if (bt->r1.size() == 0) { free_list.push_back(bt); n_batches = index; reader_done = true; cv.notify_all(); return; }
+            bt->index = index;
+            bt->b = mbl_batch{};
+            bt->b.bases = bt->r1.bases.data(); bt->b.offsets = bt->r1.offsets.data(); bt->b.n_reads = (uint32_t)bt->r1.size();
+            if (par.seqMode == 2) { bt->b.bases2 = bt->r2.bases.data(); bt->b.offsets2 = bt->r2.offsets.data(); }
+            total_reads += bt->r1.size(); total_bases += bt->r1.bases.size() + bt->r2.bases.size();
+            lk.unlock();
+            pin(bt, 0, bt->r1.bases);
+            if (par.seqMode == 2) pin(bt, 1, bt->r2.bases);
+            lk.lock();
+            ready.push_back(bt);
+            cv.notify_all();
+        }
+    });
+
     uint64_t kmers = 0, matches = 0;
     auto t0 = std::chrono::steady_clock::now();
-    std::thread writer;
-    if (total) {
-        fill(in[0], 0);
-        rc = mbl_prefetch_batch(ctx, &in[0].b);
-        if (rc != MBL_OK) die(std::string("mbl_prefetch_batch: ") + mbl_last_error(ctx));
-    }
-    int cur = 0;
-    for (size_t r0 = 0; r0 < total; r0 += step, cur ^= 1) {
-        In& s = in[cur];
-        Out& o = outb[cur];
-        const bool has_next = r0 + step < total;
-        if (has_next) fill(in[cur ^ 1], r0 + step);
-        o.r0 = s.r0; o.n = s.n;
-        o.res.assign(s.n, mbl_read_result{});
-        if (o.pairs.size() < 10 * s.n + 32) o.pairs.assign(10 * s.n + 32, 0);
-        rc = mbl_classify_prefetched(ctx, has_next ? &in[cur ^ 1].b : nullptr, o.res.data(), o.pairs.data(), o.pairs.size() / 2, &o.used);
-        if (rc == MBL_E_CAPACITY) {                       // the batch is classified and resident: only the download is repeated
-            o.pairs.assign(2 * (o.used + 16), 0);
-            rc = mbl_download_results(ctx, o.res.data(), o.pairs.data(), o.pairs.size() / 2, &o.used);
+    auto next_ready = [&]() -> Batch* {                                     // blocks; nullptr at the end of the input
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return failed || !ready.empty() || reader_done; });
+        if (failed || ready.empty()) return nullptr;
+        Batch* bt = ready.front(); ready.pop_front();
+        return bt;
+    };
+    std::vector<std::thread> workers;
+    for (size_t g = 0; g < G; ++g) workers.emplace_back([&, g] {
+        mbl_ctx* ctx = ctxs[g];
+        Batch* cur = next_ready();
+        if (cur && mbl_prefetch_batch(ctx, &cur->b) != MBL_OK) { fail_with(std::string("mbl_prefetch_batch: ") + mbl_last_error(ctx)); return; }
+        while (cur) {
+            Batch* nxt = next_ready();
+            const size_t n = cur->r1.size();
+            cur->res.assign(n, mbl_read_result{});
+            if (cur->pairs.size() < 10 * n + 32) cur->pairs.assign(10 * n + 32, 0);
+            int rc = mbl_classify_prefetched(ctx, nxt ? &nxt->b : nullptr, cur->res.data(), cur->pairs.data(), cur->pairs.size() / 2, &cur->used);
+            if (rc == MBL_E_CAPACITY) {                       // the batch is classified and resident: only the download is repeated
+                cur->pairs.assign(2 * (cur->used + 16), 0);
+                rc = mbl_download_results(ctx, cur->res.data(), cur->pairs.data(), cur->pairs.size() / 2, &cur->used);
+            }
+            if (rc != MBL_OK) { fail_with(std::string("mbl_classify_prefetched: ") + mbl_last_error(ctx)); return; }
+            mbl_stats st;
+            mbl_get_stats(ctx, &st);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                kmers += st.n_query_kmers; matches += st.n_matches;
+                finished[cur->index] = cur;
+            }
+            cv.notify_all();
+            cur = nxt;
         }
-        if (rc != MBL_OK) die(std::string("mbl_classify_prefetched: ") + mbl_last_error(ctx));
-        mbl_stats st;
-        mbl_get_stats(ctx, &st);
-        kmers += st.n_query_kmers; matches += st.n_matches;
-        if (writer.joinable()) writer.join();             // rows of batch i-1 are out before batch i+1 reuses that buffer
-        writer = std::thread([&, cur] {
-            const Out& w = outb[cur];
+    });
+
+    std::thread writer([&] {
+        size_t processed = 0;
+        for (size_t want = 0;; ++want) {
+            Batch* bt = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || finished.count(want) || (reader_done && want >= n_batches); });
+                if (failed || !finished.count(want)) return;
+                bt = finished[want]; finished.erase(want);
+            }
             std::vector<std::string> rows;
-            mblhost::format_rows(tv, r1.names, w.r0, w.n, w.res.data(), w.pairs.data(), T, rows, par.lineage != 0);
+            mblhost::format_rows(tv, bt->r1.names, 0, bt->r1.size(), bt->res.data(), bt->pairs.data(), T, rows, par.lineage != 0);
             for (const std::string& x : rows) fwrite(x.data(), 1, x.size(), out);
-            for (size_t i = 0; i < w.n; ++i) ++taxCounts[(size_t)w.res[i].classification];
-        });
-        printf("Processed read count   : %zu (%g)\n", r0 + s.n, (double)(r0 + s.n) / (double)total);
-    }
-    if (writer.joinable()) writer.join();
+            for (size_t i = 0; i < bt->r1.size(); ++i) ++taxCounts[(size_t)bt->res[i].classification];
+            processed += bt->r1.size();
+            printf("Processed read count   : %zu\n", processed);
+            std::lock_guard<std::mutex> lk(mu);
+            free_list.push_back(bt);
+            cv.notify_all();
+        }
+    });
+
+    reader.join();
+    for (auto& w : workers) w.join();
+    { std::lock_guard<std::mutex> lk(mu); reader_done = true; }
+    cv.notify_all();
+    writer.join();
+    if (failed) die(fail_msg);
     fclose(out);
+    printf("--------------------\nTotal read count : %zu\nTotal read length: %zunt\n--------------------\n", total_reads, total_bases);
     {                                                           // <jobid>_report.tsv (Reporter.cpp:19, :117-137)
         std::string report;
-        mblhost::write_report(rt, taxCounts, total, report);
+        mblhost::write_report(rt, taxCounts, total_reads, report);
         FILE* rf = fopen((outDir + "/" + jobId + "_report.tsv").c_str(), "wb");
         if (!rf) die("cannot write " + outDir + "/" + jobId + "_report.tsv");
         fwrite(report.data(), 1, report.size(), rf);
         fclose(rf);
     }
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    printf("Query k-mer number     : %llu\nTotal k-mer match count: %llu\nTaxonomic classification completed. (%.3f s)\n",
-           (unsigned long long)kmers, (unsigned long long)matches, sec);
-    if (!r1.bases.empty()) mbl_host_unregister(r1.bases.data());
-    if (!r2.bases.empty()) mbl_host_unregister(r2.bases.data());
-    mbl_destroy(ctx);
+    (void)tl0;
+    printf("Query k-mer number     : %llu\nTotal k-mer match count: %llu\nTaxonomic classification completed on %zu GPU(s). (%.3f s)\n",
+           (unsigned long long)kmers, (unsigned long long)matches, G, sec);
+    for (auto& p : pool) for (int k = 0; k < 2; ++k) if (p->pinned[k]) mbl_host_unregister(const_cast<void*>(p->pinned[k]));
+    for (mbl_ctx* c : ctxs) mbl_destroy(c);
     return 0;
 }
 
@@ -368,7 +460,7 @@ int main(int argc, char** argv) {
     if (argc < 2 || strcmp(argv[1], "classify") != 0) {
         fprintf(stderr, "usage: %s classify [--seq-mode 1|2|3] [--min-score F] [--min-sp-score F] [--tie-ratio F] [--min-cons-cnt N]\n"
                         "          [--min-cons-cnt-euk N] [--accession-level N] [--lineage 0|1] [--match-per-kmer N] [--device N]\n"
-                        "          [--batch-reads N] [--threads N]\n"
+                        "          [--gpus N | --devices a,b,...] [--batch-reads N] [--threads N]\n"
                         "          <fastx> [<fastx2>] <dbdir> <outdir> <jobid>\n", argv[0]);
         return 2;
     }

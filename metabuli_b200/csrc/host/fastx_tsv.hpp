@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -27,6 +28,7 @@ struct ReadSet {                       // SoA layout of mbl_batch + the names th
     std::vector<std::string> names;
     std::vector<char> bases;
     std::vector<uint64_t> offsets{0};
+    std::function<void()> before_realloc;   // called before `bases` moves to a larger block (the host unpins the old one)
     size_t size() const { return names.size(); }
 };
 
@@ -231,6 +233,11 @@ public:
             const uint64_t b0 = pend_.offsets[pos_], b1 = pend_.offsets[pos_ + n];
             out.names.reserve(n);
             for (size_t i = 0; i < n; ++i) out.names.emplace_back(std::move(pend_.names[pos_ + i]));
+            if (b1 - b0 > out.bases.capacity()) {             // grow with head room so that a steady stream of batches stops reallocating
+                if (out.before_realloc) out.before_realloc();
+                std::vector<char>().swap(out.bases);
+                out.bases.reserve((size_t)(b1 - b0) + (size_t)(b1 - b0) / 8 + 4096);
+            }
             out.bases.assign(pend_.bases.begin() + (ptrdiff_t)b0, pend_.bases.begin() + (ptrdiff_t)b1);
             out.offsets.reserve(n + 1);
             for (size_t i = 1; i <= n; ++i) out.offsets.push_back(pend_.offsets[pos_ + i] - b0);

@@ -115,3 +115,23 @@ def test_cpp_host_cli_writes_the_reference_tsv(db, mode, batch, ext, fixtures_di
     # the Kraken-style report (Reporter::writeReportFile)
     report = gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_report.tsv.gz"), "rb").read()
     assert open(tmp_path / "job_report.tsv", "rb").read() == report
+
+
+@pytest.mark.parametrize("devices,batch", [("0,0", 400), ("0,0,0", 333)])
+def test_cpp_host_multi_replica_keeps_the_read_order(devices, batch, fixtures_dir, golden_dir, tmp_path):
+    """`--gpus N` / `--devices a,b,...`: one replica of the index per device, the batches of the input go to whichever device is
+    free and the writer puts the rows back in input order.  Several contexts on device 0 exercise that host logic on a one-GPU
+    box; many small batches make the devices finish out of order."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "metabuli_b200", "_lib", "metabuli-b200")
+    reads = [os.path.join(fixtures_dir, "reads", f"ERR9594652_5000_{k}.fna.gz") for k in (1, 2)]
+    cmd = [exe, "classify", "--seq-mode", "2", "--threads", "3", "--devices", devices, "--batch-reads", str(batch)] + reads + \
+          [os.path.join(fixtures_dir, "db_in"), str(tmp_path), "job"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    golden = gzip.open(os.path.join(golden_dir, "ref_tsv", "in_pe_classifications.tsv.gz"), "rb").read()
+    assert open(tmp_path / "job_classifications.tsv", "rb").read() == golden
+    report = gzip.open(os.path.join(golden_dir, "ref_tsv", "in_pe_report.tsv.gz"), "rb").read()
+    assert open(tmp_path / "job_report.tsv", "rb").read() == report
+    assert "Total read count : 5000" in r.stdout and f"on {len(devices.split(','))} GPU(s)" in r.stdout
