@@ -10,18 +10,15 @@
 // a slice of its queries; the item carries the tile geometry, fetched into shared memory with cp.async one item ahead):
 //   1. stage   two 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) bring the tile's fragments and taxids
 //              into shared memory; the fragments of the next tile are requested as soon as this one is decoded;
-//   2. decode  all eight warps decode the tile together (delta_decode.cuh: one 16-byte octet per thread, shuffle scan
-//              of (count, sum), one barrier per 2048 fragments) into a value array; a second, k-mer-parallel pass
+//   2. decode  the warps that hold fragments decode the tile together (delta_decode.cuh: one 16-byte octet per thread,
+//              shuffle scan of (count, sum), one barrier per sweep) into a value array; a second, k-mer-parallel pass
 //              marks the first k-mer of every amino-acid group in a bitmap (one ballot per 32 k-mers) and enters it
 //              into a bucketed hash table keyed by the 40-bit amino-acid part;
-//   3. match   a warp looks up 32 queries per iteration (the next 32 are already in flight) and queues the hits;
-//              the slot index of a hit (payload of the K2 sort) is fetched straight into the queue record with
-//              cp.async.  32 queued hits are expanded into their (query, candidate) pairs, spread evenly over the lanes:
-//              sweep 1 finds every hit's minimum Hamming sum over an 8 KiB two-codon table while the hits' qinfo words
-//              are in flight (cp.async again), sweep 2 keeps the candidates with sum <= min(2*min, 7), assembles their
-//              Match rows in a per-warp staging buffer and writes them as contiguous 8-byte words (whole sectors).
+//   3. match   CTA-wide: probe (hit list + pair owners) -> pass 1 (Hamming sums, group minima) -> pass 2 (survivors,
+//              ballot-compacted, staged per warp, written as contiguous 8-byte words); see merge_kernel_v2 below.
 //              Output slots come from warp-private chunks of 1024 (one global atomic per chunk).
-// HBM traffic per launch = index once + 8 B per query + (4 B slot + 8 B qinfo, sector granular) per hit + 24 B per match.
+// HBM traffic per launch = index once + 16 B per query (value and qinfo, both sorted streams) + 24 B per match: ncu measures
+// 1.01x these algorithmic bytes (profiles/r02_v3_merge_ncu.md).
 #include "delta_decode.cuh"
 #include "kernels.cuh"
 
@@ -29,9 +26,8 @@ namespace mbl {
 
 namespace {
 
-// CTA shapes: 256 threads x 3 CTAs per SM (76 registers) or 512 threads x 2 CTAs per SM (64 registers, 32 warps per SM);
+// CTA shapes: 512 threads x 2 CTAs per SM (default) or 256 threads x up to 4 CTAs per SM, 64 registers either way;
 // MergeArgs::cta_threads selects one at launch
-constexpr uint32_t kQueue = 64;              // per-warp hit queue (power of two, >= 63)
 constexpr uint32_t kOutChunk = 1024;         // match slots a warp reserves from the global cursor at a time
 constexpr uint64_t kNone = ~0ull;
 constexpr uint32_t kFull = 0xffffffffu;
@@ -41,31 +37,6 @@ constexpr uint32_t kEmpty = 0xffffffffu;     // hash table: free slot
 // Bucket and tag come from disjoint bits of a multiplicative hash of the 40-bit amino-acid part; a tag match is
 // verified against the value array.
 __device__ __forceinline__ uint32_t aa_hash(uint64_t aa40) { return (uint32_t)((aa40 * 0x9E3779B97F4A7C15ull) >> 32); }
-
-// dynamic shared memory layout (sizes depend on the tile geometry chosen at load time)
-struct SmemLayout {
-    uint32_t off_rec, off_scan, off_ham, off_queue, off_own, off_qinfo, off_stage, off_bits, off_frag, off_info, off_vals, off_tab, total;
-};
-__host__ __device__ inline SmemLayout smem_layout(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets, uint32_t kWarps) {
-    SmemLayout l;
-    uint32_t o = 64;                                   // two mbarriers + two item slots
-    l.off_rec = o;    o += 2 * 64;                     // work item records: current / next
-    l.off_scan = o;   o += 2 * 2 * kWarps * 8;         // block_decode cross-warp scan
-    l.off_ham = o;    o += 8192;                       // two-codon table: sum | plain nibble | reversed nibble (u16)
-    l.off_queue = o;  o += kWarps * kQueue * 12;       // per-warp hit queues {group start, query dna, slot / query offset}
-    l.off_own = o;    o += kWarps * 32 * 4;            // per-warp, per-hit minimum Hamming sum of the current round
-    l.off_qinfo = o;  o += kWarps * 32 * 8;            // per-warp, per-hit qinfo word of the current round
-    l.off_stage = o;  o += kWarps * 32 * 24;           // per-warp staging of up to 32 Match rows
-    l.off_bits = o;   o += ((max_kmers + 63) / 32) * 4;   // bitmap: k-mer starts an amino-acid group
-    o = (o + 15) & ~15u;
-    l.off_frag = o;   o += (max_u16 + 16) * 2;         // fragment tile (the next tile streams in once this one is decoded)
-    l.off_info = o;   o += (max_kmers + 8) * 4;        // taxids of the current tile
-    o = (o + 15) & ~15u;
-    l.off_vals = o;   o += max_kmers * 8;
-    l.off_tab = o;    o += n_buckets * 4;              // hash table (n_buckets entries = n_buckets / 2 two-entry buckets)
-    l.total = (o + 15) & ~15u;
-    return l;
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -218,349 +189,11 @@ __global__ void merge_item_fill_kernel(const Tile* __restrict__ tiles, uint64_t 
     }
 }
 
-// ---- the merge kernel ------------------------------------------------------------------------------
-// v1 (MBL_MERGE_V1=1): warp-private hit queues + two pair sweeps per 32 hits.
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 3 : 2)
-merge_kernel(MergeArgs a) {
-    constexpr int kWarps = kThreads / 32;
-    extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout L = smem_layout(a.max_u16, a.max_kmers, a.n_buckets, kWarps);
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem);          // [0] fragments, [1] taxids
-    unsigned int* s_item = reinterpret_cast<unsigned int*>(smem + 32);                 // [2] claimed item numbers
-    unsigned int* s_chunk = reinterpret_cast<unsigned int*>(smem + 40);                // query chunk cursor of the current item
-    MergeItem* s_rec = reinterpret_cast<MergeItem*>(smem + L.off_rec);                 // [2] their records
-    uint64_t* s_scan = reinterpret_cast<uint64_t*>(smem + L.off_scan);
-    uint16_t* s_ham = reinterpret_cast<uint16_t*>(smem + L.off_ham);
-    uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + L.off_queue);
-    uint32_t* s_own = reinterpret_cast<uint32_t*>(smem + L.off_own);
-    uint64_t* s_qinfo = reinterpret_cast<uint64_t*>(smem + L.off_qinfo);
-    uint64_t* s_stage = reinterpret_cast<uint64_t*>(smem + L.off_stage);
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.off_bits);
-    uint16_t* s_frag = reinterpret_cast<uint16_t*>(smem + L.off_frag);
-    int32_t* s_info = reinterpret_cast<int32_t*>(smem + L.off_info);
-    uint64_t* s_vals = reinterpret_cast<uint64_t*>(smem + L.off_vals);
-    uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + L.off_tab);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 4096; i += kThreads) s_ham[i] = a.ham_pair[i];
-    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); }
-    unsigned parity_bits = 0u;                        // bit b = phase parity of mbarrier b
-    const uint32_t n_items_all = a.item_off[a.n_tiles];
-    const uint32_t n_items = (uint32_t)min((uint64_t)n_items_all, a.items_cap);
-    if (n_items_all > n_items && blockIdx.x == 0 && tid == 0) atomicOr(a.error_flag, 2u);   // work list too short: host retries
-    const bool fmt2 = a.kmer_format == 2;
-    const bool via_idx = a.q_idx != nullptr;
-    const uint32_t bucket_mask = a.n_buckets / 2 - 1;
-    const int hash_shift = 32 - (31 - __clz(a.n_buckets / 2));
-    uint32_t* my_queue = s_queue + warp * kQueue * 3;
-    uint32_t* my_own = s_own + warp * 32;
-    uint64_t* my_qinfo = s_qinfo + warp * 32;
-    uint64_t* my_stage = s_stage + warp * 96;
-    unsigned long long my_matches = 0;
-    OutChunk chunk;
-
-    // thread 0: start the TMA copy of a tile's fragments
-    auto stage_frag = [&](const MergeItem& r) {
-        if (r.jumbo_off != kNone) return;
-        const uint64_t d0 = r.diff_begin, d1 = r.diff_begin + r.n_u16;
-        const uint64_t a0 = d0 & ~7ull, a1 = (d1 + 7ull) & ~7ull;
-        fence_proxy_async();
-        mbar_expect_tx(mbar, (unsigned)((a1 - a0) * 2));
-        tma_load_1d(s_frag, a.diff + a0, (unsigned)((a1 - a0) * 2), mbar);
-    };
-
-    // prologue: claim two items; the first one's record is fetched synchronously
-    if (tid == 0) {
-        s_item[0] = atomicAdd(a.item_cursor, 1u);
-        s_item[1] = atomicAdd(a.item_cursor, 1u);
-        if (s_item[0] < n_items) { s_rec[0] = a.items[s_item[0]]; }
-    }
-    __syncthreads();
-    uint32_t item = s_item[0];
-    int slot = 0;
-    if (tid == 0 && item < n_items) stage_frag(s_rec[0]);
-    // every warp keeps its next 32 queries in flight
-    uint64_t qv_next = kBlank;
-    if (item < n_items) {
-        const uint64_t qi = s_rec[0].q_begin + (uint64_t)warp * 32 + lane;
-        if (qi < s_rec[0].q_end) qv_next = ld_stream_u64(a.q_value + qi);
-    }
-
-    while (item < n_items) {
-        const MergeItem it = s_rec[slot];
-        const uint32_t nk = it.n_kmers;
-        const uint32_t nw = (nk + 31) >> 5;
-        const bool jumbo = it.jumbo_off != kNone;
-        const uint32_t next_item = s_item[slot ^ 1];
-        const uint64_t* vals;
-        const int32_t* infos;
-        unsigned int pending = 0;
-        if (tid == 0) {
-            pending = atomicAdd(a.item_cursor, 1u);           // the item after next; published at the end of this one
-            *s_chunk = kWarps;                                // chunks 0..kWarps-1 are taken (one per warp)
-            if (!jumbo) {                                     // this tile's taxids (buffer idle since the last barrier)
-                const uint64_t i0 = it.info_begin & ~3ull, i1 = (it.info_begin + nk + 3ull) & ~3ull;
-                fence_proxy_async();
-                mbar_expect_tx(mbar + 1, (unsigned)((i1 - i0) * 4));
-                tma_load_1d(s_info, a.info + i0, (unsigned)((i1 - i0) * 4), mbar + 1);
-            }
-        }
-        if (warp == 1 && lane < 4 && next_item < n_items)     // next item's record, four 16-byte words
-            cp_async16(reinterpret_cast<unsigned char*>(s_rec + (slot ^ 1)) + 16 * lane,
-                       reinterpret_cast<const unsigned char*>(a.items + next_item) + 16 * lane);
-        if (!jumbo) {
-            for (uint32_t x = tid; x < a.n_buckets; x += kThreads) s_tab[x] = kEmpty;
-            // -- 1. the tile's fragments were requested one item ago
-            const uint64_t d0 = it.diff_begin, d1 = it.diff_begin + it.n_u16;
-            const uint64_t a0 = d0 & ~7ull;
-            mbar_wait(mbar, parity_bits & 1u);
-            parity_bits ^= 1u;
-            // -- 2. block-wide decode into the value array
-            uint64_t v = it.base_value, k = it.info_begin;
-            const uint64_t kb = it.info_begin;
-            block_decode<kThreads>(s_frag, (int)(d0 - a0), (int)(d0 - a0), (int)(d1 - a0), v, k, s_scan,
-                                   [&](uint64_t kk, uint64_t val, uint64_t) {
-                const uint64_t rel = kk - kb;
-                if (rel < nk) s_vals[rel] = val;
-            });
-            if (warp == 1 && lane < 4) cp_async_wait_all();
-            __syncthreads();
-            if (tid == 0 && next_item < n_items) stage_frag(s_rec[slot ^ 1]);      // streams in during the match phase
-            // -- 2b. amino-acid group starts: bitmap + hash table (the table was cleared before the decode barriers)
-            for (uint32_t base = (uint32_t)warp * 32; base < nw * 32; base += kThreads) {
-                const uint32_t rel = base + lane;
-                bool start = false;
-                uint64_t aa = 0;
-                if (rel < nk) {
-                    aa = s_vals[rel] >> 24;
-                    start = rel == 0 || (s_vals[rel - 1] >> 24) != aa;
-                }
-                const uint32_t b = __ballot_sync(kFull, start);
-                if (lane == 0) s_bits[base >> 5] = b;
-                if (start) {
-                    const uint32_t h = aa_hash(aa);
-                    const uint32_t entry = (rel << 19) | (h & 0x7FFFFu);
-                    uint32_t bs = 2u * (h >> hash_shift);
-                    while (true) {
-                        if (atomicCAS(&s_tab[bs], kEmpty, entry) == kEmpty) break;
-                        if (atomicCAS(&s_tab[bs + 1], kEmpty, entry) == kEmpty) break;
-                        bs = (bs + 2) & (2u * bucket_mask + 1u);
-                    }
-                }
-            }
-            mbar_wait(mbar + 1, (parity_bits >> 1) & 1u);
-            parity_bits ^= 2u;
-            __syncthreads();
-            vals = s_vals;
-            infos = s_info + (it.info_begin & 3ull);
-        } else {
-            if (warp == 1 && lane < 4) cp_async_wait_all();
-            __syncthreads();
-            if (tid == 0 && next_item < n_items) stage_frag(s_rec[slot ^ 1]);
-            vals = a.jumbo_vals + it.jumbo_off;
-            infos = a.info + it.info_begin;
-        }
-
-        // -- 3. stream the query slice.  A warp looks up 32 queries per iteration and appends the ones that found
-        //       their amino-acid group ("hits") to its private queue.  32 queued hits are expanded into their
-        //       (query, candidate) pairs, which are spread evenly over the lanes in batches of 32: sweep 1 finds every
-        //       hit's minimum Hamming sum, sweep 2 keeps the candidates with sum <= min(2*min, 7) (KmerMatcher.cpp:1117-
-        //       1146) and writes them, ballot-compacted, as coalesced 24-byte Match rows.
-        uint32_t q_head = 0, q_count = 0;
-        // ballot-compact the selected lanes' Match rows (Match.h:9-26 without the vptr) into the staging buffer and write them
-        // as contiguous 8-byte words; Q2: taxid 0 / unmapped species raise the error flag
-        auto emit = [&](bool sel, uint32_t o, uint32_t j, uint32_t oq, uint32_t td, uint32_t sum, const HamQuad& hq) {
-            const uint32_t bal = __ballot_sync(kFull, sel);
-            if (!bal) return;
-            const uint32_t cnt = __popc(bal);
-            const Reservation rs = reserve(chunk, cnt, a.out_count, lane);
-            if (sel) {
-                const uint64_t qinfo = my_qinfo[o];
-                const int32_t taxid = (int32_t)((uint32_t)infos[j] & a.info_mask);
-                const int32_t species = (taxid > 0 && taxid <= a.max_taxid) ? a.taxid2species[taxid] : 0;
-                if (taxid == 0 || species == 0) atomicOr(a.error_flag, 1u);
-                uint32_t field = 0u;
-                if (sum) field = ham_fields(hq, oq, td, !((qi_frame(qinfo) < 3) ^ fmt2));   // KmerMatcher.cpp:1140
-                uint64_t* w = my_stage + 3u * (uint32_t)__popc(bal & ((1u << lane) - 1));
-                w[0] = qinfo;
-                w[1] = (uint64_t)(uint32_t)taxid | ((uint64_t)(uint32_t)species << 32);
-                w[2] = (uint64_t)td | ((uint64_t)(field & 0xFFFFu) << 32) | ((uint64_t)(sum & 0xFFu) << 48);
-            }
-            __syncwarp();
-            if (cnt <= rs.rem) {                                                    // one contiguous run of slots (the usual case)
-                const uint64_t s0 = rs.old_base + rs.old_used;
-                if (s0 + cnt <= a.out_cap) {
-                    uint64_t* dst = reinterpret_cast<uint64_t*>(a.out + s0);
-                    const uint32_t nw3 = 3u * cnt;                                  // <= 96 words: three predicated copies
-                    if ((uint32_t)lane < nw3) dst[lane] = my_stage[lane];
-                    if ((uint32_t)lane + 32u < nw3) dst[lane + 32] = my_stage[lane + 32];
-                    if ((uint32_t)lane + 64u < nw3) dst[lane + 64] = my_stage[lane + 64];
-                }
-            } else {
-                for (uint32_t w = lane; w < 3u * cnt; w += 32) {
-                    const uint32_t r = w / 3u;
-                    const uint64_t sl = slot_of(rs, r);
-                    if (sl < a.out_cap) reinterpret_cast<uint64_t*>(a.out + sl)[w - 3u * r] = my_stage[w];
-                }
-            }
-            __syncwarp();
-            my_matches += cnt;
-        };
-        auto process_hits = [&](uint32_t m) {
-            const bool valid = (uint32_t)lane < m;
-            cp_async_wait_all();                                                    // slot indices of the queued hits
-            __syncwarp();
-            const uint32_t* rec = my_queue + 3u * ((q_head + lane) & (kQueue - 1));
-            const uint32_t g0 = valid ? rec[0] : 0u;                                // group start inside the tile
-            const uint32_t qd = valid ? rec[1] : 0u;                                // query DNA part
-            if (valid) cp_async8(my_qinfo + lane, a.q_info + (via_idx ? (uint64_t)rec[2] : it.q_begin + rec[2]));
-            q_head = (q_head + m) & (kQueue - 1);
-            q_count -= m;
-            // group size = distance to the next group start
-            uint32_t n = 0;
-            if (valid) {
-                if (!jumbo) {
-                    uint32_t w = (g0 + 1) >> 5;
-                    uint32_t bits = w < nw ? s_bits[w] & (0xffffffffu << ((g0 + 1) & 31)) : 0u;
-                    while (!bits && ++w < nw) bits = s_bits[w];
-                    const uint32_t nxt = bits ? (w << 5) + (uint32_t)__ffs(bits) - 1u : nk;
-                    n = min(nxt, nk) - g0;
-                } else {
-                    const uint64_t aa = vals[g0] >> 24;
-                    uint32_t j = g0 + 1;
-                    while (j < nk && (vals[j] >> 24) == aa) ++j;
-                    n = j - g0;
-                }
-            }
-            uint32_t incl = n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-            const uint32_t total = __shfl_sync(kFull, incl, 31);
-            const uint32_t excl = incl - n;
-            my_own[lane] = 255u;
-            __syncwarp();
-            // sweep 1: per-hit minimum (an identical DNA part is the only way to distance 0)
-            for (uint32_t pb = 0; pb < total; pb += 32) {
-                const uint32_t p = pb + lane;
-                const bool pv = p < total;
-                uint32_t o = 0;
-#pragma unroll
-                for (int st = 16; st > 0; st >>= 1) { const uint32_t t = __shfl_sync(kFull, incl, (o + st - 1) & 31); if (t <= p) o += st; }
-                o &= 31u;
-                const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
-                const uint32_t oq = __shfl_sync(kFull, qd, o);
-                if (pv) {
-                    const uint32_t td = (uint32_t)vals[j] & 0xFFFFFFu;
-                    const uint32_t sum = td == oq ? 0u : ham_sum(ham_lookup(s_ham, oq, td));
-                    atomicMin(&my_own[o], sum);
-                }
-            }
-            cp_async_wait_all();                                                    // qinfo words
-            __syncwarp();
-            // sweep 2: survivors
-            for (uint32_t pb = 0; pb < total; pb += 32) {
-                const uint32_t p = pb + lane;
-                const bool pv = p < total;
-                uint32_t o = 0;
-#pragma unroll
-                for (int st = 16; st > 0; st >>= 1) { const uint32_t t = __shfl_sync(kFull, incl, (o + st - 1) & 31); if (t <= p) o += st; }
-                o &= 31u;
-                const uint32_t j = __shfl_sync(kFull, g0, o) + (p - __shfl_sync(kFull, excl, o));
-                const uint32_t oq = __shfl_sync(kFull, qd, o);
-                uint32_t td = 0, sum = 255u;
-                HamQuad hq{0u, 0u, 0u, 0u};
-                if (pv) {
-                    td = (uint32_t)vals[j] & 0xFFFFFFu;
-                    if (td == oq) sum = 0u; else { hq = ham_lookup(s_ham, oq, td); sum = ham_sum(hq); }
-                }
-                emit(pv && sum <= min(my_own[o] * 2u, 7u), o, j, oq, td, sum, hq);      // KmerMatcher.cpp:1136
-            }
-        };
-
-        // 32-query chunks: the first round is fixed (chunk = warp, already in flight), later chunks are claimed from a
-        // shared counter so that no warp idles at the closing barrier for long
-        const uint32_t n_chunks = (uint32_t)((it.q_end - it.q_begin + 31) >> 5);
-        uint32_t ch = (uint32_t)warp;
-        while (ch < n_chunks) {
-            uint32_t ch_next = 0;
-            if (a.dyn_chunks) {
-                if (lane == 0) ch_next = atomicAdd(s_chunk, 1u);
-                ch_next = __shfl_sync(kFull, ch_next, 0);
-            } else {
-                ch_next = ch + kWarps;
-            }
-            const uint64_t qi = it.q_begin + (uint64_t)ch * 32 + lane;
-            const bool active = qi < it.q_end;
-            const uint64_t qv = qv_next;
-            {
-                const uint64_t nqi = it.q_begin + (uint64_t)ch_next * 32 + lane;
-                qv_next = (ch_next < n_chunks && nqi < it.q_end) ? ld_stream_u64(a.q_value + nqi) : kBlank;
-            }
-            ch = ch_next;
-            const uint64_t q40 = qv >> 24;
-            uint32_t g0 = 0;
-            bool hit = false;
-            if (!jumbo) {
-                if (active) {
-                    const uint32_t h = aa_hash(q40);
-                    const uint32_t tag = h & 0x7FFFFu;
-                    uint32_t bkt = h >> hash_shift;
-                    while (true) {
-                        const uint2 e = *reinterpret_cast<const uint2*>(s_tab + 2u * bkt);
-                        if (e.x == kEmpty) break;
-                        if ((e.x & 0x7FFFFu) == tag && (vals[e.x >> 19] >> 24) == q40) { g0 = e.x >> 19; hit = true; break; }
-                        if (e.y == kEmpty) break;
-                        if ((e.y & 0x7FFFFu) == tag && (vals[e.y >> 19] >> 24) == q40) { g0 = e.y >> 19; hit = true; break; }
-                        bkt = (bkt + 1) & bucket_mask;
-                    }
-                }
-            } else if (active) {
-                uint32_t lo = 0, hi = nk;
-                while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((vals[mid] >> 24) < q40) lo = mid + 1; else hi = mid; }
-                if (lo < nk && (vals[lo] >> 24) == q40) { g0 = lo; hit = true; }
-            }
-            const uint32_t bal = __ballot_sync(kFull, hit);
-            if (bal) {
-                if (hit) {
-                    uint32_t* rec = my_queue + 3u * ((q_head + q_count + __popc(bal & ((1u << lane) - 1))) & (kQueue - 1));
-                    rec[0] = g0; rec[1] = (uint32_t)qv & 0xFFFFFFu;
-                    if (via_idx) cp_async4(rec + 2, a.q_idx + qi); else rec[2] = (uint32_t)(qi - it.q_begin);
-                }
-                q_count += __popc(bal);
-                __syncwarp();
-                if (q_count >= 32) process_hits(32);
-            }
-        }
-        if (q_count) process_hits(q_count);
-        // first queries of the next item (its record arrived before the decode barrier)
-        if (next_item < n_items) {
-            const MergeItem* nr = s_rec + (slot ^ 1);
-            const uint64_t qi = nr->q_begin + (uint64_t)warp * 32 + lane;
-            qv_next = qi < nr->q_end ? ld_stream_u64(a.q_value + qi) : kBlank;
-        }
-        if (tid == 0) s_item[slot] = pending;
-        __syncthreads();
-        item = next_item;
-        slot ^= 1;
-    }
-    // blank out the unused tail of the warp's last chunk (seqID 0 == not a match)
-    if (chunk.used < kOutChunk) {
-        for (uint32_t w = chunk.used + lane; w < kOutChunk; w += 32) {
-            const uint64_t sl = chunk.base + w;
-            if (sl < a.out_cap) {
-                uint64_t* o = reinterpret_cast<uint64_t*>(a.out + sl);
-                o[0] = 0; o[1] = 0; o[2] = 0;
-            }
-        }
-    }
-    if (lane == 0 && my_matches) atomicAdd(a.out_count + 1, my_matches);
-}
-
-// ---- the merge kernel, v2 -------------------------------------------------------------------------------------------------
-// Same staging and decode as v1, but the match stage is balanced over the whole CTA instead of living in warp-private queues
-// (v1 left 17 % of the stall samples at the closing barrier of an item, waiting for the warp with the fullest queue, and paid
-// ~365 warp instructions per 32 (query, candidate) pairs for two shuffle-searched sweeps):
+// ---- the merge kernel ------------------------------------------------------------------------------------------------------
+// The match stage is balanced over the whole CTA.  (Round 1 kept hits in warp-private queues and found their pairs with
+// shuffle searches: 17 % of the stall samples sat at the closing barrier of an item, waiting for the warp with the fullest
+// queue, and 32 (query, candidate) pairs cost ~365 warp instructions in two sweeps; measured 48.9 ms against 38.0 ms for this
+// kernel on the benchmark, profiles/r02_v2_bench_*.json.)
 //   probe   a thread looks up one query per step; a hit appends {group start | length, pair offset, minimum | query DNA, qinfo}
 //           to a CTA-wide hit list (one shared-memory atomic per warp and step), its qinfo word is loaded right there (it travels
 //           through the K2 sort next to the value, so this is a coalesced stream and not a gather), and the hit's thread writes
@@ -977,16 +610,6 @@ void launch_merge_plan(const MergeArgs& a, cudaStream_t st) {
 }
 
 template <int kThreads>
-static void launch_merge_v1(const MergeArgs& a, int sm_count, cudaStream_t st) {
-    const size_t smem = smem_layout(a.max_u16, a.max_kmers, a.n_buckets, kThreads / 32).total;
-    // set on every launch (microseconds): two pipeline lanes may launch from two host threads
-    MBL_CUDA(cudaFuncSetAttribute(merge_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    MBL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel<kThreads>, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    merge_kernel<kThreads><<<(unsigned)(sm_count * per_sm), kThreads, smem, st>>>(a);
-}
-template <int kThreads>
 static void launch_merge_v2(const MergeArgs& a, int sm_count, cudaStream_t st) {
     const size_t smem = smem_layout2(a.max_u16, a.max_kmers, a.n_buckets, kThreads).total;
     MBL_CUDA(cudaFuncSetAttribute(merge_kernel_v2<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -997,11 +620,6 @@ static void launch_merge_v2(const MergeArgs& a, int sm_count, cudaStream_t st) {
 }
 
 void launch_merge(const MergeArgs& a, int sm_count, cudaStream_t st) {
-    if (a.version == 1) {                             // needs q_idx (qinfo gathered through the sort permutation) or sorted qinfo alike
-        if (a.cta_threads == 512) launch_merge_v1<512>(a, sm_count, st);
-        else launch_merge_v1<256>(a, sm_count, st);
-        return;
-    }
     if (a.cta_threads == 256) launch_merge_v2<256>(a, sm_count, st);
     else launch_merge_v2<512>(a, sm_count, st);
 }

@@ -103,7 +103,7 @@ struct MergeArgs {
     const uint64_t* jumbo_vals;
     const uint64_t* q_value;        // sorted by amino-acid part
     const uint64_t* q_info;
-    const uint32_t* q_idx;          // optional: q_info is indexed through q_idx[sorted position] (unsorted qinfo array)
+    const uint32_t* q_idx;          // optional (index-sharded mode): q_info is indexed through q_idx[sorted position]
     uint64_t n_query;               // non-blank
     const int32_t* taxid2species;
     int32_t max_taxid;
@@ -118,9 +118,7 @@ struct MergeArgs {
     // work list
     uint64_t* q_lo;                 // [2 * (n_tiles + 1)]: per tile first query / one past the last query of its prefix range
     int prefix_shift;               // queries are ordered by value >> prefix_shift only
-    int dyn_chunks;                 // 1: warps claim 32-query chunks from a shared counter, 0: fixed striding
-    int cta_threads;                // 256 (3 CTAs per SM) or 512 (2 CTAs per SM)
-    int version;                    // 2 (default): CTA-wide balanced match stage; 1 (MBL_MERGE_V1=1): warp-private queues + pair sweeps
+    int cta_threads;                // 512 (2 CTAs per SM, default) or 256 (up to 4 CTAs per SM)
     uint32_t* item_cnt;             // [n_tiles + 1]
     uint32_t* item_off;             // [n_tiles + 1]
     MergeItem* items;

@@ -54,12 +54,10 @@ struct mbl_ctx {
     uint16_t* d_ham_pair = nullptr;
     uint8_t* d_ham_single = nullptr;
     uint32_t tile_cells = 2;            // MBL_TILE_CELLS (measured best on the 8 GiB benchmark index: 3 CTAs per SM)
-    int dyn_chunks = 0;                 // MBL_DYN_CHUNKS (measured: no gain over fixed striding)
     int filter_minimizer = 1;           // MBL_FILTER_MINIMIZER=0: filter line from the whole amino-acid part instead of its minimizer
     int filter_bits = 16;               // MBL_FILTER_BITS: bits per index k-mer of the amino-acid presence filter, 0 = no filter
     uint64_t arena_S8 = 0;              // slot stride of the phase-1 arena layout (set by whoever fills it)
-    int merge_version = 2;              // MBL_MERGE_V1=1: the round-1 match stage (warp-private hit queues, two pair sweeps)
-    int merge_threads = 0;              // MBL_MERGE_THREADS: 256 or 512 threads per merge CTA (default: 512 for v2, 256 for v1)
+    int merge_threads = 512;            // MBL_MERGE_THREADS: 512 (2 CTAs per SM) or 256 (up to 4 CTAs per SM) threads per merge CTA
     bool no_probe = false;              // the index-sharded phases work on whole batches: no probe sub-batch
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // test hooks: force the capacity guesses low so that the retry paths run on small inputs (tests/test_gpu_edge_paths.py)
@@ -408,9 +406,7 @@ int stage_sort_merge(mbl_ctx* c, uint64_t S, uint64_t cap_basis, double* ratio, 
     ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
     ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
     ma.prefix_shift = c->dir.sort_begin_bit;
-    ma.dyn_chunks = c->dyn_chunks;
-    ma.version = c->merge_version;
-    ma.cta_threads = c->merge_threads ? c->merge_threads : (c->merge_version == 1 ? 256 : 512);
+    ma.cta_threads = c->merge_threads;
     ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
     ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
     ma.items_cap = c->dir.n_tiles + n_query / kItemQueries + 2;
@@ -662,7 +658,6 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         c->d_codon = upload(c, t.codon, 512);
         c->d_ham_pair = upload(c, t.ham_pair, 4096);
         c->d_ham_single = upload(c, t.ham_sum, 64);
-        if (const char* e = getenv("MBL_DYN_CHUNKS")) c->dyn_chunks = atoi(e) != 0;
         if (const char* e = getenv("MBL_PIPELINE")) { int v = atoi(e); c->pipeline = v < 0 ? 0 : (v > 2 ? 2 : v); }
         if (const char* e = getenv("MBL_PIPELINE_PARTS")) { int v = atoi(e); if (v >= 2 && v <= 16) c->pipeline_parts = v; }
         // L2 fetch granularity on a DRAM miss (32, 64 or 128 bytes; the default fetches 128): the presence-filter probes of K1 and
@@ -673,7 +668,6 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         }
         if (const char* e = getenv("MBL_FILTER_MINIMIZER")) c->filter_minimizer = atoi(e) != 0;
         if (const char* e = getenv("MBL_FILTER_BITS")) { int v = atoi(e); if (v >= 0 && v <= 64) c->filter_bits = v; }
-        if (const char* e = getenv("MBL_MERGE_V1")) c->merge_version = atoi(e) != 0 ? 1 : 2;
         if (const char* e = getenv("MBL_MERGE_THREADS")) { int v = atoi(e); if (v == 256 || v == 512) c->merge_threads = v; }
         if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }
         if (const char* e = getenv("MBL_TEST_MATCH_CAP")) c->test_match_cap = strtoull(e, nullptr, 10);
@@ -725,7 +719,7 @@ mbl_ctx* ensure_shadow(mbl_ctx* c) {
     }
     mbl_ctx* s = c->shadow;
     s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
-    s->tile_cells = c->tile_cells; s->dyn_chunks = c->dyn_chunks; s->merge_threads = c->merge_threads; s->merge_version = c->merge_version; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
+    s->tile_cells = c->tile_cells; s->merge_threads = c->merge_threads; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
     s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
     s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded; s->filter_complete = c->filter_complete;
     s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed
@@ -1638,9 +1632,7 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
         ma.error_flag = reinterpret_cast<unsigned int*>(counters + 3);
         ma.item_cursor = reinterpret_cast<unsigned int*>(counters + 3) + 1;
         ma.q_lo = c->q_lo.get<uint64_t>(2 * c->dir.n_tiles + 2);
-        ma.dyn_chunks = c->dyn_chunks;
-        ma.version = c->merge_version;
-        ma.cta_threads = c->merge_threads ? c->merge_threads : (c->merge_version == 1 ? 256 : 512);
+        ma.cta_threads = c->merge_threads;
         ma.prefix_shift = 24;                // the stage API takes fully ordered queries; any coarser grouping is valid too
         ma.item_cnt = c->item_cnt.get<uint32_t>(c->dir.n_tiles + 2);
         ma.item_off = c->item_off.get<uint32_t>(c->dir.n_tiles + 2);
