@@ -153,7 +153,8 @@ __global__ void match_gather_fix_kernel(const mbl_match_rec* __restrict__ in, co
 // sort: three 8-bit radix passes over (32-bit seqID, 32-bit row index) instead of six over (64-bit key, index).  The rest of the
 // order is local to a read's ~100 rows: one warp per read gathers the rows through the permutation (the one random read of the
 // rows that any ordering needs), keeps a 64-bit (species | frame | pos | hamming | dna) key per row in shared memory, ranks every
-// row by counting the keys that order before it, and writes the rows to their final places.
+// row, orders the keys with a bitonic network in shared memory (a rank-by-counting version cost n^2 / 32 steps per read and was
+// slower than the six radix passes it replaced), and writes the rows to their final places.
 constexpr int kOrderWarps = 8;
 constexpr uint32_t kOrderMaxRows = 1024;        // rows of one read that fit a warp's key buffer; longer segments => single-key path
 
@@ -188,6 +189,7 @@ match_order_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restr
     extern __shared__ __align__(16) uint64_t order_keys[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t* keys = order_keys + (size_t)warp * kOrderMaxRows;
+    uint16_t* ord = reinterpret_cast<uint16_t*>(order_keys + (size_t)kOrderWarps * kOrderMaxRows) + (size_t)warp * kOrderMaxRows;
     for (uint32_t r = blockIdx.x * kOrderWarps + warp; r < n_reads; r += gridDim.x * kOrderWarps) {
         const uint64_t b = seg_begin[r];
         const uint32_t n = (uint32_t)(seg_end[r] - b);
@@ -196,29 +198,42 @@ match_order_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restr
             if (lane < 3) reinterpret_cast<uint64_t*>(out + b)[lane] = reinterpret_cast<const uint64_t*>(in + idx[b])[lane];
             continue;
         }
-        for (uint32_t j = lane; j < n; j += 32) {
-            const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + j]);
-            const uint64_t q = s[0], w1 = s[1], w2 = s[2];       // qinfo | target, species | dna, field, hamming
-            uint64_t k = w1 >> 32;                                // species
-            k = (k << 3) | (q >> 61);                             // frame
-            k = (k << pos_bits) | (q & 0xFFFFFFFFull);            // pos
-            k = (k << 3) | ((w2 >> 48) & 7ull);                   // hamming (<= 7 by construction, KmerMatcher.cpp:1136)
-            k = (k << 24) | (w2 & 0xFFFFFFull);                   // dna
+        // keys (and the local row numbers that travel with them) into shared memory, padded to a power of two with +infinity
+        const uint32_t n_pad = n <= 2 ? 2u : 1u << (32 - __clz(n - 1));
+        for (uint32_t j = lane; j < n_pad; j += 32) {
+            uint64_t k = ~0ull;
+            if (j < n) {
+                const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + j]);
+                const uint64_t q = s[0], w1 = s[1], w2 = s[2];   // qinfo | target, species | dna, field, hamming
+                k = w1 >> 32;                                     // species
+                k = (k << 3) | (q >> 61);                         // frame
+                k = (k << pos_bits) | (q & 0xFFFFFFFFull);        // pos
+                k = (k << 3) | ((w2 >> 48) & 7ull);               // hamming (<= 7 by construction, KmerMatcher.cpp:1136)
+                k = (k << 24) | (w2 & 0xFFFFFFull);               // dna
+            }
             keys[j] = k;
+            ord[j] = (uint16_t)j;
         }
         __syncwarp();
-        for (uint32_t j = lane; j < n; j += 32) {
-            const uint64_t k = keys[j];
-            uint32_t rank = 0;
-            uint32_t q = 0;
-            for (; q + 2 <= n; q += 2) {                          // two keys per 16-byte broadcast load
-                const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(keys + q);
-                rank += (y.x < k || (y.x == k && q < j)) ? 1u : 0u;
-                rank += (y.y < k || (y.y == k && q + 1 < j)) ? 1u : 0u;
+        // bitonic network over shared memory: n_pad / 2 compare-exchanges per step, spread over the lanes
+        for (uint32_t k = 2; k <= n_pad; k <<= 1) {
+            for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
+                for (uint32_t t = lane; t < (n_pad >> 1); t += 32) {
+                    const uint32_t i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+                    const uint32_t l = i | jj;
+                    const uint64_t x = keys[i], y = keys[l];
+                    if ((x > y) == ((i & k) == 0)) {
+                        keys[i] = y; keys[l] = x;
+                        const uint16_t oi = ord[i]; ord[i] = ord[l]; ord[l] = oi;
+                    }
+                }
+                __syncwarp();
             }
-            if (q < n) { const uint64_t y = keys[q]; rank += (y < k || (y == k && q < j)) ? 1u : 0u; }
-            const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + j]);
-            uint64_t* d = reinterpret_cast<uint64_t*>(out + b + rank);
+        }
+        // equal keys cannot occur (one index entry per (value, species)), so the order is total: row ord[p] goes to place p
+        for (uint32_t p = lane; p < n; p += 32) {
+            const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + ord[p]]);
+            uint64_t* d = reinterpret_cast<uint64_t*>(out + b + p);
             const uint64_t a0 = s[0], a1 = s[1], a2 = s[2];
             d[0] = a0; d[1] = a1; d[2] = a2;
         }
@@ -320,7 +335,7 @@ bool sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
         MBL_CUDA(cudaStreamSynchronize(st));
         if (h_cnt[1] <= kOrderMaxRows) {
             if (h_cnt[0]) MBL_CUDA(cudaMemsetAsync(out, 0, sizeof(mbl_match_rec) * (size_t)h_cnt[0], st));   // blank rows (seqID 0) come first
-            const size_t smem = (size_t)kOrderWarps * kOrderMaxRows * 8;
+            const size_t smem = (size_t)kOrderWarps * kOrderMaxRows * (8 + 2);
             static bool attr_set = false;
             if (!attr_set) { MBL_CUDA(cudaFuncSetAttribute(match_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
             const unsigned ob = (unsigned)std::min<uint64_t>((n_reads + kOrderWarps - 1) / kOrderWarps, 148ull * 12);
