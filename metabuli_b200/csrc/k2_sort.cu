@@ -156,7 +156,8 @@ __global__ void match_gather_fix_kernel(const mbl_match_rec* __restrict__ in, co
 // row, orders the keys with a bitonic network in shared memory (a rank-by-counting version cost n^2 / 32 steps per read and was
 // slower than the six radix passes it replaced), and writes the rows to their final places.
 constexpr int kOrderWarps = 8;
-constexpr uint32_t kOrderMaxRows = 1024;        // rows of one read that fit a warp's key buffer; longer segments => single-key path
+constexpr uint32_t kOrderSmallRows = 256;       // two launches: reads of up to 256 rows (2.5 KB of shared memory per warp, full occupancy:
+constexpr uint32_t kOrderMaxRows = 2048;        // the gather is latency-bound) and the few with up to 2048; longer segments => single-key path
 
 __global__ void match_seqkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,17 +184,19 @@ __global__ void seg_maxlen_kernel(const uint64_t* __restrict__ seg_begin, const 
     for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
     if ((threadIdx.x & 31) == 0 && len) atomicMax(max_len, len);
 }
+// reads with kMinRows < rows <= kMaxRows
+template <uint32_t kMinRows, uint32_t kMaxRows>
 __global__ void __launch_bounds__(kOrderWarps * 32)
 match_order_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ seg_begin,
                    const uint64_t* __restrict__ seg_end, uint32_t n_reads, int pos_bits, mbl_match_rec* __restrict__ out) {
     extern __shared__ __align__(16) uint64_t order_keys[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t* keys = order_keys + (size_t)warp * kOrderMaxRows;
-    uint16_t* ord = reinterpret_cast<uint16_t*>(order_keys + (size_t)kOrderWarps * kOrderMaxRows) + (size_t)warp * kOrderMaxRows;
+    uint64_t* keys = order_keys + (size_t)warp * kMaxRows;
+    uint16_t* ord = reinterpret_cast<uint16_t*>(order_keys + (size_t)kOrderWarps * kMaxRows) + (size_t)warp * kMaxRows;
     for (uint32_t r = blockIdx.x * kOrderWarps + warp; r < n_reads; r += gridDim.x * kOrderWarps) {
         const uint64_t b = seg_begin[r];
         const uint32_t n = (uint32_t)(seg_end[r] - b);
-        if (n == 0) continue;
+        if (n <= kMinRows || n > kMaxRows) continue;
         if (n == 1) {
             if (lane < 3) reinterpret_cast<uint64_t*>(out + b)[lane] = reinterpret_cast<const uint64_t*>(in + idx[b])[lane];
             continue;
@@ -335,11 +338,17 @@ bool sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
         MBL_CUDA(cudaStreamSynchronize(st));
         if (h_cnt[1] <= kOrderMaxRows) {
             if (h_cnt[0]) MBL_CUDA(cudaMemsetAsync(out, 0, sizeof(mbl_match_rec) * (size_t)h_cnt[0], st));   // blank rows (seqID 0) come first
-            const size_t smem = (size_t)kOrderWarps * kOrderMaxRows * (8 + 2);
+            const size_t smem_small = (size_t)kOrderWarps * kOrderSmallRows * (8 + 2), smem_big = (size_t)kOrderWarps * kOrderMaxRows * (8 + 2);
             static bool attr_set = false;
-            if (!attr_set) { MBL_CUDA(cudaFuncSetAttribute(match_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-            const unsigned ob = (unsigned)std::min<uint64_t>((n_reads + kOrderWarps - 1) / kOrderWarps, 148ull * 12);
-            match_order_kernel<<<ob, kOrderWarps * 32, smem, st>>>(in, v.Current(), seg_begin, seg_end, n_reads, pos_bits, out);
+            if (!attr_set) {
+                MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<kOrderSmallRows, kOrderMaxRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+                attr_set = true;
+            }
+            const unsigned ob = (unsigned)std::min<uint64_t>((n_reads + kOrderWarps - 1) / kOrderWarps, 148ull * 32);
+            match_order_kernel<0, kOrderSmallRows><<<ob, kOrderWarps * 32, smem_small, st>>>(in, v.Current(), seg_begin, seg_end, n_reads, pos_bits, out);
+            if (h_cnt[1] > kOrderSmallRows)
+                match_order_kernel<kOrderSmallRows, kOrderMaxRows><<<148 * 2, kOrderWarps * 32, smem_big, st>>>(in, v.Current(), seg_begin, seg_end, n_reads,
+                                                                                                                pos_bits, out);
             return true;
         }
         // a read with more rows than a warp orders in shared memory (long reads): the single-key path below redoes the order
