@@ -8,8 +8,10 @@
 //                    bits the batch actually uses (48 for 150-bp reads), then the short runs that share that
 //                    key are ordered by (hamming, dna) in place — together the reference's total order.
 //                    Batches whose packed key would not fit 64 bits fall back to two stable LSD passes.
-#include <algorithm>
-#include <cstdlib>
+//                    (Round 2 tried a two-level order — three radix passes over (32-bit seqID, index) and a warp per read that
+//                    orders its ~150 rows in shared memory while gathering them: bit-identical, but 99-106 ms against 74.6 ms
+//                    for this single-key path on the benchmark, as a rank-by-counting and as a bitonic network alike: a
+//                    256-key network costs ~3 k warp instructions per read, more than the three 8-byte radix passes it saves.)
 #include <cub/cub.cuh>
 
 #include "kernels.cuh"
@@ -148,102 +150,6 @@ __global__ void match_gather_fix_kernel(const mbl_match_rec* __restrict__ in, co
         copy(idx[r], i + rank);
     }
 }
-// ---- two-level ordering (the default for short-read batches) -----------------------------------------------------------------
-// compareMatches (KmerMatcher.cpp:1149-1166) orders by (seqID, species, frame, pos, hamming, dna).  Only the seqID needs a global
-// sort: three 8-bit radix passes over (32-bit seqID, 32-bit row index) instead of six over (64-bit key, index).  The rest of the
-// order is local to a read's ~100 rows: one warp per read gathers the rows through the permutation (the one random read of the
-// rows that any ordering needs), keeps a 64-bit (species | frame | pos | hamming | dna) key per row in shared memory, ranks every
-// row, orders the keys with a bitonic network in shared memory (a rank-by-counting version cost n^2 / 32 steps per read and was
-// slower than the six radix passes it replaced), and writes the rows to their final places.
-constexpr int kOrderWarps = 8;
-constexpr uint32_t kOrderSmallRows = 256;       // two launches: reads of up to 256 rows (2.5 KB of shared memory per warp, full occupancy:
-constexpr uint32_t kOrderMaxRows = 2048;        // the gather is latency-bound) and the few with up to 2048; longer segments => single-key path
-
-__global__ void match_seqkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    key[i] = qi_seq(m[i].qinfo);
-    idx[i] = (uint32_t)i;
-}
-// per-read segments from the sorted seqIDs; blank rows (seqID 0) sort first, n_blank[0] = their count
-__global__ void seq_segments_kernel(const uint32_t* __restrict__ key, size_t n, uint32_t n_reads, uint64_t* __restrict__ seg_begin,
-                                    uint64_t* __restrict__ seg_end, unsigned long long* __restrict__ n_blank) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t s = key[i];
-    const uint32_t sp = i > 0 ? key[i - 1] : ~s, sn = i + 1 < n ? key[i + 1] : ~s;
-    if (s == 0) { if (sn != 0) *n_blank = i + 1; return; }
-    if (s > n_reads) return;
-    if (sp != s) seg_begin[s - 1] = i;
-    if (sn != s) seg_end[s - 1] = i + 1;
-}
-__global__ void seg_maxlen_kernel(const uint64_t* __restrict__ seg_begin, const uint64_t* __restrict__ seg_end, uint32_t n_reads,
-                                  unsigned long long* __restrict__ max_len) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long len = r < n_reads ? seg_end[r] - seg_begin[r] : 0ull;
-    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
-    if ((threadIdx.x & 31) == 0 && len) atomicMax(max_len, len);
-}
-// reads with kMinRows < rows <= kMaxRows
-template <uint32_t kMinRows, uint32_t kMaxRows>
-__global__ void __launch_bounds__(kOrderWarps * 32)
-match_order_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ seg_begin,
-                   const uint64_t* __restrict__ seg_end, uint32_t n_reads, int pos_bits, mbl_match_rec* __restrict__ out) {
-    extern __shared__ __align__(16) uint64_t order_keys[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t* keys = order_keys + (size_t)warp * kMaxRows;
-    uint16_t* ord = reinterpret_cast<uint16_t*>(order_keys + (size_t)kOrderWarps * kMaxRows) + (size_t)warp * kMaxRows;
-    for (uint32_t r = blockIdx.x * kOrderWarps + warp; r < n_reads; r += gridDim.x * kOrderWarps) {
-        const uint64_t b = seg_begin[r];
-        const uint32_t n = (uint32_t)(seg_end[r] - b);
-        if (n <= kMinRows || n > kMaxRows) continue;
-        if (n == 1) {
-            if (lane < 3) reinterpret_cast<uint64_t*>(out + b)[lane] = reinterpret_cast<const uint64_t*>(in + idx[b])[lane];
-            continue;
-        }
-        // keys (and the local row numbers that travel with them) into shared memory, padded to a power of two with +infinity
-        const uint32_t n_pad = n <= 2 ? 2u : 1u << (32 - __clz(n - 1));
-        for (uint32_t j = lane; j < n_pad; j += 32) {
-            uint64_t k = ~0ull;
-            if (j < n) {
-                const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + j]);
-                const uint64_t q = s[0], w1 = s[1], w2 = s[2];   // qinfo | target, species | dna, field, hamming
-                k = w1 >> 32;                                     // species
-                k = (k << 3) | (q >> 61);                         // frame
-                k = (k << pos_bits) | (q & 0xFFFFFFFFull);        // pos
-                k = (k << 3) | ((w2 >> 48) & 7ull);               // hamming (<= 7 by construction, KmerMatcher.cpp:1136)
-                k = (k << 24) | (w2 & 0xFFFFFFull);               // dna
-            }
-            keys[j] = k;
-            ord[j] = (uint16_t)j;
-        }
-        __syncwarp();
-        // bitonic network over shared memory: n_pad / 2 compare-exchanges per step, spread over the lanes
-        for (uint32_t k = 2; k <= n_pad; k <<= 1) {
-            for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
-                for (uint32_t t = lane; t < (n_pad >> 1); t += 32) {
-                    const uint32_t i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
-                    const uint32_t l = i | jj;
-                    const uint64_t x = keys[i], y = keys[l];
-                    if ((x > y) == ((i & k) == 0)) {
-                        keys[i] = y; keys[l] = x;
-                        const uint16_t oi = ord[i]; ord[i] = ord[l]; ord[l] = oi;
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        // equal keys cannot occur (one index entry per (value, species)), so the order is total: row ord[p] goes to place p
-        for (uint32_t p = lane; p < n; p += 32) {
-            const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + ord[p]]);
-            uint64_t* d = reinterpret_cast<uint64_t*>(out + b + p);
-            const uint64_t a0 = s[0], a1 = s[1], a2 = s[2];
-            d[0] = a0; d[1] = a1; d[2] = a2;
-        }
-        __syncwarp();
-    }
-}
-
 // seg_begin/seg_end per read from the sorted match list (Classifier.cpp:174-185 MatchBlocks)
 __global__ void segment_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t n_reads, uint64_t* __restrict__ seg_begin,
                                uint64_t* __restrict__ seg_end) {
@@ -320,39 +226,6 @@ bool sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
     const int seq_bits = bits_for(n_reads);
     const uint32_t pos_div = codon_spaced ? 3u : 1u;     // true for matches produced by K3 (see match_fullkey_kernel)
     const int pos3_bits = bits_for(max_pos / pos_div);
-    static const bool force_fullkey = getenv("MBL_SORT_FULLKEY") && atoi(getenv("MBL_SORT_FULLKEY")) != 0;   // tests: the single-key path
-    if (seg_begin && seg_end && !force_fullkey && sp_bits + pos_bits + 30 <= 64) {
-        // two-level: global sort by seqID, then per-read ordering fused into the gather
-        uint32_t *k32a = reinterpret_cast<uint32_t*>(key_a), *k32b = reinterpret_cast<uint32_t*>(key_b);
-        match_seqkey_kernel<<<blocks, 256, 0, st>>>(in, n, k32a, idx_a);
-        cub::DoubleBuffer<uint32_t> k(k32a, k32b), v(idx_a, idx_b);
-        MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, seq_bits, st));
-        MBL_CUDA(cudaMemsetAsync(seg_begin, 0, 8 * (size_t)n_reads, st));
-        MBL_CUDA(cudaMemsetAsync(seg_end, 0, 8 * (size_t)n_reads, st));
-        unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(tmp);      // the sort is done with its scratch
-        MBL_CUDA(cudaMemsetAsync(d_cnt, 0, 16, st));
-        seq_segments_kernel<<<blocks, 256, 0, st>>>(k.Current(), n, n_reads, seg_begin, seg_end, d_cnt);
-        seg_maxlen_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(seg_begin, seg_end, n_reads, d_cnt + 1);
-        unsigned long long h_cnt[2] = {0, 0};
-        MBL_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
-        MBL_CUDA(cudaStreamSynchronize(st));
-        if (h_cnt[1] <= kOrderMaxRows) {
-            if (h_cnt[0]) MBL_CUDA(cudaMemsetAsync(out, 0, sizeof(mbl_match_rec) * (size_t)h_cnt[0], st));   // blank rows (seqID 0) come first
-            const size_t smem_small = (size_t)kOrderWarps * kOrderSmallRows * (8 + 2), smem_big = (size_t)kOrderWarps * kOrderMaxRows * (8 + 2);
-            static bool attr_set = false;
-            if (!attr_set) {
-                MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<kOrderSmallRows, kOrderMaxRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
-                attr_set = true;
-            }
-            const unsigned ob = (unsigned)std::min<uint64_t>((n_reads + kOrderWarps - 1) / kOrderWarps, 148ull * 32);
-            match_order_kernel<0, kOrderSmallRows><<<ob, kOrderWarps * 32, smem_small, st>>>(in, v.Current(), seg_begin, seg_end, n_reads, pos_bits, out);
-            if (h_cnt[1] > kOrderSmallRows)
-                match_order_kernel<kOrderSmallRows, kOrderMaxRows><<<148 * 2, kOrderWarps * 32, smem_big, st>>>(in, v.Current(), seg_begin, seg_end, n_reads,
-                                                                                                                pos_bits, out);
-            return true;
-        }
-        // a read with more rows than a warp orders in shared memory (long reads): the single-key path below redoes the order
-    }
     if (seq_bits + sp_bits + 3 + pos3_bits <= 64) {
         match_fullkey_kernel<<<blocks, 256, 0, st>>>(in, n, sp_bits, pos3_bits, pos_div, key_a, idx_a);
         cub::DoubleBuffer<uint64_t> k(key_a, key_b);
