@@ -40,7 +40,6 @@ struct ScoreParams {
     int min_cons_cnt, min_cons_cnt_euk, accession_level, denominator, kmer_format;
     int max_codon_shift, dna_shift;   // Taxonomer.cpp:34-42: 1 / 3, or (8 - s) / 3 (8 - s) for syncmer databases
     int force_scratch_dp;      // tests only: skip the register-resident DP fast path
-    int prefetch_rows;         // rows ahead of the current one that a task asks L2 for (MBL_SCORE_PREFETCH, 0 = off)
 };
 
 // K1

@@ -57,7 +57,6 @@ struct mbl_ctx {
     int filter_minimizer = 1;           // MBL_FILTER_MINIMIZER=0: filter line from the whole amino-acid part instead of its minimizer
     int filter_bits = 16;               // MBL_FILTER_BITS: bits per index k-mer of the amino-acid presence filter, 0 = no filter
     uint64_t arena_S8 = 0;              // slot stride of the phase-1 arena layout (set by whoever fills it)
-    int score_prefetch = 8;             // MBL_SCORE_PREFETCH: rows a scoring task prefetches ahead (0 = off)
     int merge_threads = 512;            // MBL_MERGE_THREADS: 512 (2 CTAs per SM) or 256 (up to 4 CTAs per SM) threads per merge CTA
     bool no_probe = false;              // the index-sharded phases work on whole batches: no probe sub-batch
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
@@ -503,7 +502,6 @@ int stage_sort_score(mbl_ctx* c, const SubBatch& sb, uint64_t M) {
         sa.par.kmer_format = c->cfg.kmer_format;
         sa.par.max_codon_shift = c->cfg.syncmer ? 8 - c->cfg.smer_len : 1;               // Taxonomer.cpp:34-42
         sa.par.dna_shift = 3 * sa.par.max_codon_shift;
-        sa.par.prefetch_rows = c->score_prefetch;
         sa.q_tax = c->q_tax.get<int32_t>(sb.quots + 1); sa.q_ham = c->q_ham.get<uint8_t>(sb.quots + 1); sa.q_has = c->q_has.get<uint8_t>(sb.quots + 1);
         sa.taxcnt_pairs = c->pairs_raw.get<int32_t>(2 * (sb.quots + 1));
         sa.results = c->res_sub.get<mbl_read_result>(n);
@@ -671,7 +669,6 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         }
         if (const char* e = getenv("MBL_FILTER_MINIMIZER")) c->filter_minimizer = atoi(e) != 0;
         if (const char* e = getenv("MBL_FILTER_BITS")) { int v = atoi(e); if (v >= 0 && v <= 64) c->filter_bits = v; }
-        if (const char* e = getenv("MBL_SCORE_PREFETCH")) { int v = atoi(e); if (v >= 0 && v <= 64) c->score_prefetch = v; }
         if (const char* e = getenv("MBL_MERGE_THREADS")) { int v = atoi(e); if (v == 256 || v == 512) c->merge_threads = v; }
         if (const char* e = getenv("MBL_PIPELINE_MIN_READS")) { long v = atol(e); if (v > 0) c->pipeline_min_reads = (uint32_t)v; }
         if (const char* e = getenv("MBL_TEST_MATCH_CAP")) c->test_match_cap = strtoull(e, nullptr, 10);
@@ -723,7 +720,7 @@ mbl_ctx* ensure_shadow(mbl_ctx* c) {
     }
     mbl_ctx* s = c->shadow;
     s->d_base_code = c->d_base_code; s->d_codon = c->d_codon; s->d_ham_pair = c->d_ham_pair; s->d_ham_single = c->d_ham_single;
-    s->tile_cells = c->tile_cells; s->merge_threads = c->merge_threads; s->score_prefetch = c->score_prefetch; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
+    s->tile_cells = c->tile_cells; s->merge_threads = c->merge_threads; s->filter_bits = c->filter_bits; s->filter_minimizer = c->filter_minimizer;
     s->d_diff = c->d_diff; s->d_info = c->d_info; s->n_u16 = c->n_u16; s->n_kmers = c->n_kmers;
     s->dir = c->dir; s->tax = c->tax; s->db_loaded = c->db_loaded; s->filter_complete = c->filter_complete;
     s->bases1 = c->bases1; s->bases2 = c->bases2; s->off1 = c->off1; s->off2 = c->off2; s->results = c->results;   // borrowed

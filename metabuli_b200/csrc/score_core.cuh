@@ -120,16 +120,6 @@ MBL_HD void stl_sort(int32_t* a, int n, Less less) {
     }
 }
 
-// rows of a task are consecutive in the sorted match list; asking L2 for the row `ahead` rows further on while the current one is
-// processed takes most DRAM misses off a thread's dependent chain (one 128-byte line holds 5 rows).  No-op on the host.
-MBL_HD void prefetch_row(const mbl_match_rec* m, uint64_t i, uint64_t end, int ahead) {
-#ifdef __CUDA_ARCH__
-    if (ahead > 0 && i + (uint64_t)ahead < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(m + i + ahead));
-#else
-    (void)m; (void)i; (void)end; (void)ahead;
-#endif
-}
-
 // ---- taxonomy primitives -----------------------------------------------------------------------------
 MBL_HD bool tax_exists(const DeviceTaxonomy& t, int32_t id) { return id >= 0 && id <= t.max_taxid && t.D[id] != -1; }
 MBL_HD int tax_lca_nodes(const DeviceTaxonomy& t, int i, int j) {          // NcbiTaxonomy::lcaHelper (Q5)
@@ -197,7 +187,6 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
     DpCell bufA[kDpWidth], bufB[kDpWidth];
     int ncur = 0, nnxt = 0;
     auto load = [&](DpCell& c, uint64_t i) {
-        prefetch_row(ml, i, ge, a.par.prefetch_rows);
         c.score = match_score(ml[i].right_end_hamming);
         c.start = (int32_t)qi_pos(ml[i].qinfo);
         c.ham = ml[i].hamming; c.depth = 1; c.smatch = (uint32_t)(i - gs); c.idx = (uint32_t)(i - gs);
@@ -568,7 +557,6 @@ MBL_HD void score_read(const ScoreArgs& a, uint32_t r) {
     const uint32_t q0 = a.quot_off[r], nq = a.quot_off[r + 1] - q0;
     for (uint32_t k = 0; k < nq; ++k) a.q_has[q0 + k] = 0;
     for (uint64_t k = bestS; k < bestE; ++k) {
-        prefetch_row(ml, k, bestE, a.par.prefetch_rows);
         const uint32_t quo = qi_pos(ml[k].qinfo) / (uint32_t)a.par.dna_shift;      // Taxonomer.cpp:217 (dnaShift: 3, or 3 (8 - s) with syncmers)
         if (quo >= nq) continue;
         const uint8_t h = ml[k].hamming;
