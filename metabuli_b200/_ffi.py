@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libmetabuli_b200.so")
+LIB_PATH = os.environ.get("MBL_LIB_PATH") or os.path.join(_HERE, "_lib", "libmetabuli_b200.so")   # MBL_LIB_PATH: development builds side by side
 
 MBL_OK = 0
 MBL_E_MATCH_OVERFLOW = 1

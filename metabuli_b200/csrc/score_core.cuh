@@ -175,70 +175,91 @@ MBL_HD int left_part_ham(uint32_t reh, int range) { int s = 0; for (int i = 0; i
 // matches (the common case: one or two target k-mers per query position and species) the state of the
 // "current" and "next" position lives in registers and nothing but the emitted paths touches HBM.
 // Groups with a wider position fall back to the scratch-array version below (same arithmetic, same order).
-constexpr int kDpWidth = 4;
+constexpr int kDpWidth = 2;
 
-struct DpCell { float score; int32_t start, ham, depth; uint32_t smatch, idx, dna; bool conn; };
+// Every array below is indexed by unrolled compile-time constants only, so the DP state really stays in registers (a version that
+// appended with buf[n++] and swapped two buffers through pointers compiled to a 256-byte stack frame: every cell access was a
+// local-memory load on the thread's dependent chain), and a row is fetched as three 8-byte words two rows ahead of its use.
+struct DpCell { float score; int32_t start, ham, depth; uint32_t smatch, idx, dna, reh; bool conn; };   // (all cells of a buffer share the position)
+struct Row3 { uint64_t w0, w1, w2; };                // qinfo | target, species | dna, right_end_hamming, hamming
+MBL_HD Row3 load_row(const mbl_match_rec* ml, uint64_t i) {
+    const uint64_t* s = reinterpret_cast<const uint64_t*>(ml + i);
+    return Row3{s[0], s[1], s[2]};
+}
+MBL_HD void dp_put(DpCell (&buf)[kDpWidth], int at, const DpCell& x) {
+#pragma unroll
+    for (int k = 0; k < kDpWidth; ++k) if (k == at) buf[k] = x;
+}
 
 MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge, int min_depth, uint64_t pbase, uint32_t& np) {
     const mbl_match_rec* ml = a.matches;
     const uint32_t np_in = np;                       // a position wider than kDpWidth: undo and let the caller fall back
-    const bool forward = qi_frame(ml[gs].qinfo) < 3;
     const bool fmt2 = a.par.kmer_format == 2;
-    DpCell bufA[kDpWidth], bufB[kDpWidth];
+    DpCell cur[kDpWidth], nxt[kDpWidth];
     int ncur = 0, nnxt = 0;
-    auto load = [&](DpCell& c, uint64_t i) {
-        c.score = match_score(ml[i].right_end_hamming);
-        c.start = (int32_t)qi_pos(ml[i].qinfo);
-        c.ham = ml[i].hamming; c.depth = 1; c.smatch = (uint32_t)(i - gs); c.idx = (uint32_t)(i - gs);
-        c.dna = ml[i].dna_encoding; c.conn = false;
+    uint64_t i = gs;
+    Row3 r0 = load_row(ml, gs);
+    Row3 r1 = gs + 1 < ge ? load_row(ml, gs + 1) : r0;
+    const bool forward = (uint32_t)(r0.w0 >> 61) < 3;
+    auto advance = [&]() {                           // row i consumed: r0 becomes row i + 1, row i + 2 is requested
+        ++i;
+        r0 = r1;
+        if (i + 1 < ge) r1 = load_row(ml, i + 1);
     };
-    auto push = [&](const DpCell& c) {
+    auto cell = [&]() {                              // a fresh path that starts (and ends) at row i
+        DpCell c;
+        c.reh = (uint32_t)(r0.w2 >> 32) & 0xFFFFu;
+        c.score = match_score(c.reh);
+        c.start = (int32_t)(uint32_t)r0.w0;
+        c.ham = (int32_t)((r0.w2 >> 48) & 0xFFu); c.depth = 1; c.smatch = (uint32_t)(i - gs); c.idx = (uint32_t)(i - gs);
+        c.dna = (uint32_t)r0.w2; c.conn = false;
+        return c;
+    };
+    auto push = [&](const DpCell& c, uint64_t pos) {
         const uint64_t o = pbase + np++;
-        const uint64_t i = gs + c.idx;
         a.p_start[o] = c.start;
-        a.p_end[o] = (int32_t)qi_pos(ml[i].qinfo) + 23;
+        a.p_end[o] = (int32_t)pos + 23;
         a.p_score[o] = c.score; a.p_ham[o] = c.ham; a.p_depth[o] = c.depth;
         a.p_smatch[o] = (uint32_t)(gs + c.smatch);                // absolute match indices
-        a.p_ematch[o] = (uint32_t)i;
+        a.p_ematch[o] = (uint32_t)(gs + c.idx);
     };
-    uint64_t i = gs;
-    uint64_t curPos = qi_pos(ml[gs].qinfo);
+    uint64_t curPos = (uint32_t)r0.w0;
     bool wide = false;                               // keep going on overflow (results are discarded), no extra control flow
-    while (i < ge && qi_pos(ml[i].qinfo) == curPos) {
-        if (ncur < kDpWidth) load(bufA[ncur++], i); else wide = true;
-        ++i;
+    while (i < ge && (uint32_t)r0.w0 == curPos) {
+        if (ncur < kDpWidth) { dp_put(cur, ncur, cell()); ++ncur; } else wide = true;
+        advance();
     }
-    // one DP step: `cur` holds the paths ending at curPos, `nxt` receives those ending at the next position
-    auto step = [&](DpCell* cur, DpCell* nxt) {
-        const uint32_t nextPos = qi_pos(ml[i].qinfo);
+    while (i < ge) {
+        // one DP step: `cur` holds the paths ending at curPos, `nxt` receives those ending at the next position
+        const uint32_t nextPos = (uint32_t)r0.w0;
         nnxt = 0;
-        while (i < ge && qi_pos(ml[i].qinfo) == nextPos) {
-            if (nnxt < kDpWidth) load(nxt[nnxt++], i); else wide = true;
-            ++i;
+        while (i < ge && (uint32_t)r0.w0 == nextPos) {
+            if (nnxt < kDpWidth) { dp_put(nxt, nnxt, cell()); ++nnxt; } else wide = true;
+            advance();
         }
         const int shift = (int)(((uint64_t)nextPos - curPos) / 3);
         if (shift > 0 && shift <= a.par.max_codon_shift) {              // maxCodonShift: 1, or 8 - s with syncmers (Taxonomer.cpp:34-42)
             const uint32_t lowMask = (1u << (24 - 3 * shift)) - 1;
 #pragma unroll
             for (int nx = 0; nx < kDpWidth; ++nx) {
-                if (nx >= nnxt) break;
-                const uint32_t reh = ml[gs + nxt[nx].idx].right_end_hamming;
-                int h = 0;                                               // calHammingDistIncrement / calScoreIncrement (:650-669)
-                float inc = 0.f;
-                for (int sft = 0; sft < shift; ++sft) { const int d = (reh >> (2 * sft)) & 3; h += d; inc += codon_score(d); }
-                int best = -1;
-                float bestScore = 0.f;
+                if (nx < nnxt) {
+                    const uint32_t reh = nxt[nx].reh;
+                    int h = 0;                                           // calHammingDistIncrement / calScoreIncrement (:650-669)
+                    float inc = 0.f;
+                    for (int sft = 0; sft < shift; ++sft) { const int d = (reh >> (2 * sft)) & 3; h += d; inc += codon_score(d); }
+                    int best = -1;
+                    float bestScore = 0.f;
 #pragma unroll
-                for (int cu = 0; cu < kDpWidth; ++cu) {
-                    if (cu >= ncur) break;
-                    const uint32_t m1 = forward ? cur[cu].dna : nxt[nx].dna, m2 = forward ? nxt[nx].dna : cur[cu].dna;
-                    const bool cons = fmt2 ? ((m1 & lowMask) == (m2 >> (3 * shift))) : ((m1 >> (3 * shift)) == (m2 & lowMask));
-                    if (cons) {
-                        cur[cu].conn = true;
-                        if (cur[cu].score > bestScore) { best = cu; bestScore = cur[cu].score; }
+                    for (int cu = 0; cu < kDpWidth; ++cu) {
+                        if (cu < ncur) {
+                            const uint32_t m1 = forward ? cur[cu].dna : nxt[nx].dna, m2 = forward ? nxt[nx].dna : cur[cu].dna;
+                            const bool cons = fmt2 ? ((m1 & lowMask) == (m2 >> (3 * shift))) : ((m1 >> (3 * shift)) == (m2 & lowMask));
+                            if (cons) {
+                                cur[cu].conn = true;
+                                if (cur[cu].score > bestScore) { best = cu; bestScore = cur[cu].score; }
+                            }
+                        }
                     }
-                }
-                if (best >= 0) {
 #pragma unroll
                     for (int cu = 0; cu < kDpWidth; ++cu)
                         if (cu == best) {
@@ -250,19 +271,16 @@ MBL_HD bool score_frame_group_fast(const ScoreArgs& a, uint64_t gs, uint64_t ge,
         }
 #pragma unroll
         for (int cu = 0; cu < kDpWidth; ++cu)
-            if (cu < ncur && !cur[cu].conn && cur[cu].depth >= min_depth) push(cur[cu]);
+            if (cu < ncur && !cur[cu].conn && cur[cu].depth >= min_depth) push(cur[cu], curPos);
         if (i == ge) {
 #pragma unroll
             for (int nx = 0; nx < kDpWidth; ++nx)
-                if (nx < nnxt && nxt[nx].depth >= min_depth) push(nxt[nx]);
+                if (nx < nnxt && nxt[nx].depth >= min_depth) push(nxt[nx], nextPos);
         }
+#pragma unroll
+        for (int k = 0; k < kDpWidth; ++k) cur[k] = nxt[k];
         ncur = nnxt;
         curPos = nextPos;
-    };
-    while (i < ge) {
-        step(bufA, bufB);
-        if (i >= ge) break;
-        step(bufB, bufA);
     }
     if (wide) { np = np_in; return false; }
     return true;
