@@ -358,7 +358,10 @@ def sharded_leg(args, rank, local_rank, world, dist):
         classified, recv_k, n_m = 0, 0, 0
         d2h = 0
         for sl in slices:
+            tc0 = time.perf_counter()
             res, pairs = sharded.classify_index_sharded(sc, ex, *sl, timings=tm if timed else None, transport=args.transport)
+            if timed:
+                tm["s_whole_call"] = tm.get("s_whole_call", 0.0) + time.perf_counter() - tc0
             classified += int(res["is_classified"].sum())
             d2h += int(res.nbytes + pairs.nbytes)
             st = sc.clf.stats()

@@ -4,7 +4,7 @@ set -u
 N=${1:-2}; STEPS=${2:-3}; WARM=${3:-2}; shift 3 || true
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-nvidia-smi topo -m > gpurun_out/r02_topo_n$N.txt 2>&1
+nvidia-smi topo -m > gpurun_out/r02_topo_n$N.txt 2>&1; nvidia-smi nvlink -gt d -i 0 > gpurun_out/r02_nvlink_raw_n$N.txt 2>&1
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps $STEPS --warmup $WARM "$@" \
    > gpurun_out/r02_bench_n$N.out 2> gpurun_out/r02_bench_n$N.err
 echo "rc=$?"
