@@ -362,7 +362,8 @@ def sharded_leg(args, rank, local_rank, world, dist):
             res, pairs = sharded.classify_index_sharded(sc, ex, *sl, timings=tm if timed else None, transport=args.transport)
             if timed:
                 tm["s_whole_call"] = tm.get("s_whole_call", 0.0) + time.perf_counter() - tc0
-            classified += int(res["is_classified"].sum())
+            if not timed:                            # instrumentation only (a strided numpy reduction): kept out of the timed steps
+                classified += int(res["is_classified"].sum())
             d2h += int(res.nbytes + pairs.nbytes)
             st = sc.clf.stats()
             recv_k += st["n_query_kmers"]; n_m += st["n_matches"]
@@ -374,15 +375,16 @@ def sharded_leg(args, rank, local_rank, world, dist):
                 merge_launches += st["merge_launches"]
         return classified, recv_k, n_m
 
-    for _ in range(args.warmup):
-        one_step(False)
+    classified = 0
+    for _ in range(max(1, args.warmup)):
+        classified, _, _ = one_step(False)
     barrier()
     note(f"warm-up done, {n_rounds} exchange round(s) per step")
     sampler = ClockSampler(local_rank)
     nv0 = nvlink_tx_rx_kib(local_rank) if rank == 0 else None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        classified, recv_kmers, n_matches = one_step(True)
+        _, recv_kmers, n_matches = one_step(True)
     barrier()
     t_step = time.perf_counter() - t0
     nv1 = nvlink_tx_rx_kib(local_rank) if rank == 0 else None
@@ -417,7 +419,10 @@ def sharded_leg(args, rank, local_rank, world, dist):
                "phases_ms_per_step_rank0": {k: round(1000 * v / args.steps, 2) for k, v in tm.items() if k.startswith("s_")},
                "a2a_rank0": {"kmer_gb_out_per_step": k_gb, "match_gb_out_per_step": m_gb,
                              "kmer_exchange_gbs": k_gb / k_s if k_s > 0 else None, "match_exchange_gbs": m_gb / m_s if m_s > 0 else None,
-                             "note": "bytes this rank stores into its peers' buffers / wall time of the exchange phase (push kernel + count all-gather + barrier)"},
+                             "kmer_push_kernel_gbs": k_gb / (stage_ms.get("ms_push_kmers", 0) / args.steps / 1e3) if stage_ms.get("ms_push_kmers") else None,
+                             "match_push_kernel_gbs": m_gb / (stage_ms.get("ms_push_matches", 0) / args.steps / 1e3) if stage_ms.get("ms_push_matches") else None,
+                             "note": "bytes this rank stores into its peers' buffers over the wall time of the exchange phase (push kernel + barrier: the "
+                                     "wait for the slowest rank is in it) and over the CUDA-event time of the push kernel alone"},
                "nvlink_rank0": None if not (nv0 and nv1) else {"tx_gb_per_step": (nv1[0] - nv0[0]) * 1024 / 1e9 / args.steps,
                                                               "rx_gb_per_step": (nv1[1] - nv0[1]) * 1024 / 1e9 / args.steps,
                                                               "source": "nvidia-smi nvlink -gt d, GPU of rank 0, before/after the timed steps"},

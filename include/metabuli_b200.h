@@ -242,6 +242,8 @@ typedef struct {
     float    ms_bucket_kmers;         /* sharded mode: bucketing + packing of the metamers / of the matches    */
     float    ms_bucket_matches;
     uint64_t n_merge_queries;         /* metamers that reached the sort and the merge (after the amino-acid presence filter) */
+    float    ms_push_kmers;           /* sharded mode, peer transport: the push kernels alone (stores into the peers' buffers) */
+    float    ms_push_matches;
 } mbl_stats;
 int  mbl_get_stats(const mbl_ctx* ctx, mbl_stats* out);
 

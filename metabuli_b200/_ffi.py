@@ -62,7 +62,8 @@ class ReadResult(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms", C.c_float * 7), ("merge_kernel_ms", C.c_float), ("n_query_kmers", C.c_uint64), ("n_matches", C.c_uint64), ("merge_bytes", C.c_uint64),
                 ("merge_launches", C.c_uint32), ("kernel_launches", C.c_uint32), ("overflow_retries", C.c_uint32),
-                ("sub_batches", C.c_uint32), ("ms_bucket_kmers", C.c_float), ("ms_bucket_matches", C.c_float), ("n_merge_queries", C.c_uint64)]
+                ("sub_batches", C.c_uint32), ("ms_bucket_kmers", C.c_float), ("ms_bucket_matches", C.c_float), ("n_merge_queries", C.c_uint64),
+                ("ms_push_kmers", C.c_float), ("ms_push_matches", C.c_float)]
 
 
 class Shard(C.Structure):

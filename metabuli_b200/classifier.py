@@ -192,7 +192,8 @@ class Classifier:
         d.update(ms_merge_kernel=float(s.merge_kernel_ms), n_query_kmers=int(s.n_query_kmers), n_matches=int(s.n_matches), merge_bytes=int(s.merge_bytes),
                  merge_launches=int(s.merge_launches), kernel_launches=int(s.kernel_launches),
                  overflow_retries=int(s.overflow_retries), sub_batches=int(s.sub_batches), ms_bucket_kmers=float(s.ms_bucket_kmers),
-                 ms_bucket_matches=float(s.ms_bucket_matches), n_merge_queries=int(s.n_merge_queries))
+                 ms_bucket_matches=float(s.ms_bucket_matches), n_merge_queries=int(s.n_merge_queries),
+                 ms_push_kmers=float(s.ms_push_kmers), ms_push_matches=float(s.ms_push_matches))
         return d
 
     def db_info(self) -> dict:

@@ -1476,6 +1476,7 @@ int mbl_shard_push_kmers(mbl_ctx* c, const uint64_t* dst_row_offset, const uint6
         c->stats.kernel_launches += 1;
         t.stop();
         c->stats.ms_bucket_kmers += c->stats.ms[MBL_STAGE_EXTRACT] - ms_before;
+        c->stats.ms_push_kmers += c->stats.ms[MBL_STAGE_EXTRACT] - ms_before;
         MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
@@ -1503,6 +1504,7 @@ int mbl_shard_push_matches(mbl_ctx* c, const uint64_t* dst_row_offset) {
         c->stats.kernel_launches += 1;
         t.stop();
         c->stats.ms_bucket_matches += c->stats.ms[MBL_STAGE_MSORT] - ms_before;
+        c->stats.ms_push_matches += c->stats.ms[MBL_STAGE_MSORT] - ms_before;
         MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
