@@ -28,6 +28,7 @@ extern "C" {
 #define MBL_E_BAD_ARG         -3
 #define MBL_E_BAD_DB          -4   /* Q2: target k-mer with taxid 0 / unmapped species (KmerMatcher.cpp:292-300) */
 #define MBL_E_UNSUPPORTED     -5
+#define MBL_E_HOST         (-6)   /* host-side failure inside the library (allocation, thread creation); message in mbl_last_error */
 
 typedef struct mbl_ctx mbl_ctx;
 

@@ -19,6 +19,7 @@ MBL_E_CUDA = -2
 MBL_E_BAD_ARG = -3
 MBL_E_BAD_DB = -4
 MBL_E_UNSUPPORTED = -5
+MBL_E_HOST = -6
 
 IPC_HANDLE_BYTES = 64
 STAGE_NAMES = ["h2d", "extract", "sort", "merge", "match_sort", "score", "d2h"]

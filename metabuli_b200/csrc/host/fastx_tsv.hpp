@@ -46,7 +46,7 @@ inline bool slurp_maybe_gz(const std::string& path, std::string& data) {
 
 // sequential kseq grammar over data[i0, i1): a record starts at a line whose first character is '>' or '@'; name = first
 // whitespace-delimited token; sequence = the graphic characters of the following lines up to a line starting with '>', '@'
-// or '+'; a FASTQ record then skips the '+' line and as many quality characters as it has bases.
+// or '+'; after a '+' line as many quality characters as the record has bases are skipped (for '>' records too, as kseq does).
 // Returns false on an entry without a sequence or a name (QueryIndexer.cpp:50-53); *bad = its ordinal in the range.
 inline bool parse_range(const std::string& data, size_t i0, size_t i1, ReadSet& out, size_t* bad) {
     size_t i = i0;
@@ -63,7 +63,6 @@ inline bool parse_range(const std::string& data, size_t i0, size_t i1, ReadSet& 
     while (i < n) {
         while (i < n && d[i] != '>' && d[i] != '@') line(b, e);
         if (i >= n) break;
-        const char tag = d[i];
         line(b, e);
         size_t p = b + 1;
         while (p < e && !isspace((unsigned char)d[p])) ++p;
@@ -81,7 +80,7 @@ inline bool parse_range(const std::string& data, size_t i0, size_t i1, ReadSet& 
                 out.bases.resize(w);
             }
         }
-        if (tag == '@' && i < n && d[i] == '+') {
+        if (i < n && d[i] == '+') {                          // kseq reads qualities after a '+' line whatever the record's tag was
             line(b, e);
             size_t ql = 0;
             const size_t sl = out.bases.size() - start;

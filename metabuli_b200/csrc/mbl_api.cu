@@ -58,6 +58,7 @@ struct mbl_ctx {
     int filter_bits = 16;               // MBL_FILTER_BITS: bits per index k-mer of the amino-acid presence filter, 0 = no filter
     uint64_t arena_S8 = 0;              // slot stride of the phase-1 arena layout (set by whoever fills it)
     int merge_threads = 512;            // MBL_MERGE_THREADS: 512 (2 CTAs per SM) or 256 (up to 4 CTAs per SM) threads per merge CTA
+    bool budget_low = false;            // slots_budget found (almost) no workspace left next to the index
     bool no_probe = false;              // the index-sharded phases work on whole batches: no probe sub-batch
     int force_sort_bit = 0;             // MBL_SORT_BIT: override the load-time choice of TileDirectory::sort_begin_bit
     // test hooks: force the capacity guesses low so that the retry paths run on small inputs (tests/test_gpu_edge_paths.py)
@@ -141,6 +142,12 @@ int fail(mbl_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
     return code;
 }
+// no exception may cross the C boundary (a std::bad_alloc from a planning vector, a std::system_error from thread creation
+// would abort a ctypes / C caller): every entry point ends with this after its CudaError handler
+#define MBL_CATCH_HOST(c)                                                                                       \
+    catch (const std::bad_alloc&) { return fail(c, MBL_E_HOST, "host memory allocation failed"); }              \
+    catch (const std::exception& e) { return fail(c, MBL_E_HOST, std::string("host error: ") + e.what()); }     \
+    catch (...) { return fail(c, MBL_E_HOST, "unknown host error"); }
 int fail_cuda(mbl_ctx* c, const CudaError& e) {
     char buf[512];
     snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.file, e.line);
@@ -292,10 +299,12 @@ uint64_t slots_budget(mbl_ctx* c) {
     // with the presence filter the phase-1 arena only holds the survivors (the guess of run_sub_batch)
     const double kept = (c->dir.filter && c->filter_complete) ? std::min(1.0, c->pass_ratio > 0 ? 1.3 * c->pass_ratio + 0.05 : 0.45) : 1.0;
     const double per_slot = std::max(32.0 * kept, 48.0 * r) + 24.0 * r + 4.0;
-    double budget = 0.88 * (double)(free_b + held) - 10.0e9;
+    // fixed part: scoring scratch of one chunk, results, CUB scratch — 10 GB on a B200, never more than 6 % of the device
+    double budget = 0.88 * (double)(free_b + held) - std::min(10.0e9, 0.06 * (double)total_b);
     uint64_t s = budget > 0 ? (uint64_t)(budget / per_slot) : 0;
     s = std::min<uint64_t>(s, (uint64_t)(3.9e9 / r));            // 32-bit match permutation
     s = std::min<uint64_t>(s, 4000000000ull);                    // 32-bit slot index (K2 payload)
+    c->budget_low = s < (1ull << 22);                          // a few thousand reads per sub-batch: the run would look hung
     s = std::max<uint64_t>(s, 1ull << 16);
     return s;
 }
@@ -679,8 +688,11 @@ int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
         MBL_CUDA(cudaStreamSynchronize(c->st));
     } catch (const CudaError& e) {
         fail_cuda(c, e);
-        delete c;
+        mbl_destroy(c);                 // stream, events and the tables uploaded so far
         return MBL_E_CUDA;
+    } catch (...) {
+        mbl_destroy(c);
+        return MBL_E_HOST;
     }
     *out = c;
     return MBL_OK;
@@ -795,7 +807,7 @@ int load_db_range(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx, const mb
         c->db_loaded = true;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -928,13 +940,24 @@ int mbl_upload_batch(mbl_ctx* c, const mbl_batch* b) {
         summarize_reads(b, c->summary);                        // host work overlaps the copies
         c->subs.clear();
         c->probe_first = c->match_ratio == 0.0 && !c->no_probe;
-        plan_sub_batches(c, c->summary, 0, slots_budget(c), c->probe_first, c->subs);
+        const uint64_t max_slots = slots_budget(c);
+        plan_sub_batches(c, c->summary, 0, max_slots, c->probe_first, c->subs);
+        if (c->budget_low && c->subs.size() > 64) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            char msg[256];
+            snprintf(msg, sizeof msg, "only %.1f of %.1f GB of device memory are free next to the index: the batch would be cut into %zu "
+                     "sub-batches of ~%llu k-mer slots (each streams the whole index); use a GPU with more memory or the index-sharded mode",
+                     free_b / 1e9, total_b / 1e9, c->subs.size(), (unsigned long long)max_slots);
+            t.stop();
+            return fail(c, MBL_E_CAPACITY, msg);
+        }
         c->probe_first = c->probe_first && c->subs.size() > 1;
         c->plan_has_probe = c->probe_first;
         t.stop();
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -984,6 +1007,7 @@ int mbl_classify_resident(mbl_ctx* c) {
                     }
                     int rc = MBL_OK;
                     try { rc = sub_front(lanes[k & 1], c->subs[k], &reserved[k]); } catch (const CudaError& e) { rc = fail_cuda(lanes[k & 1], e); }
+                    catch (...) { rc = fail(lanes[k & 1], MBL_E_HOST, "host error in the pipeline lane"); }
                     std::lock_guard<std::mutex> lk(mu);
                     if (rc != MBL_OK) { rc1 = rc; c->err = lanes[k & 1]->err; stop = true; cv.notify_all(); return; }
                     fdone[k] = 1;
@@ -1000,6 +1024,7 @@ int mbl_classify_resident(mbl_ctx* c) {
                 mbl_ctx* L = lanes[k & 1];
                 const uint64_t off = L->n_pairs;
                 try { rcb = sub_back(L, c->subs[k], reserved[k]); } catch (const CudaError& e) { rcb = fail_cuda(L, e); }
+                catch (...) { rcb = fail(L, MBL_E_HOST, "host error in the pipeline lane"); }
                 std::lock_guard<std::mutex> lk(mu);
                 if (rcb != MBL_OK) { if (L != c) c->err = L->err; stop = true; cv.notify_all(); break; }
                 done[k] = SubDone{(int)(k & 1), off, L->n_pairs - off};
@@ -1021,6 +1046,8 @@ int mbl_classify_resident(mbl_ctx* c) {
                     }
                 } catch (const CudaError& e) {
                     rc1 = fail_cuda(s, e);
+                } catch (...) {
+                    rc1 = fail(s, MBL_E_HOST, "host error in the pipeline lane");
                 }
             });
         }
@@ -1102,7 +1129,7 @@ int mbl_classify_resident(mbl_ctx* c) {
         MBL_CUDA(cudaStreamSynchronize(c->st));
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1118,7 +1145,7 @@ int mbl_download_results(mbl_ctx* c, mbl_read_result* out, int32_t* taxcnt_pairs
         t.stop();
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1163,7 +1190,7 @@ int mbl_prefetch_batch(mbl_ctx* c, const mbl_batch* b) {
         c->staged = true;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1188,7 +1215,7 @@ int mbl_classify_prefetched(mbl_ctx* c, const mbl_batch* next, mbl_read_result* 
         c->stats.ms[MBL_STAGE_H2D] = ms;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     if (next) {
         int rc = mbl_prefetch_batch(c, next);
         if (rc != MBL_OK) return rc;
@@ -1218,7 +1245,7 @@ int mbl_shard_filter_or(mbl_ctx* c, const void* d_other, uint64_t n_bytes, int c
         if (complete) c->filter_complete = true;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1287,7 +1314,7 @@ int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_
         MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1311,7 +1338,7 @@ int mbl_shard_pack_kmers(mbl_ctx* c, const uint64_t** d_send_value, const uint64
         *d_send_value = sv; *d_send_qinfo = sq;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1358,7 +1385,7 @@ int mbl_shard_match(mbl_ctx* c, const uint64_t* d_value, const uint64_t* d_qinfo
         MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1380,7 +1407,7 @@ int mbl_shard_pack_matches(mbl_ctx* c, const mbl_match_rec** d_send_match) {
         *d_send_match = sm;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1412,7 +1439,7 @@ int mbl_shard_recv_buffers(mbl_ctx* c, uint64_t kmer_rows, uint64_t match_rows, 
         *d_kmers = c->recv_kmers; *d_matches = c->recv_matches;
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1437,7 +1464,7 @@ int mbl_shard_attach_peer(mbl_ctx* c, uint32_t peer, const uint8_t* handle_kmers
         }
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1480,7 +1507,7 @@ int mbl_shard_push_kmers(mbl_ctx* c, const uint64_t* dst_row_offset, const uint6
         MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1508,7 +1535,7 @@ int mbl_shard_push_matches(mbl_ctx* c, const uint64_t* dst_row_offset) {
         MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1530,7 +1557,7 @@ int mbl_shard_score(mbl_ctx* c, const mbl_match_rec* d_match, uint64_t n_match) 
         MBL_CUDA(cudaStreamSynchronize(c->st));
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1592,7 +1619,7 @@ int mbl_extract(mbl_ctx* c, const mbl_batch* b, uint64_t* value, uint64_t* qinfo
         MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1612,7 +1639,7 @@ int mbl_sort_kmers(mbl_ctx* c, uint64_t* value, uint64_t* qinfo, size_t n) {
         MBL_CUDA(cudaStreamSynchronize(st));
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1678,7 +1705,7 @@ int mbl_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, size_t n
         if (w != h_cnt[2]) return fail(c, MBL_E_CUDA, "internal: match count mismatch");
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1706,7 +1733,7 @@ int mbl_sort_matches(mbl_ctx* c, mbl_match_rec* m, size_t n) {
         MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 
@@ -1773,7 +1800,7 @@ int mbl_score(mbl_ctx* c, const mbl_match_rec* sorted_h, size_t M, uint32_t n, c
         MBL_CUDA(cudaGetLastError());
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
-    }
+    } MBL_CATCH_HOST(c)
     return MBL_OK;
 }
 

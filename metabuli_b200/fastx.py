@@ -21,9 +21,12 @@ def read_fastx(path: str):
         if not ln or ln[:1] not in (b">", b"@"):
             i += 1
             continue
-        tag = ln[:1]
         hdr = ln[1:].rstrip(b"\r")
-        names.append(hdr.split(None, 1)[0].decode() if hdr.strip() else "")
+        # kseq: the name is what stands between the tag and the first whitespace — "> x" has an EMPTY name
+        k = 0
+        while k < len(hdr) and hdr[k] not in b" \t\v\f\r\n":
+            k += 1
+        names.append(hdr[:k].decode())
         i += 1
         parts = []
         while i < n and lines[i][:1] not in (b">", b"@", b"+"):
@@ -31,13 +34,15 @@ def read_fastx(path: str):
             i += 1
         seq = b"".join(parts)
         seq = bytes(c for c in seq if 33 <= c <= 126) if any(c < 33 or c > 126 for c in seq) else seq
-        if tag == b"@" and i < n and lines[i][:1] == b"+":
+        if i < n and lines[i][:1] == b"+":                  # kseq reads qualities after a '+' line whatever the record's tag was
             i += 1
             ql = 0
             while i < n and ql < len(seq):
                 ql += len(lines[i].rstrip(b"\r"))
                 i += 1
         seqs.append(seq)
+        if not seq or not names[-1]:                        # QueryIndexer.cpp:50-53 / KmerExtractor.cpp:447-451: the reference exits
+            raise ValueError(f"{len(seqs)}th entry has no sequence or name.")
     offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
     if seqs:
         offsets[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)

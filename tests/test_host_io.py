@@ -100,6 +100,23 @@ def test_streaming_reader_equals_whole_file_load(hio, tmp_path, fixtures_dir, ba
         assert np.array_equal(offs, want[2]) and np.array_equal(bases, want[1]), p
 
 
+def test_header_with_leading_blank_has_an_empty_name(hio, tmp_path):
+    """kseq takes the name up to the first whitespace after the tag, so "> x" has an empty name and the reference stops with
+    "1th entry has no sequence or name." (checked against the reference binary, round 2); all three readers agree."""
+    from metabuli_b200.fastx import read_fastx
+    p = tmp_path / "blank.fna"
+    p.write_bytes(b"> x\nACGTACGT\n")
+    assert hio.hio_load(str(p).encode(), 1) == -1 and b"1th entry has no sequence or name." in hio.hio_text()
+    with pytest.raises(ValueError, match="1th entry has no sequence or name"):
+        read_fastx(str(p))
+    # qualities after a '+' line are skipped whatever the record's tag was (kseq grammar)
+    q = tmp_path / "plus.fna"
+    q.write_bytes(b">a d\nACGT\n+\n>III\n>b\nGGCC\n")
+    names, bases, offs = read_fastx(str(q))
+    assert names == ["a", "b"] and bytes(bases) == b"ACGTGGCC"
+    assert hio.hio_load(str(q).encode(), 1) == 2 and hio.hio_total_bases() == 8
+
+
 def test_reader_rejects_empty_entries(hio, tmp_path):
     p = tmp_path / "bad.fna"
     p.write_bytes(b">a\nACGT\n>b\n>c\nAC\n")
