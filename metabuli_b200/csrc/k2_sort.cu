@@ -8,10 +8,8 @@
 //                    bits the batch actually uses (48 for 150-bp reads), then the short runs that share that
 //                    key are ordered by (hamming, dna) in place — together the reference's total order.
 //                    Batches whose packed key would not fit 64 bits fall back to two stable LSD passes.
-//                    (Round 2 tried a two-level order — three radix passes over (32-bit seqID, index) and a warp per read that
-//                    orders its ~150 rows in shared memory while gathering them: bit-identical, but 99-106 ms against 74.6 ms
-//                    for this single-key path on the benchmark, as a rank-by-counting and as a bitonic network alike: a
-//                    256-key network costs ~3 k warp instructions per read, more than the three 8-byte radix passes it saves.)
+#include <algorithm>
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "kernels.cuh"
@@ -150,6 +148,156 @@ __global__ void match_gather_fix_kernel(const mbl_match_rec* __restrict__ in, co
         copy(idx[r], i + rank);
     }
 }
+// ---- two-level ordering (short-read batches) -------------------------------------------------------------------------------------
+// compareMatches (KmerMatcher.cpp:1149-1166) orders by (seqID, species, frame, pos, hamming, dna).  Only the seqID needs a global
+// sort: three 8-bit radix passes over (32-bit seqID, 32-bit row index) instead of six over (64-bit key, index).  The rest of the
+// order is local to a read's ~100-150 rows: one warp per read gathers the rows through the permutation (the one random read of
+// the rows that any ordering needs), radix-sorts (species | frame | pos) keys in shared memory — 8-bit digits, histogram by
+// shared-memory atomics, stable ranks from match.any ballots, ~250 warp instructions per pass — orders the rare rows that share
+// that key by (hamming, dna), and writes the rows to their final places.  (Ranking by counting, n^2 / 32 steps, and a bitonic
+// network, ~3 k instructions per read, both lost to the six global passes: 99-106 ms against 74.6 ms.)
+constexpr uint32_t kOrderSmallRows = 256;       // first launch: reads of up to 256 rows, 8 warps per CTA, ~5 KB of shared memory per warp
+constexpr uint32_t kOrderMaxRows = 2048;        // second launch (2 warps per CTA) for the few longer ones; beyond that => single-key path
+
+__global__ void match_seqkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    key[i] = qi_seq(m[i].qinfo);
+    idx[i] = (uint32_t)i;
+}
+// per-read segments from the sorted seqIDs; blank rows (seqID 0) sort first, n_blank[0] = their count
+__global__ void seq_segments_kernel(const uint32_t* __restrict__ key, size_t n, uint32_t n_reads, uint64_t* __restrict__ seg_begin,
+                                    uint64_t* __restrict__ seg_end, unsigned long long* __restrict__ n_blank) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = key[i];
+    const uint32_t sp = i > 0 ? key[i - 1] : ~s, sn = i + 1 < n ? key[i + 1] : ~s;
+    if (s == 0) { if (sn != 0) *n_blank = i + 1; return; }
+    if (s > n_reads) return;
+    if (sp != s) seg_begin[s - 1] = i;
+    if (sn != s) seg_end[s - 1] = i + 1;
+}
+__global__ void seg_maxlen_kernel(const uint64_t* __restrict__ seg_begin, const uint64_t* __restrict__ seg_end, uint32_t n_reads,
+                                  unsigned long long* __restrict__ max_len) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long len = r < n_reads ? seg_end[r] - seg_begin[r] : 0ull;
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len) atomicMax(max_len, len);
+}
+
+// reads with kMinRows < rows <= kMaxRows; KeyT holds species | frame | pos / pos_div (local_bits bits)
+template <class KeyT, uint32_t kMinRows, uint32_t kMaxRows, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32)
+match_order_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ seg_begin,
+                   const uint64_t* __restrict__ seg_end, uint32_t n_reads, int pos_bits, uint32_t pos_div, int local_bits,
+                   mbl_match_rec* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char order_smem[];
+    constexpr size_t kPerWarp = (size_t)kMaxRows * (2 * sizeof(KeyT) + 2 * 2 + 4) + 256 * 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    unsigned char* base = order_smem + (size_t)warp * kPerWarp;
+    KeyT* ka = reinterpret_cast<KeyT*>(base);
+    KeyT* kb = ka + kMaxRows;
+    uint32_t* tie = reinterpret_cast<uint32_t*>(kb + kMaxRows);
+    uint32_t* hist = tie + kMaxRows;
+    uint16_t* oa = reinterpret_cast<uint16_t*>(hist + 256);
+    uint16_t* ob = oa + kMaxRows;
+    for (uint32_t r = blockIdx.x * kWarps + warp; r < n_reads; r += gridDim.x * kWarps) {
+        const uint64_t b = seg_begin[r];
+        const uint32_t n = (uint32_t)(seg_end[r] - b);
+        if (n <= kMinRows || n > kMaxRows) continue;
+        if (n == 1) {
+            if (lane < 3) reinterpret_cast<uint64_t*>(out + b)[lane] = reinterpret_cast<const uint64_t*>(in + idx[b])[lane];
+            continue;
+        }
+        // keys of the read's rows, in gather order
+        for (uint32_t j = lane; j < n; j += 32) {
+            const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + j]);
+            const uint64_t q = s[0], w1 = s[1], w2 = s[2];       // qinfo | target, species | dna, field, hamming
+            uint64_t k = w1 >> 32;                                // species
+            k = (k << 3) | (q >> 61);                             // frame
+            k = (k << pos_bits) | (uint64_t)((uint32_t)q / pos_div);
+            ka[j] = (KeyT)k;
+            oa[j] = (uint16_t)j;
+            tie[j] = ((uint32_t)((w2 >> 48) & 7ull) << 24) | (uint32_t)(w2 & 0xFFFFFFull);   // hamming (<= 7, KmerMatcher.cpp:1136) | dna
+        }
+        __syncwarp();
+        KeyT *src = ka, *dst = kb;
+        uint16_t *osrc = oa, *odst = ob;
+        for (int shift = 0; shift < local_bits; shift += 8) {
+            for (uint32_t k = lane; k < 256; k += 32) hist[k] = 0u;
+            __syncwarp();
+            for (uint32_t j = lane; j < n; j += 32) atomicAdd(&hist[(uint32_t)(src[j] >> shift) & 255u], 1u);
+            __syncwarp();
+            {   // exclusive scan of the 256 counts: 8 bins per lane, shuffle scan of the lane sums
+                uint32_t c[8], sum = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { c[t] = hist[8 * lane + t]; sum += c[t]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                uint32_t run = incl - sum;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { hist[8 * lane + t] = run; run += c[t]; }
+            }
+            __syncwarp();
+            for (uint32_t j0 = 0; j0 < n; j0 += 32) {            // stable: chunks in order, lanes of a chunk ranked by match.any
+                const uint32_t j = j0 + lane;
+                const bool active = j < n;
+                const KeyT k = active ? src[j] : (KeyT)0;
+                const uint32_t d = active ? ((uint32_t)(k >> shift) & 255u) : (0x10000u | (uint32_t)lane);
+                const uint32_t same = __match_any_sync(0xffffffffu, d);
+                const uint32_t rank = __popc(same & lt);
+                const uint32_t at = active ? hist[d] : 0u;
+                __syncwarp();
+                if (active && rank == 0) hist[d] = at + __popc(same);
+                __syncwarp();
+                if (active) { dst[at + rank] = k; odst[at + rank] = osrc[j]; }
+            }
+            __syncwarp();
+            { KeyT* t = src; src = dst; dst = t; }
+            { uint16_t* t = osrc; osrc = odst; odst = t; }
+        }
+        // rows that share (species, frame, pos): order by (hamming, dna); the first lane of a run does it (runs of 2-3)
+        for (uint32_t p = lane; p < n; p += 32) {
+            if ((p == 0 || src[p - 1] != src[p]) && p + 1 < n && src[p + 1] == src[p]) {
+                uint32_t e = p + 2;
+                while (e < n && src[e] == src[p]) ++e;
+                for (uint32_t x = p + 1; x < e; ++x) {
+                    const uint16_t v = osrc[x];
+                    const uint32_t tv = tie[v];
+                    uint32_t y = x;
+                    while (y > p && tie[osrc[y - 1]] > tv) { osrc[y] = osrc[y - 1]; --y; }
+                    osrc[y] = v;
+                }
+            }
+        }
+        __syncwarp();
+        for (uint32_t p = lane; p < n; p += 32) {
+            const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + osrc[p]]);
+            uint64_t* d = reinterpret_cast<uint64_t*>(out + b + p);
+            const uint64_t a0 = s[0], a1 = s[1], a2 = s[2];
+            d[0] = a0; d[1] = a1; d[2] = a2;
+        }
+        __syncwarp();
+    }
+}
+
+template <class KeyT>
+static void launch_match_order(const mbl_match_rec* in, const uint32_t* idx, const uint64_t* seg_begin, const uint64_t* seg_end, uint32_t n_reads,
+                               int pos_bits, uint32_t pos_div, int local_bits, uint64_t max_len, mbl_match_rec* out, cudaStream_t st) {
+    constexpr int kW1 = 8, kW2 = 2;
+    const size_t smem1 = (size_t)kW1 * ((size_t)kOrderSmallRows * (2 * sizeof(KeyT) + 2 * 2 + 4) + 256 * 4);
+    const size_t smem2 = (size_t)kW2 * ((size_t)kOrderMaxRows * (2 * sizeof(KeyT) + 2 * 2 + 4) + 256 * 4);
+    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, 0, kOrderSmallRows, kW1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kOrderSmallRows, kOrderMaxRows, kW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const unsigned blocks1 = (unsigned)std::min<uint64_t>((n_reads + kW1 - 1) / kW1, 148ull * 32);
+    match_order_kernel<KeyT, 0, kOrderSmallRows, kW1><<<blocks1, kW1 * 32, smem1, st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits, pos_div, local_bits, out);
+    if (max_len > kOrderSmallRows)
+        match_order_kernel<KeyT, kOrderSmallRows, kOrderMaxRows, kW2><<<148 * 3, kW2 * 32, smem2, st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits,
+                                                                                                      pos_div, local_bits, out);
+}
+
 // seg_begin/seg_end per read from the sorted match list (Classifier.cpp:174-185 MatchBlocks)
 __global__ void segment_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t n_reads, uint64_t* __restrict__ seg_begin,
                                uint64_t* __restrict__ seg_end) {
@@ -226,6 +374,31 @@ bool sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
     const int seq_bits = bits_for(n_reads);
     const uint32_t pos_div = codon_spaced ? 3u : 1u;     // true for matches produced by K3 (see match_fullkey_kernel)
     const int pos3_bits = bits_for(max_pos / pos_div);
+    static const bool force_fullkey = getenv("MBL_SORT_FULLKEY") && atoi(getenv("MBL_SORT_FULLKEY")) != 0;   // tests / A-B: the single-key path
+    const int local_bits = sp_bits + 3 + pos3_bits;
+    if (seg_begin && seg_end && !force_fullkey && local_bits <= 40) {
+        // two-level: global sort by seqID, then per-read ordering fused into the gather
+        uint32_t *k32a = reinterpret_cast<uint32_t*>(key_a), *k32b = reinterpret_cast<uint32_t*>(key_b);
+        match_seqkey_kernel<<<blocks, 256, 0, st>>>(in, n, k32a, idx_a);
+        cub::DoubleBuffer<uint32_t> k(k32a, k32b), v(idx_a, idx_b);
+        MBL_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k, v, (long long)n, 0, seq_bits, st));
+        MBL_CUDA(cudaMemsetAsync(seg_begin, 0, 8 * (size_t)n_reads, st));
+        MBL_CUDA(cudaMemsetAsync(seg_end, 0, 8 * (size_t)n_reads, st));
+        unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(tmp);      // the sort is done with its scratch
+        MBL_CUDA(cudaMemsetAsync(d_cnt, 0, 16, st));
+        seq_segments_kernel<<<blocks, 256, 0, st>>>(k.Current(), n, n_reads, seg_begin, seg_end, d_cnt);
+        seg_maxlen_kernel<<<(n_reads + 255) / 256, 256, 0, st>>>(seg_begin, seg_end, n_reads, d_cnt + 1);
+        unsigned long long h_cnt[2] = {0, 0};
+        MBL_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
+        MBL_CUDA(cudaStreamSynchronize(st));
+        if (h_cnt[1] <= kOrderMaxRows) {
+            if (h_cnt[0]) MBL_CUDA(cudaMemsetAsync(out, 0, sizeof(mbl_match_rec) * (size_t)h_cnt[0], st));   // blank rows (seqID 0) come first
+            if (local_bits <= 32) launch_match_order<uint32_t>(in, v.Current(), seg_begin, seg_end, n_reads, pos3_bits, pos_div, local_bits, h_cnt[1], out, st);
+            else launch_match_order<uint64_t>(in, v.Current(), seg_begin, seg_end, n_reads, pos3_bits, pos_div, local_bits, h_cnt[1], out, st);
+            return true;
+        }
+        // a read with more rows than a warp orders in shared memory (long reads): the single-key path below redoes the order
+    }
     if (seq_bits + sp_bits + 3 + pos3_bits <= 64) {
         match_fullkey_kernel<<<blocks, 256, 0, st>>>(in, n, sp_bits, pos3_bits, pos_div, key_a, idx_a);
         cub::DoubleBuffer<uint64_t> k(key_a, key_b);

@@ -1726,8 +1726,10 @@ int mbl_sort_matches(mbl_ctx* c, mbl_match_rec* m, size_t n) {
         mbl_match_rec* sorted = c->m_sorted.get<mbl_match_rec>(n + 1);
         MBL_CUDA(cudaMemcpyAsync(raw, m, sizeof(mbl_match_rec) * n, cudaMemcpyHostToDevice, st));
         void* tmp = c->cub_tmp.get<uint8_t>(sort_matches_temp_bytes(n));
+        // with segment arrays the two-level ordering (seqID radix sort + per-read ordering) runs, as in the pipeline
         sort_matches(tmp, c->cub_tmp.cap, raw, sorted, n, max_seq, max_sp, max_pos, false, c->key_a.get<uint64_t>(n + 1),
-                     c->key_b.get<uint64_t>(n + 1), c->idx_a.get<uint32_t>(n + 1), c->idx_b.get<uint32_t>(n + 1), st);
+                     c->key_b.get<uint64_t>(n + 1), c->idx_a.get<uint32_t>(n + 1), c->idx_b.get<uint32_t>(n + 1), st,
+                     c->seg_b.get<uint64_t>((size_t)max_seq + 1), c->seg_e.get<uint64_t>((size_t)max_seq + 1));
         MBL_CUDA(cudaMemcpyAsync(m, sorted, sizeof(mbl_match_rec) * n, cudaMemcpyDeviceToHost, st));
         MBL_CUDA(cudaStreamSynchronize(st));
         MBL_CUDA(cudaGetLastError());

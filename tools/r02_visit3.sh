@@ -23,6 +23,13 @@ for cfg in "$@"; do
   echo "== bench $tag ($envs)"
   env $envs timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/r02_${T}_bench_$tag.json | summ
 done
+if [ "${LAUNCHES:-0}" = "1" ]; then
+echo "== ncu launch list (one step)"
+KRE='regex:(merge_|extract_kernel|read_meta|score_|segment|match_|seq_|seg_|taxcnt|RadixSort|DeviceScan|DeviceSelect|filter_|fg_len|read_len|read_first)'
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KRE" -c 700 --csv --log-file gpurun_out/r02_${T}_launches.csv \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r02_${T}_ncu_launch_run.log 2>&1
+tail -1 gpurun_out/r02_${T}_ncu_launch_run.log | cut -c1-120
+fi
 if [ "${SKIP_NCU:-0}" = "1" ]; then exit 0; fi
 echo "== ncu full: merge kernel"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:merge_kernel -s 1 -c 1 -o gpurun_out/r02_${T}_merge_prof -f \
