@@ -156,8 +156,8 @@ __global__ void match_gather_fix_kernel(const mbl_match_rec* __restrict__ in, co
 // shared-memory atomics, stable ranks from match.any ballots, ~250 warp instructions per pass — orders the rare rows that share
 // that key by (hamming, dna), and writes the rows to their final places.  (Ranking by counting, n^2 / 32 steps, and a bitonic
 // network, ~3 k instructions per read, both lost to the six global passes: 99-106 ms against 74.6 ms.)
-constexpr uint32_t kOrderSmallRows = 256;       // first launch: reads of up to 256 rows, 8 warps per CTA, ~5 KB of shared memory per warp
-constexpr uint32_t kOrderMaxRows = 2048;        // second launch (2 warps per CTA) for the few longer ones; beyond that => single-key path
+constexpr uint32_t kOrderSmallRows = 256;       // first launch: reads of up to 256 rows, 4 warps per CTA, ~10 KB of shared memory per warp
+constexpr uint32_t kOrderMaxRows = 2048;        // second launch (1 warp per CTA) for the few longer ones; beyond that => single-key path
 
 __global__ void match_seqkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,113 +185,142 @@ __global__ void seg_maxlen_kernel(const uint64_t* __restrict__ seg_begin, const 
     if ((threadIdx.x & 31) == 0 && len) atomicMax(max_len, len);
 }
 
-// reads with kMinRows < rows <= kMaxRows; KeyT holds species | frame | pos / pos_div (local_bits bits)
+__device__ __forceinline__ void order_cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+// reads with kMinRows < rows <= kMaxRows; KeyT holds species | frame | pos / pos_div (local_bits bits).  A warp takes 32
+// consecutive reads at a time (segments loaded coalesced, the reads in range picked by ballot); a read's rows are gathered into
+// shared memory with cp.async — every row of the read in flight at once instead of one dependent load chain per 32 rows, which
+// made the first version of this kernel latency-bound (45 ms) — sorted there, and written out coalesced.
 template <class KeyT, uint32_t kMinRows, uint32_t kMaxRows, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32)
 match_order_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ seg_begin,
                    const uint64_t* __restrict__ seg_end, uint32_t n_reads, int pos_bits, uint32_t pos_div, int local_bits,
                    mbl_match_rec* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char order_smem[];
-    constexpr size_t kPerWarp = (size_t)kMaxRows * (2 * sizeof(KeyT) + 2 * 2 + 4) + 256 * 4;
+    constexpr size_t kPerWarp = (size_t)kMaxRows * (24 + 2 * sizeof(KeyT) + 2 * 2) + 256 * 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     unsigned char* base = order_smem + (size_t)warp * kPerWarp;
-    KeyT* ka = reinterpret_cast<KeyT*>(base);
+    uint64_t* rows = reinterpret_cast<uint64_t*>(base);                      // [3 * kMaxRows]
+    KeyT* ka = reinterpret_cast<KeyT*>(rows + 3 * (size_t)kMaxRows);
     KeyT* kb = ka + kMaxRows;
-    uint32_t* tie = reinterpret_cast<uint32_t*>(kb + kMaxRows);
-    uint32_t* hist = tie + kMaxRows;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(kb + kMaxRows);
     uint16_t* oa = reinterpret_cast<uint16_t*>(hist + 256);
     uint16_t* ob = oa + kMaxRows;
-    for (uint32_t r = blockIdx.x * kWarps + warp; r < n_reads; r += gridDim.x * kWarps) {
-        const uint64_t b = seg_begin[r];
-        const uint32_t n = (uint32_t)(seg_end[r] - b);
-        if (n <= kMinRows || n > kMaxRows) continue;
-        if (n == 1) {
-            if (lane < 3) reinterpret_cast<uint64_t*>(out + b)[lane] = reinterpret_cast<const uint64_t*>(in + idx[b])[lane];
-            continue;
-        }
-        // keys of the read's rows, in gather order
-        for (uint32_t j = lane; j < n; j += 32) {
-            const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + j]);
-            const uint64_t q = s[0], w1 = s[1], w2 = s[2];       // qinfo | target, species | dna, field, hamming
-            uint64_t k = w1 >> 32;                                // species
-            k = (k << 3) | (q >> 61);                             // frame
-            k = (k << pos_bits) | (uint64_t)((uint32_t)q / pos_div);
-            ka[j] = (KeyT)k;
-            oa[j] = (uint16_t)j;
-            tie[j] = ((uint32_t)((w2 >> 48) & 7ull) << 24) | (uint32_t)(w2 & 0xFFFFFFull);   // hamming (<= 7, KmerMatcher.cpp:1136) | dna
-        }
-        __syncwarp();
-        KeyT *src = ka, *dst = kb;
-        uint16_t *osrc = oa, *odst = ob;
-        for (int shift = 0; shift < local_bits; shift += 8) {
-            for (uint32_t k = lane; k < 256; k += 32) hist[k] = 0u;
-            __syncwarp();
-            for (uint32_t j = lane; j < n; j += 32) atomicAdd(&hist[(uint32_t)(src[j] >> shift) & 255u], 1u);
-            __syncwarp();
-            {   // exclusive scan of the 256 counts: 8 bins per lane, shuffle scan of the lane sums
-                uint32_t c[8], sum = 0;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) { c[t] = hist[8 * lane + t]; sum += c[t]; }
-                uint32_t incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                uint32_t run = incl - sum;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) { hist[8 * lane + t] = run; run += c[t]; }
+    for (uint32_t r0 = (blockIdx.x * kWarps + warp) * 32u; r0 < n_reads; r0 += gridDim.x * kWarps * 32u) {
+        uint64_t my_b = 0;
+        uint32_t my_n = 0;
+        if (r0 + lane < n_reads) { my_b = seg_begin[r0 + lane]; my_n = (uint32_t)(seg_end[r0 + lane] - my_b); }
+        uint32_t todo = __ballot_sync(0xffffffffu, my_n > kMinRows && my_n <= kMaxRows);
+        while (todo) {
+            const int t = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint64_t b = __shfl_sync(0xffffffffu, my_b, t);
+            const uint32_t n = __shfl_sync(0xffffffffu, my_n, t);
+            if (n == 1) {
+                if (lane < 3) reinterpret_cast<uint64_t*>(out + b)[lane] = reinterpret_cast<const uint64_t*>(in + idx[b])[lane];
+                continue;
             }
-            __syncwarp();
-            for (uint32_t j0 = 0; j0 < n; j0 += 32) {            // stable: chunks in order, lanes of a chunk ranked by match.any
-                const uint32_t j = j0 + lane;
-                const bool active = j < n;
-                const KeyT k = active ? src[j] : (KeyT)0;
-                const uint32_t d = active ? ((uint32_t)(k >> shift) & 255u) : (0x10000u | (uint32_t)lane);
-                const uint32_t same = __match_any_sync(0xffffffffu, d);
-                const uint32_t rank = __popc(same & lt);
-                const uint32_t at = active ? hist[d] : 0u;
-                __syncwarp();
-                if (active && rank == 0) hist[d] = at + __popc(same);
-                __syncwarp();
-                if (active) { dst[at + rank] = k; odst[at + rank] = osrc[j]; }
-            }
-            __syncwarp();
-            { KeyT* t = src; src = dst; dst = t; }
-            { uint16_t* t = osrc; osrc = odst; odst = t; }
-        }
-        // rows that share (species, frame, pos): order by (hamming, dna); the first lane of a run does it (runs of 2-3)
-        for (uint32_t p = lane; p < n; p += 32) {
-            if ((p == 0 || src[p - 1] != src[p]) && p + 1 < n && src[p + 1] == src[p]) {
-                uint32_t e = p + 2;
-                while (e < n && src[e] == src[p]) ++e;
-                for (uint32_t x = p + 1; x < e; ++x) {
-                    const uint16_t v = osrc[x];
-                    const uint32_t tv = tie[v];
-                    uint32_t y = x;
-                    while (y > p && tie[osrc[y - 1]] > tv) { osrc[y] = osrc[y - 1]; --y; }
-                    osrc[y] = v;
+            // gather: the permutation entries of 8 rows per lane at a time, then all their words in flight
+            for (uint32_t j0 = 0; j0 < n; j0 += 256) {
+                uint32_t ix[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const uint32_t j = j0 + 32u * u + lane; ix[u] = j < n ? idx[b + j] : 0u; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t j = j0 + 32u * u + lane;
+                    if (j < n) {
+                        const uint64_t* s = reinterpret_cast<const uint64_t*>(in + ix[u]);
+                        order_cp_async8(rows + 3 * j, s);
+                        order_cp_async8(rows + 3 * j + 1, s + 1);
+                        order_cp_async8(rows + 3 * j + 2, s + 2);
+                    }
                 }
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            for (uint32_t j = lane; j < n; j += 32) {
+                const uint64_t q = rows[3 * j], w1 = rows[3 * j + 1];       // qinfo | target, species
+                uint64_t k = w1 >> 32;                                        // species
+                k = (k << 3) | (q >> 61);                                     // frame
+                k = (k << pos_bits) | (uint64_t)((uint32_t)q / pos_div);
+                ka[j] = (KeyT)k;
+                oa[j] = (uint16_t)j;
+            }
+            __syncwarp();
+            KeyT *src = ka, *dst = kb;
+            uint16_t *osrc = oa, *odst = ob;
+            for (int shift = 0; shift < local_bits; shift += 8) {
+                for (uint32_t k = lane; k < 256; k += 32) hist[k] = 0u;
+                __syncwarp();
+                for (uint32_t j = lane; j < n; j += 32) atomicAdd(&hist[(uint32_t)(src[j] >> shift) & 255u], 1u);
+                __syncwarp();
+                {   // exclusive scan of the 256 counts: 8 bins per lane, shuffle scan of the lane sums
+                    uint32_t c[8], sum = 0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { c[u] = hist[8 * lane + u]; sum += c[u]; }
+                    uint32_t incl = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                    uint32_t run = incl - sum;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { hist[8 * lane + u] = run; run += c[u]; }
+                }
+                __syncwarp();
+                for (uint32_t j0 = 0; j0 < n; j0 += 32) {            // stable: chunks in order, lanes of a chunk ranked by match.any
+                    const uint32_t j = j0 + lane;
+                    const bool active = j < n;
+                    const KeyT k = active ? src[j] : (KeyT)0;
+                    const uint32_t d = active ? ((uint32_t)(k >> shift) & 255u) : (0x10000u | (uint32_t)lane);
+                    const uint32_t same = __match_any_sync(0xffffffffu, d);
+                    const uint32_t rank = __popc(same & lt);
+                    const uint32_t at = active ? hist[d] : 0u;
+                    __syncwarp();
+                    if (active && rank == 0) hist[d] = at + __popc(same);
+                    __syncwarp();
+                    if (active) { dst[at + rank] = k; odst[at + rank] = osrc[j]; }
+                }
+                __syncwarp();
+                { KeyT* x = src; src = dst; dst = x; }
+                { uint16_t* x = osrc; osrc = odst; odst = x; }
+            }
+            // rows that share (species, frame, pos): order by (hamming, dna); the first lane of a run does it (runs of 2-3)
+            auto tie_of = [&](uint16_t o) { const uint64_t w2 = rows[3 * (uint32_t)o + 2]; return ((uint32_t)((w2 >> 48) & 7ull) << 24) | (uint32_t)(w2 & 0xFFFFFFull); };
+            for (uint32_t p = lane; p < n; p += 32) {
+                if ((p == 0 || src[p - 1] != src[p]) && p + 1 < n && src[p + 1] == src[p]) {
+                    uint32_t e = p + 2;
+                    while (e < n && src[e] == src[p]) ++e;
+                    for (uint32_t x = p + 1; x < e; ++x) {
+                        const uint16_t v = osrc[x];
+                        const uint32_t tv = tie_of(v);
+                        uint32_t y = x;
+                        while (y > p && tie_of(osrc[y - 1]) > tv) { osrc[y] = osrc[y - 1]; --y; }
+                        osrc[y] = v;
+                    }
+                }
+            }
+            __syncwarp();
+            // out: 3 n consecutive 8-byte words, word w of the output = word (w % 3) of row osrc[w / 3]
+            uint64_t* d = reinterpret_cast<uint64_t*>(out + b);
+            for (uint32_t w = lane; w < 3 * n; w += 32) {
+                const uint32_t p = w / 3u;
+                d[w] = rows[3 * (uint32_t)osrc[p] + (w - 3 * p)];
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        for (uint32_t p = lane; p < n; p += 32) {
-            const uint64_t* s = reinterpret_cast<const uint64_t*>(in + idx[b + osrc[p]]);
-            uint64_t* d = reinterpret_cast<uint64_t*>(out + b + p);
-            const uint64_t a0 = s[0], a1 = s[1], a2 = s[2];
-            d[0] = a0; d[1] = a1; d[2] = a2;
-        }
-        __syncwarp();
     }
 }
 
 template <class KeyT>
 static void launch_match_order(const mbl_match_rec* in, const uint32_t* idx, const uint64_t* seg_begin, const uint64_t* seg_end, uint32_t n_reads,
                                int pos_bits, uint32_t pos_div, int local_bits, uint64_t max_len, mbl_match_rec* out, cudaStream_t st) {
-    constexpr int kW1 = 8, kW2 = 2;
-    const size_t smem1 = (size_t)kW1 * ((size_t)kOrderSmallRows * (2 * sizeof(KeyT) + 2 * 2 + 4) + 256 * 4);
-    const size_t smem2 = (size_t)kW2 * ((size_t)kOrderMaxRows * (2 * sizeof(KeyT) + 2 * 2 + 4) + 256 * 4);
+    constexpr int kW1 = 4, kW2 = 1;
+    const size_t smem1 = (size_t)kW1 * ((size_t)kOrderSmallRows * (24 + 2 * sizeof(KeyT) + 2 * 2) + 256 * 4);
+    const size_t smem2 = (size_t)kW2 * ((size_t)kOrderMaxRows * (24 + 2 * sizeof(KeyT) + 2 * 2) + 256 * 4);
     MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, 0, kOrderSmallRows, kW1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kOrderSmallRows, kOrderMaxRows, kW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    const unsigned blocks1 = (unsigned)std::min<uint64_t>((n_reads + kW1 - 1) / kW1, 148ull * 32);
+    const unsigned blocks1 = (unsigned)std::min<uint64_t>((n_reads + 32 * kW1 - 1) / (32 * kW1), 148ull * 32);
     match_order_kernel<KeyT, 0, kOrderSmallRows, kW1><<<blocks1, kW1 * 32, smem1, st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits, pos_div, local_bits, out);
     if (max_len > kOrderSmallRows)
         match_order_kernel<KeyT, kOrderSmallRows, kOrderMaxRows, kW2><<<148 * 3, kW2 * 32, smem2, st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits,
