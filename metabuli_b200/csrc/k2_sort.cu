@@ -315,16 +315,22 @@ match_order_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restr
 template <class KeyT>
 static void launch_match_order(const mbl_match_rec* in, const uint32_t* idx, const uint64_t* seg_begin, const uint64_t* seg_end, uint32_t n_reads,
                                int pos_bits, uint32_t pos_div, int local_bits, uint64_t max_len, mbl_match_rec* out, cudaStream_t st) {
-    constexpr int kW1 = 4, kW2 = 1;
-    const size_t smem1 = (size_t)kW1 * ((size_t)kOrderSmallRows * (24 + 2 * sizeof(KeyT) + 2 * 2) + 256 * 4);
-    const size_t smem2 = (size_t)kW2 * ((size_t)kOrderMaxRows * (24 + 2 * sizeof(KeyT) + 2 * 2) + 256 * 4);
-    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, 0, kOrderSmallRows, kW1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kOrderSmallRows, kOrderMaxRows, kW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    // three tiers by rows per read: <= 256 (4 warps per CTA, 10 KB per warp: 20 warps per SM), <= 512 (2 warps per CTA), <= 2048 (1)
+    constexpr int kW1 = 4, kW2 = 2, kW3 = 1;
+    constexpr uint32_t kMid = 512;
+    auto bytes = [](uint32_t rows, int warps) { return (size_t)warps * ((size_t)rows * (24 + 2 * sizeof(KeyT) + 2 * 2) + 256 * 4); };
+    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, 0, kOrderSmallRows, kW1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(kOrderSmallRows, kW1)));
+    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kOrderSmallRows, kMid, kW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(kMid, kW2)));
+    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kMid, kOrderMaxRows, kW3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(kOrderMaxRows, kW3)));
     const unsigned blocks1 = (unsigned)std::min<uint64_t>((n_reads + 32 * kW1 - 1) / (32 * kW1), 148ull * 32);
-    match_order_kernel<KeyT, 0, kOrderSmallRows, kW1><<<blocks1, kW1 * 32, smem1, st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits, pos_div, local_bits, out);
+    match_order_kernel<KeyT, 0, kOrderSmallRows, kW1><<<blocks1, kW1 * 32, bytes(kOrderSmallRows, kW1), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits,
+                                                                                                            pos_div, local_bits, out);
     if (max_len > kOrderSmallRows)
-        match_order_kernel<KeyT, kOrderSmallRows, kOrderMaxRows, kW2><<<148 * 3, kW2 * 32, smem2, st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits,
-                                                                                                      pos_div, local_bits, out);
+        match_order_kernel<KeyT, kOrderSmallRows, kMid, kW2><<<148 * 5, kW2 * 32, bytes(kMid, kW2), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits, pos_div,
+                                                                                                        local_bits, out);
+    if (max_len > kMid)
+        match_order_kernel<KeyT, kMid, kOrderMaxRows, kW3><<<148 * 3, kW3 * 32, bytes(kOrderMaxRows, kW3), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits,
+                                                                                                               pos_div, local_bits, out);
 }
 
 // seg_begin/seg_end per read from the sorted match list (Classifier.cpp:174-185 MatchBlocks)
