@@ -156,8 +156,8 @@ __global__ void match_gather_fix_kernel(const mbl_match_rec* __restrict__ in, co
 // shared-memory atomics, stable ranks from match.any ballots, ~250 warp instructions per pass — orders the rare rows that share
 // that key by (hamming, dna), and writes the rows to their final places.  (Ranking by counting, n^2 / 32 steps, and a bitonic
 // network, ~3 k instructions per read, both lost to the six global passes: 99-106 ms against 74.6 ms.)
-constexpr uint32_t kOrderSmallRows = 256;       // first launch: reads of up to 256 rows, 4 warps per CTA, ~10 KB of shared memory per warp
-constexpr uint32_t kOrderMaxRows = 2048;        // second launch (1 warp per CTA) for the few longer ones; beyond that => single-key path
+constexpr uint32_t kOrderSmallRows = 256;       // the tier most reads with real hits fall into (launch_match_order)
+constexpr uint32_t kOrderMaxRows = 2048;        // rows of one read a warp can order in shared memory; beyond that => single-key path
 
 __global__ void match_seqkey_kernel(const mbl_match_rec* __restrict__ m, size_t n, uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,22 +315,25 @@ match_order_kernel(const mbl_match_rec* __restrict__ in, const uint32_t* __restr
 template <class KeyT>
 static void launch_match_order(const mbl_match_rec* in, const uint32_t* idx, const uint64_t* seg_begin, const uint64_t* seg_end, uint32_t n_reads,
                                int pos_bits, uint32_t pos_div, int local_bits, uint64_t max_len, mbl_match_rec* out, cudaStream_t st) {
-    // three tiers by rows per read: <= 256 (4 warps per CTA, 10 KB per warp: 20 warps per SM), <= 512 (2 warps per CTA), <= 2048 (1)
-    constexpr int kW1 = 4, kW2 = 2, kW3 = 1;
-    constexpr uint32_t kMid = 512;
+    // four tiers by rows per read, so that the many reads with a handful of rows (chance hits only) run at full occupancy and only the
+    // few long ones pay for a large row buffer: <= 64 rows (8 warps per CTA, 2.8 KB per warp), <= 256 (4 warps, 10 KB), <= 512 (2), <= 2048 (1)
+    constexpr uint32_t kTiny = 64, kMid = 512;
     auto bytes = [](uint32_t rows, int warps) { return (size_t)warps * ((size_t)rows * (24 + 2 * sizeof(KeyT) + 2 * 2) + 256 * 4); };
-    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, 0, kOrderSmallRows, kW1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(kOrderSmallRows, kW1)));
-    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kOrderSmallRows, kMid, kW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(kMid, kW2)));
-    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kMid, kOrderMaxRows, kW3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(kOrderMaxRows, kW3)));
-    const unsigned blocks1 = (unsigned)std::min<uint64_t>((n_reads + 32 * kW1 - 1) / (32 * kW1), 148ull * 32);
-    match_order_kernel<KeyT, 0, kOrderSmallRows, kW1><<<blocks1, kW1 * 32, bytes(kOrderSmallRows, kW1), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits,
-                                                                                                            pos_div, local_bits, out);
+    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kTiny, kOrderSmallRows, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(kOrderSmallRows, 4)));
+    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kOrderSmallRows, kMid, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(kMid, 2)));
+    MBL_CUDA(cudaFuncSetAttribute(match_order_kernel<KeyT, kMid, kOrderMaxRows, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes(kOrderMaxRows, 1)));
+    const unsigned blocks0 = (unsigned)std::min<uint64_t>((n_reads + 32 * 8 - 1) / (32 * 8), 148ull * 16);
+    match_order_kernel<KeyT, 0, kTiny, 8><<<blocks0, 8 * 32, bytes(kTiny, 8), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits, pos_div, local_bits, out);
+    const unsigned blocks1 = (unsigned)std::min<uint64_t>((n_reads + 32 * 4 - 1) / (32 * 4), 148ull * 32);
+    if (max_len > kTiny)
+        match_order_kernel<KeyT, kTiny, kOrderSmallRows, 4><<<blocks1, 4 * 32, bytes(kOrderSmallRows, 4), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits,
+                                                                                                              pos_div, local_bits, out);
     if (max_len > kOrderSmallRows)
-        match_order_kernel<KeyT, kOrderSmallRows, kMid, kW2><<<148 * 5, kW2 * 32, bytes(kMid, kW2), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits, pos_div,
-                                                                                                        local_bits, out);
+        match_order_kernel<KeyT, kOrderSmallRows, kMid, 2><<<148 * 5, 2 * 32, bytes(kMid, 2), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits, pos_div,
+                                                                                                  local_bits, out);
     if (max_len > kMid)
-        match_order_kernel<KeyT, kMid, kOrderMaxRows, kW3><<<148 * 3, kW3 * 32, bytes(kOrderMaxRows, kW3), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits,
-                                                                                                               pos_div, local_bits, out);
+        match_order_kernel<KeyT, kMid, kOrderMaxRows, 1><<<148 * 3, 1 * 32, bytes(kOrderMaxRows, 1), st>>>(in, idx, seg_begin, seg_end, n_reads, pos_bits,
+                                                                                                         pos_div, local_bits, out);
 }
 
 // seg_begin/seg_end per read from the sorted match list (Classifier.cpp:174-185 MatchBlocks)
