@@ -167,6 +167,7 @@ struct Params {
     float minScore = 0.f, minSpScore = 0.f, tieRatio = 0.95f;
     size_t batchReads = 0;
     std::vector<int> devices;            // --gpus N (devices 0..N-1) or --devices a,b,c: one replica of the index per device
+    int indexSharded = 0;                // --index-sharded 1: the index is range-partitioned over the devices instead of replicated
     std::vector<std::string> files;
 };
 
@@ -185,6 +186,7 @@ int classify(int argc, char** argv) {
         else if (a == "--accession-level") par.accessionLevel = atoi(val());
         else if (a == "--match-per-kmer") par.matchPerKmer = atoi(val());
         else if (a == "--device") par.device = atoi(val());
+        else if (a == "--index-sharded") par.indexSharded = atoi(val());
         else if (a == "--gpus") { const int n = atoi(val()); if (n < 1 || n > 64) die("--gpus takes 1..64"); par.devices.clear(); for (int d = 0; d < n; ++d) par.devices.push_back(d); }
         else if (a == "--devices") { par.devices.clear(); std::string v = val(); size_t p0 = 0; while (p0 <= v.size()) { size_t c = v.find(',', p0); if (c == std::string::npos) c = v.size(); if (c > p0) par.devices.push_back(atoi(v.substr(p0, c - p0).c_str())); p0 = c + 1; } if (par.devices.empty()) die("--devices takes a comma-separated list"); }
         else if (a == "--batch-reads") par.batchReads = (size_t)atoll(val());
@@ -258,6 +260,9 @@ int classify(int argc, char** argv) {
     mbl_db db{diff.data(), diff.size(), info.data(), info.size(), split.data(), split.size() / 3};
     mbl_taxonomy tx{tax.maxNodes, tax.maxTaxID, tax.eukaryota, tax.D, tax.E, tax.L, tax.H, tax.M, tax.Mk,
                     tax.nodeTaxId.data(), tax.nodeParent.data(), tax.prune.data(), tax.rank.data(), t2s.data()};
+    const bool sharded = par.indexSharded != 0 && G > 1;
+    std::vector<mbl_shard> shards(G);
+    if (sharded && mbl_plan_shards(&db, (uint32_t)G, shards.data()) != MBL_OK) die("mbl_plan_shards failed");
     {
         std::vector<std::thread> loaders;
         std::vector<std::string> lerr(G);
@@ -266,11 +271,22 @@ int classify(int argc, char** argv) {
             cg.device = par.devices[g];
             int rc = mbl_create(&cg, &ctxs[g]);
             if (rc != MBL_OK) { lerr[g] = rc == MBL_E_NO_DEVICE ? "no usable CUDA device " + std::to_string(cg.device) + " (this build has no CPU fallback)" : "mbl_create failed"; return; }
-            rc = mbl_load_db(ctxs[g], &db, &tx);
+            rc = sharded ? mbl_load_db_shard(ctxs[g], &db, &tx, &shards[g]) : mbl_load_db(ctxs[g], &db, &tx);
             if (rc != MBL_OK) lerr[g] = std::string("mbl_load_db: ") + mbl_last_error(ctxs[g]);
         });
         for (auto& t : loaders) t.join();
         for (size_t g = 0; g < G; ++g) if (!lerr[g].empty()) die(lerr[g]);
+    }
+    if (sharded) {
+        // every shard's presence filter covers its own value range only: OR the parts together (each context reads its peers'
+        // filters through peer access; OR-ing a part that already holds other parts changes nothing)
+        std::vector<void*> fptr(G, nullptr);
+        uint64_t fbytes = 0;
+        for (size_t g = 0; g < G; ++g) if (mbl_shard_filter(ctxs[g], &fptr[g], &fbytes) != MBL_OK) die(mbl_last_error(ctxs[g]));
+        for (size_t g = 0; g < G; ++g)
+            for (size_t h = 0; h < G; ++h)
+                if (h != g && fptr[h] && mbl_shard_filter_or(ctxs[g], fptr[h], fbytes, 0) != MBL_OK) die(std::string("mbl_shard_filter_or: ") + mbl_last_error(ctxs[g]));
+        for (size_t g = 0; g < G; ++g) if (mbl_shard_filter_or(ctxs[g], nullptr, fbytes, 1) != MBL_OK) die(mbl_last_error(ctxs[g]));
     }
 
     const unsigned T = par.threads > 0 ? (unsigned)par.threads : std::max(1u, std::thread::hardware_concurrency());
@@ -310,8 +326,10 @@ int classify(int argc, char** argv) {
         const void* pinned[2] = {nullptr, nullptr};
         size_t pinned_cap[2] = {0, 0};
     };
-    const size_t step = par.batchReads ? par.batchReads : (size_t)8000000;
-    const size_t n_batches_in_flight = 2 * G + 2;
+    // index-sharded: a batch is one exchange round over all devices (receive buffers and match buffers are sized by what one
+    // round moves: 1.25 M reads or pairs per device by default)
+    const size_t step = par.batchReads ? par.batchReads : (sharded ? (size_t)1250000 * G : (size_t)8000000);
+    const size_t n_batches_in_flight = sharded ? 4 : 2 * G + 2;
     std::vector<std::unique_ptr<Batch>> pool;
     for (size_t i = 0; i < n_batches_in_flight; ++i) pool.emplace_back(new Batch());
     std::mutex mu;
@@ -380,7 +398,116 @@ int classify(int argc, char** argv) {
         return bt;
     };
     std::vector<std::thread> workers;
-    for (size_t g = 0; g < G; ++g) workers.emplace_back([&, g] {
+    // ---- index-sharded rounds: the batch's reads are cut evenly over the devices; every device thread runs the three
+    // phases of its rank around two exchanges, in lock step through a barrier; the exchanges are the library's push kernels
+    // storing straight into the owners' receive buffers (peer access inside one process), the counts travel through host memory
+    struct Barrier {
+        std::mutex m; std::condition_variable c; size_t n, waiting = 0, gen = 0;
+        explicit Barrier(size_t k) : n(k) {}
+        void wait() { std::unique_lock<std::mutex> lk(m); const size_t g = gen; if (++waiting == n) { waiting = 0; ++gen; c.notify_all(); } else c.wait(lk, [&] { return gen != g; }); }
+    } bar(G);
+    struct Round {
+        Batch* bt = nullptr;
+        std::vector<uint64_t> first_read;                 // [G + 1] read ranges of the ranks
+        std::vector<std::vector<uint64_t>> K, M;          // counts [src][dst]: metamers to shards, matches to read owners
+        std::vector<std::vector<int32_t>> pairs;          // per rank
+        std::vector<size_t> used;
+        std::vector<void*> rk, rm;                        // receive buffers of the ranks
+        uint64_t cap_k = 0, cap_m = 0;
+        bool stop = false;
+    } rd;
+    rd.K.assign(G, std::vector<uint64_t>(G, 0)); rd.M = rd.K; rd.pairs.resize(G); rd.used.assign(G, 0); rd.rk.assign(G, nullptr); rd.rm.assign(G, nullptr);
+    std::vector<uint64_t> first_values(G);
+    for (size_t g = 0; g < G; ++g) first_values[g] = shards[g].first_value;
+    auto ensure_recv = [&](uint64_t need_k, uint64_t need_m) {   // thread 0, between barriers: grow every rank's receive buffers together
+        if (need_k <= rd.cap_k && need_m <= rd.cap_m) return;
+        rd.cap_k = std::max(rd.cap_k, need_k + need_k / 4 + 4096); rd.cap_m = std::max(rd.cap_m, need_m + need_m / 4 + 4096);
+        for (size_t g = 0; g < G; ++g) mbl_shard_detach_peers(ctxs[g]);
+        for (size_t g = 0; g < G; ++g)
+            if (mbl_shard_recv_buffers(ctxs[g], rd.cap_k, rd.cap_m, &rd.rk[g], &rd.rm[g], nullptr, nullptr) != MBL_OK) { fail_with(std::string("mbl_shard_recv_buffers: ") + mbl_last_error(ctxs[g])); return; }
+        for (size_t g = 0; g < G; ++g)
+            for (size_t h = 0; h < G; ++h)
+                if (mbl_shard_attach_peer(ctxs[g], (uint32_t)h, nullptr, nullptr, rd.rk[h], rd.rm[h]) != MBL_OK) { fail_with(std::string("mbl_shard_attach_peer: ") + mbl_last_error(ctxs[g])); return; }
+    };
+    if (sharded) for (size_t g = 0; g < G; ++g) workers.emplace_back([&, g] {
+        mbl_ctx* ctx = ctxs[g];
+        auto check = [&](int rc, const char* what) { if (rc != MBL_OK) fail_with(std::string(what) + ": " + mbl_last_error(ctx)); };
+        while (true) {
+            if (g == 0) {
+                rd.bt = next_ready();
+                rd.stop = rd.bt == nullptr;
+                if (!rd.stop) {
+                    const size_t n = rd.bt->r1.size();
+                    rd.first_read.assign(G + 1, 0);
+                    for (size_t k = 0; k <= G; ++k) rd.first_read[k] = n * k / G;
+                    rd.bt->res.assign(n, mbl_read_result{});
+                }
+            }
+            bar.wait();
+            if (rd.stop || failed) return;
+            Batch* bt = rd.bt;
+            const uint64_t r0 = rd.first_read[g], r1 = rd.first_read[g + 1];
+            // this rank's reads as a batch of their own (offsets rebased)
+            std::vector<uint64_t> o1(r1 - r0 + 1), o2;
+            for (uint64_t k = 0; k <= r1 - r0; ++k) o1[k] = bt->r1.offsets[r0 + k] - bt->r1.offsets[r0];
+            mbl_batch b{};
+            b.bases = bt->r1.bases.data() + bt->r1.offsets[r0]; b.offsets = o1.data(); b.n_reads = (uint32_t)(r1 - r0);
+            if (par.seqMode == 2) {
+                o2.resize(r1 - r0 + 1);
+                for (uint64_t k = 0; k <= r1 - r0; ++k) o2[k] = bt->r2.offsets[r0 + k] - bt->r2.offsets[r0];
+                b.bases2 = bt->r2.bases.data() + bt->r2.offsets[r0]; b.offsets2 = o2.data();
+            }
+            check(mbl_shard_extract(ctx, &b, r0, (uint32_t)G, first_values.data(), rd.K[g].data()), "mbl_shard_extract");
+            bar.wait();
+            if (failed) return;
+            std::vector<uint64_t> tot(G, 0), off(G, 0);
+            for (size_t h = 0; h < G; ++h) for (size_t src = 0; src < G; ++src) { tot[h] += rd.K[src][h]; if (src < g) off[h] += rd.K[src][h]; }
+            if (g == 0) ensure_recv(*std::max_element(tot.begin(), tot.end()), 0);
+            bar.wait();
+            if (failed) return;
+            check(mbl_shard_push_kmers(ctx, off.data(), tot.data()), "mbl_shard_push_kmers");
+            bar.wait();
+            if (failed) return;
+            const uint64_t nk = tot[g];
+            check(mbl_shard_match(ctx, (const uint64_t*)rd.rk[g], (const uint64_t*)rd.rk[g] + nk, nk, (uint32_t)G, rd.first_read.data(), rd.M[g].data()), "mbl_shard_match");
+            bar.wait();
+            if (failed) return;
+            std::fill(tot.begin(), tot.end(), 0); std::fill(off.begin(), off.end(), 0);
+            for (size_t h = 0; h < G; ++h) for (size_t src = 0; src < G; ++src) { tot[h] += rd.M[src][h]; if (src < g) off[h] += rd.M[src][h]; }
+            if (g == 0) ensure_recv(0, *std::max_element(tot.begin(), tot.end()));
+            bar.wait();
+            if (failed) return;
+            check(mbl_shard_push_matches(ctx, off.data()), "mbl_shard_push_matches");
+            bar.wait();
+            if (failed) return;
+            check(mbl_shard_score(ctx, (const mbl_match_rec*)rd.rm[g], tot[g]), "mbl_shard_score");
+            std::vector<int32_t>& pr = rd.pairs[g];
+            if (pr.size() < 10 * (r1 - r0) + 32) pr.assign(10 * (r1 - r0) + 32, 0);
+            int rc = mbl_download_results(ctx, bt->res.data() + r0, pr.data(), pr.size() / 2, &rd.used[g]);
+            if (rc == MBL_E_CAPACITY) { pr.assign(2 * (rd.used[g] + 16), 0); rc = mbl_download_results(ctx, bt->res.data() + r0, pr.data(), pr.size() / 2, &rd.used[g]); }
+            check(rc, "mbl_download_results");
+            mbl_stats st;
+            mbl_get_stats(ctx, &st);
+            { std::lock_guard<std::mutex> lk(mu); matches += st.n_matches; kmers += st.n_query_kmers; }
+            bar.wait();
+            if (failed) return;
+            if (g == 0) {                                   // the ranks' pair lists behind one another, offsets re-based
+                size_t total = 0;
+                for (size_t h = 0; h < G; ++h) total += rd.used[h];
+                bt->pairs.assign(2 * total + 2, 0);
+                size_t base = 0;
+                for (size_t h = 0; h < G; ++h) {
+                    if (rd.used[h]) memcpy(bt->pairs.data() + 2 * base, rd.pairs[h].data(), 8 * rd.used[h]);
+                    for (uint64_t r = rd.first_read[h]; r < rd.first_read[h + 1]; ++r) bt->res[r].taxcnt_begin += (uint32_t)base;
+                    base += rd.used[h];
+                }
+                bt->used = total;
+                { std::lock_guard<std::mutex> lk(mu); finished[bt->index] = bt; }
+                cv.notify_all();
+            }
+        }
+    });
+    else for (size_t g = 0; g < G; ++g) workers.emplace_back([&, g] {
         mbl_ctx* ctx = ctxs[g];
         Batch* cur = next_ready();
         if (cur && mbl_prefetch_batch(ctx, &cur->b) != MBL_OK) { fail_with(std::string("mbl_prefetch_batch: ") + mbl_last_error(ctx)); return; }
@@ -447,8 +574,8 @@ int classify(int argc, char** argv) {
     }
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     (void)tl0;
-    printf("Query k-mer number     : %llu\nTotal k-mer match count: %llu\nTaxonomic classification completed on %zu GPU(s). (%.3f s)\n",
-           (unsigned long long)kmers, (unsigned long long)matches, G, sec);
+    printf("Query k-mer number     : %llu\nTotal k-mer match count: %llu\nTaxonomic classification completed on %zu GPU(s)%s. (%.3f s)\n",
+           (unsigned long long)kmers, (unsigned long long)matches, G, sharded ? ", index sharded" : "", sec);
     for (auto& p : pool) for (int k = 0; k < 2; ++k) if (p->pinned[k]) mbl_host_unregister(const_cast<void*>(p->pinned[k]));
     for (mbl_ctx* c : ctxs) mbl_destroy(c);
     return 0;
@@ -460,7 +587,7 @@ int main(int argc, char** argv) {
     if (argc < 2 || strcmp(argv[1], "classify") != 0) {
         fprintf(stderr, "usage: %s classify [--seq-mode 1|2|3] [--min-score F] [--min-sp-score F] [--tie-ratio F] [--min-cons-cnt N]\n"
                         "          [--min-cons-cnt-euk N] [--accession-level N] [--lineage 0|1] [--match-per-kmer N] [--device N]\n"
-                        "          [--gpus N | --devices a,b,...] [--batch-reads N] [--threads N]\n"
+                        "          [--gpus N | --devices a,b,...] [--index-sharded 0|1] [--batch-reads N] [--threads N]\n"
                         "          <fastx> [<fastx2>] <dbdir> <outdir> <jobid>\n", argv[0]);
         return 2;
     }

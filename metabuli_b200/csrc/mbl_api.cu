@@ -1226,6 +1226,23 @@ int mbl_classify_prefetched(mbl_ctx* c, const mbl_batch* next, mbl_read_result* 
 }
 
 // ---- index-sharded mode: the phases one rank runs around the two exchanges (include/metabuli_b200.h) ---------------------
+namespace {
+// same-process ranks hand each other raw device pointers: a kernel of this context may only touch memory of another device
+// after peer access is enabled from this context's device (cross-process peers come through cudaIpcOpenMemHandle, which does it)
+void enable_peer_for(mbl_ctx* c, const void* p) {
+    if (!p) return;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+    if (at.type != cudaMemoryTypeDevice || at.device == c->cfg.device) return;
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, c->cfg.device, at.device);
+    if (!can) throw CudaError{cudaErrorPeerAccessUnsupported, __FILE__, __LINE__};
+    cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) throw CudaError{e, __FILE__, __LINE__};
+    cudaGetLastError();
+}
+}  // namespace
+
 int mbl_shard_filter(mbl_ctx* c, void** d_words, uint64_t* n_bytes) {
     if (!c || !d_words || !n_bytes) return fail(c, MBL_E_BAD_ARG, "null argument");
     *d_words = c->dir.filter;
@@ -1239,6 +1256,7 @@ int mbl_shard_filter_or(mbl_ctx* c, const void* d_other, uint64_t n_bytes, int c
     if (d_other && n_bytes != 128ull * c->dir.filter_lines) return fail(c, MBL_E_BAD_ARG, "filter sizes differ between the ranks");
     try {
         MBL_CUDA(cudaSetDevice(c->cfg.device));
+        enable_peer_for(c, d_other);
         if (d_other) launch_filter_or(c->dir.filter, (const uint32_t*)d_other, n_bytes / 4, c->st);
         MBL_CUDA(cudaStreamSynchronize(c->st));
         MBL_CUDA(cudaGetLastError());
@@ -1455,7 +1473,7 @@ int mbl_shard_attach_peer(mbl_ctx* c, uint32_t peer, const uint8_t* handle_kmers
             opened = false; slot = nullptr;
             void* raw = k ? raw_matches : raw_kmers;
             const uint8_t* h = k ? handle_matches : handle_kmers;
-            if (raw) { slot = raw; continue; }                       // same process (or this rank itself)
+            if (raw) { enable_peer_for(c, raw); slot = raw; continue; }   // same process (or this rank itself)
             if (!h) return fail(c, MBL_E_BAD_ARG, "neither a handle nor a pointer for the peer buffer");
             cudaIpcMemHandle_t hh;
             memcpy(&hh, h, sizeof hh);

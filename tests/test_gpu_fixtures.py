@@ -135,3 +135,24 @@ def test_cpp_host_multi_replica_keeps_the_read_order(devices, batch, fixtures_di
     report = gzip.open(os.path.join(golden_dir, "ref_tsv", "in_pe_report.tsv.gz"), "rb").read()
     assert open(tmp_path / "job_report.tsv", "rb").read() == report
     assert "Total read count : 5000" in r.stdout and f"on {len(devices.split(','))} GPU(s)" in r.stdout
+
+
+@pytest.mark.parametrize("devices,batch,db,mode", [("0,0", 1700, "in", "pe"), ("0,0,0", 0, "ex", "se"), ("0,0,0,0", 640, "in", "se")])
+def test_cpp_host_index_sharded(devices, batch, db, mode, fixtures_dir, golden_dir, tmp_path):
+    """`--index-sharded 1`: the C++ host cuts the index into one value range per device (mbl_plan_shards), ORs the shards' presence
+    filters, and runs every batch as one exchange round — extract + bucket, push metamers to the owning shard, match, push matches
+    back to the read owner, score — with one thread per device in lock step.  Several contexts on device 0 exercise the whole
+    protocol (peer pointers inside one process) on a one-GPU box; the TSV must be the reference's."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "metabuli_b200", "_lib", "metabuli-b200")
+    reads = [os.path.join(fixtures_dir, "reads", f"ERR9594652_5000_{k}.fna.gz") for k in ((1, 2) if mode == "pe" else (1,))]
+    cmd = [exe, "classify", "--seq-mode", "2" if mode == "pe" else "1", "--threads", "3", "--devices", devices, "--index-sharded", "1"]
+    if batch:
+        cmd += ["--batch-reads", str(batch)]
+    cmd += reads + [os.path.join(fixtures_dir, f"db_{db}"), str(tmp_path), "job"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    golden = gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_classifications.tsv.gz"), "rb").read()
+    assert open(tmp_path / "job_classifications.tsv", "rb").read() == golden
+    assert "index sharded" in r.stdout and "Total read count : 5000" in r.stdout
