@@ -220,8 +220,28 @@ def cpu_arm(sdb, reads, n_sample, threads, steps, warmup, budget_s=240.0, keep_r
                     n_cur = max(100_000, int(n_cur * budget_s / (dt * left)))
             if keep_results:
                 tsv = open(os.path.join(work, "job_classifications.tsv"), "rb").read()
+            cli = None
+            cli_exe = os.path.join(ROOT, "metabuli_b200", "_lib", "metabuli-b200")
+            if keep_results and os.path.exists(cli_exe):
+                # the product's own C++ host on the very same files (database directory and FASTA the reference just read):
+                # byte comparison of the two <jobid>_classifications.tsv and of the two <jobid>_report.tsv
+                t0 = time.perf_counter()
+                r = subprocess.run([cli_exe, "classify", "--seq-mode", "1", "--threads", str(threads), q, db_dir, work, "b200"],
+                                   capture_output=True, text=True)
+                dt = time.perf_counter() - t0
+                cli = {"rc": r.returncode, "seconds_whole_run": round(dt, 2)}
+                if r.returncode == 0:
+                    cli["tsv_equal"] = open(os.path.join(work, "b200_classifications.tsv"), "rb").read() == tsv
+                    cli["report_equal"] = open(os.path.join(work, "b200_report.tsv"), "rb").read() == open(os.path.join(work, "job_report.tsv"), "rb").read()
+                    for ln in r.stdout.split("\n"):
+                        if "classification completed" in ln and "(" in ln:
+                            cli["seconds_classify"] = float(ln.split("(")[-1].split()[0])
+                    cli["reads"] = secs[-1][0]
+                    cli["note"] = "metabuli-b200 classify (C++ host + libmetabuli_b200.so) on the database directory and FASTA the reference binary read; whole run includes loading the index from disk"
+                else:
+                    cli["error"] = (r.stdout + r.stderr)[-300:]
             n_reads = sum(x for x, _ in secs)
-            return dict(n=secs[-1][0], rate=n_reads / sum(t for _, t in secs), secs=[t for _, t in secs], kind="reference", tsv=tsv,
+            return dict(n=secs[-1][0], rate=n_reads / sum(t for _, t in secs), secs=[t for _, t in secs], kind="reference", tsv=tsv, cli=cli,
                         sample=f"first {secs[-1][0]} reads of the step's batch per pass, `metabuli classify --threads {threads}` "
                                f"(unmodified reference binary, whole CLI run incl. FASTA parse and TSV write, database in the page cache)")
         finally:
@@ -672,6 +692,8 @@ def main():
             cpu = {"value": arm["rate"], "unit": "reads/s", "cores": threads, "kind": arm["kind"], "sample": arm["sample"] + "; one warm-up pass, one timed pass"}
             # the only parity evidence at benchmark scale: the timed batch's GPU results for the sample reads == the reference's
             parity = parity_sample(clf, arm, out, pairs[: used.value])
+            if parity is not None and arm.get("cli") is not None:
+                parity["cpp_host_cli"] = arm["cli"]
         except Exception as e:  # the baseline is a reported number, never a reason to fail the bench
             cpu = {"value": None, "unit": "reads/s", "cores": threads, "kind": "reference" if os.path.exists(REF_BIN) else "port", "sample": f"failed: {e}"}
 
