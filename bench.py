@@ -402,6 +402,7 @@ def sharded_leg(args, rank, local_rank, world, dist):
     note(f"warm-up done, {n_rounds} exchange round(s) per step")
     sampler = ClockSampler(local_rank)
     nv0 = nvlink_tx_rx_kib(local_rank) if rank == 0 else None
+    barrier()                                    # rank 0 just spent ~0.5 s in nvidia-smi: nobody's clock starts before everybody is here
     t0 = time.perf_counter()
     for _ in range(args.steps):
         _, recv_kmers, n_matches = one_step(True)
