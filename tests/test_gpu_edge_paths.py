@@ -124,3 +124,29 @@ def test_no_presence_filter(golden_dir, monkeypatch):
     clf.close()
     assert st["n_merge_queries"] == st["n_query_kmers"]
     assert tsv == _golden(golden_dir, "multi_pe")
+
+
+@pytest.mark.parametrize("name", ["multi_pe", "ties_se", "format1_pe", "sync_se"])
+@pytest.mark.parametrize("knob", ["MBL_SORT_FULLKEY", "MBL_TEST_TWO_PASS_SORT"])
+def test_match_ordering_fallbacks(name, knob, golden_dir, monkeypatch):
+    """K4 has three ways to reach compareMatches' order: the default (radix sort by read + per-read ordering in shared memory), the
+    single 64-bit-key radix sort that batches with very long reads fall back to (MBL_SORT_FULLKEY=1 forces it), and two stable
+    passes for batches whose packed key would not fit 64 bits (2^29 reads of extreme length; MBL_TEST_TWO_PASS_SORT=1 forces it).
+    The env knobs are read once per process, so every combination runs in a process of its own."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import gzip, os, sys
+sys.path.insert(0, {os.path.join(root, 'tests')!r}); sys.path.insert(0, {root!r})
+import synth_cases
+from metabuli_b200 import Classifier, ClassifyOptions
+sdb, reads, seq_mode = synth_cases.build({name!r})
+clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
+res, pairs = clf.classify_batch(*reads)
+tsv = clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode()
+golden = gzip.open(os.path.join({golden_dir!r}, "synth", {name!r} + ".tsv.gz"), "rb").read()
+sys.exit(0 if tsv == golden else 3)
+"""
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **{knob: "1"}), timeout=300, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
