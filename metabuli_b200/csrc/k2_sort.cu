@@ -412,6 +412,7 @@ bool sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
     const int seq_bits = bits_for(n_reads);
     const uint32_t pos_div = codon_spaced ? 3u : 1u;     // true for matches produced by K3 (see match_fullkey_kernel)
     const int pos3_bits = bits_for(max_pos / pos_div);
+    static const bool force_two_pass = getenv("MBL_TEST_TWO_PASS_SORT") && atoi(getenv("MBL_TEST_TWO_PASS_SORT")) != 0;   // tests: keys wider than 64 bits
     static const bool force_fullkey = getenv("MBL_SORT_FULLKEY") && atoi(getenv("MBL_SORT_FULLKEY")) != 0;   // tests / A-B: the single-key path
     const int local_bits = sp_bits + 3 + pos3_bits;
     if (seg_begin && seg_end && !force_fullkey && !force_two_pass && local_bits <= 40) {
@@ -437,7 +438,6 @@ bool sort_matches(void* tmp, size_t tmp_bytes, const mbl_match_rec* in, mbl_matc
         }
         // a read with more rows than a warp orders in shared memory (long reads): the single-key path below redoes the order
     }
-    static const bool force_two_pass = getenv("MBL_TEST_TWO_PASS_SORT") && atoi(getenv("MBL_TEST_TWO_PASS_SORT")) != 0;   // tests: keys wider than 64 bits
     if (seq_bits + sp_bits + 3 + pos3_bits <= 64 && !force_two_pass) {
         match_fullkey_kernel<<<blocks, 256, 0, st>>>(in, n, sp_bits, pos3_bits, pos_div, key_a, idx_a);
         cub::DoubleBuffer<uint64_t> k(key_a, key_b);
