@@ -204,9 +204,9 @@ __global__ void merge_item_fill_kernel(const Tile* __restrict__ tiles, uint64_t 
 //           survivors into its staging buffer and write the rows out as contiguous 8-byte words.
 // A round takes up to 2 * kThreads queries and 8 * kThreads pairs; a round with more pairs (a hot amino-acid group) walks the
 // pair range in windows and recomputes the sums in pass 2.  Jumbo items (an amino-acid group larger than a shared-memory tile:
-// values pre-decoded in HBM) take a plain lane-per-query path.
+// values pre-decoded in HBM) run the same passes over HBM-resident values, their queries finding the group by binary search.
 struct SmemLayout2 {
-    uint32_t off_rec, off_scan, off_ham, off_hg, off_hp, off_hm, off_hq, off_owner, off_psum, off_stage, off_bits, off_frag, off_info, off_vals,
+    uint32_t off_rec, off_scan, off_ham, off_hg, off_hl, off_hp, off_hm, off_hq, off_owner, off_psum, off_stage, off_bits, off_frag, off_info, off_vals,
         off_tab, total;
 };
 __host__ __device__ inline SmemLayout2 smem_layout2(uint32_t max_u16, uint32_t max_kmers, uint32_t n_buckets, uint32_t kThreads) {
@@ -217,7 +217,8 @@ __host__ __device__ inline SmemLayout2 smem_layout2(uint32_t max_u16, uint32_t m
     l.off_scan = o;   o += 2 * 2 * kWarps * 8;         // block_decode cross-warp scan
     l.off_ham = o;    o += 8192;                       // two-codon table
     l.off_hq = o;     o += kQR * 8;                    // hit list: qinfo
-    l.off_hg = o;     o += kQR * 4;                    //           group start | length << 16
+    l.off_hg = o;     o += kQR * 4;                    //           group start
+    l.off_hl = o;     o += kQR * 4;                    //           group length
     l.off_hp = o;     o += kQR * 4;                    //           first pair of the hit
     l.off_hm = o;     o += kQR * 4;                    //           minimum Hamming sum << 24 | query DNA part
     l.off_owner = o;  o += kPC * 2;                    // pair -> hit
@@ -252,6 +253,7 @@ merge_kernel_v2(MergeArgs a) {
     uint16_t* s_ham = reinterpret_cast<uint16_t*>(smem + L.off_ham);
     uint64_t* s_hq = reinterpret_cast<uint64_t*>(smem + L.off_hq);
     uint32_t* s_hg = reinterpret_cast<uint32_t*>(smem + L.off_hg);
+    uint32_t* s_hl = reinterpret_cast<uint32_t*>(smem + L.off_hl);
     uint32_t* s_hp = reinterpret_cast<uint32_t*>(smem + L.off_hp);
     uint32_t* s_hm = reinterpret_cast<uint32_t*>(smem + L.off_hm);
     uint16_t* s_owner = reinterpret_cast<uint16_t*>(smem + L.off_owner);
@@ -354,60 +356,19 @@ merge_kernel_v2(MergeArgs a) {
         if (warp == 1 && lane < 4 && next_item < n_items)     // next item's record, four 16-byte words
             cp_async16(reinterpret_cast<unsigned char*>(s_rec + (slot ^ 1)) + 16 * lane,
                        reinterpret_cast<const unsigned char*>(a.items + next_item) + 16 * lane);
+        const uint64_t* vals;
+        const int32_t* infos;
+        uint64_t qv_first = kBlank;
         if (jumbo) {
+            // an amino-acid group larger than a shared-memory tile: values pre-decoded in HBM at load, taxids read from HBM; no
+            // hash table — a query finds its group with two binary searches — but the same balanced pair passes as a tile, so a
+            // group of 10^5 candidates (a universally conserved 8-mer of a large index) is spread over all threads, window by window
             if (warp == 1 && lane < 4) cp_async_wait_all();
             __syncthreads();
             if (tid == 0 && next_item < n_items) stage_frag(s_rec[slot ^ 1]);
-            // lane per query over the pre-decoded values in HBM: binary search for the group, one walk for the minimum, one for the
-            // survivors (every lane steps to its next surviving candidate, the warp writes those rows together)
-            const uint64_t* vals = a.jumbo_vals + it.jumbo_off;
-            const int32_t* infos = a.info + it.info_begin;
-            const uint32_t n_chunks = (uint32_t)((it.q_end - it.q_begin + 31) >> 5);
-            for (uint32_t ch = (uint32_t)warp; ch < n_chunks; ch += kWarps) {
-                const uint64_t qi = it.q_begin + (uint64_t)ch * 32 + lane;
-                const bool active = qi < it.q_end;
-                const uint64_t qv = active ? ld_stream_u64(a.q_value + qi) : kBlank;
-                const uint64_t q40 = qv >> 24;
-                const uint32_t qd = (uint32_t)qv & 0xFFFFFFu;
-                uint32_t g0 = 0;
-                bool hit = false;
-                if (active) {
-                    uint32_t lo = 0, hi = nk;
-                    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((vals[mid] >> 24) < q40) lo = mid + 1; else hi = mid; }
-                    if (lo < nk && (vals[lo] >> 24) == q40) { g0 = lo; hit = true; }
-                }
-                if (!__any_sync(kFull, hit)) continue;
-                uint64_t qinfo = 0;
-                uint32_t end = g0, best = 255u;
-                if (hit) {
-                    qinfo = via_idx ? a.q_info[a.q_idx[qi]] : a.q_info[qi];
-                    while (end < nk && (vals[end] >> 24) == q40) {
-                        const uint32_t td = (uint32_t)vals[end] & 0xFFFFFFu;
-                        best = min(best, td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td)));
-                        ++end;
-                    }
-                }
-                const uint32_t limit = min(best * 2u, 7u);                 // KmerMatcher.cpp:1136
-                uint32_t j = g0;
-                while (true) {
-                    uint32_t td = 0, sum = 255u;
-                    while (j < end) {                                      // this lane's next surviving candidate
-                        td = (uint32_t)vals[j] & 0xFFFFFFu;
-                        sum = td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td));
-                        if (sum <= limit) break;
-                        ++j;
-                    }
-                    const bool sel = j < end;
-                    if (!__any_sync(kFull, sel)) break;
-                    emit(sel, qinfo, sel ? infos[j] : 0, qd, td, sum);
-                    if (sel) ++j;
-                }
-            }
-            __syncthreads();
-            item = next_item;
-            slot ^= 1;
-            continue;
-        }
+            vals = a.jumbo_vals + it.jumbo_off;
+            infos = a.info + it.info_begin;
+        } else {
         for (uint32_t x = tid; x < a.n_buckets / 4; x += kThreads) reinterpret_cast<uint4*>(s_tab)[x] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
         // the first round's queries: pull this thread's second query (and both qinfo words) towards L2 now, load the first one
         // into a register after the decode — the probe then starts without a cold DRAM miss
@@ -434,7 +395,6 @@ merge_kernel_v2(MergeArgs a) {
         if (warp == 1 && lane < 4) cp_async_wait_all();
         __syncthreads();
         if (tid == 0 && next_item < n_items) stage_frag(s_rec[slot ^ 1]);      // streams in during the match phase
-        uint64_t qv_first = kBlank;
         if (it.q_begin + (uint64_t)tid < it.q_end) qv_first = ld_stream_u64(a.q_value + it.q_begin + tid);
         // -- 2b. amino-acid group starts: bitmap + hash table (the table was cleared before the decode barriers)
         for (uint32_t base = (uint32_t)warp * 32; base < nw * 32; base += kThreads) {
@@ -461,22 +421,33 @@ merge_kernel_v2(MergeArgs a) {
         mbar_wait(mbar + 1, (parity_bits >> 1) & 1u);
         parity_bits ^= 2u;
         __syncthreads();
-        const uint64_t* vals = s_vals;
-        const int32_t* infos = s_info + (it.info_begin & 3ull);
+        vals = s_vals;
+        infos = s_info + (it.info_begin & 3ull);
+        }
 
-        // -- 3. rounds of up to kQR queries
-        for (uint64_t r0 = it.q_begin; r0 < it.q_end; r0 += kQR) {
-            const uint32_t nq = (uint32_t)min((uint64_t)kQR, it.q_end - r0);
+        // -- 3. rounds of up to kQR queries (a jumbo item: few enough that hits x group length stays below 2^31 pairs)
+        const uint32_t round_q = jumbo ? max(1u, min(kQR, 0x7FFFFFFFu / max(nk, 1u))) : kQR;
+        for (uint64_t r0 = it.q_begin; r0 < it.q_end; r0 += round_q) {
+            const uint32_t nq = (uint32_t)min((uint64_t)round_q, it.q_end - r0);
             // probe: hit list + owner slots of the first pair window
             for (uint32_t qb = (uint32_t)warp * 32; qb < nq; qb += kThreads) {
                 const uint32_t q = qb + lane;
                 const bool active = q < nq;
                 const uint64_t qi = r0 + q;
-                const uint64_t qv = (r0 == it.q_begin && qb == (uint32_t)warp * 32) ? qv_first : (active ? ld_stream_u64(a.q_value + qi) : kBlank);
+                const uint64_t qv = (!jumbo && r0 == it.q_begin && qb == (uint32_t)warp * 32) ? qv_first : (active ? ld_stream_u64(a.q_value + qi) : kBlank);
                 const uint64_t q40 = qv >> 24;
-                uint32_t g0 = 0;
+                uint32_t g0 = 0, len = 0;
                 bool hit = false;
-                if (active) {
+                if (active && jumbo) {
+                    uint32_t lo = 0, hi = nk;
+                    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((vals[mid] >> 24) < q40) lo = mid + 1; else hi = mid; }
+                    if (lo < nk && (vals[lo] >> 24) == q40) {
+                        g0 = lo; hit = true;
+                        hi = nk;
+                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((vals[mid] >> 24) <= q40) lo = mid + 1; else hi = mid; }
+                        len = lo - g0;
+                    }
+                } else if (active) {
                     const uint32_t h = aa_hash(q40);
                     const uint32_t tag = h & 0x7FFFFu;
                     uint32_t bkt = h >> hash_shift;
@@ -492,15 +463,15 @@ merge_kernel_v2(MergeArgs a) {
                 const uint32_t bal = __ballot_sync(kFull, hit);
                 if (!bal) continue;
                 uint64_t qinfo = 0;
-                uint32_t len = 0;
                 if (hit) {
                     qinfo = via_idx ? a.q_info[a.q_idx[qi]] : ld_stream_u64(a.q_info + qi);
-                    // group length = distance to the next group start
-                    uint32_t w = (g0 + 1) >> 5;
-                    uint32_t bits = w < nw ? s_bits[w] & (0xffffffffu << ((g0 + 1) & 31)) : 0u;
-                    while (!bits && ++w < nw) bits = s_bits[w];
-                    const uint32_t nxt = bits ? (w << 5) + (uint32_t)__ffs(bits) - 1u : nk;
-                    len = min(nxt, nk) - g0;
+                    if (!jumbo) {                                   // group length = distance to the next group start
+                        uint32_t w = (g0 + 1) >> 5;
+                        uint32_t bits = w < nw ? s_bits[w] & (0xffffffffu << ((g0 + 1) & 31)) : 0u;
+                        while (!bits && ++w < nw) bits = s_bits[w];
+                        const uint32_t nxt = bits ? (w << 5) + (uint32_t)__ffs(bits) - 1u : nk;
+                        len = min(nxt, nk) - g0;
+                    }
                 }
                 uint32_t incl = len;
 #pragma unroll
@@ -514,7 +485,8 @@ merge_kernel_v2(MergeArgs a) {
                     const uint32_t h = hb + (uint32_t)__popc(bal & lt);
                     const uint32_t pbase = pb + incl - len;
                     s_hq[h] = qinfo;
-                    s_hg[h] = g0 | (len << 16);
+                    s_hg[h] = g0;
+                    s_hl[h] = len;
                     s_hp[h] = pbase;
                     s_hm[h] = 0xFF000000u | ((uint32_t)qv & 0xFFFFFFu);
                     for (uint32_t p = pbase, e = min(pbase + len, kPC); p < e; ++p) s_owner[p] = (uint16_t)h;
@@ -525,7 +497,7 @@ merge_kernel_v2(MergeArgs a) {
             // pair p of the window starting at w0 -> (hit o, candidate j)
             auto fill = [&](uint32_t w0) {
                 for (uint32_t h = tid; h < nh; h += kThreads) {
-                    const uint32_t pbase = s_hp[h], len = s_hg[h] >> 16;
+                    const uint32_t pbase = s_hp[h], len = s_hl[h];
                     const uint32_t b = max(pbase, w0), e = min(pbase + len, w0 + kPC);
                     for (uint32_t p = b; p < e; ++p) s_owner[p - w0] = (uint16_t)h;
                 }
@@ -534,7 +506,7 @@ merge_kernel_v2(MergeArgs a) {
                 const uint32_t wend = min(np, w0 + kPC);
                 for (uint32_t p = w0 + tid; p < wend; p += kThreads) {
                     const uint32_t o = s_owner[p - w0];
-                    const uint32_t j = (s_hg[o] & 0xFFFFu) + (p - s_hp[o]);
+                    const uint32_t j = s_hg[o] + (p - s_hp[o]);
                     const uint32_t qd = s_hm[o] & 0xFFFFFFu;
                     const uint32_t td = (uint32_t)vals[j] & 0xFFFFFFu;
                     const uint32_t sum = td == qd ? 0u : ham_sum(ham_lookup(s_ham, qd, td));
@@ -550,7 +522,7 @@ merge_kernel_v2(MergeArgs a) {
                     bool sel = false;
                     if (p < wend) {
                         o = s_owner[p - w0];
-                        j = (s_hg[o] & 0xFFFFu) + (p - s_hp[o]);
+                        j = s_hg[o] + (p - s_hp[o]);
                         const uint32_t mq = s_hm[o];
                         qd = mq & 0xFFFFFFu;
                         td = (uint32_t)vals[j] & 0xFFFFFFu;
