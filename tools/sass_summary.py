@@ -67,7 +67,7 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_sass_summary.md"), "w") as f:
     f.write("| kernel | regs | smem (static) | SASS instr | " + " | ".join(OPS[:9]) + " | LDS | STS | LDG | STG |\n|---|---|---|---|" + "---|" * 13 + "\n")
     for k in own:
         u = usage.get(k, {})
-        name = re.sub(r"\(.*", "", demangle(k)).replace("mbl::", "").replace("(anonymous namespace)::", "")[:60]
+        name = re.sub(r"\(.*", "", demangle(k).replace("(anonymous namespace)::", "")).replace("mbl::", "")[:60]
         c = counts[k]
         f.write(f"| `{name}` | {u.get('REG', '?')} | {u.get('SHARED', '?')} | {total[k]} | " + " | ".join(str(c[o]) for o in OPS[:9]) +
                 f" | {c['LDS']} | {c['STS']} | {c['LDG']} | {c['STG']} |\n")
