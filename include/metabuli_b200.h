@@ -216,6 +216,11 @@ int  mbl_shard_detach_peers(mbl_ctx* ctx);      /* unmap every peer buffer (befo
 int  mbl_shard_push_kmers(mbl_ctx* ctx, const uint64_t* dst_row_offset, const uint64_t* dst_total_rows);
 int  mbl_shard_push_matches(mbl_ctx* ctx, const uint64_t* dst_row_offset);
 
+/* `--mask 1` (KmerExtractor.cpp:308-314, SeqIterator::maskLowComplexityRegions, SeqIterator.cpp:154-175): tantan's repeat
+ * probability per letter of every read; letters at or above mask_prob (and letters that are not nucleotides) become 'N' in
+ * place.  Host work (no device needed); call it on a batch before mbl_classify_batch / mbl_prefetch_batch. */
+int  mbl_mask_reads(char* bases, const uint64_t* offsets, uint32_t n_reads, float mask_prob, int threads);
+
 /* Pin / unpin a caller buffer (cudaHostRegister) so the copies inside mbl_classify_batch run at PCIe
  * speed; purely an optimisation, pageable buffers work too. */
 int  mbl_host_register(void* ptr, size_t bytes);

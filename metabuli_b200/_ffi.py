@@ -92,7 +92,7 @@ EXPORTS = ["mbl_create", "mbl_destroy", "mbl_last_error", "mbl_load_db", "mbl_cl
            "mbl_score", "mbl_get_stats", "mbl_get_db_info", "mbl_host_register", "mbl_host_unregister",
            "mbl_plan_shards", "mbl_load_db_shard", "mbl_shard_extract", "mbl_shard_match", "mbl_shard_score",
            "mbl_shard_pack_kmers", "mbl_shard_pack_matches", "mbl_shard_recv_buffers", "mbl_shard_attach_peer", "mbl_shard_detach_peers", "mbl_shard_push_kmers",
-           "mbl_shard_push_matches", "mbl_shard_filter", "mbl_shard_filter_or"]
+           "mbl_shard_push_matches", "mbl_shard_filter", "mbl_shard_filter_or", "mbl_mask_reads"]
 
 _lib = None
 
@@ -140,6 +140,7 @@ def load_library() -> C.CDLL:
     lib.mbl_shard_push_matches.argtypes = [vp, vp]
     lib.mbl_shard_filter.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     lib.mbl_shard_filter_or.argtypes = [vp, vp, C.c_uint64, C.c_int]
+    lib.mbl_mask_reads.argtypes = [vp, vp, C.c_uint32, C.c_float, C.c_int]
     lib.mbl_host_register.argtypes = [vp, sz]
     lib.mbl_host_unregister.argtypes = [vp]
     for name in EXPORTS:

@@ -30,6 +30,9 @@ class ClassifyOptions:
     accession_level: int = 0
     match_per_kmer: int = 4
     device: int = 0
+    mask: int = 0                 # --mask 1: tantan masking of the queries before extraction (KmerExtractor.cpp:308-314)
+    mask_prob: float = 0.9
+    threads: int = 0              # host threads of the masking (0 = all)
 
 
 def _ptr(a):
@@ -92,12 +95,24 @@ class Classifier:
         except Exception:
             pass
 
-    @staticmethod
-    def make_batch(bases1, off1, bases2=None, off2=None):
+    def mask_reads(self, bases, offsets, mask_prob: float | None = None):
+        """SeqIterator::maskLowComplexityRegions (SeqIterator.cpp:154-175) over a batch: a masked COPY of `bases` (letters whose
+        tantan repeat probability reaches --mask-prob, and letters that are no nucleotides, become 'N').  Host work
+        (mbl_mask_reads); the reads handed to the extractor are these, the lengths the TSV prints are unchanged."""
+        b = np.array(bases, dtype=np.uint8, copy=True, order="C")
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(self.lib.mbl_mask_reads(_ptr(b), _ptr(o), o.size - 1, C.c_float(self.opt.mask_prob if mask_prob is None else mask_prob),
+                                            self.opt.threads))
+        return b
+
+    def make_batch(self, bases1, off1, bases2=None, off2=None):
         b1 = np.ascontiguousarray(bases1, dtype=np.uint8)
         o1 = np.ascontiguousarray(off1, dtype=np.uint64)
         b2 = np.ascontiguousarray(bases2, dtype=np.uint8) if bases2 is not None else None
         o2 = np.ascontiguousarray(off2, dtype=np.uint64) if off2 is not None else None
+        if self.opt.mask:
+            b1 = self.mask_reads(b1, o1)
+            b2 = self.mask_reads(b2, o2) if b2 is not None else None
         batch = _ffi.Batch(_ptr(b1), _ptr(o1), _ptr(b2), _ptr(o2), o1.size - 1)
         return batch, (b1, o1, b2, o2)
 

@@ -165,6 +165,8 @@ struct Params {
     int lineage = 0;
     int seqMode = 2, threads = 0, accessionLevel = 0, minConsCnt = 4, minConsCntEuk = 9, matchPerKmer = 4, device = 0;
     float minScore = 0.f, minSpScore = 0.f, tieRatio = 0.95f;
+    int maskMode = 0;                    // --mask 1: tantan masking of the queries before extraction (classify.cpp:31-32 defaults)
+    float maskProb = 0.9f;
     size_t batchReads = 0;
     std::vector<int> devices;            // --gpus N (devices 0..N-1) or --devices a,b,c: one replica of the index per device
     int indexSharded = 0;                // --index-sharded 1: the index is range-partitioned over the devices instead of replicated
@@ -191,15 +193,17 @@ int classify(int argc, char** argv) {
         else if (a == "--devices") { par.devices.clear(); std::string v = val(); size_t p0 = 0; while (p0 <= v.size()) { size_t c = v.find(',', p0); if (c == std::string::npos) c = v.size(); if (c > p0) par.devices.push_back(atoi(v.substr(p0, c - p0).c_str())); p0 = c + 1; } if (par.devices.empty()) die("--devices takes a comma-separated list"); }
         else if (a == "--batch-reads") par.batchReads = (size_t)atoll(val());
         else if (a == "--lineage") par.lineage = atoi(val());
+        // --mask 1 masks low-complexity regions before extraction (KmerExtractor.cpp:308-314, SeqIterator.cpp:154-175): done by
+        // the reader thread through mbl_mask_reads
+        else if (a == "--mask") par.maskMode = atoi(val());
+        else if (a == "--mask-prob") par.maskProb = (float)atof(val());
         // flags that change the reference's output and are not implemented here must fail, never be dropped silently:
-        // --mask 1 masks low-complexity regions before extraction (KmerExtractor.cpp:308-314, SeqIterator.cpp:154-175),
         // --taxonomy-path replaces the database's taxonomy (classify.cpp / TaxonomyWrapper)
-        else if (a == "--mask") { if (atoi(val()) != 0) die("--mask 1 (tantan masking of the queries) is not supported by the B200 path; run with --mask 0 (the default)"); }
         else if (a == "--taxonomy-path") { if (std::string(val()) != "") die("--taxonomy-path is not supported by the B200 path: the taxonomy is read from <dbdir>/taxonomyDB"); }
         else if (a == "--reduced-aa") { if (atoi(val()) != 0) die("--reduced-aa 1 is not supported by the B200 path"); }
         // flags without influence on the classifications: --max-ram only sizes the reference's query splits (here: HBM budget),
-        // --mask-prob is read by --mask 1 only, --hamming-margin is parsed but unused by the reference (KmerMatcher.cpp:1117-1146), -v is verbosity
-        else if (a == "--max-ram" || a == "--mask-prob" || a == "-v" || a == "--hamming-margin") val();
+        // --hamming-margin is parsed but unused by the reference (KmerMatcher.cpp:1117-1146), -v is verbosity
+        else if (a == "--max-ram" || a == "-v" || a == "--hamming-margin") val();
         // the validators only check the inputs and exit on malformed files; on valid inputs the output is unchanged
         else if (a == "--validate-input" || a == "--validate-db") { if (atoi(val()) != 0) fprintf(stderr, "warning: %s is ignored by the B200 path (inputs are not validated)\n", a.c_str()); }
         else if (a.rfind("--", 0) == 0) die("unknown flag " + a);
@@ -371,6 +375,13 @@ int classify(int argc, char** argv) {
             if (par.seqMode == 2) {
                 if (!s2.next(bt->r2, step, T, &err)) { fail_with(err); return; }
                 if (bt->r1.size() != bt->r2.size()) { fail_with("The number of reads in the two files are not equal."); return; }
+            }
+            if (par.maskMode) {
+                // the names and lengths the Reporter prints stay the file's; only the letters the extractor sees change
+                if (mbl_mask_reads(bt->r1.bases.data(), bt->r1.offsets.data(), (uint32_t)bt->r1.size(), par.maskProb, (int)T) != MBL_OK ||
+                    (par.seqMode == 2 && mbl_mask_reads(bt->r2.bases.data(), bt->r2.offsets.data(), (uint32_t)bt->r2.size(), par.maskProb, (int)T) != MBL_OK)) {
+                    fail_with("masking the queries failed"); return;
+                }
             }
             std::unique_lock<std::mutex> lk(mu);
             if (bt->r1.size() == 0) { free_list.push_back(bt); n_batches = index; reader_done = true; cv.notify_all(); return; }

@@ -8,7 +8,7 @@
 set -euo pipefail
 HERE=$(cd "$(dirname "$0")" && pwd)
 OUT=$HERE/_ref
-if [ -x "$OUT/metabuli" ] && [ "${1:-}" != "force" ]; then echo "oracle/_ref/metabuli already built"; exit 0; fi
+if [ -x "$OUT/metabuli" ] && [ -x "$OUT/ref_mask" ] && [ "${1:-}" != "force" ]; then echo "oracle/_ref/metabuli and ref_mask already built"; exit 0; fi
 if [ ! -d /root/reference ]; then echo "no /root/reference here: cannot build oracle/_ref"; exit 0; fi
 W=${MBL_REF_BUILD_DIR:-/tmp/oracle}
 if [ ! -x $W/build/src/metabuli ]; then
@@ -20,4 +20,13 @@ fi
 mkdir -p "$OUT"
 cp $W/build/src/metabuli "$OUT/metabuli"
 strip "$OUT/metabuli" || true
-ls -la "$OUT/metabuli"
+# oracle/ref_mask_main.cpp: the reference's own NucleotideMatrix / ProbabilityMatrix / tantan objects behind a line filter
+# (golden generator of the --mask 1 cases); compiled with the flags and include paths of the reference's own build
+FL=$W/build/src/CMakeFiles/metabuli.dir/flags.make
+INC=$(grep '^CXX_INCLUDES' $FL | sed 's/CXX_INCLUDES = //'); DEF=$(grep '^CXX_DEFINES' $FL | sed 's/CXX_DEFINES = //')
+L=$W/build/lib/mmseqs
+/usr/bin/g++ -O3 -DNDEBUG -fsigned-char -march=native -std=c++1y -fopenmp $DEF $INC -c "$HERE/ref_mask_main.cpp" -o $W/ref_mask.o
+/usr/bin/g++ -fopenmp $W/ref_mask.o -o "$OUT/ref_mask" $L/src/libmmseqs-framework.a $W/build/src/version/libversion.a -latomic \
+  $L/lib/tinyexpr/libtinyexpr.a $L/lib/zstd/build/cmake/lib/libzstd.a $L/lib/microtar/libmicrotar.a $L/lib/tantan/libtantan.a -lz -lpthread
+strip "$OUT/ref_mask" || true
+ls -la "$OUT/metabuli" "$OUT/ref_mask"

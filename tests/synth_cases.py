@@ -75,10 +75,19 @@ EDGE_CASES = {
     # only {T, W, Y, V, stop}: every value is >= 2^63, so the very first k-mer of the stream takes five fragments
     "fivefrag_first_se": (dict(codons=2400, seed=71, residue_sets=(("T", "W", "Y", "V", "X"),), species_div=0.1),
                           dict(n_reads=2000, length=150, seed=72, sub_rate=0.02), 1),
+    # --mask 1 (tantan masking of the queries, KmerExtractor.cpp:308-314): genomes with low-complexity DNA — amino-acid
+    # homopolymers (period 3 with synonymous noise) and exact tandem repeats of 1-14 codons shared by all genomes — so that
+    # masking removes k-mers that would match; reads also carry injected tandem repeats, lower-case and IUPAC letters
+    "mask_se": (dict(codons=2600, seed=73, stretches=(("L", 200, 150), ("S", 900, 120), ("G", 1500, 90)),
+                     tandems=((400, 120, 1), (700, 150, 2), (1100, 160, 5), (1700, 200, 9), (2100, 210, 14))),
+                dict(n_reads=3000, length=150, seed=74, sub_rate=0.01, n_rate=0.001), 1),
+    "mask_pe": (dict(codons=2600, seed=75, stretches=(("L", 200, 150), ("S", 900, 120)),
+                     tandems=((400, 120, 1), (700, 150, 3), (1100, 160, 6), (1700, 200, 11))),
+                dict(n_reads=2000, length=150, seed=76, sub_rate=0.01, paired=True, length_jitter=60), 2),
 }
 
 
-def _edge_db(codons, seed, stretches=(), residue_sets=(), species_div=0.12, strain_div=0.01):
+def _edge_db(codons, seed, stretches=(), residue_sets=(), tandems=(), species_div=0.12, strain_div=0.01):
     import torch
     from metabuli_b200 import synth
     tx = synth.make_taxonomy(2, 2, 2)
@@ -102,7 +111,64 @@ def _edge_db(codons, seed, stretches=(), residue_sets=(), species_div=0.12, stra
         pool = codons_of(letter)
         pick = torch.randint(0, pool.numel(), (genomes.shape[0], length), generator=gen)
         genomes[:, start:start + length] = pool[pick]
+    for start, length, period in tandems:
+        unit = torch.randint(0, 61, (period,), generator=gen).to(torch.uint8)
+        unit = torch.as_tensor([c for c in range(64) if synth._AA[c] != synth._AA_ORDER.index("X")], dtype=torch.uint8)[unit.long()]   # no stop codons
+        genomes[:, start:start + length] = unit[torch.arange(length) % period]
     return synth.build_db(tx, genomes)
+
+
+def _inject_read_repeats(reads, seed):
+    """Every fifth read gets a window overwritten by a tandem repeat (period 1..40, 0-8 % substitutions); a few letters become
+    lower-case or IUPAC codes (masking must keep them as they are unless masked; NucleotideMatrix.cpp:18-57 maps them)."""
+    rng = np.random.default_rng(seed)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    out = []
+    for k in range(0, len(reads), 2):
+        bases, offsets = reads[k].copy(), reads[k + 1]
+        for r in range(0, offsets.size - 1, 5):
+            b0, b1 = int(offsets[r]), int(offsets[r + 1])
+            if b1 - b0 < 30:
+                continue
+            a = int(rng.integers(0, b1 - b0 - 20))
+            ln = int(rng.integers(12, b1 - b0 - a + 1))
+            unit = letters[rng.integers(0, 4, int(rng.integers(1, 41)))]
+            rep = np.resize(unit, ln)
+            mut = rng.random(ln) < rng.choice([0.0, 0.03, 0.08])
+            bases[b0 + a:b0 + a + ln] = np.where(mut, letters[rng.integers(0, 4, ln)], rep)
+        odd = rng.integers(0, bases.size, bases.size // 400)
+        bases[odd] = np.frombuffer(b"acgtRYKMSWn", dtype=np.uint8)[rng.integers(0, 11, odd.size)]
+        out += [bases, offsets]
+    return tuple(out)
+
+
+def mask_misc_reads():
+    """Odd inputs for the masking alone (no database): empty and one-letter reads, reads of Ns / lower case / IUPAC codes, exact
+    and noisy tandem repeats with periods around the 50-offset limit, and multi-kilobase reads (the forward and backward sweeps
+    rescale every 16 letters, so long reads walk through thousands of rescalings)."""
+    rng = np.random.default_rng(97)
+    L = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = [b"", b"A", b"N", b"ac", b"NNNNNNNNNNNNNNNNNNNN", b"A" * 15, b"A" * 16, b"A" * 17, b"ACGT" * 12 + b"T", b"acgtnRYKM*-x" * 9]
+    for per in (1, 2, 3, 7, 16, 33, 49, 50, 51, 64):
+        unit = L[rng.integers(0, 4, per)]
+        for noise in (0.0, 0.05):
+            n = int(rng.integers(60, 500))
+            rep = np.resize(unit, n)
+            seqs.append(bytes(np.where(rng.random(n) < noise, L[rng.integers(0, 4, n)], rep)))
+    for n in (1000, 1001, 4097, 20000):
+        s_ = L[rng.integers(0, 4, n)]
+        for _ in range(n // 400):
+            a = int(rng.integers(0, n - 50)); b = min(n, a + int(rng.integers(10, 600)))
+            s_[a:b] = np.resize(L[rng.integers(0, 4, int(rng.integers(1, 56)))], b - a)
+        seqs.append(bytes(s_))
+    for _ in range(300):
+        seqs.append(bytes(L[rng.integers(0, 4, int(rng.integers(1, 300)))]))
+    offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([len(x) for x in seqs])
+    return np.frombuffer(b"".join(seqs), dtype=np.uint8).copy(), offsets
+
+
+MASK_MISC_PROBS = (0.5, 0.9, 0.99)
 
 
 # classify flags of a case (reference spelling -> value); cases without an entry run the defaults
@@ -110,6 +176,8 @@ FLAGS = {
     "flags_se": {"--min-score": 0.3, "--min-sp-score": 0.6, "--tie-ratio": 0.9, "--min-cons-cnt": 6, "--min-cons-cnt-euk": 11},
     "acc_lvl1_se": {"--accession-level": 1},
     "lineage_se": {"--lineage": 1},
+    "mask_se": {"--mask": 1},
+    "mask_pe": {"--mask": 1, "--mask-prob": 0.5},
 }
 
 
@@ -120,12 +188,21 @@ def oracle_flags(name):
                 accession_level=f.get("--accession-level", 0), lineage=f.get("--lineage", 0))
 
 
+def mask_flags(name):
+    """(--mask, --mask-prob) of a case."""
+    f = FLAGS.get(name, {})
+    return int(f.get("--mask", 0)), float(f.get("--mask-prob", 0.9))
+
+
 def build(name):
     from metabuli_b200 import synth
     if name in EDGE_CASES:
         dbkw, rkw, seq_mode = EDGE_CASES[name]
         sdb = _edge_db(**dbkw)
-        return sdb, synth.make_reads(sdb, **rkw), seq_mode
+        reads = synth.make_reads(sdb, **rkw)
+        if name.startswith("mask_"):
+            reads = _inject_read_repeats(reads, rkw["seed"] + 500)
+        return sdb, reads, seq_mode
     dbkw, rkw, seq_mode = (CASES.get(name) or CPU_CASES[name])
     sdb = synth.make_db(**dbkw)
     if name == "redund_se":

@@ -57,14 +57,15 @@ def test_product_does_not_touch_oracle():
 
 
 def test_cli_rejects_flags_that_would_change_the_output():
-    """`--mask 1`, `--taxonomy-path X`, `--reduced-aa 1` change the reference's classifications and are not implemented on the
-    B200 path: the C++ host must die with a message, not drop them (argument parsing needs no GPU)."""
+    """`--taxonomy-path X`, `--reduced-aa 1` change the reference's classifications and are not implemented on the
+    B200 path: the C++ host must die with a message, not drop them (argument parsing needs no GPU).
+    (`--mask 1` is implemented since round 2: tests/test_host_mask.py, test_gpu_synth.py::test_masked_queries.)"""
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metabuli_b200", "_lib", "metabuli-b200")
-    for flags in (["--mask", "1"], ["--taxonomy-path", "/some/where"], ["--reduced-aa", "1"], ["--no-such-flag", "1"]):
+    for flags in (["--taxonomy-path", "/some/where"], ["--reduced-aa", "1"], ["--no-such-flag", "1"]):
         r = subprocess.run([exe, "classify", "--seq-mode", "1", *flags, "a.fna", "db", "out", "job"], capture_output=True, text=True)
         assert r.returncode != 0 and "Error" in (r.stdout + r.stderr), flags
     # harmless spellings are accepted up to the input checks
-    r = subprocess.run([exe, "classify", "--seq-mode", "1", "--mask", "0", "--max-ram", "8", "--hamming-margin", "1", "a.fna", "db", "out", "job"],
+    r = subprocess.run([exe, "classify", "--seq-mode", "1", "--mask", "1", "--mask-prob", "0.8", "--max-ram", "8", "--hamming-margin", "1", "a.fna", "db", "out", "job"],
                        capture_output=True, text=True)
     assert "not supported" not in (r.stdout + r.stderr)

@@ -206,3 +206,40 @@ def test_batch_without_any_kmer():
         assert not res["is_classified"].any() and clf.stats()["n_query_kmers"] == 0
     finally:
         clf.close()
+
+
+@pytest.mark.parametrize("name", ["mask_se", "mask_pe"])
+def test_masked_queries(name, golden_dir, tmp_path):
+    """--mask 1 (KmerExtractor.cpp:308-314): the host masks the batch (mbl_mask_reads), the CUDA path classifies the masked reads;
+    against the reference binary's TSV written with --mask 1 [--mask-prob p], through the Python mirror and through the C++ host."""
+    import subprocess
+    from metabuli_b200 import Classifier, ClassifyOptions
+    sdb, reads, seq_mode = synth_cases.build(name)
+    assert synth_cases.fingerprint(sdb, reads) == open(os.path.join(golden_dir, "synth", name + ".md5")).read().strip()
+    mask, prob = synth_cases.mask_flags(name)
+    golden = gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
+    clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode, mask=mask, mask_prob=prob), database=sdb.database)
+    try:
+        before = [a.copy() for a in reads]
+        res, pairs = clf.classify_batch(*reads)
+        assert all(np.array_equal(a, b) for a, b in zip(before, reads)), "the caller's reads must not be modified"
+        assert clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode() == golden
+        clf.opt.mask = 0
+        res0, pairs0 = clf.classify_batch(*reads)
+        assert clf.format_tsv(synth_cases.names(reads[1].size - 1), res0, pairs0).encode() != golden      # the flag matters here
+    finally:
+        clf.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "metabuli_b200", "_lib", "metabuli-b200")
+    db_dir = str(tmp_path / "db")
+    sdb.write(db_dir)
+    files = [str(tmp_path / "r1.fna")]
+    synth_cases.write_fasta(files[0], reads[0], reads[1])
+    if seq_mode == 2:
+        files.append(str(tmp_path / "r2.fna"))
+        synth_cases.write_fasta(files[1], reads[2], reads[3])
+    cmd = [exe, "classify", "--seq-mode", str(seq_mode), "--threads", "4", "--batch-reads", "700", "--mask", "1", "--mask-prob", str(prob)]
+    r = subprocess.run(cmd + files + [db_dir, str(tmp_path), "job"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert open(tmp_path / "job_classifications.tsv", "rb").read() == golden
+    assert open(tmp_path / "job_report.tsv", "rb").read() == gzip.open(os.path.join(golden_dir, "synth", name + ".report.gz"), "rb").read()
