@@ -49,6 +49,9 @@ typedef struct {
     int   accession_level;    /* 0, or 2 = prune ""/"accession" leaves (Taxonomer.cpp:256-267)         */
     int   device;             /* CUDA device ordinal                                                   */
     int   match_per_kmer;     /* initial match-buffer factor (--match-per-kmer, 4); grows on overflow  */
+    int   mask_mode;          /* --mask 1: every uploaded batch is tantan-masked on the device before extraction        */
+                              /* (KmerExtractor.cpp:308-314); 0 when off or when the caller masked with mbl_mask_reads  */
+    float mask_prob;          /* --mask-prob (0.9)                                                     */
 } mbl_config;
 
 /* The on-disk index as the reference reads it (KmerMatcher.cpp:137-139, 212-217): whole files. */
@@ -218,8 +221,13 @@ int  mbl_shard_push_matches(mbl_ctx* ctx, const uint64_t* dst_row_offset);
 
 /* `--mask 1` (KmerExtractor.cpp:308-314, SeqIterator::maskLowComplexityRegions, SeqIterator.cpp:154-175): tantan's repeat
  * probability per letter of every read; letters at or above mask_prob (and letters that are not nucleotides) become 'N' in
- * place.  Host work (no device needed); call it on a batch before mbl_classify_batch / mbl_prefetch_batch. */
+ * place.  Host work (no device needed); call it on a batch before mbl_classify_batch / mbl_prefetch_batch — or set
+ * mbl_config.mask_mode and let the device do the same, letter for letter, after the upload (k0_mask.cu). */
 int  mbl_mask_reads(char* bases, const uint64_t* offsets, uint32_t n_reads, float mask_prob, int threads);
+
+/* The letters of the resident batch as the extractor sees them (mate 1 or 2; after the device masking when mask_mode is 1):
+ * n_bytes = offsets[n_reads] of that mate.  Diagnostics and tests. */
+int  mbl_download_reads(mbl_ctx* ctx, int mate, char* out, size_t n_bytes);
 
 /* Pin / unpin a caller buffer (cudaHostRegister) so the copies inside mbl_classify_batch run at PCIe
  * speed; purely an optimisation, pageable buffers work too. */
@@ -250,6 +258,8 @@ typedef struct {
     uint64_t n_merge_queries;         /* metamers that reached the sort and the merge (after the amino-acid presence filter) */
     float    ms_push_kmers;           /* sharded mode, peer transport: the push kernels alone (stores into the peers' buffers) */
     float    ms_push_matches;
+    float    ms_mask;                 /* mask_mode 1: the masking kernel of the last upload              */
+    uint32_t reserved0;
 } mbl_stats;
 int  mbl_get_stats(const mbl_ctx* ctx, mbl_stats* out);
 

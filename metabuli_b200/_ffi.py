@@ -35,7 +35,8 @@ class Config(C.Structure):
     _fields_ = [("kmer_format", C.c_int), ("reduced_aa", C.c_int), ("skip_redundancy", C.c_int), ("syncmer", C.c_int),
                 ("smer_len", C.c_int), ("seq_mode", C.c_int), ("min_score", C.c_float), ("min_sp_score", C.c_float),
                 ("tie_ratio", C.c_float), ("min_cons_cnt", C.c_int), ("min_cons_cnt_euk", C.c_int),
-                ("accession_level", C.c_int), ("device", C.c_int), ("match_per_kmer", C.c_int)]
+                ("accession_level", C.c_int), ("device", C.c_int), ("match_per_kmer", C.c_int),
+                ("mask_mode", C.c_int), ("mask_prob", C.c_float)]
 
 
 class Db(C.Structure):
@@ -64,7 +65,7 @@ class Stats(C.Structure):
     _fields_ = [("ms", C.c_float * 7), ("merge_kernel_ms", C.c_float), ("n_query_kmers", C.c_uint64), ("n_matches", C.c_uint64), ("merge_bytes", C.c_uint64),
                 ("merge_launches", C.c_uint32), ("kernel_launches", C.c_uint32), ("overflow_retries", C.c_uint32),
                 ("sub_batches", C.c_uint32), ("ms_bucket_kmers", C.c_float), ("ms_bucket_matches", C.c_float), ("n_merge_queries", C.c_uint64),
-                ("ms_push_kmers", C.c_float), ("ms_push_matches", C.c_float)]
+                ("ms_push_kmers", C.c_float), ("ms_push_matches", C.c_float), ("ms_mask", C.c_float), ("reserved0", C.c_uint32)]
 
 
 class Shard(C.Structure):
@@ -92,7 +93,7 @@ EXPORTS = ["mbl_create", "mbl_destroy", "mbl_last_error", "mbl_load_db", "mbl_cl
            "mbl_score", "mbl_get_stats", "mbl_get_db_info", "mbl_host_register", "mbl_host_unregister",
            "mbl_plan_shards", "mbl_load_db_shard", "mbl_shard_extract", "mbl_shard_match", "mbl_shard_score",
            "mbl_shard_pack_kmers", "mbl_shard_pack_matches", "mbl_shard_recv_buffers", "mbl_shard_attach_peer", "mbl_shard_detach_peers", "mbl_shard_push_kmers",
-           "mbl_shard_push_matches", "mbl_shard_filter", "mbl_shard_filter_or", "mbl_mask_reads"]
+           "mbl_shard_push_matches", "mbl_shard_filter", "mbl_shard_filter_or", "mbl_mask_reads", "mbl_download_reads"]
 
 _lib = None
 
@@ -141,6 +142,7 @@ def load_library() -> C.CDLL:
     lib.mbl_shard_filter.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     lib.mbl_shard_filter_or.argtypes = [vp, vp, C.c_uint64, C.c_int]
     lib.mbl_mask_reads.argtypes = [vp, vp, C.c_uint32, C.c_float, C.c_int]
+    lib.mbl_download_reads.argtypes = [vp, C.c_int, vp, sz]
     lib.mbl_host_register.argtypes = [vp, sz]
     lib.mbl_host_unregister.argtypes = [vp]
     for name in EXPORTS:

@@ -32,7 +32,9 @@ class ClassifyOptions:
     device: int = 0
     mask: int = 0                 # --mask 1: tantan masking of the queries before extraction (KmerExtractor.cpp:308-314)
     mask_prob: float = 0.9
-    threads: int = 0              # host threads of the masking (0 = all)
+    mask_on_host: bool = False    # False: the library masks every uploaded batch on the device (mbl_config.mask_mode, k0_mask.cu);
+                                  # True: mbl_mask_reads on the host threads before the upload — same letters either way
+    threads: int = 0              # host threads of the host-side masking (0 = all)
 
 
 def _ptr(a):
@@ -61,7 +63,8 @@ class Classifier:
                                syncmer=p.syncmer, smer_len=p.smer_len, seq_mode=self.opt.seq_mode,
                                min_score=self.opt.min_score, min_sp_score=self.opt.min_sp_score, tie_ratio=self.opt.tie_ratio,
                                min_cons_cnt=self.opt.min_cons_cnt, min_cons_cnt_euk=self.opt.min_cons_cnt_euk,
-                               accession_level=acc, device=self.opt.device, match_per_kmer=self.opt.match_per_kmer)
+                               accession_level=acc, device=self.opt.device, match_per_kmer=self.opt.match_per_kmer,
+                               mask_mode=1 if (self.opt.mask and not self.opt.mask_on_host) else 0, mask_prob=self.opt.mask_prob)
         self.ctx = C.c_void_p()
         rc = self.lib.mbl_create(C.byref(self.cfg), C.byref(self.ctx))
         if rc != _ffi.MBL_OK:
@@ -110,7 +113,7 @@ class Classifier:
         o1 = np.ascontiguousarray(off1, dtype=np.uint64)
         b2 = np.ascontiguousarray(bases2, dtype=np.uint8) if bases2 is not None else None
         o2 = np.ascontiguousarray(off2, dtype=np.uint64) if off2 is not None else None
-        if self.opt.mask:
+        if self.opt.mask and self.opt.mask_on_host:
             b1 = self.mask_reads(b1, o1)
             b2 = self.mask_reads(b2, o2) if b2 is not None else None
         batch = _ffi.Batch(_ptr(b1), _ptr(o1), _ptr(b2), _ptr(o2), o1.size - 1)
@@ -208,7 +211,7 @@ class Classifier:
                  merge_launches=int(s.merge_launches), kernel_launches=int(s.kernel_launches),
                  overflow_retries=int(s.overflow_retries), sub_batches=int(s.sub_batches), ms_bucket_kmers=float(s.ms_bucket_kmers),
                  ms_bucket_matches=float(s.ms_bucket_matches), n_merge_queries=int(s.n_merge_queries),
-                 ms_push_kmers=float(s.ms_push_kmers), ms_push_matches=float(s.ms_push_matches))
+                 ms_push_kmers=float(s.ms_push_kmers), ms_push_matches=float(s.ms_push_matches), ms_mask=float(s.ms_mask))
         return d
 
     def db_info(self) -> dict:

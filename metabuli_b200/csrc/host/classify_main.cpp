@@ -167,6 +167,7 @@ struct Params {
     float minScore = 0.f, minSpScore = 0.f, tieRatio = 0.95f;
     int maskMode = 0;                    // --mask 1: tantan masking of the queries before extraction (classify.cpp:31-32 defaults)
     float maskProb = 0.9f;
+    int maskHost = 0;                    // --mask-host 1: mask in the reader thread (mbl_mask_reads) instead of on the device (K0)
     size_t batchReads = 0;
     std::vector<int> devices;            // --gpus N (devices 0..N-1) or --devices a,b,c: one replica of the index per device
     int indexSharded = 0;                // --index-sharded 1: the index is range-partitioned over the devices instead of replicated
@@ -193,10 +194,11 @@ int classify(int argc, char** argv) {
         else if (a == "--devices") { par.devices.clear(); std::string v = val(); size_t p0 = 0; while (p0 <= v.size()) { size_t c = v.find(',', p0); if (c == std::string::npos) c = v.size(); if (c > p0) par.devices.push_back(atoi(v.substr(p0, c - p0).c_str())); p0 = c + 1; } if (par.devices.empty()) die("--devices takes a comma-separated list"); }
         else if (a == "--batch-reads") par.batchReads = (size_t)atoll(val());
         else if (a == "--lineage") par.lineage = atoi(val());
-        // --mask 1 masks low-complexity regions before extraction (KmerExtractor.cpp:308-314, SeqIterator.cpp:154-175): done by
-        // the reader thread through mbl_mask_reads
+        // --mask 1 masks low-complexity regions before extraction (KmerExtractor.cpp:308-314, SeqIterator.cpp:154-175): on the
+        // device after every upload (mbl_config.mask_mode), or with --mask-host 1 by the reader thread through mbl_mask_reads
         else if (a == "--mask") par.maskMode = atoi(val());
         else if (a == "--mask-prob") par.maskProb = (float)atof(val());
+        else if (a == "--mask-host") par.maskHost = atoi(val());
         // flags that change the reference's output and are not implemented here must fail, never be dropped silently:
         // --taxonomy-path replaces the database's taxonomy (classify.cpp / TaxonomyWrapper)
         else if (a == "--taxonomy-path") { if (std::string(val()) != "") die("--taxonomy-path is not supported by the B200 path: the taxonomy is read from <dbdir>/taxonomyDB"); }
@@ -228,6 +230,7 @@ int classify(int argc, char** argv) {
     cfg.min_score = par.minScore; cfg.min_sp_score = par.minSpScore; cfg.tie_ratio = par.tieRatio;
     cfg.min_cons_cnt = par.minConsCnt; cfg.min_cons_cnt_euk = par.minConsCntEuk;
     cfg.accession_level = par.accessionLevel; cfg.device = par.device; cfg.match_per_kmer = par.matchPerKmer;
+    cfg.mask_mode = (par.maskMode && !par.maskHost) ? 1 : 0; cfg.mask_prob = par.maskProb;
     {
         std::ifstream pf(dbDir + "/db.parameters");
         std::string line;
@@ -376,7 +379,7 @@ int classify(int argc, char** argv) {
                 if (!s2.next(bt->r2, step, T, &err)) { fail_with(err); return; }
                 if (bt->r1.size() != bt->r2.size()) { fail_with("The number of reads in the two files are not equal."); return; }
             }
-            if (par.maskMode) {
+            if (par.maskMode && par.maskHost) {
                 // the names and lengths the Reporter prints stay the file's; only the letters the extractor sees change
                 if (mbl_mask_reads(bt->r1.bases.data(), bt->r1.offsets.data(), (uint32_t)bt->r1.size(), par.maskProb, (int)T) != MBL_OK ||
                     (par.seqMode == 2 && mbl_mask_reads(bt->r2.bases.data(), bt->r2.offsets.data(), (uint32_t)bt->r2.size(), par.maskProb, (int)T) != MBL_OK)) {

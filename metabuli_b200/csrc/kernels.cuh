@@ -42,6 +42,12 @@ struct ScoreParams {
     int force_scratch_dp;      // tests only: skip the register-resident DP fast path
 };
 
+// K0 (--mask 1): tantan masking of the resident reads, in place, one warp per read
+struct MaskPlan { uint32_t blocks; uint64_t stride, prob_floats, scale_doubles; };
+MaskPlan plan_mask(uint32_t n_reads, uint64_t max_len, int sm_count);
+void launch_mask(uint8_t* bases, const uint64_t* off, uint32_t n_reads, float mask_prob, const MaskPlan& plan, float* prob_scratch,
+                 double* scale_scratch, unsigned long long* counter, cudaStream_t st);
+
 // K1
 void launch_read_meta(const uint64_t* off1, const uint64_t* off2, uint32_t n_reads, int32_t* cov1, int32_t* cov2,
                       int32_t* w1, int32_t* w2, uint64_t* slots, uint32_t* quot_cnt, cudaStream_t st);

@@ -37,8 +37,8 @@ struct Buf {
 };
 
 struct SubBatch { uint32_t r0, r1; uint64_t slots, quots; uint32_t max_pos; uint32_t b0, b1; };   // reads [r0, r1) = blocks [b0, b1)
-struct ReadBlock { uint64_t slots, quots; uint32_t max_pos; };
-struct BatchSummary { uint32_t n_reads = 0, block_reads = 1; std::vector<ReadBlock> blocks; };
+struct ReadBlock { uint64_t slots, quots; uint32_t max_pos; uint64_t max_len; };
+struct BatchSummary { uint32_t n_reads = 0, block_reads = 1; uint64_t max_len = 0; std::vector<ReadBlock> blocks; };
 constexpr uint32_t kScoreChunkReads = 1u << 20;   // reads scored per launch (bounds the per-match scratch)
 
 }  // namespace
@@ -98,6 +98,8 @@ struct mbl_ctx {
         c_start, c_end, s_score;
     Buf q_tax, q_ham, q_has, pairs_raw;
     Buf q_lo, item_cnt, item_off, items, counters;
+    Buf mask_prob, mask_scale, mask_counter;            // K0 scratch (mask_mode 1)
+    float ms_mask = 0.f;                                // masking kernel of the last upload (kept across the stats reset of a classify call)
     // index-sharded mode (mbl_shard_*): bucket keys / permutations, send buffers, bucket starts
     Buf sh_key_a, sh_key_b, sh_idx_a, sh_idx_b, sh_begin, send_value, send_qinfo, send_match, sh_tmp;
     uint64_t seq_base = 0;              // index of the resident batch's first read among all ranks' reads
@@ -203,13 +205,15 @@ void summarize_reads(const mbl_batch* b, BatchSummary& sum) {
     sum.n_reads = n;
     sum.block_reads = std::max<uint32_t>(1, std::min<uint32_t>(4096, n / 256));
     const size_t nb = ((size_t)n + sum.block_reads - 1) / sum.block_reads;
-    sum.blocks.assign(nb, ReadBlock{0, 0, 0});
+    sum.blocks.assign(nb, ReadBlock{0, 0, 0, 0});
     auto work = [&](size_t b0, size_t b1) {
         for (size_t k = b0; k < b1; ++k) {
-            ReadBlock acc{0, 0, 0};
+            ReadBlock acc{0, 0, 0, 0};
             const uint32_t r1 = (uint32_t)std::min<uint64_t>(n, (uint64_t)(k + 1) * sum.block_reads);
             for (uint32_t r = (uint32_t)(k * sum.block_reads); r < r1; ++r) {
                 const int l1 = (int)(b->offsets[r + 1] - b->offsets[r]);
+                acc.max_len = std::max<uint64_t>(acc.max_len, b->offsets[r + 1] - b->offsets[r]);
+                if (b->offsets2) acc.max_len = std::max<uint64_t>(acc.max_len, b->offsets2[r + 1] - b->offsets2[r]);
                 int w1 = windows_per_frame(l1), c1 = max_covered_length(l1), w2 = 0, c2 = 0;
                 if (b->offsets2) {
                     const int l2 = (int)(b->offsets2[r + 1] - b->offsets2[r]);
@@ -233,6 +237,8 @@ void summarize_reads(const mbl_batch* b, BatchSummary& sum) {
     } else {
         work(0, nb);
     }
+    sum.max_len = 0;
+    for (const ReadBlock& x : sum.blocks) sum.max_len = std::max(sum.max_len, x.max_len);
 }
 
 SubBatch sub_of_blocks(const BatchSummary& sum, size_t b0, size_t b1) {
@@ -640,6 +646,26 @@ int run_sub_batch(mbl_ctx* c, const SubBatch& sb) {
 }  // namespace
 
 // =====================================================================================================
+// mask_mode 1: the batch that has just become resident is masked in place on the context's stream (K0), once per upload
+void mask_resident(mbl_ctx* c) {
+    c->ms_mask = 0.f;
+    if (!c->cfg.mask_mode || !c->n_reads) return;
+    const MaskPlan plan = plan_mask(c->n_reads, c->summary.max_len, c->sm_count);
+    if (!plan.blocks) return;
+    float* prob = c->mask_prob.get<float>(plan.prob_floats);
+    double* scale = c->mask_scale.get<double>(plan.scale_doubles);
+    unsigned long long* counter = c->mask_counter.get<unsigned long long>(2);
+    cudaEvent_t a = c->ev[14], b = c->ev[15];
+    MBL_CUDA(cudaEventRecord(a, c->st));
+    launch_mask((uint8_t*)c->bases1.p, (const uint64_t*)c->off1.p, c->n_reads, c->cfg.mask_prob, plan, prob, scale, counter, c->st);
+    if (c->paired) launch_mask((uint8_t*)c->bases2.p, (const uint64_t*)c->off2.p, c->n_reads, c->cfg.mask_prob, plan, prob, scale, counter + 1, c->st);
+    MBL_CUDA(cudaGetLastError());
+    MBL_CUDA(cudaEventRecord(b, c->st));
+    MBL_CUDA(cudaEventSynchronize(b));
+    MBL_CUDA(cudaEventElapsedTime(&c->ms_mask, a, b));
+    if (c->mask_prob.cap > (256u << 20)) { c->mask_prob.release(); c->mask_scale.release(); }      // long reads: give the scratch back
+}
+
 extern "C" {
 
 int mbl_create(const mbl_config* cfg, mbl_ctx** out) {
@@ -955,6 +981,7 @@ int mbl_upload_batch(mbl_ctx* c, const mbl_batch* b) {
         c->probe_first = c->probe_first && c->subs.size() > 1;
         c->plan_has_probe = c->probe_first;
         t.stop();
+        mask_resident(c);
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
     } MBL_CATCH_HOST(c)
@@ -1213,6 +1240,7 @@ int mbl_classify_prefetched(mbl_ctx* c, const mbl_batch* next, mbl_read_result* 
         c->n_reads = c->staged_reads; c->paired = c->staged_paired;
         c->staged = false;
         c->stats.ms[MBL_STAGE_H2D] = ms;
+        mask_resident(c);
     } catch (const CudaError& e) {
         return fail_cuda(c, e);
     } MBL_CATCH_HOST(c)
@@ -1579,6 +1607,20 @@ int mbl_shard_score(mbl_ctx* c, const mbl_match_rec* d_match, uint64_t n_match) 
     return MBL_OK;
 }
 
+int mbl_download_reads(mbl_ctx* c, int mate, char* out, size_t n_bytes) {
+    if (!c || !out || (mate != 1 && mate != 2)) return fail(c, MBL_E_BAD_ARG, "null argument or mate not 1 / 2");
+    const Buf& src = mate == 1 ? c->bases1 : c->bases2;
+    if ((mate == 2 && !c->paired) || n_bytes + 64 > src.cap) return fail(c, MBL_E_BAD_ARG, "no such resident reads");
+    try {
+        MBL_CUDA(cudaSetDevice(c->cfg.device));
+        MBL_CUDA(cudaMemcpyAsync(out, src.p, n_bytes, cudaMemcpyDeviceToHost, c->st));
+        MBL_CUDA(cudaStreamSynchronize(c->st));
+    } catch (const CudaError& e) {
+        return fail_cuda(c, e);
+    } MBL_CATCH_HOST(c)
+    return MBL_OK;
+}
+
 int mbl_host_register(void* ptr, size_t bytes) {
     if (!ptr || !bytes) return MBL_E_BAD_ARG;
     cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
@@ -1595,6 +1637,7 @@ int mbl_host_unregister(void* ptr) {
 int mbl_get_stats(const mbl_ctx* c, mbl_stats* out) {
     if (!c || !out) return MBL_E_BAD_ARG;
     *out = c->stats;
+    out->ms_mask = c->ms_mask;
     return MBL_OK;
 }
 

@@ -29,7 +29,8 @@ def test_struct_layouts():
     from metabuli_b200 import _ffi
     assert C.sizeof(_ffi.ReadResult) == 28
     assert _ffi.MATCH_DTYPE.itemsize == 24
-    assert C.sizeof(_ffi.Stats) == 4 * 8 + 3 * 8 + 4 * 4 + 2 * 4 + 8 + 2 * 4
+    assert C.sizeof(_ffi.Stats) == 4 * 8 + 3 * 8 + 4 * 4 + 2 * 4 + 8 + 2 * 4 + 2 * 4
+    assert C.sizeof(_ffi.Config) == 16 * 4
     assert C.sizeof(_ffi.Shard) == 56
 
 

@@ -208,25 +208,45 @@ def test_batch_without_any_kmer():
         clf.close()
 
 
+def _download_reads(clf, n_bytes, mate=1):
+    """The resident (masked) letters of the last upload, for the device-masking checks."""
+    import ctypes as C
+    out = np.zeros(n_bytes, dtype=np.uint8)
+    clf._check(clf.lib.mbl_download_reads(clf.ctx, mate, out.ctypes.data_as(C.c_void_p), n_bytes))
+    return out
+
+
 @pytest.mark.parametrize("name", ["mask_se", "mask_pe"])
 def test_masked_queries(name, golden_dir, tmp_path):
-    """--mask 1 (KmerExtractor.cpp:308-314): the host masks the batch (mbl_mask_reads), the CUDA path classifies the masked reads;
-    against the reference binary's TSV written with --mask 1 [--mask-prob p], through the Python mirror and through the C++ host."""
+    """--mask 1 (KmerExtractor.cpp:308-314) against the reference binary's TSV written with --mask 1 [--mask-prob p]: masked by the
+    device kernel (K0, mbl_config.mask_mode), masked on the host (mbl_mask_reads), and through the C++ host in both modes."""
     import subprocess
     from metabuli_b200 import Classifier, ClassifyOptions
     sdb, reads, seq_mode = synth_cases.build(name)
     assert synth_cases.fingerprint(sdb, reads) == open(os.path.join(golden_dir, "synth", name + ".md5")).read().strip()
     mask, prob = synth_cases.mask_flags(name)
     golden = gzip.open(os.path.join(golden_dir, "synth", name + ".tsv.gz"), "rb").read()
-    clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode, mask=mask, mask_prob=prob), database=sdb.database)
+    names = synth_cases.names(reads[1].size - 1)
+    for on_host in (False, True):
+        clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode, mask=mask, mask_prob=prob, mask_on_host=on_host), database=sdb.database)
+        try:
+            before = [a.copy() for a in reads]
+            res, pairs = clf.classify_batch(*reads)
+            assert all(np.array_equal(a, b) for a, b in zip(before, reads)), "the caller's reads must not be modified"
+            if not on_host:
+                # the letters the device masked == the letters the host masks (itself pinned on the reference in test_host_mask.py)
+                for mate in range(len(reads) // 2):
+                    want = clf.mask_reads(reads[2 * mate], reads[2 * mate + 1])
+                    got = _download_reads(clf, want.size, mate + 1)
+                    assert np.array_equal(got, want), (on_host, mate, int((got != want).sum()))
+                assert clf.stats()["ms_mask"] > 0
+            assert clf.format_tsv(names, res, pairs).encode() == golden, on_host
+        finally:
+            clf.close()
+    clf = Classifier(None, ClassifyOptions(seq_mode=seq_mode), database=sdb.database)
     try:
-        before = [a.copy() for a in reads]
-        res, pairs = clf.classify_batch(*reads)
-        assert all(np.array_equal(a, b) for a, b in zip(before, reads)), "the caller's reads must not be modified"
-        assert clf.format_tsv(synth_cases.names(reads[1].size - 1), res, pairs).encode() == golden
-        clf.opt.mask = 0
         res0, pairs0 = clf.classify_batch(*reads)
-        assert clf.format_tsv(synth_cases.names(reads[1].size - 1), res0, pairs0).encode() != golden      # the flag matters here
+        assert clf.format_tsv(names, res0, pairs0).encode() != golden      # the flag matters on this case
     finally:
         clf.close()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -238,8 +258,37 @@ def test_masked_queries(name, golden_dir, tmp_path):
     if seq_mode == 2:
         files.append(str(tmp_path / "r2.fna"))
         synth_cases.write_fasta(files[1], reads[2], reads[3])
-    cmd = [exe, "classify", "--seq-mode", str(seq_mode), "--threads", "4", "--batch-reads", "700", "--mask", "1", "--mask-prob", str(prob)]
-    r = subprocess.run(cmd + files + [db_dir, str(tmp_path), "job"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout[-2000:]
-    assert open(tmp_path / "job_classifications.tsv", "rb").read() == golden
-    assert open(tmp_path / "job_report.tsv", "rb").read() == gzip.open(os.path.join(golden_dir, "synth", name + ".report.gz"), "rb").read()
+    for extra in ([], ["--mask-host", "1"]):
+        cmd = [exe, "classify", "--seq-mode", str(seq_mode), "--threads", "4", "--batch-reads", "700", "--mask", "1", "--mask-prob", str(prob)] + extra
+        r = subprocess.run(cmd + files + [db_dir, str(tmp_path), "job"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:]
+        assert open(tmp_path / "job_classifications.tsv", "rb").read() == golden, extra
+        assert open(tmp_path / "job_report.tsv", "rb").read() == gzip.open(os.path.join(golden_dir, "synth", name + ".report.gz"), "rb").read()
+
+
+def test_device_masking_of_odd_and_long_reads(golden_dir):
+    """K0 on the inputs of tests/golden/synth/mask_misc.masked.gz (written by the reference's own tantan objects): empty and
+    one-letter reads, Ns, lower case, IUPAC, periods around the 50-offset limit, 1-20 kb reads (the code window moves, thousands of
+    rescalings) at three thresholds; and a batch whose longest read shrinks the number of warps in flight."""
+    from metabuli_b200 import Classifier, ClassifyOptions
+    sdb, _, _ = synth_cases.build("multi_se")
+    b, o = synth_cases.mask_misc_reads()
+    want_all = gzip.open(os.path.join(golden_dir, "synth", "mask_misc.masked.gz"), "rb").read()
+    n_line = int(o[-1]) + o.size - 1
+    for i, prob in enumerate(synth_cases.MASK_MISC_PROBS):
+        clf = Classifier(None, ClassifyOptions(seq_mode=3, mask=1, mask_prob=prob), database=sdb.database)
+        try:
+            clf.classify_batch(b, o)
+            got = _download_reads(clf, b.size)
+            lines = b"".join(bytes(got[int(o[k]):int(o[k + 1])]) + b"\n" for k in range(o.size - 1))
+            assert lines == want_all[i * n_line:(i + 1) * n_line], prob
+        finally:
+            clf.close()
+    # long ragged reads: device == host letters
+    sdb2, reads, _ = synth_cases.build("ont_ragged")
+    clf = Classifier(None, ClassifyOptions(seq_mode=3, mask=1), database=sdb2.database)
+    try:
+        clf.classify_batch(*reads)
+        assert np.array_equal(_download_reads(clf, reads[0].size), clf.mask_reads(reads[0], reads[1]))
+    finally:
+        clf.close()
