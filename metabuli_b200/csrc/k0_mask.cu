@@ -12,10 +12,15 @@
 //
 // Per warp: two 52-double staging rows (alternating steps, so one __syncwarp per step), a 320-letter window of letter codes, and in
 // global scratch one float per letter (the forward background probabilities) plus one double per 16 letters (the rescalings).
+//
+// tests/host/k0_emulation.cpp compiles THIS file for the CPU (MBL_K0_EMULATION: a 128-thread lock-step emulation of one block with
+// the shuffles and barriers the kernel uses) so that the kernel's logic is checked against the goldens in the CPU suite as well.
 #include <algorithm>
 
 #include "host/tantan_model.hpp"
+#ifndef MBL_K0_EMULATION
 #include "kernels.cuh"
+#endif
 
 namespace mbl {
 
@@ -198,6 +203,7 @@ MaskTables make_tables(float mask_prob) {
 
 }  // namespace
 
+#ifndef MBL_K0_EMULATION
 // warps the launch will use and the scratch they need: every warp owns `stride` floats and stride / 16 + 1 doubles
 MaskPlan plan_mask(uint32_t n_reads, uint64_t max_len, int sm_count) {
     MaskPlan p{};
@@ -221,5 +227,7 @@ void launch_mask(uint8_t* bases, const uint64_t* off, uint32_t n_reads, float ma
     cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
     tantan_mask_kernel<<<plan.blocks, kMaskWarps * 32, 0, st>>>(bases, off, n_reads, tb, prob_scratch, scale_scratch, plan.stride, counter);
 }
+
+#endif  // MBL_K0_EMULATION
 
 }  // namespace mbl

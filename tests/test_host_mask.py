@@ -57,3 +57,28 @@ def test_empty_batch_and_bad_arguments():
     off = np.zeros(1, dtype=np.uint64)
     assert lib.mbl_mask_reads(None, off.ctypes.data_as(C.c_void_p), 0, C.c_float(0.9), 1) == 0
     assert lib.mbl_mask_reads(None, None, 0, C.c_float(0.9), 1) == _ffi.MBL_E_BAD_ARG
+
+
+def test_device_kernel_source_under_cpu_emulation(golden_dir):
+    """The source of K0 (csrc/k0_mask.cu) compiled for the CPU by tests/host/k0_emulation.cpp — one block of four warps as 128
+    lock-step host threads — against the reference's per-letter golden: odd reads, tandem repeats around the 50-offset limit and
+    reads of 1000 / 1001 / 4097 letters (the code window moves in both sweeps).  The GPU suite runs the same inputs on the device."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "host", "k0_emulation.cpp")
+    out = os.path.join(root, "tests", "host", "_build", "k0_emulation")
+    deps = [src, os.path.join(root, "metabuli_b200", "csrc", "k0_mask.cu"), os.path.join(root, "metabuli_b200", "csrc", "host", "tantan_model.hpp")]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-ffp-contract=off", "-mfma", "-pthread", src, "-o", out])
+    b, o = synth_cases.mask_misc_reads()
+    n_reads = 33                                     # up to and including the 4097-letter read; the 20 kb one is left to the GPU
+    assert int(o[n_reads] - o[n_reads - 1]) == 4097
+    lines = _lines(b, o[: n_reads + 1])
+    want_all = gzip.open(os.path.join(golden_dir, "synth", "mask_misc.masked.gz"), "rb").read()
+    n_line = int(o[-1]) + o.size - 1
+    k = synth_cases.MASK_MISC_PROBS.index(0.9)
+    want = want_all[k * n_line:k * n_line + len(lines)]
+    r = subprocess.run([out, "0.9"], input=lines, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert r.stdout == want
