@@ -348,7 +348,7 @@ int classify(int argc, char** argv) {
     std::string fail_msg;
     size_t n_batches = 0, total_reads = 0, total_bases = 0;
     auto fail_with = [&](const std::string& m) { std::lock_guard<std::mutex> lk(mu); if (!failed) { failed = true; fail_msg = m; } cv.notify_all(); };
-    auto pin = [&](Batch* bt, int k, const std::vector<char>& v) {          // (re)register a batch buffer when it moved or grew
+    auto pin = [&](Batch* bt, int k, const mblhost::ByteBuf& v) {          // (re)register a batch buffer when it moved or grew
         if (v.data() == bt->pinned[k] && v.capacity() == bt->pinned_cap[k]) return;
         if (bt->pinned[k]) mbl_host_unregister(const_cast<void*>(bt->pinned[k]));
         bt->pinned[k] = nullptr; bt->pinned_cap[k] = 0;

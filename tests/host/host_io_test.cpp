@@ -54,6 +54,39 @@ unsigned long long hio_format(unsigned long long n, const mbl_read_result* res, 
     for (auto& r : rows) g_text += r;
     return g_text.size();
 }
+// put_float_g against printf("%g") on every `stride`-th float of [1e-4, 10) (plus a margin into the snprintf fallback on both
+// sides) and on a list of values outside it; -> number of mismatches
+unsigned long long hio_check_float_g(unsigned stride, unsigned threads) {
+    float lo = 1e-4f, hi = 10.0f;
+    uint32_t a, b;
+    memcpy(&a, &lo, 4); memcpy(&b, &hi, 4);
+    a -= 1000; b += 1000;
+    std::vector<unsigned long long> bad(threads ? threads : 1, 0);
+    const unsigned T = (unsigned)bad.size();
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t) th.emplace_back([&, t] {
+        char x[64], y[64];
+        for (uint64_t u = (uint64_t)a + (uint64_t)t * stride; u <= b; u += (uint64_t)T * stride) {
+            const uint32_t v = (uint32_t)u;
+            float f;
+            memcpy(&f, &v, 4);
+            *mblhost::put_float_g(x, f) = 0;
+            snprintf(y, sizeof y, "%g", (double)f);
+            if (strcmp(x, y)) ++bad[t];
+        }
+    });
+    for (auto& x : th) x.join();
+    unsigned long long n = 0;
+    for (auto v : bad) n += v;
+    const float odd[] = {0.0f, -0.0f, 1e-5f, 9.99999e-5f, 10.0f, 123456.0f, 1e6f, 1e7f, -0.5f, 1e-30f, 3.4e38f, NAN, INFINITY, 0.99999964f, 0.9999995f, 9.999996f};
+    for (float f : odd) {
+        char x[64], y[64];
+        *mblhost::put_float_g(x, f) = 0;
+        snprintf(y, sizeof y, "%g", (double)f);
+        if (strcmp(x, y)) ++n;
+    }
+    return n;
+}
 // <jobid>_report.tsv from per-read classifications (internal taxids) and the taxonomy arrays
 unsigned long long hio_report(unsigned long long n_reads, const int32_t* classification, unsigned long long n_nodes, int32_t max_taxid,
                               const int32_t* node_taxid, const int32_t* node_parent, const int32_t* D, const int32_t* orig,

@@ -225,3 +225,11 @@ def test_cpp_report_on_the_reference_fixture(hio, db, fixtures_dir, golden_dir):
                             t.node_parent.ctypes.data_as(C.c_void_p), t.D.ctypes.data_as(C.c_void_p),
                             orig.ctypes.data_as(C.c_void_p) if orig is not None else None, ranks, names)
     assert hio.hio_text()[:length] == gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_se_report.tsv.gz"), "rb").read()
+
+
+def test_fast_float_formatting_equals_printf_g(hio):
+    """The TSV's score column is `ostream << float` = printf("%g") (Reporter.cpp:62).  The formatter's integer fast path covers
+    1e-4 <= v < 10: compared with snprintf on EVERY float of that range (139 M values) and on values outside it."""
+    hio.hio_check_float_g.restype = C.c_ulonglong
+    hio.hio_check_float_g.argtypes = [C.c_uint, C.c_uint]
+    assert hio.hio_check_float_g(1, os.cpu_count() or 4) == 0
