@@ -374,11 +374,17 @@ int classify(int argc, char** argv) {
                 if (failed) return;
                 bt = free_list.front(); free_list.pop_front();
             }
-            if (!s1.next(bt->r1, step, T, &err)) { fail_with(err); return; }
             if (par.seqMode == 2) {
-                if (!s2.next(bt->r2, step, T, &err)) { fail_with(err); return; }
+                // the two mate files are read, inflated and parsed side by side
+                std::string err2;
+                bool ok2 = true;
+                std::thread mate2([&] { ok2 = s2.next(bt->r2, step, std::max(1u, T / 2), &err2); });
+                const bool ok1 = s1.next(bt->r1, step, std::max(1u, T - T / 2), &err);
+                mate2.join();
+                if (!ok1) { fail_with(err); return; }
+                if (!ok2) { fail_with(err2); return; }
                 if (bt->r1.size() != bt->r2.size()) { fail_with("The number of reads in the two files are not equal."); return; }
-            }
+            } else if (!s1.next(bt->r1, step, T, &err)) { fail_with(err); return; }
             if (par.maskMode && par.maskHost) {
                 // the names and lengths the Reporter prints stay the file's; only the letters the extractor sees change
                 if (mbl_mask_reads(bt->r1.bases.data(), bt->r1.offsets.data(), (uint32_t)bt->r1.size(), par.maskProb, (int)T) != MBL_OK ||
