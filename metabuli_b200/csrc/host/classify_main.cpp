@@ -7,6 +7,7 @@
 // Host work kept here: argument checks, db.parameters, taxonomyDB / taxID_list parsing, FASTA/FASTQ
 // reading (kseq semantics), batching, and writing <jobid>_classifications.tsv.  No CPU fallback: if the
 // library cannot reach a CUDA device the run stops with an error.
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -54,6 +55,35 @@ std::vector<T> slurp(const std::string& path) {
     fclose(f);
     return v;
 }
+
+// The index files are mapped, not copied (the reference does the same: mmapData, KmerMatcher.cpp:137-139): a 40 GiB diffIdx is
+// neither read into a second host copy nor zero-filled first; the library's upload reads the pages straight from the page cache.
+template <class T>
+class MappedFile {
+public:
+    explicit MappedFile(const std::string& path) {
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) die("cannot open " + path);
+        struct stat st;
+        if (fstat(fd, &st) != 0) die("cannot stat " + path);
+        bytes_ = (size_t)st.st_size;
+        if (bytes_) {
+            p_ = mmap(nullptr, bytes_, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p_ == MAP_FAILED) die("cannot map " + path);
+            madvise(p_, bytes_, MADV_SEQUENTIAL);
+            madvise(p_, bytes_, MADV_WILLNEED);
+        }
+        close(fd);
+    }
+    MappedFile(const MappedFile&) = delete;
+    MappedFile& operator=(const MappedFile&) = delete;
+    ~MappedFile() { if (p_ && p_ != MAP_FAILED) munmap(p_, bytes_); }
+    const T* data() const { return static_cast<const T*>(p_); }
+    size_t size() const { return bytes_ / sizeof(T); }
+private:
+    void* p_ = nullptr;
+    size_t bytes_ = 0;
+};
 
 // ---- taxonomyDB (TaxonomyWrapper.cpp:363-421) -------------------------------------------------------------
 struct TaxonomyHost {
@@ -256,8 +286,8 @@ int classify(int argc, char** argv) {
     TaxonomyHost tax;
     tax.load(dbDir + "/taxonomyDB");
     std::vector<int32_t> t2s = tax.taxid2species(dbDir + "/taxID_list");
-    std::vector<uint16_t> diff = slurp<uint16_t>(dbDir + "/diffIdx");
-    std::vector<int32_t> info = slurp<int32_t>(dbDir + "/info");
+    const MappedFile<uint16_t> diff(dbDir + "/diffIdx");
+    const MappedFile<int32_t> info(dbDir + "/info");
     std::vector<uint64_t> split = slurp<uint64_t>(dbDir + "/split");
 
     // one context per device, each holding a replica of the index (the host arrays are shared)
@@ -335,7 +365,13 @@ int classify(int argc, char** argv) {
     };
     // index-sharded: a batch is one exchange round over all devices (receive buffers and match buffers are sized by what one
     // round moves: 1.25 M reads or pairs per device by default)
-    const size_t step = par.batchReads ? par.batchReads : (sharded ? (size_t)1250000 * G : (size_t)8000000);
+    // Default batch (replicas): every batch streams the whole index through the merge kernel once (~4.6 ms per GiB on a B200,
+    // DESIGN §7) while the host needs ~0.1 us per read to parse and format it (§6), so a batch of ~110 k reads per GiB of index
+    // keeps the device's fixed cost under half of the host's time for the same batch; smaller batches than that starve the GPU,
+    // larger ones only delay the first output and stop the reader and the writer from overlapping.  Clamped to [1 M, 8 M].
+    const double index_gib = (2.0 * (double)diff.size() + 4.0 * (double)info.size()) / (double)(1ull << 30);
+    const size_t auto_step = (size_t)std::min(8.0e6, std::max(1.0e6, 110.0e3 * index_gib));
+    const size_t step = par.batchReads ? par.batchReads : (sharded ? (size_t)1250000 * G : auto_step);
     const size_t n_batches_in_flight = sharded ? 4 : 2 * G + 2;
     std::vector<std::unique_ptr<Batch>> pool;
     for (size_t i = 0; i < n_batches_in_flight; ++i) pool.emplace_back(new Batch());

@@ -21,6 +21,7 @@ struct mbl_ctx {
     // staged batch (copied: the double keeps no pointers into the caller's buffers)
     std::vector<orc::Read> m1, m2;
     bool staged = false, paired = false;
+    uint32_t staged_n = 0;
     // results of the last classified batch
     std::vector<mbl_read_result> res;
     std::vector<int32_t> pairs;
@@ -30,7 +31,12 @@ struct mbl_ctx {
 namespace {
 int fail(mbl_ctx* c, int rc, const std::string& m) { if (c) c->err = m; return rc; }
 
+// MBL_STUB_NULL=1: no classification at all (every read comes back unclassified at once) — what is left is the host's own
+// pipeline, so the CLI's wall time is its host-side ceiling (tools/host_ceiling.sh)
+bool null_mode() { static const bool on = getenv("MBL_STUB_NULL") != nullptr; return on; }
+
 void stage(mbl_ctx* c, const mbl_batch* b) {
+    if (null_mode()) { c->staged_n = b->n_reads; c->staged = true; return; }
     auto fill = [&](const char* bases, const uint64_t* off, std::vector<orc::Read>& out) {
         out.assign(b->n_reads, orc::Read());
         std::string all(bases, bases + off[b->n_reads]);
@@ -44,6 +50,7 @@ void stage(mbl_ctx* c, const mbl_batch* b) {
 }
 
 int classify_staged(mbl_ctx* c) {
+    if (null_mode()) { c->res.assign(c->staged_n, mbl_read_result{}); c->pairs.clear(); c->stats = mbl_stats{}; c->staged = false; return MBL_OK; }
     orc::Options opt;
     opt.seqMode = c->cfg.seq_mode; opt.minScore = c->cfg.min_score; opt.minSpScore = c->cfg.min_sp_score; opt.tieRatio = c->cfg.tie_ratio;
     opt.minConsCnt = c->cfg.min_cons_cnt; opt.minConsCntEuk = c->cfg.min_cons_cnt_euk; opt.accessionLevel = c->cfg.accession_level;

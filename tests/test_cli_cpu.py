@@ -108,3 +108,15 @@ def test_unequal_mate_files_are_an_error(cli, tmp_path):
     r = subprocess.run([cli, "classify", "--seq-mode", "2", "--threads", "2"] + files + [db_dir, str(tmp_path), "job"], capture_output=True, text=True,
                        timeout=300, env=env)
     assert r.returncode != 0 and "The number of reads in the two files are not equal." in (r.stdout + r.stderr)
+
+
+@pytest.mark.parametrize("devices,batch", [("0,1,2", 333), ("0,0", 1250)])
+def test_replica_workers_keep_the_read_order(cli, devices, batch, fixtures_dir, golden_dir, tmp_path):
+    """--devices a,b,c: one worker thread per context, batches handed to whichever is free, rows written in input order (the
+    double ignores the device ordinal, so this is the host's scheduling and ordering logic alone)."""
+    reads = [os.path.join(fixtures_dir, "reads", f"ERR9594652_5000_{k}.fna.gz") for k in (1, 2)]
+    args = ["--seq-mode", "2", "--threads", "4", "--devices", devices, "--batch-reads", str(batch)] + reads
+    tsv, report, log = _run(cli, args, os.path.join(fixtures_dir, "db_in"), str(tmp_path))
+    assert tsv == gzip.open(os.path.join(golden_dir, "ref_tsv", "in_pe_classifications.tsv.gz"), "rb").read()
+    assert report == gzip.open(os.path.join(golden_dir, "ref_tsv", "in_pe_report.tsv.gz"), "rb").read()
+    assert "completed on %d GPU(s)" % len(devices.split(",")) in log
