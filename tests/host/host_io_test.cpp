@@ -1,6 +1,7 @@
 // TEST HARNESS for metabuli_b200/csrc/host/fastx_tsv.hpp (the C++ host's parallel FASTA/FASTQ reader and TSV row formatter):
 // C entry points so the CPU tests can compare them with the Python mirror (metabuli_b200/fastx.py, Classifier.format_tsv).
 #include "../../metabuli_b200/csrc/host/fastx_tsv.hpp"
+#include "../../metabuli_b200/csrc/host/fast_inflate.hpp"
 
 namespace {
 mblhost::ReadSet g_reads;
@@ -53,6 +54,24 @@ unsigned long long hio_format(unsigned long long n, const mbl_read_result* res, 
     g_text.clear();
     for (auto& r : rows) g_text += r;
     return g_text.size();
+}
+// GzInflater on a gzip stream in memory, read in pieces of `piece` bytes (0 = one call for everything): 0 when the output equals
+// want[0, want_n), 1 on a decoder error (text via hio_text), 2 on different output, 3 when more bytes came than expected
+int hio_inflate_check(const unsigned char* gz, unsigned long long n, const unsigned char* want, unsigned long long want_n, unsigned long long piece) {
+    mblhost::GzInflater inf;
+    inf.attach(gz, (size_t)n);
+    std::vector<char> out((size_t)want_n + 1024);
+    size_t got = 0;
+    while (true) {
+        const size_t ask = piece ? std::min<size_t>((size_t)piece, out.size() - got) : out.size() - got;
+        if (!ask) return 3;
+        const long long r = inf.read(out.data() + got, ask);
+        if (r < 0) { g_text = inf.error(); return 1; }
+        got += (size_t)r;
+        if ((size_t)r < ask) break;
+    }
+    if (got != want_n || (want_n && memcmp(out.data(), want, (size_t)want_n) != 0)) return 2;
+    return 0;
 }
 // put_float_g against printf("%g") on every `stride`-th float of [1e-4, 10) (plus a margin into the snprintf fallback on both
 // sides) and on a list of values outside it; -> number of mismatches

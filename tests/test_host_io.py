@@ -233,3 +233,72 @@ def test_fast_float_formatting_equals_printf_g(hio):
     hio.hio_check_float_g.restype = C.c_ulonglong
     hio.hio_check_float_g.argtypes = [C.c_uint, C.c_uint]
     assert hio.hio_check_float_g(1, os.cpu_count() or 4) == 0
+
+
+def _gzip_streams():
+    """(label, compressed, plain) over block types, levels, strategies, window sizes and contents."""
+    import zlib
+    rng = np.random.default_rng(11)
+    dna = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 300000)])
+    fastq = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, dna[i * 100:i * 100 + 100], bytes(rng.integers(33, 74, 100).astype(np.uint8))) for i in range(1500))
+    texts = {
+        "empty": b"", "one": b"A", "dna": dna, "fastq": fastq, "random": bytes(rng.integers(0, 256, 200000).astype(np.uint8)),
+        "zeros": bytes(400000), "run": b"AC" * 150000, "period7": b"ACGTTGA" * 40000,
+        "far": dna[:40000] + dna[:40000] + dna[5000:38000],                         # distances close to 32 KiB
+        "skew": bytes(np.minimum(rng.geometric(0.02, 300000), 255).astype(np.uint8)),   # long Huffman codes (sub-tables)
+    }
+    out = []
+    for name, t in texts.items():
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+                for wbits in (31, 25):
+                    if wbits == 25 and (level != 6 or strategy != zlib.Z_DEFAULT_STRATEGY):
+                        continue
+                    c = zlib.compressobj(level, zlib.DEFLATED, wbits, 8, strategy)
+                    out.append(("%s/l%d/s%d/w%d" % (name, level, strategy, wbits), c.compress(t) + c.flush(), t))
+    # several members, an FEXTRA / FNAME / FCOMMENT / FHCRC header, sync-flush blocks (empty stored blocks), trailing zero padding
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    parts = c.compress(dna[:1000]) + c.flush(zlib.Z_SYNC_FLUSH) + c.compress(dna[1000:70000]) + c.flush(zlib.Z_FULL_FLUSH) + c.compress(dna[70000:]) + c.flush()
+    out.append(("flushes", parts, dna))
+    m1 = zlib.compressobj(9, zlib.DEFLATED, 31); a = m1.compress(fastq[:5000]) + m1.flush()
+    m2 = zlib.compressobj(1, zlib.DEFLATED, 31); b = m2.compress(fastq[5000:]) + m2.flush()
+    out.append(("members", a + b + bytes(37), fastq))
+    raw = zlib.compressobj(6, zlib.DEFLATED, -15); body = raw.compress(dna) + raw.flush()
+    import struct
+    hdr = b"\x1f\x8b\x08" + bytes([4 | 8 | 16 | 2]) + b"\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC\x02\x00\x10\x00" + b"name.fq\0" + b"a comment\0" + b"\x12\x34"
+    out.append(("header-fields", hdr + body + struct.pack("<II", zlib.crc32(dna), len(dna) & 0xFFFFFFFF), dna))
+    return out
+
+
+def test_own_inflate_equals_zlib(hio):
+    """The reader's gzip decoder (csrc/host/fast_inflate.hpp) against zlib-written streams: stored, fixed and dynamic blocks, every
+    strategy, 8 KiB..32 KiB windows, long codes, far distances, members / header fields / flushes / padding; the output is taken
+    in one call, in odd pieces and byte by byte (matches resumed across calls, history in front of the buffer)."""
+    hio.hio_inflate_check.restype = C.c_int
+    hio.hio_inflate_check.argtypes = [C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong, C.c_ulonglong]
+    for label, comp, plain in _gzip_streams():
+        pieces = (0, 1, 263, 40000) if len(plain) <= 70000 or label.startswith(("far", "members", "flushes")) else (0, 263, 40000)
+        for piece in pieces:
+            rc = hio.hio_inflate_check(comp, len(comp), plain, len(plain), piece)
+            assert rc == 0, (label, piece, rc, hio.hio_text())
+
+
+def test_own_inflate_rejects_damaged_streams(hio):
+    """Truncations and bit flips: an error or (for flips the format cannot see) a CRC / length mismatch — never a crash, never
+    silently different output."""
+    import zlib
+    hio.hio_inflate_check.restype = C.c_int
+    hio.hio_inflate_check.argtypes = [C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong, C.c_ulonglong]
+    rng = np.random.default_rng(12)
+    plain = b"".join(b">r%d\n%s\n" % (i, bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 150)])) for i in range(400))
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    comp = c.compress(plain) + c.flush()
+    assert hio.hio_inflate_check(comp, len(comp), plain, len(plain), 0) == 0
+    for cut in (1, 5, 10, 11, 50, len(comp) // 2, len(comp) - 9, len(comp) - 8, len(comp) - 1):
+        assert hio.hio_inflate_check(comp[:cut], cut, plain, len(plain), 0) == 1, cut
+    for k in range(600):
+        pos = int(rng.integers(0, len(comp)))
+        bad = bytearray(comp)
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        rc = hio.hio_inflate_check(bytes(bad), len(bad), plain, len(plain), int(rng.choice([0, 97])))
+        assert rc == 1 or (rc == 0 and 4 <= pos < 10), (pos, rc)      # MTIME / XFL / OS bytes of the header carry no checked information
