@@ -7,8 +7,9 @@
 // three literals are emitted per refill, and matches are copied eight bytes at a time.  Output is produced into the caller's
 // buffer in exact amounts (a match that does not fit is resumed by the next call), with a 32 KiB history kept across calls.
 // Every member's CRC-32 and length are verified (zlib's crc32() is used for that), members may be concatenated (bgzip files),
-// and any malformed stream is an error — there is no fallback.  tests/test_host_io.py compares it with zlib on every compression
-// level and strategy, stored / fixed / dynamic blocks, multi-member files and adversarial call patterns (1-byte outputs).
+// and any malformed stream is an error — there is no fallback.  On top of the serial decoder, GzParallel (end of this file)
+// decodes ONE stream with several threads.  tests/test_host_io.py compares both with zlib on every compression level and
+// strategy, stored / fixed / dynamic blocks, multi-member files, adversarial call patterns (1-byte outputs) and damaged streams.
 #pragma once
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -17,11 +18,45 @@
 #include <zlib.h>
 
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
+#include <cstdlib>
+#include <memory>
+#include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace mblhost {
+
+// growable array without value-initialisation (decoded symbols; a std::vector would zero-fill every growth)
+template <class T>
+class RawBuf {
+public:
+    RawBuf() = default;
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    ~RawBuf() { free(p_); }
+    T* data() { return p_; }
+    const T* data() const { return p_; }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    void clear() { n_ = 0; }
+    void resize(size_t n) {                                       // keeps the first min(n, size()) elements; new ones are NOT initialised
+        if (n > cap_) {
+            const size_t c = std::max(n, cap_ + cap_ / 2);
+            T* q = static_cast<T*>(realloc(p_, c * sizeof(T)));
+            if (!q) throw std::bad_alloc();
+            p_ = q; cap_ = c;
+        }
+        n_ = n;
+    }
+    T& operator[](size_t i) { return p_[i]; }
+    const T& operator[](size_t i) const { return p_[i]; }
+private:
+    T* p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+};
 
 class GzInflater {
 public:
@@ -52,7 +87,8 @@ public:
         state_ = kMemberHeader;
         hist_len_ = 0; pending_len_ = 0; stored_left_ = 0;
         failed_ = false; eof_ = false;
-        error_.clear();
+        error_ = nullptr;
+        base_ = data;
         return true;
     }
     static bool looks_gzip(const std::string& path) {
@@ -68,7 +104,7 @@ public:
         map_ = nullptr; size_ = 0; in_ = end_ = nullptr;
     }
     bool eof() const { return eof_; }
-    const std::string& error() const { return error_; }
+    std::string error() const { return error_ ? std::string("gzip: ") + error_ : std::string(); }
 
     // Produces up to cap bytes at out; returns the number produced (less than cap only at the end of the input), or -1 on a
     // malformed stream (error() says why).
@@ -99,7 +135,7 @@ public:
                 }
                 case kHuffman: {
                     uint8_t* const start = out;
-                    const int r = huffman(out0, out, out_end);
+                    const int r = huffman<uint8_t>(out0, out, out_end);
                     account(start, (size_t)(out - start));
                     if (r < 0) return fail_ret();
                     if (r == 1) state_ = final_ ? kTrailer : kBlockHeader;       // end of block
@@ -124,7 +160,7 @@ private:
     struct Entry { uint16_t val; uint8_t bits; uint8_t op; };
 
     long long fail_ret() { failed_ = true; return -1; }
-    void set_err(const char* m) { if (error_.empty()) error_ = std::string("gzip: ") + m; }
+    void set_err(const char* m) { if (!error_) error_ = m; }
 
     void account(const uint8_t* p, size_t n) {
         if (!n) return;
@@ -358,30 +394,40 @@ private:
         return true;
     }
 
-    // copies len bytes from dist back; the source may lie before this call's buffer (history)
-    inline bool copy_match(uint8_t* const out0, uint8_t*& out, uint32_t len, uint32_t dist) {
+    // copies len symbols from dist back; the source may lie before this call's buffer: bytes come from the history, and in the
+    // 16-bit mode of the parallel decoder (the 32 KiB in front of the segment are not known yet) they become markers
+    // 256 + position in that window, resolved once the previous segment is complete
+    template <class Sym>
+    inline bool copy_match(Sym* const out0, Sym*& out, uint32_t len, uint32_t dist) {
         const size_t have = (size_t)(out - out0);
         if (dist > have) {
-            const size_t back = dist - have;                      // bytes the source starts before out0
-            if (back > hist_len_) { set_err("distance reaches before the start of the data"); return false; }
-            const uint8_t* h = hist_.data() + hist_len_ - back;
-            while (len && h < hist_.data() + hist_len_) { *out++ = *h++; --len; }
-            // whatever is left continues at out0 (dist bytes behind out again)
+            size_t back = dist - have;                            // symbols the source starts before out0
+            if (sizeof(Sym) == 2) {
+                if (back > kWindow) { set_err("distance reaches before the window"); return false; }
+                while (len && back) { *out++ = (Sym)(256 + (kWindow - back)); --back; --len; }
+            } else {
+                if (back > hist_len_) { set_err("distance reaches before the start of the data"); return false; }
+                const uint8_t* h = hist_.data() + hist_len_ - back;
+                while (len && h < hist_.data() + hist_len_) { *out++ = (Sym)*h++; --len; }
+            }
+            // whatever is left continues at out0 (dist symbols behind out again)
         }
-        const uint8_t* src = out - dist;
+        const Sym* src = out - dist;
         while (len--) *out++ = *src++;
         return true;
     }
 
     // Decodes symbols of the current block into [out, out_end).  Returns 1 at the end of the block, 0 when the output is full,
     // -1 on error.
-    int huffman(uint8_t* const out0, uint8_t*& out, uint8_t* const out_end) {
+    template <class Sym>
+    int huffman(Sym* const out0, Sym*& out, Sym* const out_end) {
+        constexpr uint32_t kWord = 8 / sizeof(Sym);                // symbols per 8-byte copy
         const Entry* const lit = lit_;
         const Entry* const dst = dist_;
         const uint32_t lit_mask = (1u << kLitBits) - 1, dist_mask = (1u << kDistBits) - 1;
         if (pending_len_) {                                       // a match the previous call could not finish
             const uint32_t n = (uint32_t)std::min<size_t>(pending_len_, (size_t)(out_end - out));
-            if (!copy_match(out0, out, n, pending_dist_)) return -1;
+            if (!copy_match<Sym>(out0, out, n, pending_dist_)) return -1;
             pending_len_ -= n;
             if (pending_len_) return 0;
         }
@@ -391,15 +437,15 @@ private:
             Entry e = lit[bitbuf_ & lit_mask];
             if (e.op == 0x10) {                                   // up to three literals per refill (3 x 15 bits)
                 bitbuf_ >>= e.bits; bitcnt_ -= e.bits;
-                *out++ = (uint8_t)e.val;
+                *out++ = (Sym)e.val;
                 e = lit[bitbuf_ & lit_mask];
                 if (e.op == 0x10) {
                     bitbuf_ >>= e.bits; bitcnt_ -= e.bits;
-                    *out++ = (uint8_t)e.val;
+                    *out++ = (Sym)e.val;
                     e = lit[bitbuf_ & lit_mask];
                     if (e.op == 0x10) {
                         bitbuf_ >>= e.bits; bitcnt_ -= e.bits;
-                        *out++ = (uint8_t)e.val;
+                        *out++ = (Sym)e.val;
                         continue;
                     }
                 }
@@ -408,7 +454,7 @@ private:
             if (e.op & 0x40) {                                    // code longer than the primary table
                 bitbuf_ >>= e.bits; bitcnt_ -= e.bits;
                 e = lit[e.val + (bitbuf_ & ((1u << (e.op & 0x0F)) - 1))];
-                if (e.op == 0x10) { bitbuf_ >>= e.bits; bitcnt_ -= e.bits; *out++ = (uint8_t)e.val; continue; }
+                if (e.op == 0x10) { bitbuf_ >>= e.bits; bitcnt_ -= e.bits; *out++ = (Sym)e.val; continue; }
             }
             bitbuf_ >>= e.bits; bitcnt_ -= e.bits;
             if (e.op >= 0x10) {
@@ -429,22 +475,22 @@ private:
             const uint32_t dist = d.val + (uint32_t)(bitbuf_ & ((1u << d.op) - 1));
             bitbuf_ >>= d.op; bitcnt_ -= d.op;
             if (dist > (size_t)(out - out0)) {
-                if (!copy_match(out0, out, len, dist)) return -1;
-            } else if (dist >= 8) {                                // eight bytes at a time; writes up to 15 bytes past the match
-                const uint8_t* s = out - dist;
-                uint8_t* o = out;
-                uint8_t* const oe = out + len;
+                if (!copy_match<Sym>(out0, out, len, dist)) return -1;
+            } else if (dist >= kWord) {                            // eight bytes at a time; writes up to 2 words past the match
+                const Sym* s = out - dist;
+                Sym* o = out;
+                Sym* const oe = out + len;
                 uint64_t w;
                 memcpy(&w, s, 8); memcpy(o, &w, 8);
-                memcpy(&w, s + 8, 8); memcpy(o + 8, &w, 8);       // most matches in sequence data are shorter than 16
-                if (len > 16) {
-                    s += 16; o += 16;
-                    do { memcpy(&w, s, 8); memcpy(o, &w, 8); s += 8; o += 8; } while (o < oe);
+                memcpy(&w, s + kWord, 8); memcpy(o + kWord, &w, 8);    // most matches in sequence data are shorter than 16
+                if (len > 2 * kWord) {
+                    s += 2 * kWord; o += 2 * kWord;
+                    do { memcpy(&w, s, 8); memcpy(o, &w, 8); s += kWord; o += kWord; } while (o < oe);
                 }
                 out = oe;
             } else {
-                const uint8_t* s = out - dist;
-                uint8_t* const oe = out + len;
+                const Sym* s = out - dist;
+                Sym* const oe = out + len;
                 while (out < oe) *out++ = *s++;
             }
         }
@@ -461,7 +507,7 @@ private:
             if (e.op & 0x80) { set_err("invalid literal/length code"); return -1; }
             if (used + e.bits > bitcnt_) { set_err("truncated stream"); return -1; }
             take(used + e.bits);
-            if (e.op == 0x10) { *out++ = (uint8_t)e.val; continue; }
+            if (e.op == 0x10) { *out++ = (Sym)e.val; continue; }
             if (e.op == 0x20) return 1;
             if (!need(e.op)) return -1;
             const uint32_t len = e.val + take(e.op);
@@ -479,15 +525,86 @@ private:
             if (!need(d.op)) return -1;
             const uint32_t dist = d.val + take(d.op);
             const uint32_t n = (uint32_t)std::min<size_t>(len, (size_t)(out_end - out));
-            if (!copy_match(out0, out, n, dist)) return -1;
+            if (!copy_match<Sym>(out0, out, n, dist)) return -1;
             if (n < len) { pending_len_ = len - n; pending_dist_ = dist; return 0; }
         }
         return 0;
     }
 
+
+    // ---- block-granular interface of the parallel reader (GzParallel) ----------------------------------------------------------
+    uint64_t tell_bits() const { return (uint64_t)(in_ - base_) * 8 - (uint64_t)bitcnt_; }
+    bool seek_bits(uint64_t pos) {
+        in_ = base_ + (pos >> 3);
+        bitbuf_ = 0; bitcnt_ = 0;
+        pending_len_ = 0; stored_left_ = 0;
+        state_ = kBlockHeader;
+        const int skip = (int)(pos & 7);
+        if (in_ > end_) return false;
+        if (skip) { if (!need(skip)) return false; take(skip); }
+        return true;
+    }
+    enum Stop { kAtStop = 0, kPastEnd = 1, kFinalBlock = 2, kFailed = 3 };
+    // Decodes whole blocks from the current block boundary, appending symbols to out, until the position equals one of the
+    // sorted stop positions (checked at block boundaries only), reaches end_bit, or the member's last block is done.
+    template <class Sym>
+    Stop run_blocks(RawBuf<Sym>& out, const uint64_t* stops, size_t n_stops, uint64_t end_bit, size_t* stop_index) {
+        size_t used = out.size();
+        size_t next_stop = 0;
+        for (bool first = true;; first = false) {
+            const uint64_t pos = tell_bits();
+            while (next_stop < n_stops && stops[next_stop] < pos) ++next_stop;
+            if (!first && next_stop < n_stops && stops[next_stop] == pos) { out.resize(used); *stop_index = next_stop; return kAtStop; }
+            if (!first && pos >= end_bit) { out.resize(used); return kPastEnd; }
+            if (!block_header()) { out.resize(used); return kFailed; }
+            if (state_ == kStored) {
+                if ((size_t)(end_ - in_) < stored_left_) { set_err("truncated stored block"); out.resize(used); return kFailed; }
+                out.resize(used + stored_left_);
+                for (uint32_t i = 0; i < stored_left_; ++i) out[used + i] = (Sym)in_[i];
+                used += stored_left_; in_ += stored_left_; stored_left_ = 0;
+            } else if (state_ == kHuffman) {
+                for (;;) {
+                    if (out.size() < used + (1u << 20)) out.resize(used + (4u << 20));
+                    Sym* o = out.data() + used;
+                    const int r = huffman<Sym>(out.data(), o, out.data() + out.size());
+                    used = (size_t)(o - out.data());
+                    if (r < 0) { out.resize(used); return kFailed; }
+                    if (r == 1) break;
+                }
+            }
+            state_ = kBlockHeader;
+            if (final_) { out.resize(used); return kFinalBlock; }
+        }
+    }
+    // Is there a non-final dynamic block at bit position pos whose first symbols decode to text?  (candidate test of the block
+    // search; a false positive is caught later because the previous segment will not end exactly there)
+    bool probe(uint64_t pos) {
+        const uint8_t* p = base_ + (pos >> 3);
+        if (end_ - p < 64) return false;
+        uint64_t w;
+        memcpy(&w, p, 8);
+        w >>= (pos & 7);
+        if ((w & 7) != 4) return false;                           // BFINAL 0, BTYPE 2 (dynamic)
+        const uint32_t hlit = (uint32_t)((w >> 3) & 31) + 257, hdist = (uint32_t)((w >> 8) & 31) + 1;
+        if (hlit > 286 || hdist > 30) return false;
+        error_ = nullptr;
+        if (!seek_bits(pos) || !block_header() || state_ != kHuffman) { error_ = nullptr; return false; }
+        uint16_t buf[1024 + 300];
+        uint16_t* o = buf;
+        const int r = huffman<uint16_t>(buf, o, buf + 1024);
+        if (r < 0) { error_ = nullptr; return false; }
+        if (o - buf < 64 && r != 1) return false;
+        for (const uint16_t* q = buf; q < o; ++q) {
+            const uint16_t c = *q;
+            if (c >= 256) continue;                               // from the unknown window
+            if (!((c >= 32 && c < 127) || c == '\n' || c == '\r' || c == '\t')) return false;
+        }
+        return true;
+    }
+
     void* map_ = nullptr;
     size_t size_ = 0;
-    const uint8_t *in_ = nullptr, *end_ = nullptr;
+    const uint8_t *in_ = nullptr, *end_ = nullptr, *base_ = nullptr;
     uint64_t bitbuf_ = 0;
     int bitcnt_ = 0;
     State state_ = kMemberHeader;
@@ -500,7 +617,226 @@ private:
     size_t hist_len_ = 0;
     uLong crc_ = 0;
     uint64_t member_out_ = 0;
-    std::string error_;
+    const char* error_ = nullptr;
+    friend class GzParallel;
+};
+
+
+// Parallel decoding of ONE gzip stream (the idea of pugz, Kerbiriou & Chikhi 2019, for text): a group of the compressed file is
+// cut into segments; a dynamic block start is searched near every cut (bit by bit: header fields, complete Huffman codes, text-
+// like first symbols); every segment is decoded from its block start by its own thread — the first one continues the stream with
+// the known history, the others do not know the 32 KiB in front of them and emit 16-bit symbols in which a reference into that
+// window is a marker; a segment ends exactly where the next one starts (a searched position that no segment ends on was a false
+// positive and its segment is dropped; the one before it simply runs on).  Then the windows are resolved in order (32 KiB per
+// segment), the bulk in parallel, CRC-32s are combined, and the serial decoder's state is moved to the end of the group.  Anything
+// unusual inside a group (member end, stored or fixed blocks where a cut falls, no block start found) only means fewer segments;
+// the serial decoder handles the rest.  The output is identical by construction and the member's CRC-32 still has to match.
+class GzParallel {
+public:
+    bool open(const std::string& path, std::string* err) { return main_.open(path, err); }
+    bool attach(const uint8_t* data, size_t n) { return main_.attach(data, n); }
+    bool eof() const { return main_.eof(); }
+    std::string error() const { return main_.error(); }
+    // groups decoded in parallel / segments that took part in them / block starts that turned out to be false positives
+    size_t groups() const { return groups_; }
+    size_t segments() const { return segments_; }
+    size_t false_starts() const { return false_starts_; }
+
+    // Appends decoded bytes to dst[at..) (dst is grown as needed): whole blocks, about `want` bytes when the stream allows, at least
+    // one byte unless the input is at its end.  Returns the number of bytes, 0 at the end of the input, -1 on a malformed stream.
+    // Between calls the stream always stands at a block or member boundary.
+    template <class Buf>
+    long long read_some(Buf& dst, size_t at, size_t want, unsigned threads) {
+        const size_t seg_bytes = (size_t)2 << 20;                 // compressed bytes per segment
+        const unsigned T = std::max(1u, threads);
+        GzInflater& m = main_;
+        for (;;) {
+            if (m.failed_) return -1;
+            if (m.eof_) return 0;
+            if (m.state_ == GzInflater::kMemberHeader) {
+                if (!m.skip_zero_padding()) { m.eof_ = true; return 0; }
+                if (!m.parse_header()) { m.failed_ = true; return -1; }
+                m.crc_ = crc32(0L, Z_NULL, 0); m.member_out_ = 0; m.hist_len_ = 0;
+                m.state_ = GzInflater::kBlockHeader;
+            } else if (m.state_ == GzInflater::kTrailer) {
+                if (!m.trailer()) { m.failed_ = true; return -1; }
+                m.state_ = GzInflater::kMemberHeader;
+                continue;
+            }
+            const uint64_t c0 = m.tell_bits();
+            const size_t left = (size_t)(m.end_ - m.base_) - (size_t)(c0 >> 3);
+            const size_t n_seg = std::min<size_t>(T, left / seg_bytes);
+            if (n_seg >= 2) {
+                const long long r = group(dst, at, c0, n_seg, seg_bytes);
+                if (r < 0) return r;
+                if (r > 0) return r;
+                if (m.state_ != GzInflater::kBlockHeader) continue;   // an empty last block ended the member
+            }
+            // serial: the tail of the file, one thread, or a place where no second block start was found
+            serial_.clear();
+            size_t dummy = 0;
+            const uint64_t end_bit = c0 + (uint64_t)std::max<size_t>(want / 4, 1u << 16) * 8;
+            const GzInflater::Stop how = m.run_blocks<uint8_t>(serial_, nullptr, 0, end_bit, &dummy);
+            if (how == GzInflater::kFailed) { m.failed_ = true; return -1; }
+            if (how == GzInflater::kFinalBlock) m.state_ = GzInflater::kTrailer;
+            if (serial_.empty()) continue;                        // blocks without output (sync flushes)
+            if (dst.size() < at + serial_.size()) dst.resize(at + serial_.size());
+            memcpy(dst.data() + at, serial_.data(), serial_.size());
+            m.account(serial_.data(), serial_.size());
+            m.remember(serial_.data(), serial_.size());
+            return (long long)serial_.size();
+        }
+    }
+
+private:
+    struct Seg {
+        uint64_t start = 0, end = 0;
+        RawBuf<uint16_t> sym;                                     // segments 1..: symbols with markers
+        RawBuf<uint8_t> bytes;                                    // segment 0: plain bytes
+        GzInflater::Stop how = GzInflater::kFailed;
+        size_t stop_index = 0;
+        bool found = false;
+    };
+
+    template <class Buf>
+    long long group(Buf& dst, size_t at, uint64_t c0, size_t n_seg, size_t seg_bytes) {
+        const uint8_t* base = main_.base_;
+        const size_t total = (size_t)(main_.end_ - base);
+        if (seg_.size() < n_seg) { seg_.clear(); for (size_t j = 0; j < n_seg; ++j) seg_.emplace_back(new Seg()); }   // buffers are reused
+        struct SegView { std::vector<std::unique_ptr<Seg>>& v; Seg& operator[](size_t j) { return *v[j]; } } seg{seg_};
+        for (size_t j = 0; j < n_seg; ++j) { Seg& x = seg[j]; x.start = x.end = 0; x.how = GzInflater::kFailed; x.stop_index = 0; x.found = false; x.sym.clear(); x.bytes.clear(); }
+        if (dec_.size() < n_seg) dec_.resize(n_seg);
+        for (auto& d : dec_) if (!d) d.reset(new GzInflater());
+        seg[0].start = c0; seg[0].found = true;
+        // 1. block starts near the cuts
+        {
+            std::vector<std::thread> th;
+            for (size_t j = 1; j < n_seg; ++j) th.emplace_back([&, j] {
+                GzInflater& d = *dec_[j];
+                d.attach(base, total);
+                const uint64_t from = ((c0 >> 3) + j * seg_bytes) * 8, to = from + (uint64_t)seg_bytes * 4;   // half a segment
+                for (uint64_t pos = from; pos < to; ++pos)
+                    if (d.probe(pos)) { seg[j].start = pos; seg[j].found = true; break; }
+            });
+            for (auto& t : th) t.join();
+        }
+        std::vector<uint64_t> stops;
+        for (size_t j = 1; j < n_seg; ++j) if (seg[j].found) stops.push_back(seg[j].start);
+        if (stops.empty()) return 0;
+        const uint64_t end_bit = ((c0 >> 3) + n_seg * seg_bytes) * 8;
+        // 2. decode the segments
+        {
+            std::vector<std::thread> th;
+            for (size_t j = 1; j < n_seg; ++j) if (seg[j].found) th.emplace_back([&, j] {
+                GzInflater& d = *dec_[j];
+                d.error_ = nullptr;
+                if (!d.seek_bits(seg[j].start)) { seg[j].how = GzInflater::kFailed; return; }
+                seg[j].sym.clear();
+                seg[j].how = d.run_blocks<uint16_t>(seg[j].sym, stops.data(), stops.size(), end_bit, &seg[j].stop_index);
+                seg[j].end = d.tell_bits();
+            });
+            seg[0].bytes.clear();
+            seg[0].how = main_.run_blocks<uint8_t>(seg[0].bytes, stops.data(), stops.size(), end_bit, &seg[0].stop_index);
+            seg[0].end = main_.tell_bits();
+            for (auto& t : th) t.join();
+        }
+        if (seg[0].how == GzInflater::kFailed) { main_.failed_ = true; return -1; }
+        // 3. the chain of segments that really follow each other
+        std::vector<size_t> chain{0};
+        for (size_t cur = 0; seg[cur].how == GzInflater::kAtStop;) {
+            const uint64_t pos = stops[seg[cur].stop_index];
+            size_t nxt = 0;
+            for (size_t j = 1; j < n_seg; ++j) if (seg[j].found && seg[j].start == pos) nxt = j;
+            if (!nxt || seg[nxt].how == GzInflater::kFailed) {
+                // the segment behind this stop is unusable (cannot happen for a true block start of a well-formed stream): go on serially
+                break;
+            }
+            chain.push_back(nxt);
+            cur = nxt;
+        }
+        Seg& last = seg[chain.back()];
+        // 4. sizes, windows, bytes
+        size_t n_out = seg[0].bytes.size();
+        for (size_t k = 1; k < chain.size(); ++k) n_out += seg[chain[k]].sym.size();
+        if (dst.size() < at + n_out) dst.resize(at + n_out);
+        uint8_t* out = reinterpret_cast<uint8_t*>(dst.data()) + at;
+        if (!seg[0].bytes.empty()) memcpy(out, seg[0].bytes.data(), seg[0].bytes.size());
+        // windows in order: the last 32 KiB in front of every 16-bit segment (history of the stream + what the group has produced)
+        std::vector<std::vector<uint8_t>> window(chain.size());
+        std::vector<size_t> off(chain.size() + 1, 0);
+        off[1] = seg[0].bytes.size();
+        for (size_t k = 1; k < chain.size(); ++k) off[k + 1] = off[k] + seg[chain[k]].sym.size();
+        bool bad_marker = false;
+        std::vector<size_t> invalid_below(chain.size(), 0);       // window positions below this hold no data (start of a member)
+        for (size_t k = 1; k < chain.size(); ++k) {
+            std::vector<uint8_t>& w = window[k];
+            w.assign(GzInflater::kWindow, 0);
+            // bytes in front of segment k: out[0, off[k]) preceded by the stream's history
+            const size_t have = off[k];
+            size_t valid;                                          // how many of the window's last positions hold real data
+            if (have >= GzInflater::kWindow) { memcpy(w.data(), out + have - GzInflater::kWindow, GzInflater::kWindow); valid = GzInflater::kWindow; }
+            else {
+                const size_t from_hist = std::min(main_.hist_len_, GzInflater::kWindow - have);
+                memcpy(w.data() + GzInflater::kWindow - have - from_hist, main_.hist_.data() + main_.hist_len_ - from_hist, from_hist);
+                memcpy(w.data() + GzInflater::kWindow - have, out, have);
+                valid = have + from_hist;
+            }
+            // resolve the tail of segment k now (the next window needs it); the bulk follows in parallel
+            const RawBuf<uint16_t>& sy = seg[chain[k]].sym;
+            const size_t n = sy.size(), tail = std::min<size_t>(n, GzInflater::kWindow);
+            for (size_t i = n - tail; i < n; ++i) {
+                const uint16_t c = sy[i];
+                if (c >= 256 && (size_t)(c - 256) < GzInflater::kWindow - valid) bad_marker = true;
+                out[off[k] + i] = c < 256 ? (uint8_t)c : w[c - 256];
+            }
+            invalid_below[k] = GzInflater::kWindow - valid;
+        }
+        std::vector<char> bad_bulk(chain.size(), 0);
+        std::vector<uLong> part_crc(chain.size(), 0);
+        {
+            std::vector<std::thread> th;
+            for (size_t k = 1; k < chain.size(); ++k) th.emplace_back([&, k] {
+                const RawBuf<uint16_t>& sy = seg[chain[k]].sym;
+                const uint8_t* w = window[k].data();
+                const size_t n = sy.size(), bulk = n - std::min<size_t>(n, GzInflater::kWindow);
+                uint8_t* o = out + off[k];
+                const size_t lo = invalid_below[k];
+                bool bad = false;
+                for (size_t i = 0; i < bulk; ++i) {
+                    const uint16_t c = sy[i];
+                    if (c >= 256 && (size_t)(c - 256) < lo) bad = true;
+                    o[i] = c < 256 ? (uint8_t)c : w[c - 256];
+                }
+                bad_bulk[k] = bad;
+                part_crc[k] = GzInflater::crc32_big(crc32(0L, Z_NULL, 0), o, n);      // the tail was resolved above
+            });
+            part_crc[0] = GzInflater::crc32_big(crc32(0L, Z_NULL, 0), out, off[1]);
+            for (auto& t : th) t.join();
+        }
+        for (char b : bad_bulk) bad_marker |= b != 0;
+        if (bad_marker) { main_.set_err("distance reaches before the start of the data"); main_.failed_ = true; return -1; }
+        // 5. the serial decoder continues behind the group
+        if (chain.size() > 1) {
+            if (!main_.seek_bits(last.end)) { main_.failed_ = true; return -1; }
+        }
+        if (last.how == GzInflater::kFinalBlock) main_.state_ = GzInflater::kTrailer;
+        else if (last.how == GzInflater::kFailed) { main_.failed_ = true; main_.error_ = dec_[chain.back()]->error_; return -1; }
+        for (size_t k = 0; k < chain.size(); ++k)                 // CRC-32 of the group from the segments' own CRCs
+            if (off[k + 1] > off[k]) main_.crc_ = crc32_combine(main_.crc_, part_crc[k], (z_off_t)(off[k + 1] - off[k]));
+        main_.member_out_ += n_out;
+        main_.remember(out, n_out);
+        if (chain.size() > 1) {
+            ++groups_; segments_ += chain.size();
+            for (size_t j = 1; j <= chain.back(); ++j) if (seg[j].found && std::find(chain.begin(), chain.end(), j) == chain.end()) ++false_starts_;
+        }
+        return (long long)n_out;
+    }
+
+    GzInflater main_;
+    std::vector<std::unique_ptr<GzInflater>> dec_;
+    RawBuf<uint8_t> serial_;
+    std::vector<std::unique_ptr<Seg>> seg_;
+    size_t groups_ = 0, segments_ = 0, false_starts_ = 0;
 };
 
 }  // namespace mblhost

@@ -73,6 +73,24 @@ int hio_inflate_check(const unsigned char* gz, unsigned long long n, const unsig
     if (got != want_n || (want_n && memcmp(out.data(), want, (size_t)want_n) != 0)) return 2;
     return 0;
 }
+// GzParallel on a gzip stream in memory with `threads` decoder threads, taken in calls of about `want` bytes: same return codes
+int hio_parallel_inflate_check(const unsigned char* gz, unsigned long long n, const unsigned char* want, unsigned long long want_n,
+                               unsigned threads, unsigned long long piece) {
+    mblhost::GzParallel inf;
+    inf.attach(gz, (size_t)n);
+    mblhost::ByteBuf out;
+    size_t got = 0;
+    while (true) {
+        const long long r = inf.read_some(out, got, (size_t)piece, threads);
+        if (r < 0) { g_text = inf.error(); return 1; }
+        if (r == 0) break;
+        got += (size_t)r;
+        if (got > want_n + 1024) return 3;
+    }
+    g_text = "groups " + std::to_string(inf.groups()) + " segments " + std::to_string(inf.segments()) + " false " + std::to_string(inf.false_starts());
+    if (got != want_n || (want_n && memcmp(out.data(), want, (size_t)want_n) != 0)) return 2;
+    return 0;
+}
 // put_float_g against printf("%g") on every `stride`-th float of [1e-4, 10) (plus a margin into the snprintf fallback on both
 // sides) and on a list of values outside it; -> number of mismatches
 unsigned long long hio_check_float_g(unsigned stride, unsigned threads) {

@@ -302,3 +302,55 @@ def test_own_inflate_rejects_damaged_streams(hio):
         bad[pos] ^= 1 << int(rng.integers(0, 8))
         rc = hio.hio_inflate_check(bytes(bad), len(bad), plain, len(plain), int(rng.choice([0, 97])))
         assert rc == 1 or (rc == 0 and 4 <= pos < 10), (pos, rc)      # MTIME / XFL / OS bytes of the header carry no checked information
+
+
+def test_parallel_inflate_equals_zlib(hio):
+    """GzParallel (one gzip stream decoded by several threads: block-start search, 16-bit symbols with window markers, in-order
+    resolution) must give zlib's bytes for every thread count — on sequence text at several levels (many dynamic blocks), on a
+    file of several members, on data whose blocks cannot be found (binary: falls back to the serial path) and on small inputs."""
+    import zlib
+    hio.hio_parallel_inflate_check.restype = C.c_int
+    hio.hio_parallel_inflate_check.argtypes = [C.c_char_p, C.c_ulonglong, C.c_char_p, C.c_ulonglong, C.c_uint, C.c_ulonglong]
+    rng = np.random.default_rng(21)
+    L = np.frombuffer(b"ACGT", dtype=np.uint8)
+    n = 150000
+    seqs = L[rng.integers(0, 4, (n, 150))]
+    qual = rng.integers(35, 74, (n, 150)).astype(np.uint8)
+    fastq = b"".join(b"@read%d/1\n%s\n+\n%s\n" % (i, seqs[i].tobytes(), qual[i].tobytes()) for i in range(n))       # ~47 MB
+    fasta = b"".join(b">r%d\n%s\n" % (i, seqs[i].tobytes()) for i in range(n))
+    cases = []
+    for level in (1, 6):
+        c = zlib.compressobj(level, zlib.DEFLATED, 31)
+        cases.append(("fastq-l%d" % level, c.compress(fastq) + c.flush(), fastq))
+    c = zlib.compressobj(1, zlib.DEFLATED, 31)
+    cases.append(("fasta-l1", c.compress(fasta) + c.flush(), fasta))
+    parts = []
+    for k in range(3):
+        c = zlib.compressobj(4, zlib.DEFLATED, 31)
+        parts.append(c.compress(fastq[k * len(fastq) // 3:(k + 1) * len(fastq) // 3]) + c.flush())
+    cases.append(("members", b"".join(parts), fastq))
+    binary = bytes(rng.integers(0, 256, 9_000_000).astype(np.uint8))
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    cases.append(("binary", c.compress(binary) + c.flush(), binary))
+    mixed = fastq[:6_000_000] + binary[:5_000_000] + fastq[6_000_000:14_000_000]
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    cases.append(("mixed", c.compress(mixed) + c.flush(), mixed))
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    cases.append(("small", c.compress(fastq[:100000]) + c.flush(), fastq[:100000]))
+    cases.append(("empty", zlib.compressobj(6, zlib.DEFLATED, 31).flush(), b""))
+    for label, comp, plain in cases:
+        for threads, piece in ((2, 64 << 20), (3, 1 << 20), (8, 64 << 20), (1, 64 << 20)):
+            rc = hio.hio_parallel_inflate_check(comp, len(comp), plain, len(plain), threads, piece)
+            assert rc == 0, (label, threads, piece, rc, hio.hio_text())
+            words = hio.hio_text().decode().split()
+            groups, segments = int(words[1]), int(words[3])
+            if threads >= 2 and label.startswith(("fastq", "fasta", "members")):
+                assert groups >= 1 and segments >= 2 * groups, (label, threads, hio.hio_text())     # the parallel path really ran
+            if threads == 1 or label in ("small", "empty"):
+                assert groups == 0
+    # damage inside the parallel region is an error, not different output
+    label, comp, plain = cases[0]
+    for pos in (len(comp) // 3, len(comp) // 2, len(comp) - 100):
+        bad = bytearray(comp)
+        bad[pos] ^= 0x10
+        assert hio.hio_parallel_inflate_check(bytes(bad), len(bad), plain, len(plain), 4, 64 << 20) == 1, pos
