@@ -660,13 +660,14 @@ public:
                 m.state_ = GzInflater::kBlockHeader;
             } else if (m.state_ == GzInflater::kTrailer) {
                 if (!m.trailer()) { m.failed_ = true; return -1; }
+                small_members_ = m.member_out_ < ((uint64_t)8 << 20);   // bgzip-style files: members of 64 KiB, nothing to split
                 m.state_ = GzInflater::kMemberHeader;
                 continue;
             }
             const uint64_t c0 = m.tell_bits();
             const size_t left = (size_t)(m.end_ - m.base_) - (size_t)(c0 >> 3);
             const size_t n_seg = std::min<size_t>(T, left / seg_bytes);
-            if (n_seg >= 2) {
+            if (n_seg >= 2 && !small_members_) {
                 const long long r = group(dst, at, c0, n_seg, seg_bytes);
                 if (r < 0) return r;
                 if (r > 0) return r;
@@ -837,6 +838,7 @@ private:
     RawBuf<uint8_t> serial_;
     std::vector<std::unique_ptr<Seg>> seg_;
     size_t groups_ = 0, segments_ = 0, false_starts_ = 0;
+    bool small_members_ = false;
 };
 
 }  // namespace mblhost

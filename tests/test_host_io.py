@@ -329,6 +329,11 @@ def test_parallel_inflate_equals_zlib(hio):
         c = zlib.compressobj(4, zlib.DEFLATED, 31)
         parts.append(c.compress(fastq[k * len(fastq) // 3:(k + 1) * len(fastq) // 3]) + c.flush())
     cases.append(("members", b"".join(parts), fastq))
+    bgzf = []
+    for k in range(0, 12_000_000, 65000):                                          # bgzip-style: hundreds of small members
+        c = zlib.compressobj(6, zlib.DEFLATED, 31)
+        bgzf.append(c.compress(fastq[k:k + 65000]) + c.flush())
+    cases.append(("small-members", b"".join(bgzf), fastq[:12_025_000]))
     binary = bytes(rng.integers(0, 256, 9_000_000).astype(np.uint8))
     c = zlib.compressobj(6, zlib.DEFLATED, 31)
     cases.append(("binary", c.compress(binary) + c.flush(), binary))
