@@ -120,3 +120,18 @@ def test_replica_workers_keep_the_read_order(cli, devices, batch, fixtures_dir, 
     assert tsv == gzip.open(os.path.join(golden_dir, "ref_tsv", "in_pe_classifications.tsv.gz"), "rb").read()
     assert report == gzip.open(os.path.join(golden_dir, "ref_tsv", "in_pe_report.tsv.gz"), "rb").read()
     assert "completed on %d GPU(s)" % len(devices.split(",")) in log
+
+
+def test_damaged_gzip_input_is_an_error(cli, fixtures_dir, tmp_path):
+    """A truncated or corrupted .gz stops the run with the decoder's message (CRC / length of every member are checked); no partial
+    TSV is reported as success."""
+    src = os.path.join(fixtures_dir, "reads", "ERR9594652_5000_1.fna.gz")
+    data = open(src, "rb").read()
+    db_dir = os.path.join(fixtures_dir, "db_in")
+    env = dict(os.environ, MBL_STUB_DB_DIR=db_dir)
+    for label, blob in (("cut", data[: len(data) // 2]), ("flip", data[:5000] + bytes([data[5000] ^ 0x20]) + data[5001:])):
+        p = tmp_path / (label + ".fna.gz")
+        p.write_bytes(blob)
+        r = subprocess.run([cli, "classify", "--seq-mode", "1", "--threads", "2", str(p), db_dir, str(tmp_path), label], capture_output=True, text=True,
+                           timeout=300, env=env)
+        assert r.returncode != 0 and "gzip:" in (r.stdout + r.stderr), (label, r.stdout[-500:], r.stderr[-500:])
