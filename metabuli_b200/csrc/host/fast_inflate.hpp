@@ -641,6 +641,7 @@ public:
     size_t groups() const { return groups_; }
     size_t segments() const { return segments_; }
     size_t false_starts() const { return false_starts_; }
+    size_t bgzf_groups() const { return bgzf_groups_; }
 
     // Appends decoded bytes to dst[at..) (dst is grown as needed): whole blocks, about `want` bytes when the stream allows, at least
     // one byte unless the input is at its end.  Returns the number of bytes, 0 at the end of the input, -1 on a malformed stream.
@@ -655,6 +656,11 @@ public:
             if (m.eof_) return 0;
             if (m.state_ == GzInflater::kMemberHeader) {
                 if (!m.skip_zero_padding()) { m.eof_ = true; return 0; }
+                if (T >= 2) {                                     // BGZF (bgzip): members carry their own size, decode a run of them side by side
+                    const long long r = bgzf_group(dst, at, want, T);
+                    if (r == -2) continue;                        // only empty blocks (the BGZF end marker) were consumed
+                    if (r != 0) return r;
+                }
                 if (!m.parse_header()) { m.failed_ = true; return -1; }
                 m.crc_ = crc32(0L, Z_NULL, 0); m.member_out_ = 0; m.hist_len_ = 0;
                 m.state_ = GzInflater::kBlockHeader;
@@ -690,6 +696,70 @@ public:
     }
 
 private:
+    // size of the BGZF block at p (RFC 1952 extra subfield 'B','C': BSIZE = block size - 1), 0 when p is not a BGZF header
+    static size_t bgzf_block_size(const uint8_t* p, const uint8_t* end) {
+        if (end - p < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+        const size_t xlen = p[10] | ((size_t)p[11] << 8);
+        if ((size_t)(end - p) < 12 + xlen) return 0;
+        for (size_t i = 0; i + 4 <= xlen;) {
+            const uint8_t* f = p + 12 + i;
+            const size_t slen = f[2] | ((size_t)f[3] << 8);
+            if (f[0] == 'B' && f[1] == 'C' && slen == 2 && i + 6 <= xlen) return (size_t)(f[4] | ((size_t)f[5] << 8)) + 1;
+            i += 4 + slen;
+        }
+        return 0;
+    }
+    // A run of BGZF blocks (up to ~want bytes of output) decoded by T threads, every block with its own CRC check, outputs
+    // appended in order.  0 when the stream is not BGZF here, -2 when blocks without output were consumed, -1 on error.
+    template <class Buf>
+    long long bgzf_group(Buf& dst, size_t at, size_t want, unsigned T) {
+        GzInflater& m = main_;
+        std::vector<std::pair<const uint8_t*, size_t>> blocks;
+        const uint8_t* p = m.in_;
+        size_t comp = 0;
+        while (p < m.end_ && comp < std::max<size_t>(want / 3, 1u << 20)) {
+            const size_t bs = bgzf_block_size(p, m.end_);
+            if (!bs || (size_t)(m.end_ - p) < bs) break;
+            blocks.emplace_back(p, bs);
+            p += bs; comp += bs;
+        }
+        if (blocks.size() < 2) return 0;
+        T = (unsigned)std::min<size_t>(T, blocks.size());
+        std::vector<RawBuf<uint8_t>> part(T);
+        std::vector<const char*> perr(T, nullptr);
+        std::vector<std::thread> th;
+        auto work = [&](unsigned t) {
+            GzInflater d;
+            RawBuf<uint8_t>& o = part[t];
+            size_t used = 0;
+            for (size_t b = blocks.size() * t / T; b < blocks.size() * (t + 1) / T; ++b) {
+                d.attach(blocks[b].first, blocks[b].second);
+                for (;;) {                                         // a BGZF block holds at most 64 KiB
+                    o.resize(used + (1u << 17));
+                    const long long r = d.read(reinterpret_cast<char*>(o.data() + used), 1u << 17);
+                    if (r < 0) { perr[t] = d.error_ ? d.error_ : "bad block"; o.resize(used); return; }
+                    used += (size_t)r;
+                    if (r < (1 << 17)) break;
+                }
+            }
+            o.resize(used);
+        };
+        for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+        for (unsigned t = 0; t < T; ++t) if (perr[t]) { m.set_err(perr[t]); m.failed_ = true; return -1; }
+        size_t n_out = 0;
+        for (auto& o : part) n_out += o.size();
+        m.in_ = p;                                                // behind the run, at the next member header (or the end)
+        m.bitbuf_ = 0; m.bitcnt_ = 0;
+        if (!n_out) return -2;                                    // only empty blocks (the BGZF end marker): progress without output
+        if (dst.size() < at + n_out) dst.resize(at + n_out);
+        size_t o = at;
+        for (auto& x : part) { if (x.size()) memcpy(dst.data() + o, x.data(), x.size()); o += x.size(); }
+        ++bgzf_groups_;
+        return (long long)n_out;
+    }
+
     struct Seg {
         uint64_t start = 0, end = 0;
         RawBuf<uint16_t> sym;                                     // segments 1..: symbols with markers
@@ -837,7 +907,7 @@ private:
     std::vector<std::unique_ptr<GzInflater>> dec_;
     RawBuf<uint8_t> serial_;
     std::vector<std::unique_ptr<Seg>> seg_;
-    size_t groups_ = 0, segments_ = 0, false_starts_ = 0;
+    size_t groups_ = 0, segments_ = 0, false_starts_ = 0, bgzf_groups_ = 0;
     bool small_members_ = false;
 };
 

@@ -87,7 +87,7 @@ int hio_parallel_inflate_check(const unsigned char* gz, unsigned long long n, co
         got += (size_t)r;
         if (got > want_n + 1024) return 3;
     }
-    g_text = "groups " + std::to_string(inf.groups()) + " segments " + std::to_string(inf.segments()) + " false " + std::to_string(inf.false_starts());
+    g_text = "groups " + std::to_string(inf.groups()) + " segments " + std::to_string(inf.segments()) + " false " + std::to_string(inf.false_starts()) + " bgzf " + std::to_string(inf.bgzf_groups());
     if (got != want_n || (want_n && memcmp(out.data(), want, (size_t)want_n) != 0)) return 2;
     return 0;
 }

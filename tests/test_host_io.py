@@ -334,6 +334,17 @@ def test_parallel_inflate_equals_zlib(hio):
         c = zlib.compressobj(6, zlib.DEFLATED, 31)
         bgzf.append(c.compress(fastq[k:k + 65000]) + c.flush())
     cases.append(("small-members", b"".join(bgzf), fastq[:12_025_000]))
+    import struct
+    blocks = []
+    for k in range(0, 9_000_000, 65280):                                           # BGZF as bgzip writes it: BC subfield, 64 KiB blocks, end marker
+        chunk = fastq[k:k + 65280]
+        raw = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = raw.compress(chunk) + raw.flush()
+        bsize = 12 + 6 + len(body) + 8
+        blocks.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + body +
+                      struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    blocks.append(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    cases.append(("bgzf", b"".join(blocks), fastq[:len(range(0, 9_000_000, 65280)) * 65280][:9_000_000 + 65280]))
     binary = bytes(rng.integers(0, 256, 9_000_000).astype(np.uint8))
     c = zlib.compressobj(6, zlib.DEFLATED, 31)
     cases.append(("binary", c.compress(binary) + c.flush(), binary))
@@ -353,6 +364,8 @@ def test_parallel_inflate_equals_zlib(hio):
                 assert groups >= 1 and segments >= 2 * groups, (label, threads, hio.hio_text())     # the parallel path really ran
             if threads == 1 or label in ("small", "empty"):
                 assert groups == 0
+            if label == "bgzf":
+                assert (int(words[7]) >= 1) == (threads >= 2), hio.hio_text()
     # damage inside the parallel region is an error, not different output
     label, comp, plain = cases[0]
     for pos in (len(comp) // 3, len(comp) // 2, len(comp) - 100):
