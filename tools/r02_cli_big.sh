@@ -5,6 +5,22 @@ set -u
 mkdir -p gpurun_out /tmp/cliq
 Q=tests/host/_build/gpu_quick
 E=${MBL_CLI:-metabuli_b200/_lib/metabuli-b200}
+if [ ! -f $Q/big_1.fna.gz ]; then   # inputs are not kept in the tree (113 MB): the fixture's reads x 200, the reference's TSV rows x 200
+  mkdir -p $Q
+  python3 - <<'PY'
+import gzip, hashlib
+F = 'tests/golden/fixtures/reads/'
+Q = 'tests/host/_build/gpu_quick/'
+for k in (1, 2):
+    raw = gzip.open(F + 'ERR9594652_5000_%d.fna.gz' % k).read()
+    with gzip.open(Q + 'big_%d.fna.gz' % k, 'wb', compresslevel=4) as f:
+        for i in range(200):
+            f.write(raw)
+gold = gzip.open('tests/golden/ref_tsv/in_pe_classifications.tsv.gz').read()
+nl = gold.index(b"\n") + 1
+open(Q + 'big.want.md5', 'w').write(hashlib.md5(gold[:nl] + gold[nl:] * 200).hexdigest() + "\n")
+PY
+fi
 want=$(cat $Q/big.want.md5)
 nproc
 for mode in gz plain; do
