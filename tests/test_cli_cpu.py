@@ -135,3 +135,22 @@ def test_damaged_gzip_input_is_an_error(cli, fixtures_dir, tmp_path):
         r = subprocess.run([cli, "classify", "--seq-mode", "1", "--threads", "2", str(p), db_dir, str(tmp_path), label], capture_output=True, text=True,
                            timeout=300, env=env)
         assert r.returncode != 0 and "gzip:" in (r.stdout + r.stderr), (label, r.stdout[-500:], r.stderr[-500:])
+
+
+def test_large_gzip_input_goes_through_the_parallel_decoder(cli, fixtures_dir, golden_dir, tmp_path):
+    """Two .gz mate files big enough (> 2 x 2 MB compressed) for the reader to decode each of them with several threads: the
+    fixture's pairs x 24 -> the reference's rows x 24."""
+    files = []
+    for k in (1, 2):
+        raw = gzip.open(os.path.join(fixtures_dir, "reads", f"ERR9594652_5000_{k}.fna.gz"), "rb").read()
+        p = tmp_path / f"big_{k}.fna.gz"
+        with gzip.open(p, "wb", compresslevel=1) as f:
+            for _ in range(24):
+                f.write(raw)
+        assert os.path.getsize(p) > 5 << 20
+        files.append(str(p))
+    tsv, _, log = _run(cli, ["--seq-mode", "2", "--threads", "6", "--batch-reads", "50000"] + files, os.path.join(fixtures_dir, "db_in"), str(tmp_path), timeout=1200)
+    gold = gzip.open(os.path.join(golden_dir, "ref_tsv", "in_pe_classifications.tsv.gz"), "rb").read()
+    nl = gold.index(b"\n") + 1
+    assert tsv == gold[:nl] + gold[nl:] * 24
+    assert "Total read count : 120000" in log
