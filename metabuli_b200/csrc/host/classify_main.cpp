@@ -229,9 +229,11 @@ int classify(int argc, char** argv) {
         else if (a == "--mask") par.maskMode = atoi(val());
         else if (a == "--mask-prob") par.maskProb = (float)atof(val());
         else if (a == "--mask-host") par.maskHost = atoi(val());
+        // --taxonomy-path: the reference reads it only when <dbdir>/taxonomyDB is missing (loadTaxonomy, common.cpp:50-86; checked
+        // against the reference binary: with taxonomyDB present even a non-existent path changes nothing).  This host needs
+        // taxonomyDB (checked below), so the flag is accepted and has no effect, as in the reference.
+        else if (a == "--taxonomy-path") val();
         // flags that change the reference's output and are not implemented here must fail, never be dropped silently:
-        // --taxonomy-path replaces the database's taxonomy (classify.cpp / TaxonomyWrapper)
-        else if (a == "--taxonomy-path") { if (std::string(val()) != "") die("--taxonomy-path is not supported by the B200 path: the taxonomy is read from <dbdir>/taxonomyDB"); }
         else if (a == "--reduced-aa") { if (atoi(val()) != 0) die("--reduced-aa 1 is not supported by the B200 path"); }
         // flags without influence on the classifications: --max-ram only sizes the reference's query splits (here: HBM budget),
         // --hamming-margin is parsed but unused by the reference (KmerMatcher.cpp:1117-1146), -v is verbosity
@@ -250,8 +252,10 @@ int classify(int argc, char** argv) {
     if (par.seqMode == 2 && !valid_query_file(q2)) die(q2 + " is not a valid query file.");
     if (!file_exists(q1)) die("Query file " + q1 + " is NOT found.");
     if (par.seqMode == 2 && !file_exists(q2)) die("Query file " + q2 + " is NOT found.");
-    for (const char* f : {"/diffIdx", "/info", "/split", "/taxonomyDB", "/taxID_list"})
+    for (const char* f : {"/diffIdx", "/info", "/split", "/taxID_list"})
         if (!file_exists(dbDir + f)) die(dbDir + f + " is NOT found.");
+    if (!file_exists(dbDir + "/taxonomyDB"))
+        die(dbDir + "/taxonomyDB is NOT found (building the taxonomy from names.dmp / nodes.dmp — <dbdir>/taxonomy or --taxonomy-path — is not implemented on the B200 path).");
     if (!file_exists(outDir)) mkdir(outDir.c_str(), 0755);
 
     // loadDbParameters (common.cpp:88-133)

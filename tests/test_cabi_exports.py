@@ -58,12 +58,13 @@ def test_product_does_not_touch_oracle():
 
 
 def test_cli_rejects_flags_that_would_change_the_output():
-    """`--taxonomy-path X`, `--reduced-aa 1` change the reference's classifications and are not implemented on the
-    B200 path: the C++ host must die with a message, not drop them (argument parsing needs no GPU).
-    (`--mask 1` is implemented since round 2: tests/test_host_mask.py, test_gpu_synth.py::test_masked_queries.)"""
+    """`--reduced-aa 1` changes the reference's classifications and is not implemented on the B200 path: the C++ host must die
+    with a message, not drop it (argument parsing needs no GPU).  (`--mask 1` is implemented since round 2:
+    tests/test_host_mask.py, test_gpu_synth.py::test_masked_queries; `--taxonomy-path` is accepted: the reference ignores it whenever
+    <dbdir>/taxonomyDB exists, which this host requires — test_cli_cpu.py::test_taxonomy_path_is_ignored_like_in_the_reference.)"""
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metabuli_b200", "_lib", "metabuli-b200")
-    for flags in (["--taxonomy-path", "/some/where"], ["--reduced-aa", "1"], ["--no-such-flag", "1"]):
+    for flags in (["--reduced-aa", "1"], ["--no-such-flag", "1"]):
         r = subprocess.run([exe, "classify", "--seq-mode", "1", *flags, "a.fna", "db", "out", "job"], capture_output=True, text=True)
         assert r.returncode != 0 and "Error" in (r.stdout + r.stderr), flags
     # harmless spellings are accepted up to the input checks

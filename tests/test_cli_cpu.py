@@ -154,3 +154,21 @@ def test_large_gzip_input_goes_through_the_parallel_decoder(cli, fixtures_dir, g
     nl = gold.index(b"\n") + 1
     assert tsv == gold[:nl] + gold[nl:] * 24
     assert "Total read count : 120000" in log
+
+
+def test_taxonomy_path_is_ignored_like_in_the_reference(cli, fixtures_dir, golden_dir, tmp_path):
+    """loadTaxonomy (common.cpp:50-86) reads --taxonomy-path only when <dbdir>/taxonomyDB is missing; with the file present the
+    reference binary writes the same TSV even for a path that does not exist (checked here in round 2).  Same behaviour: accepted,
+    no effect; a database without taxonomyDB is an error that says why."""
+    reads = [os.path.join(fixtures_dir, "reads", "ERR9594652_5000_1.fna.gz")]
+    tsv, _, _ = _run(cli, ["--seq-mode", "1", "--threads", "3", "--taxonomy-path", "/no/such/dir"] + reads, os.path.join(fixtures_dir, "db_in"), str(tmp_path))
+    assert tsv == gzip.open(os.path.join(golden_dir, "ref_tsv", "in_se_classifications.tsv.gz"), "rb").read()
+    bare = tmp_path / "db_without_taxonomy"
+    bare.mkdir()
+    for f in ("diffIdx", "info", "split", "taxID_list", "db.parameters"):
+        src = os.path.join(fixtures_dir, "db_in", f)
+        if os.path.exists(src):
+            shutil.copy(src, bare / f)
+    r = subprocess.run([cli, "classify", "--seq-mode", "1"] + reads + [str(bare), str(tmp_path), "x"], capture_output=True, text=True,
+                       env=dict(os.environ, MBL_STUB_DB_DIR=str(bare)))
+    assert r.returncode != 0 and "taxonomyDB is NOT found" in (r.stdout + r.stderr)
