@@ -195,6 +195,7 @@ struct Params {
     int lineage = 0;
     int seqMode = 2, threads = 0, accessionLevel = 0, minConsCnt = 4, minConsCntEuk = 9, matchPerKmer = 4, device = 0;
     float minScore = 0.f, minSpScore = 0.f, tieRatio = 0.95f;
+    int syncmer = 0, smerLen = 5, kmerFormat = 1;   // classify.cpp:11-13 defaults; db.parameters overrides them (loadDbParameters)
     int maskMode = 0;                    // --mask 1: tantan masking of the queries before extraction (classify.cpp:31-32 defaults)
     float maskProb = 0.9f;
     int maskHost = 0;                    // --mask-host 1: mask in the reader thread (mbl_mask_reads) instead of on the device (K0)
@@ -233,6 +234,21 @@ int classify(int argc, char** argv) {
         // against the reference binary: with taxonomyDB present even a non-existent path changes nothing).  This host needs
         // taxonomyDB (checked below), so the flag is accepted and has no effect, as in the reference.
         else if (a == "--taxonomy-path") val();
+        // defaults for databases whose db.parameters lacks the entry (older builds); the database's own values win
+        else if (a == "--syncmer") par.syncmer = atoi(val());
+        else if (a == "--smer-len") par.smerLen = atoi(val());
+        else if (a == "--kmer-format") par.kmerFormat = atoi(val());
+        else if (a == "--print-log") val();
+        // --em (a switch, optionally followed by a boolean): EM re-assignment changes what classify writes and is not implemented
+        else if (a == "--em") {
+            bool on = true;
+            if (i + 1 < argc) {
+                std::string v = argv[i + 1];
+                for (auto& ch : v) ch = (char)tolower((unsigned char)ch);
+                if (v == "0" || v == "false") { on = false; ++i; } else if (v == "1" || v == "true") ++i;
+            }
+            if (on) die("--em (expectation-maximisation re-assignment) is not supported by the B200 path");
+        }
         // flags that change the reference's output and are not implemented here must fail, never be dropped silently:
         else if (a == "--reduced-aa") { if (atoi(val()) != 0) die("--reduced-aa 1 is not supported by the B200 path"); }
         // flags without influence on the classifications: --max-ram only sizes the reference's query splits (here: HBM budget),
@@ -260,7 +276,7 @@ int classify(int argc, char** argv) {
 
     // loadDbParameters (common.cpp:88-133)
     mbl_config cfg{};
-    cfg.kmer_format = 1; cfg.smer_len = 5; cfg.seq_mode = par.seqMode;
+    cfg.kmer_format = par.kmerFormat; cfg.smer_len = par.smerLen; cfg.syncmer = par.syncmer ? 1 : 0; cfg.seq_mode = par.seqMode;
     cfg.min_score = par.minScore; cfg.min_sp_score = par.minSpScore; cfg.tie_ratio = par.tieRatio;
     cfg.min_cons_cnt = par.minConsCnt; cfg.min_cons_cnt_euk = par.minConsCntEuk;
     cfg.accession_level = par.accessionLevel; cfg.device = par.device; cfg.match_per_kmer = par.matchPerKmer;

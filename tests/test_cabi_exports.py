@@ -64,10 +64,10 @@ def test_cli_rejects_flags_that_would_change_the_output():
     <dbdir>/taxonomyDB exists, which this host requires — test_cli_cpu.py::test_taxonomy_path_is_ignored_like_in_the_reference.)"""
     import subprocess
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metabuli_b200", "_lib", "metabuli-b200")
-    for flags in (["--reduced-aa", "1"], ["--no-such-flag", "1"]):
+    for flags in (["--reduced-aa", "1"], ["--em"], ["--em", "1"], ["--no-such-flag", "1"]):
         r = subprocess.run([exe, "classify", "--seq-mode", "1", *flags, "a.fna", "db", "out", "job"], capture_output=True, text=True)
         assert r.returncode != 0 and "Error" in (r.stdout + r.stderr), flags
     # harmless spellings are accepted up to the input checks
-    r = subprocess.run([exe, "classify", "--seq-mode", "1", "--mask", "1", "--mask-prob", "0.8", "--max-ram", "8", "--hamming-margin", "1", "a.fna", "db", "out", "job"],
+    r = subprocess.run([exe, "classify", "--seq-mode", "1", "--mask", "1", "--mask-prob", "0.8", "--em", "0", "--syncmer", "0", "--smer-len", "5", "--kmer-format", "1", "--print-log", "0", "--taxonomy-path", "x", "--max-ram", "8", "--hamming-margin", "1", "a.fna", "db", "out", "job"],
                        capture_output=True, text=True)
     assert "not supported" not in (r.stdout + r.stderr)
