@@ -88,7 +88,7 @@ def test_masked_queries(cli, name, extra, golden_dir, tmp_path):
     assert report == gzip.open(os.path.join(golden_dir, "synth", name + ".report.gz"), "rb").read()
 
 
-@pytest.mark.parametrize("name", ["ragged_pe", "flags_se", "lineage_se", "sync_pe"])
+@pytest.mark.parametrize("name", ["ragged_pe", "flags_se", "lineage_se", "sync_pe", "long", "format1_pe", "acc_lvl1_se", "redund_se"])
 def test_synthetic_cases_through_the_host(cli, name, golden_dir, tmp_path):
     """Ragged paired mates from plain FASTQ (qualities starting with '@'), non-default thresholds, --lineage 1, a syncmer database."""
     db_dir, files, seq_mode = _write_case(name, tmp_path, plain_fastq=(name == "ragged_pe"))
