@@ -419,6 +419,7 @@ int classify(int argc, char** argv) {
     auto tl0 = std::chrono::steady_clock::now();
 
     std::thread reader([&] {
+        try {
         mblhost::FastxStream s1, s2;
         std::string err;
         if (!s1.open(q1, &err) || (par.seqMode == 2 && !s2.open(q2, &err))) { fail_with(err); return; }
@@ -462,6 +463,8 @@ int classify(int argc, char** argv) {
             ready.push_back(bt);
             cv.notify_all();
         }
+        } catch (const std::exception& e) { fail_with(std::string("host thread failed: ") + e.what()); }
+          catch (...) { fail_with("host thread failed"); }
     });
 
     uint64_t kmers = 0, matches = 0;
@@ -506,6 +509,7 @@ int classify(int argc, char** argv) {
                 if (mbl_shard_attach_peer(ctxs[g], (uint32_t)h, nullptr, nullptr, rd.rk[h], rd.rm[h]) != MBL_OK) { fail_with(std::string("mbl_shard_attach_peer: ") + mbl_last_error(ctxs[g])); return; }
     };
     if (sharded) for (size_t g = 0; g < G; ++g) workers.emplace_back([&, g] {
+        try {
         mbl_ctx* ctx = ctxs[g];
         auto check = [&](int rc, const char* what) { if (rc != MBL_OK) fail_with(std::string(what) + ": " + mbl_last_error(ctx)); };
         while (true) {
@@ -582,8 +586,11 @@ int classify(int argc, char** argv) {
                 cv.notify_all();
             }
         }
+        } catch (const std::exception& e) { fail_with(std::string("host thread failed: ") + e.what()); }
+          catch (...) { fail_with("host thread failed"); }
     });
     else for (size_t g = 0; g < G; ++g) workers.emplace_back([&, g] {
+        try {
         mbl_ctx* ctx = ctxs[g];
         Batch* cur = next_ready();
         if (cur && mbl_prefetch_batch(ctx, &cur->b) != MBL_OK) { fail_with(std::string("mbl_prefetch_batch: ") + mbl_last_error(ctx)); return; }
@@ -608,9 +615,12 @@ int classify(int argc, char** argv) {
             cv.notify_all();
             cur = nxt;
         }
+        } catch (const std::exception& e) { fail_with(std::string("host thread failed: ") + e.what()); }
+          catch (...) { fail_with("host thread failed"); }
     });
 
     std::thread writer([&] {
+        try {
         size_t processed = 0;
         for (size_t want = 0;; ++want) {
             Batch* bt = nullptr;
@@ -630,6 +640,8 @@ int classify(int argc, char** argv) {
             free_list.push_back(bt);
             cv.notify_all();
         }
+        } catch (const std::exception& e) { fail_with(std::string("host thread failed: ") + e.what()); }
+          catch (...) { fail_with("host thread failed"); }
     });
 
     reader.join();

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <exception>
 #include <memory>
 #include <new>
 #include <string>
@@ -28,6 +29,29 @@
 #include <vector>
 
 namespace mblhost {
+
+// Worker threads must not let an exception (an allocation failure on a huge input) escape — that is std::terminate.  A pool keeps
+// the first exception of every worker and hands it to the thread that joins.
+class Workers {
+public:
+    template <class F>
+    void spawn(F&& fn) {
+        const size_t slot = err_.size();
+        err_.emplace_back();
+        th_.emplace_back([this, slot, fn]() mutable { try { fn(); } catch (...) { err_[slot] = std::current_exception(); } });
+    }
+    void reserve(size_t n) { err_.reserve(n); th_.reserve(n); }       // spawn() must not move err_ while workers run
+    void join() {
+        for (auto& t : th_) t.join();
+        th_.clear();
+        for (auto& e : err_) if (e) { std::exception_ptr x = e; err_.clear(); std::rethrow_exception(x); }
+        err_.clear();
+    }
+    ~Workers() { for (auto& t : th_) if (t.joinable()) t.join(); }
+private:
+    std::vector<std::thread> th_;
+    std::vector<std::exception_ptr> err_;
+};
 
 // growable array without value-initialisation (decoded symbols; a std::vector would zero-fill every growth)
 template <class T>
@@ -727,7 +751,8 @@ private:
         T = (unsigned)std::min<size_t>(T, blocks.size());
         std::vector<RawBuf<uint8_t>> part(T);
         std::vector<const char*> perr(T, nullptr);
-        std::vector<std::thread> th;
+        Workers th;
+        th.reserve(T);
         auto work = [&](unsigned t) {
             GzInflater d;
             RawBuf<uint8_t>& o = part[t];
@@ -744,9 +769,9 @@ private:
             }
             o.resize(used);
         };
-        for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+        for (unsigned t = 1; t < T; ++t) th.spawn([&work, t] { work(t); });
         work(0);
-        for (auto& x : th) x.join();
+        th.join();
         for (unsigned t = 0; t < T; ++t) if (perr[t]) { m.set_err(perr[t]); m.failed_ = true; return -1; }
         size_t n_out = 0;
         for (auto& o : part) n_out += o.size();
@@ -781,15 +806,16 @@ private:
         seg[0].start = c0; seg[0].found = true;
         // 1. block starts near the cuts
         {
-            std::vector<std::thread> th;
-            for (size_t j = 1; j < n_seg; ++j) th.emplace_back([&, j] {
+            Workers th;
+            th.reserve(n_seg);
+            for (size_t j = 1; j < n_seg; ++j) th.spawn([&, j] {
                 GzInflater& d = *dec_[j];
                 d.attach(base, total);
                 const uint64_t from = ((c0 >> 3) + j * seg_bytes) * 8, to = from + (uint64_t)seg_bytes * 4;   // half a segment
                 for (uint64_t pos = from; pos < to; ++pos)
                     if (d.probe(pos)) { seg[j].start = pos; seg[j].found = true; break; }
             });
-            for (auto& t : th) t.join();
+            th.join();
         }
         std::vector<uint64_t> stops;
         for (size_t j = 1; j < n_seg; ++j) if (seg[j].found) stops.push_back(seg[j].start);
@@ -797,8 +823,9 @@ private:
         const uint64_t end_bit = ((c0 >> 3) + n_seg * seg_bytes) * 8;
         // 2. decode the segments
         {
-            std::vector<std::thread> th;
-            for (size_t j = 1; j < n_seg; ++j) if (seg[j].found) th.emplace_back([&, j] {
+            Workers th;
+            th.reserve(n_seg);
+            for (size_t j = 1; j < n_seg; ++j) if (seg[j].found) th.spawn([&, j] {
                 GzInflater& d = *dec_[j];
                 d.error_ = nullptr;
                 if (!d.seek_bits(seg[j].start)) { seg[j].how = GzInflater::kFailed; return; }
@@ -809,7 +836,7 @@ private:
             seg[0].bytes.clear();
             seg[0].how = main_.run_blocks<uint8_t>(seg[0].bytes, stops.data(), stops.size(), end_bit, &seg[0].stop_index);
             seg[0].end = main_.tell_bits();
-            for (auto& t : th) t.join();
+            th.join();
         }
         if (seg[0].how == GzInflater::kFailed) { main_.failed_ = true; return -1; }
         // 3. the chain of segments that really follow each other
@@ -865,8 +892,9 @@ private:
         std::vector<char> bad_bulk(chain.size(), 0);
         std::vector<uLong> part_crc(chain.size(), 0);
         {
-            std::vector<std::thread> th;
-            for (size_t k = 1; k < chain.size(); ++k) th.emplace_back([&, k] {
+            Workers th;
+            th.reserve(chain.size());
+            for (size_t k = 1; k < chain.size(); ++k) th.spawn([&, k] {
                 const RawBuf<uint16_t>& sy = seg[chain[k]].sym;
                 const uint8_t* w = window[k].data();
                 const size_t n = sy.size(), bulk = n - std::min<size_t>(n, GzInflater::kWindow);
@@ -882,7 +910,7 @@ private:
                 part_crc[k] = GzInflater::crc32_big(crc32(0L, Z_NULL, 0), o, n);      // the tail was resolved above
             });
             part_crc[0] = GzInflater::crc32_big(crc32(0L, Z_NULL, 0), out, off[1]);
-            for (auto& t : th) t.join();
+            th.join();
         }
         for (char b : bad_bulk) bad_marker |= b != 0;
         if (bad_marker) { main_.set_err("distance reaches before the start of the data"); main_.failed_ = true; return -1; }

@@ -188,10 +188,11 @@ inline bool parse_parts(const char* d, size_t begin, size_t end, bool fastq, uns
         part[t].offsets.reserve(guess + 1);
         ok[t] = parse_range(d, cut[t], cut[t + 1], part[t], &badv[t]) ? 1 : 0;
     };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+    Workers th;
+    th.reserve(T);
+    for (unsigned t = 1; t < T; ++t) th.spawn([&work, t] { work(t); });
     work(0);
-    for (auto& x : th) x.join();
+    th.join();
     size_t n_reads = 0;
     for (unsigned t = 0; t < T; ++t) {
         if (!ok[t]) { if (bad) *bad = n_reads + badv[t]; return false; }
@@ -251,10 +252,11 @@ inline void gather_reads(std::vector<ReadSet>& parts, size_t p0, size_t r0, size
         }
     };
     T = (unsigned)std::min<size_t>(T, std::max<size_t>(1, tasks.size()));
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < T; ++t) th.emplace_back(run, tasks.size() * t / T, tasks.size() * (t + 1) / T);
+    Workers th;
+    th.reserve(T);
+    for (unsigned t = 1; t < T; ++t) th.spawn([&run, &tasks, t, T] { run(tasks.size() * t / T, tasks.size() * (t + 1) / T); });
     run(0, tasks.size() / T);
-    for (auto& x : th) x.join();
+    th.join();
 }
 
 inline bool sniff_fastq(const char* d, size_t n) {
@@ -368,6 +370,7 @@ private:
         fill_at_ = at;
         io_ = std::thread([this, &b, at, want] {
             size_t got = 0;
+            try {
             while (got < want) {
                 const size_t ask = std::min<size_t>(want - got, 1u << 30);
                 // gzip: whole groups of blocks, decoded by io_threads_ threads (the buffer grows when a group is larger than asked)
@@ -376,6 +379,7 @@ private:
                 if (r == 0) { eof_io_ = true; break; }
                 got += (size_t)r;
             }
+            } catch (...) { io_error_ = std::current_exception(); eof_io_ = true; }
             got_ = got;
         });
     }
@@ -388,6 +392,7 @@ private:
     }
     size_t finish_read() {
         if (io_.joinable()) io_.join();
+        if (io_error_) { std::exception_ptr x = io_error_; io_error_ = nullptr; std::rethrow_exception(x); }
         if (eof_io_) eof_ = true;
         return fill_at_ + got_;
     }
@@ -410,6 +415,7 @@ private:
     ByteBuf raw_[2];
     int cur_ = 0;
     std::thread io_;
+    std::exception_ptr io_error_;
     size_t fill_at_ = 0, got_ = 0;
     bool eof_io_ = false, eof_ = false, done_ = false, started_ = false, fastq_ = false, sniffed_ = false;
     std::vector<ReadSet> parts_;
@@ -527,10 +533,11 @@ void format_rows(const Tax& tax, const std::vector<std::string>& names, size_t n
         }
         out[t].assign(buf.data(), len);
     };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+    Workers th;
+    th.reserve(T);
+    for (unsigned t = 1; t < T; ++t) th.spawn([&work, t] { work(t); });
     work(0);
-    for (auto& x : th) x.join();
+    th.join();
 }
 
 // ---- Reporter::writeReportFile / writeReport (Reporter.cpp:117-193) with NcbiTaxonomy::getParentToChildren / getCladeCounts
