@@ -481,9 +481,10 @@ int classify(int argc, char** argv) {
     // phases of its rank around two exchanges, in lock step through a barrier; the exchanges are the library's push kernels
     // storing straight into the owners' receive buffers (peer access inside one process), the counts travel through host memory
     struct Barrier {
-        std::mutex m; std::condition_variable c; size_t n, waiting = 0, gen = 0;
+        std::mutex m; std::condition_variable c; size_t n, waiting = 0, gen = 0; bool aborted = false;
         explicit Barrier(size_t k) : n(k) {}
-        void wait() { std::unique_lock<std::mutex> lk(m); const size_t g = gen; if (++waiting == n) { waiting = 0; ++gen; c.notify_all(); } else c.wait(lk, [&] { return gen != g; }); }
+        void wait() { std::unique_lock<std::mutex> lk(m); if (aborted) return; const size_t g = gen; if (++waiting == n) { waiting = 0; ++gen; c.notify_all(); } else c.wait(lk, [&] { return gen != g || aborted; }); }
+        void abort() { std::lock_guard<std::mutex> lk(m); aborted = true; c.notify_all(); }      // a rank left the loop (exception): nobody may wait for it
     } bar(G);
     struct Round {
         Batch* bt = nullptr;
@@ -586,8 +587,8 @@ int classify(int argc, char** argv) {
                 cv.notify_all();
             }
         }
-        } catch (const std::exception& e) { fail_with(std::string("host thread failed: ") + e.what()); }
-          catch (...) { fail_with("host thread failed"); }
+        } catch (const std::exception& e) { fail_with(std::string("host thread failed: ") + e.what()); bar.abort(); }
+          catch (...) { fail_with("host thread failed"); bar.abort(); }
     });
     else for (size_t g = 0; g < G; ++g) workers.emplace_back([&, g] {
         try {
