@@ -358,6 +358,7 @@ public:
                 if (read0_ == parts_[part0_].size()) { parts_[part0_] = ReadSet(); ++part0_; read0_ = 0; }
             }
             if (part0_ == parts_.size()) { parts_.clear(); part0_ = 0; }
+            else if (part0_ >= 256) { parts_.erase(parts_.begin(), parts_.begin() + (ptrdiff_t)part0_); part0_ = 0; }   // drop the used-up slots
         }
         return true;
     }
