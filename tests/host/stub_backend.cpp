@@ -1,5 +1,5 @@
 // TEST DOUBLE of libmetabuli_b200.so for the CPU suite: the C-ABI entry points the C++ host (`metabuli-b200 classify`) calls in
-// its replica mode, answered by the oracle (oracle/mbl_oracle.cpp) instead of the GPU.  tests/test_cli_cpu.py puts this library
+// its replica and index-sharded modes, answered by the oracle (oracle/mbl_oracle.cpp) instead of the GPU.  tests/test_cli_cpu.py puts this library
 // next to a copy of the CLI binary (its rpath is $ORIGIN), so that the host's own code — streaming reader, batch pipeline, masking
 // flags, row formatter, report — runs end to end without a device and is compared with the reference binary's files.  It is test
 // infrastructure like the oracle: nothing under metabuli_b200/ links or loads it, and the real library never falls back to it.
@@ -22,6 +22,15 @@ struct mbl_ctx {
     std::vector<orc::Read> m1, m2;
     bool staged = false, paired = false;
     uint32_t staged_n = 0;
+    // index-sharded phases: what this rank extracted / matched, its receive buffers (plain host memory here) and its peers'
+    uint64_t seq_base = 0;
+    std::vector<orc::QueryInfo> q;
+    std::vector<std::vector<orc::Kmer>> kbucket;
+    std::vector<std::vector<orc::Match>> mbucket;
+    std::vector<uint64_t> recv_k;
+    std::vector<orc::Match> recv_m;
+    std::vector<uint64_t*> peer_k;
+    std::vector<orc::Match*> peer_m;
     // results of the last classified batch
     std::vector<mbl_read_result> res;
     std::vector<int32_t> pairs;
@@ -49,20 +58,14 @@ void stage(mbl_ctx* c, const mbl_batch* b) {
     c->staged = true;
 }
 
-int classify_staged(mbl_ctx* c) {
-    if (null_mode()) { c->res.assign(c->staged_n, mbl_read_result{}); c->pairs.clear(); c->stats = mbl_stats{}; c->staged = false; return MBL_OK; }
+orc::Options options_of(const mbl_ctx* c) {
     orc::Options opt;
     opt.seqMode = c->cfg.seq_mode; opt.minScore = c->cfg.min_score; opt.minSpScore = c->cfg.min_sp_score; opt.tieRatio = c->cfg.tie_ratio;
     opt.minConsCnt = c->cfg.min_cons_cnt; opt.minConsCntEuk = c->cfg.min_cons_cnt_euk; opt.accessionLevel = c->cfg.accession_level;
-    std::vector<orc::QueryInfo> q;
-    std::vector<orc::Kmer> k;
-    orc::extract_kmers(c->m1, c->paired ? &c->m2 : nullptr, c->db.params.kmerFormat, q, k, c->db.params.syncmer, c->db.params.smerLen);
-    orc::sort_kmers(k, 2);
-    std::vector<orc::Match> m;
-    std::string err;
-    if (!orc::match_kmers(c->db, k, m, 2, &err)) return fail(c, MBL_E_BAD_DB, err);
-    orc::sort_matches(m, 2);
-    orc::score_reads(c->db, opt, m, q, 2);
+    return opt;
+}
+
+void fill_results(mbl_ctx* c, const std::vector<orc::QueryInfo>& q) {
     c->res.assign(q.size(), mbl_read_result{});
     c->pairs.clear();
     for (size_t i = 0; i < q.size(); ++i) {
@@ -72,10 +75,24 @@ int classify_staged(mbl_ctx* c) {
         r.taxcnt_begin = (uint32_t)(c->pairs.size() / 2); r.taxcnt_len = (uint32_t)q[i].taxCnt.size();
         for (auto& t : q[i].taxCnt) { c->pairs.push_back(t.first); c->pairs.push_back(t.second); }
     }
+}
+
+int classify_staged(mbl_ctx* c) {
+    if (null_mode()) { c->res.assign(c->staged_n, mbl_read_result{}); c->pairs.clear(); c->stats = mbl_stats{}; c->staged = false; return MBL_OK; }
+    const orc::Options opt = options_of(c);
+    std::vector<orc::QueryInfo> q;
+    std::vector<orc::Kmer> k;
+    orc::extract_kmers(c->m1, c->paired ? &c->m2 : nullptr, c->db.params.kmerFormat, q, k, c->db.params.syncmer, c->db.params.smerLen);
+    orc::sort_kmers(k, 2);
+    std::vector<orc::Match> m;
+    std::string err;
+    if (!orc::match_kmers(c->db, k, m, 2, &err)) return fail(c, MBL_E_BAD_DB, err);
+    orc::sort_matches(m, 2);
+    orc::score_reads(c->db, opt, m, q, 2);
+    fill_results(c, q);
     c->stats = mbl_stats{};
     for (auto& x : k) if ((x.qinfo >> 32) & 0x1FFFFFFFu) ++c->stats.n_query_kmers;
     c->stats.n_matches = m.size();
-    c->stats.kernel_launches = 0;
     c->staged = false;
     return MBL_OK;
 }
@@ -144,19 +161,107 @@ int mbl_mask_reads(char* bases, const uint64_t* offsets, uint32_t n_reads, float
     return MBL_OK;
 }
 
-// the index-sharded phases need devices: the double refuses them
-#define MBL_STUB_UNSUPPORTED(name, ...) int name(__VA_ARGS__) { return MBL_E_UNSUPPORTED; }
-MBL_STUB_UNSUPPORTED(mbl_load_db_shard, mbl_ctx*, const mbl_db*, const mbl_taxonomy*, const mbl_shard*)
-MBL_STUB_UNSUPPORTED(mbl_plan_shards, const mbl_db*, uint32_t, mbl_shard*)
-MBL_STUB_UNSUPPORTED(mbl_shard_filter, mbl_ctx*, void**, uint64_t*)
-MBL_STUB_UNSUPPORTED(mbl_shard_filter_or, mbl_ctx*, const void*, uint64_t, int)
-MBL_STUB_UNSUPPORTED(mbl_shard_extract, mbl_ctx*, const mbl_batch*, uint64_t, uint32_t, const uint64_t*, uint64_t*)
-MBL_STUB_UNSUPPORTED(mbl_shard_match, mbl_ctx*, const uint64_t*, const uint64_t*, uint64_t, uint32_t, const uint64_t*, uint64_t*)
-MBL_STUB_UNSUPPORTED(mbl_shard_recv_buffers, mbl_ctx*, uint64_t, uint64_t, void**, void**, uint8_t*, uint8_t*)
-MBL_STUB_UNSUPPORTED(mbl_shard_attach_peer, mbl_ctx*, uint32_t, const uint8_t*, const uint8_t*, void*, void*)
-MBL_STUB_UNSUPPORTED(mbl_shard_detach_peers, mbl_ctx*)
-MBL_STUB_UNSUPPORTED(mbl_shard_push_kmers, mbl_ctx*, const uint64_t*, const uint64_t*)
-MBL_STUB_UNSUPPORTED(mbl_shard_push_matches, mbl_ctx*, const uint64_t*)
-MBL_STUB_UNSUPPORTED(mbl_shard_score, mbl_ctx*, const mbl_match_rec*, uint64_t)
+// ---- index-sharded phases on host memory: "device pointers" are plain pointers, every rank keeps the whole database (a metamer
+// still goes to exactly one rank, by value range, so the matches are the same), the exchanges are the pushes below -----------------
+int mbl_plan_shards(const mbl_db* db, uint32_t n_shards, mbl_shard* out) {
+    if (!db || !out || n_shards < 1 || n_shards > MBL_MAX_SHARDS) return MBL_E_BAD_ARG;
+    for (uint32_t s = 0; s < n_shards; ++s) {
+        out[s] = mbl_shard{};
+        out[s].first_value = s == 0 ? 0 : ((~0ull / n_shards) * s) & ~0xFFFFFFull;       // amino-acid-group aligned
+    }
+    return MBL_OK;
+}
+int mbl_load_db_shard(mbl_ctx* c, const mbl_db* db, const mbl_taxonomy* tx, const mbl_shard*) { return mbl_load_db(c, db, tx); }
+int mbl_shard_filter(mbl_ctx* c, void** d_words, uint64_t* n_bytes) { if (!c || !d_words || !n_bytes) return MBL_E_BAD_ARG; *d_words = nullptr; *n_bytes = 0; return MBL_OK; }
+int mbl_shard_filter_or(mbl_ctx*, const void*, uint64_t, int) { return MBL_OK; }
+
+int mbl_shard_extract(mbl_ctx* c, const mbl_batch* b, uint64_t seq_base, uint32_t n_shards, const uint64_t* first, uint64_t* send_counts) {
+    if (!c || !b || !first || !send_counts) return MBL_E_BAD_ARG;
+    stage(c, b);
+    c->staged = false;
+    c->seq_base = seq_base;
+    std::vector<orc::Kmer> k;
+    orc::extract_kmers(c->m1, c->paired ? &c->m2 : nullptr, c->db.params.kmerFormat, c->q, k, c->db.params.syncmer, c->db.params.smerLen);
+    c->kbucket.assign(n_shards, {});
+    c->stats = mbl_stats{};
+    for (const orc::Kmer& x : k) {
+        if (!((x.qinfo >> 32) & 0x1FFFFFFFu)) continue;                      // blank slot
+        ++c->stats.n_query_kmers;
+        uint32_t s = 0;
+        while (s + 1 < n_shards && first[s + 1] <= x.value) ++s;
+        c->kbucket[s].push_back(orc::Kmer{x.value, x.qinfo + (seq_base << 32)});   // seqIDs are global on the wire
+    }
+    for (uint32_t s = 0; s < n_shards; ++s) send_counts[s] = c->kbucket[s].size();
+    return MBL_OK;
+}
+
+int mbl_shard_recv_buffers(mbl_ctx* c, uint64_t kmer_rows, uint64_t match_rows, void** d_kmers, void** d_matches, uint8_t*, uint8_t*) {
+    if (!c || !d_kmers || !d_matches) return MBL_E_BAD_ARG;
+    c->recv_k.assign(2 * kmer_rows + 2, 0);
+    c->recv_m.assign(match_rows + 1, orc::Match{});
+    *d_kmers = c->recv_k.data(); *d_matches = c->recv_m.data();
+    return MBL_OK;
+}
+int mbl_shard_attach_peer(mbl_ctx* c, uint32_t peer, const uint8_t*, const uint8_t*, void* raw_kmers, void* raw_matches) {
+    if (!c || peer >= MBL_MAX_SHARDS) return MBL_E_BAD_ARG;
+    if (c->peer_k.size() <= peer) { c->peer_k.resize(peer + 1, nullptr); c->peer_m.resize(peer + 1, nullptr); }
+    c->peer_k[peer] = static_cast<uint64_t*>(raw_kmers); c->peer_m[peer] = static_cast<orc::Match*>(raw_matches);
+    return MBL_OK;
+}
+int mbl_shard_detach_peers(mbl_ctx* c) { if (!c) return MBL_E_BAD_ARG; c->peer_k.clear(); c->peer_m.clear(); return MBL_OK; }
+
+int mbl_shard_push_kmers(mbl_ctx* c, const uint64_t* off, const uint64_t* tot) {
+    if (!c || !off || !tot) return MBL_E_BAD_ARG;
+    for (size_t h = 0; h < c->kbucket.size(); ++h) {
+        if (c->kbucket[h].empty()) continue;
+        if (h >= c->peer_k.size() || !c->peer_k[h]) return fail(c, MBL_E_BAD_ARG, "peer not attached");
+        uint64_t* buf = c->peer_k[h];
+        for (size_t i = 0; i < c->kbucket[h].size(); ++i) { buf[off[h] + i] = c->kbucket[h][i].value; buf[tot[h] + off[h] + i] = c->kbucket[h][i].qinfo; }
+    }
+    return MBL_OK;
+}
+
+int mbl_shard_match(mbl_ctx* c, const uint64_t* value, const uint64_t* qinfo, uint64_t n, uint32_t n_owners, const uint64_t* owner_first_read,
+                    uint64_t* send_counts) {
+    if (!c || !owner_first_read || !send_counts || (n && (!value || !qinfo))) return MBL_E_BAD_ARG;
+    std::vector<orc::Kmer> k(n);
+    for (uint64_t i = 0; i < n; ++i) k[i] = orc::Kmer{value[i], qinfo[i]};
+    orc::sort_kmers(k, 2);
+    std::vector<orc::Match> m;
+    std::string err;
+    if (!orc::match_kmers(c->db, k, m, 2, &err)) return fail(c, MBL_E_BAD_DB, err);
+    c->mbucket.assign(n_owners, {});
+    for (const orc::Match& x : m) {
+        const uint64_t read = ((x.qinfo >> 32) & 0x1FFFFFFFu) - 1;            // global read index
+        uint32_t o = 0;
+        while (o + 1 < n_owners && owner_first_read[o + 1] <= read) ++o;
+        c->mbucket[o].push_back(x);
+    }
+    for (uint32_t o = 0; o < n_owners; ++o) send_counts[o] = c->mbucket[o].size();
+    c->stats.n_matches = m.size();
+    return MBL_OK;
+}
+
+int mbl_shard_push_matches(mbl_ctx* c, const uint64_t* off) {
+    if (!c || !off) return MBL_E_BAD_ARG;
+    for (size_t o = 0; o < c->mbucket.size(); ++o) {
+        if (c->mbucket[o].empty()) continue;
+        if (o >= c->peer_m.size() || !c->peer_m[o]) return fail(c, MBL_E_BAD_ARG, "peer not attached");
+        memcpy(c->peer_m[o] + off[o], c->mbucket[o].data(), c->mbucket[o].size() * sizeof(orc::Match));
+    }
+    return MBL_OK;
+}
+
+int mbl_shard_score(mbl_ctx* c, const mbl_match_rec* d_match, uint64_t n_match) {
+    if (!c || (n_match && !d_match)) return MBL_E_BAD_ARG;
+    static_assert(sizeof(orc::Match) == sizeof(mbl_match_rec), "match record layout");
+    std::vector<orc::Match> m(n_match);
+    if (n_match) memcpy(m.data(), d_match, n_match * sizeof(orc::Match));
+    for (orc::Match& x : m) x.qinfo -= c->seq_base << 32;                    // back to the batch's own read numbers
+    orc::sort_matches(m, 2);
+    orc::score_reads(c->db, options_of(c), m, c->q, 2);
+    fill_results(c, c->q);
+    return MBL_OK;
+}
 
 }  // extern "C"

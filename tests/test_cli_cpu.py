@@ -172,3 +172,17 @@ def test_taxonomy_path_is_ignored_like_in_the_reference(cli, fixtures_dir, golde
     r = subprocess.run([cli, "classify", "--seq-mode", "1"] + reads + [str(bare), str(tmp_path), "x"], capture_output=True, text=True,
                        env=dict(os.environ, MBL_STUB_DB_DIR=str(bare)))
     assert r.returncode != 0 and "taxonomyDB is NOT found" in (r.stdout + r.stderr)
+
+
+@pytest.mark.parametrize("devices,batch,db,mode", [("0,1", 1300, "in", "pe"), ("0,1,2", 999, "ex", "se"), ("0,1,2,3", 0, "in", "se")])
+def test_index_sharded_orchestration(cli, devices, batch, db, mode, fixtures_dir, golden_dir, tmp_path):
+    """--index-sharded 1: the host cuts every batch over the ranks and runs extract -> exchange -> match -> exchange -> score in
+    lock step (barriers, count tables through host memory, receive buffers grown on demand, results stitched back in read order).
+    The double answers the phases on host memory; what is checked is the host's orchestration: TSV and report of the reference."""
+    reads = [os.path.join(fixtures_dir, "reads", f"ERR9594652_5000_{k}.fna.gz") for k in ((1, 2) if mode == "pe" else (1,))]
+    args = ["--seq-mode", "2" if mode == "pe" else "1", "--threads", "4", "--devices", devices, "--index-sharded", "1"]
+    args += (["--batch-reads", str(batch)] if batch else []) + reads
+    tsv, report, log = _run(cli, args, os.path.join(fixtures_dir, f"db_{db}"), str(tmp_path))
+    assert tsv == gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_classifications.tsv.gz"), "rb").read()
+    assert report == gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_report.tsv.gz"), "rb").read()
+    assert "index sharded" in log
