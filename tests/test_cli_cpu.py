@@ -186,3 +186,15 @@ def test_index_sharded_orchestration(cli, devices, batch, db, mode, fixtures_dir
     assert tsv == gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_classifications.tsv.gz"), "rb").read()
     assert report == gzip.open(os.path.join(golden_dir, "ref_tsv", f"{db}_{mode}_report.tsv.gz"), "rb").read()
     assert "index sharded" in log
+
+
+def test_more_ranks_than_reads_in_a_batch(cli, fixtures_dir, golden_dir, tmp_path):
+    """Batches of three reads over four ranks (a rank without reads in every round) and of one read over three replicas."""
+    raw = gzip.open(os.path.join(fixtures_dir, "reads", "ERR9594652_5000_1.fna.gz"), "rb").read().split(b"\n")
+    small = tmp_path / "small.fna"
+    small.write_bytes(b"\n".join(raw[:46]) + b"\n")                     # 23 records
+    want = b"\n".join(gzip.open(os.path.join(golden_dir, "ref_tsv", "in_se_classifications.tsv.gz"), "rb").read().split(b"\n")[:24]) + b"\n"
+    db = os.path.join(fixtures_dir, "db_in")
+    for extra in (["--devices", "0,1,2,3", "--index-sharded", "1", "--batch-reads", "3"], ["--devices", "0,1,2", "--batch-reads", "1"]):
+        tsv, _, _ = _run(cli, ["--seq-mode", "1", "--threads", "2"] + extra + [str(small)], db, str(tmp_path))
+        assert tsv == want, extra
